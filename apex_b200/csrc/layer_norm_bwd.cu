@@ -1,0 +1,322 @@
+// LayerNorm / RMSNorm backward for sm_100a. ONE pass over (dy, x): each persistent CTA keeps its rows in registers,
+// produces dx, and accumulates its share of dgamma/dbeta in registers; a tiny second kernel folds the <=296 per-CTA partials.
+// (The reference reads dy and x twice: cuComputePartGradGammaBeta + cuComputeGradInput, layer_norm_cuda_kernel.cu:481-801.)
+// memory_efficient: the saved tensor is the OUTPUT y; xhat is rebuilt as (y-beta)/clamp(gamma) (reference :378-394,416,761).
+#include "norm_common.cuh"
+
+namespace ab {
+
+__device__ __forceinline__ float clamp_mag(float g, float eps) {
+  return fabsf(g) < eps ? copysignf(eps, g) : g;
+}
+
+// Tin: dtype of x and dx. Tout: dtype of dy, gamma, beta (and of y when MEMEFF).
+template <int MAXV, typename Tin, typename Tout, bool RMS, bool MEMEFF>
+__global__ void __launch_bounds__(256) ln_bwd_vec(const Tout* __restrict__ dy, const void* __restrict__ saved, const float* __restrict__ mean,
+                           const float* __restrict__ invvar, const Tout* __restrict__ gamma, const Tout* __restrict__ beta,
+                           Tin* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b, int n1, int n2,
+                           float eps, int tpr) {
+  constexpr int E = 16 / sizeof(Tin);
+  __shared__ float sred[64];
+  __shared__ float sacc[2][4096];
+  RowReducer red(sred, tpr);
+  const int rows_per_cta = blockDim.x / tpr;
+  const int nvec = n2 / E;
+  const float inv_n = 1.f / (float)n2;
+  float acc_g[MAXV][E], acc_b[MAXV][E];
+#pragma unroll
+  for (int v = 0; v < MAXV; v++)
+#pragma unroll
+    for (int e = 0; e < E; e++) { acc_g[v][e] = 0.f; acc_b[v][e] = 0.f; }
+
+  constexpr int DW = E * sizeof(Tout) / 4;  // 32-bit words of one dy / y vector
+  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += gridDim.x * rows_per_cta) {
+    const int row = row0 + red.rg;
+    const bool valid = row < n1;
+    const float mu = (valid && !RMS && !MEMEFF) ? mean[row] : 0.f;
+    const float rstd = valid ? invvar[row] : 0.f;
+    // keep the row as RAW bits (half the registers of fp32 copies); decode twice
+    uint32_t draw[MAXV][DW], sraw[MAXV][MEMEFF ? DW : 4];
+#pragma unroll
+    for (int v = 0; v < MAXV; v++) {
+      const int idx = v * tpr + red.lane_r;
+      const bool on = valid && idx < nvec;
+      const uint32_t* dp = reinterpret_cast<const uint32_t*>(dy + (size_t)row * n2 + (size_t)idx * E);
+      if (DW >= 4) {
+#pragma unroll
+        for (int q = 0; q < DW / 4; q++) {
+          uint4 t = on ? __ldg(reinterpret_cast<const uint4*>(dp) + q) : make_uint4(0, 0, 0, 0);
+          draw[v][q * 4 + 0] = t.x; draw[v][q * 4 + 1] = t.y; draw[v][q * 4 + 2] = t.z; draw[v][q * 4 + 3] = t.w;
+        }
+      } else {
+        uint2 t = on ? __ldg(reinterpret_cast<const uint2*>(dp)) : make_uint2(0, 0);
+        draw[v][0] = t.x; draw[v][1] = t.y;
+      }
+      if (MEMEFF) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(reinterpret_cast<const Tout*>(saved) + (size_t)row * n2 + (size_t)idx * E);
+        if (DW >= 4) {
+#pragma unroll
+          for (int q = 0; q < DW / 4; q++) {
+            uint4 t = on ? __ldg(reinterpret_cast<const uint4*>(sp) + q) : make_uint4(0, 0, 0, 0);
+            sraw[v][q * 4 + 0] = t.x; sraw[v][q * 4 + 1] = t.y; sraw[v][q * 4 + 2] = t.z; sraw[v][q * 4 + 3] = t.w;
+          }
+        } else {
+          uint2 t = on ? __ldg(reinterpret_cast<const uint2*>(sp)) : make_uint2(0, 0);
+          sraw[v][0] = t.x; sraw[v][1] = t.y;
+        }
+      } else {
+        uint4 t = on ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const Tin*>(saved) + (size_t)row * n2 + (size_t)idx * E))
+                     : make_uint4(0, 0, 0, 0);
+        sraw[v][0] = t.x; sraw[v][1] = t.y; sraw[v][2] = t.z; sraw[v][3] = t.w;
+      }
+    }
+    // decode vector v -> xhat, dy, gamma
+    auto decode = [&](int v, int idx, float (&xh)[E], float (&d)[E], float (&g)[E]) {
+      const Tout* de = reinterpret_cast<const Tout*>(draw[v]);
+#pragma unroll
+      for (int e = 0; e < E; e++) d[e] = to_f<Tout>(de[e]);
+      if (gamma) load_vec<Tout, E>(g, gamma + (size_t)idx * E);
+      else {
+#pragma unroll
+        for (int e = 0; e < E; e++) g[e] = 1.f;
+      }
+      if (MEMEFF) {
+        const Tout* ye = reinterpret_cast<const Tout*>(sraw[v]);
+        float b[E];
+        if (!RMS && beta) load_vec<Tout, E>(b, beta + (size_t)idx * E);
+        else {
+#pragma unroll
+          for (int e = 0; e < E; e++) b[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const float yv = to_f<Tout>(ye[e]) - b[e];
+          xh[e] = gamma ? yv / clamp_mag(g[e], eps) : yv;
+        }
+      } else {
+        const Tin* xe = reinterpret_cast<const Tin*>(sraw[v]);
+#pragma unroll
+        for (int e = 0; e < E; e++) xh[e] = (to_f<Tin>(xe[e]) - mu) * rstd;
+      }
+    };
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; v++) {
+      const int idx = v * tpr + red.lane_r;
+      if (valid && idx < nvec) {
+        float xh[E], d[E], g[E];
+        decode(v, idx, xh, d, g);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          acc_g[v][e] += d[e] * xh[e];
+          acc_b[v][e] += d[e];
+          const float w = d[e] * g[e];
+          s1 += w;
+          s2 += w * xh[e];
+        }
+      }
+    }
+    if (!RMS) s1 = red.sum(s1) * inv_n; else s1 = 0.f;
+    s2 = red.sum(s2) * inv_n;
+    if (valid) {
+#pragma unroll
+      for (int v = 0; v < MAXV; v++) {
+        const int idx = v * tpr + red.lane_r;
+        if (idx < nvec) {
+          float xh[E], d[E], g[E], o[E];
+          decode(v, idx, xh, d, g);
+#pragma unroll
+          for (int e = 0; e < E; e++) o[e] = rstd * (d[e] * g[e] - s1 - xh[e] * s2);
+          store_vec<Tin, E>(dx + (size_t)row * n2 + (size_t)idx * E, o);
+        }
+      }
+    }
+  }
+
+  if (part_g == nullptr) return;  // no affine parameters
+  // fold the row groups of this CTA, then one partial row per CTA
+  if (rows_per_cta > 1) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) { sacc[0][i] = 0.f; sacc[1][i] = 0.f; }
+    __syncthreads();
+    for (int g = 0; g < rows_per_cta; g++) {
+      if (red.rg == g) {
+#pragma unroll
+        for (int v = 0; v < MAXV; v++) {
+          const int idx = v * tpr + red.lane_r;
+          if (idx < nvec) {
+#pragma unroll
+            for (int e = 0; e < E; e++) { sacc[0][idx * E + e] += acc_g[v][e]; sacc[1][idx * E + e] += acc_b[v][e]; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      part_g[(size_t)blockIdx.x * n2 + i] = sacc[0][i];
+      if (part_b) part_b[(size_t)blockIdx.x * n2 + i] = sacc[1][i];
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < MAXV; v++) {
+      const int idx = v * tpr + red.lane_r;
+      if (idx < nvec) {
+        store_vec<float, E>(part_g + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_g[v]);
+        if (part_b) store_vec<float, E>(part_b + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_b[v]);
+      }
+    }
+  }
+}
+
+// dgamma[c] = sum_k part_g[k][c] (fixed order => deterministic)
+template <typename Tout>
+__global__ void __launch_bounds__(512) ln_bwd_fold(const float* __restrict__ part_g, const float* __restrict__ part_b, int k, int n2,
+                                                   Tout* __restrict__ dgamma, Tout* __restrict__ dbeta) {
+  __shared__ float sg[16][33], sb[16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float g = 0.f, b = 0.f;
+  if (c < n2) {
+    for (int r = threadIdx.y; r < k; r += 16) {
+      g += part_g[(size_t)r * n2 + c];
+      if (part_b) b += part_b[(size_t)r * n2 + c];
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = g; sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n2) {
+#pragma unroll
+    for (int r = 1; r < 16; r++) { g += sg[r][threadIdx.x]; b += sb[r][threadIdx.x]; }
+    dgamma[c] = from_f<Tout>(g);
+    if (dbeta) dbeta[c] = from_f<Tout>(b);
+  }
+}
+
+// ---- generic fallback (any n2 / alignment): dx one CTA per row; dgamma/dbeta by column strips re-reading dy and x.
+template <typename Tin, typename Tout, bool RMS, bool MEMEFF>
+__global__ void __launch_bounds__(256) ln_bwd_dx_generic(const Tout* __restrict__ dy, const void* __restrict__ saved,
+                                                         const float* __restrict__ mean, const float* __restrict__ invvar,
+                                                         const Tout* __restrict__ gamma, const Tout* __restrict__ beta,
+                                                         Tin* __restrict__ dx, int n1, int n2, float eps) {
+  __shared__ float red[40];
+  for (int row = blockIdx.x; row < n1; row += gridDim.x) {
+    const float mu = (!RMS && !MEMEFF) ? mean[row] : 0.f, rstd = invvar[row];
+    auto xhat = [&](int i) -> float {
+      if (MEMEFF) {
+        float yv = to_f<Tout>(reinterpret_cast<const Tout*>(saved)[(size_t)row * n2 + i]);
+        if (!RMS && beta) yv -= to_f<Tout>(beta[i]);
+        return gamma ? yv / clamp_mag(to_f<Tout>(gamma[i]), eps) : yv;
+      }
+      return (to_f<Tin>(reinterpret_cast<const Tin*>(saved)[(size_t)row * n2 + i]) - mu) * rstd;
+    };
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const float w = to_f<Tout>(dy[(size_t)row * n2 + i]) * (gamma ? to_f<Tout>(gamma[i]) : 1.f);
+      s1 += w; s2 += w * xhat(i);
+    }
+    s1 = RMS ? 0.f : block_sum(s1, red) / (float)n2;
+    s2 = block_sum(s2, red) / (float)n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const float w = to_f<Tout>(dy[(size_t)row * n2 + i]) * (gamma ? to_f<Tout>(gamma[i]) : 1.f);
+      dx[(size_t)row * n2 + i] = from_f<Tin>(rstd * (w - s1 - xhat(i) * s2));
+    }
+  }
+}
+
+template <typename Tin, typename Tout, bool RMS, bool MEMEFF>
+__global__ void __launch_bounds__(512) ln_bwd_gamma_generic(const Tout* __restrict__ dy, const void* __restrict__ saved,
+                                                            const float* __restrict__ mean, const float* __restrict__ invvar,
+                                                            const Tout* __restrict__ gamma, const Tout* __restrict__ beta,
+                                                            Tout* __restrict__ dgamma, Tout* __restrict__ dbeta, int n1, int n2,
+                                                            float eps) {
+  __shared__ float sg[16][33], sb[16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float g = 0.f, b = 0.f;
+  if (c < n2) {
+    for (int r = threadIdx.y; r < n1; r += 16) {
+      const float d = to_f<Tout>(dy[(size_t)r * n2 + c]);
+      float xh;
+      if (MEMEFF) {
+        float yv = to_f<Tout>(reinterpret_cast<const Tout*>(saved)[(size_t)r * n2 + c]);
+        if (!RMS && beta) yv -= to_f<Tout>(beta[c]);
+        xh = gamma ? yv / clamp_mag(to_f<Tout>(gamma[c]), eps) : yv;
+      } else {
+        const float mu = RMS ? 0.f : mean[r];
+        xh = (to_f<Tin>(reinterpret_cast<const Tin*>(saved)[(size_t)r * n2 + c]) - mu) * invvar[r];
+      }
+      g += d * xh; b += d;
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = g; sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n2) {
+#pragma unroll
+    for (int r = 1; r < 16; r++) { g += sg[r][threadIdx.x]; b += sb[r][threadIdx.x]; }
+    dgamma[c] = from_f<Tout>(g);
+    if (dbeta) dbeta[c] = from_f<Tout>(b);
+  }
+}
+
+template <typename Tin, typename Tout, bool RMS, bool MEMEFF>
+int ln_bwd_launch(const void* dy, const void* saved, const float* mean, const float* invvar, const void* gamma, const void* beta,
+                  void* dx, void* dgamma, void* dbeta, float* ws, int n1, int n2, float eps, cudaStream_t st) {
+  constexpr int E = 16 / sizeof(Tin);
+  const bool vec_ok = (n2 % E == 0) && aligned16(dy) && aligned16(saved) && aligned16(dx) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 &&
+                      ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
+  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 4, 256);
+  const bool small_rows_ok = c.rows_per_cta == 1 || n2 <= 4096;
+  if (vec_ok && c.ok && small_rows_ok && ws != nullptr) {
+    int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
+    const int cap = kNumSMs * 2;
+    if (grid > cap) grid = cap;
+    float* part_g = dgamma ? ws : nullptr;
+    float* part_b = (dgamma && dbeta) ? ws + (size_t)cap * n2 : nullptr;
+#define LN_BWD_GO(MV)                                                                                                   \
+  ln_bwd_vec<MV, Tin, Tout, RMS, MEMEFF><<<grid, c.threads, 0, st>>>((const Tout*)dy, saved, mean, invvar, (const Tout*)gamma, \
+                                                                     (const Tout*)beta, (Tin*)dx, part_g, part_b, n1, n2, eps, c.tpr)
+    switch (c.maxv) {
+      case 1: LN_BWD_GO(1); break;
+      case 2: LN_BWD_GO(2); break;
+      case 4: LN_BWD_GO(4); break;
+      default: LN_BWD_GO(8); break;
+    }
+    if (dgamma)
+      ln_bwd_fold<Tout><<<(n2 + 31) / 32, dim3(32, 16), 0, st>>>(part_g, part_b, grid, n2, (Tout*)dgamma, (Tout*)dbeta);
+  } else {
+    int grid = n1 < kNumSMs * 8 ? n1 : kNumSMs * 8;
+    ln_bwd_dx_generic<Tin, Tout, RMS, MEMEFF><<<grid, 256, 0, st>>>((const Tout*)dy, saved, mean, invvar, (const Tout*)gamma,
+                                                                    (const Tout*)beta, (Tin*)dx, n1, n2, eps);
+    if (dgamma)
+      ln_bwd_gamma_generic<Tin, Tout, RMS, MEMEFF><<<(n2 + 31) / 32, dim3(32, 16), 0, st>>>(
+          (const Tout*)dy, saved, mean, invvar, (const Tout*)gamma, (const Tout*)beta, (Tout*)dgamma, (Tout*)dbeta, n1, n2, eps);
+  }
+  AB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+// workspace floats needed: 2 * (148*2) * n2
+AB_API int64_t ab_layer_norm_bwd_ws_floats(int n2) { return (int64_t)2 * kNumSMs * 2 * n2; }
+
+// dy[n1,n2] (dt_out), saved = x (dt_in) or y (dt_out, memory_efficient) -> dx (dt_in), dgamma/dbeta (dt_out, nullable).
+AB_API int ab_layer_norm_bwd(const void* dy, const void* saved, const float* mean, const float* invvar, const void* gamma,
+                             const void* beta, void* dx, void* dgamma, void* dbeta, float* ws, int n1, int n2, float eps, int dt_in,
+                             int dt_out, int rms, int memory_efficient, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return 0;
+#define LNB(TI, TO)                                                                                                              \
+  {                                                                                                                              \
+    if (rms) return memory_efficient ? ln_bwd_launch<TI, TO, true, true>(dy, saved, mean, invvar, gamma, beta, dx, dgamma, dbeta, ws, n1, n2, eps, st)   \
+                                     : ln_bwd_launch<TI, TO, true, false>(dy, saved, mean, invvar, gamma, beta, dx, dgamma, dbeta, ws, n1, n2, eps, st); \
+    return memory_efficient ? ln_bwd_launch<TI, TO, false, true>(dy, saved, mean, invvar, gamma, beta, dx, dgamma, dbeta, ws, n1, n2, eps, st)          \
+                            : ln_bwd_launch<TI, TO, false, false>(dy, saved, mean, invvar, gamma, beta, dx, dgamma, dbeta, ws, n1, n2, eps, st);        \
+  }
+  if (dt_in == kF32 && dt_out == kF32) LNB(float, float)
+  if (dt_in == kF16 && dt_out == kF16) LNB(f16, f16)
+  if (dt_in == kBF16 && dt_out == kBF16) LNB(bf16, bf16)
+  if (dt_in == kF16 && dt_out == kF32) LNB(f16, float)
+  if (dt_in == kBF16 && dt_out == kF32) LNB(bf16, float)
+  if (dt_in == kF32 && dt_out == kF16) LNB(float, f16)
+  if (dt_in == kF32 && dt_out == kBF16) LNB(float, bf16)
+  return -1;
+}

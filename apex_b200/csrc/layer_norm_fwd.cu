@@ -1,0 +1,160 @@
+// LayerNorm / RMSNorm forward for sm_100a: the row lives in registers (one global read of x, one write of y), rows are
+// spread over a persistent grid sized to the 148 SMs, statistics are a register two-pass (mean, then centred variance).
+// Spec: reference csrc/layer_norm_cuda_kernel.cu:317-376,803-835 (cuApplyLayerNorm / cuApplyRMSNorm: outputs y, mean[n1],
+// invvar[n1] fp32; gamma/beta have the OUTPUT dtype) and apex/contrib/csrc/layer_norm/ln_fwd_kernels.cuh:6-107.
+#include "norm_common.cuh"
+
+namespace ab {
+
+template <int MAXV, typename Tin, typename Tout, bool RMS>
+__global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
+                                                   float* __restrict__ invvar, const Tout* __restrict__ gamma,
+                                                   const Tout* __restrict__ beta, int n1, int n2, float eps, int tpr) {
+  constexpr int E = 16 / sizeof(Tin);
+  __shared__ float sred[64];
+  RowReducer red(sred, tpr);
+  const int rows_per_cta = blockDim.x / tpr;
+  const int nvec = n2 / E;
+  const float inv_n = 1.f / (float)n2;
+  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += gridDim.x * rows_per_cta) {
+    const int row = row0 + red.rg;
+    const bool valid = row < n1;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * n2);
+    uint4 raw[MAXV];
+#pragma unroll
+    for (int v = 0; v < MAXV; v++) {
+      const int idx = v * tpr + red.lane_r;
+      raw[v] = (valid && idx < nvec) ? __ldg(xr + idx) : make_uint4(0, 0, 0, 0);
+    }
+    float mu = 0.f, rstd;
+    if (!RMS) {
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < MAXV; v++) {
+        float f[E]; unpack16<Tin>(raw[v], f);
+#pragma unroll
+        for (int e = 0; e < E; e++) s += f[e];
+      }
+      mu = red.sum(s) * inv_n;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; v++) {
+      const int idx = v * tpr + red.lane_r;
+      if (idx < nvec) {
+        float f[E]; unpack16<Tin>(raw[v], f);
+#pragma unroll
+        for (int e = 0; e < E; e++) { const float d = f[e] - mu; ss += d * d; }
+      }
+    }
+    rstd = rsqrtf(red.sum(ss) * inv_n + eps);
+    if (valid) {
+      if (red.lane_r == 0) {
+        if (!RMS && mean) mean[row] = mu;
+        invvar[row] = rstd;
+      }
+      Tout* yr = y + (size_t)row * n2;
+#pragma unroll
+      for (int v = 0; v < MAXV; v++) {
+        const int idx = v * tpr + red.lane_r;
+        if (idx < nvec) {
+          float f[E]; unpack16<Tin>(raw[v], f);
+          float o[E];
+          if (gamma) {
+            float g[E]; load_vec<Tout, E>(g, gamma + (size_t)idx * E);
+            if (beta) {
+              float b[E]; load_vec<Tout, E>(b, beta + (size_t)idx * E);
+#pragma unroll
+              for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd * g[e] + b[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd * g[e];
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd;
+          }
+          store_vec<Tout, E>(yr + (size_t)idx * E, o);
+        }
+      }
+    }
+  }
+}
+
+// Any n2 / any alignment: one CTA per row, strided scalar access, x re-read from L2 for the second pass.
+template <typename Tin, typename Tout, bool RMS>
+__global__ void __launch_bounds__(256) ln_fwd_generic(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
+                                                      float* __restrict__ invvar, const Tout* __restrict__ gamma,
+                                                      const Tout* __restrict__ beta, int n1, int n2, float eps) {
+  __shared__ float red[40];
+  for (int row = blockIdx.x; row < n1; row += gridDim.x) {
+    const Tin* xr = x + (size_t)row * n2;
+    float mu = 0.f;
+    if (!RMS) {
+      float s = 0.f;
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) s += to_f<Tin>(xr[i]);
+      mu = block_sum(s, red) / (float)n2;
+    }
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) { const float d = to_f<Tin>(xr[i]) - mu; ss += d * d; }
+    const float rstd = rsqrtf(block_sum(ss, red) / (float)n2 + eps);
+    if (threadIdx.x == 0) { if (!RMS && mean) mean[row] = mu; invvar[row] = rstd; }
+    Tout* yr = y + (size_t)row * n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      float o = (to_f<Tin>(xr[i]) - mu) * rstd;
+      if (gamma) o *= to_f<Tout>(gamma[i]);
+      if (beta) o += to_f<Tout>(beta[i]);
+      yr[i] = from_f<Tout>(o);
+    }
+  }
+}
+
+template <typename Tin, typename Tout, bool RMS>
+int ln_fwd_launch(const void* x, void* y, float* mean, float* invvar, const void* gamma, const void* beta, int n1, int n2,
+                  float eps, cudaStream_t st) {
+  constexpr int E = 16 / sizeof(Tin);
+  const bool vec_ok = (n2 % E == 0) && aligned16(x) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 && aligned16(y) &&
+                      ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
+  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 4, 512);
+  if (vec_ok && c.ok) {
+    int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
+    const int cap = kNumSMs * (2048 / c.threads);
+    if (grid > cap) grid = cap;
+#define LN_FWD_GO(MV)                                                                                                 \
+  ln_fwd_vec<MV, Tin, Tout, RMS><<<grid, c.threads, 0, st>>>((const Tin*)x, (Tout*)y, mean, invvar, (const Tout*)gamma, \
+                                                             (const Tout*)beta, n1, n2, eps, c.tpr)
+    switch (c.maxv) {
+      case 1: LN_FWD_GO(1); break;
+      case 2: LN_FWD_GO(2); break;
+      case 4: LN_FWD_GO(4); break;
+      default: LN_FWD_GO(8); break;
+    }
+  } else {
+    int grid = n1 < kNumSMs * 8 ? n1 : kNumSMs * 8;
+    ln_fwd_generic<Tin, Tout, RMS><<<grid, 256, 0, st>>>((const Tin*)x, (Tout*)y, mean, invvar, (const Tout*)gamma,
+                                                        (const Tout*)beta, n1, n2, eps);
+  }
+  AB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+// x[n1,n2] (dt_in) -> y[n1,n2] (dt_out); gamma/beta (dt_out) may be null; mean may be null for RMSNorm.
+AB_API int ab_layer_norm_fwd(const void* x, void* y, float* mean, float* invvar, const void* gamma, const void* beta, int n1,
+                             int n2, float eps, int dt_in, int dt_out, int rms, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return 0;
+#define LN_PAIR(TI, TO)                                                                     \
+  return rms ? ln_fwd_launch<TI, TO, true>(x, y, mean, invvar, gamma, beta, n1, n2, eps, st) \
+             : ln_fwd_launch<TI, TO, false>(x, y, mean, invvar, gamma, beta, n1, n2, eps, st)
+  if (dt_in == kF32 && dt_out == kF32) { LN_PAIR(float, float); }
+  if (dt_in == kF16 && dt_out == kF16) { LN_PAIR(f16, f16); }
+  if (dt_in == kBF16 && dt_out == kBF16) { LN_PAIR(bf16, bf16); }
+  if (dt_in == kF16 && dt_out == kF32) { LN_PAIR(f16, float); }
+  if (dt_in == kBF16 && dt_out == kF32) { LN_PAIR(bf16, float); }
+  if (dt_in == kF32 && dt_out == kF16) { LN_PAIR(float, f16); }
+  if (dt_in == kF32 && dt_out == kBF16) { LN_PAIR(float, bf16); }
+  return -1;
+}

@@ -1,0 +1,61 @@
+// Shared pieces of the row-normalisation kernels (LayerNorm / RMSNorm fwd+bwd).
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+// Sum across the `tpr` threads that share a row. tpr is a power of two in [8, 1024]; rows never straddle a warp when
+// tpr < 32. For tpr > 32 partial sums go through shared memory; `buf` alternates between two banks so one barrier per
+// reduction is enough. EVERY thread of the CTA must call this (uniform control flow).
+struct RowReducer {
+  float* smem;  // [2][32] floats
+  int tpr, lane_r, rg, bank;
+  __device__ __forceinline__ RowReducer(float* s, int tpr_) : smem(s), tpr(tpr_), bank(0) {
+    lane_r = threadIdx.x % tpr_;
+    rg = threadIdx.x / tpr_;
+  }
+  __device__ __forceinline__ float sum(float v) {
+    if (tpr <= 32) {
+      for (int o = tpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    }
+    v = warp_sum(v);
+    const int wpr = tpr >> 5;            // warps per row
+    const int w = threadIdx.x >> 5;      // warp in CTA; rows own consecutive warps
+    float* b = smem + bank * 32;
+    if ((threadIdx.x & 31) == 0) b[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    const int w0 = rg * wpr;
+    for (int i = 0; i < wpr; i++) t += b[w0 + i];
+    bank ^= 1;
+    return t;
+  }
+};
+
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& raw, float (&r)[16 / sizeof(T)]) {
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < (int)(16 / sizeof(T)); i++) r[i] = to_f<T>(e[i]);
+}
+
+struct NormCfg { int tpr, maxv, threads, rows_per_cta; bool ok; };
+
+// Pick threads-per-row / vectors-per-thread for a row of `nvec` 16-byte vectors.
+inline NormCfg norm_cfg(int nvec, int target_v = 4, int max_tpr = 1024) {
+  NormCfg c{};
+  int want = (nvec + target_v - 1) / target_v;
+  int tpr = 8;
+  while (tpr < want) tpr <<= 1;
+  if (tpr > max_tpr) tpr = max_tpr;
+  int mv = (nvec + tpr - 1) / tpr;
+  int maxv = 1;
+  while (maxv < mv) maxv <<= 1;
+  c.tpr = tpr; c.maxv = maxv;
+  c.threads = tpr > 256 ? tpr : 256;
+  c.rows_per_cta = c.threads / tpr;
+  c.ok = maxv <= 8;
+  return c;
+}
+
+}  // namespace ab

@@ -1,0 +1,76 @@
+"""Shared machinery for the fused optimizers: per-(group, dtype) cached device tensor tables.
+
+The reference optimizers rebuild four python lists over every parameter on every step and hand them to a launcher that
+re-validates and re-packs them (apex/optimizers/fused_adam.py:190-232, csrc/multi_tensor_apply.cuh:35-102). Here the table
+for a (param group, dtype) bucket is built once; each step a single C++ call re-reads the ``.grad`` pointers and uploads
+that one column only if it changed. ``step()`` is O(1) python work per bucket.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from ..ops.amp_C import TensorTable
+
+CHUNK = 65536  # elements per work item (same granule as the reference's multi_tensor_applier)
+
+
+class BucketCache:
+    """One cached TensorTable per key (group index, dtype, ...)."""
+
+    def __init__(self):
+        self._tables: dict = {}
+
+    def clear(self):
+        self._tables.clear()
+
+    def cached(self, key):
+        """The cached table with its gradient column refreshed, or None if it must be (re)built."""
+        tb = self._tables.get(key)
+        if tb is None:
+            return None
+        return tb if tb.refresh_grads() else None
+
+    def build(self, key, candidates, members, lists, grad_slot=0, param_slot=1, chunk=CHUNK):
+        """candidates: every param that could belong to this bucket; members: those that currently have a grad;
+        lists: the tensor lists (``.grad`` of members in ``grad_slot``)."""
+        tb = TensorTable(lists, chunk)
+        if grad_slot is not None:
+            tb.track_grads(grad_slot, param_slot)
+            mem = {id(p) for p in members}
+            tb.track_universe(candidates, [id(p) in mem for p in candidates])
+        self._tables[key] = tb
+        return tb
+
+
+def partition_by_dtype(params):
+    """{dtype: [params]} for CUDA/CPU dense params, preserving order."""
+    out: dict = {}
+    for p in params:
+        out.setdefault(p.dtype, []).append(p)
+    return out
+
+
+def flat_state_like(params, dtype=torch.float32):
+    """One flat zero buffer + per-parameter views (fewer allocations, contiguous optimizer state)."""
+    if not params:
+        return []
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, dtype=dtype, device=params[0].device)
+    out, off = [], 0
+    for p in params:
+        n = p.numel()
+        if p.is_contiguous():
+            out.append(flat[off:off + n].view(p.shape))
+        else:
+            out.append(torch.zeros_like(p, dtype=dtype))
+        off += n
+    return out
+
+
+def use_native(params) -> bool:
+    """CUDA params -> native kernels (hard error if the library is missing); CPU params -> PyTorch reference path."""
+    any_cuda = any(p.is_cuda for p in params)
+    if any_cuda and not _lib.available():
+        raise _lib.gpu_required_error("fused optimizer")
+    return any_cuda

@@ -1,0 +1,225 @@
+"""FusedSGD, FusedNovoGrad, FusedAdagrad on the cached device-table engine.
+
+Reference: apex/optimizers/fused_sgd.py:8-284, fused_novograd.py:5-255, fused_adagrad.py:5-134.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from ..ops import amp_C
+from ..ops import reference as ref
+from ._base import BucketCache, partition_by_dtype
+
+
+class _TableOptimizer(torch.optim.Optimizer):
+    set_grad_none = True
+
+    def _init_cache(self):
+        self._cache = BucketCache()
+        self._parts: dict = {}
+
+    def add_param_group(self, g):
+        super().add_param_group(g)
+        if hasattr(self, "_cache"):
+            self._cache.clear()
+            self._parts.clear()
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        self._cache.clear()
+
+    def zero_grad(self, set_to_none: bool | None = None):
+        if self.set_grad_none if set_to_none is None else set_to_none:
+            for group in self.param_groups:
+                for p in group["params"]:
+                    p.grad = None
+        else:
+            super().zero_grad(set_to_none=False)
+
+    def _partition(self, gi, group):
+        parts = self._parts.get(gi)
+        if parts is None:
+            parts = self._parts[gi] = partition_by_dtype(group["params"])
+        return parts
+
+
+class FusedSGD(_TableOptimizer):
+    """SGD with momentum / dampening / nesterov / ``wd_after_momentum``; momentum buffers are created on the first step and that
+    step runs with ``first_run`` semantics (buffer := grad). ``scale`` of the most recent loss scale can be folded into the
+    update via ``most_recent_scale`` (reference :276)."""
+
+    def __init__(self, params, lr, momentum=0, dampening=0, weight_decay=0, nesterov=False, wd_after_momentum=False,
+                 materialize_master_grads=True, set_grad_none=False):
+        if lr is None or lr < 0.0:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if momentum < 0.0:
+            raise ValueError("Invalid momentum value: {}".format(momentum))
+        if weight_decay < 0.0:
+            raise ValueError("Invalid weight_decay value: {}".format(weight_decay))
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        super().__init__(params, defaults)
+        self.wd_after_momentum = wd_after_momentum
+        self.materialize_master_grads = materialize_master_grads
+        self.most_recent_scale = 1.0
+        self.scale_set_by_backward = False
+        self.set_grad_none = set_grad_none
+        self._init_cache()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for group in self.param_groups:
+            group.setdefault("nesterov", False)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            for dtype, cands in self._partition(gi, group).items():
+                is_cuda = cands[0].is_cuda
+                key = (gi, dtype)
+                first_run = False
+                tb = self._cache.cached(key) if is_cuda else None
+                lists = None
+                if tb is None:
+                    members = [p for p in cands if p.grad is not None]
+                    if not members:
+                        continue
+                    for p in members:
+                        st = self.state[p]
+                        if "momentum_buffer" not in st:
+                            first_run = True
+                            st["momentum_buffer"] = torch.zeros_like(p)
+                    lists = [[p.grad for p in members], list(members), [self.state[p]["momentum_buffer"] for p in members]]
+                    if is_cuda:
+                        if not _lib.available():
+                            raise _lib.gpu_required_error("FusedSGD")
+                        tb = self._cache.build(key, cands, members, lists)
+                args = (group["weight_decay"], group["momentum"], group["dampening"], group["lr"], group["nesterov"], first_run,
+                        self.wd_after_momentum, 1.0 / self.most_recent_scale)
+                if tb is not None:
+                    amp_C.multi_tensor_sgd(0, None, tb, *args)
+                else:
+                    ref.multi_tensor_sgd(None, lists, *args)
+        self.most_recent_scale = 1.0
+        self.scale_set_by_backward = False
+        return loss
+
+
+class FusedNovoGrad(_TableOptimizer):
+    """NovoGrad: per-TENSOR second moment (a scalar norm per parameter), kept as one float tensor per (group, dtype)."""
+
+    def __init__(self, params, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False,
+                 reg_inside_moment=False, grad_averaging=True, norm_type=2, init_zero=False, set_grad_none=True):
+        if amsgrad:
+            raise RuntimeError("FusedNovoGrad does not support the AMSGrad variant.")
+        if norm_type not in (0, 2):
+            raise RuntimeError("FusedNovoGrad only support l2/inf norm now.")
+        defaults = dict(lr=lr, bias_correction=bias_correction, betas=betas, eps=eps, weight_decay=weight_decay,
+                        grad_averaging=grad_averaging, norm_type=norm_type, init_zero=init_zero)
+        super().__init__(params, defaults)
+        self.moment_mode = 0 if reg_inside_moment else 1
+        self.set_grad_none = set_grad_none
+        self._init_cache()
+        self._norms: dict = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:  # per-group norm tensors must live with the params (reference :118-124)
+            if "exp_avg_sq" in group and group["params"]:
+                dev = group["params"][0].device
+                group["exp_avg_sq"] = [t.to(dev) if torch.is_tensor(t) else t for t in group["exp_avg_sq"]]
+        self._norms.clear()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            beta1, beta2 = group["betas"]
+            group["step"] = group.get("step", 0) + 1
+            for dtype, cands in self._partition(gi, group).items():
+                is_cuda = cands[0].is_cuda
+                key = (gi, dtype)
+                tb = self._cache.cached(key) if is_cuda else None
+                lists = None
+                if tb is None or key not in self._norms:
+                    members = [p for p in cands if p.grad is not None]
+                    if not members:
+                        continue
+                    for p in members:
+                        if "exp_avg" not in self.state[p]:
+                            self.state[p]["exp_avg"] = torch.zeros_like(p)
+                    lists = [[p.grad for p in members], list(members), [self.state[p]["exp_avg"] for p in members]]
+                    norms = self._norms.get(key)
+                    if norms is None or norms.numel() != len(members):
+                        if group["init_zero"]:
+                            norms = torch.zeros(len(members), dtype=torch.float32, device=members[0].device)
+                        elif group["norm_type"] == 0:
+                            norms = torch.stack([p.grad.float().abs().max() for p in members])
+                        else:
+                            norms = torch.stack([p.grad.float().norm() for p in members])
+                        self._norms[key] = norms
+                        group.setdefault("exp_avg_sq", {})
+                        if isinstance(group["exp_avg_sq"], dict):
+                            group["exp_avg_sq"][str(dtype)] = norms
+                    if is_cuda:
+                        if not _lib.available():
+                            raise _lib.gpu_required_error("FusedNovoGrad")
+                        tb = self._cache.build(key, cands, members, lists)
+                args = (self._norms[key], group["lr"], beta1, beta2, group["eps"], group["step"], 1 if group["bias_correction"] else 0,
+                        group["weight_decay"], 1 if group["grad_averaging"] else 0, self.moment_mode, group["norm_type"])
+                if tb is not None:
+                    amp_C.multi_tensor_novograd(0, None, tb, *args)
+                else:
+                    ref.multi_tensor_novograd(lists, *args)
+        return loss
+
+
+class FusedAdagrad(_TableOptimizer):
+    def __init__(self, params, lr=1e-2, eps=1e-10, weight_decay=0.0, set_grad_none=True, adagrad_w_mode=False):
+        defaults = dict(lr=lr, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.adagrad_w_mode = 1 if adagrad_w_mode else 0
+        self.set_grad_none = set_grad_none
+        self._init_cache()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            for dtype, cands in self._partition(gi, group).items():
+                is_cuda = cands[0].is_cuda
+                key = (gi, dtype)
+                tb = self._cache.cached(key) if is_cuda else None
+                lists = None
+                if tb is None:
+                    members = [p for p in cands if p.grad is not None]
+                    if not members:
+                        continue
+                    for p in members:
+                        if p.grad.is_sparse:
+                            raise RuntimeError("FusedAdagrad does not support sparse gradients")
+                        if "sum" not in self.state[p]:
+                            self.state[p]["sum"] = torch.zeros_like(p)
+                    lists = [[p.grad for p in members], list(members), [self.state[p]["sum"] for p in members]]
+                    if is_cuda:
+                        if not _lib.available():
+                            raise _lib.gpu_required_error("FusedAdagrad")
+                        tb = self._cache.build(key, cands, members, lists)
+                args = (group["lr"], group["eps"], self.adagrad_w_mode, group["weight_decay"])
+                if tb is not None:
+                    amp_C.multi_tensor_adagrad(0, None, tb, *args)
+                else:
+                    ref.multi_tensor_adagrad(lists, *args)
+        return loss

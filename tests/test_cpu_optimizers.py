@@ -1,0 +1,77 @@
+"""CPU path: the PyTorch-reference fallbacks must match torch.optim (BASELINE.json config #1 plumbing)."""
+import copy
+
+import pytest
+import torch
+
+from apex_b200.normalization import FusedLayerNorm, FusedRMSNorm
+from apex_b200.optimizers import FusedAdagrad, FusedAdam, FusedLAMB, FusedNovoGrad, FusedSGD
+
+
+def _params(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.nn.Parameter(torch.randn(s, generator=g)) for s in [(37, 5), (278,), (4, 3, 3)]]
+
+
+def _run(opt_a, opt_b, pa, pb, iters=7):
+    g = torch.Generator().manual_seed(1)
+    for _ in range(iters):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        opt_a.step()
+        opt_b.step()
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("adam_w", [True, False])
+def test_fused_adam_cpu_matches_torch(adam_w):
+    pa, pb = _params(), _params()
+    a = FusedAdam(pa, lr=1e-2, weight_decay=0.05, adam_w_mode=adam_w)
+    b = (torch.optim.AdamW if adam_w else torch.optim.Adam)(pb, lr=1e-2, weight_decay=0.05)
+    _run(a, b, pa, pb)
+
+
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_fused_sgd_cpu_matches_torch(nesterov):
+    pa, pb = _params(), _params()
+    a = FusedSGD(pa, lr=1e-2, momentum=0.9, weight_decay=0.01, nesterov=nesterov)
+    b = torch.optim.SGD(pb, lr=1e-2, momentum=0.9, weight_decay=0.01, nesterov=nesterov)
+    _run(a, b, pa, pb)
+
+
+def test_fused_adagrad_cpu_matches_torch():
+    pa, pb = _params(), _params()
+    _run(FusedAdagrad(pa, lr=1e-2, weight_decay=0.01), torch.optim.Adagrad(pb, lr=1e-2, weight_decay=0.01), pa, pb)
+
+
+def test_mlp_trains_on_cpu():
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(16, 32), FusedLayerNorm(32), torch.nn.ReLU(), torch.nn.Linear(32, 4), FusedRMSNorm(4))
+    x, y = torch.randn(64, 16), torch.randn(64, 4)
+    for Opt, kw in [(FusedAdam, dict(lr=1e-2)), (FusedLAMB, dict(lr=1e-2)), (FusedNovoGrad, dict(lr=1e-2))]:
+        mm = copy.deepcopy(m)
+        opt = Opt(mm.parameters(), **kw)
+        first = last = None
+        for _ in range(25):
+            loss = ((mm(x) - y) ** 2).mean()
+            first = first if first is not None else loss.item()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            last = loss.item()
+        assert last < first, (Opt.__name__, first, last)
+
+
+def test_state_dict_roundtrip_cpu():
+    pa = _params()
+    a = FusedAdam(pa, lr=1e-2)
+    for p in pa:
+        p.grad = torch.ones_like(p)
+    a.step()
+    sd = copy.deepcopy(a.state_dict())
+    b = FusedAdam(_params(), lr=1e-2)
+    b.load_state_dict(sd)
+    assert b.state_dict()["param_groups"][0]["step"] == 1

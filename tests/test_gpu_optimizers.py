@@ -1,0 +1,129 @@
+"""Fused optimizers on the GPU vs torch.optim / in-file oracles (reference tests/L0/run_optimizers)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(dev, dtype=torch.float32):
+    g = torch.Generator().manual_seed(0)
+    return [torch.nn.Parameter(torch.randn(s, generator=g).to(dev, dtype)) for s in [(4096, 64), (4096,), (278011,), (3, 5, 7)]]
+
+
+def _drive(opt_a, opt_b, pa, pb, iters=7, set_none=False):
+    g = torch.Generator().manual_seed(1)
+    for _ in range(iters):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g)
+            a.grad = gr.to(a.device, a.dtype)
+            b.grad = gr.to(b.device, b.dtype)
+        opt_a.step()
+        opt_b.step()
+        if set_none:
+            opt_a.zero_grad()
+
+
+@pytest.mark.parametrize("adam_w", [True, False])
+def test_fused_adam_vs_torch(cuda_dev, adam_w):
+    from apex_b200.optimizers import FusedAdam
+    pa, pb = _params(cuda_dev), _params(cuda_dev)
+    a = FusedAdam(pa, lr=5e-3, weight_decay=0.1, adam_w_mode=adam_w)
+    b = (torch.optim.AdamW if adam_w else torch.optim.Adam)(pb, lr=5e-3, weight_decay=0.1)
+    _drive(a, b, pa, pb, set_none=True)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 1e-3
+
+
+def test_fused_adam_table_is_cached(cuda_dev):
+    from apex_b200.optimizers import FusedAdam
+    pa = _params(cuda_dev)
+    a = FusedAdam(pa, lr=1e-3)
+    grads = [torch.randn_like(p) for p in pa]
+    for _ in range(5):
+        for p, g in zip(pa, grads):
+            p.grad = g
+        a.step()
+    tb = a._cache._tables[(0, torch.float32)]
+    assert tb.uploads == 1  # built once; the grad pointers never moved so nothing was re-uploaded
+
+
+def test_fused_adam_bf16_and_frozen_param(cuda_dev):
+    from apex_b200.optimizers import FusedAdam
+    pa = _params(cuda_dev, torch.bfloat16)
+    a = FusedAdam(pa, lr=1e-2)
+    for it in range(3):
+        for i, p in enumerate(pa):
+            p.grad = None if (i == 1 and it == 1) else torch.ones_like(p)
+        before = pa[1].clone()
+        a.step()
+        if it == 1:
+            assert torch.equal(before, pa[1])  # no grad -> untouched (table rebuilt)
+    assert all(torch.isfinite(p.float()).all() for p in pa)
+
+
+def test_fused_adam_capturable_with_grad_scaler(cuda_dev):
+    from apex_b200.optimizers import FusedAdam
+    pa, pb = _params(cuda_dev), _params(cuda_dev)
+    a = FusedAdam(pa, lr=5e-3, capturable=True)
+    b = torch.optim.AdamW(pb, lr=5e-3, weight_decay=0.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=64.0)
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).to(cuda_dev)
+            x.grad = gr * 64.0
+            y.grad = gr.clone()
+        if it == 2:
+            pa[0].grad[0, 0] = float("inf")  # this step must be skipped
+            scaler._scale = torch.full((), 64.0, device=cuda_dev)
+        scaler._lazy_init_scale_growth_tracker(cuda_dev) if scaler._scale is None else None
+        scaler.step(a)
+        scaler.update(64.0)
+        if it != 2:
+            b.step()
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 1e-3
+
+
+def test_fused_sgd_adagrad_vs_torch(cuda_dev):
+    from apex_b200.optimizers import FusedAdagrad, FusedSGD
+    pa, pb = _params(cuda_dev), _params(cuda_dev)
+    _drive(FusedSGD(pa, lr=0.05, momentum=0.9, weight_decay=0.01, nesterov=True),
+           torch.optim.SGD(pb, lr=0.05, momentum=0.9, weight_decay=0.01, nesterov=True), pa, pb)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 1e-3
+    pa, pb = _params(cuda_dev), _params(cuda_dev)
+    _drive(FusedAdagrad(pa, lr=0.05, weight_decay=0.01), torch.optim.Adagrad(pb, lr=0.05, weight_decay=0.01), pa, pb)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 1e-3
+
+
+def test_fused_lamb_and_novograd_vs_cpu_reference_path(cuda_dev):
+    """The CPU path of the same optimizer class is plain PyTorch math: GPU kernels must agree with it."""
+    from apex_b200.optimizers import FusedLAMB, FusedNovoGrad
+    for Opt, kw in [(FusedLAMB, dict(lr=1e-2, weight_decay=0.01, max_grad_norm=1.0)), (FusedNovoGrad, dict(lr=1e-2, weight_decay=0.01))]:
+        pa, pb = _params(cuda_dev), _params("cpu")
+        _drive(Opt(pa, **kw), Opt(pb, **kw), pa, pb, iters=4)
+        for x, y in zip(pa, pb):
+            assert (x.cpu() - y).abs().max().item() <= 2e-3, Opt.__name__
+
+
+def test_mixed_precision_lamb(cuda_dev):
+    from apex_b200.optimizers import FusedMixedPrecisionLamb
+    pa = _params(cuda_dev, torch.bfloat16)
+    opt = FusedMixedPrecisionLamb(pa, lr=1e-2, reduced_precision_dtype=torch.bfloat16)
+    ref0 = [p.clone() for p in pa]
+    for _ in range(3):
+        for p in pa:
+            p.grad = torch.randn_like(p)
+        opt.step()
+    assert int(opt.param_groups[0]["step"].item()) == 3
+    assert all(torch.isfinite(p.float()).all() for p in pa)
+    assert any((p.float() - r.float()).abs().max() > 0 for p, r in zip(pa, ref0))
+    sd = copy.deepcopy(opt.state_dict())
+    opt.load_state_dict(sd)
+    for p in pa:
+        p.grad = torch.randn_like(p)
+    opt.step()
