@@ -1,0 +1,306 @@
+// ZeRO-2 optimizer step as in-kernel collectives over NVLink 5 / NVSwitch (no NCCL on this path):
+//
+//   MODE_FUSED : reduce-scatter (pull peers' grad shards, or ONE multimem.ld_reduce through the switch) + scale + grad-norm
+//                + Adam/AdamW on the fp32 shard + all-gather (push the new low-precision params to every rank, or ONE
+//                multimem.st) — a single pass; HBM traffic of the update hides under the link traffic.
+//   MODE_RS    : reduce-scatter + norm only (writes the fp32 reduced shard) — used when the update needs the global norm
+//                first (clipping / GradScaler), and per bucket while backward is still running (overlap_grad_sync).
+//   MODE_ADAM  : Adam on the reduced shard + all-gather push.
+//
+// Replaces the reference pipeline: _grad_copy into buckets (distributed_fused_adam.py:1600-1666) -> NCCL
+// reduce_scatter_tensor (:1929-1947) -> multi_tensor_l2norm (:2216) -> DistAdamFunctor (multi_tensor_distopt_adam_kernel.cu:84-168)
+// -> NCCL all_gather_into_tensor (:2067-2082) -> maybe_cast_mt copy-out (:1716-1767).
+//
+// Layout: the flat parameter space is cut into `n_buckets` buckets of `bucket_elems`; bucket b is sharded D ways, rank r owns
+// flat range [b*B + r*Sb, b*B + (r+1)*Sb). Local state (p, m, v fp32) is bucket-major: local index = b*Sb + o.
+// Cross-rank ordering uses epoch signals (symm_device.cuh): start = "my grads are final and my params buffer may be
+// overwritten"; end = "I no longer read your grads and everything I pushed into your params is visible".
+#include "symm_device.cuh"
+
+namespace ab {
+
+constexpr int kDChunk = 2048;   // elements per CTA work item (256 threads x 8)
+constexpr int kDThreads = 256;
+
+enum { MODE_FUSED = 0, MODE_RS = 1, MODE_ADAM = 2 };
+
+struct DistArgs {
+  PeerPtrs grads;    // every rank's full gradient buffer (TG) as mapped here
+  PeerPtrs params;   // every rank's full parameter buffer (TP)
+  const void* mc_grads;  // multicast alias of the gradient buffers (NVLS) or null
+  void* mc_params;       // multicast alias of the parameter buffers or null
+  float* p; float* m; float* v;  // local fp32 shards
+  float* reduced;                // local fp32 reduced-gradient shard (MODE_RS out / MODE_ADAM in)
+  long long bucket_elems;
+  int shard_elems, bucket_begin, bucket_end;
+  int lay_rank;  // which shard of every bucket this rank owns (== sig.rank on the fused path; sig.world may be 1 when the
+                 // collectives are done by NCCL around the kernel and only the layout is sharded)
+  Signal sig;
+  int chan_start, chan_end, norm_slot;
+  unsigned int* done_ctr;
+  float* norm_partials;  // [gridDim.x]
+  float* norm_out;       // [0] = this shard's sum of squares, [1] = sum over all ranks
+  const float* grad_scale;
+  float pre_scale;
+  float lr, beta1, beta2, bc1, bc2, eps, decay;
+  int mode;
+  const int* noop;
+  const float* lr_ptr;   // capturable: learning rate and step count live on the device
+  const int* step_ptr;
+  int bias_correction;
+};
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4* raw, float (&f)[8]) {
+  const T* e = reinterpret_cast<const T*>(raw);
+#pragma unroll
+  for (int i = 0; i < 8; i++) f[i] = to_f<T>(e[i]);
+}
+
+__device__ __forceinline__ float lerp_f(float t, float x, float y) { return fmaf(t, y, fmaf(-t, x, x)); }
+
+template <typename TG, typename TP, int MODE, bool NVLS>
+__global__ void __launch_bounds__(kDThreads, 2) dist_step_kernel(DistArgs a) {
+  constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
+  constexpr int PV = sizeof(TP) * 8 / 16;
+  __shared__ float red[40];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int D = a.sig.world, rank = a.sig.rank;
+
+  if (MODE != MODE_ADAM && D > 1) {
+    if (blockIdx.x == 0) signal_all(a.sig, a.chan_start, tid);
+    wait_all(a.sig, a.chan_start, tid);
+    __syncthreads();
+  }
+
+  const bool skip = (MODE != MODE_RS) && a.noop != nullptr && *a.noop != 0;
+  float lr = a.lr, bc1 = a.bc1, bc2 = a.bc2;
+  if (MODE != MODE_RS) {
+    if (a.lr_ptr) lr = *a.lr_ptr;
+    if (a.step_ptr && a.bias_correction) {
+      const float sf = (float)(*a.step_ptr);
+      bc1 = 1.f - powf(a.beta1, sf);
+      bc2 = 1.f - powf(a.beta2, sf);
+    }
+  }
+  const float gs = (MODE != MODE_RS && a.grad_scale) ? *a.grad_scale : 1.f;
+  const int cpb = a.shard_elems / kDChunk;  // chunks per bucket shard
+  const long long c0 = (long long)a.bucket_begin * cpb, c1 = (long long)a.bucket_end * cpb;
+  float nsq = 0.f;
+
+  if (!skip) {
+    for (long long c = c0 + blockIdx.x; c < c1; c += gridDim.x) {
+      const long long b = c / cpb;
+      const int oc = (int)(c - b * cpb);
+      const long long local = c * kDChunk + tid * 8;
+      const long long flat = b * a.bucket_elems + (long long)a.lay_rank * a.shard_elems + (long long)oc * kDChunk + tid * 8;
+      float g[8];
+      if (MODE == MODE_ADAM) {
+        const float4 r0 = *reinterpret_cast<const float4*>(a.reduced + local);
+        const float4 r1 = *reinterpret_cast<const float4*>(a.reduced + local + 4);
+        g[0] = r0.x; g[1] = r0.y; g[2] = r0.z; g[3] = r0.w; g[4] = r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) g[i] = 0.f;
+        if (NVLS) {
+          uint4 raw[GV];
+#pragma unroll
+          for (int q = 0; q < GV; q++)
+            raw[q] = multimem_ld_reduce16<TG>(reinterpret_cast<const char*>(a.mc_grads) + flat * sizeof(TG) + q * 16);
+          unpack8<TG>(raw, g);
+        } else {
+          uint4 raw[kMaxPeers][GV];
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; p++) {
+            if (p < D) {
+#pragma unroll
+              for (int q = 0; q < GV; q++)
+                raw[p][q] = ld_peer16(reinterpret_cast<const char*>(a.grads.p[p]) + flat * sizeof(TG) + q * 16);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; p++) {  // fixed summation order => bitwise reproducible
+            if (p < D) {
+              float f[8];
+              unpack8<TG>(raw[p], f);
+#pragma unroll
+              for (int i = 0; i < 8; i++) g[i] += f[i];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { g[i] *= a.pre_scale; nsq += g[i] * g[i]; }
+      }
+      if (MODE == MODE_RS) {
+        *reinterpret_cast<float4*>(a.reduced + local) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(a.reduced + local + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      } else {
+        float p[8], m[8], v[8];
+        {
+          const float4 x0 = *reinterpret_cast<const float4*>(a.p + local), x1 = *reinterpret_cast<const float4*>(a.p + local + 4);
+          const float4 y0 = *reinterpret_cast<const float4*>(a.m + local), y1 = *reinterpret_cast<const float4*>(a.m + local + 4);
+          const float4 z0 = *reinterpret_cast<const float4*>(a.v + local), z1 = *reinterpret_cast<const float4*>(a.v + local + 4);
+          p[0] = x0.x; p[1] = x0.y; p[2] = x0.z; p[3] = x0.w; p[4] = x1.x; p[5] = x1.y; p[6] = x1.z; p[7] = x1.w;
+          m[0] = y0.x; m[1] = y0.y; m[2] = y0.z; m[3] = y0.w; m[4] = y1.x; m[5] = y1.y; m[6] = y1.z; m[7] = y1.w;
+          v[0] = z0.x; v[1] = z0.y; v[2] = z0.z; v[3] = z0.w; v[4] = z1.x; v[5] = z1.y; v[6] = z1.z; v[7] = z1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          float sg = g[i] * gs;
+          if (a.mode == 0) sg += a.decay * p[i];
+          m[i] = lerp_f(a.beta1, sg, m[i]);
+          v[i] = lerp_f(a.beta2, sg * sg, v[i]);
+          float upd = (m[i] / bc1) / (sqrtf(v[i] / bc2) + a.eps);
+          if (a.mode != 0) upd += a.decay * p[i];
+          p[i] -= lr * upd;
+        }
+        *reinterpret_cast<float4*>(a.p + local) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(a.p + local + 4) = make_float4(p[4], p[5], p[6], p[7]);
+        *reinterpret_cast<float4*>(a.m + local) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(a.m + local + 4) = make_float4(m[4], m[5], m[6], m[7]);
+        *reinterpret_cast<float4*>(a.v + local) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(a.v + local + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        uint4 out[PV];
+        {
+          TP* e = reinterpret_cast<TP*>(out);
+#pragma unroll
+          for (int i = 0; i < 8; i++) e[i] = from_f<TP>(p[i]);
+        }
+        if (NVLS) {
+#pragma unroll
+          for (int q = 0; q < PV; q++) multimem_st16(reinterpret_cast<char*>(a.mc_params) + flat * sizeof(TP) + q * 16, out[q]);
+        } else {
+#pragma unroll
+          for (int p2 = 0; p2 < kMaxPeers; p2++) {
+            if (p2 < D) {
+              const int dst = (rank + p2) % D;  // stagger targets so the D ranks do not all hit the same peer at once
+#pragma unroll
+              for (int q = 0; q < PV; q++) st_peer16(reinterpret_cast<char*>(a.params.p[dst]) + flat * sizeof(TP) + q * 16, out[q]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: per-CTA norm partial, then the last CTA to finish closes the collective
+  if (MODE != MODE_ADAM) {
+    const float s = block_sum(nsq, red);
+    if (tid == 0) a.norm_partials[blockIdx.x] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    const unsigned int ticket = atomicAdd(a.done_ctr, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (MODE != MODE_ADAM) {
+    float s = 0.f;
+    for (int k = tid; k < (int)gridDim.x; k += kDThreads) s += __ldcg(a.norm_partials + k);
+    s = block_sum(s, red);
+    if (tid == 0) a.norm_out[0] = s;
+    if (D > 1) {
+      // publish this shard's sum of squares into slot [norm_slot][rank] of every pad
+      if (tid < D) {
+        float* scratch = reinterpret_cast<float*>(reinterpret_cast<uint32_t*>(a.sig.pads.p[tid]) + kPadChannels * kMaxPeers);
+        st_relaxed_sys_f32(scratch + a.norm_slot * kMaxPeers + rank, s);
+      }
+      __threadfence_system();
+      __syncthreads();
+    } else if (tid == 0) {
+      a.norm_out[1] = s;
+    }
+  }
+  if (D > 1) {
+    signal_all(a.sig, a.chan_end, tid);
+    wait_all(a.sig, a.chan_end, tid);
+    __syncthreads();
+    if (MODE != MODE_ADAM && tid == 0) {
+      const float* scratch = reinterpret_cast<const float*>(reinterpret_cast<const uint32_t*>(a.sig.pads.p[rank]) + kPadChannels * kMaxPeers);
+      float tot = 0.f;
+      for (int r = 0; r < D; r++) tot += ld_relaxed_sys_f32(scratch + a.norm_slot * kMaxPeers + r);
+      a.norm_out[1] = tot;
+    }
+  }
+  if (tid == 0) *a.done_ctr = 0u;
+}
+
+template <typename TG, typename TP>
+int dist_launch(const DistArgs& a, int mode, int nvls, int grid, cudaStream_t st) {
+#define DGO(M, N) dist_step_kernel<TG, TP, M, N><<<grid, kDThreads, 0, st>>>(a)
+  if (mode == MODE_FUSED) { if (nvls) DGO(MODE_FUSED, true); else DGO(MODE_FUSED, false); }
+  else if (mode == MODE_RS) { if (nvls) DGO(MODE_RS, true); else DGO(MODE_RS, false); }
+  else { if (nvls) DGO(MODE_ADAM, true); else DGO(MODE_ADAM, false); }
+  AB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+// grads/params/pads: arrays of `world` pointers (this process's mappings of every rank's buffers).
+AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const uint64_t* params, const uint64_t* pads,
+                             uint64_t mc_grads, uint64_t mc_params, float* p, float* m, float* v, float* reduced,
+                             long long bucket_elems, int shard_elems, int bucket_begin, int bucket_end, int lay_rank, int rank, int world,
+                             unsigned int epoch, int chan_start, int chan_end, int norm_slot, unsigned int* done_ctr,
+                             float* norm_partials, float* norm_out, const float* grad_scale, float pre_scale, float lr, float beta1,
+                             float beta2, float eps, int step, int adam_mode, int bias_correction, float decay, const int* noop,
+                             const float* lr_ptr, const int* step_ptr,
+                             int dt_g, int dt_p, int grid, cudaStream_t st) {
+  if (world < 1 || world > kMaxPeers) return -3;
+  if (shard_elems % kDChunk != 0) return -4;
+  DistArgs a;
+  for (int i = 0; i < kMaxPeers; i++) {
+    a.grads.p[i] = i < world && grads ? (void*)grads[i] : nullptr;
+    a.params.p[i] = i < world && params ? (void*)params[i] : nullptr;
+    a.sig.pads.p[i] = i < world && pads ? (void*)pads[i] : nullptr;
+  }
+  a.mc_grads = (const void*)mc_grads; a.mc_params = (void*)mc_params;
+  a.p = p; a.m = m; a.v = v; a.reduced = reduced;
+  a.bucket_elems = bucket_elems; a.shard_elems = shard_elems; a.bucket_begin = bucket_begin; a.bucket_end = bucket_end;
+  a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch; a.lay_rank = lay_rank;
+  a.chan_start = chan_start; a.chan_end = chan_end; a.norm_slot = norm_slot;
+  a.done_ctr = done_ctr; a.norm_partials = norm_partials; a.norm_out = norm_out;
+  a.grad_scale = grad_scale; a.pre_scale = pre_scale;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.decay = decay; a.mode = adam_mode;
+  a.bc1 = 1.f; a.bc2 = 1.f;
+  if (bias_correction) {
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    a.bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  }
+  a.noop = noop; a.lr_ptr = lr_ptr; a.step_ptr = step_ptr; a.bias_correction = bias_correction;
+  if (grid <= 0) grid = kNumSMs * 2;
+  const long long chunks = (long long)(bucket_end - bucket_begin) * (shard_elems / kDChunk);
+  if (chunks <= 0) return 0;
+  if (chunks < grid) grid = (int)chunks;
+  const bool use_nvls = nvls && world > 1 && ((mode == MODE_ADAM) || mc_grads) && ((mode == MODE_RS) || mc_params);
+#define DPAIR(TG, TP) return dist_launch<TG, TP>(a, mode, use_nvls ? 1 : 0, grid, st)
+  if (dt_g == kBF16 && dt_p == kBF16) DPAIR(bf16, bf16);
+  if (dt_g == kF16 && dt_p == kF16) DPAIR(f16, f16);
+  if (dt_g == kF32 && dt_p == kF32) DPAIR(float, float);
+  if (dt_g == kBF16 && dt_p == kF32) DPAIR(bf16, float);
+  if (dt_g == kF16 && dt_p == kF32) DPAIR(f16, float);
+  if (dt_g == kF32 && dt_p == kBF16) DPAIR(float, bf16);
+  if (dt_g == kF32 && dt_p == kF16) DPAIR(float, f16);
+  return -1;
+}
+
+// Plain cross-rank barrier kernel on a channel (used by tests and by buffer (re)initialisation).
+__global__ void symm_barrier_kernel(Signal s, int channel) {
+  signal_all(s, channel, threadIdx.x);
+  wait_all(s, channel, threadIdx.x);
+}
+AB_API int ab_symm_barrier(const uint64_t* pads, int rank, int world, unsigned int epoch, int channel, cudaStream_t st) {
+  Signal s;
+  for (int i = 0; i < kMaxPeers; i++) s.pads.p[i] = i < world ? (void*)pads[i] : nullptr;
+  s.rank = rank; s.world = world; s.epoch = epoch;
+  symm_barrier_kernel<<<1, 32, 0, st>>>(s, channel);
+  AB_CHECK_LAUNCH();
+  return 0;
+}
+
+AB_API int ab_symm_pad_words() { return kPadWords; }

@@ -1,0 +1,139 @@
+"""DistributedFusedAdam on GPUs: the one-kernel step (csrc/dist_adam.cu) vs AdamW / DDP oracles.
+Single-GPU cases always run; multi-GPU cases need >= 2 devices (gpurun --gpus 2)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("two_phase", [False, True])
+def test_world1_fused_kernel_matches_adamw(cuda_dev, pdtype, two_phase):
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    shapes = [(300, 77), (4099,), (64, 64), (5,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=cuda_dev).to(pdtype)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().float().clone()) for p in ps]
+    a = DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.1, bucket_cap_mb=0.05)
+    b = torch.optim.AdamW(qs, lr=1e-2, weight_decay=0.1)
+    assert a.fused_collectives
+    for it in range(4):
+        a.zero_grad()
+        for p, q in zip(ps, qs):
+            g = torch.randn(p.shape, device=cuda_dev).to(pdtype)
+            p.grad.copy_(g)
+            q.grad = g.float()
+        if two_phase:
+            n = a.clip_grad_norm(0.5)
+            nr = torch.nn.utils.clip_grad_norm_(qs, 0.5)
+            torch.testing.assert_close(n, nr, rtol=1e-4, atol=1e-5)
+        a.step()
+        b.step()
+    tol = 1e-5 if pdtype == torch.float32 else 2e-2
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.float(), q, rtol=tol, atol=tol)
+    assert a.kernel_launches == (8 if two_phase else 4)
+    if not two_phase:
+        torch.testing.assert_close(a.last_grad_norm(), torch.stack([q.grad.norm() for q in qs]).norm(), rtol=1e-4, atol=1e-5)
+
+
+def test_world1_capturable_and_state_dict(cuda_dev):
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(1000, 33, device=cuda_dev, dtype=torch.bfloat16))]
+    qs = [torch.nn.Parameter(ps[0].detach().float().clone())]
+    a = DistributedFusedAdam(ps, lr=1e-2, capturable=True, bucket_cap_mb=0.05)
+    b = torch.optim.AdamW(qs, lr=1e-2, weight_decay=0.0)
+    for it in range(3):
+        a.zero_grad()
+        g = torch.randn_like(ps[0])
+        ps[0].grad.copy_(g)
+        qs[0].grad = g.float()
+        a.param_groups[0]["lr"].fill_(1e-2 * (it + 1))
+        b.param_groups[0]["lr"] = 1e-2 * (it + 1)
+        a.step()
+        b.step()
+    torch.testing.assert_close(ps[0].float(), qs[0], rtol=2e-2, atol=2e-2)
+    sd = a.state_dict()
+    torch.testing.assert_close(sd["state"][0]["param"].to(cuda_dev), qs[0].detach(), rtol=1e-4, atol=1e-4)
+    assert int(a.param_groups[0]["step"].item()) == 3
+
+
+def test_generic_path_matches_fused_path(cuda_dev):
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    base = [torch.randn(513, 31, device=cuda_dev), torch.randn(70000, device=cuda_dev)]
+    res = []
+    for fused in ("auto", False):
+        ps = [torch.nn.Parameter(t.clone()) for t in base]
+        o = DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.05, fused_collectives=fused, bucket_cap_mb=0.1)
+        g = torch.Generator(device=cuda_dev).manual_seed(5)
+        for _ in range(3):
+            o.zero_grad()
+            for p in ps:
+                p.grad.copy_(torch.randn(p.shape, device=cuda_dev, generator=g))
+            o.step()
+        res.append([p.detach().clone() for p in ps])
+    for x, y in zip(*res):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
+
+
+def test_param_remainders_generic(cuda_dev):
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    w = torch.randn(4096, 9, device=cuda_dev)
+    p = torch.nn.Parameter(w.bfloat16())
+    q = torch.nn.Parameter(w.bfloat16().float())
+    a = DistributedFusedAdam([p], lr=1e-2, store_param_remainders=True, bucket_cap_mb=0.05)
+    b = torch.optim.AdamW([q], lr=1e-2, weight_decay=0.0)
+    for _ in range(3):
+        a.zero_grad()
+        g = torch.randn_like(p)
+        p.grad.copy_(g)
+        q.grad = g.float()
+        a.step()
+        b.step()
+    # bf16 param + int16 remainder reproduces the fp32 master exactly -> the bf16 view is the rounded fp32 value
+    torch.testing.assert_close(p.float(), q.detach().bfloat16().float(), rtol=0, atol=1e-2)
+
+
+# ---------------------------------------------------------------- multi-GPU (NVLink P2P / NVLS in-kernel collectives)
+@pytest.mark.parametrize("clip", [False, True])
+def test_two_gpus_fused_matches_ddp_adamw(cuda_dev, clip):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 2, "cuda", True, 4, clip, backend="nccl")
+
+
+def test_two_gpus_fused_bf16(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 2, "cuda", True, 3, False, torch.bfloat16, None, backend="nccl")
+
+
+def test_two_gpus_nccl_path_matches_ddp_adamw(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 2, "cuda", False, 3, True, backend="nccl")
+
+
+def test_two_gpus_grad_scaler(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_grad_scaler_skips_on_inf, 2, "cuda", backend="nccl")
+
+
+def test_four_gpus_fused(cuda_dev):
+    _need(4)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 4, "cuda", True, 3, True, backend="nccl")

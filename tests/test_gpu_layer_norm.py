@@ -27,7 +27,10 @@ def test_norm_fwd_bwd(cuda_dev, shape, n2, dtype, rms, memory_efficient):
     torch.manual_seed(0)
     mod = (FusedRMSNorm if rms else FusedLayerNorm)(n2, eps=1e-5, memory_efficient=memory_efficient).to(cuda_dev, dtype)
     with torch.no_grad():
-        mod.weight.copy_(torch.randn(n2) * 0.5 + 1.0)
+        w = torch.randn(n2) * 0.5 + 1.0
+        if memory_efficient:  # x-hat is rebuilt as (y-b)/w: keep |w| away from 0 or 16-bit rounding is amplified without bound
+            w = w.abs() + 0.5
+        mod.weight.copy_(w)
         if not rms:
             mod.bias.copy_(torch.randn(n2) * 0.1)
     x = torch.randn(shape, device=cuda_dev, dtype=dtype, requires_grad=True)
