@@ -1,0 +1,121 @@
+"""tcgen05 / TMEM / TMA GEMM front-end (csrc/gemm_sm100.cu): ``D = op(A) @ op(B)`` with fused epilogues.
+
+``linear_*`` helpers express the three GEMMs of a linear layer (forward, dgrad, wgrad) without materialising transposes:
+the kernel reads either operand K-major or MN-major straight from its row-major storage.
+Shapes the kernel does not take (fp32/fp64 operands, inner extents that are not multiples of 8) go to cuBLAS via torch.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+
+_lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l i p")
+_lib.declare("ab_colsum", "p p p i i l i p")
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_ACCUM, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_RELU, EPI_SIGMOID = range(9)
+
+_ws: dict = {}
+stats = {"native": 0, "fallback": 0}
+
+
+def _native_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return (a.is_cuda and a.dtype in (torch.bfloat16, torch.float16) and a.dtype == b.dtype and _lib.available()
+            and a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_dtype=None, epi: int = EPI_NONE,
+         bias: torch.Tensor | None = None, aux: torch.Tensor | None = None, c: torch.Tensor | None = None,
+         out: torch.Tensor | None = None, sms: int = 0) -> torch.Tensor | None:
+    """a: [M,K] (a_mn=False) or [K,M] (a_mn=True), row-major with unit inner stride; b: [N,K] or [K,N] likewise.
+    Returns D [M,N], or None if the native kernel cannot take this problem (caller falls back)."""
+    if not _native_ok(a, b):
+        return None
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, f"inner dimensions differ: {K} vs {Kb}"
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    if c is not None:
+        assert c.dtype == out.dtype and c.stride(1) == 1
+    if bias is not None and bias.dtype != out.dtype:
+        bias = bias.to(out.dtype)
+    try:
+        rc_ok = True
+        _lib.fn("ab_gemm_bf16")(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
+                                int(b_mn), _lib.dt(a), _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux),
+                                aux.stride(0) if aux is not None else 0, _lib.ptr(c), c.stride(0) if c is not None else 0, int(sms),
+                                _lib.stream_ptr(a.device))
+    except RuntimeError as e:
+        if "bad argument (-10)" in str(e):
+            rc_ok = False
+        else:
+            raise
+    if not rc_ok:
+        stats["fallback"] += 1
+        return None
+    stats["native"] += 1
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D row-major matrix (bias gradients), deterministic, fp32 accumulation."""
+    if not (x.is_cuda and _lib.available() and x.dtype in (torch.float32, torch.float16, torch.bfloat16) and x.stride(1) == 1):
+        return x.float().sum(0).to(x.dtype)
+    M, N = x.shape
+    key = x.device
+    ws = _ws.get(key)
+    if ws is None or ws.numel() < 64 * N:
+        ws = _ws[key] = torch.empty(64 * N, dtype=torch.float32, device=x.device)
+    out = torch.empty(N, dtype=x.dtype, device=x.device)
+    _lib.fn("ab_colsum")(x.data_ptr(), out.data_ptr(), ws.data_ptr(), M, N, x.stride(0), _lib.dt(x), _lib.stream_ptr(x.device))
+    return out
+
+
+# ---- the GEMMs of y = x W^T + b  (x [M,in], W [out,in]) ----------------------------------------------------------------
+def linear_fwd(x, w, bias=None, epi=None, aux=None, out_dtype=None):
+    epi = (EPI_BIAS if bias is not None else EPI_NONE) if epi is None else epi
+    y = gemm(x, w, epi=epi, bias=bias, aux=aux, out_dtype=out_dtype)
+    if y is not None:
+        return y
+    y = torch.matmul(x, w.t())
+    if bias is not None:
+        y = y + bias
+    if epi == EPI_BIAS_GELU:
+        aux.copy_(y)
+        y = torch.nn.functional.gelu(y)
+    elif epi in (EPI_BIAS_RELU, EPI_RELU):
+        y = torch.relu(y)
+    elif epi in (EPI_BIAS_SIGMOID, EPI_SIGMOID):
+        y = torch.sigmoid(y)
+    return y
+
+
+def linear_dgrad(dy, w, dgelu_aux=None):
+    """dx = dy @ W  (optionally fused with * gelu'(aux))."""
+    dx = gemm(dy, w, b_mn=True, epi=EPI_DGELU if dgelu_aux is not None else EPI_NONE, aux=dgelu_aux)
+    if dx is not None:
+        return dx
+    dx = torch.matmul(dy, w)
+    if dgelu_aux is not None:
+        a = dgelu_aux.float()
+        cdf = 0.5 * (1 + torch.erf(a * 0.7071067811865476))
+        pdf = torch.exp(-0.5 * a * a) * 0.3989422804014327
+        dx = (dx.float() * (cdf + a * pdf)).to(dy.dtype)
+    return dx
+
+
+def linear_wgrad(dy, x, accum_into: torch.Tensor | None = None, out_dtype=None):
+    """dW = dy^T @ x; with ``accum_into`` the result is ADDED to that tensor (beta = 1 main-grad accumulation)."""
+    if accum_into is not None:
+        r = gemm(dy, x, a_mn=True, b_mn=True, epi=EPI_ACCUM, c=accum_into, out=accum_into, out_dtype=accum_into.dtype)
+        if r is None:
+            accum_into.add_(torch.matmul(dy.t().to(x.dtype), x).to(accum_into.dtype))
+        return accum_into
+    dw = gemm(dy, x, a_mn=True, b_mn=True, out_dtype=out_dtype)
+    if dw is None:
+        dw = torch.matmul(dy.t(), x)
+        if out_dtype is not None:
+            dw = dw.to(out_dtype)
+    return dw

@@ -147,7 +147,7 @@ def main():
         dev_lr = lr_tensor()
         scratch = torch.zeros(1, dtype=torch.float32, device=dev)
         host_out = torch.empty(1, dtype=torch.float32).pin_memory()
-        probe = params[-1].view(-1)
+        probe = params[-1].detach().view(-1)
 
         def e2e_step(i):
             tgt = dev_lr if dev_lr is not None else scratch
