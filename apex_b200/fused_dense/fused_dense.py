@@ -1,0 +1,140 @@
+"""FusedDense / FusedDenseGeluDense on the tcgen05 GEMM (csrc/gemm_sm100.cu).
+
+Reference: apex/fused_dense/fused_dense.py:1-114 over csrc/fused_dense_cuda.cu (every FLOP a cuBLASLt call with an epilogue).
+Same autograd structure and saved tensors (FusedDenseGeluDense saves ``gelu_in`` and ``output1``); inputs may have any number
+of leading dimensions (the reference requires 2-D); the bias gradient is a deterministic column reduction.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..ops import gemm as G
+
+
+def _cast_if_autocast_enabled(*args):
+    if not torch.is_autocast_enabled():
+        return args
+    dt = torch.get_autocast_dtype("cuda")
+    return tuple(a.to(dt) if (torch.is_tensor(a) and a.is_floating_point() and a.is_cuda) else a for a in args)
+
+
+def _2d(x):
+    return x.reshape(-1, x.shape[-1]).contiguous() if (x.dim() != 2 or not x.is_contiguous()) else x
+
+
+class FusedDenseFunc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weight, bias):
+        x = _2d(input)
+        ctx.save_for_backward(x, weight)
+        ctx.in_shape = input.shape
+        y = G.linear_fwd(x, weight.contiguous(), bias)
+        return y.view(*input.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        dy = _2d(grad_output)
+        dx = G.linear_dgrad(dy, weight.contiguous()) if ctx.needs_input_grad[0] else None
+        dw = G.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        db = G.colsum(dy) if ctx.needs_input_grad[2] else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+
+
+class DenseNoBiasFunc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weight):
+        x = _2d(input)
+        ctx.save_for_backward(x, weight)
+        ctx.in_shape = input.shape
+        return G.linear_fwd(x, weight.contiguous(), None).view(*input.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        dy = _2d(grad_output)
+        dx = G.linear_dgrad(dy, weight.contiguous()) if ctx.needs_input_grad[0] else None
+        dw = G.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw
+
+
+class FusedDenseGeluDenseFunc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weight1, bias1, weight2, bias2):
+        x = _2d(input)
+        gelu_in = torch.empty(x.shape[0], weight1.shape[0], dtype=x.dtype, device=x.device)
+        output1 = G.linear_fwd(x, weight1.contiguous(), bias1, epi=G.EPI_BIAS_GELU, aux=gelu_in)   # GEMM1 + bias + GELU (+aux)
+        output2 = G.linear_fwd(output1, weight2.contiguous(), bias2)                                 # GEMM2 + bias
+        ctx.save_for_backward(x, weight1, weight2, gelu_in, output1)
+        ctx.in_shape = input.shape
+        return output2.view(*input.shape[:-1], weight2.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight1, weight2, gelu_in, output1 = ctx.saved_tensors
+        dy = _2d(grad_output)
+        dw2 = G.linear_wgrad(dy, output1)
+        db2 = G.colsum(dy)
+        d_gelu_in = G.linear_dgrad(dy, weight2.contiguous(), dgelu_aux=gelu_in)   # dgrad2 fused with gelu'
+        db1 = G.colsum(d_gelu_in)
+        dw1 = G.linear_wgrad(d_gelu_in, x)
+        dx = G.linear_dgrad(d_gelu_in, weight1.contiguous()) if ctx.needs_input_grad[0] else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw1, db1, dw2, db2
+
+
+def fused_dense_function(input, weight, bias=None):
+    if bias is None:
+        args = _cast_if_autocast_enabled(input, weight)
+        with torch.amp.autocast("cuda", enabled=False):
+            return DenseNoBiasFunc.apply(*args)
+    args = _cast_if_autocast_enabled(input, weight, bias)
+    with torch.amp.autocast("cuda", enabled=False):
+        return FusedDenseFunc.apply(*args)
+
+
+def fused_dense_gelu_dense_function(input, weight1, bias1, weight2, bias2):
+    args = _cast_if_autocast_enabled(input, weight1, bias1, weight2, bias2)
+    with torch.amp.autocast("cuda", enabled=False):
+        return FusedDenseGeluDenseFunc.apply(*args)
+
+
+class FusedDense(nn.Module):
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        if self.bias is not None:
+            bound = 1 / self.in_features ** 0.5
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, input):
+        return fused_dense_function(input, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+
+class FusedDenseGeluDense(nn.Module):
+    def __init__(self, in_features, intermediate_features, out_features, bias=True):
+        super().__init__()
+        assert bias, "DenseGeluDense module without bias is currently not supported"
+        self.in_features, self.intermediate_features, self.out_features = in_features, intermediate_features, out_features
+        self.weight1 = nn.Parameter(torch.empty(intermediate_features, in_features))
+        self.bias1 = nn.Parameter(torch.empty(intermediate_features))
+        self.weight2 = nn.Parameter(torch.empty(out_features, intermediate_features))
+        self.bias2 = nn.Parameter(torch.empty(out_features))
+        for w, b, fan in ((self.weight1, self.bias1, in_features), (self.weight2, self.bias2, intermediate_features)):
+            nn.init.kaiming_uniform_(w, a=5 ** 0.5)
+            nn.init.uniform_(b, -1 / fan ** 0.5, 1 / fan ** 0.5)
+
+    def forward(self, input):
+        return fused_dense_gelu_dense_function(input, self.weight1, self.bias1, self.weight2, self.bias2)

@@ -1,0 +1,128 @@
+"""tcgen05 GEMM + fused epilogues vs fp32 torch matmul (reference test: apex/contrib/test/fused_dense/test_fused_dense.py, M=1536,
+K=1024, N=3072, atol=rtol=1e-3 on its scale) and the modules built on it."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 256, 64), (1536, 3072, 1024), (200, 328, 136), (8, 8, 8), (1000, 1000, 1000), (4096, 512, 4096), (130, 4104, 72)]
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_layouts(cuda_dev, M, N, K, dtype, a_mn, b_mn):
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=cuda_dev).to(dtype)
+    B = torch.randn(N, K, device=cuda_dev).to(dtype)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    d = G.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert d is not None, "native GEMM refused an aligned problem"
+    ref = A.float() @ B.float().t()
+    assert _rel(d, ref) < 2e-3, _rel(d, ref)
+    assert G.stats["native"] > 0
+
+
+def test_gemm_epilogues(cuda_dev):
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    M, N, K = 520, 776, 264
+    x = torch.randn(M, K, device=cuda_dev, dtype=torch.bfloat16)
+    w = torch.randn(N, K, device=cuda_dev, dtype=torch.bfloat16) * 0.05
+    bias = torch.randn(N, device=cuda_dev, dtype=torch.bfloat16)
+    ref = x.float() @ w.float().t() + bias.float()
+    y = G.gemm(x, w, epi=G.EPI_BIAS, bias=bias)
+    assert _rel(y, ref) < 1e-2
+    aux = torch.empty(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    h = G.gemm(x, w, epi=G.EPI_BIAS_GELU, bias=bias, aux=aux)
+    assert _rel(aux, ref) < 1e-2 and _rel(h, F.gelu(aux.float())) < 1e-2
+    r = G.gemm(x, w, epi=G.EPI_BIAS_RELU, bias=bias)
+    assert _rel(r, torch.relu(ref)) < 1e-2
+    s = G.gemm(x, w, epi=G.EPI_BIAS_SIGMOID, bias=bias)
+    assert _rel(s, torch.sigmoid(ref)) < 1e-2
+    # dgelu: (dy @ W2) * gelu'(aux)
+    dy = torch.randn(M, 192, device=cuda_dev, dtype=torch.bfloat16)
+    w2 = torch.randn(192, N, device=cuda_dev, dtype=torch.bfloat16) * 0.05
+    a = aux.float().requires_grad_(True)
+    (F.gelu(a) * (dy.float() @ w2.float())).sum().backward()
+    dg = G.gemm(dy, w2, b_mn=True, epi=G.EPI_DGELU, aux=aux)
+    assert _rel(dg, a.grad) < 1e-2
+    # beta=1 accumulate into fp32 and bf16 main grads
+    main = torch.randn(N, K, device=cuda_dev)
+    dyy = torch.randn(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    exp = main + dyy.float().t() @ x.float()
+    from apex_b200.transformer.functional import wgrad_gemm_accum_fp16, wgrad_gemm_accum_fp32
+    wgrad_gemm_accum_fp32(x, dyy, main)
+    assert _rel(main, exp) < 2e-3
+    main16 = torch.randn(N, K, device=cuda_dev, dtype=torch.bfloat16)
+    exp16 = main16.float() + dyy.float().t() @ x.float()
+    wgrad_gemm_accum_fp16(x.view(4, 130, K), dyy.view(4, 130, N), main16)
+    assert _rel(main16, exp16) < 1e-2
+    cs = G.colsum(dyy)
+    assert _rel(cs, dyy.float().sum(0)) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_fused_dense_modules(cuda_dev, dtype):
+    from apex_b200.fused_dense import FusedDense, FusedDenseGeluDense
+    torch.manual_seed(0)
+    tol = 2e-2 if dtype != torch.float32 else 1e-4
+    fd = FusedDense(1024, 3072).to(cuda_dev, dtype)
+    ref = torch.nn.Linear(1024, 3072).to(cuda_dev)
+    with torch.no_grad():
+        ref.weight.copy_(fd.weight.float())
+        ref.bias.copy_(fd.bias.float())
+    x = torch.randn(3, 512, 1024, device=cuda_dev, dtype=dtype, requires_grad=True)
+    xr = x.detach().float().requires_grad_(True)
+    dy = torch.randn(3, 512, 3072, device=cuda_dev, dtype=dtype)
+    fd(x).backward(dy)
+    ref(xr).backward(dy.float())
+    assert _rel(x.grad, xr.grad) < tol and _rel(fd.weight.grad, ref.weight.grad) < tol and _rel(fd.bias.grad, ref.bias.grad) < tol
+    g = FusedDenseGeluDense(1024, 4096, 1024).to(cuda_dev, dtype)
+    x2 = torch.randn(1536, 1024, device=cuda_dev, dtype=dtype, requires_grad=True)
+    x2r = x2.detach().float().requires_grad_(True)
+    ps = {n: p.detach().float().requires_grad_(True) for n, p in g.named_parameters()}
+    out_ref = F.linear(F.gelu(F.linear(x2r, ps["weight1"], ps["bias1"])), ps["weight2"], ps["bias2"])
+    out = g(x2)
+    assert _rel(out, out_ref) < tol
+    dy2 = torch.randn_like(out)
+    out.backward(dy2)
+    out_ref.backward(dy2.float())
+    assert _rel(x2.grad, x2r.grad) < tol
+    for n, p in g.named_parameters():
+        assert _rel(p.grad, ps[n].grad) < tol, n
+
+
+@pytest.mark.parametrize("activation", ["none", "relu", "sigmoid"])
+def test_mlp_module(cuda_dev, activation):
+    from apex_b200.mlp import MLP
+    torch.manual_seed(0)
+    sizes = [480, 1024, 1024, 512, 256, 8]
+    m = MLP(sizes, activation=activation).to(cuda_dev, torch.bfloat16)
+    layers = []
+    for i in range(len(sizes) - 1):
+        lin = torch.nn.Linear(sizes[i], sizes[i + 1]).to(cuda_dev)
+        with torch.no_grad():
+            lin.weight.copy_(m.weights[i].float())
+            lin.bias.copy_(m.biases[i].float())
+        layers.append(lin)
+        if activation == "relu":
+            layers.append(torch.nn.ReLU())
+        elif activation == "sigmoid":
+            layers.append(torch.nn.Sigmoid())
+    ref = torch.nn.Sequential(*layers)
+    x = torch.randn(1024, 480, device=cuda_dev, dtype=torch.bfloat16, requires_grad=True)
+    xr = x.detach().float().requires_grad_(True)
+    y, yr = m(x), ref(xr)
+    assert _rel(y, yr) < 3e-2
+    y.float().mean().backward()
+    yr.mean().backward()
+    assert _rel(x.grad, xr.grad) < 5e-2
+    assert _rel(m.weights[0].grad, layers[0].weight.grad) < 5e-2
