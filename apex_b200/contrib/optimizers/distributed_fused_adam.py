@@ -181,6 +181,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._step_supports_amp_scaling = True
         self._inited = False
         self._sync_enabled = True
+        self.last_nvls = False
         self.kernel_launches = 0  # number of csrc/dist_adam.cu launches so far (bench.py reports it)
         self._last_grad_norm = None
         if capturable:
@@ -308,8 +309,13 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             pad = self._pad
             epoch = pad.next_epoch()
             g_arr, p_arr, pads = seg.symm_g.peer_ptr_array(), seg.symm_p.peer_ptr_array(), pad.ptrs
-            nvls = int(seg.symm_g.has_multicast and seg.symm_p.has_multicast)
+            # NVSwitch multicast moves 16 + 16/D GB per direction per step, plain P2P (D-1)/D * 32 GB: NVLS wins from D = 4 up
+            import os as _os
+
+            pol = _os.environ.get("APEX_B200_DIST_NVLS", "auto")
+            nvls = int(seg.symm_g.has_multicast and seg.symm_p.has_multicast and (pol == "1" or (pol == "auto" and D >= 4)))
             mcg, mcp = seg.symm_g.mc_ptr, seg.symm_p.mc_ptr
+            self.last_nvls = bool(nvls)
             rank, world = seg.rank, D
         else:
             epoch, nvls, mcg, mcp, rank, world = 0, 0, 0, 0, 0, 1

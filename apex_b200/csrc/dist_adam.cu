@@ -58,10 +58,37 @@ template <typename T> __device__ __forceinline__ void unpack8(const uint4* raw, 
 
 __device__ __forceinline__ float lerp_f(float t, float x, float y) { return fmaf(t, y, fmaf(-t, x, x)); }
 
-template <typename TG, typename TP, int MODE, bool NVLS>
+// One 8-element vector of the update: Adam on fp32 (p, m, v), returns the new parameter values in p.
+struct AdamScalars { float gs, lr, bc1, bc2, beta1, beta2, eps, decay; int mode; };
+
+__device__ __forceinline__ void adam8(float (&p)[8], float (&m)[8], float (&v)[8], const float (&g)[8], const AdamScalars& h) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    float sg = g[i] * h.gs;
+    if (h.mode == 0) sg += h.decay * p[i];
+    m[i] = lerp_f(h.beta1, sg, m[i]);
+    v[i] = lerp_f(h.beta2, sg * sg, v[i]);
+    float upd = (m[i] / h.bc1) / (sqrtf(v[i] / h.bc2) + h.eps);
+    if (h.mode != 0) upd += h.decay * p[i];
+    p[i] -= h.lr * upd;
+  }
+}
+__device__ __forceinline__ void ld8(const float* src, float (&d)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(d[0], d[1], d[2], d[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(d[4], d[5], d[6], d[7]);
+}
+
+// DP: compile-time bound on the number of peers looped over (1, 2, 4, 8); U: chunks whose remote gradient loads are issued
+// before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
+template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
 __global__ void __launch_bounds__(kDThreads, 2) dist_step_kernel(DistArgs a) {
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
   constexpr int PV = sizeof(TP) * 8 / 16;
+  constexpr int NP = NVLS ? 1 : DP;        // gradient sources read per element
   __shared__ float red[40];
   __shared__ int s_last;
   const int tid = threadIdx.x;
@@ -74,108 +101,106 @@ __global__ void __launch_bounds__(kDThreads, 2) dist_step_kernel(DistArgs a) {
   }
 
   const bool skip = (MODE != MODE_RS) && a.noop != nullptr && *a.noop != 0;
-  float lr = a.lr, bc1 = a.bc1, bc2 = a.bc2;
+  AdamScalars h{1.f, a.lr, a.bc1, a.bc2, a.beta1, a.beta2, a.eps, a.decay, a.mode};
   if (MODE != MODE_RS) {
-    if (a.lr_ptr) lr = *a.lr_ptr;
+    if (a.grad_scale) h.gs = *a.grad_scale;
+    if (a.lr_ptr) h.lr = *a.lr_ptr;
     if (a.step_ptr && a.bias_correction) {
       const float sf = (float)(*a.step_ptr);
-      bc1 = 1.f - powf(a.beta1, sf);
-      bc2 = 1.f - powf(a.beta2, sf);
+      h.bc1 = 1.f - powf(a.beta1, sf);
+      h.bc2 = 1.f - powf(a.beta2, sf);
     }
   }
-  const float gs = (MODE != MODE_RS && a.grad_scale) ? *a.grad_scale : 1.f;
   const int cpb = a.shard_elems / kDChunk;  // chunks per bucket shard
   const long long c0 = (long long)a.bucket_begin * cpb, c1 = (long long)a.bucket_end * cpb;
   float nsq = 0.f;
 
   if (!skip) {
-    for (long long c = c0 + blockIdx.x; c < c1; c += gridDim.x) {
-      const long long b = c / cpb;
-      const int oc = (int)(c - b * cpb);
-      const long long local = c * kDChunk + tid * 8;
-      const long long flat = b * a.bucket_elems + (long long)a.lay_rank * a.shard_elems + (long long)oc * kDChunk + tid * 8;
-      float g[8];
+    for (long long cb = c0 + blockIdx.x; cb < c1; cb += (long long)gridDim.x * U) {
+      long long local[U], flat[U];
+      bool on[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long c = cb + (long long)u * gridDim.x;
+        on[u] = c < c1;
+        const long long b = c / cpb;
+        const int oc = (int)(c - b * cpb);
+        local[u] = c * kDChunk + tid * 8;
+        flat[u] = b * a.bucket_elems + (long long)a.lay_rank * a.shard_elems + (long long)oc * kDChunk + tid * 8;
+      }
+      // ---- phase 1: every gradient load of the U chunks is in flight before the first use
+      uint4 raw[U][NP][GV];
+      float red_in[U][8];
       if (MODE == MODE_ADAM) {
-        const float4 r0 = *reinterpret_cast<const float4*>(a.reduced + local);
-        const float4 r1 = *reinterpret_cast<const float4*>(a.reduced + local + 4);
-        g[0] = r0.x; g[1] = r0.y; g[2] = r0.z; g[3] = r0.w; g[4] = r1.x; g[5] = r1.y; g[6] = r1.z; g[7] = r1.w;
+#pragma unroll
+        for (int u = 0; u < U; u++) if (on[u]) ld8(a.reduced + local[u], red_in[u]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) g[i] = 0.f;
-        if (NVLS) {
-          uint4 raw[GV];
-#pragma unroll
-          for (int q = 0; q < GV; q++)
-            raw[q] = multimem_ld_reduce16<TG>(reinterpret_cast<const char*>(a.mc_grads) + flat * sizeof(TG) + q * 16);
-          unpack8<TG>(raw, g);
-        } else {
-          uint4 raw[kMaxPeers][GV];
-#pragma unroll
-          for (int p = 0; p < kMaxPeers; p++) {
-            if (p < D) {
+        for (int u = 0; u < U; u++) {
+          if (on[u]) {
+            if (NVLS) {
 #pragma unroll
               for (int q = 0; q < GV; q++)
-                raw[p][q] = ld_peer16(reinterpret_cast<const char*>(a.grads.p[p]) + flat * sizeof(TG) + q * 16);
+                raw[u][0][q] = multimem_ld_reduce16<TG>(reinterpret_cast<const char*>(a.mc_grads) + flat[u] * sizeof(TG) + q * 16);
+            } else {
+#pragma unroll
+              for (int p = 0; p < DP; p++) {
+                if (p < D) {
+#pragma unroll
+                  for (int q = 0; q < GV; q++)
+                    raw[u][p][q] = ld_peer16(reinterpret_cast<const char*>(a.grads.p[p]) + flat[u] * sizeof(TG) + q * 16);
+                }
+              }
             }
           }
+        }
+      }
+      // ---- phase 2: per chunk: reduce, (Adam), store / push
 #pragma unroll
-          for (int p = 0; p < kMaxPeers; p++) {  // fixed summation order => bitwise reproducible
-            if (p < D) {
+      for (int u = 0; u < U; u++) {
+        if (!on[u]) continue;
+        float g[8];
+        if (MODE == MODE_ADAM) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) g[i] = red_in[u][i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) g[i] = 0.f;
+#pragma unroll
+          for (int p = 0; p < NP; p++) {  // fixed summation order => bitwise reproducible
+            if (NVLS || p < D) {
               float f[8];
-              unpack8<TG>(raw[p], f);
+              unpack8<TG>(raw[u][p], f);
 #pragma unroll
               for (int i = 0; i < 8; i++) g[i] += f[i];
             }
           }
-        }
 #pragma unroll
-        for (int i = 0; i < 8; i++) { g[i] *= a.pre_scale; nsq += g[i] * g[i]; }
-      }
-      if (MODE == MODE_RS) {
-        *reinterpret_cast<float4*>(a.reduced + local) = make_float4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<float4*>(a.reduced + local + 4) = make_float4(g[4], g[5], g[6], g[7]);
-      } else {
-        float p[8], m[8], v[8];
-        {
-          const float4 x0 = *reinterpret_cast<const float4*>(a.p + local), x1 = *reinterpret_cast<const float4*>(a.p + local + 4);
-          const float4 y0 = *reinterpret_cast<const float4*>(a.m + local), y1 = *reinterpret_cast<const float4*>(a.m + local + 4);
-          const float4 z0 = *reinterpret_cast<const float4*>(a.v + local), z1 = *reinterpret_cast<const float4*>(a.v + local + 4);
-          p[0] = x0.x; p[1] = x0.y; p[2] = x0.z; p[3] = x0.w; p[4] = x1.x; p[5] = x1.y; p[6] = x1.z; p[7] = x1.w;
-          m[0] = y0.x; m[1] = y0.y; m[2] = y0.z; m[3] = y0.w; m[4] = y1.x; m[5] = y1.y; m[6] = y1.z; m[7] = y1.w;
-          v[0] = z0.x; v[1] = z0.y; v[2] = z0.z; v[3] = z0.w; v[4] = z1.x; v[5] = z1.y; v[6] = z1.z; v[7] = z1.w;
+          for (int i = 0; i < 8; i++) { g[i] *= a.pre_scale; nsq += g[i] * g[i]; }
         }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          float sg = g[i] * gs;
-          if (a.mode == 0) sg += a.decay * p[i];
-          m[i] = lerp_f(a.beta1, sg, m[i]);
-          v[i] = lerp_f(a.beta2, sg * sg, v[i]);
-          float upd = (m[i] / bc1) / (sqrtf(v[i] / bc2) + a.eps);
-          if (a.mode != 0) upd += a.decay * p[i];
-          p[i] -= lr * upd;
-        }
-        *reinterpret_cast<float4*>(a.p + local) = make_float4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<float4*>(a.p + local + 4) = make_float4(p[4], p[5], p[6], p[7]);
-        *reinterpret_cast<float4*>(a.m + local) = make_float4(m[0], m[1], m[2], m[3]);
-        *reinterpret_cast<float4*>(a.m + local + 4) = make_float4(m[4], m[5], m[6], m[7]);
-        *reinterpret_cast<float4*>(a.v + local) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(a.v + local + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        uint4 out[PV];
-        {
-          TP* e = reinterpret_cast<TP*>(out);
-#pragma unroll
-          for (int i = 0; i < 8; i++) e[i] = from_f<TP>(p[i]);
-        }
-        if (NVLS) {
-#pragma unroll
-          for (int q = 0; q < PV; q++) multimem_st16(reinterpret_cast<char*>(a.mc_params) + flat * sizeof(TP) + q * 16, out[q]);
+        if (MODE == MODE_RS) {
+          st8(a.reduced + local[u], g);
         } else {
+          float p[8], m[8], v[8];
+          ld8(a.p + local[u], p); ld8(a.m + local[u], m); ld8(a.v + local[u], v);
+          adam8(p, m, v, g, h);
+          st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v);
+          uint4 out[PV];
+          {
+            TP* e = reinterpret_cast<TP*>(out);
 #pragma unroll
-          for (int p2 = 0; p2 < kMaxPeers; p2++) {
-            if (p2 < D) {
-              const int dst = (rank + p2) % D;  // stagger targets so the D ranks do not all hit the same peer at once
+            for (int i = 0; i < 8; i++) e[i] = from_f<TP>(p[i]);
+          }
+          if (NVLS) {
 #pragma unroll
-              for (int q = 0; q < PV; q++) st_peer16(reinterpret_cast<char*>(a.params.p[dst]) + flat * sizeof(TP) + q * 16, out[q]);
+            for (int q = 0; q < PV; q++) multimem_st16(reinterpret_cast<char*>(a.mc_params) + flat[u] * sizeof(TP) + q * 16, out[q]);
+          } else {
+#pragma unroll
+            for (int p2 = 0; p2 < DP; p2++) {
+              if (p2 < D) {
+#pragma unroll
+                for (int q = 0; q < PV; q++) st_peer16(reinterpret_cast<char*>(a.params.p[p2]) + flat[u] * sizeof(TP) + q * 16, out[q]);
+              }
             }
           }
         }
@@ -228,14 +253,25 @@ __global__ void __launch_bounds__(kDThreads, 2) dist_step_kernel(DistArgs a) {
   if (tid == 0) *a.done_ctr = 0u;
 }
 
-template <typename TG, typename TP>
-int dist_launch(const DistArgs& a, int mode, int nvls, int grid, cudaStream_t st) {
-#define DGO(M, N) dist_step_kernel<TG, TP, M, N><<<grid, kDThreads, 0, st>>>(a)
-  if (mode == MODE_FUSED) { if (nvls) DGO(MODE_FUSED, true); else DGO(MODE_FUSED, false); }
-  else if (mode == MODE_RS) { if (nvls) DGO(MODE_RS, true); else DGO(MODE_RS, false); }
-  else { if (nvls) DGO(MODE_ADAM, true); else DGO(MODE_ADAM, false); }
+template <typename TG, typename TP, int MODE>
+int dist_launch_mode(const DistArgs& a, int nvls, int grid, cudaStream_t st) {
+  const int D = a.sig.world;
+#define DGO(N, DPV, UV) dist_step_kernel<TG, TP, MODE, N, DPV, UV><<<grid, kDThreads, 0, st>>>(a)
+  if (nvls) DGO(true, 1, 4);
+  else if (D <= 1) DGO(false, 1, 2);
+  else if (D == 2) DGO(false, 2, 4);
+  else if (D <= 4) DGO(false, 4, 2);
+  else DGO(false, 8, 2);
+#undef DGO
   AB_CHECK_LAUNCH();
   return 0;
+}
+
+template <typename TG, typename TP>
+int dist_launch(const DistArgs& a, int mode, int nvls, int grid, cudaStream_t st) {
+  if (mode == MODE_FUSED) return dist_launch_mode<TG, TP, MODE_FUSED>(a, nvls, grid, st);
+  if (mode == MODE_RS) return dist_launch_mode<TG, TP, MODE_RS>(a, nvls, grid, st);
+  return dist_launch_mode<TG, TP, MODE_ADAM>(a, nvls, grid, st);
 }
 
 }  // namespace ab
@@ -282,10 +318,7 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
   if (dt_g == kBF16 && dt_p == kBF16) DPAIR(bf16, bf16);
   if (dt_g == kF16 && dt_p == kF16) DPAIR(f16, f16);
   if (dt_g == kF32 && dt_p == kF32) DPAIR(float, float);
-  if (dt_g == kBF16 && dt_p == kF32) DPAIR(bf16, float);
-  if (dt_g == kF16 && dt_p == kF32) DPAIR(f16, float);
   if (dt_g == kF32 && dt_p == kBF16) DPAIR(float, bf16);
-  if (dt_g == kF32 && dt_p == kF16) DPAIR(float, f16);
   return -1;
 }
 

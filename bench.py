@@ -189,8 +189,7 @@ def main():
             "config": {"model": args.config, "n_params": n_params, "n_tensors": len(params), "parallelism": f"zero2-dp{D}",
                        "global_batch": None, "seq_len": None, "l2": "working set >> 126 MB L2 (no flush needed)",
                        "fused_collectives": bool(getattr(opt, "fused_collectives", False)),
-                       "nvls": bool(getattr(opt, "_segments", None) and getattr(opt._segments[0], "symm_g", None) is not None
-                                    and opt._segments[0].symm_g.has_multicast) if args.impl == "ours" else None,
+                       "nvls": bool(getattr(opt, "last_nvls", False)) if args.impl == "ours" else None,
                        "capturable": capturable},
             "clocks": {"sm_mhz": cs["sm_mhz"], "sm_max_mhz": cs["sm_max_mhz"], "reasons": cs["reasons"]},
             "gpu_launches": launches if args.impl == "ours" else None,
