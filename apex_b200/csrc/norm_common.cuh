@@ -31,6 +31,23 @@ struct RowReducer {
     bank ^= 1;
     return t;
   }
+  __device__ __forceinline__ float maxv(float v) {
+    if (tpr <= 32) {
+      for (int o = tpr >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    }
+    v = warp_max(v);
+    const int wpr = tpr >> 5;
+    const int w = threadIdx.x >> 5;
+    float* b = smem + bank * 32;
+    if ((threadIdx.x & 31) == 0) b[w] = v;
+    __syncthreads();
+    float t = -INFINITY;
+    const int w0 = rg * wpr;
+    for (int i = 0; i < wpr; i++) t = fmaxf(t, b[w0 + i]);
+    bank ^= 1;
+    return t;
+  }
 };
 
 template <typename T> __device__ __forceinline__ void unpack16(const uint4& raw, float (&r)[16 / sizeof(T)]) {
