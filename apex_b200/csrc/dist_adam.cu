@@ -257,7 +257,7 @@ template <typename TG, typename TP, int MODE>
 int dist_launch_mode(const DistArgs& a, int nvls, int grid, cudaStream_t st) {
   const int D = a.sig.world;
 #define DGO(N, DPV, UV) dist_step_kernel<TG, TP, MODE, N, DPV, UV><<<grid, kDThreads, 0, st>>>(a)
-  if (nvls) DGO(true, 1, 4);
+  if (nvls) DGO(true, 1, 8);
   else if (D <= 1) DGO(false, 1, 2);
   else if (D == 2) DGO(false, 2, 4);
   else if (D <= 4) DGO(false, 4, 2);

@@ -1,23 +1,22 @@
 // SyncBatchNorm for B200: ONE persistent kernel per direction that does local statistics, the cross-GPU reduction (P2P stores
 // into every peer's exchange buffer over NVLink + epoch flags — no NCCL, no extra launches) and the normalisation.
 //
-// Forward  phases: [1] per-(channel, split) partial (mean, M2, n)  -> grid barrier ->
-//                  [2] Chan-merge of the splits, publish (mean, M2, n) to every rank, merge the D ranks in rank order,
-//                      mean / inv_std / running stats                                   -> grid barrier ->
-//                  [4] y = (x - mean) * inv_std * w + b (+ z) (ReLU)
-// Backward phases: [1] partial (sum dy, sum dy*(x-mean))            -> grid barrier ->
-//                  [2] merge splits, grad_w / grad_b, publish the two sums, add the D ranks   -> grid barrier ->
-//                  [4] dx = (dy - sum_dy/N - (x-mean) * inv_std^2 * sum_dy_xmu/N) * w * inv_std   (dy masked by ReLU if fused)
+// Forward : [1] per-(unit, split) partial (mean, M2, n); the LAST split of a unit to finish Chan-merges the unit's channels and
+//               publishes (mean, M2, n) into every rank's exchange buffer                         -> grid barrier ->
+//           [2] epoch signal / wait across ranks; every CTA merges the D contributions of a slice of channels in rank order:
+//               mean, inv_std, running stats                                                       -> grid barrier ->
+//           [4] y = (x - mean) * inv_std * w + b (+ z) (ReLU)
+// Backward: same skeleton with (sum dy, sum dy*(x-mean)); grad_w / grad_b from the local sums;
+//           dx = (dy - sum_dy/N - (x-mean) * inv_std^2 * sum_dy_xmu/N) * w * inv_std  (dy masked by the ReLU of the fused block).
 // A `phases` bitmask selects sub-sets so the ten standalone entry points of the reference extension
 // (csrc/syncbn.cpp:71-89: welford_mean_var, welford_parallel, batchnorm_forward, reduce_bn, batchnorm_backward and the
 // _c_last variants, kernels csrc/welford.cu:217-788) are the same code. NCHW and channels-last both run coalesced,
-// 16-byte vectorised paths. Uneven per-rank batch sizes are supported: counts travel with the statistics.
+// 16-byte vectorised, 4x unrolled. Uneven per-rank batch sizes are supported: counts travel with the statistics.
 #include "symm_device.cuh"
 
 namespace ab {
 
 constexpr int kBnThreads = 256;
-constexpr int kBnMaxSplits = 64;
 
 struct BnArgs {
   const void* x; const void* dy; const void* z; void* out; void* dz;  // out: y (fwd) or dx (bwd); dz: grad of residual (bwd)
@@ -29,6 +28,8 @@ struct BnArgs {
   float* grad_w; float* grad_b;     // [C]  bwd outputs
   float* sum_dy; float* sum_dy_xmu; // [C]  bwd: global sums (phase 2 out / phase 4 in)
   float* partial;                   // [C][splits][3] scratch
+  float* merged;                    // [C][3] this rank's merged statistics
+  unsigned int* unit_ctr;           // [units] arrival counters (zero on entry, left zero on exit)
   float* count_total;               // [1]  total element count over all ranks
   unsigned int* grid_bar;           // [2]  {arrivals, generation}
   int splits, phases, fuse_relu, is_bwd;
@@ -77,29 +78,46 @@ __device__ __forceinline__ Wf wf_shfl_xor(const Wf& w, int o) {
 template <typename T> struct VecOf { static constexpr int V = 16 / sizeof(T); };
 
 // relu-masked incoming gradient for the fused (bn + add + relu) block
-template <typename T>
 __device__ __forceinline__ float masked_grad(const BnArgs& a, float g, float xv, float zv, int c, float mu, float is) {
   if (!a.fuse_relu) return g;
-  float yv = (xv - mu) * is * (a.weight ? a.weight[c] : 1.f) + (a.bias ? a.bias[c] : 0.f) + zv;
+  const float yv = (xv - mu) * is * (a.weight ? a.weight[c] : 1.f) + (a.bias ? a.bias[c] : 0.f) + zv;
   return yv > 0.f ? g : 0.f;
+}
+
+// this rank's merged per-channel value -> local `merged` and every peer's exchange slot; bwd also emits grad_w / grad_b
+__device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float v1, float v2) {
+  if (a.is_bwd) {
+    if (a.grad_w) a.grad_w[c] = v1 * a.invstd[c];
+    if (a.grad_b) a.grad_b[c] = v0;
+  }
+  float* m = a.merged + (size_t)c * 3;
+  m[0] = v0; m[1] = v1; m[2] = v2;
+  const int D = a.sig.world;
+  if (D > 1) {
+    for (int r = 0; r < D; r++) {
+      float* dst = reinterpret_cast<float*>(a.xchg.p[r]) + a.xchg_off + ((size_t)a.sig.rank * a.C + c) * 3;
+      st_relaxed_sys_f32(dst, v0); st_relaxed_sys_f32(dst + 1, v1); st_relaxed_sys_f32(dst + 2, v2);
+    }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
   constexpr int V = VecOf<T>::V;
   __shared__ float sm[3][kBnThreads + 8];
+  __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const T* x = reinterpret_cast<const T*>(a.x);
-  const T* dy = reinterpret_cast<const T*>(a.dy);
-  const T* z = reinterpret_cast<const T*>(a.z);
+  const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
+  const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+  const T* __restrict__ z = reinterpret_cast<const T*>(a.z);
   const long long per_c = (long long)a.N * a.HW;
   const int S = a.splits;
   const int C = a.C, HW = a.HW;
 
-  // ------------------------------------------------------------------ phase 1: partial statistics
+  // ------------------------------------------------------------------ phase 1: partial statistics (+ per-unit merge/publish)
   if (a.phases & 1) {
     if (!a.nhwc) {
-      // NCHW: item = (channel, split); the split is a range of the channel's N*HW elements; threads run along HW (coalesced)
+      // NCHW: unit = channel; a split is a range of the channel's N*HW elements; threads run along HW (coalesced)
       const bool vec = (HW % V == 0) && aligned16(x) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z));
       const int items = C * S;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -111,6 +129,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
           if (e1 > e0) { const long long n0 = e0 / HW; shift = to_f<T>(x[(n0 * C + c) * (long long)HW + (e0 - n0 * HW)]); }
         } else { mu = a.mean[c]; is = a.invstd[c]; }
         const int step = vec ? V : 1;
+#pragma unroll 4
         for (long long e = e0 + (long long)tid * step; e < e1; e += (long long)kBnThreads * step) {
           const long long n = e / HW;
           const long long off = (n * C + c) * (long long)HW + (e - n * HW);
@@ -129,13 +148,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
             if (j < step) {
               if (!a.is_bwd) { const float d = xv[j] - shift; acc0 += d; acc1 += d * d; cnt += 1.f; }
               else {
-                const float g = masked_grad<T>(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, c, mu, is);
+                const float g = masked_grad(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, c, mu, is);
                 acc0 += g; acc1 += g * (xv[j] - mu);
               }
             }
           }
         }
-        // block reduction
+        // block reduction -> partial[c][s]
+        float* pp = a.partial + ((size_t)c * S + s) * 3;
         if (!a.is_bwd) {
           Wf w = wf_from_sums(shift, acc0, acc1, cnt);
 #pragma unroll
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
             Wf t = lane < kBnThreads / 32 ? Wf{sm[0][lane], sm[1][lane], sm[2][lane]} : Wf{0.f, 0.f, 0.f};
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t = wf_merge(t, wf_shfl_xor(t, o));
-            if (lane == 0) { float* p = a.partial + ((size_t)c * S + s) * 3; p[0] = t.mean; p[1] = t.m2; p[2] = t.n; }
+            if (lane == 0) { pp[0] = t.mean; pp[1] = t.m2; pp[2] = t.n; }
           }
         } else {
           acc0 = warp_sum(acc0); acc1 = warp_sum(acc1);
@@ -157,12 +177,35 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
           if (wid == 0) {
             float t0 = lane < kBnThreads / 32 ? sm[0][lane] : 0.f, t1 = lane < kBnThreads / 32 ? sm[1][lane] : 0.f;
             t0 = warp_sum(t0); t1 = warp_sum(t1);
-            if (lane == 0) { float* p = a.partial + ((size_t)c * S + s) * 3; p[0] = t0; p[1] = t1; p[2] = 0.f; }
+            if (lane == 0) { pp[0] = t0; pp[1] = t1; pp[2] = 0.f; }
+          }
+        }
+        // last split of this channel merges and publishes
+        __syncthreads();
+        if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.unit_ctr + c, 1u) == (unsigned)(S - 1)); }
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          if (wid == 0) {
+            const float* base = a.partial + (size_t)c * S * 3;
+            if (!a.is_bwd) {
+              Wf w{0.f, 0.f, 0.f};
+              for (int q = lane; q < S; q += 32) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) w = wf_merge(w, wf_shfl_xor(w, o));
+              if (lane == 0) publish(a, c, w.mean, w.m2, w.n);
+            } else {
+              float s0 = 0.f, s1 = 0.f;
+              for (int q = lane; q < S; q += 32) { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
+              s0 = warp_sum(s0); s1 = warp_sum(s1);
+              if (lane == 0) publish(a, c, s0, s1, (float)per_c);
+            }
+            if (lane == 0) { a.unit_ctr[c] = 0u; __threadfence_system(); }
           }
         }
       }
     } else {
-      // NHWC: item = (channel tile, row split); thread (cx, ry): cx owns V (or 1) adjacent channels, ry strides over rows
+      // NHWC: unit = channel tile; thread (cx, ry): cx owns V (or 1) adjacent channels, ry strides over rows (4x unrolled)
       const bool vec = (C % V == 0) && aligned16(x) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z));
       const int cw = vec ? V : 1;            // channels per thread
       const int lanes_c = vec ? 8 : 32;      // threads along channels
@@ -187,6 +230,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
               else { mu[j] = a.mean[cbase + j]; is[j] = a.invstd[cbase + j]; }
             }
           }
+#pragma unroll 4
           for (long long r = r0 + ry; r < r1; r += lanes_r) {
             const long long off = r * C + cbase;
             float xv[V], gv[V], zv[V];
@@ -205,7 +249,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
               if (j < cw) {
                 if (!a.is_bwd) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] += d * d; }
                 else {
-                  const float g = masked_grad<T>(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, cbase + j, mu[j], is[j]);
+                  const float g = masked_grad(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, cbase + j, mu[j], is[j]);
                   acc0[j] += g; acc1[j] += g * (xv[j] - mu[j]);
                 }
               }
@@ -236,74 +280,80 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
             }
           }
         }
+        // last split of this channel tile merges and publishes its channels: thread (ch = tid % tile_c, grp = tid / tile_c)
+        __syncthreads();
+        if (tid == 0) { __threadfence(); s_last = (atomicAdd(a.unit_ctr + ct, 1u) == (unsigned)(S - 1)); }
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          const int ch = tid % tile_c, grp = tid / tile_c, ngrp = kBnThreads / tile_c;
+          const int c = ct * tile_c + ch;
+          Wf w{0.f, 0.f, 0.f};
+          float s0 = 0.f, s1 = 0.f;
+          if (c < C) {
+            const float* base = a.partial + (size_t)c * S * 3;
+            for (int q = grp; q < S; q += ngrp) {
+              if (!a.is_bwd) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
+              else { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
+            }
+          }
+          if (!a.is_bwd) { sm[0][tid] = w.mean; sm[1][tid] = w.m2; sm[2][tid] = w.n; } else { sm[0][tid] = s0; sm[1][tid] = s1; }
+          __syncthreads();
+          if (grp == 0 && c < C) {
+            if (!a.is_bwd) {
+              Wf t{0.f, 0.f, 0.f};
+              for (int q = 0; q < ngrp; q++) t = wf_merge(t, Wf{sm[0][q * tile_c + ch], sm[1][q * tile_c + ch], sm[2][q * tile_c + ch]});
+              publish(a, c, t.mean, t.m2, t.n);
+            } else {
+              float t0 = 0.f, t1 = 0.f;
+              for (int q = 0; q < ngrp; q++) { t0 += sm[0][q * tile_c + ch]; t1 += sm[1][q * tile_c + ch]; }
+              publish(a, c, t0, t1, (float)per_c);
+            }
+            __threadfence_system();
+          }
+          if (tid == 0) a.unit_ctr[ct] = 0u;
+        }
       }
     }
     if (a.phases & 6) grid_barrier(a.grid_bar, gridDim.x);
   }
 
-  // ------------------------------------------------------------------ phase 2: merge splits, cross-GPU exchange, finalize
+  // ------------------------------------------------------------------ phase 2: cross-GPU exchange, finalize (all CTAs)
   if (a.phases & 2) {
     const int D = a.sig.world, rank = a.sig.rank;
-    if (blockIdx.x == 0) {
-      for (int c = tid; c < C; c += kBnThreads) {
-        float v0, v1, v2;
-        if (!a.is_bwd) {
-          Wf w{0.f, 0.f, 0.f};
-          for (int s = 0; s < S; s++) { const float* p = a.partial + ((size_t)c * S + s) * 3; w = wf_merge(w, Wf{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)}); }
-          v0 = w.mean; v1 = w.m2; v2 = w.n;
-        } else {
-          float s0 = 0.f, s1 = 0.f;
-          for (int s = 0; s < S; s++) { const float* p = a.partial + ((size_t)c * S + s) * 3; s0 += __ldcg(p); s1 += __ldcg(p + 1); }
-          v0 = s0; v1 = s1; v2 = (float)per_c;
-          if (a.grad_w) a.grad_w[c] = s1 * a.invstd[c];
-          if (a.grad_b) a.grad_b[c] = s0;
-        }
-        if (D > 1) {
-          for (int r = 0; r < D; r++) {
-            float* dst = reinterpret_cast<float*>(a.xchg.p[r]) + a.xchg_off + ((size_t)rank * C + c) * 3;
-            st_relaxed_sys_f32(dst, v0); st_relaxed_sys_f32(dst + 1, v1); st_relaxed_sys_f32(dst + 2, v2);
-          }
-        } else {
-          float* p = a.partial + (size_t)c * S * 3;  // slot 0 of the channel now holds the merged local value
-          p[0] = v0; p[1] = v1; p[2] = v2;
-        }
-      }
-      if (D > 1) {
-        __threadfence_system();
-        __syncthreads();
-        signal_all(a.sig, a.channel, tid);
-        wait_all(a.sig, a.channel, tid);
-      }
+    if (D > 1) {
+      if (blockIdx.x == 0) { __threadfence_system(); signal_all(a.sig, a.channel, tid); }
+      wait_all(a.sig, a.channel, tid);
       __syncthreads();
-      const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + a.xchg_off : nullptr;
-      for (int c = tid; c < C; c += kBnThreads) {
-        if (!a.is_bwd) {
-          Wf w{0.f, 0.f, 0.f};
-          if (D > 1) {
-            for (int r = 0; r < D; r++) { const float* p = mine + ((size_t)r * C + c) * 3; w = wf_merge(w, Wf{ld_relaxed_sys_f32(p), ld_relaxed_sys_f32(p + 1), ld_relaxed_sys_f32(p + 2)}); }
-          } else {
-            const float* p = a.partial + (size_t)c * S * 3; w = Wf{p[0], p[1], p[2]};
-          }
-          const float var_b = w.n > 0.f ? w.m2 / w.n : 0.f;
-          a.mean[c] = w.mean;
-          if (a.var_biased) a.var_biased[c] = var_b;
-          if (a.invstd) a.invstd[c] = rsqrtf(var_b + a.eps);
-          if (a.running_mean) {
-            const float var_u = w.n > 1.f ? w.m2 / (w.n - 1.f) : var_b;
-            a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * w.mean;
-            a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var_u;
-          }
-          if (c == 0 && a.count_total) a.count_total[0] = w.n;
+    }
+    const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + a.xchg_off : nullptr;
+    for (int c = blockIdx.x * kBnThreads + tid; c < C; c += gridDim.x * kBnThreads) {
+      if (!a.is_bwd) {
+        Wf w{0.f, 0.f, 0.f};
+        if (D > 1) {
+          for (int r = 0; r < D; r++) { const float* p = mine + ((size_t)r * C + c) * 3; w = wf_merge(w, Wf{ld_relaxed_sys_f32(p), ld_relaxed_sys_f32(p + 1), ld_relaxed_sys_f32(p + 2)}); }
         } else {
-          float s0 = 0.f, s1 = 0.f, nt = 0.f;
-          if (D > 1) {
-            for (int r = 0; r < D; r++) { const float* p = mine + ((size_t)r * C + c) * 3; s0 += ld_relaxed_sys_f32(p); s1 += ld_relaxed_sys_f32(p + 1); nt += ld_relaxed_sys_f32(p + 2); }
-          } else {
-            const float* p = a.partial + (size_t)c * S * 3; s0 = p[0]; s1 = p[1]; nt = p[2];
-          }
-          a.sum_dy[c] = s0; a.sum_dy_xmu[c] = s1;
-          if (c == 0 && a.count_total) a.count_total[0] = nt;
+          const float* p = a.merged + (size_t)c * 3; w = Wf{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)};
         }
+        const float var_b = w.n > 0.f ? w.m2 / w.n : 0.f;
+        a.mean[c] = w.mean;
+        if (a.var_biased) a.var_biased[c] = var_b;
+        if (a.invstd) a.invstd[c] = rsqrtf(var_b + a.eps);
+        if (a.running_mean) {
+          const float var_u = w.n > 1.f ? w.m2 / (w.n - 1.f) : var_b;
+          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * w.mean;
+          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var_u;
+        }
+        if (c == 0 && a.count_total) a.count_total[0] = w.n;
+      } else {
+        float s0 = 0.f, s1 = 0.f, nt = 0.f;
+        if (D > 1) {
+          for (int r = 0; r < D; r++) { const float* p = mine + ((size_t)r * C + c) * 3; s0 += ld_relaxed_sys_f32(p); s1 += ld_relaxed_sys_f32(p + 1); nt += ld_relaxed_sys_f32(p + 2); }
+        } else {
+          const float* p = a.merged + (size_t)c * 3; s0 = __ldcg(p); s1 = __ldcg(p + 1); nt = __ldcg(p + 2);
+        }
+        a.sum_dy[c] = s0; a.sum_dy_xmu[c] = s1;
+        if (c == 0 && a.count_total) a.count_total[0] = nt;
       }
     }
     if (a.phases & 4) grid_barrier(a.grid_bar, gridDim.x);
@@ -311,13 +361,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
 
   // ------------------------------------------------------------------ phase 3: elementwise, in memory order, 16-byte vectors
   if (a.phases & 4) {
-    T* out = reinterpret_cast<T*>(a.out);
-    T* dz = reinterpret_cast<T*>(a.dz);
+    T* __restrict__ out = reinterpret_cast<T*>(a.out);
+    T* __restrict__ dz = reinterpret_cast<T*>(a.dz);
     const long long total = (long long)a.N * C * HW;
     const float inv_n = a.is_bwd ? 1.f / __ldcg(a.count_total) : 0.f;
     const bool vec = ((a.nhwc ? C : HW) % V == 0) && aligned16(x) && aligned16(out) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z)) &&
                      (!dz || aligned16(dz));
     const int step = vec ? V : 1;
+#pragma unroll 2
     for (long long i = ((long long)blockIdx.x * kBnThreads + tid) * step; i < total; i += (long long)gridDim.x * kBnThreads * step) {
       // channel of element i (+j): NCHW: (i / HW) % C, constant over the vector; NHWC: (i % C) + j
       int c0;
@@ -344,7 +395,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
             if (a.fuse_relu) yv = fmaxf(yv, 0.f);
             o[j] = yv;
           } else {
-            const float g = masked_grad<T>(a, gv[j], xv[j], z ? zv[j] : 0.f, c, mu, is);
+            const float g = masked_grad(a, gv[j], xv[j], z ? zv[j] : 0.f, c, mu, is);
             gz[j] = g;
             const float sdy = __ldcg(a.sum_dy + c) * inv_n, sdx = __ldcg(a.sum_dy_xmu + c) * inv_n;
             o[j] = (g - sdy - (xv[j] - mu) * is * is * sdx) * w * is;
@@ -366,22 +417,27 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
 
 using namespace ab;
 
-AB_API int ab_syncbn_partial_floats(int C) { return C * kBnMaxSplits * 3; }
-
 // One entry point for every SyncBN operation; see the header comment for `phases`. x is contiguous NCHW (nhwc=0) or
 // contiguous channels-last (nhwc=1), viewed as [N, C, HW] / [N, HW, C].
+// scratch: float buffer of `scratch_floats`: [merged: 3C][unit counters: C uint32][partials: the rest].
 AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, const void* z, void* out, void* dz, int N, int C, int HW,
                      int nhwc, const float* weight, const float* bias, float* mean, float* invstd, float* var_biased,
                      float* running_mean, float* running_var, float momentum, float eps, float* grad_w, float* grad_b, float* sum_dy,
-                     float* sum_dy_xmu, float* partial, float* count_total, unsigned int* grid_bar, int fuse_relu, const uint64_t* pads,
-                     const uint64_t* xchg, int xchg_off, int rank, int world, unsigned int epoch, int channel, int dt, cudaStream_t st) {
+                     float* sum_dy_xmu, float* scratch, long long scratch_floats, float* count_total, unsigned int* grid_bar,
+                     int fuse_relu, const uint64_t* pads, const uint64_t* xchg, int xchg_off, int rank, int world, unsigned int epoch,
+                     int channel, int dt, cudaStream_t st) {
   if (C <= 0 || N <= 0 || HW <= 0) return 0;
   BnArgs a;
   a.x = x; a.dy = dy; a.z = z; a.out = out; a.dz = dz; a.N = N; a.C = C; a.HW = HW; a.nhwc = nhwc;
   a.weight = weight; a.bias = bias; a.mean = mean; a.invstd = invstd; a.var_biased = var_biased; a.running_mean = running_mean;
   a.running_var = running_var; a.momentum = momentum; a.eps = eps; a.grad_w = grad_w; a.grad_b = grad_b; a.sum_dy = sum_dy;
-  a.sum_dy_xmu = sum_dy_xmu; a.partial = partial; a.count_total = count_total; a.grid_bar = grid_bar; a.phases = phases;
+  a.sum_dy_xmu = sum_dy_xmu; a.count_total = count_total; a.grid_bar = grid_bar; a.phases = phases;
   a.fuse_relu = fuse_relu; a.is_bwd = is_bwd; a.channel = channel; a.xchg_off = xchg_off;
+  a.merged = scratch;
+  a.unit_ctr = reinterpret_cast<unsigned int*>(scratch + (size_t)3 * C);
+  a.partial = scratch + (size_t)4 * C;
+  const long long partial_cap = scratch_floats - (long long)4 * C;
+  if (partial_cap < (long long)3 * C) return -5;
   for (int i = 0; i < kMaxPeers; i++) {
     a.sig.pads.p[i] = (pads && i < world) ? (void*)pads[i] : nullptr;
     a.xchg.p[i] = (xchg && i < world) ? (void*)xchg[i] : nullptr;
@@ -390,14 +446,17 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
   const long long per_c = (long long)N * HW;
   int grid = kNumSMs * 2;  // the software grid barrier needs every CTA resident: 2 CTAs/SM by __launch_bounds__
   const int units = nhwc ? (C + 63) / 64 : C;
-  int splits = (grid + units - 1) / units;
-  if (splits > kBnMaxSplits) splits = kBnMaxSplits;
-  while (splits > 1 && per_c / splits < 512) splits--;
+  long long splits = (2LL * grid + units - 1) / units;
+  const long long min_per_split = nhwc ? 128 : 4096;  // rows / elements: keep every split a few full passes long
+  if (splits > per_c / min_per_split) splits = per_c / min_per_split;
+  if (splits > partial_cap / (3LL * C)) splits = partial_cap / (3LL * C);
+  if (splits > 1024) splits = 1024;
   if (splits < 1) splits = 1;
-  a.splits = splits;
+  a.splits = (int)splits;
   const long long total = (long long)N * C * HW;
   long long want = 1;
   if (phases & 1) want = (long long)units * splits;
+  if (phases & 2) { const long long w2 = ((long long)C + kBnThreads - 1) / kBnThreads; if (w2 > want) want = w2; }
   if (phases & 4) { const long long w4 = (total + kBnThreads * 16 - 1) / (kBnThreads * 16); if (w4 > want) want = w4; }
   if (want < grid) grid = (int)want;
 #define BN_GO(T) syncbn_kernel<T><<<grid, kBnThreads, 0, st>>>(a)

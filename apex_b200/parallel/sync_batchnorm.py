@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 from .. import _lib
 
-_lib.declare("ab_syncbn", "i i p p p p p i i i i p p p p p p p f f p p p p p p p i p p i i i i i i p")
+_lib.declare("ab_syncbn", "i i p p p p p i i i i p p p p p p p f f p p p p p l p p i p p i i i i i i p")
 
 _XCHG_C = 4096  # channels the exchange buffer is sized for (grown on demand)
 
@@ -47,7 +47,8 @@ class _GroupState:
             self.xchg = SymmetricMemory(2 * self.region * 4, group=group, device=device, multicast=False, tag="bn")
             self.xchg_ptrs = self.xchg.peer_ptr_array()
         self.grid_bar = torch.zeros(2, dtype=torch.int32, device=device)
-        self.partial = torch.empty(self.cap * 64 * 3, dtype=torch.float32, device=device)
+        # [merged 3C][unit counters C][split partials]; zero-initialised (the kernel leaves the counters at zero)
+        self.scratch = torch.zeros(4 * self.cap + 24 * self.cap + 3 * 65536, dtype=torch.float32, device=device)
         self.count = torch.zeros(1, dtype=torch.float32, device=device)
 
     @classmethod
@@ -87,7 +88,7 @@ def _call(st: _GroupState, is_bwd, phases, x, dy, z, out, dz, N, C, HW, nhwc, we
     _lib.fn("ab_syncbn")(int(is_bwd), int(phases), x.data_ptr(), _lib.ptr(dy), _lib.ptr(z), _lib.ptr(out), _lib.ptr(dz), N, C, HW, nhwc,
                          _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(var_biased), _lib.ptr(rmean),
                          _lib.ptr(rvar), float(momentum), float(eps), _lib.ptr(grad_w), _lib.ptr(grad_b), _lib.ptr(sum_dy),
-                         _lib.ptr(sum_dy_xmu), st.partial.data_ptr(), st.count.data_ptr(), st.grid_bar.data_ptr(), int(fuse_relu), pads,
+                         _lib.ptr(sum_dy_xmu), st.scratch.data_ptr(), st.scratch.numel(), st.count.data_ptr(), st.grid_bar.data_ptr(), int(fuse_relu), pads,
                          xchg, off, rank, world, epoch, 32, _lib.dt(x), _lib.stream_ptr(x.device))
 
 
