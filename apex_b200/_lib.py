@@ -136,7 +136,7 @@ def gpu_required_error(what: str) -> RuntimeError:
 
 # --- signature table (kept next to the loader so a mismatch is one grep away) ------------------------------------------
 _T = "p i i i i"  # arena, n, depth, total_chunks, chunk
-declare("ab_mt_scale", _T + " i i f p p")
+declare("ab_mt_scale", _T + " i i f p p p")
 declare("ab_mt_axpby", _T + " i i i f f i p p")
 declare("ab_mt_norm", _T + " i p p p p p p i i f f p")
 declare("ab_mt_l2norm_scale", _T + " i i f p p p p p")

@@ -13,15 +13,16 @@ struct ScaleOp {
   static constexpr unsigned kRead = 1u, kWrite = 2u;
   static constexpr int kAcc = 0;
   using Ctx = NoCtx;
-  float scale; int* noop;
+  float scale; int* noop; const float* scale_ptr;  // effective scale = scale * (*scale_ptr) when a device scalar is given
   __device__ bool skip() const { return false; }
   __device__ Ctx begin(int) const { return {}; }
   template <int D, int V>
   __device__ __forceinline__ void apply(float (&r)[D][V], const Ctx&, float (&)[2], int) const {
     bool fin = true;
+    const float sc = scale_ptr ? scale * (*scale_ptr) : scale;
 #pragma unroll
-    for (int j = 0; j < V; j++) { fin = fin && finite_f(r[0][j]); r[1][j] = r[0][j] * scale; }
-    if (!fin) *noop = 1;  // benign race: every writer stores the same value
+    for (int j = 0; j < V; j++) { fin = fin && finite_f(r[0][j]); r[1][j] = r[0][j] * sc; }
+    if (!fin && noop) *noop = 1;  // benign race: every writer stores the same value
   }
   __device__ void end(const Ctx&, int, int, float (&)[2], float*) const {}
 };
@@ -146,9 +147,9 @@ using namespace ab;
 #define TB make_table(arena, n, depth, total_chunks, chunk)
 
 AB_API int ab_mt_scale(void* arena, int n, int depth, int total_chunks, int chunk, int dt_in, int dt_out, float scale,
-                       int* noop, cudaStream_t st) {
+                       int* noop, const float* scale_ptr, cudaStream_t st) {
   if (depth != 2) return -2;
-  ScaleOp op{scale, noop};
+  ScaleOp op{scale, noop, scale_ptr};
   AB_DISPATCH_FLOAT3(dt_in, TI, AB_DISPATCH_FLOAT3(dt_out, TO, return (mt_launch<4, ScaleOp, TI, TO>(TB, op, st))));
   return 0;
 }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
         const int step = vec ? V : 1;
 #pragma unroll 4
         for (long long e = e0 + (long long)tid * step; e < e1; e += (long long)kBnThreads * step) {
-          const long long n = e / HW;
+          const long long n = (per_c < 0x7fffffffLL) ? (long long)((unsigned)e / (unsigned)HW) : e / HW;
           const long long off = (n * C + c) * (long long)HW + (e - n * HW);
           float xv[V], gv[V], zv[V];
           if (vec) {
@@ -360,19 +360,24 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
   }
 
   // ------------------------------------------------------------------ phase 3: elementwise, in memory order, 16-byte vectors
+  // Per-channel coefficients so the inner loop is 1-3 FMAs per element:
+  //   fwd: y  = x*sc + sh (+z)(relu)                 sc = inv_std*w, sh = b - mean*sc
+  //   bwd: dx = g*A + x*Bc + Cc                      A = w*inv_std, Bc = -inv_std^3*w*sum_dy_xmu/N, Cc = -A*sum_dy/N - mean*Bc
   if (a.phases & 4) {
     T* __restrict__ out = reinterpret_cast<T*>(a.out);
     T* __restrict__ dz = reinterpret_cast<T*>(a.dz);
-    const long long total = (long long)a.N * C * HW;
     const float inv_n = a.is_bwd ? 1.f / __ldcg(a.count_total) : 0.f;
     const bool vec = ((a.nhwc ? C : HW) % V == 0) && aligned16(x) && aligned16(out) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z)) &&
                      (!dz || aligned16(dz));
     const int step = vec ? V : 1;
-#pragma unroll 2
-    for (long long i = ((long long)blockIdx.x * kBnThreads + tid) * step; i < total; i += (long long)gridDim.x * kBnThreads * step) {
-      // channel of element i (+j): NCHW: (i / HW) % C, constant over the vector; NHWC: (i % C) + j
-      int c0;
-      if (a.nhwc) c0 = (int)(i % C); else c0 = (int)((i / HW) % C);
+    auto coef = [&](int c, float& sc, float& sh, float& A, float& Bc, float& Cc) {
+      const float mu = __ldcg(a.mean + c), is = __ldcg(a.invstd + c), w = a.weight ? a.weight[c] : 1.f;
+      sc = is * w; sh = (a.bias ? a.bias[c] : 0.f) - mu * sc;
+      if (a.is_bwd) {
+        A = sc; Bc = -is * is * sc * __ldcg(a.sum_dy_xmu + c) * inv_n; Cc = -A * __ldcg(a.sum_dy + c) * inv_n - mu * Bc;
+      } else { A = 0.f; Bc = 0.f; Cc = 0.f; }
+    };
+    auto apply = [&](long long i, const float (&sc)[V], const float (&sh)[V], const float (&A)[V], const float (&Bc)[V], const float (&Cc)[V]) {
       float xv[V], gv[V], zv[V], o[V], gz[V];
       if (vec) {
         load_vec<T, V>(xv, x + i);
@@ -386,19 +391,16 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
 #pragma unroll
       for (int j = 0; j < V; j++) {
         if (j < step) {
-          const int c = a.nhwc ? c0 + j : c0;
-          const float mu = __ldcg(a.mean + c), is = __ldcg(a.invstd + c);
-          const float w = a.weight ? a.weight[c] : 1.f;
           if (!a.is_bwd) {
-            float yv = (xv[j] - mu) * is * w + (a.bias ? a.bias[c] : 0.f);
+            float yv = fmaf(xv[j], sc[j], sh[j]);
             if (z) yv += zv[j];
             if (a.fuse_relu) yv = fmaxf(yv, 0.f);
             o[j] = yv;
           } else {
-            const float g = masked_grad(a, gv[j], xv[j], z ? zv[j] : 0.f, c, mu, is);
+            float g = gv[j];
+            if (a.fuse_relu) { float yv = fmaf(xv[j], sc[j], sh[j]); if (z) yv += zv[j]; if (yv <= 0.f) g = 0.f; }
             gz[j] = g;
-            const float sdy = __ldcg(a.sum_dy + c) * inv_n, sdx = __ldcg(a.sum_dy_xmu + c) * inv_n;
-            o[j] = (g - sdy - (xv[j] - mu) * is * is * sdx) * w * is;
+            o[j] = fmaf(g, A[j], fmaf(xv[j], Bc[j], Cc[j]));
           }
         }
       }
@@ -408,6 +410,45 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
       } else {
         out[i] = from_f<T>(o[0]);
         if (a.is_bwd && dz) dz[i] = from_f<T>(gz[0]);
+      }
+    };
+    float sc[V], sh[V], A[V], Bc[V], Cc[V];
+    if (a.nhwc) {
+      const long long total = (long long)a.N * C * HW;
+      const long long gthreads = (long long)gridDim.x * kBnThreads;
+      const int cvecs = C / step;
+      const long long gtid = (long long)blockIdx.x * kBnThreads + tid;
+      if (gthreads % cvecs == 0) {
+        // every vector this thread touches has the same channels: coefficients live in registers for the whole loop
+        const int c0 = (int)(gtid % cvecs) * step;
+#pragma unroll
+        for (int j = 0; j < V; j++) if (j < step) coef(c0 + j, sc[j], sh[j], A[j], Bc[j], Cc[j]);
+#pragma unroll 2
+        for (long long i = gtid * step; i < total; i += gthreads * step) apply(i, sc, sh, A, Bc, Cc);
+      } else {
+        for (long long i = gtid * step; i < total; i += gthreads * step) {
+          const int c0 = (int)(i % C);
+#pragma unroll
+          for (int j = 0; j < V; j++) if (j < step) coef(c0 + j, sc[j], sh[j], A[j], Bc[j], Cc[j]);
+          apply(i, sc, sh, A, Bc, Cc);
+        }
+      }
+    } else {
+      // NCHW: tile = 256*step consecutive elements of one (n, c) plane -> one channel lookup per tile
+      const int tile = kBnThreads * step;
+      const int tpp = (HW + tile - 1) / tile;
+      const long long tiles = (long long)a.N * C * tpp;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long plane = t / tpp;
+        const int c = (int)(plane % C);
+        const int in_plane = (int)(t - plane * tpp) * tile + tid * step;
+        if (in_plane < HW) {
+          float s0, s1, s2, s3, s4;
+          coef(c, s0, s1, s2, s3, s4);
+#pragma unroll
+          for (int j = 0; j < V; j++) { sc[j] = s0; sh[j] = s1; A[j] = s2; Bc[j] = s3; Cc[j] = s4; }
+          apply(plane * HW + in_plane, sc, sh, A, Bc, Cc);
+        }
       }
     }
   }

@@ -103,13 +103,18 @@ def _s(tb: TensorTable) -> int:
 
 # ---------------------------------------------------------------------------------------------------------------------
 def multi_tensor_scale(chunk_size, noop_flag, tensor_lists, scale):
+    """out = in * scale. ``scale`` may be a python number or a 1-element DEVICE tensor (no host sync, graph-capturable)."""
     if _empty(tensor_lists):
         return
     if not _is_cuda(tensor_lists):
-        return ref.multi_tensor_scale(noop_flag, tensor_lists, scale)
+        return ref.multi_tensor_scale(noop_flag, tensor_lists, float(scale))
     tb = _table(tensor_lists, chunk_size)
     d = tb.dtypes
-    _lib.fn("ab_mt_scale")(*tb.head(), d[0], d[1], float(scale), _lib.ptr(noop_flag), _s(tb))
+    if torch.is_tensor(scale):
+        sp = scale.to(device=tb.device, dtype=torch.float32)
+        _lib.fn("ab_mt_scale")(*tb.head(), d[0], d[1], 1.0, _lib.ptr(noop_flag), sp.data_ptr(), _s(tb))
+    else:
+        _lib.fn("ab_mt_scale")(*tb.head(), d[0], d[1], float(scale), _lib.ptr(noop_flag), None, _s(tb))
 
 
 def multi_tensor_axpby(chunk_size, noop_flag, tensor_lists, a, b, arg_to_check):
