@@ -1,0 +1,117 @@
+"""NHWC GroupNorm with optional fused SiLU/swish (csrc/group_norm.cu).
+
+Reference: apex/contrib/group_norm/group_norm.py:162-457 (``GroupNorm(num_groups, num_channels, eps, affine, act)``; custom ops
+``apex::group_norm_nhwc_fprop/bprop``; v1 one/two-pass kernels for 23 channel counts, v2 Blackwell kernels for 14 (HW, C) shapes,
+else ``torch_group_norm``). Here one persistent kernel per direction covers every shape; inputs must be channels-last
+(logical NCHW, physical NHWC) like the reference; anything else goes through ``torch_group_norm``."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ... import _lib
+
+_lib.declare("ab_group_norm", "i p p p p p i p p p p p l p i i i i f i i p")
+
+_state: dict = {}
+
+
+def torch_group_norm(x, g, w, b, eps, act=""):
+    xdtype, wdtype = x.dtype, w.dtype
+    if xdtype != wdtype:
+        x = x.to(dtype=wdtype)
+    y = F.group_norm(x, g, w, b, eps)
+    if act in ("silu", "swish"):
+        y = F.silu(y)
+    if xdtype != wdtype and y.dtype != xdtype:
+        y = y.to(dtype=xdtype)
+    return y
+
+
+def _scratch(device, need):
+    st = _state.get(device)
+    if st is None or st[0].numel() < need:
+        st = _state[device] = (torch.empty(max(need, 1 << 20), dtype=torch.float32, device=device),
+                               torch.zeros(2, dtype=torch.int32, device=device))
+    return st
+
+
+def _native_ok(x, w):
+    return (x.is_cuda and _lib.available() and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16, torch.float32)
+            and x.is_contiguous(memory_format=torch.channels_last) and (w is None or w.dtype in (x.dtype, torch.float32)))
+
+
+def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
+    N, C, H, W = x.shape
+    need = N * C * 16 * 3 + N * C * 3 + N * G * 2 + 64
+    scratch, bar = _scratch(x.device, need)
+    w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
+    _lib.fn("ab_group_norm")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
+                             rstd.data_ptr(), _lib.ptr(dg), _lib.ptr(db), scratch.data_ptr(), scratch.numel(), bar.data_ptr(), N, H * W, C, G,
+                             float(eps), int(silu), _lib.dt(x), _lib.stream_ptr(x.device))
+
+
+class GroupNormNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, G, weight, bias, eps, act):
+        silu = act in ("silu", "swish")
+        N, C = x.shape[0], x.shape[1]
+        y = torch.empty_like(x)  # preserves channels_last
+        mean = torch.empty(N * G, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(N * G, dtype=torch.float32, device=x.device)
+        _launch(False, x, None, y, weight, bias, mean, rstd, None, None, G, eps, silu)
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        ctx.G, ctx.eps, ctx.silu = G, eps, silu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        C = x.shape[1]
+        dg = torch.empty(C, dtype=torch.float32, device=x.device)
+        db = torch.empty(C, dtype=torch.float32, device=x.device)
+        _launch(True, x, dy, dx, weight, bias, mean, rstd, dg, db, ctx.G, ctx.eps, ctx.silu)
+        return dx, None, dg.to(weight.dtype), db.to(bias.dtype), None, None
+
+
+def group_norm_nhwc(x, G, weight, bias, eps=1e-5, act=""):
+    if not _native_ok(x, weight) or weight is None or bias is None:
+        return torch_group_norm(x, G, weight, bias, eps, act)
+    return GroupNormNHWC.apply(x, G, weight, bias, eps, act)
+
+
+class GroupNorm(nn.Module):
+    """``torch.nn.GroupNorm`` signature + ``act`` ('' | 'silu' | 'swish'); optimised for channels-last input."""
+
+    __constants__ = ["num_groups", "num_channels", "eps", "affine", "act"]
+
+    def __init__(self, num_groups, num_channels, eps=1e-5, affine=True, device=None, dtype=None, act=""):
+        super().__init__()
+        if num_channels % num_groups != 0:
+            raise ValueError("num_channels must be divisible by num_groups")
+        self.num_groups, self.num_channels, self.eps, self.affine = num_groups, num_channels, eps, affine
+        self.act = act.lower()
+        kw = {"device": device, "dtype": dtype}
+        if affine:
+            self.weight = nn.Parameter(torch.empty(num_channels, **kw))
+            self.bias = nn.Parameter(torch.empty(num_channels, **kw))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.affine:
+            nn.init.ones_(self.weight)
+            nn.init.zeros_(self.bias)
+
+    def forward(self, input):
+        if self.affine and _native_ok(input, self.weight) and not torch.compiler.is_compiling():
+            return GroupNormNHWC.apply(input, self.num_groups, self.weight, self.bias, self.eps, self.act)
+        return torch_group_norm(input, self.num_groups, self.weight, self.bias, self.eps, self.act)
+
+    def extra_repr(self):
+        return "{num_groups}, {num_channels}, eps={eps}, affine={affine}, act={act}".format(**self.__dict__)

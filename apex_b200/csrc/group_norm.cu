@@ -1,0 +1,271 @@
+// NHWC GroupNorm (+ fused SiLU / swish), forward and backward, as ONE persistent kernel per direction:
+//   [1] per-(image, channel) partial statistics over row splits (threads own 16-byte channel vectors, rows are 4x unrolled)
+//   [2] after a grid barrier: fold splits and the C/G channels of each group -> mean / rstd per (n, g)  (bwd: the two
+//       gamma-weighted group sums, and dgamma / dbeta)
+//   [4] after a grid barrier: y = silu?(x * sc + sh) with per-(n, c) coefficients; the second read of x comes from the 126 MB L2.
+// Any C / G / H*W (the reference supports 23 hard-coded channel counts for G in {16, 32} and, for its Blackwell path,
+// 14 (HW, C) shapes: apex/contrib/group_norm/group_norm.py:247-289,390-416; kernels apex/contrib/csrc/group_norm_v2/
+// gn_cuda_kernel.cuh:195,596 use hardware clusters of 2 + DSMEM or atom.add flip barriers for the same stats->apply dependency).
+#include "common.cuh"
+#include <cstdio>
+
+namespace ab {
+
+constexpr int kGnThreads = 256;
+
+struct GnArgs {
+  const void* x; const void* dy; void* out;
+  const void* gamma; const void* beta;   // [C] in the activation dtype or fp32 (w_fp32)
+  int w_fp32;
+  float* mean; float* rstd;               // [N, G]
+  float* dgamma; float* dbeta;            // [C] fp32 (bwd)
+  float* partial;                         // [N*C][S][3]
+  float* chan;                            // [N*C][3] per-(n,c) merged values
+  float* gsum;                            // [N*G][2] bwd: gamma-weighted group sums / M
+  unsigned int* grid_bar;
+  int N, HW, C, G, splits, silu, is_bwd, phases;
+  float eps;
+};
+
+__device__ __forceinline__ void gn_grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned int* gen = bar + 1;
+    const unsigned int g = *gen;
+    __threadfence();
+    if (atomicAdd(bar, 1u) == nblocks - 1) { bar[0] = 0u; __threadfence(); atomicAdd(bar + 1, 1u); }
+    else {
+      long long t0 = clock64();
+      while (*gen == g) { if (clock64() - t0 > 20000000000LL) { printf("apex_b200 group_norm: grid barrier timeout\n"); __trap(); } }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct GW { float mean, m2, n; };
+__device__ __forceinline__ GW gw_merge(const GW& a, const GW& b) {
+  if (b.n == 0.f) return a;
+  if (a.n == 0.f) return b;
+  const float n = a.n + b.n, d = b.mean - a.mean, f = b.n / n;
+  return GW{a.mean + d * f, a.m2 + b.m2 + d * d * a.n * f, n};
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_w(const void* p, int fp32, int c) {
+  return fp32 ? reinterpret_cast<const float*>(p)[c] : to_f<T>(reinterpret_cast<const T*>(p)[c]);
+}
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float dsilu_f(float v) { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f + v * (1.f - s)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float sm[3][kGnThreads + 8];
+  const int tid = threadIdx.x;
+  const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
+  const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+  T* __restrict__ out = reinterpret_cast<T*>(a.out);
+  const int C = a.C, HW = a.HW, G = a.G, Cg = C / G, S = a.splits;
+  const bool vec = (C % V == 0) && aligned16(x) && aligned16(out) && (!a.is_bwd || aligned16(dy));
+  const int cw = vec ? V : 1, lanes_c = vec ? 8 : 32, lanes_r = kGnThreads / lanes_c, tile_c = lanes_c * cw;
+  const int ctiles = (C + tile_c - 1) / tile_c;
+  const int cx = tid % lanes_c, ry = tid / lanes_c;
+
+  // ------------------------------------------------------------------ phase 1
+  if (a.phases & 1) {
+    const int items = a.N * ctiles * S;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int s = it % S, ct = (it / S) % ctiles, n = it / (S * ctiles);
+      const int r0 = (int)((long long)HW * s / S), r1 = (int)((long long)HW * (s + 1) / S);
+      const int cbase = ct * tile_c + cx * cw;
+      const bool c_ok = cbase < C;
+      float acc0[V], acc1[V], shift[V], sc[V], sh[V], cnt = 0.f;
+#pragma unroll
+      for (int j = 0; j < V; j++) { acc0[j] = 0.f; acc1[j] = 0.f; shift[j] = 0.f; sc[j] = 0.f; sh[j] = 0.f; }
+      const T* xb = x + (size_t)n * HW * C;
+      const T* gb = a.is_bwd ? dy + (size_t)n * HW * C : nullptr;
+      if (c_ok) {
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          if (j < cw && cbase + j < C) {
+            if (!a.is_bwd) { if (r1 > r0) shift[j] = to_f<T>(xb[(size_t)r0 * C + cbase + j]); }
+            else {
+              const int g = (cbase + j) / Cg;
+              const float mu = a.mean[n * G + g], r = a.rstd[n * G + g];
+              sc[j] = r; sh[j] = -mu * r;  // xhat = x*sc + sh
+            }
+          }
+        }
+#pragma unroll 4
+        for (int r = r0 + ry; r < r1; r += lanes_r) {
+          const size_t off = (size_t)r * C + cbase;
+          float xv[V], gv[V];
+          if (vec) { load_vec<T, V>(xv, xb + off); if (a.is_bwd) load_vec<T, V>(gv, gb + off); }
+          else { xv[0] = to_f<T>(xb[off]); if (a.is_bwd) gv[0] = to_f<T>(gb[off]); }
+          cnt += 1.f;
+#pragma unroll
+          for (int j = 0; j < V; j++) {
+            if (j < cw) {
+              if (!a.is_bwd) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] += d * d; }
+              else {
+                const float xh = fmaf(xv[j], sc[j], sh[j]);
+                float g = gv[j];
+                if (a.silu) {
+                  const int c = cbase + j;
+                  const float gm = c < C ? ld_w<T>(a.gamma, a.w_fp32, c) : 0.f, bt = (c < C && a.beta) ? ld_w<T>(a.beta, a.w_fp32, c) : 0.f;
+                  g *= dsilu_f(fmaf(xh, gm, bt));
+                }
+                acc0[j] += g; acc1[j] += g * xh;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        if (j < cw) {
+          __syncthreads();
+          if (!a.is_bwd) {
+            float m = 0.f, m2 = 0.f, nn = 0.f;
+            if (c_ok && cnt > 0.f) { const float mm = acc0[j] / cnt; m = shift[j] + mm; m2 = fmaxf(acc1[j] - acc0[j] * mm, 0.f); nn = cnt; }
+            sm[0][tid] = m; sm[1][tid] = m2; sm[2][tid] = nn;
+          } else { sm[0][tid] = acc0[j]; sm[1][tid] = acc1[j]; }
+          __syncthreads();
+          if (ry == 0 && c_ok && cbase + j < C) {
+            float* p = a.partial + (((size_t)n * C + cbase + j) * S + s) * 3;
+            if (!a.is_bwd) {
+              GW t{0.f, 0.f, 0.f};
+              for (int q = 0; q < lanes_r; q++) t = gw_merge(t, GW{sm[0][q * lanes_c + cx], sm[1][q * lanes_c + cx], sm[2][q * lanes_c + cx]});
+              p[0] = t.mean; p[1] = t.m2; p[2] = t.n;
+            } else {
+              float t0 = 0.f, t1 = 0.f;
+              for (int q = 0; q < lanes_r; q++) { t0 += sm[0][q * lanes_c + cx]; t1 += sm[1][q * lanes_c + cx]; }
+              p[0] = t0; p[1] = t1; p[2] = 0.f;
+            }
+          }
+        }
+      }
+    }
+    if (a.phases & 6) gn_grid_barrier(a.grid_bar, gridDim.x);
+  }
+
+  // ------------------------------------------------------------------ phase 2: one warp per (n, g)
+  if (a.phases & 2) {
+    const int lane = tid & 31;
+    const int gw = (blockIdx.x * kGnThreads + tid) >> 5, nw = (gridDim.x * kGnThreads) >> 5;
+    for (int ng = gw; ng < a.N * G; ng += nw) {
+      const int n = ng / G, g = ng - n * G;
+      if (!a.is_bwd) {
+        GW w{0.f, 0.f, 0.f};
+        for (int q = lane; q < Cg * S; q += 32) {
+          const int c = g * Cg + q / S, s = q % S;
+          const float* p = a.partial + (((size_t)n * C + c) * S + s) * 3;
+          w = gw_merge(w, GW{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)});
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          w = gw_merge(w, GW{__shfl_xor_sync(0xffffffffu, w.mean, o), __shfl_xor_sync(0xffffffffu, w.m2, o), __shfl_xor_sync(0xffffffffu, w.n, o)});
+        if (lane == 0) { a.mean[ng] = w.mean; a.rstd[ng] = rsqrtf((w.n > 0.f ? w.m2 / w.n : 0.f) + a.eps); }
+      } else {
+        float m1 = 0.f, m2 = 0.f;
+        for (int q = lane; q < Cg; q += 32) {
+          const int c = g * Cg + q;
+          float s1 = 0.f, s2 = 0.f;
+          for (int s = 0; s < S; s++) { const float* p = a.partial + (((size_t)n * C + c) * S + s) * 3; s1 += __ldcg(p); s2 += __ldcg(p + 1); }
+          float* cc = a.chan + ((size_t)n * C + c) * 3;
+          cc[0] = s1; cc[1] = s2;
+          const float gm = ld_w<T>(a.gamma, a.w_fp32, c);
+          m1 += gm * s1; m2 += gm * s2;
+        }
+        m1 = warp_sum(m1); m2 = warp_sum(m2);
+        if (lane == 0) { const float invM = 1.f / ((float)HW * (float)Cg); a.gsum[ng * 2] = m1 * invM; a.gsum[ng * 2 + 1] = m2 * invM; }
+      }
+    }
+    if (a.is_bwd && a.dgamma) {
+      gn_grid_barrier(a.grid_bar, gridDim.x);
+      for (int c = blockIdx.x * kGnThreads + tid; c < C; c += gridDim.x * kGnThreads) {
+        float dg = 0.f, db = 0.f;
+        for (int n = 0; n < a.N; n++) { const float* cc = a.chan + ((size_t)n * C + c) * 3; db += __ldcg(cc); dg += __ldcg(cc + 1); }
+        a.dgamma[c] = dg;
+        if (a.dbeta) a.dbeta[c] = db;
+      }
+    }
+    if (a.phases & 4) gn_grid_barrier(a.grid_bar, gridDim.x);
+  }
+
+  // ------------------------------------------------------------------ phase 3: elementwise in memory order
+  if (a.phases & 4) {
+    const long long per_img = (long long)HW * C;
+    const long long total = (long long)a.N * per_img;
+    const int step = vec ? V : 1;
+    const long long gthreads = (long long)gridDim.x * kGnThreads;
+#pragma unroll 2
+    for (long long i = ((long long)blockIdx.x * kGnThreads + tid) * step; i < total; i += gthreads * step) {
+      const int n = (int)(i / per_img);
+      const int c0 = (int)(i % C);
+      float xv[V], gv[V], o[V];
+      if (vec) { load_vec<T, V>(xv, x + i); if (a.is_bwd) load_vec<T, V>(gv, dy + i); }
+      else { xv[0] = to_f<T>(x[i]); if (a.is_bwd) gv[0] = to_f<T>(dy[i]); }
+#pragma unroll
+      for (int j = 0; j < V; j++) {
+        if (j < step) {
+          const int c = c0 + j, g = c / Cg;
+          const float mu = __ldcg(a.mean + n * G + g), r = __ldcg(a.rstd + n * G + g);
+          const float gm = a.gamma ? ld_w<T>(a.gamma, a.w_fp32, c) : 1.f, bt = a.beta ? ld_w<T>(a.beta, a.w_fp32, c) : 0.f;
+          const float xh = (xv[j] - mu) * r;
+          if (!a.is_bwd) {
+            float yv = fmaf(xh, gm, bt);
+            if (a.silu) yv = silu_f(yv);
+            o[j] = yv;
+          } else {
+            float g2 = gv[j];
+            if (a.silu) g2 *= dsilu_f(fmaf(xh, gm, bt));
+            const float m1 = __ldcg(a.gsum + (n * G + g) * 2), m2 = __ldcg(a.gsum + (n * G + g) * 2 + 1);
+            o[j] = r * (gm * g2 - m1 - xh * m2);
+          }
+        }
+      }
+      if (vec) store_vec<T, V>(out + i, o); else out[i] = from_f<T>(o[0]);
+    }
+  }
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+// scratch floats: partial N*C*S*3 + chan N*C*3 + gsum N*G*2
+AB_API long long ab_group_norm_scratch_floats(int N, int C, int G, int max_splits) {
+  return (long long)N * C * max_splits * 3 + (long long)N * C * 3 + (long long)N * G * 2 + 64;
+}
+
+AB_API int ab_group_norm(int is_bwd, const void* x, const void* dy, void* out, const void* gamma, const void* beta, int w_fp32, float* mean,
+                         float* rstd, float* dgamma, float* dbeta, float* scratch, long long scratch_floats, unsigned int* grid_bar, int N,
+                         int HW, int C, int G, float eps, int silu, int dt, cudaStream_t st) {
+  if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0) return -2;
+  GnArgs a;
+  a.x = x; a.dy = dy; a.out = out; a.gamma = gamma; a.beta = beta; a.w_fp32 = w_fp32; a.mean = mean; a.rstd = rstd; a.dgamma = dgamma;
+  a.dbeta = dbeta; a.grid_bar = grid_bar; a.N = N; a.HW = HW; a.C = C; a.G = G; a.eps = eps; a.silu = silu; a.is_bwd = is_bwd; a.phases = 7;
+  int grid = kNumSMs * 2;
+  const int ctiles = (C + 63) / 64;
+  long long units = (long long)N * ctiles;
+  long long splits = (2LL * grid + units - 1) / units;
+  if (splits > HW / 64) splits = HW / 64;
+  if (splits < 1) splits = 1;
+  const long long fixed = (long long)N * C * 3 + (long long)N * G * 2 + 64;
+  while (splits > 1 && (long long)N * C * splits * 3 + fixed > scratch_floats) splits--;
+  if ((long long)N * C * splits * 3 + fixed > scratch_floats) return -5;
+  a.splits = (int)splits;
+  a.partial = scratch;
+  a.chan = scratch + (size_t)N * C * splits * 3;
+  a.gsum = a.chan + (size_t)N * C * 3;
+  const long long total = (long long)N * HW * C;
+  long long want = units * splits;
+  const long long w4 = (total + kGnThreads * 16 - 1) / (kGnThreads * 16);
+  if (w4 > want) want = w4;
+  if (want < grid) grid = (int)want;
+  AB_DISPATCH_FLOAT3(dt, T, group_norm_kernel<T><<<grid, kGnThreads, 0, st>>>(a));
+  AB_CHECK_LAUNCH();
+  return 0;
+}
