@@ -475,9 +475,13 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
   a.sum_dy_xmu = sum_dy_xmu; a.count_total = count_total; a.grid_bar = grid_bar; a.phases = phases;
   a.fuse_relu = fuse_relu; a.is_bwd = is_bwd; a.channel = channel; a.xchg_off = xchg_off;
   a.merged = scratch;
-  a.unit_ctr = reinterpret_cast<unsigned int*>(scratch + (size_t)3 * C);
-  a.partial = scratch + (size_t)4 * C;
-  const long long partial_cap = scratch_floats - (long long)4 * C;
+  // the arrival counters live at a FIXED place (the tail of the scratch) so that calls with different C never alias them with
+  // the merged / partial floats of an earlier call: they must read zero on entry
+  constexpr long long kCtrCap = 16384;
+  if (C > kCtrCap || scratch_floats < kCtrCap + 6LL * C) return -5;
+  a.unit_ctr = reinterpret_cast<unsigned int*>(scratch + (scratch_floats - kCtrCap));
+  a.partial = scratch + (size_t)3 * C;
+  const long long partial_cap = scratch_floats - kCtrCap - (long long)3 * C;
   if (partial_cap < (long long)3 * C) return -5;
   for (int i = 0; i < kMaxPeers; i++) {
     a.sig.pads.p[i] = (pads && i < world) ? (void*)pads[i] : nullptr;
