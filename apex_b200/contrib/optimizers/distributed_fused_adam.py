@@ -322,7 +322,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             g_arr = (ctypes.c_uint64 * 8)(seg.grad_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             p_arr = (ctypes.c_uint64 * 8)(seg.param_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             pads = (ctypes.c_uint64 * 8)(0, 0, 0, 0, 0, 0, 0, 0)
-        grid = 148 * 2
+        grid = 148 * (3 if D <= 2 else 2)
         cap = self.capturable
         self.kernel_launches += 1
         _lib.fn("ab_dist_adam_step")(

@@ -85,7 +85,7 @@ __device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
 // DP: compile-time bound on the number of peers looped over (1, 2, 4, 8); U: chunks whose remote gradient loads are issued
 // before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
 template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
-__global__ void __launch_bounds__(kDThreads, 2) dist_step_kernel(DistArgs a) {
+__global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_step_kernel(DistArgs a) {
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
   constexpr int PV = sizeof(TP) * 8 / 16;
   constexpr int NP = NVLS ? 1 : DP;        // gradient sources read per element

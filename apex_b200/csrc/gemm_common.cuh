@@ -1,0 +1,199 @@
+// Shared pieces of the tcgen05 GEMM kernels: parameters, PTX wrappers, descriptors, the fused epilogue.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <cstdio>
+
+namespace ab {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 x 16-bit = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;   // 8 warps
+constexpr int kEpiWarp0 = 4;
+
+enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_DGELU = 3, EPI_ACCUM = 4, EPI_BIAS_RELU = 5, EPI_BIAS_SIGMOID = 6,
+           EPI_RELU = 7, EPI_SIGMOID = 8 };
+
+struct Params {
+  int M, N, K;
+  void* D; long long ldd;          // output [M, N] row-major
+  const void* bias;                // [N] (dtype of D) or null
+  void* aux; long long ldaux;      // [M, N] pre-activation (dtype of D): written by BIAS_GELU, read by DGELU
+  const void* C; long long ldc;    // accumulate source (EPI_ACCUM), same dtype as D
+  int a_mn_major, b_mn_major;
+  int epi;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (with a message) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("apex_b200 gemm: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a_format [7,10), b_format [10,13),
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ inline uint32_t make_idesc(int is_bf16, int a_mn, int b_mn, int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;
+  d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;
+  d |= (uint32_t)(a_mn ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn ? 1 : 0) << 16;
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Epilogue of one accumulator tile for one thread-row: TMEM (32 columns at a time) -> registers -> fused op -> global.
+template <typename TOut, int BN>
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int acc, int row, int n_blk, int q) {
+  const bool row_ok = row < p.M;
+  TOut* drow = reinterpret_cast<TOut*>(p.D) + (size_t)row * p.ldd;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+    tmem_ld_wait();
+    const int col0 = n_blk * BN + c0;
+    if (row_ok && col0 < p.N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+      const bool full = (col0 + 32 <= p.N);
+      if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RELU || p.epi == EPI_BIAS_SIGMOID) {
+        const TOut* b = reinterpret_cast<const TOut*>(p.bias) + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (full || col0 + j < p.N) v[j] += to_f<TOut>(b[j]);
+      }
+      if (p.epi == EPI_BIAS_GELU) {
+        TOut* arow = reinterpret_cast<TOut*>(p.aux) + (size_t)row * p.ldaux + col0;
+        if (full && (sizeof(TOut) * p.ldaux) % 16 == 0) {
+          float tmp[8];
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) tmp[e] = v[j + e];
+            store_vec<TOut, 8>(arow + j, tmp);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) if (col0 + j < p.N) arow[j] = from_f<TOut>(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = gelu_f(to_f<TOut>(from_f<TOut>(v[j])));
+      } else if (p.epi == EPI_DGELU) {
+        const TOut* arow = reinterpret_cast<const TOut*>(p.aux) + (size_t)row * p.ldaux + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (full || col0 + j < p.N) v[j] *= dgelu_f(to_f<TOut>(arow[j]));
+      } else if (p.epi == EPI_ACCUM) {
+        const TOut* crow = reinterpret_cast<const TOut*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (full || col0 + j < p.N) v[j] += to_f<TOut>(crow[j]);
+      } else if (p.epi == EPI_BIAS_RELU || p.epi == EPI_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.epi == EPI_BIAS_SIGMOID || p.epi == EPI_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 1.f / (1.f + __expf(-v[j]));
+      }
+      if (full && (sizeof(TOut) * p.ldd) % 16 == 0 && aligned16(p.D)) {
+        float tmp[8];
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) tmp[e] = v[j + e];
+          store_vec<TOut, 8>(drow + col0 + j, tmp);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) if (col0 + j < p.N) drow[col0 + j] = from_f<TOut>(v[j]);
+      }
+    }
+  }
+}
+
+}  // namespace gemm
+}  // namespace ab

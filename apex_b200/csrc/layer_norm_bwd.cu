@@ -12,7 +12,7 @@ __device__ __forceinline__ float clamp_mag(float g, float eps) {
 
 // Tin: dtype of x and dx. Tout: dtype of dy, gamma, beta (and of y when MEMEFF).
 template <int MAXV, typename Tin, typename Tout, bool RMS, bool MEMEFF>
-__global__ void __launch_bounds__(256) ln_bwd_vec(const Tout* __restrict__ dy, const void* __restrict__ saved, const float* __restrict__ mean,
+__global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, const void* __restrict__ saved, const float* __restrict__ mean,
                            const float* __restrict__ invvar, const Tout* __restrict__ gamma, const Tout* __restrict__ beta,
                            Tin* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b, int n1, int n2,
                            float eps, int tpr) {
@@ -261,11 +261,11 @@ int ln_bwd_launch(const void* dy, const void* saved, const float* mean, const fl
   constexpr int E = 16 / sizeof(Tin);
   const bool vec_ok = (n2 % E == 0) && aligned16(dy) && aligned16(saved) && aligned16(dx) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 &&
                       ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
-  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 4, 256);
+  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 2, 512);
   const bool small_rows_ok = c.rows_per_cta == 1 || n2 <= 4096;
   if (vec_ok && c.ok && small_rows_ok && ws != nullptr) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
-    const int cap = kNumSMs * 2;
+    const int cap = kNumSMs * (512 / c.threads);
     if (grid > cap) grid = cap;
     float* part_g = dgamma ? ws : nullptr;
     float* part_b = (dgamma && dbeta) ? ws + (size_t)cap * n2 : nullptr;
