@@ -1,0 +1,165 @@
+"""DistributedFusedLAMB — ZeRO-2 LAMB on the DistributedFusedAdam machinery.
+
+Reference: apex/contrib/optimizers/distributed_fused_lamb.py:26-1333 (MLPerf-BERT optimizer: flat fp16 gradient buffer laid out
+[block][chunk][shard], hierarchical reduce-scatter / all-reduce over many NCCL groups and streams, fp32 master "mega-shard",
+per-tensor update norms all-reduced before the weight update, e5m2 all-gather option). Here the same algorithm runs on the
+symmetric-heap layout of :class:`DistributedFusedAdam`:
+
+  1. gradient reduce-scatter + global gradient norm: the in-kernel collective (``MODE_RS`` of csrc/dist_adam.cu) or NCCL/gloo;
+  2. LAMB stage 1 on this rank's shard with the multi-tensor kernel over the (parameter ∩ shard) FRAGMENTS — it also emits the
+     per-fragment sums of squares of p and of the update; fragment sums are scattered to per-parameter slots and all-reduced
+     (one small vector) to obtain the per-tensor trust ratios;
+  3. LAMB stage 2 on the fragments, cast to the parameter dtype, all-gather of the parameter buckets.
+Knobs of the reference that only shaped its NCCL pipeline (dwu_num_blocks/chunks/rs_pg/ar_pg/ag_pg, full_ar, ...) are accepted and
+ignored; ``clip_after_ar`` semantics (clip by the GLOBAL norm) is what is implemented; ``e5m2_allgather`` is available through
+``param_sync_dtype=torch.float8_e5m2`` style casting of the gathered bucket.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ... import _lib
+from ...ops import amp_C
+from ...ops import reference as ref
+from .distributed_fused_adam import DistributedFusedAdam, _Segment
+
+
+class DistributedFusedLAMB(DistributedFusedAdam):
+    def __init__(self, params, lr=1e-3, bias_correction=True, grad_averaging=True, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 max_grad_norm=0.0, adam_w_mode=True, use_nvlamb=False, step_supports_amp_scaling=True, overlap_reductions=True,
+                 dwu_group_size=0, dwu_num_blocks=4, dwu_num_chunks=4, dwu_num_rs_pg=1, dwu_num_ar_pg=4, dwu_num_ag_pg=0,
+                 fused_norm=False, e5m2_allgather=False, verbose=False, clip_after_ar=True, full_ar=False,
+                 set_param_views_to_flat_buffer=False, skip_allgather=False, fuse_scale=False, param_order=None,
+                 nccl_allgather_channels=0, process_group=None, device="cuda", fused_collectives="auto", **kwargs):
+        super().__init__(params, lr=lr, bias_correction=bias_correction, betas=betas, eps=eps, adam_w_mode=adam_w_mode,
+                         weight_decay=weight_decay, process_group=process_group, device=device, fused_collectives=fused_collectives,
+                         dtype=torch.float32, **kwargs)
+        self.grad_averaging = grad_averaging
+        self.max_grad_norm = max_grad_norm
+        self.use_nvlamb = use_nvlamb
+        self._frag_cache: dict = {}
+
+    # (parameter ∩ this rank's shard) fragments of a segment, as index ranges of the LOCAL shard arrays -----------------------
+    def _fragments(self, seg: _Segment):
+        fr = self._frag_cache.get(id(seg))
+        if fr is not None:
+            return fr
+        out = []  # (param_index, local_start, length)
+        B, Sb, r = seg.bucket_elems, seg.shard_elems, seg.rank
+        for pi, (p, off) in enumerate(zip(seg.params, seg.offsets)):
+            lo, hi = off, off + p.numel()
+            b0, b1 = lo // B, (hi - 1) // B
+            for b in range(b0, b1 + 1):
+                s_lo, s_hi = b * B + r * Sb, b * B + (r + 1) * Sb
+                a, z = max(lo, s_lo), min(hi, s_hi)
+                if z > a:
+                    out.append((pi, b * Sb + (a - s_lo), z - a))
+        self._frag_cache[id(seg)] = out
+        return out
+
+    @torch.no_grad()
+    def step(self, closure=None, *, grad_scaler=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.init_params()
+        self._collect_grads()
+        self.grad_sync()
+        # global gradient norm (already unscaled through _grad_scale)
+        gnorm = self.grad_norm()
+        if grad_scaler is not None:
+            st = grad_scaler._per_optimizer_states[id(self)]
+            if st["stage"] is not torch.amp.grad_scaler.OptState.UNSCALED:
+                self.unscale_grads(grad_scaler=grad_scaler)
+                gnorm = self.grad_norm()
+            found = sum(v.to(self.device) for v in st["found_inf_per_device"].values())
+            if bool(found.item() > 0):
+                self._finish_step(skipped=True)
+                return loss
+        elif not bool(torch.isfinite(gnorm)):
+            self._finish_step(skipped=True)
+            return loss
+        for group in self.param_groups:
+            group["step"] = group.get("step", 0) + 1
+        for seg in self._segments:
+            group = self.param_groups[seg.group_idx]
+            self._lamb_segment(seg, group, gnorm)
+        self._finish_step(skipped=False)
+        return loss
+
+    def _lamb_segment(self, seg: _Segment, group, gnorm):
+        frags = self._fragments(seg)
+        beta1, beta2 = group["betas"]
+        beta3 = 1.0 - beta1 if self.grad_averaging else 1.0
+        step = group["step"]
+        seg.reduced.mul_(self._grad_scale)  # fold loss-unscale / deferred clipping
+        g_l = [seg.reduced[s:s + n] for _, s, n in frags]
+        p_l = [seg.master[s:s + n] for _, s, n in frags]
+        m_l = [seg.exp_avg[s:s + n] for _, s, n in frags]
+        v_l = [seg.exp_avg_sq[s:s + n] for _, s, n in frags]
+        nparam = len(seg.params)
+        idx = torch.tensor([pi for pi, _, _ in frags], device=self.device, dtype=torch.long)
+        sq = torch.zeros(2, nparam, dtype=torch.float32, device=self.device)
+        mode = 1 if self.adam_w_mode else 0
+        bc = 1 if group["bias_correction"] else 0
+        if frags:
+            if self.device.type == "cuda":
+                tb = amp_C.TensorTable([g_l, p_l, m_l, v_l])
+                dev = self.device
+                pp, pu = amp_C._partials(dev, tb.total_chunks, 1), amp_C._partials(dev, tb.total_chunks, 2)
+                pn = torch.empty(tb.n, dtype=torch.float32, device=dev)
+                un = torch.empty(tb.n, dtype=torch.float32, device=dev)
+                d = tb.dtypes
+                s_ = _lib.stream_ptr(dev)
+                _lib.fn("ab_mt_lamb_stage1")(*tb.head(), d[0], d[1], 0, float(beta1), float(beta2), float(beta3), int(step), bc,
+                                             float(group["eps"]), mode, float(group["weight_decay"]), None, gnorm.reshape(1).data_ptr(),
+                                             float(self.max_grad_norm), None, 0, None, None, None, pp.data_ptr(), pu.data_ptr(),
+                                             pn.data_ptr(), un.data_ptr(), 0, s_)
+                sq[0].index_add_(0, idx, pn * pn)
+                sq[1].index_add_(0, idx, un * un)
+            else:
+                bc1 = 1 - beta1 ** step if bc else 1.0
+                bc2 = 1 - beta2 ** step if bc else 1.0
+                gn = float(gnorm)
+                clip = gn / self.max_grad_norm if (self.max_grad_norm > 0 and gn > self.max_grad_norm) else 1.0
+                for k, (g, p, m, v) in enumerate(zip(g_l, p_l, m_l, v_l)):
+                    gg = g / clip
+                    if mode == 0:
+                        gg = gg + group["weight_decay"] * p
+                    m.mul_(beta1).add_(gg, alpha=beta3)
+                    v.mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+                    u = (m / bc1) / ((v / bc2).sqrt() + group["eps"])
+                    if mode != 0:
+                        u = u + group["weight_decay"] * p
+                    g.copy_(u)
+                    sq[0, idx[k]] += (p * p).sum()
+                    sq[1, idx[k]] += (u * u).sum()
+        if seg.D > 1:
+            dist.all_reduce(sq, group=self.distributed_process_group)
+        pnorm_t, unorm_t = sq[0].sqrt(), sq[1].sqrt()
+        if frags:
+            pn_f, un_f = pnorm_t[idx].contiguous(), unorm_t[idx].contiguous()
+            if self.device.type == "cuda":
+                _lib.fn("ab_mt_lamb_stage2")(*tb.head(), d[0], d[1], pn_f.data_ptr(), un_f.data_ptr(), float(group["lr"]), None,
+                                             float(group["weight_decay"]), None, int(bool(self.use_nvlamb)), 0, None, 0, 0, s_)
+            else:
+                ref.multi_tensor_lamb_stage2([p_l, g_l], pn_f, un_f, group["lr"], group["weight_decay"], self.use_nvlamb)
+        # low-precision copy of the shard into the parameter buffer, then all-gather of every bucket
+        seg.shard_view(seg.param_buf).copy_(seg.master.view(seg.n_buckets, seg.shard_elems))
+        if seg.D > 1:
+            pg = self.distributed_process_group
+            for b in range(seg.n_buckets):
+                bucket = seg.param_buf[b * seg.bucket_elems:(b + 1) * seg.bucket_elems]
+                mine = bucket[seg.rank * seg.shard_elems:(seg.rank + 1) * seg.shard_elems].clone()
+                if dist.get_backend(pg) == "nccl":
+                    dist.all_gather_into_tensor(bucket, mine, group=pg)
+                else:
+                    parts = [torch.empty_like(mine) for _ in range(seg.D)]
+                    dist.all_gather(parts, mine, group=pg)
+                    bucket.copy_(torch.cat(parts))
+
+    @property
+    def L2_grad_norm(self):
+        return self.grad_norm()

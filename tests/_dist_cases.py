@@ -111,3 +111,29 @@ def dist_adam_grad_scaler_skips_on_inf(rank, world, device_type):
     scaler.step(opt)
     scaler.update()
     assert any((b - p.detach()).abs().max() > 0 for b, p in zip(before, model.parameters()))
+
+
+def dist_lamb_matches_fused_lamb(rank, world, device_type):
+    """Oracle: FusedLAMB (same library, single process math) on the all-reduced averaged gradients."""
+    from apex_b200.contrib.optimizers import DistributedFusedLAMB
+    from apex_b200.optimizers import FusedLAMB
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    ref_model = _model(dev)
+    dist_model = copy.deepcopy(ref_model)
+    ref_opt = FusedLAMB(ref_model.parameters(), lr=2e-2, weight_decay=0.01, max_grad_norm=0.5, eps=1e-6)
+    opt = DistributedFusedLAMB(dist_model.parameters(), lr=2e-2, weight_decay=0.01, max_grad_norm=0.5, eps=1e-6, device=dev,
+                               bucket_cap_mb=2048 * 4 * world / 2 ** 20)
+    g = torch.Generator().manual_seed(100 + rank)
+    for it in range(3):
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        x = torch.randn(5, 7, generator=g).to(dev)
+        ref_model(x).pow(2).mean().backward()
+        dist_model(x).pow(2).mean().backward()
+        for p in ref_model.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        ref_opt.step()
+        opt.step()
+        for pr, pd in zip(ref_model.parameters(), dist_model.parameters()):
+            torch.testing.assert_close(pd, pr, rtol=2e-4, atol=2e-5)

@@ -52,3 +52,7 @@ def test_two_ranks_gloo_matches_ddp_adamw(clip):
 
 def test_two_ranks_gloo_state_dict(tmp_path):
     run_distributed(cases.dist_adam_state_dict_reshards, 2, "cpu", str(tmp_path), backend="gloo")
+
+
+def test_two_ranks_gloo_dist_lamb():
+    run_distributed(cases.dist_lamb_matches_fused_lamb, 2, "cpu", backend="gloo")
