@@ -1,0 +1,168 @@
+"""Self / encoder-decoder multi-head attention modules. Reference: apex/contrib/multihead_attn/{self,encdec}_multihead_attn.py and
+the 16 ``fast_multihead_attn`` entry points (multihead_attn_frontend.cpp:573-605: cuBLAS strided-batched GEMMs / CUTLASS 1.x +
+softmax+dropout kernels, optional pre-LayerNorm + residual add + dropout).
+
+Same constructor / forward contract ([time, batch, channel] inputs, ``key_padding_mask`` or ``attn_mask``, additive or boolean masks,
+``include_norm_add`` pre-LN residual variant, ``impl`` in {"fast", "default"}). On B200 both impls run: input/output projections on
+the tcgen05 GEMM (apex_b200.ops.gemm through fused_dense_function), pre-LN on the fused LayerNorm kernel, the score softmax on the
+scaled-masked-softmax kernel; the two batched score/context products use torch.bmm (cuBLAS, a plain library GEMM)."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import Parameter
+
+from ...fused_dense import fused_dense_function
+from ...normalization import FusedLayerNorm
+from ...transformer.functional import scaled_masked_softmax, scaled_softmax
+
+
+def fast_mask_softmax_dropout_func(is_training, heads, inputs, pad_mask, mask_additive, dropout_prob):
+    """softmax(inputs + mask) -> dropout. inputs [b*heads, sq, sk]; pad_mask [b, sk] (bool/uint8 = masked, or additive float)."""
+    bh, sq, sk = inputs.shape
+    b = bh // heads
+    x = inputs.view(b, heads, sq, sk)
+    if pad_mask is not None and mask_additive:
+        x = x + pad_mask.view(b, 1, 1, sk).to(x.dtype)
+        p = scaled_softmax(x, 1.0)
+    elif pad_mask is not None:
+        p = scaled_masked_softmax(x, pad_mask.view(b, 1, 1, sk).expand(b, 1, sq, sk).to(torch.uint8), 1.0)
+    else:
+        p = scaled_softmax(x, 1.0)
+    p = F.dropout(p, dropout_prob, is_training)
+    return p.view(bh, sq, sk)
+
+
+def _attention(q, k, v, heads, scaling, key_padding_mask, attn_mask, mask_additive, dropout, training):
+    """q [tq, b, e]; k, v [tk, b, e] -> [tq, b, e]"""
+    tq, b, e = q.shape
+    tk = k.shape[0]
+    hd = e // heads
+    q = q.contiguous().view(tq, b * heads, hd).transpose(0, 1)
+    k = k.contiguous().view(tk, b * heads, hd).transpose(0, 1)
+    v = v.contiguous().view(tk, b * heads, hd).transpose(0, 1)
+    scores = torch.bmm(q, k.transpose(1, 2)) * scaling                 # [b*h, tq, tk]
+    x = scores.view(b, heads, tq, tk)
+    if attn_mask is not None:                                          # time mask [tq, tk] (e.g. causal): True/1 = masked
+        m = attn_mask.to(torch.bool).view(1, 1, tq, tk).expand(b, 1, tq, tk).to(torch.uint8)
+        p = scaled_masked_softmax(x, m, 1.0)
+    elif key_padding_mask is not None and mask_additive:
+        p = scaled_softmax(x + key_padding_mask.view(b, 1, 1, tk).to(x.dtype), 1.0)
+    elif key_padding_mask is not None:
+        m = key_padding_mask.to(torch.bool).view(b, 1, 1, tk).expand(b, 1, tq, tk).to(torch.uint8)
+        p = scaled_masked_softmax(x, m, 1.0)
+    else:
+        p = scaled_softmax(x, 1.0)
+    p = F.dropout(p, dropout, training).view(b * heads, tq, tk)
+    ctx = torch.bmm(p.to(v.dtype), v)                                   # [b*h, tq, hd]
+    return ctx.transpose(0, 1).contiguous().view(tq, b, e)
+
+
+class _MHABase(nn.Module):
+    def _post(self, outputs, query, is_training):
+        if self.include_norm_add:
+            outputs = F.dropout(outputs, self.dropout, is_training) + query
+        return outputs
+
+
+class SelfMultiheadAttn(_MHABase):
+    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=False, include_norm_add=False, impl="fast", separate_qkv_params=False,
+                 mask_additive=False):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, dropout
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        assert impl in ("fast", "default"), f"Unsupported impl: {impl} !"
+        self.bias, self.include_norm_add, self.impl = bias, include_norm_add, impl
+        self.scaling = self.head_dim ** -0.5
+        self.separate_qkv_params, self.mask_additive = separate_qkv_params, mask_additive
+        if mask_additive:
+            assert not include_norm_add, "additive mask not supported with layer norm"
+        if separate_qkv_params:
+            self.q_weight = Parameter(torch.empty(embed_dim, embed_dim))
+            self.k_weight = Parameter(torch.empty(embed_dim, embed_dim))
+            self.v_weight = Parameter(torch.empty(embed_dim, embed_dim))
+        else:
+            self.in_proj_weight = Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.out_proj_weight = Parameter(torch.empty(embed_dim, embed_dim))
+        if bias:
+            if separate_qkv_params:
+                self.q_bias, self.k_bias, self.v_bias = (Parameter(torch.empty(embed_dim)) for _ in range(3))
+            else:
+                self.in_proj_bias = Parameter(torch.empty(3 * embed_dim))
+            self.out_proj_bias = Parameter(torch.empty(embed_dim))
+        else:
+            for n in (("q_bias", "k_bias", "v_bias") if separate_qkv_params else ("in_proj_bias",)) + ("out_proj_bias",):
+                self.register_parameter(n, None)
+        self.lyr_nrm = FusedLayerNorm(embed_dim) if include_norm_add else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.separate_qkv_params:
+            for w in (self.q_weight, self.k_weight, self.v_weight):
+                nn.init.xavier_uniform_(w)
+        else:
+            nn.init.xavier_uniform_(self.in_proj_weight, gain=math.sqrt(2))
+        nn.init.xavier_uniform_(self.out_proj_weight)
+        for n in ("q_bias", "k_bias", "v_bias", "in_proj_bias", "out_proj_bias"):
+            b = getattr(self, n, None)
+            if b is not None:
+                nn.init.constant_(b, 0.0)
+
+    def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=False, attn_mask=None, is_training=True):
+        x = self.lyr_nrm(query) if self.include_norm_add else query
+        if self.separate_qkv_params:
+            w = torch.cat((self.q_weight, self.k_weight, self.v_weight), 0)
+            bias = torch.cat((self.q_bias, self.k_bias, self.v_bias), 0) if self.bias else None
+        else:
+            w, bias = self.in_proj_weight, self.in_proj_bias
+        qkv = fused_dense_function(x, w, bias)                          # [t, b, 3e]
+        q, k, v = qkv.chunk(3, dim=-1)
+        ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, self.mask_additive, self.dropout, is_training)
+        out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
+        return self._post(out, query, is_training), None
+
+
+class EncdecMultiheadAttn(_MHABase):
+    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=False, include_norm_add=False, impl="fast"):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, dropout
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        assert impl in ("fast", "default"), f"Unsupported impl: {impl} !"
+        self.bias, self.include_norm_add, self.impl = bias, include_norm_add, impl
+        self.scaling = self.head_dim ** -0.5
+        self.mask_additive = False
+        self.in_proj_weight_q = Parameter(torch.empty(embed_dim, embed_dim))
+        self.in_proj_weight_kv = Parameter(torch.empty(2 * embed_dim, embed_dim))
+        self.out_proj_weight = Parameter(torch.empty(embed_dim, embed_dim))
+        if bias:
+            self.in_proj_bias_q = Parameter(torch.empty(embed_dim))
+            self.in_proj_bias_kv = Parameter(torch.empty(2 * embed_dim))
+            self.out_proj_bias = Parameter(torch.empty(embed_dim))
+        else:
+            for n in ("in_proj_bias_q", "in_proj_bias_kv", "out_proj_bias"):
+                self.register_parameter(n, None)
+        self.lyr_nrm = FusedLayerNorm(embed_dim) if include_norm_add else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.in_proj_weight_q)
+        nn.init.xavier_uniform_(self.in_proj_weight_kv, gain=math.sqrt(1.5))
+        nn.init.xavier_uniform_(self.out_proj_weight)
+        for n in ("in_proj_bias_q", "in_proj_bias_kv", "out_proj_bias"):
+            b = getattr(self, n, None)
+            if b is not None:
+                nn.init.constant_(b, 0.0)
+
+    def forward(self, query, key, value=None, key_padding_mask=None, need_weights=False, attn_mask=None, is_training=True):
+        x = self.lyr_nrm(query) if self.include_norm_add else query
+        q = fused_dense_function(x, self.in_proj_weight_q, self.in_proj_bias_q)
+        kv = fused_dense_function(key, self.in_proj_weight_kv, self.in_proj_bias_kv)
+        k, v = kv.chunk(2, dim=-1)
+        ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, False, self.dropout, is_training)
+        out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
+        return self._post(out, query, is_training), None
