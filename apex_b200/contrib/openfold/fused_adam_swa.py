@@ -1,0 +1,80 @@
+"""FusedAdamSWA: Adam on fp32 params + bf16 compute copy + stochastic-weight-average update in two persistent launches.
+Reference: apex/contrib/openfold_triton/fused_adam_swa.py:209-400 (one Triton multi-tensor kernel over pointer tables)."""
+from __future__ import annotations
+
+from enum import Enum, unique
+from itertools import chain
+
+import torch
+from torch.optim import Optimizer
+
+from ...ops import amp_C
+from ...ops import reference as ref
+
+
+@unique
+class AdamMathType(Enum):
+    ApexAdam = 0
+    ApexAdamW = 1
+    PyTorchAdam = 2
+
+
+class FusedAdamSWA(Optimizer):
+    def __init__(self, params, compute_params, swa_params, swa_decay_rate, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-8,
+                 adam_math_mode=AdamMathType.PyTorchAdam, weight_decay=0.0, amsgrad=False, set_grad_none=True, capturable=False,
+                 master_weights=False):
+        params, compute_params, swa_params = list(params), list(compute_params), list(swa_params)
+        if not compute_params or not swa_params:
+            raise ValueError("FusedAdamSWA requires both BF16 and SWA parameters.")
+        if not len(params) == len(compute_params) == len(swa_params):
+            raise ValueError("FusedAdamSWA expects params, bf16_params, and swa_params to have same length")
+        if not all(p.shape == b.shape == s.shape for p, b, s in zip(params, compute_params, swa_params)):
+            raise ValueError("FusedAdamSWA expects each state in params, bf16_params, abd swa_params to have same shape")
+        if not all(p.is_contiguous() for p in chain(params, compute_params, swa_params)):
+            raise ValueError("FusedAdamSWA expects all input params to be contiguous")
+        if amsgrad or capturable or master_weights:
+            raise NotImplementedError("amsgrad / capturable / master_weights are not supported by FusedAdamSWA")
+        if not isinstance(adam_math_mode, AdamMathType):
+            raise ValueError(f"Unknown Adam math mode {adam_math_mode}")
+        super().__init__(params, dict(lr=lr, bias_correction=bias_correction, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.adam_math_mode, self.set_grad_none = adam_math_mode, set_grad_none
+        self.compute_param_groups = [{"params": compute_params}]
+        self.swa_param_groups = [{"params": swa_params, "n_averaged": 0}]
+        self.swa_decay_rate = swa_decay_rate
+        self._tables = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedAdamSWA does not support multiple param groups")
+        loss = closure() if closure is not None else None
+        group = self.param_groups[0]
+        params, cparams, sparams = group["params"], self.compute_param_groups[0]["params"], self.swa_param_groups[0]["params"]
+        group["step"] = group.get("step", 0) + 1
+        for p in params:
+            st = self.state[p]
+            if not st:
+                st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32), torch.zeros_like(p, dtype=torch.float32)
+        # gradients come from the bf16 compute copies (OpenFold runs fwd/bwd on them)
+        grads = [(c.grad if c.grad is not None else p.grad) for p, c in zip(params, cparams)]
+        lists = [grads, params, [self.state[p]["exp_avg"] for p in params], [self.state[p]["exp_avg_sq"] for p in params]]
+        beta1, beta2 = group["betas"]
+        mode = 1 if self.adam_math_mode == AdamMathType.ApexAdamW else 0
+        cuda = params[0].is_cuda
+        if cuda:
+            amp_C.multi_tensor_adam(65536, None, lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode,
+                                    int(group["bias_correction"]), group["weight_decay"])
+        else:
+            ref.multi_tensor_adam(lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode, int(group["bias_correction"]),
+                                  group["weight_decay"])
+        # SWA: first step copies, later steps swa += (1 - decay) * (p - swa); then the bf16 compute copy
+        n = self.swa_param_groups[0]["n_averaged"]
+        a, b = (0.0, 1.0) if n == 0 else (self.swa_decay_rate, 1.0 - self.swa_decay_rate)
+        noop = torch.zeros(1, dtype=torch.int32, device=params[0].device)
+        amp_C.multi_tensor_axpby(65536, noop, [sparams, params, sparams], a, b, -1)
+        amp_C.multi_tensor_scale(65536, noop, [params, cparams], 1.0)
+        self.swa_param_groups[0]["n_averaged"] = n + 1
+        if self.set_grad_none:
+            for c in cparams:
+                c.grad = None
+        return loss
