@@ -1,9 +1,5 @@
 from .distributed_fused_adam import DistributedFusedAdam
+from .distributed_fused_lamb import DistributedFusedLAMB
+from .legacy import FP16_Optimizer, FusedAdam, FusedLAMB, FusedSGD
 
-__all__ = ["DistributedFusedAdam"]
-try:
-    from .distributed_fused_lamb import DistributedFusedLAMB  # noqa: F401
-
-    __all__.append("DistributedFusedLAMB")
-except ImportError:
-    pass
+__all__ = ["DistributedFusedAdam", "DistributedFusedLAMB", "FusedAdam", "FusedLAMB", "FusedSGD", "FP16_Optimizer"]
