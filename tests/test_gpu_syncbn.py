@@ -114,3 +114,39 @@ def test_two_gpus_match_concatenated_batchnorm(cuda_dev, uneven, channels_last):
     _need(2)
     from apex_b200.testing.dist_harness import run_distributed
     run_distributed(_two_gpu_case, 2, uneven, channels_last, backend="nccl")
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_functional_ops(cuda_dev, channels_last, dtype):
+    """welford_mean_var -> welford_parallel -> batchnorm_forward, reduce_bn -> batchnorm_backward (csrc/syncbn.cpp:71-89)."""
+    from apex_b200.parallel import syncbn_ops as S
+    torch.manual_seed(1)
+    x = (torch.randn(6, 40, 9, 11, device=cuda_dev) * 1.5 + 0.7).to(dtype)
+    dy = torch.randn_like(x)
+    if channels_last:
+        x, dy = x.contiguous(memory_format=torch.channels_last), dy.contiguous(memory_format=torch.channels_last)
+    w = torch.rand(40, device=cuda_dev) + 0.5
+    b = torch.randn(40, device=cuda_dev)
+    mean, var = S.welford_mean_var(x)
+    xf = x.float().transpose(0, 1).reshape(40, -1)
+    torch.testing.assert_close(mean, xf.mean(1), atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(var, xf.var(1, unbiased=False), atol=1e-4, rtol=1e-3)
+    n = x.numel() // 40
+    m2, var_u, istd = S.welford_parallel(mean[None], var[None], torch.tensor([n], device=cuda_dev), 1e-5)
+    torch.testing.assert_close(var_u, xf.var(1, unbiased=True), atol=1e-4, rtol=1e-3)
+    y = S.batchnorm_forward(x, m2, istd, w, b)
+    xr = x.float().detach().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(xr, None, None, w, b, True, 0.0, 1e-5)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    torch.testing.assert_close(y.float(), ref, atol=tol, rtol=tol)
+    ref.backward(dy.float())
+    sdy, sdx, gw, gb = S.reduce_bn(dy, x, m2, istd, w)
+    dx = S.batchnorm_backward(dy, x, m2, istd, w, sdy, sdx, torch.tensor([n], device=cuda_dev))
+    torch.testing.assert_close(dx.float(), xr.grad, atol=tol * 5, rtol=tol * 5)
+    torch.testing.assert_close(gb, dy.float().sum((0, 2, 3)), atol=1e-2, rtol=1e-3)
+    z = torch.randn_like(x)
+    yz = S.batchnorm_forward_c_last(x, z, m2, istd, w, b, True)
+    torch.testing.assert_close(yz.float(), (ref.detach() + z.float()).relu(), atol=tol, rtol=tol)
+    g = S.relu_bw_c_last(dy, x, z, m2, istd, w, b)
+    torch.testing.assert_close(g.float(), torch.where(ref.detach() + z.float() > 0, dy.float(), torch.zeros_like(dy.float())), atol=0, rtol=0)
