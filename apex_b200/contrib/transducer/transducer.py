@@ -2,15 +2,23 @@
 (apex/contrib/csrc/transducer/*.cu). Same module signatures and semantics (padding mask from f_len / g_len, optional packed output
 with ``batch_offset``, ReLU / dropout on the joint, blank index, per-utterance negative log-likelihood).
 
-The joint is a broadcast add (+ReLU, +dropout) in one fused elementwise expression; the loss runs the alpha recursion over
-anti-diagonals of the (T, U) lattice, vectorised over the batch and the diagonal, in log space — T+U-1 small steps instead of a
-thread-per-cell CUDA kernel. Gradients come from autograd through the same recursion (exactly the beta recursion)."""
+On CUDA tensors both modules run the sm_100a kernels of csrc/transducer.cu (joint: one vectorised pass + one launch for both
+backward reductions; loss: log-sum-exp per lattice cell, alpha/beta along anti-diagonals with a CTA per (utterance, direction),
+backward fused with the softmax backward, no materialised log-softmax). On CPU tensors the ``_Torch*`` oracles below run: the same
+math in PyTorch ops (anti-diagonal alpha recursion vectorised over the batch; gradients through autograd)."""
 from __future__ import annotations
 
 import torch
 
+from ... import _lib
 
-class TransducerJoint(torch.nn.Module):
+_lib.declare("ab_transducer_joint_fwd", "p p p p p p p i i i i i l i f l i p")
+_lib.declare("ab_transducer_joint_bwd", "p p p p p p p i i i i i f i p")
+_lib.declare("ab_transducer_loss_fwd", "p p p p p p p p p i i i i i i l i p")
+_lib.declare("ab_transducer_loss_bwd", "p p p p p p p p p p i i i i i i i p")
+
+
+class _TorchTransducerJoint(torch.nn.Module):
     def __init__(self, pack_output=False, relu=False, dropout=False, opt=1, fwd_tile_size=4, dropout_prob=0, probe_mask=False):
         super().__init__()
         self.pack_output, self.relu, self.dropout, self.dropout_prob = pack_output, relu, dropout, dropout_prob
@@ -38,7 +46,7 @@ class TransducerJoint(torch.nn.Module):
         return h * valid.unsqueeze(-1).to(h.dtype)
 
 
-class TransducerLoss(torch.nn.Module):
+class _TorchTransducerLoss(torch.nn.Module):
     def __init__(self, fuse_softmax_backward=True, opt=1, packed_input=False):
         super().__init__()
         self.packed_input = packed_input
@@ -95,3 +103,100 @@ class TransducerLoss(torch.nn.Module):
             t_lo = max(0, d - (U - 1))
             out.append(-(diag[d][b, t - t_lo] + blank[b, t, u]))
         return torch.stack(out).to(x.dtype if x.dtype == torch.float32 else torch.float32)
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+class _JointFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, g, f_len, g_len, batch_offset, packed_batch, pack, relu, drop_p, probe):
+        f, g = f.contiguous(), g.contiguous()
+        B, T, H = f.shape
+        U = g.shape[1]
+        fl, gl = _i32(f_len), _i32(g_len)
+        bo = batch_offset.to(torch.int64).contiguous() if pack else None
+        rows = int(packed_batch) if pack else B * T * U
+        out = torch.empty((rows, H) if pack else (B, T, U, H), dtype=f.dtype, device=f.device)
+        need_mask = relu or drop_p > 0
+        mask = torch.empty(rows * H, dtype=torch.uint8, device=f.device) if need_mask else None
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if drop_p > 0 else 0
+        _lib.fn("ab_transducer_joint_fwd")(f.data_ptr(), g.data_ptr(), out.data_ptr(), _lib.ptr(mask), fl.data_ptr(), gl.data_ptr(),
+                                           _lib.ptr(bo), B, T, U, H, int(pack), rows, int(relu), float(drop_p), seed, _lib.dt(f),
+                                           _lib.stream_ptr(f.device))
+        ctx.save_for_backward(mask, fl, gl, bo)
+        ctx.dims = (B, T, U, H, pack, 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0)
+        if probe is not None and mask is not None:
+            probe.append(mask.view(out.shape).bool())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mask, fl, gl, bo = ctx.saved_tensors
+        B, T, U, H, pack, scale = ctx.dims
+        dout = dout.contiguous()
+        df = torch.empty(B, T, H, dtype=dout.dtype, device=dout.device)
+        dg = torch.empty(B, U, H, dtype=dout.dtype, device=dout.device)
+        _lib.fn("ab_transducer_joint_bwd")(dout.data_ptr(), _lib.ptr(mask), df.data_ptr(), dg.data_ptr(), fl.data_ptr(), gl.data_ptr(),
+                                           _lib.ptr(bo), B, T, U, H, int(pack), float(scale), _lib.dt(dout), _lib.stream_ptr(dout.device))
+        return df, dg, None, None, None, None, None, None, None, None
+
+
+class TransducerJoint(_TorchTransducerJoint):
+    """f [B, T, H] + g [B, U, H] -> [B, T, U, H] (padding zeroed) or packed [sum_b f_len*g_len, H] (reference transducer.py:6-86)."""
+
+    def forward(self, f, g, f_len, g_len, batch_offset=None, packed_batch=0):
+        if not (f.is_cuda and _lib.available()):
+            return super().forward(f, g, f_len, g_len, batch_offset, packed_batch)
+        if self.pack_output and (batch_offset is None or packed_batch == 0):
+            raise Exception("Please specify batch_offset and packed_batch when packing is enabled")
+        p = float(self.dropout_prob) if (self.dropout and self.training) else 0.0
+        self.mask_probe = []
+        return _JointFn.apply(f, g, f_len, g_len, batch_offset, packed_batch, self.pack_output, self.relu, p,
+                              self.mask_probe if self.probe_mask else None)
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label, f_len, y_len, batch_offset, max_f_len, blank_idx, packed):
+        x = x.contiguous()
+        B, U = label.shape[0], label.shape[1] + 1
+        T = int(max_f_len) if packed else x.shape[1]
+        V = x.shape[-1]
+        rows = x.numel() // V
+        dev = x.device
+        lab, fl, yl = _i32(label), _i32(f_len), _i32(y_len)
+        bo = batch_offset.to(torch.int64).contiguous() if packed else None
+        lse = torch.empty(rows, dtype=torch.float32, device=dev)
+        alpha = torch.empty(B, T, U, dtype=torch.float32, device=dev)
+        beta = torch.empty(B, T, U, dtype=torch.float32, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib.fn("ab_transducer_loss_fwd")(x.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(), loss.data_ptr(), lab.data_ptr(),
+                                          fl.data_ptr(), yl.data_ptr(), _lib.ptr(bo), B, T, U, V, int(blank_idx), int(packed), rows,
+                                          _lib.dt(x), _lib.stream_ptr(dev))
+        ctx.save_for_backward(x, lse, alpha, beta, lab, fl, yl, bo)
+        ctx.dims = (B, T, U, V, int(blank_idx), int(packed))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x, lse, alpha, beta, lab, fl, yl, bo = ctx.saved_tensors
+        B, T, U, V, blank, packed = ctx.dims
+        dx = torch.empty_like(x)
+        g = gloss.float().contiguous()
+        _lib.fn("ab_transducer_loss_bwd")(x.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(), g.data_ptr(), dx.data_ptr(),
+                                          lab.data_ptr(), fl.data_ptr(), yl.data_ptr(), _lib.ptr(bo), B, T, U, V, blank, packed,
+                                          _lib.dt(x), _lib.stream_ptr(x.device))
+        return dx, None, None, None, None, None, None, None
+
+
+class TransducerLoss(_TorchTransducerLoss):
+    """-log p(y | x) per utterance from joint logits x [B, T, U, V] (or packed [N, V]) (reference transducer.py:88-195)."""
+
+    def forward(self, x, label, f_len, y_len, blank_idx, batch_offset=None, max_f_len=None, debug_list=None):
+        if not (x.is_cuda and _lib.available()):
+            return super().forward(x, label, f_len, y_len, blank_idx, batch_offset, max_f_len, debug_list)
+        if self.packed_input and (batch_offset is None or max_f_len is None):
+            raise Exception("Please specify batch_offset and max_f_len when packing is enabled")
+        return _LossFn.apply(x, label, f_len, y_len, batch_offset, max_f_len, blank_idx, self.packed_input)
