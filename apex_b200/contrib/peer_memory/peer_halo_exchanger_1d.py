@@ -1,13 +1,19 @@
 """1-D halo exchange through peer memory. Reference: apex/contrib/peer_memory/peer_halo_exchanger_1d.py:5-84 over
 ``push_pull_halos_1d`` (peer_memory_cuda.cu:146-295: 16-byte "flit" stores carrying payload + flag into the neighbour's buffer and
-a volatile spin on the local one). Here each rank writes its two outgoing halos straight into the neighbours' transfer buffers
-with P2P copies over NVLink, a device-side epoch barrier on the signal pad (no NCCL, no host sync) orders them, and the incoming
-halos are copied from the local transfer buffers into the padded tensor."""
+a volatile spin on the local one, cooperative launch). Here the whole exchange is ONE launch of csrc/halo_exchange.cu: the two
+outgoing slabs are packed straight into the neighbours' transfer buffers with 16-byte P2P stores over NVLink, an epoch word per
+neighbour (release / acquire at .sys scope) orders them, and the incoming slabs are unpacked into the halo rows; transfer buffers
+are double-buffered by exchange parity, so there is no trailing barrier and no host synchronisation."""
 from __future__ import annotations
 
 import torch
 
+import ctypes
+
+from ... import _lib
 from ...parallel.symmetric import SignalPad
+
+_lib.declare("ab_halo_exchange_1d", "p i p p p p p p p i i i i i i i p i p")
 
 
 class PeerHaloExchanger1d:
@@ -32,6 +38,8 @@ class PeerHaloExchanger1d:
 
     def __call__(self, y, H_split=True, explicit_nhwc=False, numSM=0, diagnostics=False):
         low_out, low_in, high_out, high_in = self._slices(y, H_split, explicit_nhwc)
+        if y.is_cuda and _lib.available() and y.element_size() in (2, 4):
+            return self._fused(y, low_out, low_in, high_out, high_in, numSM)
         # tx[r] is the buffer living on rank r: [0] receives from its low neighbour, [1] from its high neighbour
         tx = self.peer_pool.allocate_peer_tensors([2] + list(low_out.shape), y.dtype, False, True)
         if not self.low_zero:
@@ -49,3 +57,28 @@ class PeerHaloExchanger1d:
         else:
             high_in.copy_(mine[1])
         self.pad.barrier(channel=41)                    # buffers may be reused after this
+
+    def _fused(self, y, low_out, low_in, high_out, high_in, numSM):
+        nbytes = low_out.numel() * y.element_size()
+        key = (nbytes, y.dtype)
+        st = getattr(self, "_tx", None)
+        if st is None or st[0] != key:
+            # [parity][side][slab] in the STATIC part of the pool: lives across exchanges (double buffering by parity)
+            tx = self.peer_pool.allocate_peer_tensors([2, 2, low_out.numel()], y.dtype, False, False)
+            self._tx = st = (key, tx, torch.zeros(1, dtype=torch.int32, device=y.device), [0])
+        _, tx, ticket, it = st
+        par = it[0] & 1
+        it[0] += 1
+        # innermost-last ordering of the slab dims so that 16-byte vectors run along the unit-stride dim
+        order = sorted(range(4), key=lambda d: (-low_out.stride(d), d))
+        base = y.untyped_storage().data_ptr()
+        es = y.element_size()
+        off = lambda t: (t.data_ptr() - base) // es
+        meta = (ctypes.c_longlong * 12)(*[low_out.shape[d] for d in order], *[low_out.stride(d) for d in order],
+                                        off(low_out), off(low_in), off(high_out), off(high_in))
+        pads = self.pad.mem.peer_ptrs
+        me, lo, hi = self.peer_rank, self.low_neighbor, self.high_neighbor
+        _lib.fn("ab_halo_exchange_1d")(base, es, ctypes.addressof(meta), tx[lo][par].data_ptr(), tx[hi][par].data_ptr(),
+                                       tx[me][par].data_ptr(), pads[lo], pads[hi], pads[me], me, lo, hi, int(not self.low_zero),
+                                       int(not self.high_zero), 42, self.pad.next_epoch(), ticket.data_ptr(), int(numSM),
+                                       _lib.stream_ptr(y.device))

@@ -137,3 +137,41 @@ def dist_lamb_matches_fused_lamb(rank, world, device_type):
         opt.step()
         for pr, pd in zip(ref_model.parameters(), dist_model.parameters()):
             torch.testing.assert_close(pd, pr, rtol=2e-4, atol=2e-5)
+
+
+def peer_halo_exchange_matches_allgather(rank, world, device_type):
+    """PeerHaloExchanger1d (one fused P2P kernel) against halos built from an all-gather of the interiors; NCHW, channels-last and
+    explicit NHWC, H- and W-split, fp16 and fp32, repeated to exercise the parity double-buffering."""
+    from apex_b200.contrib.peer_memory import PeerHaloExchanger1d, PeerMemoryPool
+    dev = torch.device("cuda", rank)
+    pool = PeerMemoryPool(64 << 20, 8 << 20, list(range(world)))
+    hh = 2
+    for dtype in (torch.float16, torch.float32):
+        for layout in ("nchw", "cl", "nhwc"):
+            for H_split in (True, False):
+                ex = PeerHaloExchanger1d(list(range(world)), rank, pool, hh)
+                for it in range(3):
+                    torch.manual_seed(1000 * it + rank)
+                    N, C, H, W = 2, 16, 12, 8
+                    explicit = layout == "nhwc"
+                    if explicit:
+                        shape = [N, H + 2 * hh, W, C] if H_split else [N, H, W + 2 * hh, C]
+                        y = torch.randn(shape, device=dev).to(dtype)
+                        dim = 1 if H_split else 2
+                    else:
+                        shape = [N, C, H + 2 * hh, W] if H_split else [N, C, H, W + 2 * hh]
+                        y = torch.randn(shape, device=dev).to(dtype)
+                        if layout == "cl":
+                            y = y.contiguous(memory_format=torch.channels_last)
+                        dim = 2 if H_split else 3
+                    L = y.shape[dim] - 2 * hh
+                    interior = y.narrow(dim, hh, L).contiguous()
+                    parts = [torch.empty_like(interior) for _ in range(world)]
+                    dist.all_gather(parts, interior)
+                    want = y.clone()
+                    lo = parts[rank - 1].narrow(dim, L - hh, hh) if rank > 0 else torch.zeros_like(interior.narrow(dim, 0, hh))
+                    hi = parts[rank + 1].narrow(dim, 0, hh) if rank < world - 1 else torch.zeros_like(interior.narrow(dim, 0, hh))
+                    want.narrow(dim, 0, hh).copy_(lo)
+                    want.narrow(dim, L + hh, hh).copy_(hi)
+                    ex(y, H_split=H_split, explicit_nhwc=explicit)
+                    torch.testing.assert_close(y, want, rtol=0, atol=0)

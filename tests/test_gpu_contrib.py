@@ -156,3 +156,12 @@ def test_self_multihead_attn(cuda_dev):
     out, _ = m(x, x, x, is_training=False)
     r, _ = ref(x, x, x, need_weights=False)
     torch.testing.assert_close(out, r, atol=2e-4, rtol=2e-4)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_halo_exchange(cuda_dev, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.peer_halo_exchange_matches_allgather, world, "cuda", backend="nccl")
