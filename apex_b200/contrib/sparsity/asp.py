@@ -29,6 +29,7 @@ class ASP:
     __sparse_parameters = []
     __calculate_mask = None
     __allow_permutation = False
+    __permuted = False
 
     @classmethod
     def init_model_for_pruning(cls, model, mask_calculator="m4n2_1d", verbosity=3, whitelist=(torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d),
@@ -37,6 +38,7 @@ class ASP:
         assert cls.__model is None, "ASP has been initialized already."
         cls.__model, cls.__verbosity, cls.__allow_permutation = model, verbosity, allow_permutation
         cls.__sparse_parameters = []
+        cls.__permuted = False
         if isinstance(mask_calculator, str):
             cls.__calculate_mask = lambda p: create_mask(p, mask_calculator).bool()
         else:
@@ -90,6 +92,12 @@ class ASP:
 
     @classmethod
     def compute_sparse_masks(cls):
+        if cls.__allow_permutation and not getattr(cls, "_ASP__permuted", False):
+            # search + apply function-preserving channel permutations once, before the first masks (reference asp.py:314-345)
+            from .permutation_lib import Permutation
+
+            Permutation.permute_model(cls.__model, verbosity=cls.__verbosity >= 2)
+            cls.__permuted = True
         with torch.no_grad():
             for name, mod, p_name, p, mask, pruned in cls.__sparse_parameters:
                 if mask.sum() < mask.numel() and pruned is not None:
@@ -137,3 +145,4 @@ class ASP:
         """Forget the registered model/optimizer (lets tests run more than once per process)."""
         cls.__model = cls.__optimizer = cls.__calculate_mask = None
         cls.__sparse_parameters = []
+        cls.__permuted = False

@@ -1,0 +1,124 @@
+"""CPU checks of the contrib modules: import surface, small numerics against plain PyTorch (the CUDA kernels have GPU twins)."""
+import importlib
+
+import pytest
+import torch
+import torch.nn as nn
+
+
+@pytest.mark.parametrize("mod", [
+    "apex_b200.contrib.optimizers", "apex_b200.contrib.xentropy", "apex_b200.contrib.layer_norm", "apex_b200.contrib.group_norm",
+    "apex_b200.contrib.clip_grad", "apex_b200.contrib.focal_loss", "apex_b200.contrib.index_mul_2d", "apex_b200.contrib.transducer",
+    "apex_b200.contrib.multihead_attn", "apex_b200.contrib.fmha", "apex_b200.contrib.conv_bias_relu", "apex_b200.contrib.bottleneck",
+    "apex_b200.contrib.groupbn", "apex_b200.contrib.cudnn_gbn", "apex_b200.contrib.sparsity", "apex_b200.contrib.peer_memory",
+    "apex_b200.contrib.nccl_p2p", "apex_b200.contrib.nccl_allocator", "apex_b200.contrib.gpu_direct_storage", "apex_b200.contrib.openfold",
+    "apex_b200.contrib.torchsched", "apex_b200.parallel", "apex_b200.transformer.functional", "apex_b200.fused_dense", "apex_b200.mlp",
+    "apex_b200.normalization", "apex_b200.optimizers", "apex_b200.multi_tensor_apply", "apex_b200.utils.flatten"])
+def test_imports(mod):
+    importlib.import_module(mod)
+
+
+def test_transducer_loss_oracle_matches_bruteforce():
+    from apex_b200.contrib.transducer import TransducerLoss
+    torch.manual_seed(0)
+    B, T, U, V = 2, 4, 3, 5
+    x = torch.randn(B, T, U, V, requires_grad=True)
+    label = torch.randint(1, V, (B, U - 1))
+    f_len, y_len = torch.tensor([4, 3]), torch.tensor([2, 1])
+    loss = TransducerLoss()(x, label, f_len, y_len, 0)
+    lp = torch.log_softmax(x.detach(), -1)
+
+    def brute(b):
+        Tb, Ub = int(f_len[b]), int(y_len[b]) + 1
+
+        def rec(t, u):  # log-prob of finishing from (t, u)
+            if t == Tb - 1 and u == Ub - 1:
+                return lp[b, t, u, 0]
+            opts = []
+            if t < Tb - 1:
+                opts.append(lp[b, t, u, 0] + rec(t + 1, u))
+            if u < Ub - 1:
+                opts.append(lp[b, t, u, label[b, u]] + rec(t, u + 1))
+            return torch.logsumexp(torch.stack(opts), 0)
+        return -rec(0, 0)
+
+    torch.testing.assert_close(loss.detach(), torch.stack([brute(0), brute(1)]), atol=1e-5, rtol=1e-5)
+    loss.sum().backward()
+    assert torch.isfinite(x.grad).all()
+
+
+def test_transducer_joint_cpu():
+    from apex_b200.contrib.transducer import TransducerJoint
+    f, g = torch.randn(2, 5, 8), torch.randn(2, 3, 8)
+    f_len, g_len = torch.tensor([5, 3]), torch.tensor([3, 2])
+    out = TransducerJoint(relu=True)(f, g, f_len, g_len)
+    assert out.shape == (2, 5, 3, 8)
+    torch.testing.assert_close(out[0], torch.relu(f[0, :, None] + g[0, None]))
+    assert out[1, 3:].abs().sum() == 0 and out[1, :, 2:].abs().sum() == 0
+    bo = torch.cumsum(f_len * g_len, 0)
+    packed = TransducerJoint(pack_output=True)(f, g, f_len, g_len, batch_offset=bo, packed_batch=int(bo[-1]))
+    assert packed.shape == (21, 8)
+
+
+def test_permutation_search_improves_and_is_a_permutation():
+    from apex_b200.contrib.sparsity import permutation_search as P
+    assert len(P.generate_all_unique_combinations(8)) == 35
+    torch.manual_seed(0)
+    m = torch.randn(64, 32)
+    base = float(P.sum_after_2_to_4(m))
+    for fn in (lambda: P.Channel_Swap(m), lambda: P.Exhaustive_Search(m, 8), lambda: P.Random_Search(m, 20)):
+        out, _, perm = fn()
+        assert sorted(perm) == list(range(32))
+        assert float(P.sum_after_2_to_4(out)) >= base
+        torch.testing.assert_close(out, m[:, perm])
+    out, _, _ = P.Exhaustive_Search(m, 8)
+    assert float(P.sum_after_2_to_4(out)) > base * 1.005
+
+
+def test_asp_with_permutation_preserves_function():
+    from apex_b200.contrib.sparsity import ASP
+    ASP.reset()
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 16))
+    x = torch.randn(4, 32)
+    y0 = model(x).detach()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    from apex_b200.contrib.sparsity.permutation_lib import Permutation
+    Permutation.search_options = {"strategy": "exhaustive", "stripe_group_size": 8, "escape_attempts": 1}
+    rep = Permutation.permute_model(model)
+    assert len(rep) >= 1 and all(a > b for _, b, a in rep)
+    torch.testing.assert_close(model(x), y0, atol=1e-5, rtol=1e-5)
+    ASP.init_model_for_pruning(model, "m4n2_1d", verbosity=0, whitelist=(nn.Linear,), allow_recompute_mask=False)
+    ASP.init_optimizer_for_pruning(opt)
+    ASP.compute_sparse_masks()
+    w = model[2].weight
+    assert (w.view(-1, 4) != 0).sum(1).max() <= 2
+    ASP.reset()
+
+
+def test_syncbn_functional_cpu():
+    from apex_b200.parallel import syncbn_ops as S
+    x = torch.randn(4, 6, 5, 5)
+    mean, var = S.welford_mean_var(x)
+    m2, var_u, istd = S.welford_parallel(torch.stack([mean, mean]), torch.stack([var, var]), torch.tensor([100, 100]), 1e-5)
+    torch.testing.assert_close(m2, mean)
+    w, b = torch.randn(6), torch.randn(6)
+    y = S.batchnorm_forward(x, mean, istd, w, b)
+    torch.testing.assert_close(y, torch.nn.functional.batch_norm(x, None, None, w, b, True, 0.0, 1e-5), atol=1e-5, rtol=1e-5)
+
+
+def test_legacy_contrib_optimizers_cpu():
+    from apex_b200.contrib.optimizers import FP16_Optimizer, FusedAdam
+    from apex_b200.optimizers import FusedAdam as FA
+    p = torch.nn.Parameter(torch.ones(10))
+    o = FusedAdam([p], lr=0.1)
+    o.step(grads=[torch.full((10,), 4.0)], scale=2.0)
+    torch.testing.assert_close(p.detach(), torch.full((10,), 0.9))
+    m = torch.nn.Linear(4, 4).half()
+    opt = FP16_Optimizer(FA(m.parameters(), lr=1e-2), static_loss_scale=8.0, verbose=False)
+    w0 = m.weight.detach().clone()
+    opt.backward(m(torch.randn(2, 4).half()).float().sum())
+    opt.step()
+    assert not torch.equal(w0, m.weight)
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)
