@@ -31,6 +31,18 @@ struct Smem {
   static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + tmem ptr + alignment slack
 };
 
+// Tile rasterisation: groups of kGroupM tile-rows are walked column by column, so the tiles that are in flight together
+// (one per CTA / CTA pair) cover a compact ~8 x 9 block of the output and share A and B panels in L2 instead of streaming all of A.
+constexpr int kGroupM = 8;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * num_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int m0 = g * kGroupM;
+  const int gm = min(kGroupM, num_m - m0);
+  n_blk = r / gm;
+  m_blk = m0 + (r - n_blk * gm);
+}
+
 template <typename TOut, int BN, int KSTAGES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                                            Params p, int is_bf16) {
@@ -69,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % num_m, n_blk = t / num_m;
+        int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = smem + stage * S::kStage;
@@ -94,9 +106,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (one elected lane)
-    if (lane == 0) {
+    // ===================================================== MMA issuer. The WHOLE warp runs the (uniform) loop so that descriptor
+    // arithmetic stays in the uniform datapath; one elected lane issues. Shared-memory descriptors are built once: per k-block only
+    // a 32-bit add on the address field remains (the loop body must cost less than the 4 x 64 tensor cycles it feeds).
+    {
       const uint32_t idesc = make_idesc(is_bf16, p.a_mn_major, p.b_mn_major, BM, BN);
+      // K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); advance 32 B per UMMA_K inside the atom.
+      // MN-major: 64-wide MN blocks BK*128 B apart (LBO), 8-k-row atoms 1024 B apart (SBO); advance 2 atoms per UMMA_K.
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t a0 = p.a_mn_major ? make_desc(smem0, BK * 128, 1024) : make_desc(smem0, 16, 1024);
+      const uint64_t b0 = p.b_mn_major ? make_desc(smem0 + S::kABytes, BK * 128, 1024) : make_desc(smem0 + S::kABytes, 16, 1024);
+      const uint32_t a_step = p.a_mn_major ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn_major ? (2048u >> 4) : (32u >> 4);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -106,18 +126,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStage);
-          const uint32_t sb = sa + S::kABytes;
+          if (elect_one()) {
+            const uint64_t ad = a0 + (uint32_t)(stage * (S::kStage >> 4)), bd = b0 + (uint32_t)(stage * (S::kStage >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++) {
-            // K-major: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO); advance 32 B per UMMA_K inside the atom.
-            // MN-major: 64-wide MN blocks BK*128 B apart (LBO), 8-k-row atoms 1024 B apart (SBO); advance 2 atoms per UMMA_K.
-            const uint64_t adesc = p.a_mn_major ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = p.b_mn_major ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
-            umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; k++)
+              umma_f16(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs have read it
+            if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
           }
-          umma_commit(&empty_bar[stage]);                 // frees the smem slot when these MMAs have read it
-          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          __syncwarp();
           if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int q = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may touch
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t % num_m, n_blk = t / num_m;
+      int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
@@ -240,7 +257,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m_blk = t % num_m, n_blk = t / num_m;
+        int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * 2 * BM + (int)cta * BM;         // this CTA's A rows
         const int n0 = n_blk * BN2 + (int)cta * (BN2 / 2);     // this CTA's half of B
         for (int kb = 0; kb < num_k; kb++) {
@@ -263,9 +280,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ===================================================== MMA issuer (leader CTA only; whole warp, one elected lane issues)
+    if (leader) {
       const uint32_t idesc = make_idesc(is_bf16, p.a_mn_major, p.b_mn_major, 2 * BM, BN2);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t a0 = p.a_mn_major ? make_desc(smem0, BK * 128, 1024) : make_desc(smem0, 16, 1024);
+      const uint64_t b0 = p.b_mn_major ? make_desc(smem0 + S::kABytes, BK * 128, 1024) : make_desc(smem0 + S::kABytes, 16, 1024);
+      const uint32_t a_step = p.a_mn_major ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn_major ? (2048u >> 4) : (32u >> 4);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -275,16 +296,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(&full_bar[stage], phase, 13);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStage);
-          const uint32_t sb = sa + S::kABytes;
+          if (elect_one()) {
+            const uint64_t ad = a0 + (uint32_t)(stage * (S::kStage >> 4)), bd = b0 + (uint32_t)(stage * (S::kStage >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; k++) {
-            const uint64_t adesc = p.a_mn_major ? make_desc(sa + k * 2048, BK * 128, 1024) : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = p.b_mn_major ? make_desc(sb + k * 2048, BK * 128, 1024) : make_desc(sb + k * 32, 16, 1024);
-            umma_f16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; k++)
+              umma_f16_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == num_k - 1) umma_commit_2sm(&tmem_full[acc]);
           }
-          umma_commit_2sm(&empty_bar[stage]);
-          if (kb == num_k - 1) umma_commit_2sm(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -295,7 +315,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int q = warp - kEpiWarp0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int m_blk = t % num_m, n_blk = t / num_m;
+      int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 14);
       tc_fence_after();
       const int row = m_blk * 2 * BM + (int)cta * BM + q * 32 + lane;

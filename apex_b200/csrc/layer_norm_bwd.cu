@@ -17,26 +17,36 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
                            Tin* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b, int n1, int n2,
                            float eps, int tpr) {
   constexpr int E = 16 / sizeof(Tin);
-  __shared__ float sred[64];
+  __shared__ float sred[128];
   __shared__ float sacc[2][4096];
   RowReducer red(sred, tpr);
   const int rows_per_cta = blockDim.x / tpr;
   const int nvec = n2 / E;
   const float inv_n = 1.f / (float)n2;
-  float acc_g[MAXV][E], acc_b[MAXV][E];
+  // per-thread dgamma / dbeta accumulators: registers, or (rows wider than 2 vectors per thread) this thread's private columns
+  // of a dynamic shared-memory array -- 64 accumulator registers would push the row itself out to local memory
+  constexpr bool SACC = MAXV >= 4;
+  extern __shared__ float dyn_acc[];  // [2][n2] when SACC
+  float acc_g[SACC ? 1 : MAXV][E], acc_b[SACC ? 1 : MAXV][E];
+  if (SACC) {
+    for (int i = threadIdx.x; i < 2 * n2; i += blockDim.x) dyn_acc[i] = 0.f;
+    __syncthreads();
+  } else {
 #pragma unroll
-  for (int v = 0; v < MAXV; v++)
+    for (int v = 0; v < (SACC ? 1 : MAXV); v++)
 #pragma unroll
-    for (int e = 0; e < E; e++) { acc_g[v][e] = 0.f; acc_b[v][e] = 0.f; }
+      for (int e = 0; e < E; e++) { acc_g[v][e] = 0.f; acc_b[v][e] = 0.f; }
+  }
 
   constexpr int DW = E * sizeof(Tout) / 4;  // 32-bit words of one dy / y vector
-  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += gridDim.x * rows_per_cta) {
+  constexpr int SW = MEMEFF ? DW : 4;
+  // rows are kept as RAW bits (half the registers of fp32 copies) and decoded twice; the NEXT row group's loads are issued
+  // before this one's reductions (register double buffering) so that every SM keeps ~2x the bytes in flight
+  auto load_rows = [&](int row0, uint32_t (&draw)[MAXV][DW], uint32_t (&sraw)[MAXV][SW], float& mu, float& rstd) {
     const int row = row0 + red.rg;
     const bool valid = row < n1;
-    const float mu = (valid && !RMS && !MEMEFF) ? mean[row] : 0.f;
-    const float rstd = valid ? invvar[row] : 0.f;
-    // keep the row as RAW bits (half the registers of fp32 copies); decode twice
-    uint32_t draw[MAXV][DW], sraw[MAXV][MEMEFF ? DW : 4];
+    mu = (valid && !RMS && !MEMEFF) ? mean[row] : 0.f;
+    rstd = valid ? invvar[row] : 0.f;
 #pragma unroll
     for (int v = 0; v < MAXV; v++) {
       const int idx = v * tpr + red.lane_r;
@@ -70,33 +80,49 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
         sraw[v][0] = t.x; sraw[v][1] = t.y; sraw[v][2] = t.z; sraw[v][3] = t.w;
       }
     }
-    // decode vector v -> xhat, dy, gamma
-    auto decode = [&](int v, int idx, float (&xh)[E], float (&d)[E], float (&g)[E]) {
+  };
+  // gamma (and beta for the memory-efficient variant) are loop-invariant per thread: packed raw bits in registers
+  uint32_t graw[MAXV][DW], braw[MAXV][MEMEFF ? DW : 1];
+#pragma unroll
+  for (int v = 0; v < MAXV; v++) {
+    const int idx = v * tpr + red.lane_r;
+#pragma unroll
+    for (int q = 0; q < DW; q++) {
+      graw[v][q] = (gamma && idx < nvec) ? reinterpret_cast<const uint32_t*>(gamma + (size_t)idx * E)[q] : 0u;
+      if (MEMEFF) braw[v][q] = (beta && idx < nvec) ? reinterpret_cast<const uint32_t*>(beta + (size_t)idx * E)[q] : 0u;
+    }
+  }
+  const int row_step = gridDim.x * rows_per_cta;
+  uint32_t draw[MAXV][DW], sraw[MAXV][SW], draw_n[MAXV][DW], sraw_n[MAXV][SW];
+  float mu = 0.f, rstd = 0.f, mu_n = 0.f, rstd_n = 0.f;
+  constexpr bool PREFETCH = MAXV <= 2;  // wider rows would spill: they keep one row group in flight
+  if (PREFETCH && blockIdx.x * rows_per_cta < n1) load_rows(blockIdx.x * rows_per_cta, draw, sraw, mu, rstd);
+  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += row_step) {
+    const int row = row0 + red.rg;
+    const bool valid = row < n1;
+    const bool more = PREFETCH && row0 + row_step < n1;
+    if (!PREFETCH) load_rows(row0, draw, sraw, mu, rstd);
+    if (more) load_rows(row0 + row_step, draw_n, sraw_n, mu_n, rstd_n);
+    const float nmr = -mu * rstd;
+    // decode vector v -> dy and xhat (and the raw x for the non-memory-efficient pass 2)
+    auto decode = [&](int v, float (&xh)[E], float (&d)[E], float (&xr)[E]) {
       const Tout* de = reinterpret_cast<const Tout*>(draw[v]);
 #pragma unroll
       for (int e = 0; e < E; e++) d[e] = to_f<Tout>(de[e]);
-      if (gamma) load_vec<Tout, E>(g, gamma + (size_t)idx * E);
-      else {
-#pragma unroll
-        for (int e = 0; e < E; e++) g[e] = 1.f;
-      }
       if (MEMEFF) {
         const Tout* ye = reinterpret_cast<const Tout*>(sraw[v]);
-        float b[E];
-        if (!RMS && beta) load_vec<Tout, E>(b, beta + (size_t)idx * E);
-        else {
-#pragma unroll
-          for (int e = 0; e < E; e++) b[e] = 0.f;
-        }
+        const Tout* ge = reinterpret_cast<const Tout*>(graw[v]);
+        const Tout* be = reinterpret_cast<const Tout*>(braw[v]);
 #pragma unroll
         for (int e = 0; e < E; e++) {
-          const float yv = to_f<Tout>(ye[e]) - b[e];
-          xh[e] = gamma ? yv / clamp_mag(g[e], eps) : yv;
+          const float yv = (!RMS && beta) ? to_f<Tout>(ye[e]) - to_f<Tout>(be[e]) : to_f<Tout>(ye[e]);
+          xh[e] = gamma ? yv / clamp_mag(to_f<Tout>(ge[e]), eps) : yv;
+          xr[e] = xh[e];
         }
       } else {
         const Tin* xe = reinterpret_cast<const Tin*>(sraw[v]);
 #pragma unroll
-        for (int e = 0; e < E; e++) xh[e] = (to_f<Tin>(xe[e]) - mu) * rstd;
+        for (int e = 0; e < E; e++) { xr[e] = to_f<Tin>(xe[e]); xh[e] = fmaf(xr[e], rstd, nmr); }
       }
     };
     float s1 = 0.f, s2 = 0.f;
@@ -104,38 +130,79 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
     for (int v = 0; v < MAXV; v++) {
       const int idx = v * tpr + red.lane_r;
       if (valid && idx < nvec) {
-        float xh[E], d[E], g[E];
-        decode(v, idx, xh, d, g);
+        float xh[E], d[E], xr[E];
+        decode(v, xh, d, xr);
+        const Tout* ge = reinterpret_cast<const Tout*>(graw[v]);
+        if (SACC) {
+          float* ag = dyn_acc + (size_t)idx * E;
+          float* ab = ag + n2;
+#pragma unroll
+          for (int q = 0; q < E / 4; q++) {
+            float4 g4 = reinterpret_cast<float4*>(ag)[q], b4 = reinterpret_cast<float4*>(ab)[q];
+            g4.x = fmaf(d[4 * q], xh[4 * q], g4.x); g4.y = fmaf(d[4 * q + 1], xh[4 * q + 1], g4.y);
+            g4.z = fmaf(d[4 * q + 2], xh[4 * q + 2], g4.z); g4.w = fmaf(d[4 * q + 3], xh[4 * q + 3], g4.w);
+            b4.x += d[4 * q]; b4.y += d[4 * q + 1]; b4.z += d[4 * q + 2]; b4.w += d[4 * q + 3];
+            reinterpret_cast<float4*>(ag)[q] = g4; reinterpret_cast<float4*>(ab)[q] = b4;
+          }
+        }
 #pragma unroll
         for (int e = 0; e < E; e++) {
-          acc_g[v][e] += d[e] * xh[e];
-          acc_b[v][e] += d[e];
-          const float w = d[e] * g[e];
-          s1 += w;
-          s2 += w * xh[e];
+          if (!SACC) { acc_g[v][e] = fmaf(d[e], xh[e], acc_g[v][e]); acc_b[v][e] += d[e]; }
+          const float w = gamma ? d[e] * to_f<Tout>(ge[e]) : d[e];
+          if (!RMS) s1 += w;
+          s2 = fmaf(w, xh[e], s2);
         }
       }
     }
-    if (!RMS) s1 = red.sum(s1) * inv_n; else s1 = 0.f;
-    s2 = red.sum(s2) * inv_n;
+    if (!RMS) red.sum2(s1, s2); else s2 = red.sum(s2);
     if (valid) {
+      // dx = rstd*(w - s1/n - xhat*s2/n) = rstd*w + A + B*xhat;  with xhat = x*rstd + nmr:  = rstd*w + x*(B*rstd) + (A + B*nmr)
+      const float A = RMS ? 0.f : -rstd * s1 * inv_n, B = -rstd * s2 * inv_n;
+      const float Br = MEMEFF ? B : B * rstd, C = MEMEFF ? A : fmaf(B, nmr, A);
 #pragma unroll
       for (int v = 0; v < MAXV; v++) {
         const int idx = v * tpr + red.lane_r;
         if (idx < nvec) {
-          float xh[E], d[E], g[E], o[E];
-          decode(v, idx, xh, d, g);
+          float xh[E], d[E], xr[E], o[E];
+          const Tout* de = reinterpret_cast<const Tout*>(draw[v]);
+          const Tout* ge = reinterpret_cast<const Tout*>(graw[v]);
+          if (MEMEFF) {
+            decode(v, xh, d, xr);
+          } else {
+            const Tin* xe = reinterpret_cast<const Tin*>(sraw[v]);
 #pragma unroll
-          for (int e = 0; e < E; e++) o[e] = rstd * (d[e] * g[e] - s1 - xh[e] * s2);
+            for (int e = 0; e < E; e++) { d[e] = to_f<Tout>(de[e]); xr[e] = to_f<Tin>(xe[e]); }
+          }
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            const float w = gamma ? d[e] * to_f<Tout>(ge[e]) : d[e];
+            o[e] = fmaf(xr[e], Br, fmaf(rstd, w, C));
+          }
           store_vec<Tin, E>(dx + (size_t)row * n2 + (size_t)idx * E, o);
         }
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int v = 0; v < MAXV; v++) {
+#pragma unroll
+        for (int q = 0; q < DW; q++) draw[v][q] = draw_n[v][q];
+#pragma unroll
+        for (int q = 0; q < SW; q++) sraw[v][q] = sraw_n[v][q];
+      }
+      mu = mu_n; rstd = rstd_n;
     }
   }
 
   if (part_g == nullptr) return;  // no affine parameters
   // fold the row groups of this CTA, then one partial row per CTA
-  if (rows_per_cta > 1) {
+  if (SACC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      part_g[(size_t)blockIdx.x * n2 + i] = dyn_acc[i];
+      if (part_b) part_b[(size_t)blockIdx.x * n2 + i] = dyn_acc[n2 + i];
+    }
+  } else if (rows_per_cta > 1) {
     for (int i = threadIdx.x; i < n2; i += blockDim.x) { sacc[0][i] = 0.f; sacc[1][i] = 0.f; }
     __syncthreads();
     for (int g = 0; g < rows_per_cta; g++) {
@@ -145,7 +212,7 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
           const int idx = v * tpr + red.lane_r;
           if (idx < nvec) {
 #pragma unroll
-            for (int e = 0; e < E; e++) { sacc[0][idx * E + e] += acc_g[v][e]; sacc[1][idx * E + e] += acc_b[v][e]; }
+            for (int e = 0; e < E; e++) { sacc[0][idx * E + e] += acc_g[SACC ? 0 : v][e]; sacc[1][idx * E + e] += acc_b[SACC ? 0 : v][e]; }
           }
         }
       }
@@ -160,8 +227,8 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
     for (int v = 0; v < MAXV; v++) {
       const int idx = v * tpr + red.lane_r;
       if (idx < nvec) {
-        store_vec<float, E>(part_g + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_g[v]);
-        if (part_b) store_vec<float, E>(part_b + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_b[v]);
+        store_vec<float, E>(part_g + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_g[SACC ? 0 : v]);
+        if (part_b) store_vec<float, E>(part_b + (size_t)blockIdx.x * n2 + (size_t)idx * E, acc_b[SACC ? 0 : v]);
       }
     }
   }
@@ -263,20 +330,21 @@ int ln_bwd_launch(const void* dy, const void* saved, const float* mean, const fl
                       ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
   NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 2, 512);
   const bool small_rows_ok = c.rows_per_cta == 1 || n2 <= 4096;
-  if (vec_ok && c.ok && small_rows_ok && ws != nullptr) {
+  const size_t dyn = c.maxv >= 4 ? (size_t)2 * n2 * sizeof(float) : 0;  // shared-memory accumulators of the wide-row variants
+  if (vec_ok && c.ok && c.maxv <= 4 && dyn <= 160 * 1024 && small_rows_ok && ws != nullptr) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
     const int cap = kNumSMs * (512 / c.threads);
     if (grid > cap) grid = cap;
     float* part_g = dgamma ? ws : nullptr;
     float* part_b = (dgamma && dbeta) ? ws + (size_t)cap * n2 : nullptr;
 #define LN_BWD_GO(MV)                                                                                                   \
-  ln_bwd_vec<MV, Tin, Tout, RMS, MEMEFF><<<grid, c.threads, 0, st>>>((const Tout*)dy, saved, mean, invvar, (const Tout*)gamma, \
+  if (dyn) cudaFuncSetAttribute(ln_bwd_vec<MV, Tin, Tout, RMS, MEMEFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+  ln_bwd_vec<MV, Tin, Tout, RMS, MEMEFF><<<grid, c.threads, dyn, st>>>((const Tout*)dy, saved, mean, invvar, (const Tout*)gamma, \
                                                                      (const Tout*)beta, (Tin*)dx, part_g, part_b, n1, n2, eps, c.tpr)
     switch (c.maxv) {
       case 1: LN_BWD_GO(1); break;
       case 2: LN_BWD_GO(2); break;
-      case 4: LN_BWD_GO(4); break;
-      default: LN_BWD_GO(8); break;
+      default: LN_BWD_GO(4); break;
     }
     if (dgamma)
       ln_bwd_fold<Tout><<<(n2 + 31) / 32, dim3(32, 16), 0, st>>>(part_g, part_b, grid, n2, (Tout*)dgamma, (Tout*)dbeta);

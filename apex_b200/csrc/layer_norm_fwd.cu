@@ -6,54 +6,83 @@
 
 namespace ab {
 
+// Instruction budget matters as much as bytes here (bf16: 4 B/element of traffic buys ~20 issue slots per element at the HBM
+// roofline): x is decoded twice (not three times) thanks to single-pass shifted statistics, gamma / beta are loop-invariant per
+// thread and live in registers as packed raw bits, and the output is two FFMAs per element (y = x*A + B, A = rstd*gamma,
+// B = beta - mean*A). The next row group's loads are issued before this one's reduction (register double buffering).
 template <int MAXV, typename Tin, typename Tout, bool RMS>
 __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
                                                    float* __restrict__ invvar, const Tout* __restrict__ gamma,
                                                    const Tout* __restrict__ beta, int n1, int n2, float eps, int tpr) {
   constexpr int E = 16 / sizeof(Tin);
-  __shared__ float sred[64];
+  constexpr int GW = E * sizeof(Tout) / 4;  // 32-bit words of one gamma / beta vector
+  constexpr bool PREFETCH = MAXV <= 2;
+  __shared__ float sred[128];
   RowReducer red(sred, tpr);
   const int rows_per_cta = blockDim.x / tpr;
   const int nvec = n2 / E;
   const float inv_n = 1.f / (float)n2;
-  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += gridDim.x * rows_per_cta) {
+  uint32_t graw[MAXV][GW], braw[MAXV][GW];
+#pragma unroll
+  for (int v = 0; v < MAXV; v++) {
+    const int idx = v * tpr + red.lane_r;
+#pragma unroll
+    for (int q = 0; q < GW; q++) {
+      graw[v][q] = (gamma && idx < nvec) ? reinterpret_cast<const uint32_t*>(gamma + (size_t)idx * E)[q] : 0u;
+      braw[v][q] = (beta && idx < nvec) ? reinterpret_cast<const uint32_t*>(beta + (size_t)idx * E)[q] : 0u;
+    }
+  }
+  auto load_rows = [&](int row0, uint4 (&raw)[MAXV], float& shift) {
     const int row = row0 + red.rg;
     const bool valid = row < n1;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * n2);
-    uint4 raw[MAXV];
 #pragma unroll
     for (int v = 0; v < MAXV; v++) {
       const int idx = v * tpr + red.lane_r;
       raw[v] = (valid && idx < nvec) ? __ldg(xr + idx) : make_uint4(0, 0, 0, 0);
     }
-    float mu = 0.f, rstd;
-    if (!RMS) {
-      float s = 0.f;
-#pragma unroll
-      for (int v = 0; v < MAXV; v++) {
-        float f[E]; unpack16<Tin>(raw[v], f);
-#pragma unroll
-        for (int e = 0; e < E; e++) s += f[e];
-      }
-      mu = red.sum(s) * inv_n;
-    }
-    float ss = 0.f;
+    shift = (!RMS && valid) ? to_f<Tin>(__ldg(x + (size_t)row * n2)) : 0.f;  // a sample of the row: kills the cancellation in E[d^2]-E[d]^2
+  };
+  const int row_step = gridDim.x * rows_per_cta;
+  uint4 raw[MAXV], raw_n[MAXV];
+  float shift = 0.f, shift_n = 0.f;
+  if (PREFETCH && blockIdx.x * rows_per_cta < n1) load_rows(blockIdx.x * rows_per_cta, raw, shift);
+  for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += row_step) {
+    const int row = row0 + red.rg;
+    const bool valid = row < n1;
+    const bool more = PREFETCH && row0 + row_step < n1;
+    if (!PREFETCH) load_rows(row0, raw, shift);
+    if (more) load_rows(row0 + row_step, raw_n, shift_n);
+    float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int v = 0; v < MAXV; v++) {
       const int idx = v * tpr + red.lane_r;
       if (idx < nvec) {
         float f[E]; unpack16<Tin>(raw[v], f);
 #pragma unroll
-        for (int e = 0; e < E; e++) { const float d = f[e] - mu; ss += d * d; }
+        for (int e = 0; e < E; e++) {
+          const float d = RMS ? f[e] : f[e] - shift;
+          if (!RMS) s += d;
+          ss = fmaf(d, d, ss);
+        }
       }
     }
-    rstd = rsqrtf(red.sum(ss) * inv_n + eps);
+    float mu = 0.f, rstd;
+    if (RMS) {
+      rstd = rsqrtf(red.sum(ss) * inv_n + eps);
+    } else {
+      red.sum2(s, ss);
+      const float md = s * inv_n;
+      mu = shift + md;
+      rstd = rsqrtf(fmaxf(ss * inv_n - md * md, 0.f) + eps);
+    }
     if (valid) {
       if (red.lane_r == 0) {
         if (!RMS && mean) mean[row] = mu;
         invvar[row] = rstd;
       }
       Tout* yr = y + (size_t)row * n2;
+      const float nmr = -mu * rstd;
 #pragma unroll
       for (int v = 0; v < MAXV; v++) {
         const int idx = v * tpr + red.lane_r;
@@ -61,22 +90,27 @@ __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tou
           float f[E]; unpack16<Tin>(raw[v], f);
           float o[E];
           if (gamma) {
-            float g[E]; load_vec<Tout, E>(g, gamma + (size_t)idx * E);
-            if (beta) {
-              float b[E]; load_vec<Tout, E>(b, beta + (size_t)idx * E);
+            const Tout* ge = reinterpret_cast<const Tout*>(graw[v]);
+            const Tout* be = reinterpret_cast<const Tout*>(braw[v]);
 #pragma unroll
-              for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd * g[e] + b[e];
-            } else {
-#pragma unroll
-              for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd * g[e];
+            for (int e = 0; e < E; e++) {
+              const float g = to_f<Tout>(ge[e]);
+              const float A = rstd * g;
+              const float Bc = beta ? fmaf(nmr, g, to_f<Tout>(be[e])) : nmr * g;
+              o[e] = fmaf(f[e], A, Bc);
             }
           } else {
 #pragma unroll
-            for (int e = 0; e < E; e++) o[e] = (f[e] - mu) * rstd;
+            for (int e = 0; e < E; e++) o[e] = fmaf(f[e], rstd, nmr);
           }
           store_vec<Tout, E>(yr + (size_t)idx * E, o);
         }
       }
+    }
+    if (more) {
+#pragma unroll
+      for (int v = 0; v < MAXV; v++) raw[v] = raw_n[v];
+      shift = shift_n;
     }
   }
 }
@@ -115,10 +149,10 @@ int ln_fwd_launch(const void* x, void* y, float* mean, float* invvar, const void
   constexpr int E = 16 / sizeof(Tin);
   const bool vec_ok = (n2 % E == 0) && aligned16(x) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 && aligned16(y) &&
                       ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
-  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 4, 512);
+  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 2, 512);
   if (vec_ok && c.ok) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
-    const int cap = kNumSMs * (2048 / c.threads);
+    const int cap = kNumSMs * (1024 / c.threads);  // ~3 x 256-thread CTAs are resident per SM at this register budget
     if (grid > cap) grid = cap;
 #define LN_FWD_GO(MV)                                                                                                 \
   ln_fwd_vec<MV, Tin, Tout, RMS><<<grid, c.threads, 0, st>>>((const Tin*)x, (Tout*)y, mean, invvar, (const Tout*)gamma, \

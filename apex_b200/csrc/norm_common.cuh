@@ -8,7 +8,7 @@ namespace ab {
 // tpr < 32. For tpr > 32 partial sums go through shared memory; `buf` alternates between two banks so one barrier per
 // reduction is enough. EVERY thread of the CTA must call this (uniform control flow).
 struct RowReducer {
-  float* smem;  // [2][32] floats
+  float* smem;  // [2 banks][64] floats (sum / maxv use the first 32 of a bank, sum2 all 64)
   int tpr, lane_r, rg, bank;
   __device__ __forceinline__ RowReducer(float* s, int tpr_) : smem(s), tpr(tpr_), bank(0) {
     lane_r = threadIdx.x % tpr_;
@@ -22,7 +22,7 @@ struct RowReducer {
     v = warp_sum(v);
     const int wpr = tpr >> 5;            // warps per row
     const int w = threadIdx.x >> 5;      // warp in CTA; rows own consecutive warps
-    float* b = smem + bank * 32;
+    float* b = smem + bank * 64;
     if ((threadIdx.x & 31) == 0) b[w] = v;
     __syncthreads();
     float t = 0.f;
@@ -30,6 +30,24 @@ struct RowReducer {
     for (int i = 0; i < wpr; i++) t += b[w0 + i];
     bank ^= 1;
     return t;
+  }
+  // two sums with one barrier (shared memory: [2 banks][2 values][32 warps])
+  __device__ __forceinline__ void sum2(float& a, float& c) {
+    if (tpr <= 32) {
+      for (int o = tpr >> 1; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+      return;
+    }
+    a = warp_sum(a); c = warp_sum(c);
+    const int wpr = tpr >> 5;
+    const int w = threadIdx.x >> 5;
+    float* b = smem + bank * 64;
+    if ((threadIdx.x & 31) == 0) { b[w] = a; b[32 + w] = c; }
+    __syncthreads();
+    float ta = 0.f, tc = 0.f;
+    const int w0 = rg * wpr;
+    for (int i = 0; i < wpr; i++) { ta += b[w0 + i]; tc += b[32 + w0 + i]; }
+    bank ^= 1;
+    a = ta; c = tc;
   }
   __device__ __forceinline__ float maxv(float v) {
     if (tpr <= 32) {
@@ -39,7 +57,7 @@ struct RowReducer {
     v = warp_max(v);
     const int wpr = tpr >> 5;
     const int w = threadIdx.x >> 5;
-    float* b = smem + bank * 32;
+    float* b = smem + bank * 64;
     if ((threadIdx.x & 31) == 0) b[w] = v;
     __syncthreads();
     float t = -INFINITY;

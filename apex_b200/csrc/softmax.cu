@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(512) softmax_fwd_vec(const T* __restrict__ x, 
                                                        float scale, long long rows, int sk, int sq, int heads, int mask_per_batch,
                                                        int tpr) {
   constexpr int E = 16 / sizeof(T);
-  __shared__ float sred[64];
+  __shared__ float sred[128];
   RowReducer red(sred, tpr);
   const int rows_per_cta = blockDim.x / tpr;
   const int nvec = sk / E;
@@ -84,7 +84,7 @@ template <int MAXV, typename T>
 __global__ void __launch_bounds__(512) softmax_bwd_vec(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, float scale,
                                                        long long rows, int sk, int tpr) {
   constexpr int E = 16 / sizeof(T);
-  __shared__ float sred[64];
+  __shared__ float sred[128];
   RowReducer red(sred, tpr);
   const int rows_per_cta = blockDim.x / tpr;
   const int nvec = sk / E;
