@@ -78,8 +78,8 @@ __device__ __forceinline__ Wf wf_shfl_xor(const Wf& w, int o) {
 template <typename T> struct VecOf { static constexpr int V = 16 / sizeof(T); };
 
 // relu-masked incoming gradient for the fused (bn + add + relu) block
-__device__ __forceinline__ float masked_grad(const BnArgs& a, float g, float xv, float zv, int c, float mu, float is) {
-  if (!a.fuse_relu) return g;
+__device__ __forceinline__ float masked_grad(const BnArgs& a, bool fuse_relu, float g, float xv, float zv, int c, float mu, float is) {
+  if (!fuse_relu) return g;
   const float yv = (xv - mu) * is * (a.weight ? a.weight[c] : 1.f) + (a.bias ? a.bias[c] : 0.f) + zv;
   return yv > 0.f ? g : 0.f;
 }
@@ -101,31 +101,35 @@ __device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float 
   }
 }
 
-template <typename T>
+// IS_BWD / NHWC / FUSED (residual add and/or ReLU present) are compile-time: every instantiation carries only its own inner loops
+// (the runtime-flag version was 13.7k SASS instructions at 114 registers and stalled on instruction fetch for small layers).
+template <typename T, bool IS_BWD, bool NHWC, bool FUSED>
 __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
   constexpr int V = VecOf<T>::V;
   __shared__ float sm[3][kBnThreads + 8];
   __shared__ int s_last;
+  __shared__ float csum[2][kBnThreads / 32][64];  // NHWC: per-warp channel sums of one item
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
   const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
-  const T* __restrict__ z = reinterpret_cast<const T*>(a.z);
+  const T* __restrict__ z = FUSED ? reinterpret_cast<const T*>(a.z) : nullptr;
+  const bool fuse_relu = FUSED && fuse_relu;
   const long long per_c = (long long)a.N * a.HW;
   const int S = a.splits;
   const int C = a.C, HW = a.HW;
 
   // ------------------------------------------------------------------ phase 1: partial statistics (+ per-unit merge/publish)
   if (a.phases & 1) {
-    if (!a.nhwc) {
+    if (!NHWC) {
       // NCHW: unit = channel; a split is a range of the channel's N*HW elements; threads run along HW (coalesced)
-      const bool vec = (HW % V == 0) && aligned16(x) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z));
+      const bool vec = (HW % V == 0) && aligned16(x) && (!IS_BWD || aligned16(dy)) && (!z || aligned16(z));
       const int items = C * S;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int c = it / S, s = it - c * S;
         long long e0 = per_c * s / S, e1 = per_c * (s + 1) / S;
         if (vec) { e0 = e0 / V * V; e1 = (s == S - 1) ? per_c : e1 / V * V; }
         float acc0 = 0.f, acc1 = 0.f, cnt = 0.f, shift = 0.f, mu = 0.f, is = 0.f;
-        if (!a.is_bwd) {
+        if (!IS_BWD) {
           if (e1 > e0) { const long long n0 = e0 / HW; shift = to_f<T>(x[(n0 * C + c) * (long long)HW + (e0 - n0 * HW)]); }
         } else { mu = a.mean[c]; is = a.invstd[c]; }
         const int step = vec ? V : 1;
@@ -136,19 +140,19 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
           float xv[V], gv[V], zv[V];
           if (vec) {
             load_vec<T, V>(xv, x + off);
-            if (a.is_bwd) load_vec<T, V>(gv, dy + off);
-            if (a.is_bwd && a.fuse_relu && z) load_vec<T, V>(zv, z + off);
+            if (IS_BWD) load_vec<T, V>(gv, dy + off);
+            if (IS_BWD && fuse_relu && z) load_vec<T, V>(zv, z + off);
           } else {
             xv[0] = to_f<T>(x[off]);
-            if (a.is_bwd) gv[0] = to_f<T>(dy[off]);
-            if (a.is_bwd && a.fuse_relu && z) zv[0] = to_f<T>(z[off]);
+            if (IS_BWD) gv[0] = to_f<T>(dy[off]);
+            if (IS_BWD && fuse_relu && z) zv[0] = to_f<T>(z[off]);
           }
 #pragma unroll
           for (int j = 0; j < V; j++) {
             if (j < step) {
-              if (!a.is_bwd) { const float d = xv[j] - shift; acc0 += d; acc1 += d * d; cnt += 1.f; }
+              if (!IS_BWD) { const float d = xv[j] - shift; acc0 += d; acc1 += d * d; cnt += 1.f; }
               else {
-                const float g = masked_grad(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, c, mu, is);
+                const float g = masked_grad(a, fuse_relu, gv[j], xv[j], (fuse_relu && z) ? zv[j] : 0.f, c, mu, is);
                 acc0 += g; acc1 += g * (xv[j] - mu);
               }
             }
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
         }
         // block reduction -> partial[c][s]
         float* pp = a.partial + ((size_t)c * S + s) * 3;
-        if (!a.is_bwd) {
+        if (!IS_BWD) {
           Wf w = wf_from_sums(shift, acc0, acc1, cnt);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) w = wf_merge(w, wf_shfl_xor(w, o));
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
           __threadfence();
           if (wid == 0) {
             const float* base = a.partial + (size_t)c * S * 3;
-            if (!a.is_bwd) {
+            if (!IS_BWD) {
               Wf w{0.f, 0.f, 0.f};
               for (int q = lane; q < S; q += 32) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
 #pragma unroll
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
       }
     } else {
       // NHWC: unit = channel tile; thread (cx, ry): cx owns V (or 1) adjacent channels, ry strides over rows (4x unrolled)
-      const bool vec = (C % V == 0) && aligned16(x) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z));
+      const bool vec = (C % V == 0) && aligned16(x) && (!IS_BWD || aligned16(dy)) && (!z || aligned16(z));
       const int cw = vec ? V : 1;            // channels per thread
       const int lanes_c = vec ? 8 : 32;      // threads along channels
       const int lanes_r = kBnThreads / lanes_c;
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
 #pragma unroll
           for (int j = 0; j < V; j++) {
             if (j < cw && cbase + j < C) {
-              if (!a.is_bwd) { if (r1 > r0) shift[j] = to_f<T>(x[r0 * C + cbase + j]); }
+              if (!IS_BWD) { if (r1 > r0) shift[j] = to_f<T>(x[r0 * C + cbase + j]); }
               else { mu[j] = a.mean[cbase + j]; is[j] = a.invstd[cbase + j]; }
             }
           }
@@ -236,49 +240,49 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
             float xv[V], gv[V], zv[V];
             if (vec) {
               load_vec<T, V>(xv, x + off);
-              if (a.is_bwd) load_vec<T, V>(gv, dy + off);
-              if (a.is_bwd && a.fuse_relu && z) load_vec<T, V>(zv, z + off);
+              if (IS_BWD) load_vec<T, V>(gv, dy + off);
+              if (IS_BWD && fuse_relu && z) load_vec<T, V>(zv, z + off);
             } else {
               xv[0] = to_f<T>(x[off]);
-              if (a.is_bwd) gv[0] = to_f<T>(dy[off]);
-              if (a.is_bwd && a.fuse_relu && z) zv[0] = to_f<T>(z[off]);
+              if (IS_BWD) gv[0] = to_f<T>(dy[off]);
+              if (IS_BWD && fuse_relu && z) zv[0] = to_f<T>(z[off]);
             }
             cnt += 1.f;
 #pragma unroll
             for (int j = 0; j < V; j++) {
               if (j < cw) {
-                if (!a.is_bwd) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] += d * d; }
+                if (!IS_BWD) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] += d * d; }
                 else {
-                  const float g = masked_grad(a, gv[j], xv[j], (a.fuse_relu && z) ? zv[j] : 0.f, cbase + j, mu[j], is[j]);
+                  const float g = masked_grad(a, fuse_relu, gv[j], xv[j], (fuse_relu && z) ? zv[j] : 0.f, cbase + j, mu[j], is[j]);
                   acc0[j] += g; acc1[j] += g * (xv[j] - mu[j]);
                 }
               }
             }
           }
         }
-        // reduce over the row lanes through shared memory, one channel slot at a time
+        // reduce over the row lanes: every thread of a channel column used the same shift, so plain sums combine exactly --
+        // xor-shuffles inside the warp (lanes with equal cx), then one shared-memory hop across the 8 warps
+        __syncthreads();  // the previous item's readers are done with csum
 #pragma unroll
         for (int j = 0; j < V; j++) {
           if (j < cw) {
-            __syncthreads();
-            if (!a.is_bwd) {
-              const Wf w = wf_from_sums(shift[j], acc0[j], acc1[j], c_ok ? cnt : 0.f);
-              sm[0][tid] = w.mean; sm[1][tid] = w.m2; sm[2][tid] = w.n;
-            } else { sm[0][tid] = acc0[j]; sm[1][tid] = acc1[j]; }
-            __syncthreads();
-            if (ry == 0 && c_ok && cbase + j < C) {
-              float* p = a.partial + ((size_t)(cbase + j) * S + s) * 3;
-              if (!a.is_bwd) {
-                Wf t{0.f, 0.f, 0.f};
-                for (int q = 0; q < lanes_r; q++) t = wf_merge(t, Wf{sm[0][q * lanes_c + cx], sm[1][q * lanes_c + cx], sm[2][q * lanes_c + cx]});
-                p[0] = t.mean; p[1] = t.m2; p[2] = t.n;
-              } else {
-                float t0 = 0.f, t1 = 0.f;
-                for (int q = 0; q < lanes_r; q++) { t0 += sm[0][q * lanes_c + cx]; t1 += sm[1][q * lanes_c + cx]; }
-                p[0] = t0; p[1] = t1; p[2] = 0.f;
-              }
-            }
+            float v0 = acc0[j], v1 = acc1[j];
+            for (int o = lanes_c; o < 32; o <<= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+            if (lane < lanes_c) { csum[0][wid][cx * cw + j] = v0; csum[1][wid][cx * cw + j] = v1; }
           }
+        }
+        __syncthreads();
+        if (tid < tile_c && ct * tile_c + tid < C) {
+          const int c = ct * tile_c + tid;
+          float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int w = 0; w < kBnThreads / 32; w++) { t0 += csum[0][w][tid]; t1 += csum[1][w][tid]; }
+          float* p = a.partial + ((size_t)c * S + s) * 3;
+          if (!IS_BWD) {
+            const float sh = r1 > r0 ? to_f<T>(x[r0 * C + c]) : 0.f;
+            const Wf w = wf_from_sums(sh, t0, t1, (float)(r1 - r0));
+            p[0] = w.mean; p[1] = w.m2; p[2] = w.n;
+          } else { p[0] = t0; p[1] = t1; p[2] = 0.f; }
         }
         // last split of this channel tile merges and publishes its channels: thread (ch = tid % tile_c, grp = tid / tile_c)
         __syncthreads();
@@ -293,14 +297,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
           if (c < C) {
             const float* base = a.partial + (size_t)c * S * 3;
             for (int q = grp; q < S; q += ngrp) {
-              if (!a.is_bwd) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
+              if (!IS_BWD) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
               else { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
             }
           }
-          if (!a.is_bwd) { sm[0][tid] = w.mean; sm[1][tid] = w.m2; sm[2][tid] = w.n; } else { sm[0][tid] = s0; sm[1][tid] = s1; }
+          if (!IS_BWD) { sm[0][tid] = w.mean; sm[1][tid] = w.m2; sm[2][tid] = w.n; } else { sm[0][tid] = s0; sm[1][tid] = s1; }
           __syncthreads();
           if (grp == 0 && c < C) {
-            if (!a.is_bwd) {
+            if (!IS_BWD) {
               Wf t{0.f, 0.f, 0.f};
               for (int q = 0; q < ngrp; q++) t = wf_merge(t, Wf{sm[0][q * tile_c + ch], sm[1][q * tile_c + ch], sm[2][q * tile_c + ch]});
               publish(a, c, t.mean, t.m2, t.n);
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
     }
     const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + a.xchg_off : nullptr;
     for (int c = blockIdx.x * kBnThreads + tid; c < C; c += gridDim.x * kBnThreads) {
-      if (!a.is_bwd) {
+      if (!IS_BWD) {
         Wf w{0.f, 0.f, 0.f};
         if (D > 1) {
           for (int r = 0; r < D; r++) { const float* p = mine + ((size_t)r * C + c) * 3; w = wf_merge(w, Wf{ld_relaxed_sys_f32(p), ld_relaxed_sys_f32(p + 1), ld_relaxed_sys_f32(p + 2)}); }
@@ -365,15 +369,15 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
   //   bwd: dx = g*A + x*Bc + Cc                      A = w*inv_std, Bc = -inv_std^3*w*sum_dy_xmu/N, Cc = -A*sum_dy/N - mean*Bc
   if (a.phases & 4) {
     T* __restrict__ out = reinterpret_cast<T*>(a.out);
-    T* __restrict__ dz = reinterpret_cast<T*>(a.dz);
-    const float inv_n = a.is_bwd ? 1.f / __ldcg(a.count_total) : 0.f;
-    const bool vec = ((a.nhwc ? C : HW) % V == 0) && aligned16(x) && aligned16(out) && (!a.is_bwd || aligned16(dy)) && (!z || aligned16(z)) &&
+    T* __restrict__ dz = (FUSED && IS_BWD) ? reinterpret_cast<T*>(a.dz) : nullptr;
+    const float inv_n = IS_BWD ? 1.f / __ldcg(a.count_total) : 0.f;
+    const bool vec = ((NHWC ? C : HW) % V == 0) && aligned16(x) && aligned16(out) && (!IS_BWD || aligned16(dy)) && (!z || aligned16(z)) &&
                      (!dz || aligned16(dz));
     const int step = vec ? V : 1;
     auto coef = [&](int c, float& sc, float& sh, float& A, float& Bc, float& Cc) {
       const float mu = __ldcg(a.mean + c), is = __ldcg(a.invstd + c), w = a.weight ? a.weight[c] : 1.f;
       sc = is * w; sh = (a.bias ? a.bias[c] : 0.f) - mu * sc;
-      if (a.is_bwd) {
+      if (IS_BWD) {
         A = sc; Bc = -is * is * sc * __ldcg(a.sum_dy_xmu + c) * inv_n; Cc = -A * __ldcg(a.sum_dy + c) * inv_n - mu * Bc;
       } else { A = 0.f; Bc = 0.f; Cc = 0.f; }
     };
@@ -381,24 +385,24 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
       float xv[V], gv[V], zv[V], o[V], gz[V];
       if (vec) {
         load_vec<T, V>(xv, x + i);
-        if (a.is_bwd) load_vec<T, V>(gv, dy + i);
+        if (IS_BWD) load_vec<T, V>(gv, dy + i);
         if (z) load_vec<T, V>(zv, z + i);
       } else {
         xv[0] = to_f<T>(x[i]);
-        if (a.is_bwd) gv[0] = to_f<T>(dy[i]);
+        if (IS_BWD) gv[0] = to_f<T>(dy[i]);
         if (z) zv[0] = to_f<T>(z[i]);
       }
 #pragma unroll
       for (int j = 0; j < V; j++) {
         if (j < step) {
-          if (!a.is_bwd) {
+          if (!IS_BWD) {
             float yv = fmaf(xv[j], sc[j], sh[j]);
             if (z) yv += zv[j];
-            if (a.fuse_relu) yv = fmaxf(yv, 0.f);
+            if (fuse_relu) yv = fmaxf(yv, 0.f);
             o[j] = yv;
           } else {
             float g = gv[j];
-            if (a.fuse_relu) { float yv = fmaf(xv[j], sc[j], sh[j]); if (z) yv += zv[j]; if (yv <= 0.f) g = 0.f; }
+            if (fuse_relu) { float yv = fmaf(xv[j], sc[j], sh[j]); if (z) yv += zv[j]; if (yv <= 0.f) g = 0.f; }
             gz[j] = g;
             o[j] = fmaf(g, A[j], fmaf(xv[j], Bc[j], Cc[j]));
           }
@@ -406,14 +410,14 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
       }
       if (vec) {
         store_vec<T, V>(out + i, o);
-        if (a.is_bwd && dz) store_vec<T, V>(dz + i, gz);
+        if (IS_BWD && dz) store_vec<T, V>(dz + i, gz);
       } else {
         out[i] = from_f<T>(o[0]);
-        if (a.is_bwd && dz) dz[i] = from_f<T>(gz[0]);
+        if (IS_BWD && dz) dz[i] = from_f<T>(gz[0]);
       }
     };
     float sc[V], sh[V], A[V], Bc[V], Cc[V];
-    if (a.nhwc) {
+    if (NHWC) {
       const long long total = (long long)a.N * C * HW;
       const long long gthreads = (long long)gridDim.x * kBnThreads;
       const int cvecs = C / step;
@@ -504,7 +508,15 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
   if (phases & 2) { const long long w2 = ((long long)C + kBnThreads - 1) / kBnThreads; if (w2 > want) want = w2; }
   if (phases & 4) { const long long w4 = (total + kBnThreads * 16 - 1) / (kBnThreads * 16); if (w4 > want) want = w4; }
   if (want < grid) grid = (int)want;
-#define BN_GO(T) syncbn_kernel<T><<<grid, kBnThreads, 0, st>>>(a)
+  const bool fused = fuse_relu || z != nullptr || dz != nullptr;
+#define BN_GO4(T, B, H, F) syncbn_kernel<T, B, H, F><<<grid, kBnThreads, 0, st>>>(a)
+#define BN_GO(T)                                                                                   \
+  do {                                                                                             \
+    if (is_bwd) { if (nhwc) { if (fused) BN_GO4(T, true, true, true); else BN_GO4(T, true, true, false); }        \
+                  else      { if (fused) BN_GO4(T, true, false, true); else BN_GO4(T, true, false, false); } }    \
+    else        { if (nhwc) { if (fused) BN_GO4(T, false, true, true); else BN_GO4(T, false, true, false); }      \
+                  else      { if (fused) BN_GO4(T, false, false, true); else BN_GO4(T, false, false, false); } }  \
+  } while (0)
   AB_DISPATCH_FLOAT3(dt, T, BN_GO(T));
   AB_CHECK_LAUNCH();
   return 0;

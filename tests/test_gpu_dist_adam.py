@@ -137,3 +137,10 @@ def test_four_gpus_fused(cuda_dev):
     from apex_b200.testing.dist_harness import run_distributed
     from tests import _dist_cases as cases
     run_distributed(cases.dist_adam_matches_ddp_adamw, 4, "cuda", True, 3, True, backend="nccl")
+
+
+def test_eight_gpus_fused(cuda_dev):
+    _need(8)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 8, "cuda", True, 3, True, backend="nccl")

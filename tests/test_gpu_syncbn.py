@@ -116,6 +116,13 @@ def test_two_gpus_match_concatenated_batchnorm(cuda_dev, uneven, channels_last):
     run_distributed(_two_gpu_case, 2, uneven, channels_last, backend="nccl")
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_many_gpus_match_concatenated_batchnorm(cuda_dev, world):
+    _need(world)
+    from apex_b200.testing.dist_harness import run_distributed
+    run_distributed(_two_gpu_case, world, False, True, backend="nccl")
+
+
 @pytest.mark.parametrize("channels_last", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 def test_functional_ops(cuda_dev, channels_last, dtype):
