@@ -23,7 +23,7 @@ struct GnArgs {
   float* chan;                            // [N*C][3] per-(n,c) merged values
   float* gsum;                            // [N*G][2] bwd: gamma-weighted group sums / M
   unsigned int* grid_bar;
-  int N, HW, C, G, splits, silu, is_bwd, phases;
+  int N, HW, C, G, splits, splits3, silu, is_bwd, phases;
   float eps;
 };
 
@@ -58,21 +58,24 @@ __device__ __forceinline__ float ld_w(const void* p, int fp32, int c) {
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
 __device__ __forceinline__ float dsilu_f(float v) { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f + v * (1.f - s)); }
 
-template <typename T>
+// IS_BWD / SILU are compile-time. Threads are laid out (cx, ry): cx owns V adjacent channels (one 16-byte vector), ry strides over
+// rows, so everything that depends on the channel only -- shift, gamma, beta, the per-(n, c) normalisation coefficients -- is
+// computed once per work item and the inner loops are loads + 2-3 FMAs per element (+ the SiLU exponentials).
+template <typename T, bool IS_BWD, bool SILU>
 __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
   constexpr int V = 16 / sizeof(T);
-  __shared__ float sm[3][kGnThreads + 8];
-  const int tid = threadIdx.x;
+  __shared__ float csum[2][kGnThreads / 32][64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
   const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
   T* __restrict__ out = reinterpret_cast<T*>(a.out);
   const int C = a.C, HW = a.HW, G = a.G, Cg = C / G, S = a.splits;
-  const bool vec = (C % V == 0) && aligned16(x) && aligned16(out) && (!a.is_bwd || aligned16(dy));
+  const bool vec = (C % V == 0) && aligned16(x) && aligned16(out) && (!IS_BWD || aligned16(dy));
   const int cw = vec ? V : 1, lanes_c = vec ? 8 : 32, lanes_r = kGnThreads / lanes_c, tile_c = lanes_c * cw;
   const int ctiles = (C + tile_c - 1) / tile_c;
   const int cx = tid % lanes_c, ry = tid / lanes_c;
 
-  // ------------------------------------------------------------------ phase 1
+  // ------------------------------------------------------------------ phase 1: per-(n, c, split) partial sums
   if (a.phases & 1) {
     const int items = a.N * ctiles * S;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
@@ -80,20 +83,21 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
       const int r0 = (int)((long long)HW * s / S), r1 = (int)((long long)HW * (s + 1) / S);
       const int cbase = ct * tile_c + cx * cw;
       const bool c_ok = cbase < C;
-      float acc0[V], acc1[V], shift[V], sc[V], sh[V], cnt = 0.f;
+      float acc0[V], acc1[V], shift[V], sc[V], sh[V], gm[V], bt[V];
 #pragma unroll
-      for (int j = 0; j < V; j++) { acc0[j] = 0.f; acc1[j] = 0.f; shift[j] = 0.f; sc[j] = 0.f; sh[j] = 0.f; }
+      for (int j = 0; j < V; j++) { acc0[j] = 0.f; acc1[j] = 0.f; shift[j] = 0.f; sc[j] = 0.f; sh[j] = 0.f; gm[j] = 0.f; bt[j] = 0.f; }
       const T* xb = x + (size_t)n * HW * C;
-      const T* gb = a.is_bwd ? dy + (size_t)n * HW * C : nullptr;
+      const T* gb = IS_BWD ? dy + (size_t)n * HW * C : nullptr;
       if (c_ok) {
 #pragma unroll
         for (int j = 0; j < V; j++) {
           if (j < cw && cbase + j < C) {
-            if (!a.is_bwd) { if (r1 > r0) shift[j] = to_f<T>(xb[(size_t)r0 * C + cbase + j]); }
+            if (!IS_BWD) { if (r1 > r0) shift[j] = to_f<T>(xb[(size_t)r0 * C + cbase + j]); }
             else {
               const int g = (cbase + j) / Cg;
               const float mu = a.mean[n * G + g], r = a.rstd[n * G + g];
               sc[j] = r; sh[j] = -mu * r;  // xhat = x*sc + sh
+              if (SILU) { gm[j] = ld_w<T>(a.gamma, a.w_fp32, cbase + j); bt[j] = a.beta ? ld_w<T>(a.beta, a.w_fp32, cbase + j) : 0.f; }
             }
           }
         }
@@ -101,50 +105,45 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
         for (int r = r0 + ry; r < r1; r += lanes_r) {
           const size_t off = (size_t)r * C + cbase;
           float xv[V], gv[V];
-          if (vec) { load_vec<T, V>(xv, xb + off); if (a.is_bwd) load_vec<T, V>(gv, gb + off); }
-          else { xv[0] = to_f<T>(xb[off]); if (a.is_bwd) gv[0] = to_f<T>(gb[off]); }
-          cnt += 1.f;
+          if (vec) { load_vec<T, V>(xv, xb + off); if (IS_BWD) load_vec<T, V>(gv, gb + off); }
+          else { xv[0] = to_f<T>(xb[off]); if (IS_BWD) gv[0] = to_f<T>(gb[off]); }
 #pragma unroll
           for (int j = 0; j < V; j++) {
             if (j < cw) {
-              if (!a.is_bwd) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] += d * d; }
+              if (!IS_BWD) { const float d = xv[j] - shift[j]; acc0[j] += d; acc1[j] = fmaf(d, d, acc1[j]); }
               else {
                 const float xh = fmaf(xv[j], sc[j], sh[j]);
                 float g = gv[j];
-                if (a.silu) {
-                  const int c = cbase + j;
-                  const float gm = c < C ? ld_w<T>(a.gamma, a.w_fp32, c) : 0.f, bt = (c < C && a.beta) ? ld_w<T>(a.beta, a.w_fp32, c) : 0.f;
-                  g *= dsilu_f(fmaf(xh, gm, bt));
-                }
-                acc0[j] += g; acc1[j] += g * xh;
+                if (SILU) g *= dsilu_f(fmaf(xh, gm[j], bt[j]));
+                acc0[j] += g; acc1[j] = fmaf(g, xh, acc1[j]);
               }
             }
           }
         }
       }
+      // all row lanes of a channel share the shift -> plain sums: xor-shuffles inside the warp, one shared-memory hop across warps
+      __syncthreads();
 #pragma unroll
       for (int j = 0; j < V; j++) {
         if (j < cw) {
-          __syncthreads();
-          if (!a.is_bwd) {
-            float m = 0.f, m2 = 0.f, nn = 0.f;
-            if (c_ok && cnt > 0.f) { const float mm = acc0[j] / cnt; m = shift[j] + mm; m2 = fmaxf(acc1[j] - acc0[j] * mm, 0.f); nn = cnt; }
-            sm[0][tid] = m; sm[1][tid] = m2; sm[2][tid] = nn;
-          } else { sm[0][tid] = acc0[j]; sm[1][tid] = acc1[j]; }
-          __syncthreads();
-          if (ry == 0 && c_ok && cbase + j < C) {
-            float* p = a.partial + (((size_t)n * C + cbase + j) * S + s) * 3;
-            if (!a.is_bwd) {
-              GW t{0.f, 0.f, 0.f};
-              for (int q = 0; q < lanes_r; q++) t = gw_merge(t, GW{sm[0][q * lanes_c + cx], sm[1][q * lanes_c + cx], sm[2][q * lanes_c + cx]});
-              p[0] = t.mean; p[1] = t.m2; p[2] = t.n;
-            } else {
-              float t0 = 0.f, t1 = 0.f;
-              for (int q = 0; q < lanes_r; q++) { t0 += sm[0][q * lanes_c + cx]; t1 += sm[1][q * lanes_c + cx]; }
-              p[0] = t0; p[1] = t1; p[2] = 0.f;
-            }
-          }
+          float v0 = acc0[j], v1 = acc1[j];
+          for (int o = lanes_c; o < 32; o <<= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+          if (lane < lanes_c) { csum[0][wid][cx * cw + j] = v0; csum[1][wid][cx * cw + j] = v1; }
         }
+      }
+      __syncthreads();
+      if (tid < tile_c && ct * tile_c + tid < C) {
+        const int c = ct * tile_c + tid;
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < kGnThreads / 32; w++) { t0 += csum[0][w][tid]; t1 += csum[1][w][tid]; }
+        float* p = a.partial + (((size_t)n * C + c) * S + s) * 3;
+        if (!IS_BWD) {
+          const float cnt = (float)(r1 - r0);
+          float m = 0.f, m2 = 0.f;
+          if (cnt > 0.f) { const float mm = t0 / cnt; m = to_f<T>(xb[(size_t)r0 * C + c]) + mm; m2 = fmaxf(t1 - t0 * mm, 0.f); }
+          p[0] = m; p[1] = m2; p[2] = cnt;
+        } else { p[0] = t0; p[1] = t1; p[2] = 0.f; }
       }
     }
     if (a.phases & 6) gn_grid_barrier(a.grid_bar, gridDim.x);
@@ -152,11 +151,10 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
 
   // ------------------------------------------------------------------ phase 2: one warp per (n, g)
   if (a.phases & 2) {
-    const int lane = tid & 31;
     const int gw = (blockIdx.x * kGnThreads + tid) >> 5, nw = (gridDim.x * kGnThreads) >> 5;
     for (int ng = gw; ng < a.N * G; ng += nw) {
       const int n = ng / G, g = ng - n * G;
-      if (!a.is_bwd) {
+      if (!IS_BWD) {
         GW w{0.f, 0.f, 0.f};
         for (int q = lane; q < Cg * S; q += 32) {
           const int c = g * Cg + q / S, s = q % S;
@@ -175,14 +173,14 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
           for (int s = 0; s < S; s++) { const float* p = a.partial + (((size_t)n * C + c) * S + s) * 3; s1 += __ldcg(p); s2 += __ldcg(p + 1); }
           float* cc = a.chan + ((size_t)n * C + c) * 3;
           cc[0] = s1; cc[1] = s2;
-          const float gm = ld_w<T>(a.gamma, a.w_fp32, c);
-          m1 += gm * s1; m2 += gm * s2;
+          const float gmv = ld_w<T>(a.gamma, a.w_fp32, c);
+          m1 += gmv * s1; m2 += gmv * s2;
         }
         m1 = warp_sum(m1); m2 = warp_sum(m2);
         if (lane == 0) { const float invM = 1.f / ((float)HW * (float)Cg); a.gsum[ng * 2] = m1 * invM; a.gsum[ng * 2 + 1] = m2 * invM; }
       }
     }
-    if (a.is_bwd && a.dgamma) {
+    if (IS_BWD && a.dgamma) {
       gn_grid_barrier(a.grid_bar, gridDim.x);
       for (int c = blockIdx.x * kGnThreads + tid; c < C; c += gridDim.x * kGnThreads) {
         float dg = 0.f, db = 0.f;
@@ -194,39 +192,58 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
     if (a.phases & 4) gn_grid_barrier(a.grid_bar, gridDim.x);
   }
 
-  // ------------------------------------------------------------------ phase 3: elementwise in memory order
+  // ------------------------------------------------------------------ phase 3: apply, same (cx, ry) layout, x re-read from L2
+  //   fwd: y  = silu?(x*A + B)                          A = rstd*gamma, B = beta - mean*A
+  //   bwd: dx = g*RG + xhat*NM2 + NM1, xhat = x*R + MR   g = dy (* dsilu(xhat*gamma + beta)), RG = rstd*gamma, NMk = -rstd*mk
   if (a.phases & 4) {
-    const long long per_img = (long long)HW * C;
-    const long long total = (long long)a.N * per_img;
-    const int step = vec ? V : 1;
-    const long long gthreads = (long long)gridDim.x * kGnThreads;
-#pragma unroll 2
-    for (long long i = ((long long)blockIdx.x * kGnThreads + tid) * step; i < total; i += gthreads * step) {
-      const int n = (int)(i / per_img);
-      const int c0 = (int)(i % C);
-      float xv[V], gv[V], o[V];
-      if (vec) { load_vec<T, V>(xv, x + i); if (a.is_bwd) load_vec<T, V>(gv, dy + i); }
-      else { xv[0] = to_f<T>(x[i]); if (a.is_bwd) gv[0] = to_f<T>(dy[i]); }
+    const int S3 = a.splits3;
+    const int items = a.N * ctiles * S3;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+      const int s = it % S3, ct = (it / S3) % ctiles, n = it / (S3 * ctiles);
+      const int r0 = (int)((long long)HW * s / S3), r1 = (int)((long long)HW * (s + 1) / S3);
+      const int cbase = ct * tile_c + cx * cw;
+      if (cbase >= C) continue;
+      float A[V], B[V], R[V], MR[V], NM1[V], NM2[V], gm[V], bt[V];
 #pragma unroll
       for (int j = 0; j < V; j++) {
-        if (j < step) {
-          const int c = c0 + j, g = c / Cg;
+        A[j] = B[j] = R[j] = MR[j] = NM1[j] = NM2[j] = gm[j] = bt[j] = 0.f;
+        if (j < cw && cbase + j < C) {
+          const int c = cbase + j, g = c / Cg;
           const float mu = __ldcg(a.mean + n * G + g), r = __ldcg(a.rstd + n * G + g);
-          const float gm = a.gamma ? ld_w<T>(a.gamma, a.w_fp32, c) : 1.f, bt = a.beta ? ld_w<T>(a.beta, a.w_fp32, c) : 0.f;
-          const float xh = (xv[j] - mu) * r;
-          if (!a.is_bwd) {
-            float yv = fmaf(xh, gm, bt);
-            if (a.silu) yv = silu_f(yv);
-            o[j] = yv;
-          } else {
-            float g2 = gv[j];
-            if (a.silu) g2 *= dsilu_f(fmaf(xh, gm, bt));
+          gm[j] = a.gamma ? ld_w<T>(a.gamma, a.w_fp32, c) : 1.f;
+          bt[j] = a.beta ? ld_w<T>(a.beta, a.w_fp32, c) : 0.f;
+          if (!IS_BWD) { A[j] = r * gm[j]; B[j] = fmaf(-mu, A[j], bt[j]); }
+          else {
             const float m1 = __ldcg(a.gsum + (n * G + g) * 2), m2 = __ldcg(a.gsum + (n * G + g) * 2 + 1);
-            o[j] = r * (gm * g2 - m1 - xh * m2);
+            R[j] = r; MR[j] = -mu * r; A[j] = r * gm[j]; NM1[j] = -r * m1; NM2[j] = -r * m2;
           }
         }
       }
-      if (vec) store_vec<T, V>(out + i, o); else out[i] = from_f<T>(o[0]);
+      const T* xb = x + (size_t)n * HW * C;
+      const T* gb = IS_BWD ? dy + (size_t)n * HW * C : nullptr;
+      T* ob = out + (size_t)n * HW * C;
+#pragma unroll 4
+      for (int r = r0 + ry; r < r1; r += lanes_r) {
+        const size_t off = (size_t)r * C + cbase;
+        float xv[V], gv[V], o[V];
+        if (vec) { load_vec<T, V>(xv, xb + off); if (IS_BWD) load_vec<T, V>(gv, gb + off); }
+        else { xv[0] = to_f<T>(xb[off]); if (IS_BWD) gv[0] = to_f<T>(gb[off]); }
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          if (j < cw) {
+            if (!IS_BWD) {
+              const float yv = fmaf(xv[j], A[j], B[j]);
+              o[j] = SILU ? silu_f(yv) : yv;
+            } else {
+              const float xh = fmaf(xv[j], R[j], MR[j]);
+              float g2 = gv[j];
+              if (SILU) g2 *= dsilu_f(fmaf(xh, gm[j], bt[j]));
+              o[j] = fmaf(g2, A[j], fmaf(xh, NM2[j], NM1[j]));
+            }
+          }
+        }
+        if (vec) store_vec<T, V>(ob + off, o); else ob[off] = from_f<T>(o[0]);
+      }
     }
   }
 }
@@ -262,10 +279,21 @@ AB_API int ab_group_norm(int is_bwd, const void* x, const void* dy, void* out, c
   a.gsum = a.chan + (size_t)N * C * 3;
   const long long total = (long long)N * HW * C;
   long long want = units * splits;
-  const long long w4 = (total + kGnThreads * 16 - 1) / (kGnThreads * 16);
-  if (w4 > want) want = w4;
+  (void)total;
+  long long s3 = (4LL * kNumSMs * 2 + units - 1) / units;   // row splits of the apply phase: ~4 work items per CTA
+  if (s3 > HW / 32) s3 = HW / 32;
+  if (s3 < 1) s3 = 1;
+  a.splits3 = (int)s3;
+  if (units * s3 > want) want = units * s3;
   if (want < grid) grid = (int)want;
-  AB_DISPATCH_FLOAT3(dt, T, group_norm_kernel<T><<<grid, kGnThreads, 0, st>>>(a));
+#define GN_GO(T)                                                                                              \
+  do {                                                                                                        \
+    if (is_bwd) { if (silu) group_norm_kernel<T, true, true><<<grid, kGnThreads, 0, st>>>(a);                 \
+                  else group_norm_kernel<T, true, false><<<grid, kGnThreads, 0, st>>>(a); }                   \
+    else        { if (silu) group_norm_kernel<T, false, true><<<grid, kGnThreads, 0, st>>>(a);                \
+                  else group_norm_kernel<T, false, false><<<grid, kGnThreads, 0, st>>>(a); }                  \
+  } while (0)
+  AB_DISPATCH_FLOAT3(dt, T, GN_GO(T));
   AB_CHECK_LAUNCH();
   return 0;
 }
