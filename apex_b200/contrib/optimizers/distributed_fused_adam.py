@@ -88,7 +88,43 @@ class _Segment:
         self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
         self.norm_partials = torch.zeros(1024, dtype=torch.float32, device=dev) if dev.type == "cuda" else None
         self.synced = False      # reduced shard holds this step's reduce-scattered grads
+        self.scales = None
+        if getattr(opt, "with_scaled_states", False):
+            # per-(parameter x shard) fragment scale factors for the 16-bit state (reference :2693-2774,2833-2860): element i of the
+            # local shard belongs to fragment frag_index[i]; the padding shares one extra fragment
+            frags = self.fragments()
+            idx = torch.full((self.local_elems,), len(frags), dtype=torch.int64, device=dev)
+            for f, (_, s0, n) in enumerate(frags):
+                idx[s0:s0 + n] = f
+            self.frag_index = idx
+            self.scales = {k: torch.ones(len(frags) + 1, dtype=torch.float32, device=dev) for k in ("param", "exp_avg", "exp_avg_sq")}
         self._init_views()
+
+    def fragments(self):
+        """(parameter index, start in the local shard arrays, length) of every (parameter x this rank's shard) intersection."""
+        out = []
+        B, Sb, r = self.bucket_elems, self.shard_elems, self.rank
+        for pi, (p, off) in enumerate(zip(self.params, self.offsets)):
+            lo, hi = off, off + p.numel()
+            for b in range(lo // B, (hi - 1) // B + 1):
+                s_lo, s_hi = b * B + r * Sb, b * B + (r + 1) * Sb
+                a, z = max(lo, s_lo), min(hi, s_hi)
+                if z > a:
+                    out.append((pi, b * Sb + (a - s_lo), z - a))
+        return out
+
+    def load_scaled(self, key: str) -> torch.Tensor:
+        """fp32 value of a scaled 16-bit state tensor."""
+        t = {"param": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}[key]
+        return t.float() * self.scales[key][self.frag_index]
+
+    def store_scaled(self, key: str, value: torch.Tensor) -> None:
+        """value (fp32) -> 16-bit state with a fresh per-fragment scale = absmax / largest finite value of the state dtype."""
+        t = {"param": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}[key]
+        amax = torch.zeros_like(self.scales[key]).scatter_reduce_(0, self.frag_index, value.abs(), "amax", include_self=True)
+        sc = torch.where(amax > 0, amax / torch.finfo(t.dtype).max, torch.ones_like(amax))
+        self.scales[key].copy_(sc)
+        t.copy_((value / sc[self.frag_index]).to(t.dtype))
 
     # flat <-> shard helpers ------------------------------------------------------------------------------------------
     def shard_view(self, full: torch.Tensor, r: Optional[int] = None) -> torch.Tensor:
@@ -146,8 +182,8 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                  nccl_ub: bool = False, capturable: bool = False, fused_collectives="auto"):
         if amsgrad:
             raise RuntimeError("DistributedFusedAdam does not support the AMSGrad variant.")
-        if with_scaled_states:
-            raise NotImplementedError("with_scaled_states is not implemented yet")
+        if with_scaled_states and (dtype not in (torch.float16, torch.bfloat16) or not store_params or store_param_remainders):
+            raise RuntimeError("with_scaled_states needs 16-bit optimizer state (dtype=fp16/bf16) and store_params=True")
         defaults = dict(lr=lr, bias_correction=bias_correction, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.adam_w_mode = adam_w_mode
@@ -170,6 +206,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 raise RuntimeError("store_param_remainders requires fp32 optimizer state")
         self.store_params, self.store_param_remainders = store_params, store_param_remainders
         self.capturable = capturable
+        self.with_scaled_states = with_scaled_states
         self.nccl_ub = nccl_ub
         self._fused_request = fused_collectives
         self._param_view, self._grad_view, self._init_values = {}, {}, {}
@@ -217,7 +254,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         pairs = {(torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16), (torch.float32, torch.float32),
                  (torch.bfloat16, torch.float32), (torch.float16, torch.float32), (torch.float32, torch.bfloat16),
                  (torch.float32, torch.float16)}
-        return (self.fused_collectives and dtype == torch.float32 and self.store_params and grad_dtype in f and param_dtype in f
+        return (self.fused_collectives and not self.with_scaled_states and dtype == torch.float32 and self.store_params and grad_dtype in f and param_dtype in f
                 and (grad_dtype, param_dtype) in pairs)
 
     def init_params(self, params: Optional[Iterable[torch.nn.Parameter]] = None) -> None:
@@ -444,6 +481,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         out_shard = sv.reshape(-1) if inplace else sv.contiguous().view(-1)
         mode = 1 if self.adam_w_mode else 0
         bc = 1 if group["bias_correction"] else 0
+        scaled = seg.scales is not None
+        if scaled:
+            # 16-bit state with per-fragment scales: widen to fp32 temporaries, step, re-quantise with fresh scales
+            st32 = {k: seg.load_scaled(k) for k in ("param", "exp_avg", "exp_avg_sq")}
+            real = (seg.master, seg.exp_avg, seg.exp_avg_sq)
+            seg.master, seg.exp_avg, seg.exp_avg_sq = st32["param"], st32["exp_avg"], st32["exp_avg_sq"]
         if self.device.type == "cuda":
             g = seg.reduced
             if seg.remainders is not None:
@@ -465,6 +508,10 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             p_in = seg.master if seg.master is not None else out_shard
             ref.dist_adam(p_in, seg.exp_avg, seg.exp_avg_sq, seg.reduced, out_shard, self._grad_scale, group["lr"], beta1, beta2,
                           group["eps"], step, mode, bc, group["weight_decay"])
+        if scaled:
+            seg.master, seg.exp_avg, seg.exp_avg_sq = real
+            for k in ("param", "exp_avg", "exp_avg_sq"):
+                seg.store_scaled(k, st32[k])
         # scatter the contiguous shard back into the bucket-interleaved parameter buffer and all-gather
         if not inplace:
             sv.copy_(out_shard.view(seg.n_buckets, seg.shard_elems))
@@ -569,8 +616,11 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 i += 1
         state = {}
         for seg in self._segments:
-            fulls = {"exp_avg": self._gather_full(seg, seg.exp_avg), "exp_avg_sq": self._gather_full(seg, seg.exp_avg_sq)}
-            if seg.master is not None:
+            if seg.scales is not None:
+                fulls = {k: self._gather_full(seg, seg.load_scaled(k)) for k in ("exp_avg", "exp_avg_sq", "param")}
+            else:
+                fulls = {"exp_avg": self._gather_full(seg, seg.exp_avg), "exp_avg_sq": self._gather_full(seg, seg.exp_avg_sq)}
+            if seg.master is not None and seg.scales is None:
                 fulls["param"] = self._gather_full(seg, seg.master)
             elif seg.remainders is not None:
                 fulls["param_remainder"] = self._gather_full(seg, seg.remainders)
@@ -600,7 +650,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 index[id(p)] = i
                 i += 1
         for seg in self._segments:
-            fulls = {k: torch.zeros(seg.padded, dtype=t.dtype, device=self.device)
+            fulls = {k: torch.zeros(seg.padded, dtype=torch.float32 if seg.scales is not None else t.dtype, device=self.device)
                      for k, t in (("exp_avg", seg.exp_avg), ("exp_avg_sq", seg.exp_avg_sq), ("param", seg.master)) if t is not None}
             pfull = torch.zeros(seg.padded, dtype=torch.float32, device=self.device)
             for p, off in zip(seg.params, seg.offsets):
@@ -609,10 +659,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 for k in fulls:
                     fulls[k][off:off + n].copy_(ent[k].reshape(-1).to(self.device, fulls[k].dtype))
                 pfull[off:off + n].copy_(ent["param"].reshape(-1).to(self.device, torch.float32))
-            seg.exp_avg.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg"]))
-            seg.exp_avg_sq.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg_sq"]))
-            if seg.master is not None:
-                seg.master.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["param"]))
+            if seg.scales is not None:
+                for k in ("exp_avg", "exp_avg_sq", "param"):
+                    seg.store_scaled(k, seg.shard_view(fulls[k]).contiguous().view(-1))
+            else:
+                seg.exp_avg.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg"]))
+                seg.exp_avg_sq.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg_sq"]))
+                if seg.master is not None:
+                    seg.master.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["param"]))
             if seg.remainders is not None:
                 bits = seg.shard_view(pfull).contiguous().view(-1).view(torch.int32)
                 lo = (bits & 0xFFFF).to(torch.int32)

@@ -45,16 +45,7 @@ class DistributedFusedLAMB(DistributedFusedAdam):
         fr = self._frag_cache.get(id(seg))
         if fr is not None:
             return fr
-        out = []  # (param_index, local_start, length)
-        B, Sb, r = seg.bucket_elems, seg.shard_elems, seg.rank
-        for pi, (p, off) in enumerate(zip(seg.params, seg.offsets)):
-            lo, hi = off, off + p.numel()
-            b0, b1 = lo // B, (hi - 1) // B
-            for b in range(b0, b1 + 1):
-                s_lo, s_hi = b * B + r * Sb, b * B + (r + 1) * Sb
-                a, z = max(lo, s_lo), min(hi, s_hi)
-                if z > a:
-                    out.append((pi, b * Sb + (a - s_lo), z - a))
+        out = seg.fragments()  # (param_index, local_start, length)
         self._frag_cache[id(seg)] = out
         return out
 

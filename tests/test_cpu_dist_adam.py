@@ -56,3 +56,29 @@ def test_two_ranks_gloo_state_dict(tmp_path):
 
 def test_two_ranks_gloo_dist_lamb():
     run_distributed(cases.dist_lamb_matches_fused_lamb, 2, "cpu", backend="gloo")
+
+
+def test_scaled_states_track_adamw():
+    """with_scaled_states: bf16 optimizer state + per-fragment fp32 scales stays within bf16 resolution of fp32 AdamW,
+    including parameters whose magnitude is far from 1 (reference distributed_fused_adam.py:2693-2774)."""
+    import torch
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    w = [torch.randn(300, 7), torch.randn(129) * 1e-3, torch.randn(64, 64) * 30]
+    ps = [torch.nn.Parameter(t.clone().bfloat16()) for t in w]
+    qs = [torch.nn.Parameter(t.clone().bfloat16().float()) for t in w]
+    a = DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.01, dtype=torch.bfloat16, with_scaled_states=True, device="cpu", bucket_cap_mb=0.01)
+    b = torch.optim.AdamW(qs, lr=1e-2, weight_decay=0.01)
+    for it in range(5):
+        a.zero_grad()
+        for p, q in zip(ps, qs):
+            g = torch.randn(p.shape) * (0.5 + it)
+            p.grad.copy_(g.bfloat16())
+            q.grad = g.bfloat16().float()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        assert (p.float() - q).abs().max() <= 8e-3 * q.abs().max() + 1e-6
+    sd = a.state_dict()
+    assert sd["state"][0]["exp_avg"].dtype == torch.float32
+    a.load_state_dict(sd)
