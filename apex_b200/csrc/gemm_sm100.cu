@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < KSTAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     }
   } else if (warp >= kEpiWarp0) {
     // ===================================================== epilogue: TMEM -> registers -> fused op -> global
-    const int q = warp - kEpiWarp0;  // == warp % 4: the TMEM lane quarter this warp may touch
+    const int q = (warp - kEpiWarp0) & 3, half = (warp - kEpiWarp0) >> 2;  // q == warp % 4: the TMEM lane quarter this warp may touch
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after();
       const int row = m_blk * BM + q * 32 + lane;
-      epilogue_tile<TOut, BN>(p, tmem_base, acc, row, n_blk, q);
+      epilogue_tile<TOut, BN>(p, tmem_base, acc, row, n_blk, q, half);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 // FFN GEMM), and the freed shared memory deepens the ring to 6 stages. Accumulators: rows 0-127 in CTA0's TMEM, 128-255 in CTA1's.
 //   full[s]   (leader's copy is the one waited on): both CTAs' TMA loads complete_tx on the LEADER's barrier
 //   empty[s]  / tmem_full[a]: tcgen05.commit ... multicast::cluster to both CTAs
-//   tmem_empty[a] (leader's copy): 128 local + 128 remote (mapa) arrivals from the two epilogues
+//   tmem_empty[a] (leader's copy): 256 local + 256 remote (mapa) arrivals from the two 8-warp epilogues
 // =====================================================================================================================
 constexpr int BN2 = 256;
 
@@ -242,7 +242,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < KSTAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 256); }
+    for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 512); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc2(tmem_ptr, kTmemCols);
@@ -312,14 +312,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
   } else if (warp >= kEpiWarp0) {
     // ===================================================== epilogue (both CTAs: their own 128 rows)
-    const int q = warp - kEpiWarp0;
+    const int q = (warp - kEpiWarp0) & 3, half = (warp - kEpiWarp0) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 14);
       tc_fence_after();
       const int row = m_blk * 2 * BM + (int)cta * BM + q * 32 + lane;
-      epilogue_tile<TOut, BN2>(p, tmem_base, acc, row, n_blk, q);
+      epilogue_tile<TOut, BN2>(p, tmem_base, acc, row, n_blk, q, half);
       tc_fence_before();
       if (leader) mbar_arrive(&tmem_empty[acc]);
       else mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty[acc]), 0));

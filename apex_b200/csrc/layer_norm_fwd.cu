@@ -3,34 +3,32 @@
 // Spec: reference csrc/layer_norm_cuda_kernel.cu:317-376,803-835 (cuApplyLayerNorm / cuApplyRMSNorm: outputs y, mean[n1],
 // invvar[n1] fp32; gamma/beta have the OUTPUT dtype) and apex/contrib/csrc/layer_norm/ln_fwd_kernels.cuh:6-107.
 #include "norm_common.cuh"
+#include <cstdlib>
 
 namespace ab {
 
 // Instruction budget matters as much as bytes here (bf16: 4 B/element of traffic buys ~20 issue slots per element at the HBM
-// roofline): x is decoded twice (not three times) thanks to single-pass shifted statistics, gamma / beta are loop-invariant per
-// thread and live in registers as packed raw bits, and the output is two FFMAs per element (y = x*A + B, A = rstd*gamma,
-// B = beta - mean*A). The next row group's loads are issued before this one's reduction (register double buffering).
+// roofline): x is decoded twice (not three times) thanks to single-pass shifted statistics, gamma / beta are converted to fp32
+// ONCE per CTA into shared memory (16-byte LDS instead of a global load + convert per element and row), and the output is
+// y = x*A + B with A = rstd*gamma, B = beta - mean*A. Narrow rows (<= 2 vectors per thread) also prefetch the next row group.
 template <int MAXV, typename Tin, typename Tout, bool RMS>
 __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
                                                    float* __restrict__ invvar, const Tout* __restrict__ gamma,
-                                                   const Tout* __restrict__ beta, int n1, int n2, float eps, int tpr) {
+                                                   const Tout* __restrict__ beta, int n1, int n2, float eps, int tpr, int gb_smem) {
   constexpr int E = 16 / sizeof(Tin);
-  constexpr int GW = E * sizeof(Tout) / 4;  // 32-bit words of one gamma / beta vector
   constexpr bool PREFETCH = MAXV <= 2;
   __shared__ float sred[128];
+  extern __shared__ float gb_sm[];  // [2][n2] fp32 gamma, beta when gb_smem
   RowReducer red(sred, tpr);
   const int rows_per_cta = blockDim.x / tpr;
   const int nvec = n2 / E;
   const float inv_n = 1.f / (float)n2;
-  uint32_t graw[MAXV][GW], braw[MAXV][GW];
-#pragma unroll
-  for (int v = 0; v < MAXV; v++) {
-    const int idx = v * tpr + red.lane_r;
-#pragma unroll
-    for (int q = 0; q < GW; q++) {
-      graw[v][q] = (gamma && idx < nvec) ? reinterpret_cast<const uint32_t*>(gamma + (size_t)idx * E)[q] : 0u;
-      braw[v][q] = (beta && idx < nvec) ? reinterpret_cast<const uint32_t*>(beta + (size_t)idx * E)[q] : 0u;
+  if (gb_smem && gamma) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      gb_sm[i] = to_f<Tout>(gamma[i]);
+      gb_sm[n2 + i] = beta ? to_f<Tout>(beta[i]) : 0.f;
     }
+    __syncthreads();
   }
   auto load_rows = [&](int row0, uint4 (&raw)[MAXV], float& shift) {
     const int row = row0 + red.rg;
@@ -44,7 +42,7 @@ __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tou
     shift = (!RMS && valid) ? to_f<Tin>(__ldg(x + (size_t)row * n2)) : 0.f;  // a sample of the row: kills the cancellation in E[d^2]-E[d]^2
   };
   const int row_step = gridDim.x * rows_per_cta;
-  uint4 raw[MAXV], raw_n[MAXV];
+  uint4 raw[MAXV], raw_n[PREFETCH ? MAXV : 1];
   float shift = 0.f, shift_n = 0.f;
   if (PREFETCH && blockIdx.x * rows_per_cta < n1) load_rows(blockIdx.x * rows_per_cta, raw, shift);
   for (int row0 = blockIdx.x * rows_per_cta; row0 < n1; row0 += row_step) {
@@ -52,7 +50,7 @@ __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tou
     const bool valid = row < n1;
     const bool more = PREFETCH && row0 + row_step < n1;
     if (!PREFETCH) load_rows(row0, raw, shift);
-    if (more) load_rows(row0 + row_step, raw_n, shift_n);
+    if constexpr (PREFETCH) { if (more) load_rows(row0 + row_step, raw_n, shift_n); }
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int v = 0; v < MAXV; v++) {
@@ -90,14 +88,27 @@ __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tou
           float f[E]; unpack16<Tin>(raw[v], f);
           float o[E];
           if (gamma) {
-            const Tout* ge = reinterpret_cast<const Tout*>(graw[v]);
-            const Tout* be = reinterpret_cast<const Tout*>(braw[v]);
+            float g[E], bb[E];
+            if (gb_smem) {
+#pragma unroll
+              for (int q = 0; q < E / 4; q++) {
+                const float4 g4 = reinterpret_cast<const float4*>(gb_sm + (size_t)idx * E)[q];
+                const float4 b4 = reinterpret_cast<const float4*>(gb_sm + n2 + (size_t)idx * E)[q];
+                g[4 * q] = g4.x; g[4 * q + 1] = g4.y; g[4 * q + 2] = g4.z; g[4 * q + 3] = g4.w;
+                bb[4 * q] = b4.x; bb[4 * q + 1] = b4.y; bb[4 * q + 2] = b4.z; bb[4 * q + 3] = b4.w;
+              }
+            } else {
+              load_vec<Tout, E>(g, gamma + (size_t)idx * E);
+              if (beta) load_vec<Tout, E>(bb, beta + (size_t)idx * E);
+              else {
+#pragma unroll
+                for (int e = 0; e < E; e++) bb[e] = 0.f;
+              }
+            }
 #pragma unroll
             for (int e = 0; e < E; e++) {
-              const float g = to_f<Tout>(ge[e]);
-              const float A = rstd * g;
-              const float Bc = beta ? fmaf(nmr, g, to_f<Tout>(be[e])) : nmr * g;
-              o[e] = fmaf(f[e], A, Bc);
+              const float A = rstd * g[e];
+              o[e] = fmaf(f[e], A, fmaf(nmr, g[e], bb[e]));
             }
           } else {
 #pragma unroll
@@ -107,10 +118,12 @@ __global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tou
         }
       }
     }
-    if (more) {
+    if constexpr (PREFETCH) {
+      if (more) {
 #pragma unroll
-      for (int v = 0; v < MAXV; v++) raw[v] = raw_n[v];
-      shift = shift_n;
+        for (int v = 0; v < MAXV; v++) raw[v] = raw_n[v];
+        shift = shift_n;
+      }
     }
   }
 }
@@ -149,14 +162,18 @@ int ln_fwd_launch(const void* x, void* y, float* mean, float* invvar, const void
   constexpr int E = 16 / sizeof(Tin);
   const bool vec_ok = (n2 % E == 0) && aligned16(x) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 && aligned16(y) &&
                       ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
-  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, 2, 512);
+  static const int target_v = getenv("APEX_B200_LN_FWD_V") ? atoi(getenv("APEX_B200_LN_FWD_V")) : 2;  // tuning knob (vectors / thread)
+  NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, target_v, 512);
   if (vec_ok && c.ok) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
-    const int cap = kNumSMs * (1024 / c.threads);  // ~3 x 256-thread CTAs are resident per SM at this register budget
+    // fp32 gamma / beta staged in shared memory when 4 CTAs per SM still fit (<= 48 KB each), else read through L1
+    const size_t dyn = (gamma && (size_t)2 * n2 * sizeof(float) <= 64 * 1024) ? (size_t)2 * n2 * sizeof(float) : 0;
+    const int cap = kNumSMs * (1024 / c.threads);
     if (grid > cap) grid = cap;
 #define LN_FWD_GO(MV)                                                                                                 \
-  ln_fwd_vec<MV, Tin, Tout, RMS><<<grid, c.threads, 0, st>>>((const Tin*)x, (Tout*)y, mean, invvar, (const Tout*)gamma, \
-                                                             (const Tout*)beta, n1, n2, eps, c.tpr)
+  if (dyn > 48 * 1024) cudaFuncSetAttribute(ln_fwd_vec<MV, Tin, Tout, RMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); \
+  ln_fwd_vec<MV, Tin, Tout, RMS><<<grid, c.threads, dyn, st>>>((const Tin*)x, (Tout*)y, mean, invvar, (const Tout*)gamma, \
+                                                             (const Tout*)beta, n1, n2, eps, c.tpr, dyn ? 1 : 0)
     switch (c.maxv) {
       case 1: LN_FWD_GO(1); break;
       case 2: LN_FWD_GO(2); break;

@@ -25,9 +25,10 @@ struct RowReducer {
     float* b = smem + bank * 64;
     if ((threadIdx.x & 31) == 0) b[w] = v;
     __syncthreads();
-    float t = 0.f;
-    const int w0 = rg * wpr;
-    for (int i = 0; i < wpr; i++) t += b[w0 + i];
+    const int l = threadIdx.x & 31, w0 = rg * wpr;
+    float t = l < wpr ? b[w0 + l] : 0.f;
+    for (int o = wpr >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    t = __shfl_sync(0xffffffffu, t, 0);
     bank ^= 1;
     return t;
   }
@@ -43,9 +44,11 @@ struct RowReducer {
     float* b = smem + bank * 64;
     if ((threadIdx.x & 31) == 0) { b[w] = a; b[32 + w] = c; }
     __syncthreads();
-    float ta = 0.f, tc = 0.f;
-    const int w0 = rg * wpr;
-    for (int i = 0; i < wpr; i++) { ta += b[w0 + i]; tc += b[32 + w0 + i]; }
+    // lanes [0, wpr) of every warp pick one warp partial each, xor-shuffles finish (wpr is a power of two <= 32)
+    const int l = threadIdx.x & 31, w0 = rg * wpr;
+    float ta = l < wpr ? b[w0 + l] : 0.f, tc = l < wpr ? b[32 + w0 + l] : 0.f;
+    for (int o = wpr >> 1; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tc += __shfl_xor_sync(0xffffffffu, tc, o); }
+    ta = __shfl_sync(0xffffffffu, ta, 0); tc = __shfl_sync(0xffffffffu, tc, 0);
     bank ^= 1;
     a = ta; c = tc;
   }

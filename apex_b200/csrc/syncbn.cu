@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
   const T* __restrict__ x = reinterpret_cast<const T*>(a.x);
   const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
   const T* __restrict__ z = FUSED ? reinterpret_cast<const T*>(a.z) : nullptr;
-  const bool fuse_relu = FUSED && fuse_relu;
+  const bool fuse_relu = FUSED && a.fuse_relu;
   const long long per_c = (long long)a.N * a.HW;
   const int S = a.splits;
   const int C = a.C, HW = a.HW;
