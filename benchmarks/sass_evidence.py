@@ -28,7 +28,7 @@ for f in sorted(os.listdir(objdir)):
             continue
         op = m.group(1)
         for p in PAT:
-            if p in op:
+            if (op.startswith(p) if p == "HMMA" else p in op):
                 cnt[p] += 1
     out.append(f"| {f} | " + " | ".join(str(cnt[p]) if cnt[p] else "" for p in PAT) + " |")
 open(os.path.join(ROOT, "profiles", "sass_evidence.md"), "w").write("\n".join(out) + "\n")
