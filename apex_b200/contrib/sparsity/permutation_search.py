@@ -89,6 +89,7 @@ def _score_groups(m: torch.Tensor, groups: torch.Tensor, cands_np: np.ndarray):
     G, S = groups.shape
     P, W = cands_np.shape
     base = _stripe_sums(m)[groups.long()].sum(1)
+    noise = 2e-6 * base.abs()  # the two sides are summed in different orders: differences below fp32 rounding are not improvements
     if m.is_cuda and _lib.available():
         cands = torch.from_numpy(cands_np).to(m.device)
         chunks = (P + 255) // 256
@@ -100,7 +101,8 @@ def _score_groups(m: torch.Tensor, groups: torch.Tensor, cands_np: np.ndarray):
         # ties across chunks -> the lowest candidate id
         is_best = pv == best[:, None]
         idx = torch.where(is_best, pi, torch.full_like(pi, 2 ** 31 - 1)).min(1).values
-        return best - base, idx.long()
+        imp = best - base
+        return torch.where((imp > noise) & (idx != 0), imp, torch.zeros_like(imp)), idx.long()
     a = m.abs()
     cands = torch.from_numpy(cands_np.astype(np.int64))
     cols = (groups.long()[:, :, None] * 4 + torch.arange(4)).reshape(G, W)          # [G, W] matrix columns of each group
@@ -116,7 +118,8 @@ def _score_groups(m: torch.Tensor, groups: torch.Tensor, cands_np: np.ndarray):
             if float(v) > bv:
                 bv, bi = float(v), c0 + int(i)
         best[g], idx[g] = bv, bi
-    return best - base, idx
+    imp = best - base
+    return torch.where((imp > noise) & (idx != 0), imp, torch.zeros_like(imp)), idx
 
 
 # ---------------------------------------------------------------------------------------------------------------- strategies
