@@ -12,7 +12,9 @@ from torch import nn
 
 from ... import _lib
 
-_lib.declare("ab_group_norm", "i p p p p p i p p p p p l p i i i i f i i p")
+_lib.declare("ab_group_norm", "i p p p p p i p p p p p l p i i i i i f i i p")
+
+_MAX_N = 8192  # per-image arrival counters / ready flags live in a fixed control buffer
 
 _state: dict = {}
 
@@ -32,23 +34,26 @@ def torch_group_norm(x, g, w, b, eps, act=""):
 def _scratch(device, need):
     st = _state.get(device)
     if st is None or st[0].numel() < need:
-        st = _state[device] = (torch.empty(max(need, 1 << 20), dtype=torch.float32, device=device),
-                               torch.zeros(2, dtype=torch.int32, device=device))
+        st = _state[device] = [torch.empty(max(need, 1 << 20), dtype=torch.float32, device=device),
+                               torch.zeros(1 + 2 * _MAX_N, dtype=torch.int32, device=device) if st is None else st[1], 0 if st is None else st[2]]
     return st
 
 
 def _native_ok(x, w):
     return (x.is_cuda and _lib.available() and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16, torch.float32)
-            and x.is_contiguous(memory_format=torch.channels_last) and (w is None or w.dtype in (x.dtype, torch.float32)))
+            and x.is_contiguous(memory_format=torch.channels_last) and (w is None or w.dtype in (x.dtype, torch.float32))
+            and x.shape[0] <= _MAX_N)
 
 
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
     need = N * C * 16 * 3 + N * C * 3 + N * G * 2 + 64
-    scratch, bar = _scratch(x.device, need)
+    st = _scratch(x.device, need)
+    scratch, ctrl = st[0], st[1]
+    st[2] += 1  # launch epoch: the kernel publishes "image n is normalisable" by writing this value into the image's ready flag
     w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
     _lib.fn("ab_group_norm")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
-                             rstd.data_ptr(), _lib.ptr(dg), _lib.ptr(db), scratch.data_ptr(), scratch.numel(), bar.data_ptr(), N, H * W, C, G,
+                             rstd.data_ptr(), _lib.ptr(dg), _lib.ptr(db), scratch.data_ptr(), scratch.numel(), ctrl.data_ptr(), st[2] & 0x7FFFFFFF, N, H * W, C, G,
                              float(eps), int(silu), _lib.dt(x), _lib.stream_ptr(x.device))
 
 

@@ -1,8 +1,11 @@
-// NHWC GroupNorm (+ fused SiLU / swish), forward and backward, as ONE persistent kernel per direction:
-//   [1] per-(image, channel) partial statistics over row splits (threads own 16-byte channel vectors, rows are 4x unrolled)
-//   [2] after a grid barrier: fold splits and the C/G channels of each group -> mean / rstd per (n, g)  (bwd: the two
-//       gamma-weighted group sums, and dgamma / dbeta)
-//   [4] after a grid barrier: y = silu?(x * sc + sh) with per-(n, c) coefficients; the second read of x comes from the 126 MB L2.
+// NHWC GroupNorm (+ fused SiLU / swish), forward and backward, as ONE persistent, dependency-driven kernel per direction:
+//   stage 1  per-(image, channel, row-split) partial statistics (threads own 16-byte channel vectors, rows 4x unrolled). Every work
+//            item bumps its image's arrival counter; the item that arrives LAST folds the image's groups (mean / rstd per (n, g);
+//            bwd: the gamma-weighted group sums and the per-(n, c) sums, and -- when the last image is folded -- dgamma / dbeta)
+//            and publishes the image by writing the launch epoch into its ready flag.
+//   stage 2  y = silu?(x*A + B) with per-(n, c) coefficients (bwd: dx = g*RG + xhat*NM2 + NM1); an item only waits for ITS image's
+//            flag, so images are normalised while later images are still being reduced. The second read of x comes from the 126 MB L2.
+// There is no grid-wide barrier: a CTA finishes all of its stage-1 items before it can wait, and the grid is sized to be co-resident.
 // Any C / G / H*W (the reference supports 23 hard-coded channel counts for G in {16, 32} and, for its Blackwell path,
 // 14 (HW, C) shapes: apex/contrib/group_norm/group_norm.py:247-289,390-416; kernels apex/contrib/csrc/group_norm_v2/
 // gn_cuda_kernel.cuh:195,596 use hardware clusters of 2 + DSMEM or atom.add flip barriers for the same stats->apply dependency).
@@ -22,26 +25,11 @@ struct GnArgs {
   float* partial;                         // [N*C][S][3]
   float* chan;                            // [N*C][3] per-(n,c) merged values
   float* gsum;                            // [N*G][2] bwd: gamma-weighted group sums / M
-  unsigned int* grid_bar;
-  int N, HW, C, G, splits, splits3, silu, is_bwd, phases;
+  unsigned int* ctrl;                     // [0] done-image counter, [1 .. 1+N) per-image arrival counters, [1+N .. 1+2N) per-image ready epochs
+  unsigned int epoch;                     // value that marks THIS launch in the ready flags (strictly increasing per ctrl buffer)
+  int N, HW, C, G, splits, splits3, silu, is_bwd;
   float eps;
 };
-
-__device__ __forceinline__ void gn_grid_barrier(unsigned int* bar, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned int* gen = bar + 1;
-    const unsigned int g = *gen;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == nblocks - 1) { bar[0] = 0u; __threadfence(); atomicAdd(bar + 1, 1u); }
-    else {
-      long long t0 = clock64();
-      while (*gen == g) { if (clock64() - t0 > 20000000000LL) { printf("apex_b200 group_norm: grid barrier timeout\n"); __trap(); } }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
 
 struct GW { float mean, m2, n; };
 __device__ __forceinline__ GW gw_merge(const GW& a, const GW& b) {
@@ -55,8 +43,8 @@ template <typename T>
 __device__ __forceinline__ float ld_w(const void* p, int fp32, int c) {
   return fp32 ? reinterpret_cast<const float*>(p)[c] : to_f<T>(reinterpret_cast<const T*>(p)[c]);
 }
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
-__device__ __forceinline__ float dsilu_f(float v) { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f + v * (1.f - s)); }
+__device__ __forceinline__ float silu_f(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float dsilu_f(float v) { const float s = __frcp_rn(1.f + __expf(-v)); return s * (1.f + v * (1.f - s)); }
 
 // IS_BWD / SILU are compile-time. Threads are laid out (cx, ry): cx owns V adjacent channels (one 16-byte vector), ry strides over
 // rows, so everything that depends on the channel only -- shift, gamma, beta, the per-(n, c) normalisation coefficients -- is
@@ -75,8 +63,13 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
   const int ctiles = (C + tile_c - 1) / tile_c;
   const int cx = tid % lanes_c, ry = tid / lanes_c;
 
-  // ------------------------------------------------------------------ phase 1: per-(n, c, split) partial sums
-  if (a.phases & 1) {
+  __shared__ int s_last;
+  unsigned int* img_ctr = a.ctrl + 1;
+  unsigned int* ready = a.ctrl + 1 + a.N;
+  const int lane_ = tid & 31;
+  // ------------------------------------------------------------------ stage 1: per-(n, c, split) partial sums; the LAST item of an
+  // image to finish folds that image's groups and raises the image's ready flag (no grid-wide barrier anywhere in this kernel)
+  {
     const int items = a.N * ctiles * S;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int s = it % S, ct = (it / S) % ctiles, n = it / (S * ctiles);
@@ -145,64 +138,84 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
           p[0] = m; p[1] = m2; p[2] = cnt;
         } else { p[0] = t0; p[1] = t1; p[2] = 0.f; }
       }
-    }
-    if (a.phases & 6) gn_grid_barrier(a.grid_bar, gridDim.x);
-  }
-
-  // ------------------------------------------------------------------ phase 2: one warp per (n, g)
-  if (a.phases & 2) {
-    const int gw = (blockIdx.x * kGnThreads + tid) >> 5, nw = (gridDim.x * kGnThreads) >> 5;
-    for (int ng = gw; ng < a.N * G; ng += nw) {
-      const int n = ng / G, g = ng - n * G;
-      if (!IS_BWD) {
-        GW w{0.f, 0.f, 0.f};
-        for (int q = lane; q < Cg * S; q += 32) {
-          const int c = g * Cg + q / S, s = q % S;
-          const float* p = a.partial + (((size_t)n * C + c) * S + s) * 3;
-          w = gw_merge(w, GW{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)});
-        }
+      // ---- arrival: the last item of image n folds its groups
+      __syncthreads();
+      if (tid == 0) { __threadfence(); s_last = (atomicAdd(img_ctr + n, 1u) == (unsigned)(ctiles * S - 1)); }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        for (int g = wid; g < G; g += kGnThreads / 32) {
+          const int ng = n * G + g;
+          if (!IS_BWD) {
+            GW w{0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int q = lane_; q < Cg * S; q += 32) {
+              const int c = g * Cg + q / S, sp = q % S;
+              const float* p = a.partial + (((size_t)n * C + c) * S + sp) * 3;
+              w = gw_merge(w, GW{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)});
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-          w = gw_merge(w, GW{__shfl_xor_sync(0xffffffffu, w.mean, o), __shfl_xor_sync(0xffffffffu, w.m2, o), __shfl_xor_sync(0xffffffffu, w.n, o)});
-        if (lane == 0) { a.mean[ng] = w.mean; a.rstd[ng] = rsqrtf((w.n > 0.f ? w.m2 / w.n : 0.f) + a.eps); }
-      } else {
-        float m1 = 0.f, m2 = 0.f;
-        for (int q = lane; q < Cg; q += 32) {
-          const int c = g * Cg + q;
-          float s1 = 0.f, s2 = 0.f;
-          for (int s = 0; s < S; s++) { const float* p = a.partial + (((size_t)n * C + c) * S + s) * 3; s1 += __ldcg(p); s2 += __ldcg(p + 1); }
-          float* cc = a.chan + ((size_t)n * C + c) * 3;
-          cc[0] = s1; cc[1] = s2;
-          const float gmv = ld_w<T>(a.gamma, a.w_fp32, c);
-          m1 += gmv * s1; m2 += gmv * s2;
+            for (int o = 16; o > 0; o >>= 1)
+              w = gw_merge(w, GW{__shfl_xor_sync(0xffffffffu, w.mean, o), __shfl_xor_sync(0xffffffffu, w.m2, o), __shfl_xor_sync(0xffffffffu, w.n, o)});
+            if (lane_ == 0) { a.mean[ng] = w.mean; a.rstd[ng] = rsqrtf((w.n > 0.f ? w.m2 / w.n : 0.f) + a.eps); }
+          } else {
+            float m1 = 0.f, m2 = 0.f;
+            for (int q = lane_; q < Cg; q += 32) {
+              const int c = g * Cg + q;
+              float s1 = 0.f, s2 = 0.f;
+              for (int sp = 0; sp < S; sp++) { const float* p = a.partial + (((size_t)n * C + c) * S + sp) * 3; s1 += __ldcg(p); s2 += __ldcg(p + 1); }
+              float* cc = a.chan + ((size_t)n * C + c) * 3;
+              cc[0] = s1; cc[1] = s2;
+              const float gmv = ld_w<T>(a.gamma, a.w_fp32, c);
+              m1 += gmv * s1; m2 += gmv * s2;
+            }
+            m1 = warp_sum(m1); m2 = warp_sum(m2);
+            if (lane_ == 0) { const float invM = 1.f / ((float)HW * (float)Cg); a.gsum[ng * 2] = m1 * invM; a.gsum[ng * 2 + 1] = m2 * invM; }
+          }
         }
-        m1 = warp_sum(m1); m2 = warp_sum(m2);
-        if (lane == 0) { const float invM = 1.f / ((float)HW * (float)Cg); a.gsum[ng * 2] = m1 * invM; a.gsum[ng * 2 + 1] = m2 * invM; }
+        __syncthreads();
+        if (tid == 0) {
+          img_ctr[n] = 0u;
+          __threadfence();
+          atomicExch(ready + n, a.epoch);                       // image n may now be normalised
+          s_last = IS_BWD && a.dgamma && (atomicAdd(a.ctrl, 1u) == (unsigned)(a.N - 1));
+        }
+        __syncthreads();
+        if (IS_BWD && s_last) {                                   // every image is folded: dgamma / dbeta over the batch
+          __threadfence();
+          for (int c = tid; c < C; c += kGnThreads) {
+            float dg = 0.f, db = 0.f;
+            for (int nn = 0; nn < a.N; nn++) { const float* cc = a.chan + ((size_t)nn * C + c) * 3; db += __ldcg(cc); dg += __ldcg(cc + 1); }
+            a.dgamma[c] = dg;
+            if (a.dbeta) a.dbeta[c] = db;
+          }
+          if (tid == 0) a.ctrl[0] = 0u;
+        }
       }
     }
-    if (IS_BWD && a.dgamma) {
-      gn_grid_barrier(a.grid_bar, gridDim.x);
-      for (int c = blockIdx.x * kGnThreads + tid; c < C; c += gridDim.x * kGnThreads) {
-        float dg = 0.f, db = 0.f;
-        for (int n = 0; n < a.N; n++) { const float* cc = a.chan + ((size_t)n * C + c) * 3; db += __ldcg(cc); dg += __ldcg(cc + 1); }
-        a.dgamma[c] = dg;
-        if (a.dbeta) a.dbeta[c] = db;
-      }
-    }
-    if (a.phases & 4) gn_grid_barrier(a.grid_bar, gridDim.x);
   }
 
   // ------------------------------------------------------------------ phase 3: apply, same (cx, ry) layout, x re-read from L2
   //   fwd: y  = silu?(x*A + B)                          A = rstd*gamma, B = beta - mean*A
   //   bwd: dx = g*RG + xhat*NM2 + NM1, xhat = x*R + MR   g = dy (* dsilu(xhat*gamma + beta)), RG = rstd*gamma, NMk = -rstd*mk
-  if (a.phases & 4) {
+  {
     const int S3 = a.splits3;
     const int items = a.N * ctiles * S3;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const int s = it % S3, ct = (it / S3) % ctiles, n = it / (S3 * ctiles);
+      // wait until image n's statistics are published (every CTA has already finished ALL of its stage-1 items, so the image's
+      // remaining contributors are running on other, co-resident CTAs: no deadlock)
+      if (tid == 0) {
+        long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned int*>(ready + n) != a.epoch) {
+          if (clock64() - t0 > 20000000000LL) { printf("apex_b200 group_norm: image %d never became ready\n", n); __trap(); }
+        }
+        __threadfence();
+      }
+      __syncthreads();
       const int r0 = (int)((long long)HW * s / S3), r1 = (int)((long long)HW * (s + 1) / S3);
       const int cbase = ct * tile_c + cx * cw;
-      if (cbase >= C) continue;
+      const bool c_ok3 = cbase < C;
       float A[V], B[V], R[V], MR[V], NM1[V], NM2[V], gm[V], bt[V];
 #pragma unroll
       for (int j = 0; j < V; j++) {
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
       const T* gb = IS_BWD ? dy + (size_t)n * HW * C : nullptr;
       T* ob = out + (size_t)n * HW * C;
 #pragma unroll 4
-      for (int r = r0 + ry; r < r1; r += lanes_r) {
+      for (int r = r0 + ry; c_ok3 && r < r1; r += lanes_r) {
         const size_t off = (size_t)r * C + cbase;
         float xv[V], gv[V], o[V];
         if (vec) { load_vec<T, V>(xv, xb + off); if (IS_BWD) load_vec<T, V>(gv, gb + off); }
@@ -258,12 +271,12 @@ AB_API long long ab_group_norm_scratch_floats(int N, int C, int G, int max_split
 }
 
 AB_API int ab_group_norm(int is_bwd, const void* x, const void* dy, void* out, const void* gamma, const void* beta, int w_fp32, float* mean,
-                         float* rstd, float* dgamma, float* dbeta, float* scratch, long long scratch_floats, unsigned int* grid_bar, int N,
+                         float* rstd, float* dgamma, float* dbeta, float* scratch, long long scratch_floats, unsigned int* ctrl, unsigned int epoch, int N,
                          int HW, int C, int G, float eps, int silu, int dt, cudaStream_t st) {
   if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0) return -2;
   GnArgs a;
   a.x = x; a.dy = dy; a.out = out; a.gamma = gamma; a.beta = beta; a.w_fp32 = w_fp32; a.mean = mean; a.rstd = rstd; a.dgamma = dgamma;
-  a.dbeta = dbeta; a.grid_bar = grid_bar; a.N = N; a.HW = HW; a.C = C; a.G = G; a.eps = eps; a.silu = silu; a.is_bwd = is_bwd; a.phases = 7;
+  a.dbeta = dbeta; a.ctrl = ctrl; a.epoch = epoch; a.N = N; a.HW = HW; a.C = C; a.G = G; a.eps = eps; a.silu = silu; a.is_bwd = is_bwd;
   int grid = kNumSMs * 2;
   const int ctiles = (C + 63) / 64;
   long long units = (long long)N * ctiles;

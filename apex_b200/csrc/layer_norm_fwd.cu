@@ -12,7 +12,7 @@ namespace ab {
 // ONCE per CTA into shared memory (16-byte LDS instead of a global load + convert per element and row), and the output is
 // y = x*A + B with A = rstd*gamma, B = beta - mean*A. Narrow rows (<= 2 vectors per thread) also prefetch the next row group.
 template <int MAXV, typename Tin, typename Tout, bool RMS>
-__global__ void __launch_bounds__(512) ln_fwd_vec(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
+__global__ void __launch_bounds__(512, MAXV <= 4 ? 2 : 1) ln_fwd_vec(const Tin* __restrict__ x, Tout* __restrict__ y, float* __restrict__ mean,
                                                    float* __restrict__ invvar, const Tout* __restrict__ gamma,
                                                    const Tout* __restrict__ beta, int n1, int n2, float eps, int tpr, int gb_smem) {
   constexpr int E = 16 / sizeof(Tin);
@@ -162,7 +162,7 @@ int ln_fwd_launch(const void* x, void* y, float* mean, float* invvar, const void
   constexpr int E = 16 / sizeof(Tin);
   const bool vec_ok = (n2 % E == 0) && aligned16(x) && ((size_t)n2 * sizeof(Tin)) % 16 == 0 && aligned16(y) &&
                       ((size_t)n2 * sizeof(Tout)) % 16 == 0 && (!gamma || aligned16(gamma)) && (!beta || aligned16(beta));
-  static const int target_v = getenv("APEX_B200_LN_FWD_V") ? atoi(getenv("APEX_B200_LN_FWD_V")) : 2;  // tuning knob (vectors / thread)
+  static const int target_v = getenv("APEX_B200_LN_FWD_V") ? atoi(getenv("APEX_B200_LN_FWD_V")) : 4;  // tuning knob (vectors / thread)
   NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, target_v, 512);
   if (vec_ok && c.ok) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;

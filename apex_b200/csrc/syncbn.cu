@@ -290,31 +290,29 @@ __global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
         __syncthreads();
         if (s_last) {
           __threadfence();
-          const int ch = tid % tile_c, grp = tid / tile_c, ngrp = kBnThreads / tile_c;
-          const int c = ct * tile_c + ch;
-          Wf w{0.f, 0.f, 0.f};
-          float s0 = 0.f, s1 = 0.f;
-          if (c < C) {
+          // warp w merges channels w, w+8, ...: lanes stride over the S split partials (independent loads), shuffle tree at the end.
+          // (A thread-per-(channel, group) loop made this one CTA's serial tail ~150 us long at S = 592 while 295 CTAs waited.)
+          for (int ch = wid; ch < tile_c; ch += kBnThreads / 32) {
+            const int c = ct * tile_c + ch;
+            if (c >= C) continue;
             const float* base = a.partial + (size_t)c * S * 3;
-            for (int q = grp; q < S; q += ngrp) {
-              if (!IS_BWD) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
-              else { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
-            }
-          }
-          if (!IS_BWD) { sm[0][tid] = w.mean; sm[1][tid] = w.m2; sm[2][tid] = w.n; } else { sm[0][tid] = s0; sm[1][tid] = s1; }
-          __syncthreads();
-          if (grp == 0 && c < C) {
             if (!IS_BWD) {
-              Wf t{0.f, 0.f, 0.f};
-              for (int q = 0; q < ngrp; q++) t = wf_merge(t, Wf{sm[0][q * tile_c + ch], sm[1][q * tile_c + ch], sm[2][q * tile_c + ch]});
-              publish(a, c, t.mean, t.m2, t.n);
+              Wf w{0.f, 0.f, 0.f};
+#pragma unroll 4
+              for (int q = lane; q < S; q += 32) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) w = wf_merge(w, wf_shfl_xor(w, o));
+              if (lane == 0) publish(a, c, w.mean, w.m2, w.n);
             } else {
-              float t0 = 0.f, t1 = 0.f;
-              for (int q = 0; q < ngrp; q++) { t0 += sm[0][q * tile_c + ch]; t1 += sm[1][q * tile_c + ch]; }
-              publish(a, c, t0, t1, (float)per_c);
+              float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+              for (int q = lane; q < S; q += 32) { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
+              s0 = warp_sum(s0); s1 = warp_sum(s1);
+              if (lane == 0) publish(a, c, s0, s1, (float)per_c);
             }
-            __threadfence_system();
           }
+          __threadfence_system();
+          __syncthreads();
           if (tid == 0) a.unit_ctr[ct] = 0u;
         }
       }
