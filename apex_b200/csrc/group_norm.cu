@@ -15,6 +15,7 @@
 namespace ab {
 
 constexpr int kGnThreads = 256;
+constexpr int kGnMaxN = 8192;  // images per launch (size of the control buffer: 1 + 2 * kGnMaxN words, see group_norm.py)
 
 struct GnArgs {
   const void* x; const void* dy; void* out;
@@ -25,7 +26,7 @@ struct GnArgs {
   float* partial;                         // [N*C][S][3]
   float* chan;                            // [N*C][3] per-(n,c) merged values
   float* gsum;                            // [N*G][2] bwd: gamma-weighted group sums / M
-  unsigned int* ctrl;                     // [0] done-image counter, [1 .. 1+N) per-image arrival counters, [1+N .. 1+2N) per-image ready epochs
+  unsigned int* ctrl;                     // [0] done-image counter, [1 .. 1+kGnMaxN) per-image arrival counters, [1+kGnMaxN ..) per-image ready epochs
   unsigned int epoch;                     // value that marks THIS launch in the ready flags (strictly increasing per ctrl buffer)
   int N, HW, C, G, splits, splits3, silu, is_bwd;
   float eps;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
 
   __shared__ int s_last;
   unsigned int* img_ctr = a.ctrl + 1;
-  unsigned int* ready = a.ctrl + 1 + a.N;
+  unsigned int* ready = a.ctrl + 1 + kGnMaxN;  // FIXED offsets: a layout that depended on N would alias stale flags with counters
   const int lane_ = tid & 31;
   // ------------------------------------------------------------------ stage 1: per-(n, c, split) partial sums; the LAST item of an
   // image to finish folds that image's groups and raises the image's ready flag (no grid-wide barrier anywhere in this kernel)
@@ -273,7 +274,7 @@ AB_API long long ab_group_norm_scratch_floats(int N, int C, int G, int max_split
 AB_API int ab_group_norm(int is_bwd, const void* x, const void* dy, void* out, const void* gamma, const void* beta, int w_fp32, float* mean,
                          float* rstd, float* dgamma, float* dbeta, float* scratch, long long scratch_floats, unsigned int* ctrl, unsigned int epoch, int N,
                          int HW, int C, int G, float eps, int silu, int dt, cudaStream_t st) {
-  if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0) return -2;
+  if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % G != 0 || N > kGnMaxN) return -2;
   GnArgs a;
   a.x = x; a.dy = dy; a.out = out; a.gamma = gamma; a.beta = beta; a.w_fp32 = w_fp32; a.mean = mean; a.rstd = rstd; a.dgamma = dgamma;
   a.dbeta = dbeta; a.ctrl = ctrl; a.epoch = epoch; a.N = N; a.HW = HW; a.C = C; a.G = G; a.eps = eps; a.silu = silu; a.is_bwd = is_bwd;
