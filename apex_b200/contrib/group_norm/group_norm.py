@@ -14,6 +14,8 @@ from ... import _lib
 
 _lib.declare("ab_group_norm", "i p p p p p i p p p p p l p i i i i i f i i p")
 
+_lib.declare("ab_group_norm_small", "i p p p p p i p p p p p p i i i i f i i p")
+
 _MAX_N = 8192  # per-image arrival counters / ready flags live in a fixed control buffer
 
 _state: dict = {}
@@ -45,8 +47,25 @@ def _native_ok(x, w):
             and x.shape[0] <= _MAX_N)
 
 
+def _small_ok(is_bwd, HW, C, G, esz):
+    """csrc/group_norm_small.cu: one CTA owns a whole (image, group) slab when it fits in shared memory."""
+    Cg = C // G
+    if Cg % 4 or Cg > 512 or (C * esz) % 16:
+        return False
+    slab = HW * Cg * esz
+    dyn = 2 * slab + (512 // (Cg // 4)) * Cg * 8 if is_bwd else slab
+    return dyn <= 200 * 1024
+
+
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
+    if _small_ok(is_bwd, H * W, C, G, x.element_size()):
+        st = _scratch(x.device, N * C * 2 + 64)
+        w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
+        _lib.fn("ab_group_norm_small")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
+                                       rstd.data_ptr(), _lib.ptr(dg), _lib.ptr(db), st[0].data_ptr(), st[1].data_ptr(), N, H * W, C, G, float(eps),
+                                       int(silu), _lib.dt(x), _lib.stream_ptr(x.device))
+        return
     need = N * C * 16 * 3 + N * C * 3 + N * G * 2 + 64
     st = _scratch(x.device, need)
     scratch, ctrl = st[0], st[1]
