@@ -47,19 +47,24 @@ def _native_ok(x, w):
             and x.shape[0] <= _MAX_N)
 
 
-def _small_ok(is_bwd, HW, C, G, esz):
-    """csrc/group_norm_small.cu: one CTA owns a whole (image, group) slab when it fits in shared memory."""
-    Cg = C // G
-    if Cg % 4 or Cg > 512 or (C * esz) % 16:
-        return False
-    slab = HW * Cg * esz
-    dyn = 2 * slab + (512 // (Cg // 4)) * Cg * 8 if is_bwd else slab
-    return dyn <= 200 * 1024
+_small_ok_cache: dict = {}
+
+
+def _small_ok(is_bwd, HW, C, G, dtype):
+    """csrc/group_norm_small.cu: a CTA (or a cluster of 2 / 4 CTAs) owns a whole (image, group) slab when it fits in shared memory."""
+    key = (is_bwd, HW, C, G, dtype)
+    r = _small_ok_cache.get(key)
+    if r is None:
+        import ctypes
+
+        f = _lib.raw_fn("ab_group_norm_small_ok", ctypes.c_int, [ctypes.c_int] * 5)
+        r = _small_ok_cache[key] = bool(f(int(is_bwd), HW, C, G, _lib.dt(dtype)))
+    return r
 
 
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
-    if _small_ok(is_bwd, H * W, C, G, x.element_size()):
+    if _small_ok(is_bwd, H * W, C, G, x.dtype):
         st = _scratch(x.device, N * C * 2 + 64)
         w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
         _lib.fn("ab_group_norm_small")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
