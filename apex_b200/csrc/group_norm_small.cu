@@ -20,7 +20,7 @@ __device__ __forceinline__ float gs_ld_w(const void* p, int fp32, int c) {
 __device__ __forceinline__ float gs_silu(float v) { return v * __frcp_rn(1.f + __expf(-v)); }
 __device__ __forceinline__ float gs_dsilu(float v) { const float s = __frcp_rn(1.f + __expf(-v)); return s * (1.f + v * (1.f - s)); }
 
-// VC (4 or 2) consecutive channels as one 4 / 8 / 16-byte chunk
+// VC (8, 4 or 2) consecutive channels as one 4 / 8 / 16-byte chunk
 template <int BYTES> struct RawOf;
 template <> struct RawOf<4> { using type = uint32_t; };
 template <> struct RawOf<8> { using type = uint2; };
@@ -76,7 +76,7 @@ __device__ __forceinline__ float gs_block_sum(float v, float* red) {  // red: >=
 // grid = N*G*K CTAs, cluster = K CTAs per (image, group), each owning a contiguous range of rows.
 // Thread (ch, lane): ch = its VC-channel chunk of the group (fixed), lane strides over the CTA's rows.
 template <typename T, int VC, bool SILU>
-__global__ void __launch_bounds__(kGsThreads, 1) gn_group_fwd(const T* __restrict__ x, T* __restrict__ y, const void* __restrict__ gamma,
+__global__ void __launch_bounds__(kGsThreads, 2) gn_group_fwd(const T* __restrict__ x, T* __restrict__ y, const void* __restrict__ gamma,
                                                             const void* __restrict__ beta, int w_fp32, float* __restrict__ mean,
                                                             float* __restrict__ rstd, int HW, int C, int G, float eps) {
   using Raw = typename ChunkN<T, VC>::Raw;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gn_group_fwd(const T* __restric
   T* yg = y + ((size_t)n * HW + row0) * C + (size_t)g * Cg + ch * VC;
   float s = 0.f;
   if (active) {
-#pragma unroll 4
+#pragma unroll 8
     for (int r = lane; r < rows; r += lanes) {
       const Raw v = *reinterpret_cast<const Raw*>(xg + (size_t)r * C);
       xs[r * nchunk + ch] = v;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gn_group_fwd(const T* __restric
 
 // chan: [N][C][2] (sum g, sum g*xhat per image and channel); ticket: zero on entry, left zero.
 template <typename T, int VC, bool SILU>
-__global__ void __launch_bounds__(kGsThreads, 1) gn_group_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+__global__ void __launch_bounds__(kGsThreads, 2) gn_group_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
                                                             const void* __restrict__ gamma, const void* __restrict__ beta, int w_fp32,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             float* __restrict__ chan, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kGsThreads, 1) gn_group_bwd(const T* __restric
     db[j] = 0.f; dg[j] = 0.f;
   }
   if (active) {
-#pragma unroll 2
+#pragma unroll 4
     for (int r = lane; r < rows; r += lanes) {
       const Raw xv = *reinterpret_cast<const Raw*>(x + base + (size_t)r * C);
       const Raw gv = *reinterpret_cast<const Raw*>(dy + base + (size_t)r * C);
@@ -253,14 +253,18 @@ struct GsPlan { int vc, k, max_rows; size_t dyn; };
 static bool gs_plan(int is_bwd, int HW, int C, int G, size_t esz, GsPlan& p) {
   if (G <= 0 || C % G != 0) return false;
   const int Cg = C / G;
-  p.vc = (Cg % 4 == 0) ? 4 : ((Cg % 2 == 0) ? 2 : 0);
-  if (p.vc == 0 || Cg / p.vc > kGsThreads || ((size_t)C * esz) % (p.vc * esz) != 0) return false;
+  p.vc = (esz == 2 && Cg % 8 == 0) ? 8 : (Cg % 4 == 0) ? 4 : ((Cg % 2 == 0) ? 2 : 0);
+  if (p.vc == 0 || Cg / p.vc > kGsThreads) return false;
   const int lanes = kGsThreads / (Cg / p.vc);
-  for (int k = 1; k <= 4; k *= 2) {
-    const int max_rows = (HW + k - 1) / k;
-    const size_t slab = (size_t)max_rows * Cg * esz;
-    const size_t dyn = is_bwd ? 2 * slab + ((size_t)lanes * Cg * 2 + (size_t)k * Cg * 2) * sizeof(float) : slab;
-    if (dyn <= 200 * 1024 && HW >= k) { p.k = k; p.max_rows = max_rows; p.dyn = (dyn + 15) / 16 * 16; return true; }
+  // smallest cluster whose per-CTA footprint lets two CTAs share an SM (<= 100 KB); else the smallest that fits at all (<= 200 KB)
+  for (size_t limit : {(size_t)100 * 1024, (size_t)200 * 1024}) {
+    for (int k = 1; k <= 8; k *= 2) {
+      if (HW < k) break;
+      const int max_rows = (HW + k - 1) / k;
+      const size_t slab = (size_t)max_rows * Cg * esz;
+      const size_t dyn = is_bwd ? 2 * slab + ((size_t)lanes * Cg * 2 + (size_t)k * Cg * 2) * sizeof(float) : slab;
+      if (dyn <= limit) { p.k = k; p.max_rows = max_rows; p.dyn = (dyn + 15) / 16 * 16; return true; }
+    }
   }
   return false;
 }
@@ -312,11 +316,9 @@ AB_API int ab_group_norm_small(int is_bwd, const void* x, const void* dy, void* 
   GsPlan p;
   if (!gs_plan(is_bwd, HW, C, G, dt == kF32 ? 4 : 2, p)) return -2;
   if (!aligned16(x) || !aligned16(out) || (is_bwd && !aligned16(dy))) return -3;
-#define GS_DT(T)                                                                                                                              \
-  return p.vc == 4 ? gn_small_launch<T, 4>(p, is_bwd, x, dy, out, gamma, beta, w_fp32, mean, rstd, dgamma, dbeta, chan, ticket, N, HW, C, G, eps, silu, st) \
-                   : gn_small_launch<T, 2>(p, is_bwd, x, dy, out, gamma, beta, w_fp32, mean, rstd, dgamma, dbeta, chan, ticket, N, HW, C, G, eps, silu, st)
-  if (dt == kF32) { GS_DT(float); }
-  if (dt == kF16) { GS_DT(f16); }
-  if (dt == kBF16) { GS_DT(bf16); }
+#define GS_VC(T, V) gn_small_launch<T, V>(p, is_bwd, x, dy, out, gamma, beta, w_fp32, mean, rstd, dgamma, dbeta, chan, ticket, N, HW, C, G, eps, silu, st)
+  if (dt == kF32) return p.vc == 4 ? GS_VC(float, 4) : GS_VC(float, 2);
+  if (dt == kF16) return p.vc == 8 ? GS_VC(f16, 8) : p.vc == 4 ? GS_VC(f16, 4) : GS_VC(f16, 2);
+  if (dt == kBF16) return p.vc == 8 ? GS_VC(bf16, 8) : p.vc == 4 ? GS_VC(bf16, 4) : GS_VC(bf16, 2);
   return -1;
 }
