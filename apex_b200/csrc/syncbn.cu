@@ -16,7 +16,12 @@
 
 namespace ab {
 
-constexpr int kBnThreads = 256;
+constexpr int kBnThreads = 512;
+// Multi-GPU launches leave kSmMargin SMs completely free (one CTA per SM on the others). The kernel spins on its peers, so it must
+// never hold EVERY SM: a concurrent NCCL kernel of the same process (DDP's gradient all-reduce during backward) that cannot get an
+// SM here stalls its counterpart on the peer, whose SyncBN kernel then cannot become resident either -- a cross-rank deadlock that
+// was observed at 2 and 8 GPUs with a 2-CTAs-per-SM grid. (The reference's group_norm_v2 has an sm_margin knob for the same reason.)
+constexpr int kSmMargin = 32;
 
 struct BnArgs {
   const void* x; const void* dy; const void* z; void* out; void* dz;  // out: y (fwd) or dx (bwd); dz: grad of residual (bwd)
@@ -104,7 +109,7 @@ __device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float 
 // IS_BWD / NHWC / FUSED (residual add and/or ReLU present) are compile-time: every instantiation carries only its own inner loops
 // (the runtime-flag version was 13.7k SASS instructions at 114 registers and stalled on instruction fetch for small layers).
 template <typename T, bool IS_BWD, bool NHWC, bool FUSED>
-__global__ void __launch_bounds__(kBnThreads, 2) syncbn_kernel(BnArgs a) {
+__global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
   constexpr int V = VecOf<T>::V;
   __shared__ float sm[3][kBnThreads + 8];
   __shared__ int s_last;
@@ -491,7 +496,8 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
   }
   a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch;
   const long long per_c = (long long)N * HW;
-  int grid = kNumSMs * 2;  // the software grid barrier needs every CTA resident: 2 CTAs/SM by __launch_bounds__
+  // the software grid barrier needs every CTA resident: one 512-thread CTA per SM, minus the NCCL margin when peers are involved
+  int grid = world > 1 ? kNumSMs - kSmMargin : kNumSMs;
   const int units = nhwc ? (C + 63) / 64 : C;
   long long splits = (2LL * grid + units - 1) / units;
   const long long min_per_split = nhwc ? 128 : 4096;  // rows / elements: keep every split a few full passes long
