@@ -172,6 +172,20 @@ class _Segment:
 
 
 class DistributedFusedAdam(torch.optim.Optimizer):
+    """ZeRO-2 Adam / AdamW: optimizer state and gradient reduction sharded over the data-parallel group, parameters all-gathered
+    after the update. Reference: apex/contrib/optimizers/distributed_fused_adam.py:477-3488 (same constructor arguments, methods
+    ``init_params / zero_grad / grad_buffer_view / no_sync / grad_sync / param_sync / grad_norm / clip_grad_norm / unscale_grads /
+    step(grad_scaler=) / state_dict / load_state_dict``).
+
+    On one NVSwitch node (<= 8 ranks) with fp32 state and 16/32-bit float gradients and parameters, ``step()`` is ONE kernel
+    (csrc/dist_adam.cu): reduce-scatter by P2P pulls or ``multimem.ld_reduce``, gradient norm, Adam on the fp32 shard, parameter
+    all-gather by P2P pushes or ``multimem.st`` — gradients and parameters live in symmetric-heap buffers that every rank maps.
+    Everything else (CPU / gloo, >8 ranks, redundant groups, 16-bit or scaled state, parameter remainders) takes the bucketed
+    NCCL / gloo path built on the multi-tensor kernels; both paths produce the same numbers.
+
+    The fused step spins on its peers: do not keep an NCCL collective of the same process in flight on another stream while
+    ``step()`` runs — a ZeRO training loop does not, its only collectives are inside the step."""
+
     def __init__(self, params, lr: float = 1e-3, bias_correction: bool = True, betas=(0.9, 0.999), eps: float = 1e-8,
                  adam_w_mode: bool = True, weight_decay: float = 0.0, amsgrad: bool = False, dtype: torch.dtype = torch.float32,
                  grad_sync_dtype: Optional[torch.dtype] = None, param_sync_dtype: Optional[torch.dtype] = None, device="cuda",
