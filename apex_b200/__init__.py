@@ -14,6 +14,20 @@ from . import _lib  # noqa: F401
 from . import multi_tensor_apply, optimizers, normalization  # noqa: F401
 
 
+class DeprecatedFeatureWarning(FutureWarning):
+    pass
+
+
+def deprecated_warning(msg: str) -> None:
+    """Warn once per call site, on rank 0 only (reference apex/__init__.py:35-43)."""
+    import warnings
+
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_rank() == 0:
+        warnings.warn(msg, DeprecatedFeatureWarning, stacklevel=2)
+
+
 def install_as_apex() -> None:
     """Register ``apex`` / ``amp_C`` aliases in ``sys.modules`` so ``import apex`` user code runs on this library."""
     import sys
@@ -23,7 +37,8 @@ def install_as_apex() -> None:
     mod = sys.modules[__name__]
     sys.modules.setdefault("apex", mod)
     sys.modules.setdefault("amp_C", _amp_C)
-    for name in ("optimizers", "normalization", "multi_tensor_apply", "fused_dense", "mlp", "parallel", "transformer", "contrib"):
+    for name in ("optimizers", "normalization", "multi_tensor_apply", "fused_dense", "mlp", "parallel", "transformer", "contrib", "_autocast_utils",
+                 "distributed_testing"):
         try:
             sub = __import__(f"{__name__}.{name}", fromlist=["*"])
             sys.modules.setdefault(f"apex.{name}", sub)

@@ -175,3 +175,16 @@ def peer_halo_exchange_matches_allgather(rank, world, device_type):
                     want.narrow(dim, L + hh, hh).copy_(hi)
                     ex(y, H_split=H_split, explicit_nhwc=explicit)
                     torch.testing.assert_close(y, want, rtol=0, atol=0)
+
+
+from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
+
+
+class GlooAllReduceCase(GlooDistributedTestBase):
+    """Used by tests/test_cpu_utils.py: every rank runs the decorated body with self.rank / self.world_size set."""
+
+    @distributed
+    def test_all_reduce(self):
+        t = torch.full((4,), float(self.rank + 1))
+        dist.all_reduce(t)
+        assert torch.equal(t, torch.full((4,), float(sum(range(1, self.world_size + 1))))), t
