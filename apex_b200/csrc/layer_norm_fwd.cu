@@ -166,8 +166,8 @@ int ln_fwd_launch(const void* x, void* y, float* mean, float* invvar, const void
   NormCfg c = norm_cfg(vec_ok ? n2 / E : 1, target_v, 512);
   if (vec_ok && c.ok) {
     int grid = (n1 + c.rows_per_cta - 1) / c.rows_per_cta;
-    // fp32 gamma / beta staged in shared memory when 4 CTAs per SM still fit (<= 48 KB each), else read through L1
-    const size_t dyn = (gamma && (size_t)2 * n2 * sizeof(float) <= 64 * 1024) ? (size_t)2 * n2 * sizeof(float) : 0;
+    // fp32 gamma / beta staged in shared memory while 4 CTAs per SM still fit comfortably (<= 32 KB each: hidden <= 4096), else read through L1
+    const size_t dyn = (gamma && (size_t)2 * n2 * sizeof(float) <= 32 * 1024) ? (size_t)2 * n2 * sizeof(float) : 0;
     const int cap = kNumSMs * (1024 / c.threads);
     if (grid > cap) grid = cap;
 #define LN_FWD_GO(MV)                                                                                                 \
