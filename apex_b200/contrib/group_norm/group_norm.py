@@ -144,3 +144,17 @@ class GroupNorm(nn.Module):
 
     def extra_repr(self):
         return "{num_groups}, {num_channels}, eps={eps}, affine={affine}, act={act}".format(**self.__dict__)
+
+
+# functional entry points of the reference module (group_norm.py:193-245): one implementation serves all three names
+def cuda_group_norm_nhwc_one_pass(x, G, weight, bias, eps, act=None):
+    return group_norm_nhwc(x, G, weight, bias, eps, act or "")
+
+
+cuda_group_norm_nhwc_two_pass = cuda_group_norm_nhwc_one_pass
+cuda_group_norm_v2_nhwc = cuda_group_norm_nhwc_one_pass
+
+
+def get_cc_and_sm_count(device_index: int):
+    p = torch.cuda.get_device_properties(device_index)
+    return (p.major, p.minor), p.multi_processor_count

@@ -63,3 +63,8 @@ def index_mul_2d(in1: torch.Tensor, in2: torch.Tensor, idx1: torch.Tensor) -> to
     if not _native(in1):
         return in1.index_select(0, idx1) * in2
     return _IndexMul2d.apply(in1.contiguous(), in2.contiguous(), idx1.contiguous().to(torch.int64))
+
+
+# reference class names (index_mul_2d.py:6-133)
+IndexMul2d_ = _IndexMul2d
+IndexMul2dBackward_ = _IndexMul2dBackward

@@ -18,6 +18,22 @@ def _pad_cols(matrix, m):
     return matrix, matrix.shape
 
 
+def fill(x):
+    """Fraction of non-zero entries (reference sparse_masklib.py:11-12)."""
+    return float(x.nonzero().size(0)) / torch.numel(x)
+
+
+def reshape_1d(matrix, m):
+    """(h, w) -> (h*w/m, m), zero-padding w to a multiple of m; also returns the padded shape (reference :18-28)."""
+    mat, _ = _pad_cols(matrix, m)
+    return mat.reshape(-1, m), mat.shape
+
+
+def compute_valid_1d_patterns(m, n):
+    """All 0/1 vectors of length m with n ones (reference :35-46). The calculators here use top-k instead of this table."""
+    return torch.tensor(sorted(set(itertools.permutations([1.0] * n + [0.0] * (m - n)))))
+
+
 def mn_1d_best(matrix, m, n):
     """Keep the n largest |w| in every consecutive group of m along the last dim."""
     mat, shape = _pad_cols(matrix, m)

@@ -65,6 +65,25 @@ def _backend(gm, example_inputs, **kwargs):
     return compile_fx(gm, example_inputs)
 
 
+def torchsched(gm, example_inputs, **kwargs):
+    """The backend callable itself (reference torchsched/__init__.py:30-43): ``torch.compile(model, backend=torchsched)``."""
+    return _backend(gm, example_inputs, **kwargs)
+
+
+def torchsched_compile(model=None, **kwargs):
+    """``torch.compile`` with this backend preselected (reference torchsched/__init__.py:58-81)."""
+    kwargs.setdefault("backend", "torchsched")
+    return torch.compile(model, **kwargs) if model is not None else (lambda m: torch.compile(m, **kwargs))
+
+
+def get_backend(name: str = "torchsched"):
+    return {"torchsched": torchsched, "inductor": "inductor"}[name]
+
+
+def list_backends():
+    return ["inductor", "torchsched"]
+
+
 def set_default_backend(name: str = "torchsched") -> None:
     """The reference monkey-patches torch.compile's default backend (torchsched/__init__.py:44-81); here it is an explicit call."""
     os.environ["TORCH_SCHED_DEFAULT_BACKEND"] = name
@@ -77,4 +96,4 @@ try:  # register so torch.compile(backend="torchsched") resolves
 except Exception:  # noqa: BLE001
     pass
 
-__all__ = ["StreamScheduler", "capture_graph", "set_default_backend", "config"]
+__all__ = ["StreamScheduler", "capture_graph", "set_default_backend", "config", "torchsched", "torchsched_compile", "get_backend", "list_backends"]

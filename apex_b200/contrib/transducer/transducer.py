@@ -200,3 +200,8 @@ class TransducerLoss(_TorchTransducerLoss):
         if self.packed_input and (batch_offset is None or max_f_len is None):
             raise Exception("Please specify batch_offset and max_f_len when packing is enabled")
         return _LossFn.apply(x, label, f_len, y_len, batch_offset, max_f_len, blank_idx, self.packed_input)
+
+
+# reference class names of the autograd functions (transducer.py:197-436)
+TransducerJointFunc = _JointFn
+TransducerLossFunc = _LossFn

@@ -107,6 +107,53 @@ def mixed_dtype_fused_rms_norm_affine(input, weight, normalized_shape, eps=1e-6,
     return _run(input, weight, None, normalized_shape, eps, memory_efficient, True, True)
 
 
+class _ApexNamedFunction:
+    """The reference exposes one autograd.Function per flavour (fused_layer_norm.py:38-420: FusedLayerNormAffineFunction, ...) and
+    downstream code (Megatron-LM) calls ``XFunction.apply(...)`` directly. They all map onto :class:`_NormFunction`."""
+
+    _rms = False
+    _mixed = False
+    _affine = True
+    _has_bias = True
+
+    @classmethod
+    def apply(cls, input, *args):
+        args = list(args)
+        weight = args.pop(0) if cls._affine else None
+        bias = args.pop(0) if (cls._affine and cls._has_bias) else None
+        normalized_shape, eps = args[0], args[1]
+        memory_efficient = args[2] if len(args) > 2 else False
+        return _run(input, weight, bias, normalized_shape, eps, memory_efficient, cls._rms, cls._mixed)
+
+
+class FusedLayerNormAffineFunction(_ApexNamedFunction):
+    pass
+
+
+class FusedLayerNormAffineMixedDtypesFunction(_ApexNamedFunction):
+    _mixed = True
+
+
+class FusedLayerNormFunction(_ApexNamedFunction):
+    _affine = False
+
+
+class FusedRMSNormAffineFunction(_ApexNamedFunction):
+    _rms, _has_bias = True, False
+
+
+class FusedRMSNormAffineMixedDtypesFunction(_ApexNamedFunction):
+    _rms, _has_bias, _mixed = True, False, True
+
+
+class FusedRMSNormFunction(_ApexNamedFunction):
+    _rms, _affine = True, False
+
+
+def supports_custom_op() -> bool:
+    return hasattr(torch.library, "custom_op")
+
+
 def _use_fallback(input) -> bool:
     return torch.jit.is_tracing() or torch.jit.is_scripting() or torch.compiler.is_compiling() or not input.is_cuda
 
