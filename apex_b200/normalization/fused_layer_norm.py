@@ -75,6 +75,11 @@ def _shape(normalized_shape):
 
 
 def _run(input, weight, bias, normalized_shape, eps, memory_efficient, rms, mixed):
+    if not input.is_cuda:  # CPU tensors: plain PyTorch, like the reference modules (fused_layer_norm.py:815-822)
+        shape = _shape(normalized_shape)
+        if rms:
+            return manual_rms_norm(input, shape, weight, eps)
+        return torch.nn.functional.layer_norm(input, shape, weight, bias, eps)
     if mixed and weight is not None:
         args = _cast_if_autocast_enabled(input) + (weight, bias)
     else:
