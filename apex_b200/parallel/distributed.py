@@ -3,9 +3,9 @@ from tests/distributed/DDP/ddp_race_condition_test.py:39 and README.md:77-81).
 
 Gradients are flattened into buckets of ``message_size`` elements in the order they become ready during backward; each full
 bucket is all-reduced on one of ``num_allreduce_streams`` side streams while backward continues (``delay_allreduce=True`` does one
-flat all-reduce at the end). ``gradient_predivide_factor`` splits the averaging around the reduction. When the process group is
-one NVSwitch domain the bucket all-reduce can run as an in-kernel collective on the symmetric heap instead of NCCL
-(``fused_collectives``) — same epoch-signal machinery as DistributedFusedAdam.
+flat all-reduce at the end). ``gradient_predivide_factor`` splits the averaging around the reduction. The bucket all-reduce itself
+is NCCL (gloo on CPU): it runs concurrently with backward compute, which is exactly the situation where a spinning in-kernel
+collective must not be used.
 """
 from __future__ import annotations
 

@@ -188,3 +188,56 @@ class GlooAllReduceCase(GlooDistributedTestBase):
         t = torch.full((4,), float(self.rank + 1))
         dist.all_reduce(t)
         assert torch.equal(t, torch.full((4,), float(sum(range(1, self.world_size + 1))))), t
+
+
+def ddp_matches_manual_allreduce(rank, world, device_type, delay, message_size, predivide):
+    """apex_b200.parallel.DistributedDataParallel: bucketed / delayed all-reduce == averaging the per-rank grads by hand."""
+    from apex_b200.parallel import DistributedDataParallel
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 13), torch.nn.Tanh(), torch.nn.Linear(13, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3)).to(dev)
+    ref = copy.deepcopy(net)
+    ddp = DistributedDataParallel(net, message_size=message_size, delay_allreduce=delay, gradient_predivide_factor=predivide,
+                                  num_allreduce_streams=2)
+    g = torch.Generator().manual_seed(10 + rank)
+    for it in range(3):
+        x = torch.randn(4, 7, generator=g).to(dev)
+        for m in (ddp, ref):
+            m.zero_grad()
+        ddp(x).pow(2).sum().backward()
+        ref(x).pow(2).sum().backward()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            want = q.grad.clone()
+            dist.all_reduce(want)
+            torch.testing.assert_close(p.grad, want / world, rtol=1e-5, atol=1e-6)
+
+
+def ddp_race_condition(rank, world, device_type):
+    """Race detector by construction (reference tests/distributed/DDP/ddp_race_condition_test.py:27-78): two large parameters,
+    message_size=1 (a bucket per parameter), several all-reduce streams, gradients with a closed form checked every iteration."""
+    from apex_b200.parallel import DistributedDataParallel
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    n = 1 << (22 if device_type == "cuda" else 16)
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Parameter(torch.ones(n, device=dev))
+            self.b = torch.nn.Parameter(torch.ones(n, device=dev))
+
+        def forward(self, inp):
+            return ((self.a * inp).sum() + (self.b * inp * 2).sum())
+
+    model = DistributedDataParallel(Model(), message_size=1, num_allreduce_streams=3)
+    x = torch.ones(n, device=dev)
+    for it in range(6):
+        model.zero_grad()
+        inp = x * (rank + 1 + it)
+        model(inp).backward()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        mean_scale = sum(r + 1 + it for r in range(world)) / world
+        assert float(model.module.a.grad.sum()) == mean_scale * n, (it, float(model.module.a.grad.sum()))
+        assert float(model.module.b.grad.sum()) == 2 * mean_scale * n

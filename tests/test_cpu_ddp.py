@@ -1,0 +1,15 @@
+"""apex_b200.parallel.DistributedDataParallel / Reducer on two gloo ranks (CPU): bucketing, delayed all-reduce, pre-division,
+and the reference's race-by-construction check (tests/distributed/DDP/ddp_race_condition_test.py)."""
+import pytest
+
+from apex_b200.testing.dist_harness import run_distributed
+from tests import _dist_cases as cases
+
+
+@pytest.mark.parametrize("delay,message_size,predivide", [(False, 1, 1.0), (False, 50, 2.0), (True, 10000000, 1.0)])
+def test_ddp_two_ranks_gloo(delay, message_size, predivide):
+    run_distributed(cases.ddp_matches_manual_allreduce, 2, "cpu", delay, message_size, predivide, backend="gloo")
+
+
+def test_ddp_race_condition_gloo():
+    run_distributed(cases.ddp_race_condition, 2, "cpu", backend="gloo")

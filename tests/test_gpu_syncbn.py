@@ -157,3 +157,12 @@ def test_functional_ops(cuda_dev, channels_last, dtype):
     torch.testing.assert_close(yz.float(), (ref.detach() + z.float()).relu(), atol=tol, rtol=tol)
     g = S.relu_bw_c_last(dy, x, z, m2, istd, w, b)
     torch.testing.assert_close(g.float(), torch.where(ref.detach() + z.float() > 0, dy.float(), torch.zeros_like(dy.float())), atol=0, rtol=0)
+
+
+def test_ddp_race_condition_two_gpus(cuda_dev):
+    """apex_b200.parallel.DistributedDataParallel with a bucket per parameter and 3 all-reduce streams (reference
+    tests/distributed/DDP/ddp_race_condition_test.py)."""
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.ddp_race_condition, 2, "cuda", backend="nccl")
