@@ -24,6 +24,7 @@ struct Params {
   const void* C; long long ldc;    // accumulate source (EPI_ACCUM), same dtype as D
   int a_mn_major, b_mn_major;
   int epi;
+  float alpha;                     // accumulator scale applied before the epilogue op (fp8: product of the dequantisation scales)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -113,6 +114,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a_format [7,10), b_format [10,13),
 // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+// `is_bf16` doubles as the operand format code: kind::f16 0 = F16, 1 = BF16; kind::f8f6f4 0 = E4M3, 1 = E5M2.
 __host__ __device__ inline uint32_t make_idesc(int is_bf16, int a_mn, int b_mn, int m, int n) {
   uint32_t d = 0;
   d |= 1u << 4;
@@ -160,7 +162,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
     if (row_ok && col0 < p.N) {
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * p.alpha;
       const bool full = (col0 + 32 <= p.N);
       if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RELU || p.epi == EPI_BIAS_SIGMOID) {
         const TOut* b = reinterpret_cast<const TOut*>(p.bias) + col0;

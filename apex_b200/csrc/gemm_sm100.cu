@@ -202,6 +202,10 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -217,7 +221,9 @@ struct Smem2 {
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 
-template <typename TOut, int KSTAGES>
+// F8: operands are 8-bit floats (E4M3 / E5M2, K-major only): a 128-byte swizzle row holds 128 elements, one tcgen05.mma.kind::f8f6f4
+// covers K = 32 -- every BYTE offset (stage sizes, descriptor steps) is identical to the 16-bit case, only element counts double.
+template <typename TOut, int KSTAGES, bool F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params p, int is_bf16) {
   using S = Smem2<KSTAGES>;
@@ -235,7 +241,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const bool leader = cta == 0;
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN2 - 1) / BN2;
   const int num_tiles = num_m * num_n;
-  const int num_k = (p.K + BK - 1) / BK;
+  constexpr int BKE = F8 ? 2 * BK : BK;  // elements per k-block (128 bytes per row either way)
+  const int num_k = (p.K + BKE - 1) / BKE;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   constexpr uint32_t kTmemCols = 2 * BN2;
 
@@ -265,12 +272,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           uint8_t* sa = smem + stage * S::kStage;
           uint8_t* sb = sa + S::kABytes;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStage);  // bytes of both CTAs land on the leader's barrier
-          if (!p.a_mn_major) tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BK, m0);
+          if (!p.a_mn_major) tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BKE, m0);
           else {
 #pragma unroll
             for (int i = 0; i < BM / 64; i++) tma_load_2d_2sm(sa + i * (BK * 128), &map_a, &full_bar[stage], m0 + i * 64, kb * BK);
           }
-          if (!p.b_mn_major) tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BK, n0);
+          if (!p.b_mn_major) tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BKE, n0);
           else {
 #pragma unroll
             for (int i = 0; i < (BN2 / 2) / 64; i++) tma_load_2d_2sm(sb + i * (BK * 128), &map_b, &full_bar[stage], n0 + i * 64, kb * BK);
@@ -300,7 +307,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const uint64_t ad = a0 + (uint32_t)(stage * (S::kStage >> 4)), bd = b0 + (uint32_t)(stage * (S::kStage >> 4));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++)
-              umma_f16_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (F8) umma_f8_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2sm(&empty_bar[stage]);
             if (kb == num_k - 1) umma_commit_2sm(&tmem_full[acc]);
           }
@@ -351,14 +359,14 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D row-major [rows, cols] 16-bit tensor with leading dimension ld (elements); box = {box_cols (inner), box_rows}.
 static int make_map(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                    uint32_t box_rows) {
+                    uint32_t box_rows, int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1001;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+  CUresult r = fn(m, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2, const_cast<void*>(ptr), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(2000 + (int)r);
@@ -381,11 +389,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   return (int)e;
 }
 
-template <typename TOut, int KSTAGES>
+template <typename TOut, int KSTAGES, bool F8 = false>
 static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int is_bf16, int sms, cudaStream_t st) {
   using S = Smem2<KSTAGES>;
   static bool attr_done = false;
-  auto kern = gemm2_kernel<TOut, KSTAGES>;
+  auto kern = gemm2_kernel<TOut, KSTAGES, F8>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return (int)e;
@@ -428,7 +436,7 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
-  p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi;
+  p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f;
   if (sms <= 0) sms = kNumSMs;
 #define GEMM_GO(T)                                                                      \
   if (use2) return launch2<T, 6>(ma, mb, p, is_bf16, sms, st);                          \
@@ -436,6 +444,30 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   if (dt_out == kBF16) { GEMM_GO(bf16); }
   if (dt_out == kF16) { GEMM_GO(f16); }
   if (dt_out == kF32) { GEMM_GO(float); }
+  return -1;
+}
+
+// D[M,N] (dt_out) = alpha * A B^T with A [M,K], B [N,K] row-major 8-bit floats (dt_in: kE4M3 or kE5M2, both operands the same type),
+// fp32 accumulation in TMEM (tcgen05.mma.kind::f8f6f4, cta_group::2). K, lda, ldb must be multiples of 16 (TMA 16-byte rule).
+AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd, int dt_in,
+                       int dt_out, int epi, const void* bias, void* aux, long long ldaux, float alpha, int sms, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (dt_in != kE4M3 && dt_in != kE5M2) return -10;
+  if ((K % 16) || (lda % 16) || (ldb % 16) || !aligned16(A) || !aligned16(B)) return -10;
+  if (epi == EPI_ACCUM) return -10;
+  const int fmt = dt_in == kE5M2 ? 1 : 0;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, fmt, M, K, lda, 2 * BK, BM, 1);
+  if (rc) return rc;
+  rc = make_map(&mb, B, fmt, N, K, ldb, 2 * BK, BN2 / 2, 1);
+  if (rc) return rc;
+  Params p;
+  p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = nullptr; p.ldc = 0;
+  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha;
+  if (sms <= 0) sms = kNumSMs;
+  if (dt_out == kBF16) return launch2<bf16, 6, true>(ma, mb, p, fmt, sms, st);
+  if (dt_out == kF16) return launch2<f16, 6, true>(ma, mb, p, fmt, sms, st);
+  if (dt_out == kF32) return launch2<float, 6, true>(ma, mb, p, fmt, sms, st);
   return -1;
 }
 

@@ -1,5 +1,5 @@
-from .fused_dense import (DenseNoBiasFunc, FusedDense, FusedDenseFunc, FusedDenseGeluDense, FusedDenseGeluDenseFunc, fused_dense_function,
-                          fused_dense_gelu_dense_function)
+from .fused_dense import (DenseNoBiasFunc, FusedDense, FusedDenseFP8Func, FusedDenseFunc, FusedDenseGeluDense, FusedDenseGeluDenseFunc,
+                          fused_dense_fp8_function, fused_dense_function, fused_dense_gelu_dense_function)
 
 __all__ = ["FusedDense", "FusedDenseGeluDense", "FusedDenseFunc", "DenseNoBiasFunc", "FusedDenseGeluDenseFunc", "fused_dense_function",
-           "fused_dense_gelu_dense_function"]
+           "fused_dense_gelu_dense_function", "FusedDenseFP8Func", "fused_dense_fp8_function"]

@@ -99,6 +99,34 @@ def fused_dense_gelu_dense_function(input, weight1, bias1, weight2, bias2):
         return FusedDenseGeluDenseFunc.apply(*args)
 
 
+class FusedDenseFP8Func(torch.autograd.Function):
+    """Linear with an fp8 (E4M3, per-tensor dynamic scales) forward GEMM on the tcgen05 kind::f8f6f4 path; dgrad / wgrad stay 16-bit
+    (BASELINE.md row 3 'bf16 / fp8 FFN block' -- the reference has no fp8 path at all)."""
+
+    @staticmethod
+    def forward(ctx, input, weight, bias):
+        x = _2d(input)
+        ctx.save_for_backward(x, weight)
+        ctx.in_shape, ctx.has_bias = input.shape, bias is not None
+        y = G.linear_fwd_fp8(x, weight.contiguous(), bias)
+        return y.view(*input.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        dy = _2d(grad_output)
+        dx = G.linear_dgrad(dy, weight.contiguous()) if ctx.needs_input_grad[0] else None
+        dw = G.linear_wgrad(dy, x)
+        db = G.colsum(dy) if ctx.has_bias else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+
+
+def fused_dense_fp8_function(input, weight, bias=None):
+    args = _cast_if_autocast_enabled(input, weight, bias)
+    with torch.amp.autocast("cuda", enabled=False):
+        return FusedDenseFP8Func.apply(*args)
+
+
 class FusedDense(nn.Module):
     def __init__(self, in_features, out_features, bias=True):
         super().__init__()

@@ -12,6 +12,7 @@ from .. import _lib
 
 _lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
+_lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f i p")
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_ACCUM, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_RELU, EPI_SIGMOID = range(9)
 
@@ -119,3 +120,51 @@ def linear_wgrad(dy, x, accum_into: torch.Tensor | None = None, out_dtype=None):
         if out_dtype is not None:
             dw = dw.to(out_dtype)
     return dw
+
+
+# ---- fp8 (E4M3 / E5M2) operands: tcgen05.mma.kind::f8f6f4, fp32 accumulation, per-tensor scales folded into the epilogue --------
+_F8 = tuple(getattr(torch, n) for n in ("float8_e4m3fn", "float8_e5m2") if hasattr(torch, n))
+
+
+def quantize_fp8(x: torch.Tensor, dtype=None):
+    """Per-tensor dynamic scaling: returns (x_fp8, inv_scale) with x ~= x_fp8.float() * inv_scale (amax mapped to the format's max)."""
+    dtype = dtype or torch.float8_e4m3fn
+    amax = x.detach().abs().amax().float().clamp_min(1e-12)
+    scale = torch.finfo(dtype).max / amax
+    return (x.float() * scale).to(dtype), (1.0 / scale)
+
+
+def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, out_dtype=torch.bfloat16, epi: int = EPI_NONE,
+             bias: torch.Tensor | None = None, aux: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    """D [M, N] = alpha * a8 [M, K] @ b8 [N, K]^T for 8-bit float operands (both K-major, same format). Returns None when the native
+    kernel cannot take the problem (K or a leading dimension not a multiple of 16, CPU tensors)."""
+    if not (a8.is_cuda and _lib.available() and a8.dtype in _F8 and a8.dtype == b8.dtype and a8.dim() == 2 and b8.dim() == 2
+            and a8.stride(1) == 1 and b8.stride(1) == 1):
+        return None
+    M, K = a8.shape
+    N = b8.shape[0]
+    assert b8.shape[1] == K
+    if K % 16 or a8.stride(0) % 16 or b8.stride(0) % 16:
+        return None
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a8.device)
+    if bias is not None and bias.dtype != out.dtype:
+        bias = bias.to(out.dtype)
+    _lib.fn("ab_gemm_fp8")(a8.data_ptr(), b8.data_ptr(), out.data_ptr(), M, N, K, a8.stride(0), b8.stride(0), out.stride(0), _lib.dt(a8),
+                           _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, float(alpha), 0,
+                           _lib.stream_ptr(a8.device))
+    stats["native"] += 1
+    return out
+
+
+def linear_fwd_fp8(x: torch.Tensor, w: torch.Tensor, bias=None, epi=None, aux=None, out_dtype=None):
+    """y = x W^T (+bias, +GELU) with x and W quantised to E4M3 on the fly (per-tensor scales); falls back to the 16-bit GEMM."""
+    epi = (EPI_BIAS if bias is not None else EPI_NONE) if epi is None else epi
+    out_dtype = out_dtype or x.dtype
+    if x.is_cuda and _lib.available() and _F8 and x.shape[1] % 16 == 0:
+        x8, sx = quantize_fp8(x)
+        w8, sw = quantize_fp8(w)
+        y = gemm_fp8(x8, w8, float(sx * sw), out_dtype=out_dtype, epi=epi, bias=bias, aux=aux)
+        if y is not None:
+            return y
+    return linear_fwd(x, w, bias, epi=epi, aux=aux, out_dtype=out_dtype)

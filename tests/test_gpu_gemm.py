@@ -127,3 +127,38 @@ def test_mlp_module(cuda_dev, activation):
     # five bf16 layers vs an fp32 oracle: ReLU masks flip on near-zero pre-activations, so the bound is loose
     assert _rel(x.grad, xr.grad) < 0.15
     assert _rel(m.weights[0].grad, layers[0].weight.grad) < 0.15
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (300, 264, 1040), (128, 128, 64), (1024, 2048, 4096)])
+@pytest.mark.parametrize("fmt", ["e4m3", "e5m2"])
+def test_gemm_fp8(cuda_dev, M, N, K, fmt):
+    """tcgen05.mma.kind::f8f6f4 GEMM vs the fp32 product of the dequantised operands (exact up to fp32 accumulation order)."""
+    from apex_b200.ops import gemm as G
+    dt = torch.float8_e4m3fn if fmt == "e4m3" else torch.float8_e5m2
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=cuda_dev)
+    b = torch.randn(N, K, device=cuda_dev)
+    a8, sa = G.quantize_fp8(a, dt)
+    b8, sb = G.quantize_fp8(b, dt)
+    alpha = float(sa * sb)
+    ref = (a8.float() @ b8.float().t()) * alpha
+    out = G.gemm_fp8(a8, b8, alpha, out_dtype=torch.float32)
+    assert out is not None
+    torch.testing.assert_close(out, ref, atol=2e-3 * K ** 0.5, rtol=1e-3)
+    bias = torch.randn(N, device=cuda_dev, dtype=torch.bfloat16)
+    out2 = G.gemm_fp8(a8, b8, alpha, out_dtype=torch.bfloat16, epi=G.EPI_BIAS, bias=bias)
+    torch.testing.assert_close(out2.float(), ref + bias.float(), atol=0.05 * K ** 0.5 / 8 + 0.05, rtol=2e-2)
+
+
+def test_fused_dense_fp8_close_to_bf16(cuda_dev):
+    from apex_b200.fused_dense import fused_dense_fp8_function
+    torch.manual_seed(0)
+    x = torch.randn(512, 1024, device=cuda_dev, dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(768, 1024, device=cuda_dev) * 0.03).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(768, device=cuda_dev, dtype=torch.bfloat16, requires_grad=True)
+    y = fused_dense_fp8_function(x, w, b)
+    ref = torch.nn.functional.linear(x.float(), w.float(), b.float())
+    rel = (y.float() - ref).norm() / ref.norm()
+    assert rel < 0.06, rel  # two e4m3 operands: ~2^-4 relative element noise averaged over K
+    y.float().pow(2).mean().backward()
+    assert torch.isfinite(x.grad.float()).all() and torch.isfinite(w.grad.float()).all() and b.grad is not None
