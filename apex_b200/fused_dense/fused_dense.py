@@ -121,6 +121,27 @@ class FusedDenseFP8Func(torch.autograd.Function):
         return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
 
 
+class FusedDenseGeluDenseFP8Func(FusedDenseGeluDenseFunc):
+    """Dense -> GELU -> Dense with both forward GEMMs on the fp8 path (bias + GELU (+aux) and bias epilogues fused as in the 16-bit
+    version); the backward is inherited unchanged (16-bit dgrad / wgrad on the saved activations)."""
+
+    @staticmethod
+    def forward(ctx, input, weight1, bias1, weight2, bias2):
+        x = _2d(input)
+        gelu_in = torch.empty(x.shape[0], weight1.shape[0], dtype=x.dtype, device=x.device)
+        output1 = G.linear_fwd_fp8(x, weight1.contiguous(), bias1, epi=G.EPI_BIAS_GELU, aux=gelu_in)
+        output2 = G.linear_fwd_fp8(output1, weight2.contiguous(), bias2)
+        ctx.save_for_backward(x, weight1, weight2, gelu_in, output1)
+        ctx.in_shape = input.shape
+        return output2.view(*input.shape[:-1], weight2.shape[0])
+
+
+def fused_dense_gelu_dense_fp8_function(input, weight1, bias1, weight2, bias2):
+    args = _cast_if_autocast_enabled(input, weight1, bias1, weight2, bias2)
+    with torch.amp.autocast("cuda", enabled=False):
+        return FusedDenseGeluDenseFP8Func.apply(*args)
+
+
 def fused_dense_fp8_function(input, weight, bias=None):
     args = _cast_if_autocast_enabled(input, weight, bias)
     with torch.amp.autocast("cuda", enabled=False):

@@ -157,13 +157,29 @@ def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, out_dtyp
     return out
 
 
+_wq_cache: dict = {}
+
+
+def _quantize_weight_cached(w: torch.Tensor):
+    """Weights change once per optimizer step, not once per call: key the quantised copy on (storage, version)."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _wq_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1], hit[2]
+    w8, sw = quantize_fp8(w)
+    if len(_wq_cache) > 256:
+        _wq_cache.clear()
+    _wq_cache[key] = (w._version, w8, sw)
+    return w8, sw
+
+
 def linear_fwd_fp8(x: torch.Tensor, w: torch.Tensor, bias=None, epi=None, aux=None, out_dtype=None):
     """y = x W^T (+bias, +GELU) with x and W quantised to E4M3 on the fly (per-tensor scales); falls back to the 16-bit GEMM."""
     epi = (EPI_BIAS if bias is not None else EPI_NONE) if epi is None else epi
     out_dtype = out_dtype or x.dtype
     if x.is_cuda and _lib.available() and _F8 and x.shape[1] % 16 == 0:
         x8, sx = quantize_fp8(x)
-        w8, sw = quantize_fp8(w)
+        w8, sw = _quantize_weight_cached(w)
         y = gemm_fp8(x8, w8, float(sx * sw), out_dtype=out_dtype, epi=epi, bias=bias, aux=aux)
         if y is not None:
             return y

@@ -39,6 +39,23 @@ def main():
         out.append(row)
         print(json.dumps(row))
         del a, b, a8, b8, ref, got
+    # FFN block (BASELINE.md row 3, fp8 variant): fp8 forward GEMMs incl. per-call activation quantisation, 16-bit backward
+    from apex_b200.fused_dense import FusedDenseGeluDense, fused_dense_gelu_dense_fp8_function
+    M, H, FF = 8192, 4096, 16384
+    blk = FusedDenseGeluDense(H, FF, H).to(dev, torch.bfloat16)
+    xin = torch.randn(M, H, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    dout = torch.randn(M, H, device=dev, dtype=torch.bfloat16)
+    f8 = lambda: fused_dense_gelu_dense_fp8_function(xin, blk.weight1, blk.bias1, blk.weight2, blk.bias2)  # noqa: E731
+    row = {"case": "FusedDenseGeluDense 8192 x 4096 <-> 16384"}
+    with torch.no_grad():
+        row["fwd_fp8_ms"] = round(time_fn(f8, warmup=3, iters=10)[0], 4)
+        row["fwd_bf16_ms"] = round(time_fn(lambda: blk(xin), warmup=3, iters=10)[0], 4)
+    row["fwd_bwd_fp8_ms"] = round(time_fn(lambda: f8().backward(dout), warmup=3, iters=10)[0], 4)
+    row["fwd_bwd_bf16_ms"] = round(time_fn(lambda: blk(xin).backward(dout), warmup=3, iters=10)[0], 4)
+    y8, y16 = f8().float(), blk(xin).float()
+    row["fp8_vs_bf16_rel_err"] = float((y8 - y16).norm() / y16.norm())
+    out.append(row)
+    print(json.dumps(row))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "bench_gemm_fp8.json"), "w"), indent=1)
 
