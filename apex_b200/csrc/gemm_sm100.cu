@@ -346,6 +346,19 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a DRIVER call and needs a context bound to the calling thread. A fresh thread (e.g. the autograd engine's
+// backward thread) whose first CUDA activity is this call has none yet -- runtime calls bind the primary context lazily, driver calls
+// do not (observed: CUDA_ERROR_INVALID_CONTEXT when the caching allocator served every allocation of the backward pass).
+static void bind_primary_context_once() {
+  static thread_local bool done = false;
+  if (!done) {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess) cudaSetDevice(d);
+    cudaFree(nullptr);
+    done = true;
+  }
+}
+
 static EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -362,6 +375,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows,
                     uint32_t box_rows, int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1001;
+  bind_primary_context_once();
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
