@@ -24,7 +24,8 @@ struct Params {
   const void* C; long long ldc;    // accumulate source (EPI_ACCUM), same dtype as D
   int a_mn_major, b_mn_major;
   int epi;
-  float alpha;                     // accumulator scale applied before the epilogue op (fp8: product of the dequantisation scales)
+  float alpha;                     // accumulator scale applied before the epilogue op
+  const float* scale_a; const float* scale_b;  // optional DEVICE scalars multiplied into alpha (fp8 dequantisation scales: no host sync)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -153,6 +154,7 @@ template <typename TOut, int BN>
 __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_base, int acc, int row, int n_blk, int q, int half) {
   const bool row_ok = row < p.M;
   TOut* drow = reinterpret_cast<TOut*>(p.D) + (size_t)row * p.ldd;
+  const float alpha = p.alpha * (p.scale_a ? __ldg(p.scale_a) : 1.f) * (p.scale_b ? __ldg(p.scale_b) : 1.f);
 #pragma unroll 1
   for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
     uint32_t r[32];
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
     if (row_ok && col0 < p.N) {
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * p.alpha;
+      for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * alpha;
       const bool full = (col0 + 32 <= p.N);
       if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RELU || p.epi == EPI_BIAS_SIGMOID) {
         const TOut* b = reinterpret_cast<const TOut*>(p.bias) + col0;

@@ -450,7 +450,7 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
-  p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f;
+  p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f; p.scale_a = nullptr; p.scale_b = nullptr;
   if (sms <= 0) sms = kNumSMs;
 #define GEMM_GO(T)                                                                      \
   if (use2) return launch2<T, 6>(ma, mb, p, is_bf16, sms, st);                          \
@@ -463,8 +463,10 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
 
 // D[M,N] (dt_out) = alpha * A B^T with A [M,K], B [N,K] row-major 8-bit floats (dt_in: kE4M3 or kE5M2, both operands the same type),
 // fp32 accumulation in TMEM (tcgen05.mma.kind::f8f6f4, cta_group::2). K, lda, ldb must be multiples of 16 (TMA 16-byte rule).
+// scale_a / scale_b: optional device floats multiplied into alpha in the epilogue (per-tensor dequantisation scales).
 AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd, int dt_in,
-                       int dt_out, int epi, const void* bias, void* aux, long long ldaux, float alpha, int sms, cudaStream_t st) {
+                       int dt_out, int epi, const void* bias, void* aux, long long ldaux, float alpha, const float* scale_a, const float* scale_b,
+                       int sms, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (dt_in != kE4M3 && dt_in != kE5M2) return -10;
   if ((K % 16) || (lda % 16) || (ldb % 16) || !aligned16(A) || !aligned16(B)) return -10;
@@ -477,7 +479,7 @@ AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int 
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = nullptr; p.ldc = 0;
-  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha;
+  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b;
   if (sms <= 0) sms = kNumSMs;
   if (dt_out == kBF16) return launch2<bf16, 6, true>(ma, mb, p, fmt, sms, st);
   if (dt_out == kF16) return launch2<f16, 6, true>(ma, mb, p, fmt, sms, st);

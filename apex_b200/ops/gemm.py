@@ -12,7 +12,8 @@ from .. import _lib
 
 _lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
-_lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f i p")
+_lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f p p i p")
+_lib.declare("ab_fp8_quantize", "p p l p p i i p")
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_ACCUM, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_RELU, EPI_SIGMOID = range(9)
 
@@ -126,18 +127,34 @@ def linear_wgrad(dy, x, accum_into: torch.Tensor | None = None, out_dtype=None):
 _F8 = tuple(getattr(torch, n) for n in ("float8_e4m3fn", "float8_e5m2") if hasattr(torch, n))
 
 
+_q_scratch: dict = {}
+
+
 def quantize_fp8(x: torch.Tensor, dtype=None):
-    """Per-tensor dynamic scaling: returns (x_fp8, inv_scale) with x ~= x_fp8.float() * inv_scale (amax mapped to the format's max)."""
+    """Per-tensor dynamic scaling: returns (x_fp8, inv_scale) with x ~= x_fp8.float() * inv_scale (amax mapped to the format's max).
+    On CUDA this is two kernels (csrc/fp8_quant.cu: amax, scale + cast) and ``inv_scale`` is a 1-element device tensor: no host sync."""
     dtype = dtype or torch.float8_e4m3fn
+    if x.is_cuda and _lib.available() and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        xc = x.detach().contiguous()
+        q = torch.empty(xc.shape, dtype=dtype, device=x.device)
+        inv = torch.empty(1, dtype=torch.float32, device=x.device)
+        scr = _q_scratch.get(x.device)
+        if scr is None:
+            scr = _q_scratch[x.device] = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.fn("ab_fp8_quantize")(xc.data_ptr(), q.data_ptr(), xc.numel(), scr.data_ptr(), inv.data_ptr(), _lib.dt(xc), _lib.dt(dtype),
+                                   _lib.stream_ptr(x.device))
+        return q, inv
     amax = x.detach().abs().amax().float().clamp_min(1e-12)
     scale = torch.finfo(dtype).max / amax
-    return (x.float() * scale).to(dtype), (1.0 / scale)
+    return (x.float() * scale).to(dtype), (1.0 / scale).reshape(1)
 
 
-def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, out_dtype=torch.bfloat16, epi: int = EPI_NONE,
-             bias: torch.Tensor | None = None, aux: torch.Tensor | None = None, out: torch.Tensor | None = None):
-    """D [M, N] = alpha * a8 [M, K] @ b8 [N, K]^T for 8-bit float operands (both K-major, same format). Returns None when the native
-    kernel cannot take the problem (K or a leading dimension not a multiple of 16, CPU tensors)."""
+def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, scale_a: torch.Tensor | None = None,
+             scale_b: torch.Tensor | None = None, out_dtype=torch.bfloat16, epi: int = EPI_NONE, bias: torch.Tensor | None = None,
+             aux: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    """D [M, N] = alpha * scale_a * scale_b * a8 [M, K] @ b8 [N, K]^T for 8-bit float operands (both K-major, same format);
+    ``scale_a`` / ``scale_b`` are optional 1-element fp32 DEVICE tensors (the dequantisation scales of :func:`quantize_fp8`).
+    Returns None when the native kernel cannot take the problem (K or a leading dimension not a multiple of 16, CPU tensors)."""
     if not (a8.is_cuda and _lib.available() and a8.dtype in _F8 and a8.dtype == b8.dtype and a8.dim() == 2 and b8.dim() == 2
             and a8.stride(1) == 1 and b8.stride(1) == 1):
         return None
@@ -151,8 +168,8 @@ def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, out_dtyp
     if bias is not None and bias.dtype != out.dtype:
         bias = bias.to(out.dtype)
     _lib.fn("ab_gemm_fp8")(a8.data_ptr(), b8.data_ptr(), out.data_ptr(), M, N, K, a8.stride(0), b8.stride(0), out.stride(0), _lib.dt(a8),
-                           _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, float(alpha), 0,
-                           _lib.stream_ptr(a8.device))
+                           _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, float(alpha),
+                           _lib.ptr(scale_a), _lib.ptr(scale_b), 0, _lib.stream_ptr(a8.device))
     stats["native"] += 1
     return out
 
@@ -180,7 +197,7 @@ def linear_fwd_fp8(x: torch.Tensor, w: torch.Tensor, bias=None, epi=None, aux=No
     if x.is_cuda and _lib.available() and _F8 and x.shape[1] % 16 == 0:
         x8, sx = quantize_fp8(x)
         w8, sw = _quantize_weight_cached(w)
-        y = gemm_fp8(x8, w8, float(sx * sw), out_dtype=out_dtype, epi=epi, bias=bias, aux=aux)
+        y = gemm_fp8(x8, w8, 1.0, scale_a=sx, scale_b=sw, out_dtype=out_dtype, epi=epi, bias=bias, aux=aux)
         if y is not None:
             return y
     return linear_fwd(x, w, bias, epi=epi, aux=aux, out_dtype=out_dtype)

@@ -20,7 +20,7 @@ def main():
         b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
         a8, sa = G.quantize_fp8(a)
         b8, sb = G.quantize_fp8(b)
-        alpha = float(sa * sb)
+        alpha = float((sa * sb).item())
         flops = 2.0 * M * N * K
         t8 = time_fn(lambda: G.gemm_fp8(a8, b8, alpha), warmup=3, iters=10)[0]
         t16 = time_fn(lambda: G.gemm(a, b), warmup=3, iters=10)[0]
