@@ -169,14 +169,15 @@ def test_fp8_quantize_kernel(cuda_dev, dtype):
     """csrc/fp8_quant.cu vs the torch formulation; scales stay on the device and feed the GEMM epilogue."""
     from apex_b200.ops import gemm as G
     torch.manual_seed(0)
-    x = (torch.randn(1000, 1032, device=cuda_dev) * 3).to(dtype)
+    x = (torch.randn(1000, 1040, device=cuda_dev) * 3).to(dtype)
     q, inv = G.quantize_fp8(x)
     amax = x.float().abs().max()
     torch.testing.assert_close(inv, (amax / 448.0).reshape(1), rtol=1e-6, atol=0)
     ref = (x.float() * (448.0 / amax)).to(torch.float8_e4m3fn)
     assert (q.float() - ref.float()).abs().max() <= 32.0 and (q.view(torch.uint8) != ref.view(torch.uint8)).float().mean() < 0.02
-    w = torch.randn(264, 1032, device=cuda_dev).to(dtype)
+    w = torch.randn(264, 1040, device=cuda_dev).to(dtype)
     w8, winv = G.quantize_fp8(w)
     out = G.gemm_fp8(q, w8, 1.0, scale_a=inv, scale_b=winv, out_dtype=torch.float32)
+    assert out is not None
     want = (q.float() @ w8.float().t()) * inv * winv
     torch.testing.assert_close(out, want, atol=2e-2, rtol=1e-3)
