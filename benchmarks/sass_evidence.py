@@ -6,9 +6,9 @@ import re
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PAT = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "SYNCS", "UCGABAR", "LDGMC", "LDG.E.NA.128", "STG.E.NA.128", "STRONG.SYS", "MEMBAR", "HMMA", "LDG.E.128", "STG.E.128"]
+PAT = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "LDTM", "SYNCS", "UCGABAR", "LDGMC", "LDG.E.NA.128", "STG.E.NA.128", "STRONG.SYS", "MEMBAR", "HMMA", "LDG.E.128", "STG.E.128"]
 out = ["# SASS evidence (cuobjdump -sass of build/obj/*.o, sm_100a)", "",
-       "`UTCHMMA` = tcgen05.mma, `LDTM` = tcgen05.ld, `UTMALDG` = TMA load, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops,",
+       "`UTCHMMA` = tcgen05.mma kind::f16, `UTCQMMA` = tcgen05.mma kind::f8f6f4 (fp8), `LDTM` = tcgen05.ld, `UTMALDG` = TMA load, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops,",
        "`UCGABAR` = cluster barrier, `LDGMC` = multimem.ld_reduce (NVSwitch in-fabric reduction), `LDG/STG.E.NA.128` = L1-no-allocate 16-byte peer loads / stores over NVLink, `STRONG.SYS` = system-scope signals / multimem.st. `HMMA` (legacy mma.sync) must be absent.", "",
        "| object | " + " | ".join(PAT) + " |", "|---|" + "---|" * len(PAT)]
 objdir = os.path.join(ROOT, "build", "obj")
