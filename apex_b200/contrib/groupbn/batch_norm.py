@@ -29,9 +29,11 @@ class BatchNorm2d_NHWC(SyncBatchNorm):
 
     def forward(self, x, z=None):
         """x (and the optional residual z) are [N, H, W, C] tensors; returns relu?(bn(x) + z) in the same layout."""
-        if bn_group_is_local(self) and not self.training:
-            pass
-        return super().forward(x, z)
+        if x.dim() != 4:
+            raise ValueError("BatchNorm2d_NHWC expects [N, H, W, C] input")
+        xv = x.permute(0, 3, 1, 2)  # logical NCHW view of the NHWC storage: exactly the channels-last layout the kernel reads
+        zv = None if z is None else z.permute(0, 3, 1, 2)
+        return super().forward(xv, zv).permute(0, 2, 3, 1)
 
 
 def bn_group_is_local(m) -> bool:

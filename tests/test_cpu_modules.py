@@ -1,0 +1,116 @@
+"""CPU paths of the module layer: every apex-compatible module must run (forward + backward) on CPU tensors and agree with the plain
+PyTorch formulation — the same oracles the GPU tests use for the kernels."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def test_mlp_and_fused_dense():
+    from apex_b200.fused_dense import FusedDense, FusedDenseGeluDense
+    from apex_b200.mlp import MLP
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, requires_grad=True)
+    m = MLP([16, 32, 8])
+    ref = x
+    for w, b in zip(m.weights, m.biases):  # like the reference, the activation follows EVERY layer (tests/L0/run_mlp/test_mlp.py:33-40)
+        ref = torch.relu(F.linear(ref, w, b))
+    torch.testing.assert_close(m(x), ref)
+    a, b2 = FusedDense(16, 8), FusedDenseGeluDense(16, 32, 8)
+    torch.testing.assert_close(a(x), F.linear(x, a.weight, a.bias))
+    torch.testing.assert_close(b2(x), F.linear(F.gelu(F.linear(x, b2.weight1, b2.bias1)), b2.weight2, b2.bias2))
+    (a(x).sum() + b2(x).sum()).backward()
+    assert x.grad is not None and b2.weight1.grad is not None
+
+
+def test_xentropy_focal_index_mul_clip():
+    from apex_b200.contrib.clip_grad import clip_grad_norm_
+    from apex_b200.contrib.focal_loss import focal_loss
+    from apex_b200.contrib.index_mul_2d import index_mul_2d
+    from apex_b200.contrib.xentropy import SoftmaxCrossEntropyLoss
+    torch.manual_seed(0)
+    x = torch.randn(6, 10, requires_grad=True)
+    lab = torch.randint(1, 10, (6,))
+    loss = SoftmaxCrossEntropyLoss.apply(x, lab, 0.1, 0, True)
+    torch.testing.assert_close(loss, F.cross_entropy(x, lab, label_smoothing=0.1, reduction="none"))
+    loss.sum().backward()
+    a, b = torch.randn(5, 4, requires_grad=True), torch.randn(7, 4, requires_grad=True)
+    idx = torch.randint(0, 5, (7,))
+    torch.testing.assert_close(index_mul_2d(a, b, idx), a[idx] * b)
+    fl = focal_loss(torch.randn(8, 5, requires_grad=True), torch.randint(-2, 4, (8,)), torch.tensor([3.0]), 4, 0.25, 2.0, 0.0)
+    assert torch.isfinite(fl).all()
+    ps = [nn.Parameter(torch.randn(5)) for _ in range(3)]
+    qs = [nn.Parameter(p.detach().clone()) for p in ps]
+    for p, q in zip(ps, qs):
+        p.grad = torch.randn(5)
+        q.grad = p.grad.clone()
+    torch.testing.assert_close(clip_grad_norm_(ps, 0.5).reshape(()), torch.nn.utils.clip_grad_norm_(qs, 0.5).reshape(()))
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.grad, q.grad)
+
+
+def test_norm_modules_cpu():
+    from apex_b200.contrib.group_norm import GroupNorm
+    from apex_b200.contrib.layer_norm import FastLayerNorm
+    from apex_b200.normalization import FusedLayerNorm, FusedRMSNorm
+    torch.manual_seed(0)
+    x = torch.randn(4, 32, requires_grad=True)
+    ln = FusedLayerNorm(32)
+    torch.testing.assert_close(ln(x), F.layer_norm(x, (32,), ln.weight, ln.bias, ln.eps))
+    rms = FusedRMSNorm(32)
+    torch.testing.assert_close(rms(x), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + rms.eps) * rms.weight)
+    fl = FastLayerNorm(32)
+    assert fl(x).shape == x.shape
+    g = GroupNorm(4, 16, act="silu")
+    img = torch.randn(2, 16, 5, 5).contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(g(img), F.silu(F.group_norm(img, 4, g.weight, g.bias, g.eps)))
+
+
+def test_batchnorm_family_cpu():
+    from apex_b200.contrib.cudnn_gbn import GroupBatchNorm2d
+    from apex_b200.contrib.groupbn import BatchNorm2d_NHWC
+    from apex_b200.parallel import SyncBatchNorm, convert_syncbn_model
+    torch.manual_seed(0)
+    m = BatchNorm2d_NHWC(8, fuse_relu=True)
+    x, z = torch.randn(2, 4, 4, 8, requires_grad=True), torch.randn(2, 4, 4, 8)
+    ref = torch.relu(F.batch_norm(x.permute(0, 3, 1, 2), None, None, m.weight, m.bias, True, 0.1, 1e-5) + z.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    torch.testing.assert_close(m(x, z), ref, atol=1e-5, rtol=1e-5)
+    m(x, z).sum().backward()
+    assert x.grad.shape == x.shape
+    assert GroupBatchNorm2d(8, group_size=1)(torch.randn(2, 8, 4, 4)).shape == (2, 8, 4, 4)
+    net = convert_syncbn_model(nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4)))
+    assert isinstance(net[1], SyncBatchNorm)
+    xi = torch.randn(2, 3, 6, 6)
+    torch.testing.assert_close(net(xi), F.batch_norm(net[0](xi), None, None, net[1].weight, net[1].bias, True, 0.1, 1e-5), atol=1e-5, rtol=1e-5)
+
+
+def test_attention_conv_and_transformer_functional_cpu():
+    from apex_b200.contrib.bottleneck import Bottleneck
+    from apex_b200.contrib.conv_bias_relu import ConvBias, ConvBiasReLU
+    from apex_b200.contrib.multihead_attn import EncdecMultiheadAttn, SelfMultiheadAttn
+    from apex_b200.transformer.functional import fused_apply_rotary_pos_emb, scaled_masked_softmax, scaled_upper_triang_masked_softmax
+    torch.manual_seed(0)
+    m = SelfMultiheadAttn(32, 4, bias=True)
+    ref = nn.MultiheadAttention(32, 4, bias=True)
+    with torch.no_grad():
+        ref.in_proj_weight.copy_(m.in_proj_weight)
+        ref.in_proj_bias.copy_(m.in_proj_bias)
+        ref.out_proj.weight.copy_(m.out_proj_weight)
+        ref.out_proj.bias.copy_(m.out_proj_bias)
+    x = torch.randn(6, 2, 32)
+    torch.testing.assert_close(m(x, x, x, is_training=False)[0], ref(x, x, x, need_weights=False)[0], atol=1e-5, rtol=1e-5)
+    assert EncdecMultiheadAttn(32, 4)(x, torch.randn(5, 2, 32), is_training=False)[0].shape == (6, 2, 32)
+    xi, w, b = torch.randn(2, 4, 8, 8), torch.randn(6, 4, 3, 3), torch.randn(1, 6, 1, 1)
+    torch.testing.assert_close(ConvBiasReLU(xi, w, b, 1, 1), torch.relu(F.conv2d(xi, w, b.view(-1), 1, 1)))
+    torch.testing.assert_close(ConvBias(xi, w, b, 1, 1), F.conv2d(xi, w, b.view(-1), 1, 1))
+    assert Bottleneck(16, 8, 32, stride=1)(torch.randn(2, 16, 8, 8)).shape == (2, 32, 8, 8)
+    s = torch.randn(2, 5, 5)
+    causal = torch.triu(torch.ones(5, 5, dtype=torch.bool), 1)
+    torch.testing.assert_close(scaled_upper_triang_masked_softmax(s, 0.5), torch.softmax((s * 0.5).masked_fill(causal, float("-inf")), -1))
+    mask = torch.zeros(2, 1, 5, 5, dtype=torch.uint8)
+    mask[..., 3:] = 1
+    s4 = torch.randn(2, 3, 5, 5)
+    torch.testing.assert_close(scaled_masked_softmax(s4, mask, 2.0), torch.softmax((s4 * 2.0).masked_fill(mask.bool(), -10000.0), -1))
+    t, freqs = torch.randn(6, 2, 3, 8), torch.randn(6, 1, 1, 8)
+    cos, sin = freqs.cos(), freqs.sin()
+    rot = torch.cat((-t[..., 4:], t[..., :4]), -1)
+    torch.testing.assert_close(fused_apply_rotary_pos_emb(t, freqs), t * cos + rot * sin, atol=1e-5, rtol=1e-5)
