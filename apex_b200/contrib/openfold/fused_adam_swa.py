@@ -44,7 +44,9 @@ class FusedAdamSWA(Optimizer):
         self._tables = None
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, grad_clip_scale=None):
+        """``grad_clip_scale`` (float or 0-dim tensor): factor applied to every gradient before the update — the caller's global-norm
+        clipping coefficient (reference fused_adam_swa.py:372-380)."""
         if len(self.param_groups) != 1:
             raise RuntimeError("FusedAdamSWA does not support multiple param groups")
         loss = closure() if closure is not None else None
@@ -57,6 +59,8 @@ class FusedAdamSWA(Optimizer):
                 st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32), torch.zeros_like(p, dtype=torch.float32)
         # gradients come from the bf16 compute copies (OpenFold runs fwd/bwd on them)
         grads = [(c.grad if c.grad is not None else p.grad) for p, c in zip(params, cparams)]
+        if grad_clip_scale is not None:
+            grads = [g * grad_clip_scale for g in grads]
         lists = [grads, params, [self.state[p]["exp_avg"] for p in params], [self.state[p]["exp_avg_sq"] for p in params]]
         beta1, beta2 = group["betas"]
         mode = 1 if self.adam_math_mode == AdamMathType.ApexAdamW else 0

@@ -122,3 +122,23 @@ def test_legacy_contrib_optimizers_cpu():
     assert not torch.equal(w0, m.weight)
     sd = opt.state_dict()
     opt.load_state_dict(sd)
+
+
+def test_fused_adam_swa_tracks_adam_and_averages():
+    from apex_b200.contrib.openfold import FusedAdamSWA
+    torch.manual_seed(0)
+    ps = [nn.Parameter(torch.randn(10)) for _ in range(2)]
+    cs = [nn.Parameter(p.detach().clone()) for p in ps]
+    ss = [p.detach().clone() for p in ps]
+    o = FusedAdamSWA(ps, cs, ss, swa_decay_rate=0.9, lr=1e-2)
+    qs = [nn.Parameter(p.detach().clone()) for p in ps]
+    ro = torch.optim.Adam(qs, lr=1e-2)
+    for _ in range(3):
+        for c, q in zip(cs, qs):
+            g = torch.randn(10)
+            c.grad, q.grad = g.clone(), g * 0.5
+        o.step(grad_clip_scale=0.5)
+        ro.step()
+    for p, q, c in zip(ps, qs, cs):
+        torch.testing.assert_close(p, q, atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(c.detach(), p.detach())
