@@ -241,3 +241,23 @@ def ddp_race_condition(rank, world, device_type):
         mean_scale = sum(r + 1 + it for r in range(world)) / world
         assert float(model.module.a.grad.sum()) == mean_scale * n, (it, float(model.module.a.grad.sum()))
         assert float(model.module.b.grad.sum()) == 2 * mean_scale * n
+
+
+def spatial_bottleneck_matches_full(rank, world, device_type):
+    """SpatialBottleneck (H split over the group + one-row halo exchange around the 3x3 conv) == Bottleneck on the whole image
+    (reference apex/contrib/test/bottleneck/test_bottleneck_module.py:283-345)."""
+    from apex_b200.contrib.bottleneck import Bottleneck, SpatialBottleneck
+    from apex_b200.contrib.bottleneck.halo_exchangers import HaloExchangerAllGather, HaloExchangerSendRecv
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(0)
+    full = Bottleneck(16, 8, 32).to(dev)
+    for bn in (full.bn1, full.bn2, full.bn3, full.downsample[1]):
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(2, 16, 8 * world, 6, device=dev)
+    want = full(x)
+    for make in (lambda: HaloExchangerAllGather(list(range(world)), rank, None), lambda: HaloExchangerSendRecv(list(range(world)), rank)):
+        halo_ex = make()
+        sp = SpatialBottleneck(16, 8, 32, spatial_parallel_args=(world, rank, None, halo_ex, 1)).to(dev)
+        sp.load_state_dict(full.state_dict())
+        got = sp(x[:, :, 8 * rank:8 * (rank + 1)].contiguous())
+        torch.testing.assert_close(got, want[:, :, 8 * rank:8 * (rank + 1)], atol=1e-5, rtol=1e-5)

@@ -13,3 +13,7 @@ def test_ddp_two_ranks_gloo(delay, message_size, predivide):
 
 def test_ddp_race_condition_gloo():
     run_distributed(cases.ddp_race_condition, 2, "cpu", backend="gloo")
+
+
+def test_spatial_bottleneck_gloo():
+    run_distributed(cases.spatial_bottleneck_matches_full, 2, "cpu", backend="gloo")
