@@ -114,3 +114,39 @@ def test_attention_conv_and_transformer_functional_cpu():
     cos, sin = freqs.cos(), freqs.sin()
     rot = torch.cat((-t[..., 4:], t[..., :4]), -1)
     torch.testing.assert_close(fused_apply_rotary_pos_emb(t, freqs), t * cos + rot * sin, atol=1e-5, rtol=1e-5)
+
+
+def test_fmha_varlen_matches_per_sequence_attention():
+    from types import SimpleNamespace
+
+    from apex_b200.contrib.fmha import FMHA
+    torch.manual_seed(0)
+    h, d = 4, 16
+    lens = [5, 9, 1, 12]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    qkv = torch.randn(sum(lens), 3 * h * d, requires_grad=True)
+    m = FMHA(SimpleNamespace(attention_probs_dropout_prob=0.0, num_attention_heads=h, hidden_size=h * d))
+    out = m(qkv, cu, max(lens), is_training=False)
+    assert out.shape == (sum(lens), h * d)
+    q3 = qkv.view(-1, 3, h, d)
+    for i, n in enumerate(lens):
+        s = int(cu[i])
+        q, k, v = (q3[s:s + n, j].transpose(0, 1) for j in range(3))   # [h, n, d]
+        ref = torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, -1) @ v
+        torch.testing.assert_close(out[s:s + n].view(n, h, d).transpose(0, 1), ref, atol=1e-5, rtol=1e-5)
+    out.sum().backward()
+    assert torch.isfinite(qkv.grad).all()
+
+
+def test_gds_file_roundtrip(tmp_path):
+    from apex_b200.contrib.gpu_direct_storage import GDSFile
+    a, b = torch.randn(7, 3), torch.randn(5).bfloat16()
+    path = str(tmp_path / "blob.bin")
+    with GDSFile(path, "w") as f:
+        f.save_data(a)
+        f.save_data(b)
+    a2, b2 = torch.empty_like(a), torch.empty_like(b)
+    with GDSFile(path, "r") as f:
+        f.load_data(a2)
+        f.load_data(b2)
+    assert torch.equal(a, a2) and torch.equal(b, b2)
