@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from pathlib import Path
 
 import torch
@@ -69,6 +70,9 @@ def host_runtime():
     return _C
 
 
+_tls = threading.local()
+
+
 class _Fn:
     __slots__ = ("name", "fn")
 
@@ -76,7 +80,15 @@ class _Fn:
         self.name, self.fn = name, fn
 
     def __call__(self, *args):
-        rc = self.fn(*args)
+        # Multi-device processes: every wrapper evaluates ``stream_ptr(tensor.device)`` among the arguments of this call; if that
+        # device is not the current one the launch runs under a device guard (what at::cuda::OptionalCUDAGuard does in the reference).
+        dev = getattr(_tls, "dev", None)
+        if dev is not None:
+            _tls.dev = None
+            with torch.cuda.device(dev):
+                rc = self.fn(*args)
+        else:
+            rc = self.fn(*args)
         if rc != 0:
             msg = f"cuda error {rc}" if rc > 0 else f"bad argument ({rc})"
             if rc > 0:
@@ -115,6 +127,10 @@ def raw_fn(name: str, restype, argtypes):
 
 
 def stream_ptr(device=None) -> int:
+    """Raw handle of the current stream of ``device``; also arms the device guard of the kernel call being assembled (see _Fn)."""
+    idx = getattr(device, "index", None)
+    if idx is not None and idx != torch.cuda.current_device():
+        _tls.dev = idx
     return torch.cuda.current_stream(device).cuda_stream
 
 

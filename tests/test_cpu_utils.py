@@ -67,3 +67,29 @@ def test_distributed_test_base_runs_ranks_on_gloo():
     suite = unittest.defaultTestLoader.loadTestsFromTestCase(GlooAllReduceCase)
     res = unittest.TextTestRunner(verbosity=0).run(suite)
     assert res.wasSuccessful(), res.failures + res.errors
+
+
+def test_kernel_calls_run_under_a_device_guard_when_tensors_live_elsewhere(monkeypatch):
+    """_lib.stream_ptr(device) arms a guard that _Fn.__call__ applies (multi-device processes; reference: OptionalCUDAGuard per op)."""
+    import types
+
+    from apex_b200 import _lib
+    events = []
+
+    class Guard:
+        def __init__(self, d):
+            self.d = d
+
+        def __enter__(self):
+            events.append(("enter", self.d))
+
+        def __exit__(self, *a):
+            events.append(("exit", self.d))
+
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", Guard)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: types.SimpleNamespace(cuda_stream=77))
+    f = _lib._Fn("probe", lambda *a: events.append(("call", a)) or 0)
+    f(1, _lib.stream_ptr(torch.device("cuda", 1)))
+    f(2, _lib.stream_ptr(torch.device("cuda", 0)))
+    assert events == [("enter", 1), ("call", (1, 77)), ("exit", 1), ("call", (2, 77))]
