@@ -75,7 +75,7 @@ def _shape(normalized_shape):
 
 
 def _run(input, weight, bias, normalized_shape, eps, memory_efficient, rms, mixed):
-    if not input.is_cuda:  # CPU tensors: plain PyTorch, like the reference modules (fused_layer_norm.py:815-822)
+    if not input.is_cuda or input.dtype == torch.float64:  # CPU tensors (reference :815-822) and fp64 (no fp64 kernel): plain PyTorch
         shape = _shape(normalized_shape)
         if rms:
             return manual_rms_norm(input, shape, weight, eps)
@@ -160,7 +160,8 @@ def supports_custom_op() -> bool:
 
 
 def _use_fallback(input) -> bool:
-    return torch.jit.is_tracing() or torch.jit.is_scripting() or torch.compiler.is_compiling() or not input.is_cuda
+    return (torch.jit.is_tracing() or torch.jit.is_scripting() or torch.compiler.is_compiling() or not input.is_cuda
+            or input.dtype == torch.float64)
 
 
 class FusedLayerNorm(torch.nn.Module):
