@@ -1,0 +1,319 @@
+// EXPERIMENTAL (not part of the default build, not yet validated on hardware): fused multi-head attention forward on tcgen05.
+//   O = softmax(scale * Q K^T + mask) V      Q, K, V: [rows, heads, d] views (any row / head stride: packed qkv, sbhd, bshd), d in {64, 128}
+// Spec: reference apex/contrib/csrc/fmha (mma.sync kernels, fp16, d = 64, seq <= 512) and the batched-GEMM + softmax pipeline of
+// apex/contrib/csrc/multihead_attn. Variable-length batches through cu_seqlens, optional causal mask.
+//
+// One CTA per (128-query tile, head, sequence). Warp roles as in gemm_sm100.cu: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
+// allocation, warps 4-7 softmax (one query row per thread = one TMEM lane).
+// TWO PASSES over the keys instead of online-softmax rescaling (rescaling the TMEM accumulator costs a TMEM load + store per tile):
+//   pass 1  S = Q K_j^T (TMEM, double buffered) -> row maximum only (no exponentials)
+//   pass 2  S recomputed (K tiles come from L2), P = exp2((S - m) * scale * log2e) written as bf16/fp16 into shared memory in the
+//           128-byte-swizzled K-major layout a TMA load would produce, row sums accumulated in registers,
+//           O += P V_j accumulated in TMEM with no rescale; epilogue: O / l -> global, log-sum-exp optional.
+// The extra cost is one more QK^T per tile (tensor time is not the bottleneck of attention at d <= 128; exponentials are, and those
+// are computed once).
+#include "../gemm_common.cuh"
+
+namespace ab {
+namespace fmha {
+using namespace ab::gemm;
+
+constexpr int TQ = 128;   // query rows per CTA
+constexpr int TK = 128;   // keys per tile
+constexpr int KV_STAGES = 2;
+
+struct Params {
+  int heads, d, causal, is_bf16;
+  const int* cu_seqlens_q; const int* cu_seqlens_k;  // [batch + 1] row offsets (varlen); null => fixed seq_q / seq_k per batch
+  int seq_q, seq_k;
+  float scale;
+  void* out; long long out_row_stride, out_head_stride;  // elements
+  float* lse;                                            // [batch? packed rows][heads] or null
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// byte offset of element (row r, col c) inside a [128 rows x 64 cols] 16-bit block in the SWIZZLE_128B K-major layout
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
+  const int chunk = (c >> 3) ^ (r & 7);
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + chunk * 16 + (c & 7) * 2);
+}
+
+template <int D>
+struct Smem {
+  static constexpr int kQ = TQ * D * 2;
+  static constexpr int kKV = TK * D * 2;
+  static constexpr int kP = TQ * TK * 2;
+  static constexpr int kQOff = 0;
+  static constexpr int kKOff = kQ;
+  static constexpr int kVOff = kKOff + KV_STAGES * kKV;
+  static constexpr int kPOff = kVOff + KV_STAGES * kKV;
+  static constexpr int kBarOff = kPOff + kP;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                ab::fmha::Params p) {
+  using S = Smem<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* q_full = bars;                        // 1
+  uint64_t* k_full = bars + 1;                    // KV_STAGES
+  uint64_t* k_empty = k_full + KV_STAGES;
+  uint64_t* v_full = k_empty + KV_STAGES;
+  uint64_t* v_empty = v_full + KV_STAGES;
+  uint64_t* s_full = v_empty + KV_STAGES;         // 2
+  uint64_t* s_empty = s_full + 2;                 // 2
+  uint64_t* p_full = s_empty + 2;                 // 1
+  uint64_t* p_empty = p_full + 1;                 // 1
+  uint64_t* o_full = p_empty + 1;                 // 1
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int q_row0 = p.cu_seqlens_q ? p.cu_seqlens_q[b] : b * p.seq_q;
+  const int q_len = p.cu_seqlens_q ? p.cu_seqlens_q[b + 1] - q_row0 : p.seq_q;
+  const int k_row0 = p.cu_seqlens_k ? p.cu_seqlens_k[b] : b * p.seq_k;
+  const int k_len = p.cu_seqlens_k ? p.cu_seqlens_k[b + 1] - k_row0 : p.seq_k;
+  if (qt * TQ >= q_len) return;  // whole CTA exits before any barrier is initialised
+  // causal: query i attends keys <= i + (k_len - q_len); tiles entirely above the diagonal are skipped
+  const int diag = k_len - q_len;
+  int n_kv = (k_len + TK - 1) / TK;
+  if (p.causal) { const int last_key = min(k_len - 1, qt * TQ + TQ - 1 + diag); n_kv = last_key < 0 ? 0 : last_key / TK + 1; }
+  constexpr uint32_t kTmemCols = 512;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&s_full[a], 1); mbar_init(&s_empty[a], 128); }
+    mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 256;
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, S::kQ);
+      for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kQOff + i * (TQ * 128), &map_q, q_full, i * 64, head, q_row0 + qt * TQ);
+      int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0;
+      for (int pass = 0; pass < 2; pass++) {
+        for (int j = 0; j < n_kv; j++) {
+          mbar_wait(&k_empty[ks], kph ^ 1, 101);
+          mbar_expect_tx(&k_full[ks], S::kKV);
+          for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kKOff + ks * S::kKV + i * (TK * 128), &map_k, &k_full[ks], i * 64, head, k_row0 + j * TK);
+          if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+          if (pass == 1) {
+            mbar_wait(&v_empty[vs], vph ^ 1, 102);
+            mbar_expect_tx(&v_full[vs], S::kKV);
+            for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kVOff + vs * S::kKV + i * (TK * 128), &map_v, &v_full[vs], i * 64, head, k_row0 + j * TK);
+            if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer (whole warp, one elected lane issues)
+    const uint32_t idesc_s = make_idesc(p.is_bf16, 0, 0, TQ, TK);   // S = Q K^T : both operands K-major (d contiguous)
+    const uint32_t idesc_o = make_idesc(p.is_bf16, 0, 1, TQ, D);    // O = P V   : P K-major (keys contiguous), V MN-major (d contiguous)
+    const uint32_t q_addr = smem_u32(smem + S::kQOff), p_addr = smem_u32(smem + S::kPOff);
+    mbar_wait(q_full, 0, 110);
+    int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0; int sb = 0; uint32_t sph = 0; uint32_t pph = 0;
+    auto issue_s = [&]() {  // S[sb] = Q K[ks]^T
+      mbar_wait(&k_full[ks], kph, 111);
+      mbar_wait(&s_empty[sb], sph ^ 1, 112);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t k_addr = smem_u32(smem + S::kKOff + ks * S::kKV);
+#pragma unroll
+        for (int k = 0; k < D / UMMA_K; k++) {
+          const uint32_t off = (k >> 2) * (TQ * 128) + (k & 3) * 32;  // 64-column blocks are [128 x 128 B] regions
+          umma_f16(tmem_s + sb * TK, make_desc(q_addr + off, 16, 1024), make_desc(k_addr + off, 16, 1024), idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[sb]);
+      }
+      __syncwarp();
+      if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+      if (++sb == 2) { sb = 0; sph ^= 1; }
+    };
+    for (int j = 0; j < n_kv; j++) issue_s();            // pass 1
+    if (n_kv > 0) issue_s();                             // pass 2, tile 0
+    for (int j = 0; j < n_kv; j++) {
+      if (j + 1 < n_kv) issue_s();                       // S of the next tile overlaps the softmax of this one
+      mbar_wait(p_full, pph, 113);
+      mbar_wait(&v_full[vs], vph, 114);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t v_addr = smem_u32(smem + S::kVOff + vs * S::kKV);
+#pragma unroll
+        for (int k = 0; k < TK / UMMA_K; k++) {
+          const uint64_t adesc = make_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_desc(v_addr + k * 2048, TK * 128, 1024);  // 16 key rows x 128 B per step; d blocks TK*128 B apart
+          umma_f16(tmem_o, adesc, bdesc, idesc_o, (j | k) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[vs]);
+        umma_commit(p_empty);
+        if (j == n_kv - 1) umma_commit(o_full);
+      }
+      __syncwarp();
+      pph ^= 1;
+      if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================================= softmax / epilogue: thread <-> query row
+    const int q = warp - 4, row = q * 32 + lane;            // TMEM lane == row of the tile
+    const int qi = qt * TQ + row;                           // index inside the sequence
+    const bool row_ok = qi < q_len;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    int sb = 0; uint32_t sph = 0;
+    float m = -INFINITY;
+    auto key_ok = [&](int kidx) { return kidx < k_len && (!p.causal || kidx <= qi + diag); };
+    // ---- pass 1: row maximum
+    for (int j = 0; j < n_kv; j++) {
+      mbar_wait(&s_full[sb], sph, 120);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TK; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) if (key_ok(j * TK + c0 + i)) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);
+      if (++sb == 2) { sb = 0; sph ^= 1; }
+    }
+    if (m == -INFINITY) m = 0.f;  // fully masked row: every p becomes 0
+    // ---- pass 2: P = exp2((S - m) * sl2), l = sum P, P -> shared memory (swizzled), O accumulated by the MMA warp
+    float l = 0.f;
+    uint32_t peph = 0;
+    uint8_t* pbuf = smem + S::kPOff;
+    for (int j = 0; j < n_kv; j++) {
+      mbar_wait(&s_full[sb], sph, 121);
+      mbar_wait(p_empty, peph ^ 1, 122);  // the previous PV has finished reading the P buffer (first use: passes immediately)
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TK; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float e = key_ok(j * TK + c0 + i) ? exp2f((__uint_as_float(r[i]) - m) * sl2) : 0.f;
+          pv[i] = e; l += e;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          T h8[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) h8[e] = from_f<T>(pv[i + e]);
+          const int c = c0 + i;
+          *reinterpret_cast<uint4*>(pbuf + (c >> 6) * (TQ * 128) + sw128_offset(row, c & 63)) = *reinterpret_cast<const uint4*>(h8);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();          // generic-proxy stores to shared memory -> visible to the tensor-core (async) proxy
+      mbar_arrive(p_full);
+      mbar_arrive(&s_empty[sb]);
+      peph ^= 1;
+      if (++sb == 2) { sb = 0; sph ^= 1; }
+    }
+    // ---- epilogue: O / l
+    if (n_kv > 0) { mbar_wait(o_full, 0, 123); tc_fence_after(); }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    T* orow = reinterpret_cast<T*>(p.out) + (size_t)(q_row0 + qi) * p.out_row_stride + (size_t)head * p.out_head_stride;
+#pragma unroll 1
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t r[32];
+      if (n_kv > 0) { tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r); tmem_ld_wait(); }
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float o8[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) o8[e] = n_kv > 0 ? __uint_as_float(r[i + e]) * inv_l : 0.f;
+          store_vec<T, 8>(orow + c0 + i, o8);
+        }
+      }
+    }
+    if (row_ok && p.lse) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * p.scale + logf(l) : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D view [rows][heads][d] of a 16-bit tensor: strides in elements; box = {64 d, 1 head, 128 rows}
+static int make_map3(CUtensorMap* m, const void* ptr, int is_bf16, long long rows, int heads, int d, long long row_stride, long long head_stride) {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult st;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return -1001;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)head_stride * 2, (cuuint64_t)row_stride * 2};
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(f)(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                                 const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(2000 + (int)r);
+}
+
+}  // namespace fmha
+}  // namespace ab
+
+using namespace ab;
+using ab::fmha::fmha_fwd_kernel; using ab::fmha::make_map3; using ab::fmha::TQ;
+
+// q / k / v: 16-bit tensors viewed as [rows, heads, d] with the given element strides (head stride and row stride multiples of 8).
+// cu_seqlens_*: device int32 [batch + 1] or null (then rows = batch * seq). out: [rows_q, heads, d] with its own strides.
+AB_API int ab_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* cu_seqlens_q, const int* cu_seqlens_k,
+                       int batch, int heads, int d, long long rows_q, long long rows_k, int max_seq_q, int seq_k, long long q_row_stride,
+                       long long q_head_stride, long long k_row_stride, long long k_head_stride, long long v_row_stride,
+                       long long v_head_stride, long long out_row_stride, long long out_head_stride, float scale, int causal, int dt,
+                       cudaStream_t st) {
+  if (batch <= 0 || heads <= 0 || rows_q <= 0) return 0;
+  if ((d != 64 && d != 128) || (dt != kBF16 && dt != kF16)) return -10;
+  if ((q_row_stride | q_head_stride | k_row_stride | k_head_stride | v_row_stride | v_head_stride) % 8) return -10;
+  const int is_bf16 = dt == kBF16;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map3(&mq, q, is_bf16, rows_q, heads, d, q_row_stride, q_head_stride))) return rc;
+  if ((rc = make_map3(&mk, k, is_bf16, rows_k, heads, d, k_row_stride, k_head_stride))) return rc;
+  if ((rc = make_map3(&mv, v, is_bf16, rows_k, heads, d, v_row_stride, v_head_stride))) return rc;
+  ab::fmha::Params p;
+  p.heads = heads; p.d = d; p.causal = causal; p.is_bf16 = is_bf16; p.cu_seqlens_q = cu_seqlens_q; p.cu_seqlens_k = cu_seqlens_k;
+  p.seq_q = max_seq_q; p.seq_k = seq_k; p.scale = scale; p.out = out; p.out_row_stride = out_row_stride; p.out_head_stride = out_head_stride;
+  p.lse = lse;
+  const dim3 grid((max_seq_q + TQ - 1) / TQ, heads, batch);
+#define FMHA_GO(T, DD)                                                                                              \
+  do {                                                                                                              \
+    auto kern = fmha_fwd_kernel<T, DD>;                                                                             \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ab::fmha::Smem<DD>::kTotal);      \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    kern<<<grid, 256, ab::fmha::Smem<DD>::kTotal, st>>>(mq, mk, mv, p);                                                       \
+  } while (0)
+  if (is_bf16) { if (d == 64) FMHA_GO(bf16, 64); else FMHA_GO(bf16, 128); }
+  else { if (d == 64) FMHA_GO(f16, 64); else FMHA_GO(f16, 128); }
+  return (int)cudaGetLastError();
+}

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _c_prototypes():
     protos = {}
-    for f in glob.glob(os.path.join(ROOT, "apex_b200/csrc/*.cu")) + glob.glob(os.path.join(ROOT, "apex_b200/csrc/*.cpp")):
+    for f in glob.glob(os.path.join(ROOT, "apex_b200/csrc/**/*.cu"), recursive=True) + glob.glob(os.path.join(ROOT, "apex_b200/csrc/*.cpp")):
         for m in re.finditer(r"AB_API\s+([\w\s\*]+?)\s+(\w+)\s*\(([^)]*)\)\s*\{", open(f).read(), re.S):
             codes = []
             for a in (x.strip() for x in m.group(3).replace("\n", " ").split(",") if x.strip()):

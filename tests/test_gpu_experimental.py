@@ -1,0 +1,41 @@
+"""Experimental kernels (csrc/experimental): only run when the library was built with APEX_B200_EXPERIMENTAL=1 — skipped otherwise."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _fmha():
+    from apex_b200.contrib.fmha import experimental as X
+    if not X.available():
+        pytest.skip("experimental kernels are not in this build (APEX_B200_EXPERIMENTAL=1 python -m apex_b200._build)")
+    return X
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("seq", [128, 200, 517])
+def test_fmha_fwd_fixed_length(cuda_dev, d, causal, seq):
+    X = _fmha()
+    torch.manual_seed(0)
+    b, h = 3, 4
+    qkv = torch.randn(b * seq, 3, h, d, device=cuda_dev, dtype=torch.bfloat16)
+    out, lse = X.fmha_fwd(qkv[:, 0], qkv[:, 1], qkv[:, 2], batch=b, causal=causal, return_lse=True)
+    q, k, v = (qkv[:, i].view(b, seq, h, d).transpose(1, 2).float() for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal)
+    torch.testing.assert_close(out.view(b, seq, h, d).transpose(1, 2).float(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_fmha_fwd_varlen(cuda_dev):
+    X = _fmha()
+    torch.manual_seed(0)
+    h, d = 4, 64
+    lens = [5, 130, 1, 300]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    qkv = torch.randn(sum(lens), 3, h, d, device=cuda_dev, dtype=torch.float16)
+    out = X.fmha_fwd(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens_q=cu, max_seqlen_q=max(lens))
+    for i, n in enumerate(lens):
+        s = int(cu[i])
+        q, k, v = (qkv[s:s + n, j].transpose(0, 1).float() for j in range(3))
+        ref = torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, -1) @ v
+        torch.testing.assert_close(out[s:s + n].transpose(0, 1).float(), ref, atol=2e-2, rtol=2e-2)
