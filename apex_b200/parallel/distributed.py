@@ -51,8 +51,11 @@ class DistributedDataParallel(torch.nn.Module):
     def __init__(self, module, message_size=10000000, delay_allreduce=False, shared_param=None, allreduce_trigger_params=None,
                  retain_allreduce_buffers=False, allreduce_always_fp32=False, num_allreduce_streams=1, allreduce_communicators=None,
                  gradient_average=True, gradient_predivide_factor=1.0, gradient_average_split_factor=None, prof=False,
-                 process_group=None):
+                 process_group=None, fused_collectives=False):
         super().__init__()
+        # EXPERIMENTAL: bucket all-reduce through the NVSwitch (parallel/nvls_allreduce.py) instead of NCCL; needs the experimental build
+        self.fused_collectives = bool(fused_collectives)
+        self._nvls = None
         if shared_param is not None:
             raise ValueError("shared_param is no longer supported as an option; use delay_allreduce=True for shared parameters")
         self.module = module
@@ -132,7 +135,8 @@ class DistributedDataParallel(torch.nn.Module):
                     flat = flat.float()
                 if self.gradient_predivide_factor != 1.0:
                     flat.mul_(1.0 / self.gradient_predivide_factor)
-                dist.all_reduce(flat, group=self.process_group)
+                if not self._allreduce_nvls(flat):
+                    dist.all_reduce(flat, group=self.process_group)
                 if self.gradient_average:
                     flat.mul_(self.gradient_predivide_factor / self.world_size)
                 if self.retain_allreduce_buffers:
@@ -141,6 +145,21 @@ class DistributedDataParallel(torch.nn.Module):
                     g.copy_(synced)
                     if stream is not None:
                         g.record_stream(stream)
+
+    def _allreduce_nvls(self, flat) -> bool:
+        if not (self.fused_collectives and flat.is_cuda):
+            return False
+        from . import nvls_allreduce as NV
+
+        if self._nvls is None:
+            if not NV.available(self.process_group):
+                self.fused_collectives = False
+                return False
+            self._nvls = NV.NvlsAllReduce(self.process_group, flat.device, max(64 << 20, flat.numel() * flat.element_size() * 2))
+        if flat.numel() * flat.element_size() > self._nvls.mem.nbytes - 4096:
+            return False
+        self._nvls.allreduce_(flat)
+        return True
 
     def disable_allreduce(self):
         self._disabled = True
