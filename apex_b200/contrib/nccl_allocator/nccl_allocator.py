@@ -1,3 +1,7 @@
+"""``nccl_allocator`` — memory pools NCCL can register (user-buffer registration / NVLS zero-copy). Reference:
+apex/contrib/nccl_allocator/nccl_allocator.py:18-82 over ``_apex_nccl_allocator`` (NCCLAllocator.cpp:17-38: a CUDAPluggableAllocator
+around ncclMemAlloc / ncclMemFree). torch now ships exactly that allocator on the NCCL backend (``backend.mem_allocator``), so the pool
+is built from it; :func:`symmetric_empty` is the B200-native alternative used by this library's own in-kernel collectives."""
 from __future__ import annotations
 
 import contextlib
