@@ -82,3 +82,23 @@ def test_scaled_states_track_adamw():
     sd = a.state_dict()
     assert sd["state"][0]["exp_avg"].dtype == torch.float32
     a.load_state_dict(sd)
+
+
+def test_negative_control_comparator_can_fail():
+    """A comparator that cannot fail proves nothing (reference test_dist_adam.py:392 test_raises_on_mismatch)."""
+    import pytest
+    import torch
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(33, 5))]
+    qs = [torch.nn.Parameter(ps[0].detach().clone())]
+    a = DistributedFusedAdam(ps, lr=1e-2, device="cpu", bucket_cap_mb=0.01)
+    b = torch.optim.AdamW(qs, lr=3e-2, weight_decay=0.0)   # deliberately different learning rate
+    a.zero_grad()
+    g = torch.randn(33, 5)
+    ps[0].grad.copy_(g)
+    qs[0].grad = g.clone()
+    a.step()
+    b.step()
+    with pytest.raises(AssertionError):
+        torch.testing.assert_close(ps[0], qs[0], rtol=1e-5, atol=1e-6)
