@@ -142,3 +142,42 @@ def test_fused_adam_swa_tracks_adam_and_averages():
     for p, q, c in zip(ps, qs, cs):
         torch.testing.assert_close(p, q, atol=1e-6, rtol=1e-5)
         torch.testing.assert_close(c.detach(), p.detach())
+
+
+def test_asp_masks_survive_checkpoint_and_optimizer_steps():
+    """Masks are module buffers: they travel with model.state_dict() and keep the weights 2:4 sparse through optimizer steps
+    (reference apex/contrib/sparsity/test/checkpointing_test_part{1,2}.py)."""
+    from apex_b200.contrib.sparsity import ASP
+
+    def make():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Linear(32, 64), nn.ReLU(), nn.Linear(64, 16))
+
+    ASP.reset()
+    model = make()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    ASP.init_model_for_pruning(model, "m4n2_1d", verbosity=0, whitelist=(nn.Linear,), allow_recompute_mask=True)
+    ASP.init_optimizer_for_pruning(opt)
+    ASP.compute_sparse_masks()
+    for _ in range(3):
+        opt.zero_grad()
+        model(torch.randn(8, 32)).pow(2).mean().backward()
+        opt.step()
+    w = model[0].weight
+    assert int((w.view(-1, 4) != 0).sum(1).max()) <= 2, "optimizer step must re-apply the masks"
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    assert any("mma_mask" in k for k in sd)
+    ASP.reset()
+    model2 = make()
+    opt2 = torch.optim.SGD(model2.parameters(), lr=0.1)
+    ASP.init_model_for_pruning(model2, "m4n2_1d", verbosity=0, whitelist=(nn.Linear,), allow_recompute_mask=True)
+    ASP.init_optimizer_for_pruning(opt2)
+    model2.load_state_dict(sd)
+    for k, v in model2.state_dict().items():
+        torch.testing.assert_close(v, sd[k])
+    opt2.zero_grad()
+    model2(torch.randn(8, 32)).pow(2).mean().backward()
+    opt2.step()
+    assert int((model2[0].weight.view(-1, 4) != 0).sum(1).max()) <= 2
+    ASP.restore_pruned_weights()
+    ASP.reset()
