@@ -75,3 +75,50 @@ def test_state_dict_roundtrip_cpu():
     b = FusedAdam(_params(), lr=1e-2)
     b.load_state_dict(sd)
     assert b.state_dict()["param_groups"][0]["step"] == 1
+
+
+def test_fused_lamb_cpu_matches_reference_lamb():
+    """In-file LAMB oracle like the reference's RefLAMB (tests/L0/run_optimizers/test_lamb.py:11-100): global-norm clipping, Adam
+    moments with bias correction, decoupled weight decay inside the update, per-tensor trust ratio."""
+    import torch
+    from apex_b200.optimizers import FusedLAMB
+    torch.manual_seed(0)
+
+    def ref_step(params, grads, state, lr, b1, b2, eps, wd, step, max_gn):
+        gn = torch.sqrt(sum((g ** 2).sum() for g in grads))
+        clip = max(float(gn) / max_gn, 1.0)
+        for p, g, st in zip(params, grads, state):
+            g = g / clip
+            st["m"] = b1 * st["m"] + (1 - b1) * g
+            st["v"] = b2 * st["v"] + (1 - b2) * g * g
+            u = (st["m"] / (1 - b1 ** step)) / ((st["v"] / (1 - b2 ** step)).sqrt() + eps) + wd * p
+            pn, un = p.norm(), u.norm()
+            p -= lr * (float(pn / un) if (pn > 0 and un > 0) else 1.0) * u
+
+    ps = [torch.nn.Parameter(torch.randn(37, 5)), torch.nn.Parameter(torch.randn(11))]
+    qs = [p.detach().clone() for p in ps]
+    st = [{"m": torch.zeros_like(q), "v": torch.zeros_like(q)} for q in qs]
+    opt = FusedLAMB(ps, lr=1e-2, weight_decay=0.01, max_grad_norm=1.0)
+    for step in range(1, 5):
+        gs = [torch.randn_like(p) * 3 for p in ps]
+        for p, g in zip(ps, gs):
+            p.grad = g.clone()
+        opt.step()
+        ref_step(qs, gs, st, 1e-2, 0.9, 0.999, 1e-6, 0.01, step, 1.0)
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.detach(), q, rtol=1e-5, atol=1e-6)
+
+
+def test_novograd_and_mixed_precision_lamb_run_on_cpu():
+    import torch
+    from apex_b200.optimizers import FusedMixedPrecisionLamb, FusedNovoGrad
+    torch.manual_seed(0)
+    for cls in (FusedNovoGrad, FusedMixedPrecisionLamb):
+        p = torch.nn.Parameter(torch.randn(37, 5))
+        p0 = p.detach().clone()
+        opt = cls([p], lr=1e-2)
+        for _ in range(3):
+            p.grad = torch.randn(37, 5)
+            opt.step()
+        assert torch.isfinite(p).all() and not torch.equal(p.detach(), p0)
+        opt.load_state_dict(opt.state_dict())
