@@ -122,3 +122,30 @@ def test_novograd_and_mixed_precision_lamb_run_on_cpu():
             opt.step()
         assert torch.isfinite(p).all() and not torch.equal(p.detach(), p0)
         opt.load_state_dict(opt.state_dict())
+
+
+def test_fused_novograd_cpu_matches_layerwise_oracle():
+    """NovoGrad with a per-tensor second moment (same option set as tests/L0/run_optimizers/test_fused_novograd.py:130-155:
+    betas (0.95, 0), no bias correction, norm inside the moment, L2 norm, no zero init)."""
+    import torch
+    from apex_b200.optimizers import FusedNovoGrad
+    torch.manual_seed(0)
+    shapes = [(64, 9), (31,), (1,)]
+    ps = [torch.nn.Parameter(torch.rand(s)) for s in shapes]
+    qs = [p.detach().clone() for p in ps]
+    m = [torch.zeros_like(q) for q in qs]
+    v = [torch.zeros(()) for _ in qs]
+    opt = FusedNovoGrad(ps, lr=1e-3, betas=(0.95, 0), eps=1e-8, weight_decay=0, grad_averaging=False, bias_correction=False,
+                        reg_inside_moment=True, norm_type=2, init_zero=False)
+    for _ in range(5):
+        gs = [torch.rand_like(q) for q in qs]
+        for p, g in zip(ps, gs):
+            p.grad = g.clone()
+        opt.step()
+        for i, (q, g) in enumerate(zip(qs, gs)):
+            n2 = (g * g).sum()
+            v[i] = n2 if float(v[i]) == 0 else 0.0 * v[i] + 1.0 * n2
+            m[i] = 0.95 * m[i] + g / (v[i].sqrt() + 1e-8)
+            q -= 1e-3 * m[i]
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p.detach(), q, rtol=1e-5, atol=1e-7)
