@@ -150,3 +150,24 @@ def test_gds_file_roundtrip(tmp_path):
         f.load_data(a2)
         f.load_data(b2)
     assert torch.equal(a, a2) and torch.equal(b, b2)
+
+
+def test_wgrad_accumulation_and_scale_mask_softmax_module_cpu():
+    from apex_b200.transformer.functional import FusedScaleMaskSoftmax
+    from apex_b200.transformer.functional import fused_weight_gradient as W
+    from apex_b200.transformer.functional.fused_softmax import AttnMaskType
+    torch.manual_seed(0)
+    x, dy = torch.randn(6, 4, 8), torch.randn(6, 4, 5)
+    main_grad = torch.ones(5, 8)
+    W.wgrad_gemm_accum_fp32(x, dy, main_grad)   # beta = 1 accumulation into the persistent main-grad buffer
+    torch.testing.assert_close(main_grad, 1 + dy.reshape(-1, 5).t() @ x.reshape(-1, 8))
+    m = FusedScaleMaskSoftmax(False, False, AttnMaskType.padding, True, lambda s, mk: s.masked_fill(mk, -10000.0), True, 0.5)
+    s = torch.randn(2, 3, 5, 5)
+    mk = torch.zeros(2, 1, 5, 5, dtype=torch.bool)
+    mk[..., 4] = True
+    torch.testing.assert_close(m(s, mk), torch.softmax((s * 0.5).masked_fill(mk, -10000.0), -1))
+    # 16-bit input + fusion enabled -> the fused (here: CPU oracle) causal path, which masks implicitly
+    causal = FusedScaleMaskSoftmax(False, True, AttnMaskType.causal, True, None, True, None)
+    tri = torch.triu(torch.ones(5, 5, dtype=torch.bool), 1)
+    sb = s.bfloat16()
+    torch.testing.assert_close(causal(sb, None).float(), torch.softmax(sb.float().masked_fill(tri, float("-inf")), -1), atol=1e-2, rtol=1e-2)
