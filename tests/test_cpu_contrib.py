@@ -181,3 +181,29 @@ def test_asp_masks_survive_checkpoint_and_optimizer_steps():
     assert int((model2[0].weight.view(-1, 4) != 0).sum(1).max()) <= 2
     ASP.restore_pruned_weights()
     ASP.reset()
+
+
+def test_fused_adam_cuda_entry_points_reversible_step_and_checks():
+    """reversible_adam followed by maybe_adam_undo (flag set) restores p, m, v; the strided finite check samples every k-th element
+    (reference apex/contrib/csrc/optimizers/fused_adam_cuda.cpp:92-104)."""
+    from apex_b200.contrib.optimizers import fused_adam_cuda as F
+    torch.manual_seed(0)
+    for mode in (0, 1):
+        p, m, v, g = torch.randn(100), torch.rand(100) * 0.1, torch.rand(100) * 0.1, torch.randn(100) * 4
+        p0, m0, v0 = p.clone(), m.clone(), v.clone()
+        args = (1e-2, 0.9, 0.999, 1e-8, 2.0, 3, mode, 1, 0.01)
+        copy = torch.empty(100, dtype=torch.bfloat16)
+        F.reversible_adam(p, copy, m, v, g, *args)
+        assert not torch.equal(p, p0)
+        torch.testing.assert_close(copy.float(), p, atol=2e-2, rtol=2e-2)
+        F.maybe_adam_undo(torch.zeros(1), p, m, v, g, *args)           # flag clear: nothing happens
+        assert not torch.equal(p, p0)
+        F.maybe_adam_undo(torch.ones(1), p, m, v, g, *args)
+        for a, b in ((p, p0), (m, m0), (v, v0)):
+            torch.testing.assert_close(a, b, atol=1e-6, rtol=1e-5)
+    flag, x = torch.zeros(1), torch.ones(10)
+    x[4] = float("inf")
+    F.strided_check_finite(flag, x, 2, 1)
+    assert flag.item() == 1
+    F.strided_check_finite(flag, x, 3, 1)
+    assert flag.item() == 0
