@@ -44,3 +44,9 @@ def install_as_apex() -> None:
             sys.modules.setdefault(f"apex.{name}", sub)
         except Exception:  # noqa: BLE001
             pass
+    try:  # the reference's compiled-extension names (fused_layer_norm_cuda, scaled_*_softmax_cuda, xentropy_cuda, ...)
+        from . import ext_compat
+
+        ext_compat.install()
+    except Exception:  # noqa: BLE001
+        pass

@@ -171,3 +171,33 @@ def test_wgrad_accumulation_and_scale_mask_softmax_module_cpu():
     tri = torch.triu(torch.ones(5, 5, dtype=torch.bool), 1)
     sb = s.bfloat16()
     torch.testing.assert_close(causal(sb, None).float(), torch.softmax(sb.float().masked_fill(tri, float("-inf")), -1), atol=1e-2, rtol=1e-2)
+
+
+def test_extension_name_modules():
+    """`install_as_apex` registers the reference's extension names; their raw entry points follow the reference's signatures."""
+    import importlib
+
+    import apex_b200
+
+    apex_b200.install_as_apex()
+    ln = importlib.import_module("fused_layer_norm_cuda")
+    x, w, b = torch.randn(4, 8), torch.randn(8), torch.randn(8)
+    y, mean, invvar = ln.forward_affine(x, (8,), w, b, 1e-5)
+    torch.testing.assert_close(y, torch.nn.functional.layer_norm(x, (8,), w, b, 1e-5))
+    assert mean.shape == invvar.shape == (4,)
+    y, invvar = ln.rms_forward_affine(x, (8,), w, 1e-5)
+    torch.testing.assert_close(y, x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w)
+    sm = importlib.import_module("scaled_upper_triang_masked_softmax_cuda")
+    a = torch.randn(2, 5, 5)
+    p = sm.forward(a, 0.5)
+    mask = torch.triu(torch.ones(5, 5, dtype=torch.bool), 1)
+    torch.testing.assert_close(p, torch.softmax((a * 0.5).masked_fill(mask, float("-inf")), -1))
+    assert sm.backward(torch.randn(2, 5, 5), p, 0.5).shape == a.shape
+    xe = importlib.import_module("xentropy_cuda")
+    lg, lab = torch.randn(6, 10), torch.randint(0, 10, (6,))
+    losses, mlse = xe.forward(lg, lab, 0.1, True)
+    torch.testing.assert_close(losses, torch.nn.functional.cross_entropy(lg, lab, label_smoothing=0.1, reduction="none"))
+    assert xe.backward(torch.ones(6), lg, mlse, lab, 0.1).shape == lg.shape
+    for name in ("amp_C", "syncbn", "apex_C", "fused_weight_gradient_mlp_cuda", "scaled_masked_softmax_cuda", "scaled_softmax_cuda",
+                 "generic_scaled_masked_softmax_cuda", "fused_rotary_positional_embedding"):
+        assert importlib.import_module(name) is not None
