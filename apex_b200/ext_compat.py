@@ -100,10 +100,6 @@ def _rope_mod():
 def _xentropy_mod():
     from .contrib.xentropy.softmax_xentropy import SoftmaxCrossEntropyLoss as X
 
-    class _Ctx:
-        def save_for_backward(self, *t):
-            self.saved_tensors = t
-
     def forward(logits, labels, smoothing, half_to_float):
         ctx = _Ctx()
         losses = X.forward(ctx, logits, labels, smoothing, -1, half_to_float)  # padding is applied by the python layer of the reference
@@ -118,6 +114,263 @@ def _xentropy_mod():
     return _mod("xentropy_cuda", forward=forward, backward=backward)
 
 
+def _dense_mods():
+    from .ops import gemm as G
+
+    def linear_bias_forward(input, weight, bias):
+        return G.linear_fwd(input.contiguous(), weight.contiguous(), bias)
+
+    def linear_bias_backward(input, weight, d_output):
+        dy = d_output.contiguous()
+        return [G.linear_dgrad(dy, weight.contiguous()), G.linear_wgrad(dy, input.contiguous()), G.colsum(dy)]
+
+    def linear_gelu_linear_forward(input, weight1, bias1, weight2, bias2):
+        x = input.contiguous()
+        gelu_in = torch.empty(x.shape[0], weight1.shape[0], dtype=x.dtype, device=x.device)
+        output1 = G.linear_fwd(x, weight1.contiguous(), bias1, epi=G.EPI_BIAS_GELU, aux=gelu_in)
+        return [output1, G.linear_fwd(output1, weight2.contiguous(), bias2), gelu_in]
+
+    def linear_gelu_linear_backward(input, gelu_in, output1, weight1, weight2, d_output2):
+        dy = d_output2.contiguous()
+        d_gelu_in = G.linear_dgrad(dy, weight2.contiguous(), dgelu_aux=gelu_in)
+        return [G.linear_dgrad(d_gelu_in, weight1.contiguous()), G.linear_wgrad(d_gelu_in, input.contiguous()), G.colsum(d_gelu_in),
+                G.linear_wgrad(dy, output1), G.colsum(dy)]
+
+    def _split(use_bias, inputs):
+        n = (len(inputs) - 1) // (2 if use_bias else 1)
+        return n, inputs[1:1 + n], (inputs[1 + n:1 + 2 * n] if use_bias else [None] * n)
+
+    def mlp_forward(use_bias, activation, inputs):
+        """-> [output, hidden_1, ..., hidden_{n-1}]  (the reference returns [output, reserved_space]; pass the list back to backward)."""
+        n, ws, bs = _split(use_bias, list(inputs))
+        acts = [inputs[0].contiguous()]
+        for w, b in zip(ws, bs):
+            epi = {0: (G.EPI_NONE, G.EPI_BIAS), 1: (G.EPI_RELU, G.EPI_BIAS_RELU), 2: (G.EPI_SIGMOID, G.EPI_BIAS_SIGMOID)}[int(activation)][b is not None]
+            acts.append(G.linear_fwd(acts[-1], w.contiguous(), b, epi=epi))
+        return [acts[-1], *acts[1:-1]]
+
+    def mlp_backward(use_bias, activation, grad_o, fprop_outputs, inputs):
+        n, ws, _ = _split(use_bias, list(inputs))
+        acts = [inputs[0].contiguous(), *fprop_outputs[1:], fprop_outputs[0]]
+        dy = grad_o.contiguous()
+        dws, dbs = [None] * n, [None] * n
+        for i in range(n - 1, -1, -1):
+            y = acts[i + 1]
+            if activation == 1:
+                dy = dy * (y > 0).to(dy.dtype)
+            elif activation == 2:
+                dy = (dy.float() * (y.float() * (1 - y.float()))).to(dy.dtype)
+            dws[i] = G.linear_wgrad(dy, acts[i])
+            if use_bias:
+                dbs[i] = G.colsum(dy)
+            dy = G.linear_dgrad(dy, ws[i].contiguous())
+        return [dy, *dws, *(dbs if use_bias else [])]
+
+    return {
+        "fused_dense_cuda": _mod("fused_dense_cuda", linear_bias_forward=linear_bias_forward, linear_bias_backward=linear_bias_backward,
+                                 linear_gelu_linear_forward=linear_gelu_linear_forward, linear_gelu_linear_backward=linear_gelu_linear_backward),
+        "mlp_cuda": _mod("mlp_cuda", forward=mlp_forward, backward=mlp_backward),
+    }
+
+
+def _fast_layer_norm_mod(ln):
+    def ln_fwd(x, gamma, beta, epsilon):
+        """-> [z, mu, rsigma]  (apex/contrib/csrc/layer_norm/ln_api.cpp:83)"""
+        return list(ln.forward_affine_mixed_dtypes(x, (x.shape[-1],), gamma, beta, epsilon))
+
+    def ln_bwd(dz, x_or_z, mu, rsigma, gamma, beta=None, memory_efficient=False):
+        """-> [dx, dgamma, dbeta, dgamma_part, dbeta_part]; the two partial buffers of the reference are internal scratch, returned empty."""
+        dx, dg, db = ln.backward_affine(dz, mu, rsigma, x_or_z, (x_or_z.shape[-1],), gamma, beta if beta is not None else torch.zeros_like(gamma),
+                                        0.0, memory_efficient)
+        e = dg.new_empty(0)
+        return [dx, dg, db, e, e]
+
+    return _mod("fast_layer_norm", ln_fwd=ln_fwd, ln_bwd=ln_bwd)
+
+
+def _small_contrib_mods():
+    from . import _lib
+    from .contrib.focal_loss import focal_loss as FL
+    from .contrib.index_mul_2d import index_mul_2d as IM
+
+    def focal_forward(cls_output, cls_targets_at_level, num_positives_sum, num_real_classes, alpha, gamma, smoothing_factor):
+        """-> [loss, partial_grad]"""
+        ctx = _Ctx()
+        loss = FL.FocalLoss.forward(ctx, cls_output, cls_targets_at_level, num_positives_sum, num_real_classes, alpha, gamma, smoothing_factor)
+        return [loss, ctx.saved_tensors[0]]
+
+    def focal_backward(grad_output, partial_grad, num_positives_sum):
+        ctx = _Ctx()
+        ctx.saved_tensors = (partial_grad, num_positives_sum.float().reshape(1))
+        return FL.FocalLoss.backward(ctx, grad_output)[0]
+
+    def im_forward(out, in1, in2, idx1):
+        if not IM._native(in1):
+            out.copy_(in1.index_select(0, idx1) * in2)
+            return
+        _lib.fn("ab_index_mul_2d_fwd")(in1.data_ptr(), in2.data_ptr(), idx1.data_ptr(), out.data_ptr(), in2.shape[0], in2.shape[1], _lib.dt(in1),
+                                       _lib.stream_ptr(in1.device))
+
+    def im_backward(grad_in1, grad_in2, grad_out, in1, in2, idx1):
+        """grad_in1 must arrive zero-filled (it is accumulated into), as in the reference."""
+        if not IM._native(in1):
+            grad_in1.index_add_(0, idx1, (grad_out * in2).to(grad_in1.dtype))
+            grad_in2.copy_(grad_out * in1.index_select(0, idx1))
+            return
+        g1, g2 = IM._IndexMul2dBackward.forward(_Ctx(), in1, in2, idx1, grad_out.contiguous())
+        grad_in1.add_(g1)
+        grad_in2.copy_(g2)
+
+    def im_backward_backward(grad_grad_out, grad_in1, grad_in2, grad_out, grad_grad_in1, grad_grad_in2, in1, in2, idx1):
+        gg1 = grad_grad_in1.index_select(0, idx1)
+        grad_in1.index_add_(0, idx1, (grad_grad_in2 * grad_out).to(grad_in1.dtype))
+        grad_in2.copy_(gg1 * grad_out)
+        grad_grad_out.copy_(gg1 * in2 + grad_grad_in2 * in1.index_select(0, idx1))
+
+    return {
+        "focal_loss_cuda": _mod("focal_loss_cuda", forward=focal_forward, backward=focal_backward),
+        "fused_index_mul_2d": _mod("fused_index_mul_2d", float_forward=im_forward, float_backward=im_backward, float_backward_backward=im_backward_backward,
+                                   half_forward=im_forward, half_backward=im_backward, half_backward_backward=im_backward_backward),
+    }
+
+
+def _distopt_mods():
+    from . import _lib
+    from .ops import amp_C
+    from .ops import reference as ref
+
+    def _cuda(lists):
+        return len(lists[0]) > 0 and lists[0][0].is_cuda
+
+    def multi_tensor_fused_adam(chunk_size, noop_flag, tensor_lists, grad_scale, lr, beta1, beta2, eps, step, mode, bias_correction, weight_decay):
+        """[p_in, m, v, g, p_out]  (apex/contrib/csrc/optimizers/multi_tensor_distopt_adam.cpp:3)"""
+        if not tensor_lists or not tensor_lists[0]:
+            return
+        if not _cuda(tensor_lists):
+            for p_in, m, v, g, p_out in zip(*tensor_lists):
+                ref.dist_adam(p_in, m, v, g, p_out, grad_scale, lr, beta1, beta2, eps, step, mode, bias_correction, weight_decay)
+            return
+        tb = amp_C.TensorTable(tensor_lists, chunk_size)
+        d = tb.dtypes
+        _lib.fn("ab_mt_dist_adam")(*tb.head(), d[0], d[3], d[4], grad_scale.data_ptr(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                   int(mode), int(bias_correction), float(weight_decay), 0, None, None, None, _lib.stream_ptr(tb.device))
+
+    def multi_tensor_fused_adam_capturable(chunk_size, noop_flag, tensor_lists, grad_scale, lr, beta1, beta2, eps, step, mode, bias_correction,
+                                           weight_decay):
+        """lr / step are device tensors; nothing is written when ``noop_flag`` is set."""
+        if not tensor_lists or not tensor_lists[0]:
+            return
+        if not _cuda(tensor_lists):
+            if int(noop_flag.item()) == 1:
+                return
+            for p_in, m, v, g, p_out in zip(*tensor_lists):
+                ref.dist_adam(p_in, m, v, g, p_out, grad_scale, float(lr), beta1, beta2, eps, int(step), mode, bias_correction, weight_decay)
+            return
+        tb = amp_C.TensorTable(tensor_lists, chunk_size)
+        d = tb.dtypes
+        step_i = step if step.dtype == torch.int32 else step.to(torch.int32)
+        lr_f = lr if lr.dtype == torch.float32 else lr.float()
+        _lib.fn("ab_mt_dist_adam")(*tb.head(), d[0], d[3], d[4], grad_scale.data_ptr(), 0.0, float(beta1), float(beta2), float(eps), 0, int(mode),
+                                   int(bias_correction), float(weight_decay), 1, lr_f.data_ptr(), step_i.data_ptr(), _lib.ptr(noop_flag),
+                                   _lib.stream_ptr(tb.device))
+
+    def multi_tensor_fused_adam_with_param_remainders(chunk_size, noop_flag, tensor_lists, grad_scale, lr, beta1, beta2, eps, step, mode,
+                                                      bias_correction, weight_decay):
+        """[p_in (bf16 bits as int16), p_remainder (int16), m, v, g, p_out (bf16)]: fp32 master = (p_in << 16) + remainder."""
+        if not tensor_lists or not tensor_lists[0]:
+            return
+        if not _cuda(tensor_lists):
+            for p_hi, p_lo, m, v, g, p_out in zip(*tensor_lists):
+                hi, lo = p_hi.view(torch.int16).to(torch.int32), p_lo.to(torch.int32)
+                master = ((hi << 16) + lo).view(torch.float32).clone()   # remainder is signed: hi was rounded to nearest
+                ref.dist_adam(master, m, v, g, None, grad_scale, lr, beta1, beta2, eps, step, mode, bias_correction, weight_decay)
+                bits = master.view(torch.int32)
+                new_lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000             # sign-extended low half
+                new_hi = (bits - new_lo) >> 16
+                p_lo.copy_(new_lo.to(torch.int16))
+                p_out.view(torch.int16).copy_(new_hi.to(torch.int16))    # p_in is read-only (it normally aliases p_out)
+            return
+        lists = [[t.view(torch.int16) for t in tensor_lists[0]], list(tensor_lists[1]), list(tensor_lists[2]), list(tensor_lists[3]),
+                 list(tensor_lists[4]), [t.view(torch.int16) for t in tensor_lists[5]]]
+        tb = amp_C.TensorTable(lists, chunk_size)
+        _lib.fn("ab_mt_dist_adam_remainders")(*tb.head(), tb.dtypes[4], grad_scale.data_ptr(), float(lr), float(beta1), float(beta2), float(eps),
+                                              int(step), int(mode), int(bias_correction), float(weight_decay), _lib.stream_ptr(tb.device))
+
+    def multi_tensor_lamb_compute_update_term(chunk_size, noop_flag, tensor_lists, per_tensor_beta1, per_tensor_beta2, per_tensor_beta3,
+                                              per_tensor_bias_correction, step, per_tensor_epsilon, mode, per_tensor_decay, global_scale,
+                                              global_grad_norm, max_grad_norm):
+        """[g, p, m, v, u]: Adam-style update term with per-tensor hyper-parameters held in device tensors
+        (multi_tensor_distopt_lamb_kernel.cu:98-274 of the reference). Off this library's hot path (DistributedFusedLAMB uses the fused
+        stage kernels); expressed with torch ops so device scalars never reach the host."""
+        if int(noop_flag.item()) == 1:
+            return
+        gs = global_scale.float().reshape(())
+        cs = gs
+        if max_grad_norm > 0:
+            c = max_grad_norm / (global_grad_norm.float().reshape(()) / gs + 1e-6)
+            cs = gs / torch.clamp(c, max=1.0)
+        stepf = step.float().reshape(())
+        for i, (g, p, m, v, u) in enumerate(zip(*tensor_lists)):
+            b1, b2, eps, decay = per_tensor_beta1[i], per_tensor_beta2[i], per_tensor_epsilon[i], per_tensor_decay[i]
+            bc = per_tensor_bias_correction[i] == 1
+            c1 = torch.where(bc, 1 - b1 ** stepf, torch.ones_like(b1))
+            c2 = torch.where(bc, 1 - b2 ** stepf, torch.ones_like(b2))
+            sg = g.float() / cs
+            pf = p.float()
+            if mode == 0:
+                sg = sg + decay * pf
+            mf = m.float() * b1 + (1 - b1) * sg
+            vf = v.float() * b2 + (1 - b2) * sg * sg
+            upd = (mf / c1) / ((vf / c2).sqrt() + eps)
+            if mode != 0:
+                upd = upd + decay * pf
+            m.copy_(mf)
+            v.copy_(vf)
+            u.copy_(upd)
+
+    def multi_tensor_lamb_update_weights(chunk_size, noop_flag, tensor_lists, per_tensor_param_norm, per_tensor_update_norm, update_norm_offset,
+                                         learning_rate, per_tensor_decay, global_grad_norm, use_nvlamb):
+        """[u, p, p_copy]: p -= lr * trust_ratio * u, trust ratio only where decay != 0 unless ``use_nvlamb`` (kernel :276-360)."""
+        if int(noop_flag.item()) == 1:
+            return
+        lr = learning_rate.float().reshape(())
+        for i, (u, p, p_copy) in enumerate(zip(*tensor_lists)):
+            pn, un = per_tensor_param_norm[i], per_tensor_update_norm[update_norm_offset[i]]
+            adaptive = (un != 0) & (pn != 0)
+            if not use_nvlamb:
+                adaptive = adaptive & (per_tensor_decay[i] != 0)
+            ratio = torch.where(adaptive, lr * pn / torch.where(un != 0, un, torch.ones_like(un)), lr)
+            pf = p.float() - ratio * u.float()
+            p.copy_(pf)
+            p_copy.copy_(pf)
+
+    def lamb(chunk_size, noop_flag, tensor_lists, lr, beta1, beta2, epsilon, step, bias_correction, weight_decay, grad_averaging, mode,
+             global_grad_norm, max_grad_norm):
+        """fused_lamb_cuda.lamb: the deprecated contrib LAMB with a HOST float global_grad_norm (fused_lamb_cuda.cpp:3)."""
+        dev = tensor_lists[0][0].device
+        gn = torch.full((1,), float(global_grad_norm), dtype=torch.float32, device=dev)
+        amp_C.multi_tensor_lamb(chunk_size, noop_flag, tensor_lists, lr, beta1, beta2, epsilon, step, bias_correction, weight_decay, grad_averaging,
+                                mode, gn, max_grad_norm)
+
+    return {
+        "distributed_adam_cuda": _mod("distributed_adam_cuda", multi_tensor_fused_adam=multi_tensor_fused_adam,
+                                      multi_tensor_fused_adam_capturable=multi_tensor_fused_adam_capturable,
+                                      multi_tensor_fused_adam_with_param_remainders=multi_tensor_fused_adam_with_param_remainders),
+        "distributed_lamb_cuda": _mod("distributed_lamb_cuda", multi_tensor_lamb_compute_update_term=multi_tensor_lamb_compute_update_term,
+                                      multi_tensor_lamb_update_weights=multi_tensor_lamb_update_weights),
+        "fused_lamb_cuda": _mod("fused_lamb_cuda", lamb=lamb),
+    }
+
+
+class _Ctx:
+    """Stand-in for an autograd context when a Function's forward / backward is driven directly."""
+
+    needs_input_grad = (True,) * 8
+
+    def save_for_backward(self, *t):
+        self.saved_tensors = t
+
+
 def extension_modules() -> dict:
     from .ops import amp_C
     from .parallel import syncbn_ops
@@ -128,6 +381,9 @@ def extension_modules() -> dict:
             "apex_C": _mod("apex_C", flatten=flatten.flatten, unflatten=flatten.unflatten),
             "fused_layer_norm_cuda": _layer_norm_mod(), "fused_rotary_positional_embedding": _rope_mod(), "xentropy_cuda": _xentropy_mod()}
     mods.update(_softmax_mods())
+    mods["fast_layer_norm"] = _fast_layer_norm_mod(mods["fused_layer_norm_cuda"])
+    for group in (_dense_mods, _small_contrib_mods, _distopt_mods):
+        mods.update(group())
     try:
         from .contrib.optimizers import fused_adam_cuda
 

@@ -201,3 +201,82 @@ def test_extension_name_modules():
     for name in ("amp_C", "syncbn", "apex_C", "fused_weight_gradient_mlp_cuda", "scaled_masked_softmax_cuda", "scaled_softmax_cuda",
                  "generic_scaled_masked_softmax_cuda", "fused_rotary_positional_embedding"):
         assert importlib.import_module(name) is not None
+
+
+def test_extension_name_modules_dense_and_distopt():
+    """fused_dense_cuda / mlp_cuda / fast_layer_norm / distributed_adam_cuda / distributed_lamb_cuda raw entry points on the CPU paths."""
+    import importlib
+
+    import apex_b200
+
+    apex_b200.install_as_apex()
+    torch.manual_seed(0)
+    fd, mlp_cuda = importlib.import_module("fused_dense_cuda"), importlib.import_module("mlp_cuda")
+    x, w1, b1, w2, b2 = torch.randn(8, 16), torch.randn(32, 16), torch.randn(32), torch.randn(4, 32), torch.randn(4)
+    leaves = [t.clone().requires_grad_() for t in (x, w1, b1, w2, b2)]
+    ref = F.linear(F.gelu(F.linear(leaves[0], leaves[1], leaves[2])), leaves[3], leaves[4])
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    o1, o2, gelu_in = fd.linear_gelu_linear_forward(x, w1, b1, w2, b2)
+    torch.testing.assert_close(o2, ref.detach())
+    for got, leaf in zip(fd.linear_gelu_linear_backward(x, gelu_in, o1, w1, w2, dy), leaves):
+        torch.testing.assert_close(got, leaf.grad, rtol=1e-4, atol=1e-4)
+    for t in leaves:
+        t.grad = None
+    ref = torch.sigmoid(F.linear(torch.sigmoid(F.linear(leaves[0], leaves[1], leaves[2])), leaves[3], leaves[4]))
+    ref.backward(dy)
+    outs = mlp_cuda.forward(1, 2, [x, w1, w2, b1, b2])
+    torch.testing.assert_close(outs[0], ref.detach())
+    grads = mlp_cuda.backward(1, 2, dy, outs, [x, w1, w2, b1, b2])
+    for got, leaf in zip(grads, [leaves[0], leaves[1], leaves[3], leaves[2], leaves[4]]):
+        torch.testing.assert_close(got, leaf.grad, rtol=1e-4, atol=1e-4)
+    fln = importlib.import_module("fast_layer_norm")
+    g, b = torch.randn(16), torch.randn(16)
+    z, mu, rs = fln.ln_fwd(x, g, b, 1e-5)
+    torch.testing.assert_close(z, F.layer_norm(x, (16,), g, b, 1e-5))
+
+    # distributed_adam_cuda: plain and bf16 + int16-remainder variants against torch.optim.AdamW on the fp32 master
+    da = importlib.import_module("distributed_adam_cuda")
+    p0 = torch.randn(1000)
+    grads = [torch.randn(1000) for _ in range(3)]
+    pr = p0.clone().requires_grad_()
+    opt = torch.optim.AdamW([pr], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.1)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    bits = p0.view(torch.int32)
+    lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
+    hi16 = ((bits - lo) >> 16).to(torch.int16)
+    p_bf16, rem = hi16.view(torch.bfloat16).clone(), lo.to(torch.int16)
+    m2, v2 = torch.zeros(1000), torch.zeros(1000)
+    noop, one = torch.zeros(1, dtype=torch.int32), torch.ones(1)
+    for step, gr in enumerate(grads, 1):
+        pr.grad = gr.clone()
+        opt.step()
+        da.multi_tensor_fused_adam(65536, noop, [[p], [m], [v], [gr.clone()], [p]], one, 1e-2, 0.9, 0.99, 1e-8, step, 1, 1, 0.1)
+        da.multi_tensor_fused_adam_with_param_remainders(65536, noop, [[p_bf16], [rem], [m2], [v2], [gr.clone()], [p_bf16]], one, 1e-2, 0.9, 0.99,
+                                                         1e-8, step, 1, 1, 0.1)
+    torch.testing.assert_close(p, pr.detach(), rtol=1e-5, atol=1e-6)
+    master = ((p_bf16.view(torch.int16).to(torch.int32) << 16) + rem.to(torch.int32)).view(torch.float32)
+    torch.testing.assert_close(master, pr.detach(), rtol=1e-5, atol=1e-6)          # hi + remainder IS the fp32 master
+    torch.testing.assert_close(p_bf16.float(), pr.detach(), rtol=1e-2, atol=1e-2)  # and hi alone is its bf16 rounding
+
+    # distributed_lamb_cuda: update term + weight update == the multi-tensor LAMB oracle with one hyper-parameter set
+    from apex_b200.ops import reference as oracle
+
+    dl = importlib.import_module("distributed_lamb_cuda")
+    ps = [torch.randn(50), torch.randn(7, 9)]
+    gs = [torch.randn_like(t) for t in ps]
+    n = len(ps)
+    ms, vs, us = ([torch.zeros_like(t) for t in ps] for _ in range(3))
+    p_ref, g_ref, m_ref, v_ref = ([t.clone() for t in l] for l in (ps, gs, ms, vs))
+    gnorm = torch.sqrt(sum((g * g).sum() for g in gs)).reshape(1)
+    full = lambda val, dt=torch.float32: torch.full((n,), val, dtype=dt)  # noqa: E731
+    dl.multi_tensor_lamb_compute_update_term(65536, noop, [gs, ps, ms, vs, us], full(0.9), full(0.999), full(0.1), full(1, torch.int32),
+                                             torch.tensor([1], dtype=torch.int32), full(1e-6), 1, full(0.01), one, gnorm, 1.0)
+    pn = torch.stack([t.norm() for t in ps])
+    un = torch.stack([t.norm() for t in us])
+    copies = [torch.zeros_like(t, dtype=torch.bfloat16) for t in ps]
+    dl.multi_tensor_lamb_update_weights(65536, noop, [us, ps, copies], pn, un, torch.arange(n), torch.tensor([1e-2]), full(0.01), gnorm, False)
+    oracle.multi_tensor_lamb([g_ref, p_ref, m_ref, v_ref], 1e-2, 0.9, 0.999, 1e-6, 1, 1, 0.01, 1, 1, gnorm, 1.0, False)
+    for a, b_ in zip(ps, p_ref):
+        torch.testing.assert_close(a, b_, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(copies[0].float(), ps[0], rtol=1e-2, atol=1e-2)
