@@ -12,11 +12,10 @@
 //           O += P V_j accumulated in TMEM with no rescale; epilogue: O / l -> global, log-sum-exp optional.
 // The extra cost is one more QK^T per tile (tensor time is not the bottleneck of attention at d <= 128; exponentials are, and those
 // are computed once).
-#include "../gemm_common.cuh"
+#include "fmha_common.cuh"
 
 namespace ab {
 namespace fmha {
-using namespace ab::gemm;
 
 constexpr int TQ = 128;   // query rows per CTA
 constexpr int TK = 128;   // keys per tile
@@ -30,23 +29,6 @@ struct Params {
   void* out; long long out_row_stride, out_head_stride;  // elements
   float* lse;                                            // [batch? packed rows][heads] or null
 };
-
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2: the softmax is exponential-bound, libdevice exp2f adds range fix-ups
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// byte offset of element (row r, col c) inside a [128 rows x 64 cols] 16-bit block in the SWIZZLE_128B K-major layout
-__device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
-  const int chunk = (c >> 3) ^ (r & 7);
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + chunk * 16 + (c & 7) * 2);
-}
 
 template <int D>
 struct Smem {
@@ -111,7 +93,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   if (warp == 0) {
     // ================================================= TMA producer
-    if (lane == 0) {
+    if (lane == 0 && n_kv > 0) {  // nothing may be in flight towards this CTA's shared memory when it exits
       mbar_expect_tx(q_full, S::kQ);
       for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kQOff + i * (TQ * 128), &map_q, q_full, i * 64, head, q_row0 + qt * TQ);
       int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0;
@@ -135,7 +117,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t idesc_s = make_idesc(p.is_bf16, 0, 0, TQ, TK);   // S = Q K^T : both operands K-major (d contiguous)
     const uint32_t idesc_o = make_idesc(p.is_bf16, 0, 1, TQ, D);    // O = P V   : P K-major (keys contiguous), V MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(smem + S::kQOff), p_addr = smem_u32(smem + S::kPOff);
-    mbar_wait(q_full, 0, 110);
+    if (n_kv > 0) mbar_wait(q_full, 0, 110);
     int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0; int sb = 0; uint32_t sph = 0; uint32_t pph = 0;
     auto issue_s = [&]() {  // S[sb] = Q K[ks]^T
       mbar_wait(&k_full[ks], kph, 111);
@@ -264,27 +246,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// 3-D view [rows][heads][d] of a 16-bit tensor: strides in elements; box = {64 d, 1 head, 128 rows}
-static int make_map3(CUtensorMap* m, const void* ptr, int is_bf16, long long rows, int heads, int d, long long row_stride, long long head_stride) {
-  void* f = nullptr;
-  cudaDriverEntryPointQueryResult st;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return -1001;
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
-  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)heads, (cuuint64_t)rows};
-  cuuint64_t strides[2] = {(cuuint64_t)head_stride * 2, (cuuint64_t)row_stride * 2};
-  cuuint32_t box[3] = {64, 1, 128};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(f)(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-                                                 const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -(2000 + (int)r);
-}
-
 }  // namespace fmha
 }  // namespace ab
 
@@ -300,7 +261,7 @@ AB_API int ab_fmha_fwd(const void* q, const void* k, const void* v, void* out, f
                        cudaStream_t st) {
   if (batch <= 0 || heads <= 0 || rows_q <= 0) return 0;
   if ((d != 64 && d != 128) || (dt != kBF16 && dt != kF16)) return -10;
-  if ((q_row_stride | q_head_stride | k_row_stride | k_head_stride | v_row_stride | v_head_stride) % 8) return -10;
+  if ((q_row_stride | q_head_stride | k_row_stride | k_head_stride | v_row_stride | v_head_stride | out_row_stride | out_head_stride) % 8) return -10;
   const int is_bf16 = dt == kBF16;
   CUtensorMap mq, mk, mv;
   int rc;

@@ -39,3 +39,43 @@ def test_fmha_fwd_varlen(cuda_dev):
         q, k, v = (qkv[s:s + n, j].transpose(0, 1).float() for j in range(3))
         ref = torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, -1) @ v
         torch.testing.assert_close(out[s:s + n].transpose(0, 1).float(), ref, atol=2e-2, rtol=2e-2)
+
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("seq", [128, 200, 333])
+def test_fmha_bwd_fixed_length(cuda_dev, d, causal, seq):
+    X = _fmha()
+    torch.manual_seed(0)
+    b, h = 2, 3
+    qkv = torch.randn(b * seq, 3, h, d, device=cuda_dev, dtype=torch.bfloat16, requires_grad=True)
+    out = X.FmhaFunc.apply(qkv[:, 0], qkv[:, 1], qkv[:, 2], None, None, None, None, b, causal, None)
+    dout = torch.randn_like(out)
+    (grad,) = torch.autograd.grad(out, qkv, dout)
+    ref_in = qkv.detach().float().requires_grad_()
+    q, k, v = (ref_in[:, i].view(b, seq, h, d).transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(b * seq, h, d)
+    (ref_grad,) = torch.autograd.grad(ref, ref_in, dout.float())
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(grad.float(), ref_grad, atol=5e-2, rtol=5e-2)
+
+
+def test_fmha_bwd_varlen(cuda_dev):
+    X = _fmha()
+    torch.manual_seed(0)
+    h, d = 2, 64
+    lens = [5, 130, 1, 300]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    qkv = torch.randn(sum(lens), 3, h, d, device=cuda_dev, dtype=torch.float16, requires_grad=True)
+    out = X.FmhaFunc.apply(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu, cu, max(lens), max(lens), None, False, None)
+    dout = torch.randn_like(out)
+    (grad,) = torch.autograd.grad(out, qkv, dout)
+    ref_in = qkv.detach().float().requires_grad_()
+    outs = []
+    for i, n in enumerate(lens):
+        s = int(cu[i])
+        q, k, v = (ref_in[s:s + n, j].transpose(0, 1) for j in range(3))
+        outs.append((torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, -1) @ v).transpose(0, 1))
+    (ref_grad,) = torch.autograd.grad(torch.cat(outs), ref_in, dout.float())
+    torch.testing.assert_close(grad.float(), ref_grad, atol=5e-2, rtol=5e-2)
