@@ -11,10 +11,27 @@ import torch
 import torch.nn.functional as F
 
 
+def _use_kernel(qkv: torch.Tensor, d: int, dropout: float) -> bool:
+    """Opt-in (APEX_B200_FMHA_KERNEL=1) route through the experimental tcgen05 kernels: fp16 / bf16, head dim 64 or 128, no dropout."""
+    from ...utils import config
+
+    if not (config.fmha_kernel() and qkv.is_cuda and qkv.dtype in (torch.float16, torch.bfloat16) and d in (64, 128) and dropout == 0.0):
+        return False
+    from . import experimental as X
+
+    return X.available()
+
+
 def fmha_varlen(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_s: int, p_dropout: float = 0.0, is_training: bool = True,
                 causal: bool = False) -> torch.Tensor:
     """qkv [total, 3, h, d] packed over sequences delimited by cu_seqlens [b+1] -> context [total, h, d]."""
     total, three, h, d = qkv.shape
+    if _use_kernel(qkv, d, p_dropout if is_training else 0.0):
+        from . import experimental as X
+
+        cu = cu_seqlens if cu_seqlens.dtype == torch.int32 else cu_seqlens.to(torch.int32)
+        ms = int(max_s) if max_s else int((cu[1:] - cu[:-1]).max())
+        return X.FmhaFunc.apply(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu, cu, ms, ms, None, causal, None)
     b = cu_seqlens.numel() - 1
     lens = (cu_seqlens[1:] - cu_seqlens[:-1]).long()
     max_s = int(max_s) if max_s else int(lens.max())
