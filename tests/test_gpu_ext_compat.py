@@ -125,3 +125,20 @@ def test_distopt_adam_entry_points(cuda_dev, ext):
         da.multi_tensor_fused_adam_capturable(65536, noop, [[pc], [mc], [vc], [gr.clone()], [pc]], one, lr_t, 0.9, 0.99, 1e-8, step_t, 1, 1, 0.1)
     torch.testing.assert_close(p, pr.detach(), atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(pc, pr.detach(), atol=1e-5, rtol=1e-5)
+
+
+def test_fused_adam_large_tensor_64bit_offsets(cuda_dev):
+    """> 2^31 elements in ONE tensor (reference tests/L0/run_optimizers/test_adam.py testLargeTensor): element offsets must be 64-bit."""
+    from apex_b200.optimizers import FusedAdam
+
+    n = (1 << 31) + 4096 + 3
+    p = torch.nn.Parameter(torch.zeros(n, device=cuda_dev, dtype=torch.bfloat16))
+    p.grad = torch.zeros(n, device=cuda_dev, dtype=torch.bfloat16)
+    probe = torch.tensor([0, 12345, (1 << 31) - 1, 1 << 31, n - 1], device=cuda_dev)
+    p.grad[probe] = torch.tensor([1.0, -2.0, 3.0, -4.0, 5.0], device=cuda_dev, dtype=torch.bfloat16)
+    opt = FusedAdam([p], lr=0.5, weight_decay=0.0)
+    opt.step()
+    torch.cuda.synchronize()
+    got = p.detach()[probe].float()
+    torch.testing.assert_close(got, torch.tensor([-0.5, 0.5, -0.5, 0.5, -0.5], device=cuda_dev), atol=1e-2, rtol=1e-2)  # first step: -lr * sign(g)
+    assert float(p.detach()[(1 << 31) + 1]) == 0.0
