@@ -9,7 +9,6 @@ pure-PyTorch reference implementations in ``apex_b200.ops.reference`` are used (
 from __future__ import annotations
 
 import ctypes
-import os
 import threading
 from pathlib import Path
 

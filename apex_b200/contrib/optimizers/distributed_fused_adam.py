@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
-import math
 from typing import Iterable, Optional
 
 import torch

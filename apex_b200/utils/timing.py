@@ -5,7 +5,6 @@ import json
 import statistics
 import subprocess
 import threading
-import time
 from pathlib import Path
 
 import torch
