@@ -28,8 +28,35 @@ def deprecated_warning(msg: str) -> None:
         warnings.warn(msg, DeprecatedFeatureWarning, stacklevel=2)
 
 
+class _ApexAliasFinder:
+    """Meta-path finder that resolves ``apex.<anything>`` to the SAME module object as ``apex_b200.<anything>`` — without it a deep import
+    such as ``apex.contrib.xentropy.softmax_xentropy`` would execute the file a second time under the other name (two copies of every class)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib
+        import importlib.machinery
+        import sys
+
+        if not (fullname == "apex" or fullname.startswith("apex.")) or sys.modules.get("apex") is not sys.modules[__name__]:
+            return None
+        try:
+            importlib.import_module(__name__ + fullname[4:])
+        except ImportError:
+            return None
+        return importlib.machinery.ModuleSpec(fullname, self)
+
+    def create_module(self, spec):
+        import sys
+
+        return sys.modules[__name__ + spec.name[4:]]
+
+    def exec_module(self, module):  # already executed under its apex_b200 name
+        return None
+
+
 def install_as_apex() -> None:
-    """Register ``apex`` / ``amp_C`` aliases in ``sys.modules`` so ``import apex`` user code runs on this library."""
+    """Make ``import apex`` / ``import amp_C`` / ``import fused_layer_norm_cuda`` ... user code run on this library: ``apex`` and every
+    ``apex.*`` sub-module become aliases of the corresponding ``apex_b200`` module objects (no effect if the real apex is already imported)."""
     import sys
 
     from .ops import amp_C as _amp_C
@@ -37,6 +64,8 @@ def install_as_apex() -> None:
     mod = sys.modules[__name__]
     sys.modules.setdefault("apex", mod)
     sys.modules.setdefault("amp_C", _amp_C)
+    if sys.modules["apex"] is mod and not any(isinstance(f, _ApexAliasFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _ApexAliasFinder())
     for name in ("optimizers", "normalization", "multi_tensor_apply", "fused_dense", "mlp", "parallel", "transformer", "contrib", "_autocast_utils",
                  "distributed_testing"):
         try:

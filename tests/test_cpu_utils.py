@@ -1,6 +1,8 @@
 """CPU tests of the auxiliary subsystems: profiling helpers, config flags, deprecation warning, distributed test base (gloo)."""
 import warnings
 
+import pytest
+
 import torch
 
 
@@ -93,3 +95,19 @@ def test_kernel_calls_run_under_a_device_guard_when_tensors_live_elsewhere(monke
     f(1, _lib.stream_ptr(torch.device("cuda", 1)))
     f(2, _lib.stream_ptr(torch.device("cuda", 0)))
     assert events == [("enter", 1), ("call", (1, 77)), ("exit", 1), ("call", (2, 77))]
+
+
+def test_apex_alias_resolves_deep_imports_to_the_same_module_objects():
+    import importlib
+
+    import apex_b200
+
+    apex_b200.install_as_apex()
+    for name in ("contrib.xentropy.softmax_xentropy", "optimizers.fused_adam", "contrib.openfold_triton", "_lib", "transformer.functional.fused_softmax"):
+        assert importlib.import_module("apex." + name) is importlib.import_module("apex_b200." + name), name
+    from apex.contrib.openfold_triton.fused_adam_swa import FusedAdamSWA
+    from apex_b200.contrib.openfold import FusedAdamSWA as same
+
+    assert FusedAdamSWA is same
+    with pytest.raises(ImportError):
+        importlib.import_module("apex.no_such_module")
