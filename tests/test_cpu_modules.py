@@ -1,5 +1,6 @@
 """CPU paths of the module layer: every apex-compatible module must run (forward + backward) on CPU tensors and agree with the plain
 PyTorch formulation — the same oracles the GPU tests use for the kernels."""
+import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -150,6 +151,18 @@ def test_gds_file_roundtrip(tmp_path):
         f.load_data(a2)
         f.load_data(b2)
     assert torch.equal(a, a2) and torch.equal(b, b2)
+    # non-contiguous tensors, "rw" mode, reading past the end, a missing file
+    c = torch.arange(24.0).view(4, 6).t()
+    with GDSFile(path, "rw") as f:
+        f.save_data(c)
+        f._pos = 0
+        c2 = torch.empty(4, 6).t()
+        f.load_data(c2)
+        assert torch.equal(c, c2)
+    with GDSFile(path, "r") as f, pytest.raises(EOFError):
+        f.load_data(torch.empty(1 << 20))
+    with GDSFile(str(tmp_path / "missing.bin"), "r") as f, pytest.raises(OSError):
+        f.load_data(torch.empty(4))
 
 
 def test_wgrad_accumulation_and_scale_mask_softmax_module_cpu():

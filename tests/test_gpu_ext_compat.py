@@ -142,3 +142,20 @@ def test_fused_adam_large_tensor_64bit_offsets(cuda_dev):
     got = p.detach()[probe].float()
     torch.testing.assert_close(got, torch.tensor([-0.5, 0.5, -0.5, 0.5, -0.5], device=cuda_dev), atol=1e-2, rtol=1e-2)  # first step: -lr * sign(g)
     assert float(p.detach()[(1 << 31) + 1]) == 0.0
+
+
+def test_gds_file_device_roundtrip_multi_chunk(cuda_dev, tmp_path):
+    """Device tensors larger than two staging chunks (csrc/file_io.cpp: 32 MB each) exercise the double-buffered pipeline both ways."""
+    from apex_b200.contrib.gpu_direct_storage import GDSFile
+
+    a = torch.randn(25_000_001, device=cuda_dev)                     # ~100 MB, not a multiple of the chunk size
+    b = torch.randn(3, 5, device=cuda_dev, dtype=torch.bfloat16)
+    path = str(tmp_path / "blob.bin")
+    with GDSFile(path, "w") as f:
+        f.save_data(a)
+        f.save_data(b)
+    a2, b2 = torch.empty_like(a), torch.empty_like(b)
+    with GDSFile(path, "r") as f:
+        f.load_data(a2)
+        f.load_data(b2)
+    assert torch.equal(a, a2) and torch.equal(b, b2)
