@@ -1,12 +1,12 @@
-"""``torchsched`` — multi-stream scheduling backend. Reference: apex/contrib/torchsched (2.4k lines): a ``torch.compile`` backend wrapping
-Inductor that pins the critical path of the fused-node DAG to the default stream and round-robins the rest over
+"""``torchsched`` — multi-stream scheduling backend for ``torch.compile``. Reference: apex/contrib/torchsched (2.4k lines): a backend
+wrapping Inductor that pins the critical path of the fused-node DAG to the default stream and round-robins the rest over
 ``TORCH_SCHED_NUM_STREAMS`` side streams with ref-counted CUDA events, plus a pre-grad pass swapping ``F.layer_norm`` for a fused op.
 
-This library does not use a tracing compiler on its hot paths (explicit kernels, streams and CUDA graphs instead), so the backend here
-is the eager-mode analogue: :class:`StreamScheduler` runs independent callables of one step on a fixed pool of side streams with
-event-based joins (what the reference's generated wrapper code does), :func:`capture_graph` turns a launch-bound step into a CUDA
-graph, and ``torch.compile(backend="torchsched")`` is registered as Inductor + the layer-norm replacement pass so reference call
-sites keep working."""
+This library does not generate code (explicit kernels, streams and CUDA graphs instead), so ``torch.compile(m, backend="torchsched")``
+here applies the same scheduling POLICY to the graph dynamo captures and interprets it: every node is an eager call placed on its
+planned stream, with events on the cross-stream edges (:mod:`.scheduler`); ``F.layer_norm`` nodes are rewritten to this library's
+fused kernel first. Also exported: :class:`StreamScheduler` (the same fork / join pattern for hand-written step functions) and
+:func:`capture_graph` (turn a launch-bound step into a CUDA graph). ``get_backend("inductor")`` still names the stock backend."""
 from __future__ import annotations
 
 import os
@@ -15,6 +15,7 @@ from contextlib import contextmanager
 import torch
 
 from . import config  # noqa: F401
+from .scheduler import Plan, ScheduledGraph, plan_graph  # noqa: F401
 
 
 class StreamScheduler:
@@ -59,10 +60,44 @@ def capture_graph(fn, *static_args, warmup: int = 3):
     return g.replay, out
 
 
-def _backend(gm, example_inputs, **kwargs):
-    from torch._inductor.compile_fx import compile_fx
+def fused_layer_norm_op(input, normalized_shape, weight=None, bias=None, eps=1e-5):
+    """Drop-in for ``F.layer_norm`` (reference torchsched/ops/layer_norm.py): the fused kernel for CUDA fp32 / fp16 / bf16 inputs."""
+    if input.is_cuda and input.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        from ...normalization import fused_layer_norm as N
 
-    return compile_fx(gm, example_inputs)
+        if weight is not None and bias is not None:
+            return N.fused_layer_norm_affine(input, weight, bias, tuple(normalized_shape), eps)
+        if weight is None and bias is None:
+            return N.fused_layer_norm(input, tuple(normalized_shape), eps)
+    return torch.nn.functional.layer_norm(input, normalized_shape, weight, bias, eps)
+
+
+def replace_layer_norm(gm):
+    """Pre-grad pass (reference torchsched/passes/pre_grad_passes.py): ``F.layer_norm`` / ``nn.LayerNorm`` nodes -> the fused op."""
+    changed = False
+    for node in gm.graph.nodes:
+        if node.op == "call_function" and node.target is torch.nn.functional.layer_norm:
+            node.target = fused_layer_norm_op
+            changed = True
+        elif node.op == "call_module" and isinstance(gm.get_submodule(node.target), torch.nn.LayerNorm):
+            ln = gm.get_submodule(node.target)
+            with gm.graph.inserting_before(node):
+                w = gm.graph.get_attr(node.target + ".weight") if ln.elementwise_affine else None
+                b = gm.graph.get_attr(node.target + ".bias") if ln.elementwise_affine and ln.bias is not None else None
+                new = gm.graph.call_function(fused_layer_norm_op, (node.args[0], tuple(ln.normalized_shape), w, b, ln.eps))
+            new.meta = dict(node.meta)
+            node.replace_all_uses_with(new)
+            gm.graph.erase_node(node)
+            changed = True
+    if changed:
+        gm.graph.lint()
+        gm.recompile()
+    return gm
+
+
+def _backend(gm, example_inputs, **kwargs):
+    gm = replace_layer_norm(gm)
+    return ScheduledGraph(gm, num_streams=kwargs.get("num_streams"), cuda_graph=bool(kwargs.get("cuda_graph", False)))
 
 
 def torchsched(gm, example_inputs, **kwargs):
@@ -96,4 +131,5 @@ try:  # register so torch.compile(backend="torchsched") resolves
 except Exception:  # noqa: BLE001
     pass
 
-__all__ = ["StreamScheduler", "capture_graph", "set_default_backend", "config", "torchsched", "torchsched_compile", "get_backend", "list_backends"]
+__all__ = ["StreamScheduler", "capture_graph", "set_default_backend", "config", "torchsched", "torchsched_compile", "get_backend", "list_backends",
+           "ScheduledGraph", "Plan", "plan_graph", "replace_layer_norm", "fused_layer_norm_op"]

@@ -159,3 +159,42 @@ def test_gds_file_device_roundtrip_multi_chunk(cuda_dev, tmp_path):
         f.load_data(a2)
         f.load_data(b2)
     assert torch.equal(a, a2) and torch.equal(b, b2)
+
+
+def test_torchsched_multi_stream_and_cuda_graph(cuda_dev):
+    import torch.nn as nn
+
+    from apex_b200.contrib import torchsched as ts
+
+    class Branchy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c, self.d = nn.Linear(1024, 4096), nn.Linear(4096, 1024), nn.Linear(1024, 64), nn.Linear(1024, 64)
+            self.ln = nn.LayerNorm(1024)
+
+        def forward(self, x):
+            h = self.b(F.gelu(self.a(x)))
+            return self.ln(h + x).sum(-1, keepdim=True) + self.c(x).relu() + torch.tanh(self.d(x))
+
+    torch.manual_seed(0)
+    m = Branchy().to(cuda_dev)
+    x = torch.randn(512, 1024, device=cuda_dev, requires_grad=True)
+    graphs = []
+
+    def backend(gm, example_inputs, **kw):
+        graphs.append(ts._backend(gm, example_inputs, **kw))
+        return graphs[-1]
+
+    cm = torch.compile(m, backend=backend)
+    for _ in range(3):
+        out, ref = cm(x), m(x)
+        (g,) = torch.autograd.grad(out.sum(), x)
+        (g_ref,) = torch.autograd.grad(ref.sum(), x)
+        torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
+        torch.testing.assert_close(g, g_ref, atol=2e-3, rtol=2e-3)
+    assert graphs[0].plan.streams_used == 2
+    with torch.no_grad():
+        cg = torch.compile(m, backend=lambda gm, ex: ts._backend(gm, ex, cuda_graph=True))
+        for _ in range(3):
+            xi = torch.randn(512, 1024, device=cuda_dev)
+            torch.testing.assert_close(cg(xi), m(xi), atol=2e-3, rtol=2e-3)
