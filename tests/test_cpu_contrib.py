@@ -207,3 +207,36 @@ def test_fused_adam_cuda_entry_points_reversible_step_and_checks():
     assert flag.item() == 1
     F.strided_check_finite(flag, x, 3, 1)
     assert flag.item() == 0
+
+
+def test_sparse_masks_property():
+    """2:4 masks for random shapes: 1-D pattern keeps exactly the two largest magnitudes of every group of four along the input dimension;
+    the 2-D patterns keep at most two per row AND per column of every 4x4 block; `best` (exhaustive over the 90 exact patterns) keeps exactly
+    two and is never beaten by another exact pattern — greedy may stop at a maximal mask with fewer entries, which is not comparable."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from apex_b200.contrib.sparsity import sparse_masklib as L
+
+    @settings(max_examples=25, deadline=None)
+    @given(rows=st.integers(1, 6), cols=st.integers(1, 6), seed=st.integers(0, 10_000))
+    def check(rows, cols, seed):
+        w = torch.randn(4 * rows, 4 * cols, generator=torch.Generator().manual_seed(seed))
+        m1 = L.create_mask(w, "m4n2_1d").bool()
+        g, k = w.abs().view(-1, 4), m1.view(-1, 4)
+        assert bool((k.sum(1) == 2).all())
+        kept_min = torch.where(k, g, torch.full_like(g, float("inf"))).min(1).values
+        dropped_max = torch.where(k, torch.full_like(g, -1.0), g).max(1).values
+        assert bool((kept_min >= dropped_max).all())
+        best, greedy = L.create_mask(w, "m4n2_2d_best").bool(), L.create_mask(w, "m4n2_2d_greedy").bool()
+        for m2 in (best, greedy):
+            blocks = m2.view(rows, 4, cols, 4).permute(0, 2, 1, 3)
+            assert int(blocks.sum(-1).max()) <= 2 and int(blocks.sum(-2).max()) <= 2
+        bb = best.view(rows, 4, cols, 4).permute(0, 2, 1, 3)
+        assert bool((bb.sum(-1) == 2).all()) and bool((bb.sum(-2) == 2).all())
+        gb = greedy.view(rows, 4, cols, 4).permute(0, 2, 1, 3)
+        wb = w.abs().view(rows, 4, cols, 4).permute(0, 2, 1, 3)
+        exact = (gb.sum(-1) == 2).all(-1) & (gb.sum(-2) == 2).all(-1)          # blocks where greedy happens to be an exact pattern
+        assert bool(((wb * bb).sum((-1, -2)) >= (wb * gb).sum((-1, -2)) - 1e-5)[exact].all())
+
+    check()

@@ -102,3 +102,48 @@ def test_negative_control_comparator_can_fail():
     b.step()
     with pytest.raises(AssertionError):
         torch.testing.assert_close(ps[0], qs[0], rtol=1e-5, atol=1e-6)
+
+
+def test_segment_layout_invariants_property():
+    """Shard / bucket layout of the ZeRO flat space, for random parameter sets, world sizes and bucket caps: every parameter element is
+    owned by exactly one rank, fragments never overlap inside a rank's shard arrays, parameters start on 64-element boundaries, buckets
+    split evenly into shards, and a parameter may straddle buckets (the reference's test chooses sizes to force that, test_dist_adam.py:119)."""
+    import types
+
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from apex_b200.contrib.optimizers import distributed_fused_adam as M
+
+    @settings(max_examples=40, deadline=None)
+    @given(sizes=st.lists(st.integers(1, 9000), min_size=1, max_size=7), world=st.sampled_from([1, 2, 3, 4, 8]),
+           cap_kb=st.sampled_from([1, 16, 64, 100000]))
+    def check(sizes, world, cap_kb):
+        params = [torch.nn.Parameter(torch.arange(n, dtype=torch.float32) + 1000 * i) for i, n in enumerate(sizes)]
+        owned = [torch.zeros(n, dtype=torch.int32) for n in sizes]
+        for rank in range(world):
+            opt = types.SimpleNamespace(distributed_size=world, distributed_rank=rank, bucket_cap_mb=cap_kb / 1024.0, device=torch.device("cpu"),
+                                        _fused_ok=lambda *a: False, store_params=True, store_param_remainders=False, with_scaled_states=False,
+                                        distributed_process_group=None, _param_view={}, _grad_view={}, _init_values={})
+            seg = M._Segment(opt, 0, [torch.nn.Parameter(p.detach().clone()) for p in params], torch.float32, torch.float32, torch.float32)
+            assert seg.bucket_elems % (world * M._CHUNK) == 0 and seg.shard_elems * world == seg.bucket_elems
+            assert seg.padded == seg.n_buckets * seg.bucket_elems >= seg.numel and all(o % M._ALIGN == 0 for o in seg.offsets)
+            used = torch.zeros(seg.local_elems, dtype=torch.int32)
+            per_param = {}
+            for pi, s0, n in seg.fragments():
+                assert n > 0 and 0 <= s0 and s0 + n <= seg.local_elems
+                used[s0:s0 + n] += 1
+                per_param.setdefault(pi, []).append((s0, n))
+                # the master shard was initialised from the parameter: the fragment's values identify which elements it holds
+                vals = seg.master[s0:s0 + n]
+                idx = (vals - 1000 * pi).long()
+                assert torch.equal(vals, params[pi].detach()[idx]) and torch.equal(idx, torch.arange(int(idx[0]), int(idx[0]) + n))
+                owned[pi][idx] += 1
+            assert int(used.max()) <= 1
+            seen_straddle[0] |= any(len(v) > 1 for v in per_param.values())
+        for o in owned:
+            assert bool((o == 1).all())
+
+    seen_straddle = [False]
+    check()
+    assert seen_straddle[0], "no generated case had a parameter straddling two shards / buckets"
