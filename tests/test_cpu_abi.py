@@ -49,3 +49,25 @@ def test_every_declared_signature_matches_its_c_prototype():
         elif protos[name] != spec:
             problems.append(f"{name} ({where}): python {' '.join(spec)}  !=  C {' '.join(protos[name])}")
     assert not problems, "\n".join(problems)
+
+
+def test_built_library_exports_every_declared_symbol():
+    """A stale in-tree ``_kernels.so`` (sources changed, library not rebuilt) would only fail on the GPU box: catch it here. Symbols that
+    live in csrc/experimental are only required when the library was built with APEX_B200_EXPERIMENTAL=1."""
+    import ctypes
+
+    import pytest
+
+    so = os.path.join(ROOT, "apex_b200", "_kernels.so")
+    if not os.path.exists(so):
+        pytest.skip("library not built")
+    lib = ctypes.CDLL(so)
+    experimental = set()
+    for f in glob.glob(os.path.join(ROOT, "apex_b200/csrc/experimental/*.cu")):
+        experimental.update(re.findall(r"AB_API\s+[\w\s\*]+?\s+(\w+)\s*\(", open(f).read()))
+    names = set(_declarations())
+    for f in glob.glob(os.path.join(ROOT, "apex_b200/**/*.py"), recursive=True):
+        names.update(re.findall(r'raw_fn\(\s*"(\w+)"', open(f).read()))
+    has_experimental = any(hasattr(lib, n) for n in experimental)
+    missing = [n for n in sorted(names) if not hasattr(lib, n) and (has_experimental or n not in experimental)]
+    assert not missing, f"rebuild the library (python -m apex_b200._build): {missing}"
