@@ -36,11 +36,28 @@ def fast_mask_softmax_dropout_func(is_training, heads, inputs, pad_mask, mask_ad
     return p.view(bh, sq, sk)
 
 
+def _attention_kernel(q, k, v, heads, scaling):
+    """Opt-in (APEX_B200_FMHA_KERNEL=1) route through the experimental tcgen05 attention kernels for the mask-free, dropout-free case:
+    [t, b, e] -> batch-major [b * t, heads, hd] rows (the layout the kernels' 3-D TMA maps address), and back."""
+    from ..fmha import experimental as X
+
+    tq, b, e = q.shape
+    tk, hd = k.shape[0], e // heads
+    rows = [t.transpose(0, 1).reshape(b * n, heads, hd) for t, n in ((q, tq), (k, tk), (v, tk))]
+    out = X.FmhaFunc.apply(rows[0], rows[1], rows[2], None, None, None, None, b, False, float(scaling))
+    return out.view(b, tq, e).transpose(0, 1).contiguous()
+
+
 def _attention(q, k, v, heads, scaling, key_padding_mask, attn_mask, mask_additive, dropout, training):
     """q [tq, b, e]; k, v [tk, b, e] -> [tq, b, e]"""
     tq, b, e = q.shape
     tk = k.shape[0]
     hd = e // heads
+    if key_padding_mask is None and attn_mask is None:
+        from ..fmha.fmha import _use_kernel
+
+        if _use_kernel(q, hd, dropout if training else 0.0):
+            return _attention_kernel(q, k, v, heads, scaling)
     q = q.contiguous().view(tq, b * heads, hd).transpose(0, 1)
     k = k.contiguous().view(tk, b * heads, hd).transpose(0, 1)
     v = v.contiguous().view(tk, b * heads, hd).transpose(0, 1)

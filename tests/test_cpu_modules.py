@@ -293,3 +293,46 @@ def test_extension_name_modules_dense_and_distopt():
     for a, b_ in zip(ps, p_ref):
         torch.testing.assert_close(a, b_, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(copies[0].float(), ps[0], rtol=1e-2, atol=1e-2)
+
+
+def test_attention_modules_route_through_the_kernel_entry_point_when_opted_in(monkeypatch):
+    """APEX_B200_FMHA_KERNEL=1 plumbing of contrib.fmha / contrib.multihead_attn, with the (GPU-only) kernel call replaced by an SDPA
+    stand-in that honours the same [rows, heads, d] / cu_seqlens contract: layouts, scaling and the batch-major row order must agree."""
+    from apex_b200.contrib.fmha import experimental as X
+    from apex_b200.contrib.fmha import fmha as fm
+    from apex_b200.contrib.multihead_attn import SelfMultiheadAttn
+
+    calls = []
+
+    def stand_in(q, k, v, cu_q, cu_k, max_q, max_k, batch, causal, scale):
+        calls.append((tuple(q.shape), batch, causal))
+        rows, h, d = q.shape
+        scale = d ** -0.5 if scale is None else scale
+        if cu_q is None:
+            bounds = [(i * (rows // batch), (i + 1) * (rows // batch), i * (k.shape[0] // batch), (i + 1) * (k.shape[0] // batch)) for i in range(batch)]
+        else:
+            bounds = [(int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])) for i in range(cu_q.numel() - 1)]
+        out = torch.empty_like(q)
+        for a, b_, c, e in bounds:
+            qq, kk, vv = q[a:b_].transpose(0, 1), k[c:e].transpose(0, 1), v[c:e].transpose(0, 1)
+            out[a:b_] = F.scaled_dot_product_attention(qq, kk, vv, is_causal=causal, scale=scale).transpose(0, 1)
+        return out
+
+    monkeypatch.setenv("APEX_B200_FMHA_KERNEL", "1")
+    monkeypatch.setattr(X, "available", lambda: True)
+    monkeypatch.setattr(X.FmhaFunc, "apply", staticmethod(stand_in))
+    monkeypatch.setattr(fm, "_use_kernel", lambda t, d, dropout: d in (64, 128) and dropout == 0.0)   # the real gate also demands CUDA fp16/bf16
+    torch.manual_seed(0)
+    lens = [5, 17, 9]
+    cu = torch.tensor([0, 5, 22, 31], dtype=torch.int32)
+    qkv = torch.randn(31, 3, 2, 64)
+    got = fm.fmha_varlen(qkv, cu, max(lens), 0.0, False)
+    monkeypatch.setattr(fm, "_use_kernel", lambda *a: False)
+    torch.testing.assert_close(got, fm.fmha_varlen(qkv, cu, max(lens), 0.0, False), rtol=1e-4, atol=1e-5)
+    mha = SelfMultiheadAttn(128, 2, dropout=0.0, bias=True, impl="fast").eval()
+    x = torch.randn(7, 3, 128)
+    ref, _ = mha(x, is_training=False)
+    monkeypatch.setattr(fm, "_use_kernel", lambda t, d, dropout: d in (64, 128) and dropout == 0.0)
+    out, _ = mha(x, is_training=False)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
+    assert calls[0] == ((31, 2, 64), None, False) and calls[-1] == ((21, 2, 64), 3, False)
