@@ -177,6 +177,23 @@ def peer_halo_exchange_matches_allgather(rank, world, device_type):
                     torch.testing.assert_close(y, want, rtol=0, atol=0)
 
 
+def nvls_allreduce_matches_nccl(rank, world, device_type):
+    """EXPERIMENTAL one-shot NVSwitch all-reduce (csrc/experimental/nvls_allreduce.cu) against NCCL: fp32 / bf16 / fp16, sizes that are and
+    are not multiples of the per-rank vector unit, a post-scale, repeated calls on the same staging buffer, and through DDP."""
+    from apex_b200.parallel.nvls_allreduce import NvlsAllReduce
+    dev = torch.device("cuda", rank)
+    ar = NvlsAllReduce(dist.group.WORLD, dev, 64 << 20)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2), (torch.float16, 2e-3)):
+        for n in (8, 1000, 1 << 20, (1 << 22) + 13):
+            for it in range(2):
+                torch.manual_seed(100 * it + rank)
+                x = torch.randn(n, device=dev).to(dtype)
+                want = x.float().clone()
+                dist.all_reduce(want)
+                got = ar.allreduce_(x.clone(), scale=0.5 if it else 1.0)
+                torch.testing.assert_close(got.float(), want * (0.5 if it else 1.0), rtol=tol, atol=tol * world)
+
+
 from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
 
 

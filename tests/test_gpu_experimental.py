@@ -79,3 +79,18 @@ def test_fmha_bwd_varlen(cuda_dev):
         outs.append((torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, -1) @ v).transpose(0, 1))
     (ref_grad,) = torch.autograd.grad(torch.cat(outs), ref_in, dout.float())
     torch.testing.assert_close(grad.float(), ref_grad, atol=5e-2, rtol=5e-2)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_nvls_allreduce(cuda_dev, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from apex_b200.parallel import nvls_allreduce as N
+    from apex_b200 import _lib
+    try:
+        _lib.fn("ab_nvls_allreduce")
+    except (AttributeError, KeyError, RuntimeError):
+        pytest.skip("experimental kernels are not in this build (APEX_B200_EXPERIMENTAL=1 python -m apex_b200._build)")
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.nvls_allreduce_matches_nccl, world, "cuda", backend="nccl")
