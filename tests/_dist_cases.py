@@ -194,6 +194,43 @@ def nvls_allreduce_matches_nccl(rank, world, device_type):
                 torch.testing.assert_close(got.float(), want * (0.5 if it else 1.0), rtol=tol, atol=tol * world)
 
 
+def syncbn_generic_matches_concatenated_batchnorm(rank, world, device_type, uneven, fuse_relu):
+    """The torch.distributed implementation of SyncBatchNorm (multi-node groups, CPU / gloo): statistics over uneven per-rank batches,
+    gradients, running statistics and the fused residual-add + ReLU variant against BatchNorm over the concatenated batch."""
+    from apex_b200.parallel import SyncBatchNorm
+    torch.manual_seed(0)
+    C = 6
+    nb = [4, 7, 2, 5][:world] if uneven else [5] * world
+    full = torch.randn(sum(nb), C, 5, 3) * 1.5 + 0.7
+    res_full = torch.randn(sum(nb), C, 5, 3)
+    dy_full = torch.randn(sum(nb), C, 5, 3)
+    lo = sum(nb[:rank])
+    sl = slice(lo, lo + nb[rank])
+    x = full[sl].clone().requires_grad_(True)
+    z = res_full[sl].clone().requires_grad_(True) if fuse_relu else None
+    sbn = SyncBatchNorm(C, fuse_relu=fuse_relu)
+    bn = torch.nn.BatchNorm2d(C)
+    xr, zr = full.clone().requires_grad_(True), res_full.clone().requires_grad_(True)
+    for _ in range(2):
+        x.grad = None
+        y = sbn(x, z) if fuse_relu else sbn(x)
+        y.backward(dy_full[sl])
+        xr.grad = None
+        yr = torch.relu(bn(xr) + zr) if fuse_relu else bn(xr)
+        yr.backward(dy_full)
+    torch.testing.assert_close(y, yr[sl], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(x.grad, xr.grad[sl], atol=1e-5, rtol=1e-4)
+    if fuse_relu:
+        torch.testing.assert_close(z.grad, zr.grad[sl], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(sbn.running_mean, bn.running_mean, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(sbn.running_var, bn.running_var, atol=1e-5, rtol=1e-4)
+    gw, gb = sbn.weight.grad.clone(), sbn.bias.grad.clone()
+    dist.all_reduce(gw)
+    dist.all_reduce(gb)
+    torch.testing.assert_close(gw, bn.weight.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(gb, bn.bias.grad, atol=1e-4, rtol=1e-4)
+
+
 from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
 
 
