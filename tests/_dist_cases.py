@@ -231,6 +231,35 @@ def syncbn_generic_matches_concatenated_batchnorm(rank, world, device_type, unev
     torch.testing.assert_close(gb, bn.bias.grad, atol=1e-4, rtol=1e-4)
 
 
+def halo_exchangers_match_slices_of_the_full_tensor(rank, world, device_type):
+    """AllGather and SendRecv halo exchangers (+ HaloPadder) on an H-split tensor: every rank must receive exactly the rows its neighbours
+    own next to the cut; the outer edges of the first / last rank are zero (reference test_peer_halo_exchange_module.py:284-335 checks the
+    same property for the peer-memory exchanger)."""
+    from apex_b200.contrib.bottleneck.halo_exchangers import HaloExchangerAllGather, HaloExchangerSendRecv, HaloPadder
+    torch.manual_seed(0)
+    N, C, Hs, W, hh = 2, 3, 6, 5, 2
+    full = torch.randn(N, C, Hs * world, W)
+    mine = full[:, :, rank * Hs:(rank + 1) * Hs].contiguous()
+    want = torch.zeros(N, C, Hs + 2 * hh, W)
+    want[:, :, hh:hh + Hs] = mine
+    if rank > 0:
+        want[:, :, :hh] = full[:, :, rank * Hs - hh:rank * Hs]
+    if rank < world - 1:
+        want[:, :, hh + Hs:] = full[:, :, (rank + 1) * Hs:(rank + 1) * Hs + hh]
+    ranks = list(range(world))
+    for ex in (HaloExchangerAllGather(ranks, rank, dist.group.WORLD), HaloExchangerSendRecv(ranks, rank)):
+        for explicit_nhwc in (False, True):
+            y = mine.permute(0, 2, 3, 1).contiguous() if explicit_nhwc else mine
+            got = HaloPadder(ex)(y, hh, explicit_nhwc, True)
+            got = got.permute(0, 3, 1, 2) if explicit_nhwc else got
+            torch.testing.assert_close(got, want, rtol=0, atol=0)
+        # the in-place form writes into caller-provided halos
+        li, ri = torch.full((N, C, hh, W), 7.0), torch.full((N, C, hh, W), 7.0)
+        ex.left_right_halo_exchange(mine[:, :, :hh].contiguous(), mine[:, :, -hh:].contiguous(), li, ri)
+        torch.testing.assert_close(li, want[:, :, :hh], rtol=0, atol=0)
+        torch.testing.assert_close(ri, want[:, :, hh + Hs:], rtol=0, atol=0)
+
+
 from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
 
 

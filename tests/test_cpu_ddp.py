@@ -22,3 +22,7 @@ def test_spatial_bottleneck_gloo():
 @pytest.mark.parametrize("uneven,fuse_relu", [(False, False), (True, True)])
 def test_syncbn_generic_path_gloo(uneven, fuse_relu):
     run_distributed(cases.syncbn_generic_matches_concatenated_batchnorm, 2, "cpu", uneven, fuse_relu, backend="gloo")
+
+
+def test_halo_exchangers_three_ranks_gloo():
+    run_distributed(cases.halo_exchangers_match_slices_of_the_full_tensor, 3, "cpu", backend="gloo")
