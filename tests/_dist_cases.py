@@ -260,6 +260,25 @@ def halo_exchangers_match_slices_of_the_full_tensor(rank, world, device_type):
         torch.testing.assert_close(ri, want[:, :, hh + Hs:], rtol=0, atol=0)
 
 
+def group_batchnorm_spans_only_its_group(rank, world, device_type):
+    """groupbn.BatchNorm2d_NHWC(bn_group=2) and cudnn_gbn.GroupBatchNorm2d(group_size=2) on four ranks: statistics must span the two ranks
+    of a group and nothing else (reference test_cudnn_gbn_with_two_gpus.py:93-169 compares against BN over the group's concatenated batch)."""
+    from apex_b200.contrib.cudnn_gbn import GroupBatchNorm2d
+    from apex_b200.contrib.groupbn import BatchNorm2d_NHWC
+    torch.manual_seed(0)
+    C, per = 5, 3
+    full = torch.randn(world * per, C, 4, 3) * (1.0 + torch.arange(world * per).view(-1, 1, 1, 1))   # every sample has its own scale
+    grp = rank // 2
+    mine = full[rank * per:(rank + 1) * per]
+    ref = torch.nn.functional.batch_norm(full[grp * 2 * per:(grp + 1) * 2 * per], None, None, training=True)[(rank % 2) * per:(rank % 2 + 1) * per]
+    nhwc = BatchNorm2d_NHWC(C, bn_group=2)
+    got = nhwc(mine.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+    gbn = GroupBatchNorm2d(C, group_size=2)
+    got = gbn(mine.contiguous(memory_format=torch.channels_last))
+    torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+
+
 from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
 
 

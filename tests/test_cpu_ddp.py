@@ -26,3 +26,7 @@ def test_syncbn_generic_path_gloo(uneven, fuse_relu):
 
 def test_halo_exchangers_three_ranks_gloo():
     run_distributed(cases.halo_exchangers_match_slices_of_the_full_tensor, 3, "cpu", backend="gloo")
+
+
+def test_group_batchnorm_four_ranks_gloo():
+    run_distributed(cases.group_batchnorm_spans_only_its_group, 4, "cpu", backend="gloo")
