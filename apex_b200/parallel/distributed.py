@@ -75,6 +75,7 @@ class DistributedDataParallel(torch.nn.Module):
         self._ready_elems = 0
         self._bucket_idx = 0
         self._disabled = False
+        self._callback_queued = False
         self.allreduce_buffers: list = []
         params = [p for p in module.parameters()]
         if dist.is_initialized() and self.world_size > 1:
@@ -90,6 +91,11 @@ class DistributedDataParallel(torch.nn.Module):
         def hook(param):
             if self._disabled or not (dist.is_initialized() and self.world_size > 1):
                 return
+            if not self._callback_queued:
+                # parameters that take no part in this backward never fire their hook: whatever is still pending when the engine
+                # finishes is reduced from an end-of-backward callback (the reference queues the same callback from its grad hooks)
+                self._callback_queued = True
+                torch.autograd.Variable._execution_engine.queue_callback(self._end_of_backward)
             self._n_seen += 1
             self._ready.append(param)
             self._ready_elems += param.numel()
@@ -102,6 +108,11 @@ class DistributedDataParallel(torch.nn.Module):
             elif trigger or last:
                 self._flush(final=last)
         return hook
+
+    def _end_of_backward(self):
+        self._callback_queued = False
+        if self._ready or self._n_seen:
+            self._flush(final=True)
 
     def _flush(self, final: bool):
         params, self._ready, self._ready_elems = self._ready, [], 0

@@ -316,6 +316,37 @@ def ddp_matches_manual_allreduce(rank, world, device_type, delay, message_size, 
             torch.testing.assert_close(p.grad, want / world, rtol=1e-5, atol=1e-6)
 
 
+def ddp_reduces_when_some_parameters_get_no_gradient(rank, world, device_type, delay):
+    """A parameter that does not take part in the backward never fires its hook; the buckets that did fill must still be all-reduced
+    (end-of-backward callback), for both the overlapped and the delayed mode, and on consecutive iterations."""
+    from apex_b200.parallel import DistributedDataParallel
+    dev = torch.device(device_type, rank) if device_type == "cuda" else torch.device("cpu")
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.used, self.unused = torch.nn.Linear(8, 8), torch.nn.Linear(8, 8)
+
+        def forward(self, x, both):
+            y = self.used(x)
+            return y + self.unused(x) if both else y
+
+    torch.manual_seed(0)
+    net = Net().to(dev)
+    ddp = DistributedDataParallel(net, delay_allreduce=delay, message_size=1 << 30)
+    for it, both in enumerate((False, True, False)):
+        net.zero_grad(set_to_none=True)
+        x = torch.full((4, 8), float(rank + 1 + it), device=dev)
+        ddp(x, both).sum().backward()
+        mean_input = sum(float(r + 1 + it) for r in range(world)) / world
+        want = torch.full((8, 8), 4.0 * mean_input, device=dev)       # d(sum)/dW = sum over the batch of x, averaged over ranks
+        torch.testing.assert_close(net.used.weight.grad, want)
+        if both:
+            torch.testing.assert_close(net.unused.weight.grad, want)
+        else:
+            assert net.unused.weight.grad is None
+
+
 def ddp_race_condition(rank, world, device_type):
     """Race detector by construction (reference tests/distributed/DDP/ddp_race_condition_test.py:27-78): two large parameters,
     message_size=1 (a bucket per parameter), several all-reduce streams, gradients with a closed form checked every iteration."""

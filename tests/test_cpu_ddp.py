@@ -30,3 +30,8 @@ def test_halo_exchangers_three_ranks_gloo():
 
 def test_group_batchnorm_four_ranks_gloo():
     run_distributed(cases.group_batchnorm_spans_only_its_group, 4, "cpu", backend="gloo")
+
+
+@pytest.mark.parametrize("delay", [False, True])
+def test_ddp_unused_parameters_gloo(delay):
+    run_distributed(cases.ddp_reduces_when_some_parameters_get_no_gradient, 2, "cpu", delay, backend="gloo")
