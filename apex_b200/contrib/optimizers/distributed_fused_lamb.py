@@ -25,6 +25,11 @@ from ...ops import reference as ref
 from .distributed_fused_adam import DistributedFusedAdam, _Segment
 
 
+def get_process_group_ranks(group):
+    """Global ranks of a process group (module-level helper of the reference file, :9-16)."""
+    return list(dist.get_process_group_ranks(group))
+
+
 class DistributedFusedLAMB(DistributedFusedAdam):
     def __init__(self, params, lr=1e-3, bias_correction=True, grad_averaging=True, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=0.0, adam_w_mode=True, use_nvlamb=False, step_supports_amp_scaling=True, overlap_reductions=True,
@@ -39,6 +44,30 @@ class DistributedFusedLAMB(DistributedFusedAdam):
         self.max_grad_norm = max_grad_norm
         self.use_nvlamb = use_nvlamb
         self._frag_cache: dict = {}
+        self._global_scale = None
+        self._is_accumulation_step = False
+        self._last_step = False
+
+    # ---- the MLPerf-BERT driver protocol of the reference (:787-791, 1222-1255): set_global_scale(loss_scale); backward();
+    # complete_reductions(); step(). Gradients accumulate in the flat buffer until step() here, so the two step flags only record state.
+    def set_global_scale(self, global_scale):
+        """Loss scale carried by the gradients (float or 1-element tensor); step() divides it out before the norm and the update."""
+        self._global_scale = global_scale
+
+    @property
+    def global_scale(self):
+        return self._global_scale
+
+    def set_is_accumulation_step(self, is_accumulation_step):
+        self._is_accumulation_step = bool(is_accumulation_step)
+
+    def set_last_step(self, last_step):
+        self._last_step = bool(last_step)
+
+    def complete_reductions(self):
+        """Finish the gradient reduction (the reference drains its reduce-scatter / all-reduce pipeline here)."""
+        self._collect_grads()
+        self.grad_sync()
 
     # (parameter ∩ this rank's shard) fragments of a segment, as index ranges of the LOCAL shard arrays -----------------------
     def _fragments(self, seg: _Segment):
@@ -58,6 +87,9 @@ class DistributedFusedLAMB(DistributedFusedAdam):
         self.init_params()
         self._collect_grads()
         self.grad_sync()
+        if self._global_scale is not None:
+            gs = self._global_scale
+            self._grad_scale *= (gs.detach().to(self.device, torch.float32).reshape([]).reciprocal() if torch.is_tensor(gs) else 1.0 / float(gs))
         # global gradient norm (already unscaled through _grad_scale)
         gnorm = self.grad_norm()
         if grad_scaler is not None:

@@ -147,3 +147,41 @@ def test_segment_layout_invariants_property():
     seen_straddle = [False]
     check()
     assert seen_straddle[0], "no generated case had a parameter straddling two shards / buckets"
+
+
+def test_dist_lamb_global_scale_protocol_single_process():
+    """set_global_scale(s) + gradients carrying the loss scale s == the unscaled run (reference driver protocol: set_global_scale,
+    backward, complete_reductions, step); an overflowed gradient skips the step."""
+    from apex_b200.contrib.optimizers import DistributedFusedLAMB
+    from apex_b200.contrib.optimizers.distributed_fused_lamb import get_process_group_ranks  # noqa: F401
+
+    def run(scale):
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(37, 5)), torch.nn.Parameter(torch.randn(64))]
+        opt = DistributedFusedLAMB(params, lr=1e-2, weight_decay=0.01, max_grad_norm=1.0, device="cpu")
+        if scale is not None:
+            opt.set_global_scale(scale)
+            assert opt.global_scale is scale
+        for it in range(3):
+            g = torch.Generator().manual_seed(it)
+            opt.zero_grad()
+            for p in params:
+                p.grad = torch.randn(p.shape, generator=g) * (float(scale) if scale is not None else 1.0)
+            opt.set_is_accumulation_step(False)
+            opt.set_last_step(it == 2)
+            opt.complete_reductions()
+            opt.step()
+        return [p.detach().clone() for p in params], opt, params
+
+    base, _, _ = run(None)
+    for scale in (128.0, torch.tensor([1024.0])):
+        got, opt, params = run(scale)
+        for a, b in zip(got, base):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    before = [p.detach().clone() for p in params]
+    opt.zero_grad()
+    for p in params:
+        p.grad = torch.full(p.shape, float("inf"))
+    opt.step()
+    for a, b in zip(params, before):
+        assert torch.equal(a.detach(), b)
