@@ -73,6 +73,18 @@ class FusedSGD(_TableOptimizer):
         for group in self.param_groups:
             group.setdefault("nesterov", False)
 
+    def get_momentums(self, params):
+        """(momentum buffers of ``params``, first_run): buffers are created on demand, and ``first_run`` is reported by the last parameter
+        examined, as in the reference (fused_sgd.py:137-152)."""
+        momentums, first_run = [], True
+        for p in params:
+            st = self.state[p]
+            first_run = "momentum_buffer" not in st
+            if first_run:
+                st["momentum_buffer"] = torch.zeros_like(p.data)
+            momentums.append(st["momentum_buffer"])
+        return momentums, first_run
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
