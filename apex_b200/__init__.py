@@ -14,6 +14,21 @@ from . import _lib  # noqa: F401
 from . import multi_tensor_apply, optimizers, normalization  # noqa: F401
 
 
+def check_cudnn_version_and_warn(global_option: str, required_cudnn_version: int) -> bool:
+    """True when cuDNN >= ``required_cudnn_version`` is usable, else warn and return False (reference apex/__init__.py:21-30)."""
+    import warnings
+
+    import torch
+
+    ok = torch.backends.cudnn.is_available()
+    version = torch.backends.cudnn.version() if ok else None
+    if not (ok and version >= required_cudnn_version):
+        warnings.warn(f"`{global_option}` depends on cuDNN {required_cudnn_version} or later, but "
+                      f"{'cuDNN is not available' if not ok else version}")
+        return False
+    return True
+
+
 class DeprecatedFeatureWarning(FutureWarning):
     pass
 

@@ -34,3 +34,26 @@ def ConvFrozenScaleBiasReLU(x, weight, scale, bias, padding, stride):
     x, weight = _prep(x, weight)
     y = F.conv2d(x, weight, None, stride, padding)
     return F.relu(y * scale.reshape(1, -1, 1, 1).to(y.dtype) + bias.reshape(1, -1, 1, 1).to(y.dtype))
+
+
+class _Named:
+    """``<Name>_.apply`` spelling of the reference (its module-level names are the ``.apply`` of autograd Functions, :99-102); autograd
+    flows through the composed ops here, so these only carry the name."""
+
+    apply = None
+
+
+class ConvBiasReLU_(_Named):
+    apply = staticmethod(ConvBiasReLU)
+
+
+class ConvBiasMaskReLU_(_Named):
+    apply = staticmethod(ConvBiasMaskReLU)
+
+
+class ConvBias_(_Named):
+    apply = staticmethod(ConvBias)
+
+
+class ConvFrozenScaleBiasReLU_(_Named):
+    apply = staticmethod(ConvFrozenScaleBiasReLU)

@@ -158,3 +158,38 @@ cuda_group_norm_v2_nhwc = cuda_group_norm_nhwc_one_pass
 def get_cc_and_sm_count(device_index: int):
     p = torch.cuda.get_device_properties(device_index)
     return (p.major, p.minor), p.multi_processor_count
+
+
+# fprop / bprop pair of the reference (its torch.library custom ops ``apex::group_norm_nhwc_fprop / _bprop``, group_norm.py:49-190): ``sums``
+# is the opaque statistics tensor handed from one to the other (here [2, N * G]: mean and 1 / std per (image, group)).
+def group_norm_nhwc_fprop(x, G, weight, bias, eps, act=None, passes=1, use_group_norm_v2=False):
+    act = act.lower() if act else ""
+    assert x.shape[1] % G == 0, "C % G != 0."
+    assert act in ("", "silu", "swish"), "Unsupported activation."
+    assert weight.numel() == x.shape[1] and bias.numel() == x.shape[1], "Unexpected parameter count."
+    N = x.shape[0]
+    sums = torch.empty(2, N * G, dtype=torch.float32, device=x.device)
+    if _native_ok(x, weight):
+        y = torch.empty_like(x)
+        _launch(False, x, None, y, weight, bias, sums[0], sums[1], None, None, G, eps, act in ("silu", "swish"))
+        return y, sums
+    xf = x.float().reshape(N, G, -1)
+    sums[0] = xf.mean(-1).reshape(-1)
+    sums[1] = torch.rsqrt(xf.var(-1, unbiased=False) + eps).reshape(-1)
+    return torch_group_norm(x, G, weight, bias, eps, act), sums
+
+
+def group_norm_nhwc_bprop(grad_output, sums, x, G, weight, bias, eps, act=None, passes=1, use_group_norm_v2=False):
+    act = act.lower() if act else ""
+    if _native_ok(x, weight):
+        dy = grad_output.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        C = x.shape[1]
+        dg = torch.empty(C, dtype=torch.float32, device=x.device)
+        db = torch.empty(C, dtype=torch.float32, device=x.device)
+        _launch(True, x, dy, dx, weight, bias, sums[0], sums[1], dg, db, G, eps, act in ("silu", "swish"))
+        return dx, dg.to(weight.dtype), db.to(bias.dtype)
+    with torch.enable_grad():
+        xr, wr, br = x.detach().requires_grad_(), weight.detach().requires_grad_(), bias.detach().requires_grad_()
+        y = torch_group_norm(xr, G, wr, br, eps, act)
+    return torch.autograd.grad(y, (xr, wr, br), grad_output)

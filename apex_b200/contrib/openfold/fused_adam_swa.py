@@ -43,6 +43,26 @@ class FusedAdamSWA(Optimizer):
         self.swa_decay_rate = swa_decay_rate
         self._tables = None
 
+    @classmethod
+    def from_optim(cls, adam_optimizer, fp32_params, bf16_params, swa_params, swa_decay_rate):
+        """Take over from a (possibly checkpoint-restored) ``torch.optim.Adam`` with one param group: hyper-parameters, moments and the
+        common step count carry over (reference fused_adam_swa.py:459-497)."""
+        assert len(adam_optimizer.param_groups) == 1
+        g = adam_optimizer.param_groups[0]
+        opt = cls(params=fp32_params, compute_params=bf16_params, swa_params=swa_params, swa_decay_rate=swa_decay_rate, lr=g["lr"],
+                  betas=g["betas"], eps=g["eps"], weight_decay=g["weight_decay"], amsgrad=g.get("amsgrad", False),
+                  adam_math_mode=AdamMathType.PyTorchAdam)
+        sd = adam_optimizer.state_dict()
+        steps = [v["step"] for v in sd["state"].values() if "step" in v]
+        if steps and not all(float(s) == float(steps[0]) for s in steps):
+            raise ValueError("FusedAdamSWA requires all parameters were updated by same steps!")
+        sd["param_groups"][0].setdefault("bias_correction", True)
+        sd["param_groups"][0]["step"] = int(float(steps[0])) if steps else 0
+        for v in sd["state"].values():      # per-parameter step counters become the one group-level counter
+            v.pop("step", None)
+        opt.load_state_dict(sd)
+        return opt
+
     @torch.no_grad()
     def step(self, closure=None, grad_clip_scale=None):
         """``grad_clip_scale`` (float or 0-dim tensor): factor applied to every gradient before the update — the caller's global-norm

@@ -111,8 +111,17 @@ def torchsched_compile(model=None, **kwargs):
     return torch.compile(model, **kwargs) if model is not None else (lambda m: torch.compile(m, **kwargs))
 
 
-def get_backend(name: str = "torchsched"):
-    return {"torchsched": torchsched, "inductor": "inductor"}[name]
+def get_backend(backend: str = "torchsched", scheme: str = "dwb"):
+    """``"torchsched"`` -> this package's backend callable; ``"torch"`` / ``"inductor"`` -> the stock Inductor backend name. ``scheme`` picks the
+    order in which the reference splits convolution backward ("dwb" / "wbd", backend.py:262-330); backward is run by the autograd engine
+    here, so it is validated and otherwise unused."""
+    if scheme not in ("dwb", "wbd"):
+        raise ValueError(f"Invalid {scheme=}, use scheme=dwb or wbd instead")
+    if backend in ("torch", "inductor"):
+        return "inductor"
+    if backend != "torchsched":
+        raise ValueError(f"Unknown compilation {backend=}")
+    return torchsched
 
 
 def list_backends():

@@ -1,1 +1,1 @@
-from .distributed_test_base import DistributedTestBase, NcclDistributedTestBase, GlooDistributedTestBase  # noqa: F401
+from .distributed_test_base import DistributedTestBase, GlooDistributedTestBase, NcclDistributedTestBase, UccDistributedTestBase  # noqa: F401

@@ -45,6 +45,18 @@ class DistributedTestBase(unittest.TestCase):
     def world_size(self, v: int) -> None:
         self._world_size = v
 
+    @property
+    def init_method(self) -> str:
+        """Rendezvous of the running process group (the harness uses a file:// store private to each test, 127.0.0.1 otherwise)."""
+        import os
+
+        return os.environ.get("APEX_B200_DIST_INIT_METHOD", "env://")
+
+    @property
+    def destroy_pg_upon_exit(self) -> bool:
+        """The reference overrides torch's default so that the group outlives the test body (:46-48); the harness tears it down itself."""
+        return False
+
 
 class NcclDistributedTestBase(DistributedTestBase):
     DISTRIBUTED_BACKEND = "nccl"
@@ -52,3 +64,9 @@ class NcclDistributedTestBase(DistributedTestBase):
 
 class GlooDistributedTestBase(DistributedTestBase):
     DISTRIBUTED_BACKEND = "gloo"
+
+
+@unittest.skipUnless(torch.distributed.is_available() and getattr(torch.distributed, "is_ucc_available", lambda: False)(),
+                     "this torch build has no UCC backend")
+class UccDistributedTestBase(DistributedTestBase):
+    DISTRIBUTED_BACKEND = "ucc"

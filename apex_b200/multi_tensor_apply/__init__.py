@@ -10,6 +10,14 @@ class MultiTensorApply:
     def __init__(self, chunk_size):
         self.chunk_size = chunk_size
 
+    def check_avail(self):
+        """Raises when CUDA tensors could not be served (reference :15-22). CPU-only machines use the PyTorch oracles, so this only
+        fails on a GPU machine whose native library did not load."""
+        import torch
+
+        if torch.cuda.is_available():
+            _lib.require()
+
     def __call__(self, op, noop_flag_buffer, tensor_lists, *args):
         return op(self.chunk_size, noop_flag_buffer, tensor_lists, *args)
 

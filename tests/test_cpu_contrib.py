@@ -240,3 +240,60 @@ def test_sparse_masks_property():
         assert bool(((wb * bb).sum((-1, -2)) >= (wb * gb).sum((-1, -2)) - 1e-5)[exact].all())
 
     check()
+
+
+def test_reference_helper_names_exist_and_agree():
+    """Small public helpers of the reference that tests / drivers import by name."""
+    import warnings
+
+    import apex_b200
+    from apex_b200.contrib.conv_bias_relu import ConvBiasReLU, ConvBiasReLU_
+    from apex_b200.contrib.group_norm.group_norm import group_norm_nhwc_bprop, group_norm_nhwc_fprop
+    from apex_b200.contrib.openfold import FusedAdamSWA
+    from apex_b200.contrib.transducer._transducer_ref import transducer_loss_reference
+    from apex_b200.multi_tensor_apply import multi_tensor_applier
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert apex_b200.check_cudnn_version_and_warn("x", 10 ** 9) is False
+    multi_tensor_applier.check_avail()
+    x, w, b = torch.randn(2, 3, 5, 5), torch.randn(4, 3, 3, 3), torch.randn(1, 4, 1, 1)
+    torch.testing.assert_close(ConvBiasReLU_.apply(x, w, b, 1, 1), ConvBiasReLU(x, w, b, 1, 1))
+    # GroupNorm fprop / bprop pair against autograd through torch's group_norm
+    xg = torch.randn(2, 8, 3, 3).contiguous(memory_format=torch.channels_last)
+    gw, gb = torch.randn(8), torch.randn(8)
+    y, sums = group_norm_nhwc_fprop(xg, 4, gw, gb, 1e-5, "silu")
+    leaves = [t.clone().requires_grad_() for t in (xg, gw, gb)]
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(leaves[0], 4, leaves[1], leaves[2], 1e-5))
+    torch.testing.assert_close(y, ref.detach())
+    dy = torch.randn_like(y)
+    for got, want in zip(group_norm_nhwc_bprop(dy, sums, xg, 4, gw, gb, 1e-5, "silu"), torch.autograd.grad(ref, leaves, dy)):
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    # transducer lattice oracle: loss == -beta[0, 0] == -(alpha[end] + blank[end])
+    B, T, U, V = 2, 4, 3, 5
+    lg = torch.randn(B, T, U, V, requires_grad=True)
+    label, f_len, y_len = torch.randint(1, V, (B, U - 1)), torch.tensor([4, 3]), torch.tensor([2, 1])
+    alpha, beta, grad, loss = transducer_loss_reference(lg, label, f_len, y_len, 0, torch.ones(B))
+    torch.testing.assert_close(loss, -beta[:, 0, 0])
+    end = torch.stack([alpha[i, f_len[i] - 1, y_len[i]] + torch.log_softmax(lg.detach()[i, f_len[i] - 1, y_len[i]], -1)[0] for i in range(B)])
+    torch.testing.assert_close(loss, -end)
+    assert grad.shape == lg.shape
+    # FusedAdamSWA.from_optim continues a torch Adam run exactly
+    fp32 = [torch.nn.Parameter(torch.randn(10))]
+    ref_p = [torch.nn.Parameter(fp32[0].detach().clone())]
+    adam, adam_ref = torch.optim.Adam(fp32, lr=1e-2), torch.optim.Adam(ref_p, lr=1e-2)
+    for it in range(4):
+        g = torch.randn(10, generator=torch.Generator().manual_seed(it))
+        if it == 2:
+            bf = [torch.nn.Parameter(fp32[0].detach().bfloat16())]
+            opt = FusedAdamSWA.from_optim(adam, fp32, bf, [torch.nn.Parameter(fp32[0].detach().clone())], 0.9)
+        if it < 2:
+            fp32[0].grad = g.clone()
+            adam.step()
+        else:
+            bf[0].grad = g.bfloat16()
+            g = bf[0].grad.float()
+            opt.step()
+        ref_p[0].grad = g.clone()
+        adam_ref.step()
+    torch.testing.assert_close(fp32[0], ref_p[0])
