@@ -5,7 +5,11 @@ softmax+dropout kernels, optional pre-LayerNorm + residual add + dropout).
 Same constructor / forward contract ([time, batch, channel] inputs, ``key_padding_mask`` or ``attn_mask``, additive or boolean masks,
 ``include_norm_add`` pre-LN residual variant, ``impl`` in {"fast", "default"}). On B200 both impls run: input/output projections on
 the tcgen05 GEMM (apex_b200.ops.gemm through fused_dense_function), pre-LN on the fused LayerNorm kernel, the score softmax on the
-scaled-masked-softmax kernel; the two batched score/context products use torch.bmm (cuBLAS, a plain library GEMM)."""
+scaled-masked-softmax kernel; the two batched score/context products use torch.bmm (cuBLAS, a plain library GEMM).
+
+Parameter layout is the reference's, so its checkpoints load unchanged: the packed ``in_proj_weight`` ([3 * embed, embed]) is interleaved per
+head — rows ordered [head][q | k | v][head_dim] — and ``in_proj_weight_kv`` likewise [head][k | v][head_dim]; ``separate_qkv_params``
+holds three ordinary [embed, embed] matrices. :func:`packed_to_blocked` converts to the [q; k; v] block order of ``torch.nn.MultiheadAttention``."""
 from __future__ import annotations
 
 import math
@@ -18,6 +22,18 @@ from torch.nn import Parameter
 from ...fused_dense import fused_dense_function
 from ...normalization import FusedLayerNorm
 from ...transformer.functional import scaled_masked_softmax, scaled_softmax
+
+
+def packed_to_blocked(t: torch.Tensor, heads: int, parts: int = 3) -> torch.Tensor:
+    """Per-head interleaved projection weight / bias ([head][part][head_dim] rows) -> block order ([part][head][head_dim])."""
+    rest = t.shape[1:]
+    return t.reshape(heads, parts, t.shape[0] // (heads * parts), *rest).transpose(0, 1).reshape(t.shape)
+
+
+def blocked_to_packed(t: torch.Tensor, heads: int, parts: int = 3) -> torch.Tensor:
+    """Inverse of :func:`packed_to_blocked` (e.g. to import ``torch.nn.MultiheadAttention.in_proj_weight``)."""
+    rest = t.shape[1:]
+    return t.reshape(parts, heads, t.shape[0] // (heads * parts), *rest).transpose(0, 1).reshape(t.shape)
 
 
 def fast_mask_softmax_dropout_func(is_training, heads, inputs, pad_mask, mask_additive, dropout_prob):
@@ -137,7 +153,12 @@ class SelfMultiheadAttn(_MHABase):
         else:
             w, bias = self.in_proj_weight, self.in_proj_bias
         qkv = fused_dense_function(x, w, bias)                          # [t, b, 3e]
-        q, k, v = qkv.chunk(3, dim=-1)
+        if self.separate_qkv_params:
+            q, k, v = qkv.chunk(3, dim=-1)
+        else:   # packed projection: the reference's per-head interleave [heads, 3, head_dim] (self_multihead_attn_func.py:58-66)
+            t, b = qkv.shape[0], qkv.shape[1]
+            qkv = qkv.view(t, b, self.num_heads, 3, self.head_dim)
+            q, k, v = (qkv[:, :, :, i, :].reshape(t, b, self.embed_dim) for i in range(3))
         ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, self.mask_additive, self.dropout, is_training)
         out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
         return self._post(out, query, is_training), None
@@ -179,7 +200,9 @@ class EncdecMultiheadAttn(_MHABase):
         x = self.lyr_nrm(query) if self.include_norm_add else query
         q = fused_dense_function(x, self.in_proj_weight_q, self.in_proj_bias_q)
         kv = fused_dense_function(key, self.in_proj_weight_kv, self.in_proj_bias_kv)
-        k, v = kv.chunk(2, dim=-1)
+        tk, b = kv.shape[0], kv.shape[1]   # per-head interleave [heads, 2, head_dim] of the reference (encdec_multihead_attn_func.py:86-91)
+        kv = kv.view(tk, b, self.num_heads, 2, self.head_dim)
+        k, v = (kv[:, :, :, i, :].reshape(tk, b, self.embed_dim) for i in range(2))
         ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, False, self.dropout, is_training)
         out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
         return self._post(out, query, is_training), None

@@ -92,14 +92,42 @@ def test_attention_conv_and_transformer_functional_cpu():
     torch.manual_seed(0)
     m = SelfMultiheadAttn(32, 4, bias=True)
     ref = nn.MultiheadAttention(32, 4, bias=True)
+    from apex_b200.contrib.multihead_attn.multihead_attn import blocked_to_packed, packed_to_blocked
     with torch.no_grad():
-        ref.in_proj_weight.copy_(m.in_proj_weight)
-        ref.in_proj_bias.copy_(m.in_proj_bias)
+        nn.init.normal_(m.in_proj_bias)
+        # the packed projection is interleaved per head ([head][q|k|v][head_dim] rows, the reference's layout); torch wants [q; k; v] blocks
+        ref.in_proj_weight.copy_(packed_to_blocked(m.in_proj_weight, 4))
+        ref.in_proj_bias.copy_(packed_to_blocked(m.in_proj_bias, 4))
         ref.out_proj.weight.copy_(m.out_proj_weight)
         ref.out_proj.bias.copy_(m.out_proj_bias)
+    assert torch.equal(blocked_to_packed(packed_to_blocked(m.in_proj_weight, 4), 4), m.in_proj_weight)
     x = torch.randn(6, 2, 32)
     torch.testing.assert_close(m(x, x, x, is_training=False)[0], ref(x, x, x, need_weights=False)[0], atol=1e-5, rtol=1e-5)
-    assert EncdecMultiheadAttn(32, 4)(x, torch.randn(5, 2, 32), is_training=False)[0].shape == (6, 2, 32)
+    # the same layout spelled out as the reference's functions do it: view the projection as [t, b * heads, 3, head_dim]
+    lin = F.linear(x, m.in_proj_weight, m.in_proj_bias).view(6, 2 * 4, 3, 8)
+    q, k, v = (lin[:, :, i, :].transpose(0, 1) for i in range(3))
+    ctx = torch.bmm(torch.softmax(torch.bmm(q, k.transpose(1, 2)) * m.scaling, -1), v).transpose(0, 1).reshape(6, 2, 32)
+    torch.testing.assert_close(m(x, is_training=False)[0], F.linear(ctx, m.out_proj_weight, m.out_proj_bias), atol=1e-5, rtol=1e-5)
+    sep = SelfMultiheadAttn(32, 4, bias=True, separate_qkv_params=True)
+    with torch.no_grad():   # separate q / k / v parameters are ordinary [embed, embed] matrices: same function as the packed module
+        for dst, src in zip((sep.q_weight, sep.k_weight, sep.v_weight), packed_to_blocked(m.in_proj_weight, 4).chunk(3)):
+            dst.copy_(src)
+        for dst, src in zip((sep.q_bias, sep.k_bias, sep.v_bias), packed_to_blocked(m.in_proj_bias, 4).chunk(3)):
+            dst.copy_(src)
+        sep.out_proj_weight.copy_(m.out_proj_weight)
+        sep.out_proj_bias.copy_(m.out_proj_bias)
+    torch.testing.assert_close(sep(x, is_training=False)[0], m(x, is_training=False)[0], atol=1e-5, rtol=1e-5)
+    enc = EncdecMultiheadAttn(32, 4, bias=True)
+    ref2 = nn.MultiheadAttention(32, 4, bias=True)
+    mem = torch.randn(5, 2, 32)
+    with torch.no_grad():
+        nn.init.normal_(enc.in_proj_bias_q)
+        nn.init.normal_(enc.in_proj_bias_kv)
+        ref2.in_proj_weight.copy_(torch.cat((enc.in_proj_weight_q, packed_to_blocked(enc.in_proj_weight_kv, 4, 2))))
+        ref2.in_proj_bias.copy_(torch.cat((enc.in_proj_bias_q, packed_to_blocked(enc.in_proj_bias_kv, 4, 2))))
+        ref2.out_proj.weight.copy_(enc.out_proj_weight)
+        ref2.out_proj.bias.copy_(enc.out_proj_bias)
+    torch.testing.assert_close(enc(x, mem, is_training=False)[0], ref2(x, mem, mem, need_weights=False)[0], atol=1e-5, rtol=1e-5)
     xi, w, b = torch.randn(2, 4, 8, 8), torch.randn(6, 4, 3, 3), torch.randn(1, 6, 1, 1)
     torch.testing.assert_close(ConvBiasReLU(xi, w, b, 1, 1), torch.relu(F.conv2d(xi, w, b.view(-1), 1, 1)))
     torch.testing.assert_close(ConvBias(xi, w, b, 1, 1), F.conv2d(xi, w, b.view(-1), 1, 1))

@@ -147,9 +147,10 @@ def test_self_multihead_attn(cuda_dev):
     E, Hh, S, B = 128, 8, 24, 3
     m = SelfMultiheadAttn(E, Hh, dropout=0.0, bias=True).to(cuda_dev)
     ref = torch.nn.MultiheadAttention(E, Hh, dropout=0.0, bias=True).to(cuda_dev)
-    with torch.no_grad():
-        ref.in_proj_weight.copy_(m.in_proj_weight if hasattr(m, "in_proj_weight") else torch.cat([m.q_weight, m.k_weight, m.v_weight]))
-        ref.in_proj_bias.copy_(m.in_proj_bias if hasattr(m, "in_proj_bias") else torch.cat([m.q_bias, m.k_bias, m.v_bias]))
+    from apex_b200.contrib.multihead_attn.multihead_attn import packed_to_blocked
+    with torch.no_grad():   # packed projection rows are [head][q|k|v][head_dim] (the reference's layout); torch wants [q; k; v] blocks
+        ref.in_proj_weight.copy_(packed_to_blocked(m.in_proj_weight, Hh))
+        ref.in_proj_bias.copy_(packed_to_blocked(m.in_proj_bias, Hh))
         ref.out_proj.weight.copy_(m.out_proj_weight)
         ref.out_proj.bias.copy_(m.out_proj_bias)
     x = torch.randn(S, B, E, device=cuda_dev)
