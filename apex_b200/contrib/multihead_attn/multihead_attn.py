@@ -21,6 +21,7 @@ from torch.nn import Parameter
 
 from ...fused_dense import fused_dense_function
 from ...normalization import FusedLayerNorm
+from ...normalization.fused_layer_norm import fused_layer_norm_affine
 from ...transformer.functional import scaled_masked_softmax, scaled_softmax
 
 
@@ -95,6 +96,33 @@ def _attention(q, k, v, heads, scaling, key_padding_mask, attn_mask, mask_additi
 
 
 class _MHABase(nn.Module):
+    def _init_norm(self, embed_dim, include_norm_add, impl):
+        """State-dict names of the reference: impl="fast" keeps the pre-LN affine as ``lyr_nrm_gamma_weights`` / ``lyr_nrm_beta_weights``,
+        impl="default" as a ``lyr_nrm`` FusedLayerNorm sub-module (self_multihead_attn.py:86-96)."""
+        self.lyr_nrm = None
+        if include_norm_add and impl == "fast":
+            self.lyr_nrm_gamma_weights = Parameter(torch.ones(embed_dim))
+            self.lyr_nrm_beta_weights = Parameter(torch.zeros(embed_dim))
+        else:
+            self.register_parameter("lyr_nrm_gamma_weights", None)
+            self.register_parameter("lyr_nrm_beta_weights", None)
+            if include_norm_add:
+                self.lyr_nrm = FusedLayerNorm(embed_dim)
+
+    def _norm(self, query):
+        if not self.include_norm_add:
+            return query
+        if self.lyr_nrm is not None:
+            return self.lyr_nrm(query)
+        return fused_layer_norm_affine(query, self.lyr_nrm_gamma_weights, self.lyr_nrm_beta_weights, (self.embed_dim,), 1e-5)
+
+    def _reset_norm(self):
+        if self.lyr_nrm_gamma_weights is not None:
+            nn.init.ones_(self.lyr_nrm_gamma_weights)
+            nn.init.zeros_(self.lyr_nrm_beta_weights)
+        elif self.lyr_nrm is not None:
+            self.lyr_nrm.reset_parameters()
+
     def _post(self, outputs, query, is_training):
         if self.include_norm_add:
             outputs = F.dropout(outputs, self.dropout, is_training) + query
@@ -130,7 +158,7 @@ class SelfMultiheadAttn(_MHABase):
         else:
             for n in (("q_bias", "k_bias", "v_bias") if separate_qkv_params else ("in_proj_bias",)) + ("out_proj_bias",):
                 self.register_parameter(n, None)
-        self.lyr_nrm = FusedLayerNorm(embed_dim) if include_norm_add else None
+        self._init_norm(embed_dim, include_norm_add, impl)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -140,13 +168,14 @@ class SelfMultiheadAttn(_MHABase):
         else:
             nn.init.xavier_uniform_(self.in_proj_weight, gain=math.sqrt(2))
         nn.init.xavier_uniform_(self.out_proj_weight)
+        self._reset_norm()
         for n in ("q_bias", "k_bias", "v_bias", "in_proj_bias", "out_proj_bias"):
             b = getattr(self, n, None)
             if b is not None:
                 nn.init.constant_(b, 0.0)
 
     def forward(self, query, key=None, value=None, key_padding_mask=None, need_weights=False, attn_mask=None, is_training=True):
-        x = self.lyr_nrm(query) if self.include_norm_add else query
+        x = self._norm(query)
         if self.separate_qkv_params:
             w = torch.cat((self.q_weight, self.k_weight, self.v_weight), 0)
             bias = torch.cat((self.q_bias, self.k_bias, self.v_bias), 0) if self.bias else None
@@ -184,20 +213,21 @@ class EncdecMultiheadAttn(_MHABase):
         else:
             for n in ("in_proj_bias_q", "in_proj_bias_kv", "out_proj_bias"):
                 self.register_parameter(n, None)
-        self.lyr_nrm = FusedLayerNorm(embed_dim) if include_norm_add else None
+        self._init_norm(embed_dim, include_norm_add, impl)
         self.reset_parameters()
 
     def reset_parameters(self):
         nn.init.xavier_uniform_(self.in_proj_weight_q)
         nn.init.xavier_uniform_(self.in_proj_weight_kv, gain=math.sqrt(1.5))
         nn.init.xavier_uniform_(self.out_proj_weight)
+        self._reset_norm()
         for n in ("in_proj_bias_q", "in_proj_bias_kv", "out_proj_bias"):
             b = getattr(self, n, None)
             if b is not None:
                 nn.init.constant_(b, 0.0)
 
     def forward(self, query, key, value=None, key_padding_mask=None, need_weights=False, attn_mask=None, is_training=True):
-        x = self.lyr_nrm(query) if self.include_norm_add else query
+        x = self._norm(query)
         q = fused_dense_function(x, self.in_proj_weight_q, self.in_proj_bias_q)
         kv = fused_dense_function(key, self.in_proj_weight_kv, self.in_proj_bias_kv)
         tk, b = kv.shape[0], kv.shape[1]   # per-head interleave [heads, 2, head_dim] of the reference (encdec_multihead_attn_func.py:86-91)
