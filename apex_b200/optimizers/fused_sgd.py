@@ -141,12 +141,26 @@ class FusedNovoGrad(_TableOptimizer):
         self._norms: dict = {}
 
     def load_state_dict(self, state_dict):
+        """Restores the per-tensor second moments too. They live in ``group["exp_avg_sq"]``: here a dict {dtype name: norms of that dtype's
+        parameters, in group order}; the reference's two-element list [16-bit norms, fp32 norms] (fused_novograd.py:180-218) is accepted."""
         super().load_state_dict(state_dict)
-        for group in self.param_groups:  # per-group norm tensors must live with the params (reference :118-124)
-            if "exp_avg_sq" in group and group["params"]:
-                dev = group["params"][0].device
-                group["exp_avg_sq"] = [t.to(dev) if torch.is_tensor(t) else t for t in group["exp_avg_sq"]]
         self._norms.clear()
+        names = {str(d): d for d in (torch.float16, torch.bfloat16, torch.float32, torch.float64)}
+        for gi, group in enumerate(self.param_groups):
+            saved = group.get("exp_avg_sq")
+            if not saved or not group["params"]:
+                continue
+            dev = group["params"][0].device
+            present = {p.dtype for p in group["params"]}
+            if isinstance(saved, (list, tuple)):
+                half = next((d for d in (torch.float16, torch.bfloat16) if d in present), torch.float16)
+                saved = {str(d): t for d, t in zip((half, torch.float32), saved) if torch.is_tensor(t) and t.numel()}
+            restored = {}
+            for name, t in saved.items():
+                if name in names and torch.is_tensor(t):
+                    restored[name] = t.to(device=dev, dtype=torch.float32)
+                    self._norms[(gi, names[name])] = restored[name]   # the SAME tensor the kernel updates in place
+            group["exp_avg_sq"] = restored
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -149,3 +149,65 @@ def test_fused_novograd_cpu_matches_layerwise_oracle():
             q -= 1e-3 * m[i]
     for p, q in zip(ps, qs):
         torch.testing.assert_close(p.detach(), q, rtol=1e-5, atol=1e-7)
+
+
+def _resume_factories():
+    from apex_b200.contrib.optimizers import DistributedFusedAdam, DistributedFusedLAMB
+    from apex_b200.contrib.optimizers import FusedAdam as LegacyAdam
+    from apex_b200.contrib.optimizers import FusedLAMB as LegacyLAMB
+    from apex_b200.contrib.optimizers import FusedSGD as LegacySGD
+    from apex_b200.optimizers import FusedAdagrad, FusedAdam, FusedLAMB, FusedMixedPrecisionLamb, FusedNovoGrad, FusedSGD
+
+    return {
+        "FusedAdam": lambda ps: FusedAdam(ps, lr=1e-2, weight_decay=0.01),
+        "FusedLAMB": lambda ps: FusedLAMB(ps, lr=1e-2, weight_decay=0.01),
+        "FusedMixedPrecisionLamb": lambda ps: FusedMixedPrecisionLamb(ps, lr=1e-2, weight_decay=0.01),
+        "FusedSGD": lambda ps: FusedSGD(ps, lr=1e-2, momentum=0.9, dampening=0.1, weight_decay=0.01),
+        "FusedNovoGrad": lambda ps: FusedNovoGrad(ps, lr=1e-2, weight_decay=0.01),
+        "FusedAdagrad": lambda ps: FusedAdagrad(ps, lr=1e-2, weight_decay=0.01),
+        "DistributedFusedAdam": lambda ps: DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.01, device="cpu"),
+        "DistributedFusedLAMB": lambda ps: DistributedFusedLAMB(ps, lr=1e-2, weight_decay=0.01, device="cpu"),
+        "contrib.FusedAdam": lambda ps: LegacyAdam(ps, lr=1e-2, weight_decay=0.01),
+        "contrib.FusedLAMB": lambda ps: LegacyLAMB(ps, lr=1e-2, weight_decay=0.01),
+        "contrib.FusedSGD": lambda ps: LegacySGD(ps, lr=1e-2, momentum=0.9),
+    }
+
+
+@pytest.mark.parametrize("name", ["FusedAdam", "FusedLAMB", "FusedMixedPrecisionLamb", "FusedSGD", "FusedNovoGrad", "FusedAdagrad",
+                                  "DistributedFusedAdam", "DistributedFusedLAMB", "contrib.FusedAdam", "contrib.FusedLAMB", "contrib.FusedSGD"])
+def test_checkpoint_resume_is_exact(name):
+    """6 uninterrupted steps == 3 steps, state_dict -> fresh optimizer on fresh parameters, 3 more steps (moments, step counters,
+    per-tensor norms and sharded state must all survive the round trip)."""
+    import copy
+    import warnings
+
+    make = _resume_factories()[name]
+
+    def fresh():
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(70)), torch.nn.Parameter(torch.randn(3, 5))]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return ps, make(ps)
+
+    def run(ps, opt, its):
+        for it in its:
+            g = torch.Generator().manual_seed(it)
+            opt.zero_grad()
+            for p in ps:
+                p.grad = torch.randn(p.shape, generator=g) * (it + 1)
+            opt.step()
+
+    ps, opt = fresh()
+    run(ps, opt, range(6))
+    ps_a, opt_a = fresh()
+    run(ps_a, opt_a, range(3))
+    sd = copy.deepcopy(opt_a.state_dict())
+    ps_b, opt_b = fresh()
+    with torch.no_grad():
+        for dst, src in zip(ps_b, ps_a):
+            dst.copy_(src)
+    opt_b.load_state_dict(sd)
+    run(ps_b, opt_b, range(3, 6))
+    for got, want in zip(ps_b, ps):
+        torch.testing.assert_close(got, want, rtol=0, atol=0)
