@@ -95,29 +95,39 @@ class FusedSGD(_TableOptimizer):
             for dtype, cands in self._partition(gi, group).items():
                 is_cuda = cands[0].is_cuda
                 key = (gi, dtype)
-                first_run = False
                 tb = self._cache.cached(key) if is_cuda else None
-                lists = None
-                if tb is None:
+                launches = []   # (table or tensor lists, first_run)
+                if tb is not None:
+                    launches.append((tb, False))
+                else:
                     members = [p for p in cands if p.grad is not None]
                     if not members:
                         continue
-                    for p in members:
-                        st = self.state[p]
-                        if "momentum_buffer" not in st:
-                            first_run = True
-                            st["momentum_buffer"] = torch.zeros_like(p)
-                    lists = [[p.grad for p in members], list(members), [self.state[p]["momentum_buffer"] for p in members]]
+                    # A momentum buffer starts as the first gradient the parameter ever sees (torch.optim.SGD semantics). ``first_run`` is
+                    # a per-launch flag, so parameters that receive their first gradient later than the others get their own launch for
+                    # that one step (the reference applies the flag of the last parameter to the whole list, fused_sgd.py:137-152).
+                    fresh = [p for p in members if "momentum_buffer" not in self.state[p]]
+                    for p in fresh:
+                        self.state[p]["momentum_buffer"] = torch.zeros_like(p)
+                    seen = [p for p in members if not any(p is q for q in fresh)] if fresh else members
+
+                    def lists_of(ps):
+                        return [[p.grad for p in ps], list(ps), [self.state[p]["momentum_buffer"] for p in ps]]
+
+                    if is_cuda and not _lib.available():
+                        raise _lib.gpu_required_error("FusedSGD")
+                    if fresh and seen:
+                        launches += [(lists_of(seen), False), (lists_of(fresh), True)]   # one-off; the table is cached from the next step on
+                    else:
+                        lists = lists_of(members)
+                        launches.append((self._cache.build(key, cands, members, lists) if is_cuda else lists, bool(fresh)))
+                for target, first_run in launches:
+                    args = (group["weight_decay"], group["momentum"], group["dampening"], group["lr"], group["nesterov"], first_run,
+                            self.wd_after_momentum, 1.0 / self.most_recent_scale)
                     if is_cuda:
-                        if not _lib.available():
-                            raise _lib.gpu_required_error("FusedSGD")
-                        tb = self._cache.build(key, cands, members, lists)
-                args = (group["weight_decay"], group["momentum"], group["dampening"], group["lr"], group["nesterov"], first_run,
-                        self.wd_after_momentum, 1.0 / self.most_recent_scale)
-                if tb is not None:
-                    amp_C.multi_tensor_sgd(0, None, tb, *args)
-                else:
-                    ref.multi_tensor_sgd(None, lists, *args)
+                        amp_C.multi_tensor_sgd(0, None, target, *args)
+                    else:
+                        ref.multi_tensor_sgd(None, target, *args)
         self.most_recent_scale = 1.0
         self.scale_set_by_backward = False
         return loss

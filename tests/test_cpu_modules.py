@@ -364,3 +364,33 @@ def test_attention_modules_route_through_the_kernel_entry_point_when_opted_in(mo
     out, _ = mha(x, is_training=False)
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
     assert calls[0] == ((31, 2, 64), None, False) and calls[-1] == ((21, 2, 64), 3, False)
+
+
+def test_syncbatchnorm_follows_torch_batchnorm_semantics_sweep():
+    """Every combination of input rank (2-D .. 5-D), affine, track_running_stats, momentum (0.1 / None = cumulative average) and
+    train / eval over three iterations: outputs, input gradients, running statistics and the batch counter match torch's BatchNorm."""
+    import itertools
+
+    from apex_b200.parallel import SyncBatchNorm
+    torch.manual_seed(0)
+    for shape, affine, track, mom, train in itertools.product([(6, 5), (6, 5, 7), (4, 5, 3, 3), (2, 5, 2, 3, 2)], [True, False], [True, False],
+                                                              [0.1, None], [True, False]):
+        C = shape[1]
+        a = SyncBatchNorm(C, affine=affine, track_running_stats=track, momentum=mom)
+        bn = nn.BatchNorm1d if len(shape) <= 3 else nn.BatchNorm2d if len(shape) == 4 else nn.BatchNorm3d
+        b = bn(C, affine=affine, track_running_stats=track, momentum=mom)
+        a.train(train)
+        b.train(train)
+        for _ in range(3):
+            x = torch.randn(shape) * 2 + 1
+            xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+            ya, yb = a(xa), b(xb)
+            dy = torch.randn_like(ya)
+            ya.backward(dy)
+            yb.backward(dy)
+            torch.testing.assert_close(ya, yb, atol=1e-5, rtol=1e-4)
+            torch.testing.assert_close(xa.grad, xb.grad, atol=1e-5, rtol=1e-4)
+            if track:
+                torch.testing.assert_close(a.running_mean, b.running_mean, atol=1e-5, rtol=1e-4)
+                torch.testing.assert_close(a.running_var, b.running_var, atol=1e-5, rtol=1e-4)
+                assert int(a.num_batches_tracked) == int(b.num_batches_tracked)

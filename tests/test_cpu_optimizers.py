@@ -211,3 +211,25 @@ def test_checkpoint_resume_is_exact(name):
     run(ps_b, opt_b, range(3, 6))
     for got, want in zip(ps_b, ps):
         torch.testing.assert_close(got, want, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("momentum,dampening,nesterov", [(0.9, 0.0, False), (0.9, 0.3, False), (0.9, 0.0, True), (0.0, 0.0, False)])
+def test_fused_sgd_parameters_whose_first_gradient_arrives_late(momentum, dampening, nesterov):
+    """torch.optim.SGD semantics when a parameter has no gradient on some steps: its momentum buffer starts as the first gradient IT sees,
+    and the buffers of the other parameters are not disturbed (the launch-wide ``first_run`` flag must not leak across parameters)."""
+    for skip in (0, 1, 2):
+        torch.manual_seed(1)
+        pa = [torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(2, 2, 2))]
+        pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+        kw = dict(lr=0.1, momentum=momentum, dampening=dampening, nesterov=nesterov, weight_decay=0.1)
+        a = FusedSGD([{"params": pa[:1]}, {"params": pa[1:], "lr": 0.05}], **kw)
+        b = torch.optim.SGD([{"params": pb[:1]}, {"params": pb[1:], "lr": 0.05}], **kw)
+        for it in range(5):
+            g = torch.Generator().manual_seed(it)
+            for i, (x, y) in enumerate(zip(pa, pb)):
+                grad = torch.randn(x.shape, generator=g)
+                x.grad, y.grad = (None, None) if (i == skip and it % 2 == 0) else (grad.clone(), grad.clone())
+            a.step()
+            b.step()
+        for x, y in zip(pa, pb):
+            torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
