@@ -30,6 +30,8 @@ class ASP:
     __calculate_mask = None
     __allow_permutation = False
     __permuted = False
+    __save_permutation_graph = False
+    __permutation_output_dir = "."
 
     @classmethod
     def init_model_for_pruning(cls, model, mask_calculator="m4n2_1d", verbosity=3, whitelist=(torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d),
@@ -67,6 +69,17 @@ class ASP:
                 cls.__sparse_parameters.append((name, mod, p_name, p, mask, pruned))
 
     @classmethod
+    def set_permutation_saving_params(cls, allow_permutation=True, save_permutation_graph=False, permutation_output_dir="."):
+        """Whether compute_sparse_masks() searches channel permutations first, and whether / where the traced graph is dumped
+        (reference asp.py:444-475); forwarded to :class:`Permutation`."""
+        from .permutation_lib import Permutation
+
+        cls.__allow_permutation = allow_permutation
+        cls.__save_permutation_graph = save_permutation_graph
+        cls.__permutation_output_dir = permutation_output_dir
+        Permutation.set_permutation_saving_params(allow_permutation, save_permutation_graph, permutation_output_dir)
+
+    @classmethod
     def already_init_asp_model(cls):
         return cls.__model is not None
 
@@ -96,7 +109,10 @@ class ASP:
             # search + apply function-preserving channel permutations once, before the first masks (reference asp.py:314-345)
             from .permutation_lib import Permutation
 
-            Permutation.permute_model(cls.__model, verbosity=cls.__verbosity >= 2)
+            Permutation.permute_model(cls.__model, dump_fx_graph=cls.__save_permutation_graph,
+                                      save_dumped_fx_graph=(cls.__permutation_output_dir + "/model_offline_permutation_graph.json"
+                                                            if cls.__save_permutation_graph else None),
+                                      verbosity=cls.__verbosity >= 2)
             cls.__permuted = True
         with torch.no_grad():
             for name, mod, p_name, p, mask, pruned in cls.__sparse_parameters:

@@ -34,6 +34,28 @@ class Permutation:
         cls.__seed = identical_seed
         torch.manual_seed(identical_seed)
 
+    @classmethod
+    def reset_seed(cls):
+        """Re-seed before a search so that every rank finds the same permutation (reference permutation_lib.py: reset_seed)."""
+        torch.manual_seed(cls.__seed)
+
+    @classmethod
+    def set_tcpstore_port(cls, tcpstore_port):
+        """The reference synchronises permutations through a TCPStore on this port; here every rank runs the same seeded search, so the
+        port is only recorded."""
+        cls.__tcpstore_port = tcpstore_port
+
+    @classmethod
+    def set_permutation_saving_params(cls, allow_permutation=True, save_permutation_graph=False, permutation_output_dir="."):
+        cls.__allow_permutation = allow_permutation
+        cls.__save_permutation_graph = save_permutation_graph
+        cls.__permutation_output_dir = permutation_output_dir
+
+    @classmethod
+    def set_permutation_params_from_asp(cls, model, sparse_parameters, all_parameters=None, verbosity=0):
+        """Hand-over of the ASP state (reference: called from ASP.init_model_for_pruning); the graph search works from the model alone."""
+        cls.__model, cls.__sparse_parameters, cls.__verbosity = model, sparse_parameters, verbosity
+
     # ------------------------------------------------------------------------------------------------- parameter surgery
     @staticmethod
     def apply_permutation_in_C_dim(module, perm):
@@ -179,6 +201,8 @@ class Permutation:
                 print(f"[permutation_lib] model is not fx-traceable ({type(e).__name__}: {e}); skipping channel permutations")
             return []
         report = []
+        names = {m: n for n, m in model.named_modules()}
+        dumped = []
         for cons, prods, bns in groups:
             mats = [c.weight.detach().reshape(c.weight.shape[0], c.weight.shape[1], -1).permute(0, 2, 1).reshape(-1, c.weight.shape[1]) for c in cons]
             stacked = torch.cat(mats, 0).float()
@@ -192,6 +216,14 @@ class Permutation:
             for p in prods + bns:
                 cls.apply_permutation_in_K_dim(p, perm)
             report.append((len(cons), before, after))
+            dumped.append({"consumers": [names.get(c, "?") for c in cons], "producers": [names.get(m, "?") for m in prods],
+                           "norms": [names.get(m, "?") for m in bns], "permutation": [int(i) for i in perm], "kept_magnitude_before": before,
+                           "kept_magnitude_after": after})
             if verbosity:
                 print(f"[permutation_lib] group of {len(cons)} consumer(s): kept magnitude {before:.3f} -> {after:.3f}")
+        if dump_fx_graph and save_dumped_fx_graph:   # what was permuted and how, for offline inspection (the reference dumps its annotated fx graph)
+            import json
+
+            with open(save_dumped_fx_graph, "w") as f:
+                json.dump({"groups": dumped}, f, indent=1)
         return report
