@@ -103,6 +103,8 @@ class FusedSGD(_TableOptimizer):
                     members = [p for p in cands if p.grad is not None]
                     if not members:
                         continue
+                    if any(p.grad.is_sparse for p in members):
+                        raise RuntimeError("FusedSGD does not support sparse gradients")
                     # A momentum buffer starts as the first gradient the parameter ever sees (torch.optim.SGD semantics). ``first_run`` is
                     # a per-launch flag, so parameters that receive their first gradient later than the others get their own launch for
                     # that one step (the reference applies the flag of the last parameter to the whole list, fused_sgd.py:137-152).
