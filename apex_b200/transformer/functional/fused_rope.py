@@ -42,7 +42,8 @@ def _sbhd(t, freqs, cos, sin, transpose_output, is_bwd):
     if not _native(t):
         c = cos.float() if cached else torch.cos(freqs.float())
         sn = sin.float() if cached else torch.sin(freqs.float())
-        return _ref_apply(t, c.view(-1, 1, 1, r)[:s], sn.view(-1, 1, 1, r)[:s], is_bwd)
+        out = _ref_apply(t, c.view(-1, 1, 1, r)[:s], sn.view(-1, 1, 1, r)[:s], is_bwd)
+        return out.transpose(0, 1).contiguous().transpose(0, 1) if transpose_output else out   # [s, b, h, d] values in [b, s, h, d] memory
     out = torch.empty((b, s, h, d), dtype=t.dtype, device=t.device).transpose(0, 1) if transpose_output else torch.empty_like(t, memory_format=torch.contiguous_format)
     cs = [cos.contiguous(), sin.contiguous(), None, None] if cached else [None, None, None, None]
     dt_cs = _lib.dt(cos) if cached else 0
