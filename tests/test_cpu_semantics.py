@@ -1,0 +1,185 @@
+"""Behavioural sweeps against PyTorch's own modules / optimizers on the device-independent (PyTorch) paths: option combinations a single
+example test does not reach. The CUDA kernels are checked against the same oracles in tests/test_gpu_*.py."""
+import itertools
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+def test_layer_norm_option_sweep():
+    from apex_b200.normalization import FusedLayerNorm
+    torch.manual_seed(0)
+    for shape, ns, affine, me in itertools.product([(4, 8), (2, 3, 8), (2, 3, 4, 8)], [1, 2], [True, False], [False, True]):
+        nshape = shape[-ns:]
+        a, b = FusedLayerNorm(nshape, elementwise_affine=affine, memory_efficient=me), torch.nn.LayerNorm(nshape, elementwise_affine=affine)
+        if affine:
+            with torch.no_grad():
+                a.weight.normal_()
+                a.bias.normal_()
+                b.weight.copy_(a.weight)
+                b.bias.copy_(a.bias)
+        x = torch.randn(shape)
+        xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+        ya, yb = a(xa), b(xb)
+        dy = torch.randn_like(ya)
+        ya.backward(dy)
+        yb.backward(dy)
+        torch.testing.assert_close(ya, yb, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(xa.grad, xb.grad, atol=1e-4, rtol=1e-4)
+        if affine:
+            torch.testing.assert_close(a.weight.grad, b.weight.grad, atol=1e-4, rtol=1e-4)
+            torch.testing.assert_close(a.bias.grad, b.bias.grad, atol=1e-4, rtol=1e-4)
+    with pytest.raises(RuntimeError):
+        FusedLayerNorm(8)(torch.randn(2, 7))
+
+
+def test_clip_grad_norm_types_and_nonfinite():
+    from apex_b200.contrib.clip_grad import clip_grad_norm_
+    torch.manual_seed(0)
+    for norm_type, max_norm in itertools.product([2.0, float("inf"), 1.0, 3.0], [0.5, 100.0]):
+        ps = [torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(3, 2))]
+        pr = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        for p, r in zip(ps, pr):
+            p.grad = torch.randn_like(p)
+            r.grad = p.grad.clone()
+        torch.testing.assert_close(clip_grad_norm_(ps, max_norm, norm_type=norm_type), torch.nn.utils.clip_grad_norm_(pr, max_norm, norm_type=norm_type))
+        for p, r in zip(ps, pr):
+            torch.testing.assert_close(p.grad, r.grad)
+    p = torch.nn.Parameter(torch.randn(5))
+    p.grad = torch.full((5,), float("nan"))
+    with pytest.raises(RuntimeError):
+        clip_grad_norm_([p], 1.0, error_if_nonfinite=True)
+
+
+def test_xentropy_smoothing_and_padding_sweep():
+    from apex_b200.contrib.xentropy import SoftmaxCrossEntropyLoss
+    torch.manual_seed(0)
+    for smoothing, pad in itertools.product([0.0, 0.1], [None, 0, 3]):
+        logits, labels = torch.randn(9, 7), torch.randint(0, 7, (9,))
+        if pad is not None:
+            labels[2] = pad
+        la, lb = logits.clone().requires_grad_(), logits.clone().requires_grad_()
+        got = SoftmaxCrossEntropyLoss.apply(la, labels, smoothing, -1 if pad is None else pad, True)
+        want = F.cross_entropy(lb, labels, label_smoothing=smoothing, reduction="none", ignore_index=-100 if pad is None else pad)
+        got.sum().backward()
+        want.sum().backward()
+        torch.testing.assert_close(got, want, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(la.grad, lb.grad, atol=1e-5, rtol=1e-5)
+
+
+def _rotate_half(t):
+    d = t.shape[-1] // 2
+    return torch.cat((-t[..., d:], t[..., :d]), -1)
+
+
+def _rope(t, freqs):
+    r = freqs.shape[-1]
+    return torch.cat((t[..., :r] * freqs.cos() + _rotate_half(t[..., :r]) * freqs.sin(), t[..., r:]), -1)
+
+
+def test_rope_variants():
+    from apex_b200.transformer.functional import fused_rope as R
+    torch.manual_seed(0)
+    s, b, h, d = 6, 2, 3, 8
+    for r in (8, 4):   # full and partial rotary dimension
+        t, f = torch.randn(s, b, h, d, requires_grad=True), torch.randn(s, 1, 1, r)
+        out, want = R.fused_apply_rotary_pos_emb(t, f), _rope(t, f)
+        g = torch.randn_like(out)
+        torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(torch.autograd.grad(out, t, g)[0], torch.autograd.grad(want, t, g)[0], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(R.fused_apply_rotary_pos_emb_cached(t, f.cos(), f.sin()), want, atol=1e-5, rtol=1e-5)
+        tr = R.fused_apply_rotary_pos_emb(t, f, transpose_output_memory=True)
+        torch.testing.assert_close(tr, want, atol=1e-5, rtol=1e-5)
+        assert tr.transpose(0, 1).is_contiguous()
+    cu = torch.tensor([0, 3, 7, 12], dtype=torch.int32)
+    tt, f = torch.randn(12, h, d, requires_grad=True), torch.randn(6, 1, 1, d)
+    out = R.fused_apply_rotary_pos_emb_thd(tt, cu, f)
+    want = torch.cat([_rope(tt[cu[i]:cu[i + 1]].unsqueeze(1), f[:cu[i + 1] - cu[i]]).squeeze(1) for i in range(3)])
+    g = torch.randn_like(out)
+    torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(torch.autograd.grad(out, tt, g)[0], torch.autograd.grad(want, tt, g)[0], atol=1e-5, rtol=1e-5)
+    bb, ih, iw = 2, 3, 4
+    t2 = torch.randn(bb, ih * iw, h, d)
+    ch, sh, cw, sw = torch.randn(1, ih + 1, 1, d // 2), torch.randn(1, ih + 1, 1, d // 2), torch.randn(1, iw + 2, 1, d // 2), torch.randn(1, iw + 2, 1, d // 2)
+    x = t2.view(bb, ih, iw, h, d)
+    xh, xw = x[..., :d // 2], x[..., d // 2:]
+    want = torch.cat((xh * ch[:, :ih].unsqueeze(2) + _rotate_half(xh) * sh[:, :ih].unsqueeze(2),
+                      xw * cw[:, :iw].unsqueeze(1) + _rotate_half(xw) * sw[:, :iw].unsqueeze(1)), -1).view(bb, ih * iw, h, d)
+    torch.testing.assert_close(R.fused_apply_rotary_pos_emb_2d(t2, ih, iw, ch, sh, cw, sw), want, atol=1e-5, rtol=1e-5)
+
+
+def _three_params(dtype=torch.float32):
+    torch.manual_seed(1)
+    return [torch.nn.Parameter(torch.randn(1100).to(dtype)), torch.nn.Parameter(torch.randn(40, 30).to(dtype)), torch.nn.Parameter(torch.randn(7).to(dtype))]
+
+
+def _two_groups(ps):
+    return [{"params": ps[:2], "lr": 1e-2}, {"params": ps[2:], "lr": 3e-3, "weight_decay": 0.05, "betas": (0.8, 0.9)}]
+
+
+@pytest.mark.parametrize("adam_w", [True, False])
+def test_adam_family_param_groups_match_torch(adam_w):
+    """FusedAdam and DistributedFusedAdam (several bucket / buffer configurations, deferred clipping) with per-group lr / weight decay /
+    betas against torch.optim.Adam(W)."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    from apex_b200.optimizers import FusedAdam
+    torch_cls = torch.optim.AdamW if adam_w else torch.optim.Adam
+    makers = [lambda ps: FusedAdam(_two_groups(ps), lr=1e-3, weight_decay=0.1, adam_w_mode=adam_w)]
+    for kw in (dict(), dict(bucket_cap_mb=0.001), dict(contiguous_grad_buffer=False, contiguous_param_buffer=False), dict(overlap_grad_sync=False)):
+        makers.append(lambda ps, kw=kw: DistributedFusedAdam(_two_groups(ps), lr=1e-3, weight_decay=0.1, adam_w_mode=adam_w, device="cpu", **kw))
+    for make in makers:
+        pa, pb = _three_params(), _three_params()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a = make(pa)
+        b = torch_cls(_two_groups(pb), lr=1e-3, weight_decay=0.1)
+        for it in range(4):
+            g = torch.Generator().manual_seed(it)
+            a.zero_grad()
+            b.zero_grad()
+            for x, y in zip(pa, pb):
+                grad = torch.randn(x.shape, generator=g)
+                x.grad = grad.clone() if x.grad is None else x.grad.copy_(grad)
+                y.grad = grad.clone()
+            if it == 2 and hasattr(a, "clip_grad_norm"):
+                torch.testing.assert_close(a.clip_grad_norm(0.5).reshape(()), torch.nn.utils.clip_grad_norm_(pb, 0.5).reshape(()), atol=1e-4, rtol=1e-4)
+            a.step()
+            b.step()
+        for x, y in zip(pa, pb):
+            torch.testing.assert_close(x, y, atol=2e-6, rtol=1e-5)
+
+
+def test_adagrad_matches_torch():
+    from apex_b200.optimizers import FusedAdagrad
+    for wd in (0.0, 0.1):
+        pa, pb = _three_params(), _three_params()
+        a, b = FusedAdagrad(pa, lr=0.1, weight_decay=wd), torch.optim.Adagrad(pb, lr=0.1, weight_decay=wd)
+        for it in range(4):
+            g = torch.Generator().manual_seed(it)
+            for x, y in zip(pa, pb):
+                x.grad = torch.randn(x.shape, generator=g)
+                y.grad = x.grad.clone()
+            a.step()
+            b.step()
+        for x, y in zip(pa, pb):
+            torch.testing.assert_close(x, y, atol=1e-6, rtol=1e-5)
+
+
+def test_optimizer_argument_validation():
+    from apex_b200.optimizers import FusedAdagrad, FusedAdam, FusedLAMB, FusedNovoGrad, FusedSGD
+    p = [torch.nn.Parameter(torch.randn(4, 4))]
+    for cls in (FusedAdam, FusedLAMB, FusedNovoGrad):
+        with pytest.raises(RuntimeError, match="AMSGrad"):
+            cls(p, amsgrad=True)
+    with pytest.raises(ValueError):
+        FusedSGD(p, lr=-1)
+    with pytest.raises(ValueError):
+        FusedSGD(p, lr=0.1, nesterov=True)
+    for cls, kw in ((FusedAdam, {}), (FusedLAMB, {}), (FusedSGD, {"lr": 0.1}), (FusedAdagrad, {})):
+        q = [torch.nn.Parameter(torch.randn(4, 4))]
+        opt = cls(q, **kw)
+        q[0].grad = torch.randn(4, 4).to_sparse()
+        with pytest.raises(RuntimeError, match="sparse"):
+            opt.step()
