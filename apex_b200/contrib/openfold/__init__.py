@@ -5,7 +5,7 @@ sm_100a kernels: ``FusedAdamSWA`` on the multi-tensor engine, ``LayerNormSmallSh
 kernels. ``sync_triton_auto_tune_cache_across_gpus`` is a no-op (there is no JIT cache to broadcast)."""
 from .fused_adam_swa import AdamMathType, FusedAdamSWA
 from .layer_norm import LayerNormSmallShapeOptImpl
-from .mha import AttnBiasJIT, AttnNoBiasJIT, AttnTri, CanSchTriMHA, disable, enable, is_enabled
+from .mha import AttnBiasJIT, AttnNoBiasJIT, AttnTri, CanSchTriMHA, FusedAttenionCoreFunc, disable, enable, is_enabled, schedule_triton_mha
 
 
 def sync_triton_auto_tune_cache_across_gpus(strict: bool = True, verbose: bool = False) -> None:

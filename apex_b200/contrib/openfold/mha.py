@@ -49,3 +49,15 @@ def AttnBiasJIT(q, k, v, mask, bias, inf=1e9):
 
 def AttnNoBiasJIT(q, k, v, mask, inf=1e9):
     return _core(q, k, v, mask, None, inf)
+
+
+def schedule_triton_mha(in_shape, fwd=True):
+    """Tile schedule the reference's Triton kernel would use for this shape -> (BLOCK_M, BLOCK_N, num_warps, num_stages). Kept for call-site
+    parity (mha.py:90-128 of the reference holds a per-shape table); nothing is scheduled with it here."""
+    return (64, 64, 4, 2) if fwd else (128, 64, 8, 1)
+
+
+class FusedAttenionCoreFunc:
+    """Name of the reference's autograd Function (sic); ``AttnTri`` is its ``apply``."""
+
+    apply = staticmethod(AttnTri)
