@@ -1,0 +1,3 @@
+"""Import path of the reference (apex/contrib/multihead_attn/self_multihead_attn.py)."""
+from .funcs import jit_dropout_add  # noqa: F401
+from .multihead_attn import SelfMultiheadAttn  # noqa: F401

@@ -394,3 +394,50 @@ def test_syncbatchnorm_follows_torch_batchnorm_semantics_sweep():
                 torch.testing.assert_close(a.running_mean, b.running_mean, atol=1e-5, rtol=1e-4)
                 torch.testing.assert_close(a.running_var, b.running_var, atol=1e-5, rtol=1e-4)
                 assert int(a.num_batches_tracked) == int(b.num_batches_tracked)
+
+
+def test_attention_functional_forms_match_the_modules():
+    """The reference's XxxAttnFunc.apply argument lists (self / encdec, fast, norm-add) evaluate the same function as the modules."""
+    from apex_b200.contrib.multihead_attn import EncdecMultiheadAttn, SelfMultiheadAttn
+    from apex_b200.contrib.multihead_attn.encdec_multihead_attn_func import encdec_attn_func
+    from apex_b200.contrib.multihead_attn.fast_encdec_multihead_attn_func import fast_encdec_attn_func
+    from apex_b200.contrib.multihead_attn.fast_encdec_multihead_attn_norm_add_func import fast_encdec_attn_norm_add_func
+    from apex_b200.contrib.multihead_attn.fast_self_multihead_attn_func import fast_self_attn_func
+    from apex_b200.contrib.multihead_attn.fast_self_multihead_attn_norm_add_func import fast_self_attn_norm_add_func
+    from apex_b200.contrib.multihead_attn.mask_softmax_dropout_func import MaskSoftmaxDropout, fast_mask_softmax_dropout_func
+    from apex_b200.contrib.multihead_attn.self_multihead_attn import jit_dropout_add
+    from apex_b200.contrib.multihead_attn.self_multihead_attn_func import self_attn_func
+    torch.manual_seed(0)
+    E, H, T, B = 32, 4, 6, 2
+    x, mem = torch.randn(T, B, E), torch.randn(5, B, E)
+    kpm = torch.zeros(B, T, dtype=torch.bool)
+    kpm[:, -2:] = True
+    tm = torch.triu(torch.ones(T, T, dtype=torch.bool), 1)
+    m = SelfMultiheadAttn(E, H, bias=True).eval()
+    with torch.no_grad():
+        m.in_proj_bias.normal_()
+        m.out_proj_bias.normal_()
+    w = (m.in_proj_weight, m.out_proj_weight, m.in_proj_bias, m.out_proj_bias)
+    torch.testing.assert_close(self_attn_func(False, False, H, m.scaling, x, *w, None, False, 0.0), m(x, is_training=False)[0])
+    torch.testing.assert_close(fast_self_attn_func(False, False, H, x, *w, kpm, False, 0.0), m(x, key_padding_mask=kpm, is_training=False)[0])
+    torch.testing.assert_close(self_attn_func(True, False, H, m.scaling, x, *w, tm, False, 0.0), m(x, attn_mask=tm, is_training=False)[0])
+    n = SelfMultiheadAttn(E, H, include_norm_add=True).eval()
+    with torch.no_grad():
+        n.lyr_nrm_gamma_weights.normal_()
+        n.lyr_nrm_beta_weights.normal_()
+    got = fast_self_attn_norm_add_func(False, False, H, x, n.lyr_nrm_gamma_weights, n.lyr_nrm_beta_weights, n.in_proj_weight, n.out_proj_weight, None, 0.0)
+    torch.testing.assert_close(got, n(x, is_training=False)[0])
+    e = EncdecMultiheadAttn(E, H, bias=True).eval()
+    got = encdec_attn_func(False, False, H, e.scaling, x, mem, e.in_proj_weight_q, e.in_proj_weight_kv, e.out_proj_weight, e.in_proj_bias_q,
+                           e.in_proj_bias_kv, e.out_proj_bias, None, 0.0)
+    torch.testing.assert_close(got, e(x, mem, is_training=False)[0])
+    e2 = EncdecMultiheadAttn(E, H, include_norm_add=True).eval()
+    got = fast_encdec_attn_norm_add_func(False, False, H, x, mem, e2.lyr_nrm_gamma_weights, e2.lyr_nrm_beta_weights, e2.in_proj_weight_q,
+                                         e2.in_proj_weight_kv, e2.out_proj_weight, None, 0.0)
+    torch.testing.assert_close(got, e2(x, mem, is_training=False)[0])
+    e3 = EncdecMultiheadAttn(E, H).eval()
+    torch.testing.assert_close(fast_encdec_attn_func(False, False, H, x, mem, e3.in_proj_weight_q, e3.in_proj_weight_kv, e3.out_proj_weight, None, 0.0),
+                               e3(x, mem, is_training=False)[0])
+    s = torch.randn(B * H, T, T)
+    torch.testing.assert_close(MaskSoftmaxDropout.apply(False, H, s, None, False, 0.0), fast_mask_softmax_dropout_func(False, H, s, None, False, 0.0))
+    torch.testing.assert_close(jit_dropout_add(x, x, 0.5, False), 2 * x)
