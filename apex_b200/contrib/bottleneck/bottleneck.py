@@ -5,9 +5,38 @@ Convolutions are cuDNN here as in the reference; the scale/bias/ReLU/residual ta
 convolution through a :mod:`halo_exchangers` transport (peer memory over NVLink by default)."""
 from __future__ import annotations
 
+import functools
+
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+
+def kaiming_uniform_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
+    nn.init.kaiming_uniform_(tensor, a=a, mode=mode, nonlinearity=nonlinearity)
+
+
+def compute_scale_bias_one(nhwc, weight, bias, running_mean, running_var, w_scale, w_bias):
+    """Fold one frozen BN into (scale, bias), written INTO the given tensors (reference :20-24): capturable in a CUDA graph."""
+    scale = weight * running_var.rsqrt()
+    w_scale.copy_(scale)
+    w_bias.copy_(bias - running_mean * scale)
+
+
+def compute_scale_bias_method(nhwc, args):
+    for arg in args:
+        compute_scale_bias_one(nhwc, *arg)
+
+
+def drelu_dscale1(grad_o, output, scale1):
+    """ReLU backward followed by one scale: (grad * mask * scale1, grad * mask)."""
+    dx_relu = (output > 0) * grad_o
+    return dx_relu * scale1, dx_relu
+
+
+def drelu_dscale2(grad_o, output, scale1, scale2):
+    dx_relu = (output > 0) * grad_o
+    return dx_relu * scale1, dx_relu * scale2
 
 
 class FrozenBatchNorm2d(nn.Module):
@@ -60,8 +89,26 @@ class Bottleneck(nn.Module):
         self.conv3 = conv1x1(bottleneck_channels, out_channels)
         self.bn1, self.bn2, self.bn3 = norm_func(bottleneck_channels), norm_func(bottleneck_channels), norm_func(out_channels)
         self.stride, self.use_cudnn, self.explicit_nhwc = stride, use_cudnn, explicit_nhwc
+        self.w_scale = self.w_bias = None
         for w in (self.conv1, self.conv2, self.conv3):
-            nn.init.kaiming_uniform_(w.weight, a=1)
+            kaiming_uniform_(w.weight, a=1)
+
+    def get_scale_bias_callable(self):
+        """Allocates persistent folded (scale, bias) tensors for bn1..bn3 (+ the downsample BN) and returns a callable that refreshes them from
+        the BN buffers; forward() then uses the persistent tensors. The reference's hook for recomputing the folding inside a captured graph
+        (:233-248)."""
+        self.w_scale, self.w_bias, args = [], [], []
+        norms = [self.bn1, self.bn2, self.bn3] + ([self.downsample[1]] if self.downsample is not None else [])
+        for bn in norms:
+            sc = torch.empty_like(bn.weight)
+            bi = torch.empty_like(sc)
+            args.append((bn.weight, bn.bias, bn.running_mean, bn.running_var, sc, bi))
+            self.w_scale.append(sc.reshape(1, -1, 1, 1))
+            self.w_bias.append(bi.reshape(1, -1, 1, 1))
+        return functools.partial(compute_scale_bias_method, self.explicit_nhwc, args)
+
+    def _folded(self, i, bn):
+        return (self.w_scale[i], self.w_bias[i]) if self.w_scale is not None else bn.get_scale_bias()
 
     def _to_nchw(self, x):
         return x.permute(0, 3, 1, 2) if self.explicit_nhwc else x
@@ -74,13 +121,16 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         x = self._to_nchw(x)
-        s1, b1 = self.bn1.get_scale_bias()
-        s2, b2 = self.bn2.get_scale_bias()
-        s3, b3 = self.bn3.get_scale_bias()
+        (s1, b1), (s2, b2), (s3, b3) = self._folded(0, self.bn1), self._folded(1, self.bn2), self._folded(2, self.bn3)
         out = F.relu(self.conv1(x) * s1.to(x.dtype) + b1.to(x.dtype))
         out = F.relu(self._conv2(out) * s2.to(x.dtype) + b2.to(x.dtype))
         out = self.conv3(out) * s3.to(x.dtype) + b3.to(x.dtype)
-        identity = x if self.downsample is None else self.downsample(x)
+        if self.downsample is None:
+            identity = x
+        elif self.w_scale is not None:
+            identity = self.downsample[0](x) * self.w_scale[3].to(x.dtype) + self.w_bias[3].to(x.dtype)
+        else:
+            identity = self.downsample(x)
         return self._from_nchw(F.relu(out + identity))
 
 

@@ -441,3 +441,26 @@ def test_attention_functional_forms_match_the_modules():
     s = torch.randn(B * H, T, T)
     torch.testing.assert_close(MaskSoftmaxDropout.apply(False, H, s, None, False, 0.0), fast_mask_softmax_dropout_func(False, H, s, None, False, 0.0))
     torch.testing.assert_close(jit_dropout_add(x, x, 0.5, False), 2 * x)
+
+
+def test_bottleneck_scale_bias_callable():
+    """get_scale_bias_callable(): forward() reads persistent folded (scale, bias) tensors that only change when the callable runs."""
+    from apex_b200.contrib.bottleneck import Bottleneck
+    torch.manual_seed(0)
+    for explicit in (False, True):
+        m = Bottleneck(16, 8, 32, stride=2, explicit_nhwc=explicit)
+        for bn in (m.bn1, m.bn2, m.bn3, m.downsample[1]):
+            bn.weight.normal_()
+            bn.bias.normal_()
+            bn.running_mean.normal_()
+            bn.running_var.uniform_(0.5, 2)
+        x = torch.randn(2, 16, 8, 8)
+        x = x.permute(0, 2, 3, 1).contiguous() if explicit else x
+        y0 = m(x)
+        refresh = m.get_scale_bias_callable()
+        refresh()
+        torch.testing.assert_close(m(x), y0)
+        m.bn1.weight.mul_(2)
+        torch.testing.assert_close(m(x), y0)          # stale on purpose until refreshed
+        refresh()
+        assert not torch.allclose(m(x), y0)
