@@ -183,3 +183,35 @@ def test_optimizer_argument_validation():
         q[0].grad = torch.randn(4, 4).to_sparse()
         with pytest.raises(RuntimeError, match="sparse"):
             opt.step()
+
+
+@pytest.mark.parametrize("name", ["FusedAdam", "FusedLAMB", "FusedSGD", "FusedNovoGrad", "FusedAdagrad", "FusedMixedPrecisionLamb",
+                                  "DistributedFusedAdam", "DistributedFusedLAMB"])
+def test_grad_scaler_skips_the_step_on_overflow(name):
+    """torch.amp.GradScaler drives every optimizer: an inf gradient must leave the parameters untouched and halve the scale, finite steps
+    must update (reference tests/L0/run_optimizers/test_adam.py trains a small net under a GradScaler)."""
+    from apex_b200.contrib import optimizers as CO
+    from apex_b200 import optimizers as O
+    kw = {"FusedSGD": dict(lr=1e-2, momentum=0.9)}.get(name, dict(lr=1e-2))
+    if name.startswith("Distributed"):
+        kw["device"] = "cpu"
+    torch.manual_seed(0)
+    model = torch.nn.Linear(8, 4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt = getattr(CO if name.startswith("Distributed") else O, name)(model.parameters(), **kw)
+    scaler = torch.amp.GradScaler("cpu", init_scale=1024.0, growth_interval=2)
+    for it in range(5):
+        opt.zero_grad()
+        scaler.scale(model(torch.randn(16, 8)).square().mean()).backward()
+        before = [p.detach().clone() for p in model.parameters()]
+        if it == 2:
+            for p in model.parameters():
+                p.grad[0] = float("inf")
+        scaler.step(opt)
+        scaler.update()
+        changed = any(not torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+        assert changed == (it != 2), (name, it)
+        if it == 2:
+            assert scaler.get_scale() == 1024.0    # grew to 2048 after two clean steps, halved by the overflow
+    assert all(bool(torch.isfinite(p).all()) for p in model.parameters())
