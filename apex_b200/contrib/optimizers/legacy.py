@@ -151,8 +151,9 @@ class FP16_Optimizer:
                 self.cur_scale *= self.scale_factor
         self.cur_iter += 1
 
-    state = property(lambda self: self.optimizer.state)
-    param_groups = property(lambda self: self.optimizer.param_groups)
+    # promoted so that ``fp16_optimizer.state`` / ``.param_groups`` can be read and assigned (e.g. to adjust the learning rate)
+    state = property(lambda self: self.optimizer.state, lambda self, value: setattr(self.optimizer, "state", value))
+    param_groups = property(lambda self: self.optimizer.param_groups, lambda self, value: setattr(self.optimizer, "param_groups", value))
 
     def state_dict(self):
         sd = {"dynamic_loss_scale": self.dynamic_loss_scale, "cur_scale": self.cur_scale, "cur_iter": self.cur_iter,
