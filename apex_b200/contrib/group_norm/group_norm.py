@@ -117,12 +117,12 @@ class GroupNorm(nn.Module):
 
     __constants__ = ["num_groups", "num_channels", "eps", "affine", "act"]
 
-    def __init__(self, num_groups, num_channels, eps=1e-5, affine=True, device=None, dtype=None, act=""):
+    def __init__(self, num_groups, num_channels, eps=1e-5, affine=True, device=None, dtype=None, act=None):
         super().__init__()
         if num_channels % num_groups != 0:
             raise ValueError("num_channels must be divisible by num_groups")
         self.num_groups, self.num_channels, self.eps, self.affine = num_groups, num_channels, eps, affine
-        self.act = act.lower()
+        self.act = (act or "").lower()
         kw = {"device": device, "dtype": dtype}
         if affine:
             self.weight = nn.Parameter(torch.empty(num_channels, **kw))

@@ -225,6 +225,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._param_view, self._grad_view, self._init_values = {}, {}, {}
         self._segments: list[_Segment] = []
         self._grad_scale = torch.ones([], dtype=torch.float32, device=self.device)
+        self._dtype_overrides: dict = {}
         self._grad_norm = None
         self._dummy_overflow_buf = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._pad = None
@@ -270,20 +271,28 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         return (self.fused_collectives and not self.with_scaled_states and dtype == torch.float32 and self.store_params and grad_dtype in f and param_dtype in f
                 and (grad_dtype, param_dtype) in pairs)
 
-    def init_params(self, params: Optional[Iterable[torch.nn.Parameter]] = None) -> None:
-        """Lay out parameters, allocate buffers and state (lazily called by the first step / zero_grad)."""
+    def init_params(self, params: Optional[Iterable[torch.nn.Parameter]] = None, dtype: Optional[torch.dtype] = None,
+                    grad_sync_dtype: Optional[torch.dtype] = None, param_sync_dtype: Optional[torch.dtype] = None) -> None:
+        """Lay out parameters, allocate buffers and state (lazily called by the first step / zero_grad). Called with ``params`` and dtypes
+        BEFORE that point it records per-parameter overrides of the optimizer-wide state / gradient-sync / parameter-sync dtypes, as the
+        reference allows (:1228-1273; e.g. a few fp32 parameters inside a bf16 model); the layout itself is still built in one go."""
         if self._inited:
+            return
+        if params is not None and (dtype or grad_sync_dtype or param_sync_dtype):
+            for p in params:
+                self._dtype_overrides[id(p)] = (dtype, grad_sync_dtype, param_sync_dtype)
             return
         for gi, group in enumerate(self.param_groups):
             keyed: dict = {}
             for p in group["params"]:
                 if not p.requires_grad:
                     continue
-                gd = self._grad_sync_dtype or p.dtype
-                pd = self._param_sync_dtype or p.dtype
-                keyed.setdefault((gd, pd), []).append(p)
-            for (gd, pd), ps in keyed.items():
-                self._segments.append(_Segment(self, gi, ps, self.dtype, gd, pd))
+                sd, gd, pd = self._dtype_overrides.get(id(p), (None, None, None))
+                gd = gd or self._grad_sync_dtype or p.dtype
+                pd = pd or self._param_sync_dtype or p.dtype
+                keyed.setdefault((sd or self.dtype, gd, pd), []).append(p)
+            for (sd, gd, pd), ps in keyed.items():
+                self._segments.append(_Segment(self, gi, ps, sd, gd, pd))
         if self.fused_collectives and self.distributed_size > 1:
             from ...parallel.symmetric import SignalPad
 

@@ -34,9 +34,10 @@ class ASP:
     __permutation_output_dir = "."
 
     @classmethod
-    def init_model_for_pruning(cls, model, mask_calculator="m4n2_1d", verbosity=3, whitelist=(torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d),
+    def init_model_for_pruning(cls, model, mask_calculator="m4n2_1d", verbosity=3,
+                               whitelist=(torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d, torch.nn.Conv3d, torch.nn.MultiheadAttention),
                                allowed_layer_names=None, disallowed_layer_names=(), allow_recompute_mask=False, custom_layer_dict=None,
-                               allow_permutation=False):
+                               allow_permutation=True):
         assert cls.__model is None, "ASP has been initialized already."
         cls.__model, cls.__verbosity, cls.__allow_permutation = model, verbosity, allow_permutation
         cls.__sparse_parameters = []
@@ -45,7 +46,9 @@ class ASP:
             cls.__calculate_mask = lambda p: create_mask(p, mask_calculator).bool()
         else:
             cls.__calculate_mask = mask_calculator
-        sparse_names = {torch.nn.Linear: ["weight"], torch.nn.Conv1d: ["weight"], torch.nn.Conv2d: ["weight"]}
+        sparse_names = {torch.nn.Linear: ["weight"], torch.nn.Conv1d: ["weight"], torch.nn.Conv2d: ["weight"], torch.nn.Conv3d: ["weight"],
+                        torch.nn.modules.linear.NonDynamicallyQuantizableLinear: ["weight"],
+                        torch.nn.MultiheadAttention: ["q_proj_weight", "k_proj_weight", "v_proj_weight", "in_proj_weight"]}
         if custom_layer_dict:
             sparse_names.update(custom_layer_dict)
             whitelist = tuple(whitelist) + tuple(custom_layer_dict.keys())

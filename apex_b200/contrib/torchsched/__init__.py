@@ -107,11 +107,11 @@ def torchsched(gm, example_inputs, **kwargs):
 
 def torchsched_compile(model=None, **kwargs):
     """``torch.compile`` with this backend preselected (reference torchsched/__init__.py:58-81)."""
-    kwargs.setdefault("backend", "torchsched")
+    kwargs.setdefault("backend", os.environ.get("TORCH_SCHED_DEFAULT_BACKEND", "torchsched"))
     return torch.compile(model, **kwargs) if model is not None else (lambda m: torch.compile(m, **kwargs))
 
 
-def get_backend(backend: str = "torchsched", scheme: str = "dwb"):
+def get_backend(backend: str = "torch", scheme: str = "dwb"):
     """``"torchsched"`` -> this package's backend callable; ``"torch"`` / ``"inductor"`` -> the stock Inductor backend name. ``scheme`` picks the
     order in which the reference splits convolution backward ("dwb" / "wbd", backend.py:262-330); backward is run by the autograd engine
     here, so it is validated and otherwise unused."""
@@ -128,9 +128,11 @@ def list_backends():
     return ["inductor", "torchsched"]
 
 
-def set_default_backend(name: str = "torchsched") -> None:
-    """The reference monkey-patches torch.compile's default backend (torchsched/__init__.py:44-81); here it is an explicit call."""
-    os.environ["TORCH_SCHED_DEFAULT_BACKEND"] = name
+def set_default_backend(backend: str = "torchsched") -> None:
+    """Backend :func:`torchsched_compile` uses when none is given (the reference also swaps it into ``torch.compile`` itself,
+    torchsched/__init__.py:44-81; here ``torch.compile`` is left alone)."""
+    assert backend in list_backends(), f"Unknown backend {backend}"
+    os.environ["TORCH_SCHED_DEFAULT_BACKEND"] = backend
 
 
 try:  # register so torch.compile(backend="torchsched") resolves
