@@ -154,7 +154,7 @@ class ASP:
 
     @classmethod
     def prune_trained_model(cls, model, optimizer):
-        cls.init_model_for_pruning(model, mask_calculator="m4n2_1d", verbosity=2, whitelist=(torch.nn.Linear, torch.nn.Conv2d),
+        cls.init_model_for_pruning(model, mask_calculator="m4n2_1d", verbosity=2, whitelist=(torch.nn.Linear, torch.nn.Conv2d, torch.nn.MultiheadAttention),
                                    allow_recompute_mask=False)
         cls.init_optimizer_for_pruning(optimizer)
         cls.compute_sparse_masks()
