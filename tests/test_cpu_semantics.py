@@ -215,3 +215,51 @@ def test_grad_scaler_skips_the_step_on_overflow(name):
         if it == 2:
             assert scaler.get_scale() == 1024.0    # grew to 2048 after two clean steps, halved by the overflow
     assert all(bool(torch.isfinite(p).all()) for p in model.parameters())
+
+
+def test_lamb_option_sweep_against_an_independent_oracle():
+    """FusedLAMB over adam_w_mode x use_nvlamb x grad_averaging x bias_correction x (clipping on / off) with two param groups: the gradient
+    norm is global over the groups, the trust ratio applies only where weight decay != 0 unless use_nvlamb (reference fused_lamb.py +
+    csrc/multi_tensor_lamb.cu semantics, written out independently here)."""
+    from apex_b200.optimizers import FusedLAMB
+
+    def oracle(groups, state, step, max_gn, adam_w, nvlamb, grad_avg, bias_corr):
+        gn = torch.sqrt(sum((g ** 2).sum() for grp in groups for g in grp["grads"]))
+        clip = max(float(gn) / max_gn, 1.0) if max_gn > 0 else 1.0
+        for grp in groups:
+            b1, b2 = grp["betas"]
+            b3 = 1 - b1 if grad_avg else 1.0
+            for p, g in zip(grp["params"], grp["grads"]):
+                st = state[id(p)]
+                g = g / clip
+                if not adam_w:
+                    g = g + grp["wd"] * p
+                st["m"] = b1 * st["m"] + b3 * g
+                st["v"] = b2 * st["v"] + (1 - b2) * g * g
+                c1, c2 = (1 - b1 ** step, 1 - b2 ** step) if bias_corr else (1.0, 1.0)
+                u = (st["m"] / c1) / ((st["v"] / c2).sqrt() + grp["eps"])
+                if adam_w:
+                    u = u + grp["wd"] * p
+                ratio = 1.0
+                if nvlamb or grp["wd"] != 0:
+                    pn, un = p.norm(), u.norm()
+                    ratio = float(pn / un) if (pn > 0 and un > 0) else 1.0
+                p -= grp["lr"] * ratio * u
+
+    for adam_w, nvlamb, grad_avg, bias_corr, max_gn in itertools.product([True, False], [False, True], [True, False], [True, False], [1.0, 0.0]):
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(37, 5)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(4, 4))]
+        qs = [p.detach().clone() for p in ps]
+        opt = FusedLAMB([{"params": ps[:2], "weight_decay": 0.01}, {"params": ps[2:], "weight_decay": 0.0, "lr": 3e-3, "betas": (0.8, 0.95)}], lr=1e-2,
+                        eps=1e-6, adam_w_mode=adam_w, use_nvlamb=nvlamb, grad_averaging=grad_avg, bias_correction=bias_corr, max_grad_norm=max_gn)
+        state = {id(q): {"m": torch.zeros_like(q), "v": torch.zeros_like(q)} for q in qs}
+        for step in range(1, 4):
+            gs = [torch.randn_like(p) * 3 for p in ps]
+            for p, g in zip(ps, gs):
+                p.grad = g.clone()
+            opt.step()
+            oracle([{"params": qs[:2], "grads": gs[:2], "wd": 0.01, "lr": 1e-2, "betas": (0.9, 0.999), "eps": 1e-6},
+                    {"params": qs[2:], "grads": gs[2:], "wd": 0.0, "lr": 3e-3, "betas": (0.8, 0.95), "eps": 1e-6}], state, step, max_gn, adam_w, nvlamb,
+                   grad_avg, bias_corr)
+        for p, q in zip(ps, qs):
+            torch.testing.assert_close(p.detach(), q, rtol=1e-4, atol=2e-5)
