@@ -88,7 +88,7 @@ def _table(lists, chunk_size) -> TensorTable:
         return lists
     if not _lib.available():
         raise _lib.gpu_required_error("multi_tensor_apply")
-    return TensorTable(lists, chunk_size)
+    return TensorTable(lists, chunk_size if chunk_size and chunk_size > 0 else 65536)   # optimizers pass 0 together with prebuilt tables
 
 
 def _empty(lists) -> bool:

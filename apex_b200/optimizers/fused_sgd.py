@@ -9,7 +9,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import BucketCache, partition_by_dtype
+from ._base import CHUNK, BucketCache, partition_by_dtype
 
 
 class _TableOptimizer(torch.optim.Optimizer):
@@ -127,7 +127,7 @@ class FusedSGD(_TableOptimizer):
                     args = (group["weight_decay"], group["momentum"], group["dampening"], group["lr"], group["nesterov"], first_run,
                             self.wd_after_momentum, 1.0 / self.most_recent_scale)
                     if is_cuda:
-                        amp_C.multi_tensor_sgd(0, None, target, *args)
+                        amp_C.multi_tensor_sgd(CHUNK, None, target, *args)   # CHUNK matters for the one-off list launches (tables carry their own)
                     else:
                         ref.multi_tensor_sgd(None, target, *args)
         self.most_recent_scale = 1.0
