@@ -111,3 +111,13 @@ def test_apex_alias_resolves_deep_imports_to_the_same_module_objects():
     assert FusedAdamSWA is same
     with pytest.raises(ImportError):
         importlib.import_module("apex.no_such_module")
+
+
+def test_info_cli_reports_the_build():
+    from apex_b200.__main__ import info
+
+    d = info()
+    assert d["version"] and d["declared_entry_points"] >= 50 and "APEX_B200_DIST_NVLS" in d["flags"]
+    if d["kernels_library"]:
+        experimental = 3   # ab_fmha_fwd, ab_fmha_bwd, ab_nvls_allreduce: only in APEX_B200_EXPERIMENTAL=1 builds
+        assert d["exported_entry_points"] >= d["declared_entry_points"] - experimental
