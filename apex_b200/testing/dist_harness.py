@@ -39,12 +39,25 @@ def run_distributed(fn, world_size: int, *args, backend: str | None = None, time
         procs = [ctx.Process(target=_entry, args=(r, world_size, backend, init_file, fn, args, errq), daemon=True) for r in range(world_size)]
         for p in procs:
             p.start()
-        for p in procs:
-            p.join(timeout)
+        # Poll instead of joining one by one: when a rank dies its peers usually sit in a collective until their own time-out, so the
+        # first failure ends the run after a short grace period (GPU box minutes are budgeted) and the overall deadline is a single one.
+        import time
+
+        deadline = time.monotonic() + timeout
+        failed_at = None
+        while any(p.is_alive() for p in procs):
+            now = time.monotonic()
+            if failed_at is None and any((not p.is_alive()) and p.exitcode != 0 for p in procs):
+                failed_at = now
+            if now > deadline or (failed_at is not None and now - failed_at > 10.0):
+                break
+            time.sleep(0.05)
         bad = [p for p in procs if p.is_alive() or p.exitcode != 0]
         for p in procs:
             if p.is_alive():
                 p.terminate()
+        for p in procs:
+            p.join(5.0)
         if bad:
             msg = ""
             while not errq.empty():

@@ -279,6 +279,13 @@ def group_batchnorm_spans_only_its_group(rank, world, device_type):
     torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
 
 
+def one_rank_raises_while_the_others_wait(rank, world, device_type):
+    """Harness behaviour under failure: rank 1 dies immediately, the others block in a collective."""
+    if rank == 1:
+        raise ValueError("deliberate failure on rank 1")
+    dist.barrier()
+
+
 from apex_b200.distributed_testing.distributed_test_base import GlooDistributedTestBase, distributed  # noqa: E402
 
 

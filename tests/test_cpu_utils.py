@@ -121,3 +121,15 @@ def test_info_cli_reports_the_build():
     if d["kernels_library"]:
         experimental = 3   # ab_fmha_fwd, ab_fmha_bwd, ab_nvls_allreduce: only in APEX_B200_EXPERIMENTAL=1 builds
         assert d["exported_entry_points"] >= d["declared_entry_points"] - experimental
+
+
+def test_dist_harness_fails_fast_with_the_failing_ranks_traceback():
+    import time
+
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match="deliberate failure on rank 1"):
+        run_distributed(cases.one_rank_raises_while_the_others_wait, 3, "cpu", backend="gloo", timeout=120.0)
+    assert time.monotonic() - t0 < 60.0   # first failure + grace period, not the peers' collective time-out
