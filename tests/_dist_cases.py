@@ -53,6 +53,39 @@ def dist_adam_matches_ddp_adamw(rank, world, device_type, fused, steps=4, clip=F
         torch.testing.assert_close(t, p.detach().float(), rtol=0, atol=0)
 
 
+def dist_adam_two_dimensional_grid(rank, world, device_type):
+    """distributed x redundant process-group grid (the reference's HSDP-like layout, distributed_fused_adam.py:477-560): state is sharded
+    inside each distributed group of 2 and replicated across the redundant groups; 4 ranks must still equal data-parallel AdamW over all 4."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    assert world == 4
+    dev = torch.device("cpu")
+    dgroups = [dist.new_group([0, 1]), dist.new_group([2, 3])]
+    rgroups = [dist.new_group([0, 2]), dist.new_group([1, 3])]
+    dg, rg = dgroups[rank // 2], rgroups[rank % 2]
+    ref_model = _model(dev)
+    model = copy.deepcopy(ref_model)
+    ref_opt = torch.optim.AdamW(ref_model.parameters(), lr=3e-3, weight_decay=0.05)
+    opt = DistributedFusedAdam(model.parameters(), lr=3e-3, weight_decay=0.05, device=dev, distributed_process_group=dg, redundant_process_group=rg,
+                               bucket_cap_mb=2048 * 4 * 2 / 2 ** 20)
+    assert (opt.distributed_size, opt.redundant_size) == (2, 2)
+    g = torch.Generator().manual_seed(100 + rank)
+    for it in range(3):
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        x = torch.randn(5, 7, generator=g)
+        ref_model(x).pow(2).mean().backward()
+        model(x).pow(2).mean().backward()
+        for p in ref_model.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        if it == 1:
+            torch.testing.assert_close(opt.clip_grad_norm(0.05), torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.05), rtol=1e-4, atol=1e-6)
+        ref_opt.step()
+        opt.step()
+        for pr, pd in zip(ref_model.parameters(), model.parameters()):
+            torch.testing.assert_close(pd, pr, rtol=1e-5, atol=1e-5)
+
+
 def dist_adam_state_dict_reshards(rank, world, device_type, tmpdir):
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")

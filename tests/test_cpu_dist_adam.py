@@ -185,3 +185,7 @@ def test_dist_lamb_global_scale_protocol_single_process():
     opt.step()
     for a, b in zip(params, before):
         assert torch.equal(a.detach(), b)
+
+
+def test_four_ranks_gloo_distributed_x_redundant_grid():
+    run_distributed(cases.dist_adam_two_dimensional_grid, 4, "cpu", backend="gloo")
