@@ -293,6 +293,13 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 keyed.setdefault((sd or self.dtype, gd, pd), []).append(p)
             for (sd, gd, pd), ps in keyed.items():
                 self._segments.append(_Segment(self, gi, ps, sd, gd, pd))
+        padded = sum(seg.padded for seg in self._segments)
+        # same check and wording as the reference (:1540-1549); a single bucket is already shrunk to its data, only its granule padding is left
+        if padded and any(seg.n_buckets > 1 for seg in self._segments) and sum(seg.numel for seg in self._segments) / padded < 0.7:
+            import warnings
+
+            warnings.warn(f"Only {sum(seg.numel for seg in self._segments) / padded:.1%} of buckets are used. "
+                          "Consider decreasing the bucket_cap_mb argument.")
         if self.fused_collectives and self.distributed_size > 1:
             from ...parallel.symmetric import SignalPad
 

@@ -189,3 +189,39 @@ def test_dist_lamb_global_scale_protocol_single_process():
 
 def test_four_ranks_gloo_distributed_x_redundant_grid():
     run_distributed(cases.dist_adam_two_dimensional_grid, 4, "cpu", backend="gloo")
+
+
+def test_bucket_low_utilization_warning_and_fp64_model():
+    """Reference test_dist_adam.py::test_bucket_low_utilization_warning / test_matches_pytorch_fp64 on the single-process path."""
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+
+    def count(total, cap_mb):
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            opt = DistributedFusedAdam([torch.nn.Parameter(torch.randn(total))], lr=1e-3, device="cpu", bucket_cap_mb=cap_mb)
+            opt.init_params()
+        return sum("Consider decreasing the bucket_cap_mb argument." in str(x.message) for x in w)
+
+    assert count(1_100_000, 4.0) == 1      # two 1M-element buckets, the second one 10 % full
+    assert count(1_000_000, 4.0) == 0
+    assert count(1_100_000, 100.0) == 0    # a cap larger than the data shrinks the bucket to fit
+    torch.manual_seed(0)
+    pa = [torch.nn.Parameter(torch.randn(300, dtype=torch.float64)), torch.nn.Parameter(torch.randn(7, 9, dtype=torch.float64))]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = DistributedFusedAdam(pa, lr=1e-2, weight_decay=0.1, device="cpu", dtype=torch.float32)
+    b = torch.optim.AdamW(pb, lr=1e-2, weight_decay=0.1)
+    for it in range(4):
+        g = torch.Generator().manual_seed(it)
+        a.zero_grad()
+        for x, y in zip(pa, pb):
+            x.grad = torch.randn(x.shape, generator=g, dtype=torch.float64)
+            y.grad = x.grad.clone()
+        a.step()
+        b.step()
+    for x, y in zip(pa, pb):
+        assert x.dtype == torch.float64
+        torch.testing.assert_close(x, y, rtol=1.3e-6, atol=1e-5)
