@@ -533,6 +533,16 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 _lib.fn("ab_mt_dist_adam")(*tb.head(), d[0], d[3], d[4], self._grad_scale.data_ptr(), float(group["lr"]), float(beta1),
                                            float(beta2), float(group["eps"]), int(step), mode, bc, float(group["weight_decay"]), 0, None,
                                            None, None, _lib.stream_ptr(self.device))
+        elif seg.remainders is not None:
+            # bf16 parameter + int16 remainder ARE the fp32 master: (hi << 16) + lo with a signed lo (hi was rounded to nearest)
+            hi, lo = out_shard.view(torch.int16).to(torch.int32), seg.remainders.to(torch.int32)
+            master = ((hi << 16) + lo).view(torch.float32).clone()
+            ref.dist_adam(master, seg.exp_avg, seg.exp_avg_sq, seg.reduced, None, self._grad_scale, group["lr"], beta1, beta2, group["eps"], step,
+                          mode, bc, group["weight_decay"])
+            bits = master.view(torch.int32)
+            new_lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
+            seg.remainders.copy_(new_lo.to(torch.int16))
+            out_shard.view(torch.int16).copy_(((bits - new_lo) >> 16).to(torch.int16))
         else:
             p_in = seg.master if seg.master is not None else out_shard
             ref.dist_adam(p_in, seg.exp_avg, seg.exp_avg_sq, seg.reduced, out_shard, self._grad_scale, group["lr"], beta1, beta2,

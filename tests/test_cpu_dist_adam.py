@@ -225,3 +225,34 @@ def test_bucket_low_utilization_warning_and_fp64_model():
     for x, y in zip(pa, pb):
         assert x.dtype == torch.float64
         torch.testing.assert_close(x, y, rtol=1.3e-6, atol=1e-5)
+
+
+def test_param_remainders_keep_an_exact_fp32_master():
+    """store_param_remainders: bf16 parameter + int16 remainder is the fp32 master, so after several steps the bf16 parameters equal the
+    ROUNDED parameters of an fp32 AdamW run (to one bf16 ulp at rounding ties) instead of drifting like a bf16-only update
+    (reference test_dist_adam.py::test_matches_pytorch_bf16_param_remainders), across several buckets."""
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    pa = [torch.nn.Parameter(torch.randn(300).bfloat16()), torch.nn.Parameter(torch.randn(5000).bfloat16())]
+    pb = [torch.nn.Parameter(p.detach().float().clone()) for p in pa]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = DistributedFusedAdam(pa, lr=1e-2, weight_decay=0.1, device="cpu", dtype=torch.float32, grad_sync_dtype=torch.float32,
+                                 param_sync_dtype=torch.bfloat16, store_params=False, store_param_remainders=True, bucket_cap_mb=0.008)
+    b = torch.optim.AdamW(pb, lr=1e-2, weight_decay=0.1)
+    for it in range(6):
+        g = torch.Generator().manual_seed(it)
+        a.zero_grad()
+        for x, y in zip(pa, pb):
+            grad = torch.randn(x.shape, generator=g).bfloat16()
+            x.grad, y.grad = grad.clone(), grad.float()
+        a.step()
+        b.step()
+    assert a._segments[0].n_buckets > 1
+    for x, y in zip(pa, pb):
+        want = y.detach().bfloat16().float()
+        ulp = torch.maximum(want.abs(), torch.tensor(2.0 ** -126)).log2().floor().exp2() * 2.0 ** -7
+        assert bool(((x.detach().float() - want).abs() <= ulp).all())
+        assert float(((x.detach().float() - want).abs() > 0).float().mean()) < 0.02   # ties only
