@@ -666,7 +666,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             for p, off in zip(seg.params, seg.offsets):
                 n = p.numel()
                 ent = {k: v[off:off + n].view(p.shape).cpu() for k, v in fulls.items()}
-                if "param" not in ent:
+                if "param_remainder" in ent:
+                    # the checkpoint holds the exact fp32 master: (bf16 bits << 16) + signed remainder (reference :3472-3477 does the same)
+                    hi = seg.param_buf[off:off + n].view(torch.int16).to(torch.int32)
+                    lo = fulls["param_remainder"][off:off + n].to(torch.int32)
+                    ent["param"] = ((hi << 16) + lo).view(torch.float32).view(p.shape).cpu()
+                elif "param" not in ent:
                     ent["param"] = self._param_view[id(p)].detach().float().cpu()
                 ent["step"] = self.param_groups[seg.group_idx].get("step", 0)
                 state[index[id(p)]] = ent
@@ -707,10 +712,13 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 if seg.master is not None:
                     seg.master.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["param"]))
             if seg.remainders is not None:
-                bits = seg.shard_view(pfull).contiguous().view(-1).view(torch.int32)
-                lo = (bits & 0xFFFF).to(torch.int32)
-                seg.remainders.copy_(torch.where(lo >= 32768, lo - 65536, lo).to(torch.int16))
-            seg.param_buf.copy_(pfull.to(seg.param_dtype))
+                # split the fp32 master with the SAME convention as the step kernel: signed low half, high half = (bits - lo) >> 16
+                bits = pfull.view(torch.int32)
+                lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
+                seg.remainders.copy_(seg.shard_view(lo).contiguous().view(-1).to(torch.int16))
+                seg.param_buf.view(torch.int16).copy_(((bits - lo) >> 16).to(torch.int16))
+            else:
+                seg.param_buf.copy_(pfull.to(seg.param_dtype))
             for p in seg.params:
                 if p.dtype != seg.param_dtype:
                     p.data.copy_(self._param_view[id(p)].to(p.dtype))

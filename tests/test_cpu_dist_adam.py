@@ -256,3 +256,44 @@ def test_param_remainders_keep_an_exact_fp32_master():
         ulp = torch.maximum(want.abs(), torch.tensor(2.0 ** -126)).log2().floor().exp2() * 2.0 ** -7
         assert bool(((x.detach().float() - want).abs() <= ulp).all())
         assert float(((x.detach().float() - want).abs() > 0).float().mean()) < 0.02   # ties only
+
+
+@pytest.mark.parametrize("config", ["remainders", "scaled_states", "bf16_params_fp32_master", "many_buckets"])
+def test_checkpoint_resume_is_exact_for_every_state_layout(config):
+    """state_dict -> a FRESH optimizer (parameters restored from the checkpoint alone) -> continue == uninterrupted run, for the parameter
+    remainder, scaled 16-bit state, fp32-master and multi-bucket layouts (reference test_dist_adam.py::test_checkpoint*)."""
+    import copy
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    kw = {"remainders": dict(dtype=torch.float32, grad_sync_dtype=torch.float32, param_sync_dtype=torch.bfloat16, store_params=False,
+                             store_param_remainders=True, bucket_cap_mb=0.008),
+          "scaled_states": dict(dtype=torch.bfloat16, with_scaled_states=True), "bf16_params_fp32_master": dict(dtype=torch.float32),
+          "many_buckets": dict(bucket_cap_mb=0.008)}[config]
+    dt = torch.float32 if config == "many_buckets" else torch.bfloat16
+
+    def fresh(seed):
+        torch.manual_seed(seed)
+        ps = [torch.nn.Parameter(torch.randn(300).to(dt)), torch.nn.Parameter(torch.randn(5000).to(dt))]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return ps, DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.1, device="cpu", **kw)
+
+    def run(ps, opt, its):
+        for it in its:
+            g = torch.Generator().manual_seed(it)
+            opt.zero_grad()
+            for p in ps:
+                p.grad = torch.randn(p.shape, generator=g).to(dt)
+            opt.step()
+
+    ps, opt = fresh(0)
+    run(ps, opt, range(6))
+    pa, oa = fresh(0)
+    run(pa, oa, range(3))
+    sd = copy.deepcopy(oa.state_dict())
+    pb, ob = fresh(123)          # different initial values: everything must come from the checkpoint
+    ob.load_state_dict(sd)
+    run(pb, ob, range(3, 6))
+    for got, want in zip(pb, ps):
+        torch.testing.assert_close(got, want, rtol=0, atol=0)
