@@ -638,9 +638,10 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         sh = shard.view(seg.n_buckets, seg.shard_elems)
         if D == 1:
             return sh.reshape(-1).clone()
-        parts = [torch.empty_like(sh) for _ in range(D)]
-        dist.all_gather(parts, sh.contiguous(), group=self.distributed_process_group)
-        return torch.stack(parts, dim=1).reshape(-1)
+        raw = sh.contiguous().view(torch.uint8)   # a pure data move: bytes work for every dtype on every backend (NCCL and gloo lack int16)
+        parts = [torch.empty_like(raw) for _ in range(D)]
+        dist.all_gather(parts, raw, group=self.distributed_process_group)
+        return torch.stack([p.view(shard.dtype) for p in parts], dim=1).reshape(-1)
 
     def state_dict(self, *args, **kwargs):
         """Every rank returns the same dict: per-parameter full-size CPU tensors (param master, exp_avg, exp_avg_sq), independent

@@ -122,6 +122,51 @@ def dist_adam_state_dict_reshards(rank, world, device_type, tmpdir):
     assert sd["state"][0]["exp_avg"].shape == (7, 7)
 
 
+def dist_adam_checkpoint_moves_between_world_sizes(rank, world, device_type, layout):
+    """Save on ``world`` ranks, load into a ONE-rank optimizer and into a fresh ``world``-rank optimizer, continue all three on the same data
+    (every rank sees identical batches, so the averaged gradient is the single-rank gradient): parameters must stay identical
+    (reference test_dist_adam.py::test_checkpoint_save_1gpu / test_checkpoint_load_1gpu, for the fp32-master and parameter-remainder layouts)."""
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    dt = torch.bfloat16 if layout == "remainders" else torch.float32
+    kw = dict(dtype=torch.float32, grad_sync_dtype=torch.float32, param_sync_dtype=torch.bfloat16, store_params=False, store_param_remainders=True) \
+        if layout == "remainders" else {}
+    solo_pg = dist.new_group(ranks=[0])
+
+    def make(pg, cap_world):
+        m = _model(dev).to(dt)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = DistributedFusedAdam(m.parameters(), lr=1e-2, weight_decay=0.05, device=dev, process_group=pg,
+                                     bucket_cap_mb=2048 * 4 * cap_world / 2 ** 20, fused_collectives=False, **kw)
+        return m, o
+
+    def steps(m, o, seeds):
+        for sd_ in seeds:
+            o.zero_grad()
+            x = torch.randn(5, 7, generator=torch.Generator().manual_seed(sd_)).to(dev, dt)
+            m(x).float().pow(2).mean().backward()
+            o.step()
+
+    model, opt = make(None, world)
+    steps(model, opt, range(3))
+    ck = opt.state_dict()                         # identical on every rank, independent of the world size
+    again, opt_again = make(None, world)
+    opt_again.load_state_dict(ck)
+    steps(model, opt, range(3, 6))
+    steps(again, opt_again, range(3, 6))
+    for a, b in zip(again.parameters(), model.parameters()):
+        torch.testing.assert_close(a, b, rtol=0, atol=0)
+    if rank == 0:
+        solo, opt_solo = make(solo_pg, 1)
+        opt_solo.load_state_dict(ck)
+        steps(solo, opt_solo, range(3, 6))
+        for a, b in zip(solo.parameters(), model.parameters()):
+            torch.testing.assert_close(a.float(), b.float(), rtol=1e-6, atol=1e-6)
+
+
 def dist_adam_grad_scaler_skips_on_inf(rank, world, device_type):
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank)

@@ -297,3 +297,8 @@ def test_checkpoint_resume_is_exact_for_every_state_layout(config):
     run(pb, ob, range(3, 6))
     for got, want in zip(pb, ps):
         torch.testing.assert_close(got, want, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("layout", ["fp32_master", "remainders"])
+def test_two_ranks_gloo_checkpoint_moves_between_world_sizes(layout):
+    run_distributed(cases.dist_adam_checkpoint_moves_between_world_sizes, 2, "cpu", layout, backend="gloo")
