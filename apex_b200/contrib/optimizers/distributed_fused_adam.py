@@ -121,7 +121,11 @@ class _Segment:
         """value (fp32) -> 16-bit state with a fresh per-fragment scale = absmax / largest finite value of the state dtype."""
         t = {"param": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}[key]
         amax = torch.zeros_like(self.scales[key]).scatter_reduce_(0, self.frag_index, value.abs(), "amax", include_self=True)
-        sc = torch.where(amax > 0, amax / torch.finfo(t.dtype).max, torch.ones_like(amax))
+        # scale = absmax / largest finite value, floored at the smallest NORMAL fp32: for bf16 (fp32's exponent range) the quotient is
+        # subnormal below absmax ~ 4 and underflows to zero below ~5e-7 (second moments get there), which would turn the division below
+        # into inf / nan; with the floor the stored values still fit (|value| / scale <= max) and the scale keeps its full mantissa.
+        # (The reference divides by max / 2 and zeroes the state when the scale underflows, :2834-2860.)
+        sc = torch.where(amax > 0, (amax / torch.finfo(t.dtype).max).clamp_(min=torch.finfo(torch.float32).tiny), torch.ones_like(amax))
         self.scales[key].copy_(sc)
         t.copy_((value / sc[self.frag_index]).to(t.dtype))
 

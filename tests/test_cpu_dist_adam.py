@@ -302,3 +302,30 @@ def test_checkpoint_resume_is_exact_for_every_state_layout(config):
 @pytest.mark.parametrize("layout", ["fp32_master", "remainders"])
 def test_two_ranks_gloo_checkpoint_moves_between_world_sizes(layout):
     run_distributed(cases.dist_adam_checkpoint_moves_between_world_sizes, 2, "cpu", layout, backend="gloo")
+
+
+def test_scaled_states_survive_tiny_second_moments():
+    """with_scaled_states and gradients ~1e-6: exp_avg_sq ~1e-15, whose per-fragment scale absmax / bf16.max underflows fp32 (it used to become
+    0 and the re-quantisation produced inf / nan on the next step). The run must stay finite and track fp32 AdamW."""
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    pa = [torch.nn.Parameter(torch.randn(300).bfloat16()), torch.nn.Parameter(torch.randn(40, 9).bfloat16())]
+    pb = [torch.nn.Parameter(p.detach().float().clone()) for p in pa]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = DistributedFusedAdam(pa, lr=1e-3, weight_decay=0.0, device="cpu", dtype=torch.bfloat16, with_scaled_states=True)
+    b = torch.optim.AdamW(pb, lr=1e-3, weight_decay=0.0)
+    for it in range(5):
+        g = torch.Generator().manual_seed(it)
+        a.zero_grad()
+        for x, y in zip(pa, pb):
+            grad = (torch.randn(x.shape, generator=g) * 1e-6).bfloat16()
+            x.grad, y.grad = grad.clone(), grad.float()
+        a.step()
+        b.step()
+    seg = a._segments[0]
+    assert all(bool(torch.isfinite(t.float()).all()) for t in (seg.master, seg.exp_avg, seg.exp_avg_sq)) and all(bool((v > 0).all()) for v in seg.scales.values())
+    for x, y in zip(pa, pb):
+        torch.testing.assert_close(x.detach().float(), y.detach(), rtol=2e-2, atol=2e-2)
