@@ -432,6 +432,29 @@ def ddp_reduces_when_some_parameters_get_no_gradient(rank, world, device_type, d
             assert net.unused.weight.grad is None
 
 
+def reducer_averages_gradients_and_broadcasts_parameters(rank, world, device_type):
+    """``Reducer``: construction broadcasts rank 0's parameters, ``reduce()`` averages the gradients (module form and tensor-list form,
+    mixed dtypes through one flat buffer per dtype)."""
+    from apex_b200.parallel import Reducer
+    torch.manual_seed(rank)                                  # different initial weights on purpose
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    red = Reducer(net)
+    for p in net.parameters():
+        t = p.detach().clone()
+        dist.broadcast(t, src=0)
+        torch.testing.assert_close(p.detach(), t, rtol=0, atol=0)
+    net(torch.full((2, 4), float(rank + 1))).sum().backward()
+    mine = [p.grad.clone() for p in net.parameters()]
+    red.reduce()
+    for p, g in zip(net.parameters(), mine):
+        dist.all_reduce(g)
+        torch.testing.assert_close(p.grad, g / world)
+    tensors = [torch.full((3,), float(rank)), torch.full((2, 2), float(rank), dtype=torch.float64)]
+    Reducer(tensors).reduce()
+    for t in tensors:
+        torch.testing.assert_close(t, torch.full_like(t, sum(range(world)) / world))
+
+
 def ddp_race_condition(rank, world, device_type):
     """Race detector by construction (reference tests/distributed/DDP/ddp_race_condition_test.py:27-78): two large parameters,
     message_size=1 (a bucket per parameter), several all-reduce streams, gradients with a closed form checked every iteration."""

@@ -35,3 +35,7 @@ def test_group_batchnorm_four_ranks_gloo():
 @pytest.mark.parametrize("delay", [False, True])
 def test_ddp_unused_parameters_gloo(delay):
     run_distributed(cases.ddp_reduces_when_some_parameters_get_no_gradient, 2, "cpu", delay, backend="gloo")
+
+
+def test_reducer_gloo():
+    run_distributed(cases.reducer_averages_gradients_and_broadcasts_parameters, 3, "cpu", backend="gloo")
