@@ -401,6 +401,54 @@ def ddp_matches_manual_allreduce(rank, world, device_type, delay, message_size, 
             torch.testing.assert_close(p.grad, want / world, rtol=1e-5, atol=1e-6)
 
 
+def ddp_option_matrix(rank, world, device_type):
+    """DistributedDataParallel options of the reference API: allreduce_always_fp32 + retain_allreduce_buffers on a bf16 model,
+    gradient_average=False (sums), allreduce_trigger_params (flush exactly at the named parameters), disable / enable_allreduce."""
+    from apex_b200.parallel import DistributedDataParallel
+
+    def nets(dtype=torch.float32):
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4)).to(dtype)
+        return net, copy.deepcopy(net)
+
+    def check(net, ref, ddp, x, scale, tol):
+        for m in (net, ref):
+            m.zero_grad()
+        ddp(x).float().pow(2).sum().backward()
+        ref(x).float().pow(2).sum().backward()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            want = q.grad.float().clone()
+            dist.all_reduce(want)
+            torch.testing.assert_close(p.grad.float(), want * scale, rtol=tol, atol=tol)
+
+    g = torch.Generator().manual_seed(10 + rank)
+    # bf16 gradients reduced in fp32, the flat buffers kept for inspection
+    net, ref = nets(torch.bfloat16)
+    ddp = DistributedDataParallel(net, allreduce_always_fp32=True, retain_allreduce_buffers=True, message_size=40)
+    check(net, ref, ddp, torch.randn(4, 6, generator=g).bfloat16(), 1.0 / world, 2e-2)
+    assert ddp.allreduce_buffers and all(b.dtype == torch.float32 for b in ddp.allreduce_buffers)
+    assert sum(b.numel() for b in ddp.allreduce_buffers) == sum(p.numel() for p in net.parameters())
+    # sums instead of averages
+    net, ref = nets()
+    check(net, ref, DistributedDataParallel(net, gradient_average=False), torch.randn(4, 6, generator=g), 1.0, 1e-5)
+    # buckets close exactly when a trigger parameter's gradient arrives
+    net, ref = nets()
+    ddp = DistributedDataParallel(net, allreduce_trigger_params=[net[2].weight, net[0].weight], retain_allreduce_buffers=True)
+    check(net, ref, ddp, torch.randn(4, 6, generator=g), 1.0 / world, 1e-5)
+    assert len(ddp.allreduce_buffers) >= 2
+    # disable_allreduce: gradients stay local until it is enabled again
+    net, ref = nets()
+    ddp = DistributedDataParallel(net)
+    ddp.disable_allreduce()
+    x = torch.randn(4, 6, generator=g)
+    ddp(x).pow(2).sum().backward()
+    ref(x).pow(2).sum().backward()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        torch.testing.assert_close(p.grad, q.grad)
+    ddp.enable_allreduce()
+    check(net, ref, ddp, torch.randn(4, 6, generator=g), 1.0 / world, 1e-5)
+
+
 def ddp_reduces_when_some_parameters_get_no_gradient(rank, world, device_type, delay):
     """A parameter that does not take part in the backward never fires its hook; the buckets that did fill must still be all-reduced
     (end-of-backward callback), for both the overlapped and the delayed mode, and on consecutive iterations."""

@@ -39,3 +39,7 @@ def test_ddp_unused_parameters_gloo(delay):
 
 def test_reducer_gloo():
     run_distributed(cases.reducer_averages_gradients_and_broadcasts_parameters, 3, "cpu", backend="gloo")
+
+
+def test_ddp_option_matrix_gloo():
+    run_distributed(cases.ddp_option_matrix, 2, "cpu", backend="gloo")
