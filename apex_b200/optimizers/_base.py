@@ -74,3 +74,20 @@ def use_native(params) -> bool:
     if any_cuda and not _lib.available():
         raise _lib.gpu_required_error("fused optimizer")
     return any_cuda
+
+
+def restore_fp32_state(optimizer, state_dict, keys=("exp_avg", "exp_avg_sq")) -> None:
+    """``torch.optim.Optimizer.load_state_dict`` casts every floating-point state tensor to the dtype of its parameter; moments kept in fp32
+    for 16-bit parameters would be rounded on every resume. Re-install them from the checkpoint at full precision."""
+    by_index = {}
+    for group, saved in zip(optimizer.param_groups, state_dict["param_groups"]):
+        for p, idx in zip(group["params"], saved["params"]):
+            by_index[idx] = p
+    for idx, st in state_dict["state"].items():
+        p = by_index.get(idx)
+        if p is None:
+            continue
+        for k in keys:
+            v = st.get(k)
+            if torch.is_tensor(v) and v.is_floating_point():
+                optimizer.state[p][k] = v.detach().to(device=p.device, dtype=torch.float32).clone()

@@ -12,7 +12,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import BucketCache, flat_state_like, partition_by_dtype
+from ._base import BucketCache, flat_state_like, partition_by_dtype, restore_fp32_state
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -52,13 +52,29 @@ class FusedAdam(torch.optim.Optimizer):
             else:
                 self.param_groups_master.append({"params": [None for _ in self.param_groups[-1]["params"]]})
 
+    def state_dict(self):
+        """torch's optimizer state plus, with ``master_weights``, the fp32 master copies under ``"master_params"`` (the reference keeps them out
+        of the checkpoint and re-derives them from the rounded model weights on resume, which is lossy)."""
+        sd = super().state_dict()
+        if self.master_weights:
+            sd["master_params"] = [[None if m is None else m.detach().clone() for m in g["params"]] for g in self.param_groups_master]
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         # torch casts loaded state to the parameter dtype; the kernels keep fp32 moments for every parameter dtype.
+        restore_fp32_state(self, state_dict)
         for st in self.state.values():
             for k in ("exp_avg", "exp_avg_sq"):
                 if k in st and st[k].dtype != torch.float32:
                     st[k] = st[k].float()
+        masters = state_dict.get("master_params")
+        if masters is not None and self.master_weights:
+            with torch.no_grad():
+                for g, saved in zip(self.param_groups_master, masters):
+                    for m, s_ in zip(g["params"], saved):
+                        if m is not None and s_ is not None:
+                            m.copy_(s_)
         self._cache.clear()
 
     def zero_grad(self, set_to_none: bool | None = None):

@@ -12,7 +12,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import BucketCache, partition_by_dtype
+from ._base import BucketCache, partition_by_dtype, restore_fp32_state
 
 
 def _global_grad_norm(tables, cpu_grads, device):
@@ -144,15 +144,34 @@ class FusedMixedPrecisionLamb(torch.optim.Optimizer):
         self._dummy_overflow_buf = torch.zeros(1, dtype=torch.int, device=device)
         self._cache = BucketCache()
 
+    def state_dict(self):
+        """torch's optimizer state plus the fp32 master parameters under ``"master_params"`` once they exist (the reference re-derives them
+        from the rounded model weights on resume, which is lossy)."""
+        sd = super().state_dict()
+        if self.param_groups_full_precision:
+            sd["master_params"] = [[None if m is None else m.detach().clone() for m in g["params"]] for g in self.param_groups_full_precision]
+        return sd
+
     def load_state_dict(self, state_dict):
         # lr/step are tensors: keep them as device tensors after a reload (reference :73-138)
         super().load_state_dict(state_dict)
+        masters = state_dict.get("master_params")
+        if masters is not None:
+            if len(self.param_groups_full_precision) == 0:
+                self._setup_full_precision_params()
+            with torch.no_grad():
+                for g, saved in zip(self.param_groups_full_precision, masters):
+                    for m, s_ in zip(g["params"], saved):
+                        if m is not None and s_ is not None:
+                            m.copy_(s_)
         device = self.param_groups[0]["params"][0].device
         for group in self.param_groups:
             for k, dt in (("lr", torch.float32), ("step", torch.int)):
                 v = group[k]
                 group[k] = (v if torch.is_tensor(v) else torch.tensor(v)).to(device=device, dtype=dt).reshape(-1)[:1].clone() \
                     if k == "step" else (v if torch.is_tensor(v) else torch.tensor(v)).to(device=device, dtype=dt)
+        if self.reduced_precision_dtype is not None:
+            restore_fp32_state(self, state_dict)
         for st in self.state.values():
             for k in ("exp_avg", "exp_avg_sq"):
                 if k in st and self.reduced_precision_dtype is not None and st[k].dtype != torch.float32:

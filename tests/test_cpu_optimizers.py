@@ -233,3 +233,43 @@ def test_fused_sgd_parameters_whose_first_gradient_arrives_late(momentum, dampen
             b.step()
         for x, y in zip(pa, pb):
             torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["adam_bf16_params", "adam_capturable_master_bf16", "mixed_precision_lamb_bf16"])
+def test_checkpoint_resume_is_exact_with_16_bit_parameters(name):
+    """fp32 moments and fp32 master weights of 16-bit parameters must come back at full precision: torch's load_state_dict casts state to the
+    parameter dtype, and the reference keeps master weights out of the checkpoint — both made a resumed run drift by bf16 ulps."""
+    import copy
+
+    from apex_b200.optimizers import FusedMixedPrecisionLamb
+
+    def fresh():
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(70).bfloat16()), torch.nn.Parameter(torch.randn(3, 5).bfloat16())]
+        if name == "adam_bf16_params":
+            return ps, FusedAdam(ps, lr=1e-2, weight_decay=0.01)
+        if name == "adam_capturable_master_bf16":
+            return ps, FusedAdam(ps, lr=1e-2, weight_decay=0.01, capturable=True, master_weights=True)
+        return ps, FusedMixedPrecisionLamb(ps, lr=1e-2, weight_decay=0.01, reduced_precision_dtype=torch.bfloat16)
+
+    def run(ps, opt, its):
+        for it in its:
+            g = torch.Generator().manual_seed(it)
+            opt.zero_grad()
+            for p in ps:
+                p.grad = (torch.randn(p.shape, generator=g) * (it + 1)).bfloat16()
+            opt.step()
+
+    ps, opt = fresh()
+    run(ps, opt, range(6))
+    pa, oa = fresh()
+    run(pa, oa, range(3))
+    sd = copy.deepcopy(oa.state_dict())
+    pb, ob = fresh()
+    with torch.no_grad():
+        for dst, src in zip(pb, pa):
+            dst.copy_(src)
+    ob.load_state_dict(sd)
+    run(pb, ob, range(3, 6))
+    for got, want in zip(pb, ps):
+        torch.testing.assert_close(got, want, rtol=0, atol=0)
