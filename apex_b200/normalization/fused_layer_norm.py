@@ -159,6 +159,22 @@ def supports_custom_op() -> bool:
     return hasattr(torch.library, "custom_op")
 
 
+def _compiled_cuda(input) -> bool:
+    """While ``torch.compile`` traces a CUDA graph the modules call the ``apex_b200::norm_fwd / norm_bwd`` custom ops (custom_ops.py): the fused
+    kernels stay in the compiled graph as opaque nodes (what the reference's ``apex::fused_layer_norm_affine_fwd`` ops are for)."""
+    return torch.compiler.is_compiling() and input.is_cuda and input.dtype != torch.float64 and supports_custom_op()
+
+
+def _custom_op_norm(input, weight, bias, normalized_shape, eps, rms, mixed):
+    from . import custom_ops
+
+    if mixed or weight is None:
+        x = _cast_if_autocast_enabled(input)[0]
+    else:
+        x, weight, bias = _cast_if_autocast_enabled(input, weight, bias)
+    return custom_ops.norm(x, weight, bias, _shape(normalized_shape), eps, rms=rms, mixed=mixed)
+
+
 def _use_fallback(input) -> bool:
     return (torch.jit.is_tracing() or torch.jit.is_scripting() or torch.compiler.is_compiling() or not input.is_cuda
             or input.dtype == torch.float64)
@@ -185,6 +201,8 @@ class FusedLayerNorm(torch.nn.Module):
             init.zeros_(self.bias)
 
     def forward(self, input):
+        if _compiled_cuda(input):
+            return _custom_op_norm(input, self.weight, self.bias, self.normalized_shape, self.eps, False, False)
         if _use_fallback(input):
             return F.layer_norm(input, self.normalized_shape, self.weight, self.bias, self.eps)
         if self.elementwise_affine:
@@ -213,6 +231,8 @@ class FusedRMSNorm(torch.nn.Module):
             init.ones_(self.weight)
 
     def forward(self, input):
+        if _compiled_cuda(input):
+            return _custom_op_norm(input, self.weight, None, self.normalized_shape, self.eps, True, False)
         if _use_fallback(input):
             return manual_rms_norm(input, self.normalized_shape, self.weight, self.eps)
         if self.elementwise_affine:
@@ -236,6 +256,8 @@ class MixedFusedLayerNorm(FusedLayerNorm):
         super().__init__(normalized_shape=normalized_shape, eps=eps, elementwise_affine=True, memory_efficient=memory_efficient)
 
     def forward(self, input):
+        if _compiled_cuda(input):
+            return _custom_op_norm(input, self.weight, self.bias, self.normalized_shape, self.eps, False, True)
         if _use_fallback(input):
             return F.layer_norm(input, self.normalized_shape, self.weight, self.bias, self.eps)
         return mixed_dtype_fused_layer_norm_affine(input, self.weight, self.bias, self.normalized_shape, self.eps, self.memory_efficient)
@@ -252,6 +274,8 @@ class MixedFusedRMSNorm(FusedRMSNorm):
         super().__init__(normalized_shape=normalized_shape, eps=eps, elementwise_affine=True, memory_efficient=memory_efficient)
 
     def forward(self, input):
+        if _compiled_cuda(input):
+            return _custom_op_norm(input, self.weight, None, self.normalized_shape, self.eps, True, True)
         if _use_fallback(input):
             return manual_rms_norm(input, self.normalized_shape, self.weight, self.eps)
         return mixed_dtype_fused_rms_norm_affine(input, self.weight, self.normalized_shape, self.eps, self.memory_efficient)

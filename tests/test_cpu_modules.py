@@ -464,3 +464,66 @@ def test_bottleneck_scale_bias_callable():
         torch.testing.assert_close(m(x), y0)          # stale on purpose until refreshed
         refresh()
         assert not torch.allclose(m(x), y0)
+
+
+def test_norm_custom_ops_numerics_opcheck_and_fullgraph_compile(monkeypatch):
+    """apex_b200::norm_fwd / norm_bwd (normalization/custom_ops.py): values and gradients against torch, torch.library.opcheck (schema, fake
+    implementation, autograd registration, AOT dispatch), a fullgraph torch.compile, and the modules' compile-time route (forced on for CPU
+    tensors here; on a GPU it is taken whenever a CUDA graph is being compiled)."""
+    from apex_b200.normalization import FusedLayerNorm, FusedRMSNorm, custom_ops as C
+    import importlib
+
+    M = importlib.import_module("apex_b200.normalization.fused_layer_norm")   # the package re-exports a function of the same name
+    torch.manual_seed(0)
+    x, w, b = torch.randn(6, 4, 8, requires_grad=True), torch.randn(8, requires_grad=True), torch.randn(8, requires_grad=True)
+    g = torch.randn(6, 4, 8)
+    cases = [(C.norm(x, w, b, (8,), 1e-5), F.layer_norm(x, (8,), w, b, 1e-5), (x, w, b)),
+             (C.norm(x, w, None, (8,), 1e-5, rms=True), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w, (x, w)),
+             (C.norm(x, None, None, (4, 8), 1e-5), F.layer_norm(x, (4, 8), None, None, 1e-5), (x,))]
+    for got, want, leaves in cases:
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+        for a, r in zip(torch.autograd.grad(got, leaves, g), torch.autograd.grad(want, leaves, g)):
+            torch.testing.assert_close(a, r, rtol=1e-4, atol=1e-5)
+    y, mean, invvar = C.reference_fwd(x.detach(), (8,), w.detach(), b.detach(), 1e-5, False, torch.float32)
+    plain = C.reference_bwd(g, x.detach(), mean, invvar, (8,), w.detach(), b.detach(), False, False, torch.float32)
+    from_output = C.reference_bwd(g, y, None, invvar, (8,), w.detach(), b.detach(), False, True, torch.float32)   # memory-efficient: x-hat from y
+    for a, r in zip(plain, from_output):
+        torch.testing.assert_close(a, r, rtol=1e-4, atol=1e-5)
+    for args in [(x.detach().requires_grad_(), w.detach().requires_grad_(), b.detach().requires_grad_(), [8], 1e-5, False, False),
+                 (x.detach().requires_grad_(), w.detach().requires_grad_(), None, [8], 1e-5, True, False)]:
+        assert set(torch.library.opcheck(C.norm_fwd_op, args).values()) == {"SUCCESS"}
+    monkeypatch.setattr(M, "_compiled_cuda", lambda t: torch.compiler.is_compiling())
+    net = torch.nn.Sequential(torch.nn.Linear(8, 8), FusedLayerNorm(8), torch.nn.Tanh(), FusedRMSNorm(8))
+    compiled = torch.compile(net, backend="aot_eager", fullgraph=True)   # fullgraph: the custom ops do not break the graph
+    xin = torch.randn(5, 8, requires_grad=True)
+    out, want = compiled(xin), net(xin)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(torch.autograd.grad(out.sum(), xin)[0], torch.autograd.grad(want.sum(), xin)[0], rtol=1e-4, atol=1e-5)
+
+
+def test_group_norm_custom_ops(monkeypatch):
+    """apex_b200::group_norm_nhwc_fprop / _bprop: values and gradients (with and without SiLU) against torch, opcheck, and the module's
+    compile-time route under a fullgraph torch.compile."""
+    import importlib
+
+    M = importlib.import_module("apex_b200.contrib.group_norm.group_norm")
+    torch.manual_seed(0)
+    for act in ("silu", ""):
+        x = torch.randn(2, 8, 3, 3).contiguous(memory_format=torch.channels_last).requires_grad_()
+        w, b = torch.randn(8, requires_grad=True), torch.randn(8, requires_grad=True)
+        y = M.group_norm_nhwc_fprop_op(x, 4, w, b, 1e-5, act)[0]
+        ref = F.group_norm(x, 4, w, b, 1e-5)
+        ref = F.silu(ref) if act else ref
+        g = torch.randn_like(y)
+        torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-5)
+        for a, r in zip(torch.autograd.grad(y, (x, w, b), g), torch.autograd.grad(ref, (x, w, b), g)):
+            torch.testing.assert_close(a, r, rtol=1e-4, atol=1e-5)
+    args = (x.detach().requires_grad_(), 4, w.detach().requires_grad_(), b.detach().requires_grad_(), 1e-5, "silu")
+    assert set(torch.library.opcheck(M.group_norm_nhwc_fprop_op, args).values()) == {"SUCCESS"}
+    monkeypatch.setattr(M, "_compiled_cuda", lambda t: torch.compiler.is_compiling())
+    net = torch.nn.Sequential(torch.nn.Conv2d(8, 8, 1), M.GroupNorm(4, 8, act="silu")).to(memory_format=torch.channels_last)
+    compiled = torch.compile(net, backend="aot_eager", fullgraph=True)
+    xin = torch.randn(2, 8, 3, 3).contiguous(memory_format=torch.channels_last).requires_grad_()
+    out, want = compiled(xin), net(xin)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(torch.autograd.grad(out.sum(), xin)[0], torch.autograd.grad(want.sum(), xin)[0], rtol=1e-4, atol=1e-5)
