@@ -198,3 +198,23 @@ def test_torchsched_multi_stream_and_cuda_graph(cuda_dev):
         for _ in range(3):
             xi = torch.randn(512, 1024, device=cuda_dev)
             torch.testing.assert_close(cg(xi), m(xi), atol=2e-3, rtol=2e-3)
+
+
+def test_norm_modules_under_torch_compile_use_the_custom_ops(cuda_dev):
+    """fullgraph torch.compile of a model with FusedLayerNorm / FusedRMSNorm / GroupNorm on CUDA: the apex_b200:: custom ops keep the fused
+    kernels in the graph (no graph break, no fallback), values and gradients equal eager."""
+    from apex_b200.contrib.group_norm import GroupNorm
+    from apex_b200.normalization import FusedLayerNorm, FusedRMSNorm
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(256, 256), FusedLayerNorm(256), torch.nn.Tanh(), FusedRMSNorm(256)).to(cuda_dev, torch.bfloat16)
+    x = torch.randn(64, 256, device=cuda_dev, dtype=torch.bfloat16, requires_grad=True)
+    compiled = torch.compile(net, backend="aot_eager", fullgraph=True)
+    out, want = compiled(x), net(x)
+    torch.testing.assert_close(out.float(), want.float(), atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(torch.autograd.grad(out.float().sum(), x)[0].float(), torch.autograd.grad(want.float().sum(), x)[0].float(), atol=5e-2, rtol=5e-2)
+    gn = torch.nn.Sequential(torch.nn.Conv2d(64, 64, 1), GroupNorm(8, 64, act="silu")).to(cuda_dev, torch.bfloat16).to(memory_format=torch.channels_last)
+    img = torch.randn(4, 64, 16, 16, device=cuda_dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_()
+    cgn = torch.compile(gn, backend="aot_eager", fullgraph=True)
+    out, want = cgn(img), gn(img)
+    torch.testing.assert_close(out.float(), want.float(), atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(torch.autograd.grad(out.float().sum(), img)[0].float(), torch.autograd.grad(want.float().sum(), img)[0].float(), atol=5e-2, rtol=5e-2)
