@@ -297,3 +297,20 @@ def test_reference_helper_names_exist_and_agree():
         ref_p[0].grad = g.clone()
         adam_ref.step()
     torch.testing.assert_close(fp32[0], ref_p[0])
+
+
+def test_every_submodule_imports():
+    import importlib
+    import pkgutil
+
+    import apex_b200
+
+    failures = []
+    for m in pkgutil.walk_packages(apex_b200.__path__, "apex_b200."):
+        if any(part in m.name for part in ("._C", "._build", "._kernels", ".csrc", "__main__")):
+            continue
+        try:
+            importlib.import_module(m.name)
+        except Exception as e:  # noqa: BLE001
+            failures.append((m.name, repr(e)))
+    assert not failures, failures
