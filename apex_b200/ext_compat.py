@@ -84,6 +84,11 @@ def _layer_norm_mod():
 def _rope_mod():
     from .transformer.functional import fused_rope as R
 
+    def _2d(t, cos_h, sin_h, cos_w, sin_w, is_bwd):
+        """The raw extension takes [b, img_h, img_w, heads, d] (fused_rotary_positional_embedding.cpp:137-152) and returns the same shape."""
+        b, ih, iw, h, d = t.shape
+        return R._2d(t.reshape(b, ih * iw, h, d), ih, iw, cos_h, sin_h, cos_w, sin_w, is_bwd).view(b, ih, iw, h, d)
+
     return _mod(
         "fused_rotary_positional_embedding",
         forward=lambda t, freqs, transpose_output=False: R._sbhd(t, freqs, None, None, transpose_output, False),
@@ -92,8 +97,8 @@ def _rope_mod():
         backward_cached=lambda g, cos, sin, transpose_output=False: R._sbhd(g, None, cos, sin, transpose_output, True),
         forward_thd=lambda t, cu_seqlens, freqs: R._thd(t, cu_seqlens, freqs, False),
         backward_thd=lambda g, cu_seqlens, freqs: R._thd(g, cu_seqlens, freqs, True),
-        forward_2d=lambda t, cos_h, sin_h, cos_w, sin_w: R._2d(t, cos_h.shape[1], cos_w.shape[1], cos_h, sin_h, cos_w, sin_w, False),
-        backward_2d=lambda g, cos_h, sin_h, cos_w, sin_w: R._2d(g, cos_h.shape[1], cos_w.shape[1], cos_h, sin_h, cos_w, sin_w, True),
+        forward_2d=lambda t, cos_h, sin_h, cos_w, sin_w: _2d(t, cos_h, sin_h, cos_w, sin_w, False),
+        backward_2d=lambda g, cos_h, sin_h, cos_w, sin_w: _2d(g, cos_h, sin_h, cos_w, sin_w, True),
     )
 
 

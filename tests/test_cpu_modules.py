@@ -239,6 +239,13 @@ def test_extension_name_modules():
     losses, mlse = xe.forward(lg, lab, 0.1, True)
     torch.testing.assert_close(losses, torch.nn.functional.cross_entropy(lg, lab, label_smoothing=0.1, reduction="none"))
     assert xe.backward(torch.ones(6), lg, mlse, lab, 0.1).shape == lg.shape
+    rope = importlib.import_module("fused_rotary_positional_embedding")
+    t5 = torch.randn(2, 3, 4, 2, 8)                       # the raw 2-D entry point takes [b, img_h, img_w, heads, d]
+    ch, sh, cw, sw = torch.randn(1, 4, 1, 4), torch.randn(1, 4, 1, 4), torch.randn(1, 6, 1, 4), torch.randn(1, 6, 1, 4)
+    from apex_b200.transformer.functional import fused_rope as R
+    torch.testing.assert_close(rope.forward_2d(t5, ch, sh, cw, sw), R.fused_apply_rotary_pos_emb_2d(t5.view(2, 12, 2, 8), 3, 4, ch, sh, cw, sw).view(2, 3, 4, 2, 8))
+    assert rope.backward_2d(t5, ch, sh, cw, sw).shape == t5.shape
+    assert rope.forward_thd(torch.randn(12, 2, 8), torch.tensor([0, 5, 12], dtype=torch.int32), torch.randn(8, 1, 1, 8)).shape == (12, 2, 8)
     for name in ("amp_C", "syncbn", "apex_C", "fused_weight_gradient_mlp_cuda", "scaled_masked_softmax_cuda", "scaled_softmax_cuda",
                  "generic_scaled_masked_softmax_cuda", "fused_rotary_positional_embedding"):
         assert importlib.import_module(name) is not None
