@@ -86,6 +86,40 @@ def dist_adam_two_dimensional_grid(rank, world, device_type):
             torch.testing.assert_close(pd, pr, rtol=1e-5, atol=1e-5)
 
 
+def dist_adam_scaled_states_on_several_ranks(rank, world, device_type):
+    """with_scaled_states (bf16 state + per-fragment fp32 scales) sharded over ranks, buckets that parameters straddle: stays finite, tracks
+    data-parallel fp32 AdamW to bf16 accuracy, every rank ends with identical parameters (reference test_matches_pytorch_scaled_state)."""
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    ref = _model(dev)
+    model = copy.deepcopy(ref).bfloat16()
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=3e-3, weight_decay=0.05)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt = DistributedFusedAdam(model.parameters(), lr=3e-3, weight_decay=0.05, device=dev, dtype=torch.bfloat16, with_scaled_states=True,
+                                   bucket_cap_mb=2048 * 4 * world / 2 ** 20, fused_collectives=False)
+    g = torch.Generator().manual_seed(100 + rank)
+    for it in range(4):
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        x = torch.randn(5, 7, generator=g).to(dev)
+        ref(x).pow(2).mean().backward()
+        model(x.bfloat16()).float().pow(2).mean().backward()
+        for p in ref.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        ref_opt.step()
+        opt.step()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert bool(torch.isfinite(a.float()).all())
+        torch.testing.assert_close(a.float(), b, rtol=5e-2, atol=5e-2)
+        t = a.detach().float().clone()
+        dist.broadcast(t, src=0)
+        torch.testing.assert_close(t, a.detach().float(), rtol=0, atol=0)
+
+
 def dist_adam_state_dict_reshards(rank, world, device_type, tmpdir):
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")

@@ -329,3 +329,11 @@ def test_scaled_states_survive_tiny_second_moments():
     assert all(bool(torch.isfinite(t.float()).all()) for t in (seg.master, seg.exp_avg, seg.exp_avg_sq)) and all(bool((v > 0).all()) for v in seg.scales.values())
     for x, y in zip(pa, pb):
         torch.testing.assert_close(x.detach().float(), y.detach(), rtol=2e-2, atol=2e-2)
+
+
+def test_three_ranks_gloo_matches_ddp_adamw():
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 3, "cpu", False, backend="gloo")
+
+
+def test_two_ranks_gloo_scaled_states():
+    run_distributed(cases.dist_adam_scaled_states_on_several_ranks, 2, "cpu", backend="gloo")
