@@ -18,7 +18,8 @@ p.add_argument("--iters", type=int, default=100)
 p.add_argument("--batch", type=int, default=64)
 p.add_argument("--nz", type=int, default=100)
 args = p.parse_args()
-dev = torch.device("cuda")
+dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # CPU: the same recipe on the PyTorch reference paths
+amp_dtype = torch.float16 if dev.type == "cuda" else torch.bfloat16
 
 
 def G(nz, ngf=64):
@@ -40,7 +41,7 @@ def D(ndf=64):
 netG, netD = G(args.nz).to(dev), D().to(dev)
 optD = FusedAdam(netD.parameters(), lr=2e-4, betas=(0.5, 0.999))
 optG = FusedAdam(netG.parameters(), lr=2e-4, betas=(0.5, 0.999))
-scaler = torch.amp.GradScaler("cuda")
+scaler = torch.amp.GradScaler(dev.type)
 bce = nn.BCEWithLogitsLoss()
 real = torch.randn(args.batch, 3, 64, 64, device=dev).tanh()
 for it in range(args.iters):
@@ -48,7 +49,7 @@ for it in range(args.iters):
     ones, zeros = torch.ones(args.batch, device=dev), torch.zeros(args.batch, device=dev)
     # (1) D on real, (2) D on fake
     optD.zero_grad()
-    with torch.autocast("cuda", dtype=torch.float16):
+    with torch.autocast(dev.type, dtype=amp_dtype):
         errD_real = bce(netD(real).view(-1).float(), ones)
         fake = netG(noise)
         errD_fake = bce(netD(fake.detach()).view(-1).float(), zeros)
@@ -57,10 +58,10 @@ for it in range(args.iters):
     scaler.step(optD)
     # (3) G
     optG.zero_grad()
-    with torch.autocast("cuda", dtype=torch.float16):
+    with torch.autocast(dev.type, dtype=amp_dtype):
         errG = bce(netD(fake).view(-1).float(), ones)
     scaler.scale(errG).backward()
     scaler.step(optG)
     scaler.update()
     if it % 20 == 0:
-        print(f"[{it}/{args.iters}] Loss_D {float(errD_real + errD_fake):.4f}  Loss_G {float(errG):.4f}  scale {scaler.get_scale():.0f}")
+        print(f"[{it}/{args.iters}] Loss_D {(errD_real + errD_fake).item():.4f}  Loss_G {errG.item():.4f}  scale {scaler.get_scale():.0f}")
