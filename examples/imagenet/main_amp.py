@@ -77,11 +77,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     distributed = world > 1
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    use_cuda = torch.cuda.is_available()      # without a GPU the script still runs (gloo, PyTorch reference paths): a plumbing check
+    dev = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", init_method="env://", device_id=dev)
+        if use_cuda:
+            dist.init_process_group("nccl", init_method="env://", device_id=dev)
+        else:
+            dist.init_process_group("gloo", init_method="env://")
     torch.backends.cudnn.benchmark = True
 
     model = resnet50().to(dev).to(memory_format=torch.channels_last)
@@ -90,7 +95,7 @@ def main():
     lr = args.lr * args.batch_size * world / 256.0
     optimizer = FusedSGD(model.parameters(), lr=lr, momentum=args.momentum, weight_decay=args.weight_decay)
     amp_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": None}[args.dtype]
-    scaler = torch.amp.GradScaler("cuda", enabled=args.dtype == "fp16")
+    scaler = torch.amp.GradScaler(dev.type, enabled=args.dtype == "fp16")
     start_epoch = 0
     if args.resume and os.path.isfile(args.resume):
         ck = torch.load(args.resume, map_location=dev)
@@ -100,7 +105,7 @@ def main():
         if local_rank == 0:
             print(f"=> resumed from {args.resume} (epoch {start_epoch})")
     if distributed:
-        model = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank]) if args.torch_ddp else DistributedDataParallel(model))
+        model = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank] if use_cuda else None) if args.torch_ddp else DistributedDataParallel(model))
 
     prof = ProfilerWindow(args.prof, 10)
     for epoch in range(start_epoch, args.epochs):
@@ -113,7 +118,7 @@ def main():
             with nvtx_range(f"Body of iteration {i}"):
                 x = x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
                 y = y.to(dev, non_blocking=True)
-                with nvtx_range("forward"), torch.autocast("cuda", dtype=amp_dtype, enabled=amp_dtype is not None):
+                with nvtx_range("forward"), torch.autocast(dev.type, dtype=amp_dtype, enabled=amp_dtype is not None):
                     loss = F.cross_entropy(model(x), y)
                 optimizer.zero_grad(set_to_none=True)
                 with nvtx_range("backward"):
@@ -123,7 +128,8 @@ def main():
                     scaler.update()
             if i % args.print_freq == 0:
                 rl = reduce_tensor(loss, world) if distributed else loss.detach()
-                torch.cuda.synchronize()
+                if use_cuda:
+                    torch.cuda.synchronize()
                 losses.update(float(rl), x.size(0))
                 batch_time.update((time.time() - end) / args.print_freq if i else time.time() - end)
                 end = time.time()
