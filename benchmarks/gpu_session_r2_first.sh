@@ -28,3 +28,7 @@ import os; os.environ["APEX_B200_FMHA_KERNEL"] = "0"
 b = fmha_varlen(qkv, cu, max(lens), 0.0, False)
 print("fmha kernel vs sdpa max abs diff:", (a.float() - b.float()).abs().max().item())
 PY
+echo "== 5. (run this script under gpurun --gpus 2 or more) symmetric-heap bandwidth / barrier probes"
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  timeout 300 python -m torch.distributed.run --standalone --local-addr 127.0.0.1 --nproc-per-node "$(nvidia-smi -L | wc -l)" benchmarks/bench_symm.py --mb 256 2>&1 | grep "^{" | tee gpurun_out/r2_symm.jsonl
+fi
