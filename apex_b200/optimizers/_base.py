@@ -91,3 +91,21 @@ def restore_fp32_state(optimizer, state_dict, keys=("exp_avg", "exp_avg_sq")) ->
             v = st.get(k)
             if torch.is_tensor(v) and v.is_floating_point():
                 optimizer.state[p][k] = v.detach().to(device=p.device, dtype=torch.float32).clone()
+
+
+def adopt_foreign_state(optimizer) -> None:
+    """Make a checkpoint written by a ``torch.optim`` optimizer of the same family loadable: hyper-parameters it does not know
+    (``bias_correction``, ``grad_averaging``, ...) come from this optimizer's defaults, and torch's per-parameter ``step`` counters become the
+    per-group counter these optimizers keep (they must agree inside a group, as they do after ordinary training)."""
+    for group in optimizer.param_groups:
+        for k, v in optimizer.defaults.items():
+            group.setdefault(k, v)
+        steps = []
+        for p in group["params"]:
+            st = optimizer.state.get(p)
+            if st is not None and "step" in st:
+                steps.append(int(float(st.pop("step"))))
+        if steps and not group.get("step"):
+            if len(set(steps)) != 1:
+                raise ValueError("cannot adopt a checkpoint whose parameters of one group were updated a different number of times")
+            group["step"] = steps[0]

@@ -12,7 +12,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import BucketCache, flat_state_like, partition_by_dtype, restore_fp32_state
+from ._base import BucketCache, adopt_foreign_state, flat_state_like, partition_by_dtype, restore_fp32_state
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -62,6 +62,15 @@ class FusedAdam(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
+        adopt_foreign_state(self)   # e.g. a torch.optim.Adam(W) checkpoint
+        if self.capturable:         # lr / step live on the device in capturable mode, whatever the checkpoint stored
+            for group in self.param_groups:
+                if not group["params"]:
+                    continue
+                dev = group["params"][0].device
+                group["lr"] = torch.as_tensor(group["lr"], dtype=torch.float32).to(dev)
+                if "step" in group:
+                    group["step"] = torch.as_tensor(group["step"], dtype=torch.int).reshape(-1)[:1].to(dev).clone()
         # torch casts loaded state to the parameter dtype; the kernels keep fp32 moments for every parameter dtype.
         restore_fp32_state(self, state_dict)
         for st in self.state.values():

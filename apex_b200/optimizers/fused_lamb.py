@@ -12,7 +12,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import BucketCache, partition_by_dtype, restore_fp32_state
+from ._base import BucketCache, adopt_foreign_state, partition_by_dtype, restore_fp32_state
 
 
 def _global_grad_norm(tables, cpu_grads, device):
@@ -50,6 +50,7 @@ class FusedLAMB(torch.optim.Optimizer):
 
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
+        adopt_foreign_state(self)
         self._cache.clear()
 
     def zero_grad(self, set_to_none: bool | None = None):

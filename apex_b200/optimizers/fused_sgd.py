@@ -9,7 +9,7 @@ import torch
 from .. import _lib
 from ..ops import amp_C
 from ..ops import reference as ref
-from ._base import CHUNK, BucketCache, partition_by_dtype
+from ._base import CHUNK, BucketCache, adopt_foreign_state, partition_by_dtype
 
 
 class _TableOptimizer(torch.optim.Optimizer):
@@ -27,6 +27,7 @@ class _TableOptimizer(torch.optim.Optimizer):
 
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
+        adopt_foreign_state(self)   # checkpoints of the torch.optim counterpart: missing hyper-parameters, per-parameter step counters
         self._cache.clear()
 
     def zero_grad(self, set_to_none: bool | None = None):

@@ -273,3 +273,41 @@ def test_checkpoint_resume_is_exact_with_16_bit_parameters(name):
     run(pb, ob, range(3, 6))
     for got, want in zip(pb, ps):
         torch.testing.assert_close(got, want, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("family", ["adamw", "adamw_capturable", "sgd", "adagrad"])
+def test_checkpoints_of_the_torch_optimizers_continue_in_the_fused_ones(family):
+    """Migration path: train with torch.optim, load that optimizer's state_dict into the fused counterpart, keep training: identical
+    trajectory (missing apex-only hyper-parameters come from the defaults, per-parameter step counters become the per-group counter)."""
+    import copy
+
+    torch_make, fused_make = {
+        "adamw": (lambda p: torch.optim.AdamW(p, lr=1e-2, weight_decay=0.01), lambda p: FusedAdam(p, lr=1e-2, weight_decay=0.01)),
+        "adamw_capturable": (lambda p: torch.optim.AdamW(p, lr=1e-2, weight_decay=0.01), lambda p: FusedAdam(p, lr=1e-2, weight_decay=0.01, capturable=True)),
+        "sgd": (lambda p: torch.optim.SGD(p, lr=1e-2, momentum=0.9, weight_decay=0.01), lambda p: FusedSGD(p, lr=1e-2, momentum=0.9, weight_decay=0.01)),
+        "adagrad": (lambda p: torch.optim.Adagrad(p, lr=1e-2), lambda p: FusedAdagrad(p, lr=1e-2)),
+    }[family]
+
+    def grads(ps, it):
+        g = torch.Generator().manual_seed(it)
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=g)
+
+    torch.manual_seed(0)
+    pa = [torch.nn.Parameter(torch.randn(9)), torch.nn.Parameter(torch.randn(3, 4))]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ta, tb = torch_make(pa), torch_make(pb)
+    for it in range(3):
+        grads(pa, it)
+        ta.step()
+        grads(pb, it)
+        tb.step()
+    fused = fused_make(pa)
+    fused.load_state_dict(copy.deepcopy(ta.state_dict()))
+    for it in range(3, 6):
+        grads(pa, it)
+        fused.step()
+        grads(pb, it)
+        tb.step()
+    for x, y in zip(pa, pb):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
