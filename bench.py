@@ -51,6 +51,13 @@ def main():
     import torch
     import torch.distributed as dist
 
+    if not torch.cuda.is_available():   # this benchmark is a GPU measurement; say so in one line instead of a CUDA-init traceback
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "no CUDA device on this machine"}))
+            return 0
+        print("bench.py needs a CUDA device (B200); run it through gpurun or on the GPU box", file=sys.stderr)
+        return 2
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
