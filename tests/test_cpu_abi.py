@@ -3,6 +3,7 @@ prototype of ``name`` in csrc/ argument for argument (pointer / int32 / int64 / 
 import glob
 import os
 import re
+from pathlib import Path
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -10,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _c_prototypes():
     protos = {}
     for f in glob.glob(os.path.join(ROOT, "apex_b200/csrc/**/*.cu"), recursive=True) + glob.glob(os.path.join(ROOT, "apex_b200/csrc/*.cpp")):
-        for m in re.finditer(r"AB_API\s+([\w\s\*]+?)\s+(\w+)\s*\(([^)]*)\)\s*\{", open(f).read(), re.S):
+        for m in re.finditer(r"AB_API\s+([\w\s\*]+?)\s+(\w+)\s*\(([^)]*)\)\s*\{", Path(f).read_text(), re.S):
             codes = []
             for a in (x.strip() for x in m.group(3).replace("\n", " ").split(",") if x.strip()):
                 a = re.sub(r"\s+", " ", a)
@@ -33,7 +34,7 @@ def _c_prototypes():
 def _declarations():
     decl = {}
     for f in glob.glob(os.path.join(ROOT, "apex_b200/**/*.py"), recursive=True):
-        src = open(f).read().replace('_T + "', '"p i i i i ').replace('_T+"', '"p i i i i ')
+        src = Path(f).read_text().replace('_T + "', '"p i i i i ').replace('_T+"', '"p i i i i ')
         for m in re.finditer(r'declare\(\s*"(\w+)"\s*,\s*"([^"]*)"', src):
             decl[m.group(1)] = (m.group(2).split(), os.path.relpath(f, ROOT))
     return decl
@@ -64,10 +65,10 @@ def test_built_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(so)
     experimental = set()
     for f in glob.glob(os.path.join(ROOT, "apex_b200/csrc/experimental/*.cu")):
-        experimental.update(re.findall(r"AB_API\s+[\w\s\*]+?\s+(\w+)\s*\(", open(f).read()))
+        experimental.update(re.findall(r"AB_API\s+[\w\s\*]+?\s+(\w+)\s*\(", Path(f).read_text()))
     names = set(_declarations())
     for f in glob.glob(os.path.join(ROOT, "apex_b200/**/*.py"), recursive=True):
-        names.update(re.findall(r'raw_fn\(\s*"(\w+)"', open(f).read()))
+        names.update(re.findall(r'raw_fn\(\s*"(\w+)"', Path(f).read_text()))
     has_experimental = any(hasattr(lib, n) for n in experimental)
     missing = [n for n in sorted(names) if not hasattr(lib, n) and (has_experimental or n not in experimental)]
     assert not missing, f"rebuild the library (python -m apex_b200._build): {missing}"
