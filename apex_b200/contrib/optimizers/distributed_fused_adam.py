@@ -42,6 +42,17 @@ def _world(group):
     return 1, 0
 
 
+def _pack_msb(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """Bit transport between a floating-point tensor and an INTEGER ``param_sync_dtype`` (reference :2810-2824): the most significant bytes of
+    every element are copied (little-endian), missing low bytes are zero. int32 / int64 carry fp32 losslessly, uint8 keeps sign + 7 exponent bits."""
+    a = src.contiguous().unsqueeze(-1).view(torch.uint8)
+    b = dst.unsqueeze(-1).view(torch.uint8)
+    n = min(a.size(-1), b.size(-1))
+    if n < b.size(-1):
+        b[..., :-n].zero_()
+    b[..., -n:].copy_(a[..., -n:])
+
+
 class _Segment:
     """All parameters of one (param group, dtype triple): a flat space cut into buckets, each bucket sharded D ways."""
 
@@ -140,12 +151,15 @@ class _Segment:
             for p, off in zip(self.params, self.offsets):
                 n = p.numel()
                 pv = self.param_buf[off:off + n].view(p.shape)
-                pv.copy_(p.detach().to(self.param_dtype))
+                if self.param_dtype.is_floating_point:
+                    pv.copy_(p.detach().to(self.param_dtype))
+                else:
+                    _pack_msb(p.detach(), pv)
                 if p.dtype == self.param_dtype:
                     p.data = pv  # the model weight IS the all-gather destination
                 self.opt._param_view[id(p)] = pv
                 self.opt._grad_view[id(p)] = self.grad_buf[off:off + n].view(p.shape)
-            has_init = any(id(p) in self.opt._init_values for p in self.params)
+            has_init = any(id(p) in self.opt._init_values for p in self.params) or not self.param_dtype.is_floating_point
             if self.master is not None and not has_init:
                 # master := current parameter values of this rank's shard (strided read, no full-size temporary)
                 self.master.view(self.n_buckets, self.shard_elems).copy_(self.shard_view(self.param_buf))
@@ -515,6 +529,11 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         mode = 1 if self.adam_w_mode else 0
         bc = 1 if group["bias_correction"] else 0
         scaled = seg.scales is not None
+        int_sync = not seg.param_dtype.is_floating_point   # integer transport dtype: Adam runs on the master, its top bytes are what is gathered
+        if int_sync:
+            if seg.master is None:
+                raise RuntimeError("an integer param_sync_dtype needs store_params=True (the master holds the real values)")
+            int_shard, out_shard = out_shard, seg.master   # the step writes the master in place; packing follows below
         if scaled:
             # 16-bit state with per-fragment scales: widen to fp32 temporaries, step, re-quantise with fresh scales
             st32 = {k: seg.load_scaled(k) for k in ("param", "exp_avg", "exp_avg_sq")}
@@ -551,6 +570,9 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             p_in = seg.master if seg.master is not None else out_shard
             ref.dist_adam(p_in, seg.exp_avg, seg.exp_avg_sq, seg.reduced, out_shard, self._grad_scale, group["lr"], beta1, beta2,
                           group["eps"], step, mode, bc, group["weight_decay"])
+        if int_sync:
+            _pack_msb(seg.master, int_shard)
+            out_shard = int_shard
         if scaled:
             seg.master, seg.exp_avg, seg.exp_avg_sq = real
             for k in ("param", "exp_avg", "exp_avg_sq"):
@@ -630,7 +652,9 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         for seg in self._segments:
             seg.synced = False
             for p in seg.params:  # parameters whose dtype differs from the sync dtype get a cast copy
-                if p.dtype != seg.param_dtype:
+                if not seg.param_dtype.is_floating_point:
+                    _pack_msb(self._param_view[id(p)], p.data)   # the same byte transport in the other direction
+                elif p.dtype != seg.param_dtype:
                     p.data.copy_(self._param_view[id(p)].to(p.dtype))
         self._grad_scale.fill_(1.0)
         self._grad_norm = None
@@ -722,10 +746,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
                 seg.remainders.copy_(seg.shard_view(lo).contiguous().view(-1).to(torch.int16))
                 seg.param_buf.view(torch.int16).copy_(((bits - lo) >> 16).to(torch.int16))
+            elif not seg.param_dtype.is_floating_point:
+                _pack_msb(pfull.to(seg.dtype), seg.param_buf)
             else:
                 seg.param_buf.copy_(pfull.to(seg.param_dtype))
             for p in seg.params:
-                if p.dtype != seg.param_dtype:
+                if not seg.param_dtype.is_floating_point:
+                    _pack_msb(self._param_view[id(p)], p.data)
+                elif p.dtype != seg.param_dtype:
                     p.data.copy_(self._param_view[id(p)].to(p.dtype))
 
     def __repr__(self):

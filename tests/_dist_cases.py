@@ -12,7 +12,7 @@ def _model(device, dtype=torch.float32, seed=0):
     return m
 
 
-def dist_adam_matches_ddp_adamw(rank, world, device_type, fused, steps=4, clip=False, dtype=torch.float32, grad_sync_dtype=None):
+def dist_adam_matches_ddp_adamw(rank, world, device_type, fused, steps=4, clip=False, dtype=torch.float32, grad_sync_dtype=None, param_sync_dtype=None):
     """Oracle = every rank holds the full model + torch.optim.AdamW on all-reduced (averaged) grads."""
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
@@ -22,7 +22,7 @@ def dist_adam_matches_ddp_adamw(rank, world, device_type, fused, steps=4, clip=F
                         {"params": [p for n, p in m.named_parameters() if "bias" in n], "lr": 1e-2, "weight_decay": 0.0}]
     ref_opt = torch.optim.AdamW(groups(ref_model), lr=3e-3, weight_decay=0.05)
     opt = DistributedFusedAdam(groups(dist_model), lr=3e-3, weight_decay=0.05, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20,
-                               fused_collectives=("auto" if fused else False), grad_sync_dtype=grad_sync_dtype)
+                               fused_collectives=("auto" if fused else False), grad_sync_dtype=grad_sync_dtype, param_sync_dtype=param_sync_dtype)
     assert opt.fused_collectives == (fused and device_type == "cuda")
     g = torch.Generator().manual_seed(100 + rank)
     for it in range(steps):

@@ -337,3 +337,46 @@ def test_three_ranks_gloo_matches_ddp_adamw():
 
 def test_two_ranks_gloo_scaled_states():
     run_distributed(cases.dist_adam_scaled_states_on_several_ranks, 2, "cpu", backend="gloo")
+
+
+@pytest.mark.parametrize("model_dtype,state_dtype,sync_dtype,tol", [(torch.float32, torch.float32, torch.int64, 1e-5), (torch.float32, torch.float32, torch.int32, 1e-5),
+                                                                    (torch.float16, torch.float16, torch.uint8, 0.6)])
+def test_integer_param_sync_dtype(model_dtype, state_dtype, sync_dtype, tol):
+    """Integer ``param_sync_dtype``: the gathered buffer carries the most significant bytes of the master values (lossless for int32 / int64
+    with fp32, sign + exponent only for uint8), parameters are rebuilt from those bytes; several buckets; checkpoint restores the parameters
+    (reference test_matches_pytorch_int64_param_sync / _int32_ / _uint8_)."""
+    import copy
+    import warnings
+
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+
+    def make(seed):
+        torch.manual_seed(seed)
+        ps = [torch.nn.Parameter(torch.randn(3000).to(model_dtype)), torch.nn.Parameter(torch.randn(400, 9).to(model_dtype))]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return ps, DistributedFusedAdam(ps, lr=1e-2, weight_decay=0.1, device="cpu", dtype=state_dtype, param_sync_dtype=sync_dtype, bucket_cap_mb=0.008)
+
+    pa, a = make(0)
+    pb = [torch.nn.Parameter(p.detach().float().clone()) for p in pa]
+    b = torch.optim.AdamW(pb, lr=1e-2, weight_decay=0.1)
+    for it in range(4):
+        g = torch.Generator().manual_seed(it)
+        a.zero_grad()
+        for x, y in zip(pa, pb):
+            grad = torch.randn(x.shape, generator=g).to(model_dtype)
+            x.grad, y.grad = grad.clone(), grad.float()
+        a.step()
+        b.step()
+    assert a._segments[0].param_buf.dtype == sync_dtype and a._segments[0].n_buckets > 1
+    for x, y in zip(pa, pb):
+        assert x.dtype == model_dtype
+        torch.testing.assert_close(x.detach().float(), y.detach(), rtol=tol, atol=tol)
+    pc, c = make(5)
+    c.load_state_dict(copy.deepcopy(a.state_dict()))
+    for x, y in zip(pa, pc):
+        assert torch.equal(x, y)
+
+
+def test_two_ranks_gloo_int32_param_sync():
+    run_distributed(cases.dist_adam_matches_ddp_adamw, 2, "cpu", False, 4, False, torch.float32, None, torch.int32, backend="gloo")
