@@ -42,20 +42,10 @@ def _layer_norm_mod():
     from .ops import norm as N
 
     def _cpu(x, shape, w, b, eps, rms):
-        xf = x.float()
-        dims = tuple(range(x.dim() - len(shape), x.dim()))
-        if rms:
-            invvar = torch.rsqrt(xf.pow(2).mean(dims, keepdim=True) + eps)
-            y, mean = xf * invvar, None
-        else:
-            mean = xf.mean(dims, keepdim=True)
-            invvar = torch.rsqrt(xf.var(dims, unbiased=False, keepdim=True) + eps)
-            y = (xf - mean) * invvar
-        if w is not None:
-            y = y * w.float()
-        if b is not None:
-            y = y + b.float()
-        return y.to(w.dtype if w is not None else x.dtype), (None if mean is None else mean.reshape(-1)), invvar.reshape(-1)
+        from .normalization.custom_ops import reference_fwd
+
+        y, mean, invvar = reference_fwd(x, shape, w, b, eps, rms, w.dtype if w is not None else x.dtype)
+        return y, mean, invvar
 
     def _fwd(x, shape, w, b, eps, rms, mixed=False):
         shape = tuple(shape)
@@ -64,6 +54,10 @@ def _layer_norm_mod():
         return N.norm_fwd(x, shape, w, b, eps, rms, w.dtype if (mixed and w is not None) else None)
 
     def _bwd(dy, mean, invvar, saved, shape, w, b, eps, rms, memory_efficient):
+        if not dy.is_cuda:
+            from .normalization.custom_ops import reference_bwd
+
+            return reference_bwd(dy, saved, mean, invvar, tuple(shape), w, b, rms, memory_efficient, saved.dtype if not memory_efficient else dy.dtype)
         return N.norm_bwd(dy, saved, mean, invvar, tuple(shape), w, b, eps, rms, memory_efficient, saved.dtype if not memory_efficient else dy.dtype)
 
     return _mod(
@@ -194,17 +188,29 @@ def _fast_layer_norm_mod(ln):
 
 
 def _small_contrib_mods():
+    import importlib
+
     from . import _lib
-    from .contrib.focal_loss import focal_loss as FL
-    from .contrib.index_mul_2d import index_mul_2d as IM
+
+    # the packages re-export a FUNCTION under the sub-module's own name (focal_loss, index_mul_2d): import the modules explicitly
+    FL = importlib.import_module(__package__ + ".contrib.focal_loss.focal_loss")
+    IM = importlib.import_module(__package__ + ".contrib.index_mul_2d.index_mul_2d")
 
     def focal_forward(cls_output, cls_targets_at_level, num_positives_sum, num_real_classes, alpha, gamma, smoothing_factor):
         """-> [loss, partial_grad]"""
+        if not cls_output.is_cuda:
+            with torch.enable_grad():
+                x = cls_output.detach().requires_grad_()
+                loss = FL._ref(x, cls_targets_at_level, num_positives_sum, num_real_classes, alpha, gamma, smoothing_factor)
+                (pgrad,) = torch.autograd.grad(loss, x)
+            return [loss.detach(), pgrad]
         ctx = _Ctx()
         loss = FL.FocalLoss.forward(ctx, cls_output, cls_targets_at_level, num_positives_sum, num_real_classes, alpha, gamma, smoothing_factor)
         return [loss, ctx.saved_tensors[0]]
 
     def focal_backward(grad_output, partial_grad, num_positives_sum):
+        if not partial_grad.is_cuda:
+            return partial_grad * grad_output
         ctx = _Ctx()
         ctx.saved_tensors = (partial_grad, num_positives_sum.float().reshape(1))
         return FL.FocalLoss.backward(ctx, grad_output)[0]

@@ -559,3 +559,52 @@ def test_state_dict_keys_match_the_reference_constructors():
         assert out["ours"][case] == ref_keys, case
         compared += 1
     assert compared >= 15
+
+
+def test_extension_name_modules_losses_and_layer_norm_backward():
+    """focal_loss_cuda / fused_index_mul_2d / fused_layer_norm_cuda.backward* / fast_layer_norm.ln_bwd shims on the PyTorch paths."""
+    import importlib
+
+    import apex_b200
+    from apex_b200.contrib.focal_loss.focal_loss import _ref as focal_ref
+
+    apex_b200.install_as_apex()
+    torch.manual_seed(0)
+    fl = importlib.import_module("focal_loss_cuda")
+    co, tg, npos = torch.randn(4, 30, 10), torch.randint(-2, 10, (4, 30)), torch.tensor([11.0])
+    loss, pgrad = fl.forward(co, tg, npos, 8, 0.25, 2.0, 0.0)
+    cr = co.clone().requires_grad_()
+    ref = focal_ref(cr, tg, npos, 8, 0.25, 2.0, 0.0)
+    ref.backward()
+    torch.testing.assert_close(loss, ref.detach())
+    torch.testing.assert_close(fl.backward(torch.tensor(2.0), pgrad, npos), 2.0 * cr.grad)
+    im = importlib.import_module("fused_index_mul_2d")
+    in1, in2, idx = torch.randn(7, 5), torch.randn(20, 5), torch.randint(0, 7, (20,))
+    out = torch.empty_like(in2)
+    im.float_forward(out, in1, in2, idx)
+    torch.testing.assert_close(out, in1[idx] * in2)
+    g1, g2, go = torch.zeros_like(in1), torch.empty_like(in2), torch.randn_like(in2)
+    im.float_backward(g1, g2, go, in1, in2, idx)
+    torch.testing.assert_close(g2, go * in1[idx])
+    torch.testing.assert_close(g1, torch.zeros_like(in1).index_add_(0, idx, go * in2))
+    ln = importlib.import_module("fused_layer_norm_cuda")
+    x, w, b = torch.randn(6, 16), torch.randn(16), torch.randn(16)
+    leaves = [t.clone().requires_grad_() for t in (x, w, b)]
+    want = F.layer_norm(leaves[0], (16,), leaves[1], leaves[2], 1e-5)
+    dy = torch.randn_like(want)
+    y, mean, invvar = ln.forward_affine(x, (16,), w, b, 1e-5)
+    for got, r in zip(ln.backward_affine(dy, mean, invvar, x, (16,), w, b, 1e-5), torch.autograd.grad(want, leaves, dy)):
+        torch.testing.assert_close(got, r, rtol=1e-4, atol=1e-5)
+    plain = ln.backward_affine(dy, mean, invvar, x, (16,), w, b, 1e-5)
+    for got, r in zip(ln.backward_affine(dy, mean, invvar, y, (16,), w, b, 1e-5, True), plain):
+        torch.testing.assert_close(got, r, rtol=1e-4, atol=1e-5)          # memory-efficient form (saved OUTPUT) == plain form (saved input)
+    yr, iv = ln.rms_forward_affine(x, (16,), w, 1e-5)
+    wr = [t.clone().requires_grad_() for t in (x, w)]
+    want_r = wr[0] * torch.rsqrt(wr[0].pow(2).mean(-1, keepdim=True) + 1e-5) * wr[1]
+    for got, r in zip(ln.rms_backward_affine(dy, iv, x, (16,), w, 1e-5), torch.autograd.grad(want_r, wr, dy)):
+        torch.testing.assert_close(got, r, rtol=1e-4, atol=1e-5)
+    fast = importlib.import_module("fast_layer_norm")
+    z, mu, rs = fast.ln_fwd(x, w, b, 1e-5)
+    dx, dg, db, _, _ = fast.ln_bwd(dy, x, mu, rs, w)
+    for got, r in zip((dx, dg, db), torch.autograd.grad(F.layer_norm(leaves[0], (16,), leaves[1], leaves[2], 1e-5), leaves, dy)):
+        torch.testing.assert_close(got, r, rtol=1e-4, atol=1e-5)
