@@ -63,12 +63,13 @@ def capture_graph(fn, *static_args, warmup: int = 3):
 def fused_layer_norm_op(input, normalized_shape, weight=None, bias=None, eps=1e-5):
     """Drop-in for ``F.layer_norm`` (reference torchsched/ops/layer_norm.py): the fused kernel for CUDA fp32 / fp16 / bf16 inputs."""
     if input.is_cuda and input.dtype in (torch.float32, torch.float16, torch.bfloat16):
-        from ...normalization import fused_layer_norm as N
+        # (the package attribute ``normalization.fused_layer_norm`` is the FUNCTION of that name: import from the sub-module)
+        from ...normalization.fused_layer_norm import fused_layer_norm, fused_layer_norm_affine
 
         if weight is not None and bias is not None:
-            return N.fused_layer_norm_affine(input, weight, bias, tuple(normalized_shape), eps)
+            return fused_layer_norm_affine(input, weight, bias, tuple(normalized_shape), eps)
         if weight is None and bias is None:
-            return N.fused_layer_norm(input, tuple(normalized_shape), eps)
+            return fused_layer_norm(input, tuple(normalized_shape), eps)
     return torch.nn.functional.layer_norm(input, normalized_shape, weight, bias, eps)
 
 
