@@ -133,3 +133,61 @@ def test_dist_harness_fails_fast_with_the_failing_ranks_traceback():
     with pytest.raises(RuntimeError, match="deliberate failure on rank 1"):
         run_distributed(cases.one_rank_raises_while_the_others_wait, 3, "cpu", backend="gloo", timeout=120.0)
     assert time.monotonic() - t0 < 60.0   # first failure + grace period, not the peers' collective time-out
+
+
+def test_every_apex_b200_import_in_the_repo_resolves():
+    """GPU-only scripts (benchmarks, examples, GPU tests, CUDA branches of the package) cannot be executed here, but their imports can be
+    resolved: every ``from apex_b200... import X`` names something that exists, and an imported FUNCTION or CLASS is never used as if it were
+    the sub-module of the same name (``from pkg import focal_loss as FL; FL.FocalLoss`` — the package re-exports a function called focal_loss)."""
+    import ast
+    import importlib
+    import pathlib
+    import types
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    files = [p for p in root.joinpath("apex_b200").rglob("*.py") if "csrc" not in p.parts]
+    files += list(root.joinpath("tests").glob("*.py")) + list(root.joinpath("benchmarks").glob("*.py")) + list(root.joinpath("examples").rglob("*.py"))
+    files += [root / "bench.py", root / "__graft_entry__.py"]
+    problems = []
+    for path in files:
+        rel = path.relative_to(root)
+        pkg = None
+        if rel.parts[0] == "apex_b200":
+            mod = ".".join(rel.with_suffix("").parts)
+            pkg = mod[:-9] if mod.endswith(".__init__") else mod.rsplit(".", 1)[0]
+        tree = ast.parse(path.read_text())
+        resolved = {}
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.ImportFrom):
+                continue
+            base = node.module or ""
+            if node.level:
+                if pkg is None:
+                    continue
+                parts = pkg.split(".")
+                base = ".".join(parts[:len(parts) - (node.level - 1)] + ([node.module] if node.module else []))
+            if not base.startswith("apex_b200") or base.startswith("apex_b200._C"):
+                continue
+            try:
+                module = importlib.import_module(base)
+            except Exception as e:  # noqa: BLE001
+                problems.append(f"{rel}:{node.lineno}: import {base}: {e!r}")
+                continue
+            for a in node.names:
+                if a.name == "*":
+                    continue
+                try:
+                    obj = getattr(module, a.name)
+                except AttributeError:
+                    try:
+                        obj = importlib.import_module(base + "." + a.name)
+                    except Exception:  # noqa: BLE001
+                        problems.append(f"{rel}:{node.lineno}: {base} has no {a.name}")
+                        continue
+                resolved.setdefault(a.asname or a.name, []).append(obj)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in resolved:
+                objs = resolved[node.value.id]
+                if all(isinstance(o, (types.FunctionType, type)) and not hasattr(o, node.attr) for o in objs):
+                    problems.append(f"{rel}:{node.lineno}: {node.value.id}.{node.attr} on a {type(objs[0]).__name__}")
+    assert not problems, "\n".join(problems)
