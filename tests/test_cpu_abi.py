@@ -72,3 +72,41 @@ def test_built_library_exports_every_declared_symbol():
     has_experimental = any(hasattr(lib, n) for n in experimental)
     missing = [n for n in sorted(names) if not hasattr(lib, n) and (has_experimental or n not in experimental)]
     assert not missing, f"rebuild the library (python -m apex_b200._build): {missing}"
+
+
+def test_kernel_call_sites_pass_as_many_arguments_as_their_signature_declares():
+    """ctypes only complains about a wrong argument count when the call executes, and most call sites are CUDA-only branches: count the
+    arguments of every ``_lib.fn("name")(...)`` statically (``*table.head()`` expands to 5; calls with other star-arguments are skipped)."""
+    import ast
+
+    specs = {name: len(spec) for name, (spec, _) in _declarations().items()}
+    for f in glob.glob(os.path.join(ROOT, "benchmarks/*.py")):
+        for m in re.finditer(r'declare\(\s*"(\w+)"\s*,\s*"([^"]*)"', Path(f).read_text()):
+            specs[m.group(1)] = len(m.group(2).split())
+    problems, checked = [], 0
+    files = glob.glob(os.path.join(ROOT, "apex_b200/**/*.py"), recursive=True) + glob.glob(os.path.join(ROOT, "benchmarks/*.py")) + \
+        glob.glob(os.path.join(ROOT, "tests/*.py"))
+    for f in files:
+        for node in ast.walk(ast.parse(Path(f).read_text())):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Call)):
+                continue
+            inner = node.func
+            if not (isinstance(inner.func, ast.Attribute) and inner.func.attr == "fn" and inner.args and isinstance(inner.args[0], ast.Constant)
+                    and isinstance(inner.args[0].value, str)):
+                continue
+            name, n, unknown = inner.args[0].value, 0, False
+            for a in node.args:
+                if not isinstance(a, ast.Starred):
+                    n += 1
+                elif isinstance(a.value, ast.Call) and isinstance(a.value.func, ast.Attribute) and a.value.func.attr == "head":
+                    n += 5
+                elif isinstance(a.value, (ast.Tuple, ast.List)):
+                    n += len(a.value.elts)
+                else:
+                    unknown = True
+            if unknown or name not in specs:
+                continue
+            checked += 1
+            if n != specs[name]:
+                problems.append(f"{os.path.relpath(f, ROOT)}:{node.lineno}: {name} called with {n} arguments, declared with {specs[name]}")
+    assert checked >= 50 and not problems, "\n".join(problems)
