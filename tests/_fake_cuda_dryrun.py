@@ -80,6 +80,11 @@ _base.TensorTable = _Table
 failures = 0
 
 
+class _Dev(str):
+    """Passes for a device wherever a string does ("cpu": allocations succeed) while reporting ``type == "cuda"`` to branch selection."""
+    type, index = "cuda", 0
+
+
 def attempt(label, fn, expect=()):
     global failures
     n = len(calls)
@@ -149,6 +154,55 @@ def main():
     attempt("fast_layer_norm", lambda: fast.ln_bwd(torch.randn(4, 16), torch.randn(4, 16), *fast.ln_fwd(torch.randn(4, 16), w16, b16, 1e-5)[1:], w16),
             ["ab_layer_norm_fwd", "ab_layer_norm_bwd"])
 
+    # ---- GEMM front-ends (bf16 so the tcgen05 path is chosen) ---------------------------------------------------------------------
+    from apex_b200 import fused_dense as FD
+    from apex_b200.mlp import MLP
+    from apex_b200.ops import gemm as GM
+
+    bf = torch.bfloat16
+    xb = torch.randn(4, 6, 32, dtype=bf, requires_grad=True)
+    attempt("FusedDense", lambda: FD.FusedDense(32, 16).to(bf)(xb).sum().backward(), ["ab_gemm_bf16", "ab_colsum"])
+    attempt("FusedDense no bias", lambda: FD.FusedDense(32, 16, bias=False).to(bf)(xb).sum().backward(), ["ab_gemm_bf16"])
+    attempt("FusedDenseGeluDense", lambda: FD.FusedDenseGeluDense(32, 64, 16).to(bf)(xb).sum().backward(), ["ab_gemm_bf16", "ab_colsum"])
+    for act in ("none", "relu", "sigmoid"):
+        attempt(f"MLP {act}", lambda act=act: MLP([32, 64, 16], activation=act).to(bf)(xb.reshape(-1, 32)).sum().backward(), ["ab_gemm_bf16"])
+    attempt("MLP no bias", lambda: MLP([32, 64, 16], bias=False).to(bf)(xb.reshape(-1, 32)).sum().backward(), ["ab_gemm_bf16"])
+    if hasattr(FD, "fused_dense_fp8_function"):
+        w1, b1 = torch.randn(64, 32, dtype=bf, requires_grad=True), torch.zeros(64, dtype=bf, requires_grad=True)
+        w2, b2 = torch.randn(16, 64, dtype=bf, requires_grad=True), torch.zeros(16, dtype=bf, requires_grad=True)
+        attempt("fused_dense_fp8_function", lambda: FD.fused_dense_fp8_function(xb, w1, b1).sum().backward(), ["ab_gemm_fp8", "ab_fp8_quantize"])
+        attempt("fused_dense_gelu_dense_fp8_function", lambda: FD.fused_dense_gelu_dense_fp8_function(xb, w1, b1, w2, b2).sum().backward(),
+                ["ab_gemm_fp8", "ab_fp8_quantize"])
+    main_grad = torch.zeros(16, 32)
+    attempt("linear_wgrad accumulate fp32", lambda: GM.linear_wgrad(torch.randn(24, 16, dtype=bf), torch.randn(24, 32, dtype=bf), accum_into=main_grad), ["ab_gemm_bf16"])
+    wg = m["fused_weight_gradient_mlp_cuda"]
+    attempt("fused_weight_gradient_mlp_cuda", lambda: (wg.wgrad_gemm_accum_fp32(torch.randn(24, 32, dtype=bf), torch.randn(24, 16, dtype=bf), main_grad),
+                                                       wg.wgrad_gemm_accum_fp16(torch.randn(24, 32, dtype=bf), torch.randn(24, 16, dtype=bf), main_grad.to(bf))), ["ab_gemm_bf16"])
+    fdc = m["fused_dense_cuda"]
+    attempt("fused_dense_cuda", lambda: (fdc.linear_bias_forward(torch.randn(8, 32, dtype=bf), torch.randn(16, 32, dtype=bf), torch.zeros(16, dtype=bf)),
+                                         fdc.linear_bias_backward(torch.randn(8, 32, dtype=bf), torch.randn(16, 32, dtype=bf), torch.randn(8, 16, dtype=bf))), ["ab_gemm_bf16"])
+
+    # ---- softmax / cross entropy / transducer modules -------------------------------------------------------------------------------
+    from apex_b200.contrib.transducer import TransducerJoint, TransducerLoss
+    from apex_b200.contrib.xentropy import SoftmaxCrossEntropyLoss
+    from apex_b200.transformer.functional.fused_softmax import AttnMaskType, FusedScaleMaskSoftmax
+
+    sc = torch.randn(2, 4, 8, 8, dtype=bf, requires_grad=True)
+    attempt("FusedScaleMaskSoftmax causal", lambda: FusedScaleMaskSoftmax(False, True, AttnMaskType.causal, True, None, False, None)(sc, None).sum().backward(),
+            ["ab_softmax_fwd", "ab_softmax_bwd"])
+    attempt("FusedScaleMaskSoftmax padding", lambda: FusedScaleMaskSoftmax(False, True, AttnMaskType.padding, True, None, True, 2.0)(
+        sc, torch.zeros(2, 1, 8, 8, dtype=torch.bool)).sum().backward(), ["ab_softmax_fwd", "ab_softmax_bwd"])
+    lg = torch.randn(6, 11, requires_grad=True)
+    attempt("SoftmaxCrossEntropyLoss", lambda: SoftmaxCrossEntropyLoss.apply(lg, torch.randint(0, 11, (6,)), 0.1, 0, True).sum().backward(),
+            ["ab_xentropy_fwd", "ab_xentropy_bwd"])
+    f, g = torch.randn(2, 5, 8, requires_grad=True), torch.randn(2, 3, 8, requires_grad=True)
+    fl_, gl_ = torch.tensor([5, 4], dtype=torch.int32), torch.tensor([3, 2], dtype=torch.int32)
+    attempt("TransducerJoint", lambda: TransducerJoint()(f, g, fl_, gl_).sum().backward(), ["ab_transducer_joint_fwd", "ab_transducer_joint_bwd"])
+    attempt("TransducerJoint relu + dropout", lambda: TransducerJoint(relu=True, dropout=True, dropout_prob=0.1)(f, g, fl_, gl_).sum().backward(),
+            ["ab_transducer_joint_fwd", "ab_transducer_joint_bwd"])
+    lx = torch.randn(2, 5, 4, 7, requires_grad=True)
+    attempt("TransducerLoss", lambda: TransducerLoss()(lx, torch.randint(1, 7, (2, 3)), fl_, gl_, 0).sum().backward(), ["ab_transducer_loss_fwd", "ab_transducer_loss_bwd"])
+
     def drive(make, late=False):
         ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(4))]
         opt = make(ps)
@@ -187,6 +241,63 @@ def main():
         d.multi_tensor_fused_adam_with_param_remainders(65536, noop, [[pb], [rem], [mm], [v], [g], [pb]], one, 1e-2, 0.9, 0.99, 1e-8, 1, 1, 1, 0.1)
 
     attempt("distributed_adam_cuda", distopt, ["ab_mt_dist_adam", "ab_mt_dist_adam_remainders"])
+    # ---- remaining single-process entry points ---------------------------------------------------------------------------------------
+    big = torch.randn(1, 8, 512, 512).contiguous(memory_format=torch.channels_last).requires_grad_()
+    attempt("GroupNorm large slab", lambda: G.GroupNorm(4, 8)(big).sum().backward(), ["ab_group_norm"])
+    from apex_b200.parallel import SyncBatchNorm
+    from apex_b200.parallel import sync_batchnorm as SB
+
+    _get = SB._GroupState.get.__func__
+    SB._GroupState.get = classmethod(lambda cls, group, device, channels: _get(cls, group, _Dev("cpu"), channels))
+
+    xi = torch.randn(4, 6, 5, 5, requires_grad=True)
+    attempt("SyncBatchNorm training", lambda: SyncBatchNorm(6)(xi).sum().backward(), ["ab_syncbn"])
+    attempt("SyncBatchNorm channels-last + relu + residual", lambda: SyncBatchNorm(6, channel_last=True, fuse_relu=True)(
+        xi.permute(0, 2, 3, 1).contiguous(), torch.randn(4, 5, 5, 6)).sum().backward(), ["ab_syncbn"])
+    attempt("SyncBatchNorm eval (running statistics: F.batch_norm)", lambda: SyncBatchNorm(6).eval()(xi).sum().backward())
+    noop = torch.zeros(1, dtype=torch.int32)
+    a, b, c = [torch.randn(40), torch.randn(7)], [torch.randn(40), torch.randn(7)], [torch.empty(40), torch.empty(7)]
+    attempt("amp_C scale / axpby / cast", lambda: (amp_C.multi_tensor_scale(65536, noop, [a, c], 0.5), amp_C.multi_tensor_axpby(65536, noop, [a, b, c], 1.0, 2.0, -1),
+                                                  amp_C.multi_tensor_cast(65536, noop, [a, [t.bfloat16() for t in c]])), ["ab_mt_scale", "ab_mt_axpby", "ab_mt_cast"])
+    attempt("amp_C norms", lambda: (amp_C.multi_tensor_l2norm(65536, noop, [a], True), amp_C.multi_tensor_l2norm_mp(65536, noop, [a], False),
+                                   amp_C.multi_tensor_unscale_l2norm(65536, noop, [a], torch.ones(1), True), amp_C.multi_tensor_l2norm_scale(65536, noop, [a, c], 0.5, True),
+                                   amp_C.multi_tensor_norm_out(65536, noop, [a, [torch.zeros(2)]], torch.zeros(2), 0.5, 0.5, 0)), ["ab_mt_norm", "ab_mt_l2norm_scale"])
+    attempt("amp_C update_scale_hysteresis", lambda: amp_C.update_scale_hysteresis(torch.ones(1), torch.zeros(1, dtype=torch.int32), torch.ones(1, dtype=torch.int32),
+                                                                                  torch.zeros(1), 2.0, 0.5, 100, 2), ["ab_update_scale_hysteresis"])
+
+    # ---- DistributedFusedAdam: one rank, device object that reports type "cuda" but allocates on the CPU --------------------------
+    import torch.distributed as dist
+
+    from apex_b200.contrib.optimizers.distributed_fused_adam import DistributedFusedAdam
+
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29613")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+
+    def dfa(fused, pdtype=torch.float32, **kw):
+        ps = [torch.nn.Parameter(torch.randn(33, 7, dtype=pdtype)), torch.nn.Parameter(torch.randn(50, dtype=pdtype))]
+        opt = DistributedFusedAdam(ps, lr=1e-2, device="cpu", **kw)
+        opt.device, opt.fused_collectives = _Dev("cpu"), fused
+        for _ in range(2):
+            for q in ps:
+                q.grad = torch.randn_like(q)
+            opt.clip_grad_norm(1.0)
+            opt.step()
+            opt.zero_grad()
+        sd = opt.state_dict()
+        opt.load_state_dict(sd)
+        for q in ps:
+            q.grad = torch.randn_like(q)
+        opt.step()
+
+    attempt("DistributedFusedAdam one-kernel path", lambda: dfa(True), ["ab_dist_adam_step"])
+    attempt("DistributedFusedAdam one-kernel path bf16", lambda: dfa(True, torch.bfloat16), ["ab_dist_adam_step"])
+    attempt("DistributedFusedAdam capturable", lambda: dfa(True, capturable=True), ["ab_dist_adam_step"])
+    attempt("DistributedFusedAdam generic path", lambda: dfa(False), ["ab_mt_dist_adam"])
+    attempt("DistributedFusedAdam remainders", lambda: dfa(False, torch.bfloat16, store_params=False, store_param_remainders=True), ["ab_mt_dist_adam_remainders"])
+    attempt("DistributedFusedAdam scaled states", lambda: dfa(False, torch.bfloat16, dtype=torch.bfloat16, with_scaled_states=True), ["ab_mt_dist_adam"])
+    attempt("DistributedFusedAdam integer param sync", lambda: dfa(False, param_sync_dtype=torch.uint8), ["ab_mt_dist_adam"])
+    dist.destroy_process_group()
     return failures
 
 
