@@ -265,6 +265,15 @@ def main():
     attempt("amp_C update_scale_hysteresis", lambda: amp_C.update_scale_hysteresis(torch.ones(1), torch.zeros(1, dtype=torch.int32), torch.ones(1, dtype=torch.int32),
                                                                                   torch.zeros(1), 2.0, 0.5, 100, 2), ["ab_update_scale_hysteresis"])
 
+    import numpy as np
+
+    from apex_b200.contrib.sparsity import permutation_search as PS
+
+    wm = torch.randn(16, 32)
+    attempt("permutation scoring kernels", lambda: (PS.sum_after_2_to_4(wm), PS.sum_after_2_to_4(wm, torch.stack([torch.randperm(32) for _ in range(3)])),
+                                                   PS._score_groups(wm, PS._all_groups(8, 2, "cpu"), np.stack([np.random.permutation(8) for _ in range(5)]).astype(np.uint8))),
+            ["ab_perm_eval", "ab_stripe_search"])
+
     # ---- DistributedFusedAdam: one rank, device object that reports type "cuda" but allocates on the CPU --------------------------
     import torch.distributed as dist
 
