@@ -274,6 +274,36 @@ def main():
                                                    PS._score_groups(wm, PS._all_groups(8, 2, "cpu"), np.stack([np.random.permutation(8) for _ in range(5)]).astype(np.uint8))),
             ["ab_perm_eval", "ab_stripe_search"])
 
+    # ---- module / functional forms of the small fused ops ------------------------------------------------------------------------------
+    from apex_b200.contrib.layer_norm import FastLayerNorm
+    from apex_b200.normalization import MixedFusedLayerNorm, MixedFusedRMSNorm
+    from apex_b200.transformer.functional import fused_rope as RP
+
+    FLm = importlib.import_module("apex_b200.contrib.focal_loss.focal_loss")
+    IMm = importlib.import_module("apex_b200.contrib.index_mul_2d.index_mul_2d")
+    xh = torch.randn(4, 8, 16, dtype=torch.bfloat16, requires_grad=True)
+    attempt("FastLayerNorm", lambda: FastLayerNorm(16)(x).sum().backward(), ["ab_layer_norm_fwd", "ab_layer_norm_bwd"])
+    attempt("MixedFusedLayerNorm bf16 input", lambda: MixedFusedLayerNorm(16)(xh).sum().backward(), ["ab_layer_norm_fwd", "ab_layer_norm_bwd"])
+    attempt("MixedFusedRMSNorm memory efficient", lambda: MixedFusedRMSNorm(16, memory_efficient=True)(xh).sum().backward(), ["ab_layer_norm_fwd", "ab_layer_norm_bwd"])
+    attempt("FusedLayerNorm no affine + memory efficient", lambda: (FusedLayerNorm(16, elementwise_affine=False)(x).sum().backward(),
+                                                                   FusedLayerNorm(16, memory_efficient=True)(x).sum().backward()), ["ab_layer_norm_fwd", "ab_layer_norm_bwd"])
+    co = torch.randn(4, 30, 10, requires_grad=True)
+    attempt("focal_loss", lambda: FLm.focal_loss(co, torch.randint(-2, 10, (4, 30)), torch.tensor([11.0]), 8, 0.25, 2.0, 0.1).backward(),
+            ["ab_focal_loss_fwd", "ab_focal_loss_bwd"])
+    i1, i2 = torch.randn(7, 5, requires_grad=True), torch.randn(20, 5, requires_grad=True)
+    attempt("index_mul_2d (+ double backward)", lambda: torch.autograd.grad(torch.autograd.grad(IMm.index_mul_2d(i1, i2, torch.randint(0, 7, (20,))).sum(), i1,
+                                                                                               create_graph=True)[0].sum(), i2), ["ab_index_mul_2d_fwd", "ab_index_mul_2d_bwd"])
+    tq = torch.randn(6, 2, 2, 8, requires_grad=True)
+    fr = torch.randn(6, 1, 1, 8)
+    attempt("RoPE sbhd / cached / transposed", lambda: (RP.fused_apply_rotary_pos_emb(tq, fr).sum().backward(),
+                                                       RP.fused_apply_rotary_pos_emb(tq, fr, transpose_output_memory=True).sum().backward(),
+                                                       RP.fused_apply_rotary_pos_emb_cached(tq, fr.cos(), fr.sin()).sum().backward()), ["ab_rope"])
+    tt = torch.randn(12, 2, 8, requires_grad=True)
+    attempt("RoPE thd", lambda: RP.fused_apply_rotary_pos_emb_thd(tt, torch.tensor([0, 5, 12], dtype=torch.int32), torch.randn(8, 1, 1, 8)).sum().backward(), ["ab_rope"])
+    t2 = torch.randn(2, 12, 2, 8, requires_grad=True)
+    attempt("RoPE 2d", lambda: RP.fused_apply_rotary_pos_emb_2d(t2, 3, 4, torch.randn(1, 3, 1, 4), torch.randn(1, 3, 1, 4), torch.randn(1, 4, 1, 4),
+                                                               torch.randn(1, 4, 1, 4)).sum().backward(), ["ab_rope"])
+
     # ---- DistributedFusedAdam: one rank, device object that reports type "cuda" but allocates on the CPU --------------------------
     import torch.distributed as dist
 
