@@ -21,6 +21,11 @@ def main():
     ref_cls = None
     try:
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        try:
+            import group_norm_cuda  # noqa: F401  (v1 library, 104 MB: not shipped to the GPU box, see .gpurunignore)
+        except ImportError:
+            import types
+            sys.modules["group_norm_cuda"] = types.ModuleType("group_norm_cuda")  # v2 is auto-selected on sm_100; v1 is never called
         from apex.contrib.group_norm import GroupNorm as ref_cls  # noqa: F811
     except Exception as e:  # extension not built
         print(json.dumps({"reference_group_norm": "unavailable", "why": f"{type(e).__name__}: {e}"[:200]}))

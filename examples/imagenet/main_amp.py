@@ -8,6 +8,7 @@ import argparse
 import os
 import shutil
 import sys
+import tempfile
 import time
 
 import torch
@@ -36,7 +37,8 @@ def parse():
     p.add_argument("--prof", type=int, default=-1, help="profile 10 iterations starting at this one (cudaProfilerStart/Stop + NVTX)")
     p.add_argument("--print-freq", type=int, default=10)
     p.add_argument("--resume", default="", help="checkpoint to resume from")
-    p.add_argument("--checkpoint", default="checkpoint.pth.tar")
+    p.add_argument("--save-dir", default=os.path.join(tempfile.gettempdir(), "apex_b200_imagenet"), help="directory for checkpoints (never the source tree)")
+    p.add_argument("--checkpoint", default="checkpoint.pth.tar", help="file name inside --save-dir (or an absolute path)")
     return p.parse_args()
 
 
@@ -139,8 +141,10 @@ def main():
                           f"Loss {losses.val:.4f} ({losses.avg:.4f})")
         if local_rank == 0:
             net = model.module if hasattr(model, "module") else model
-            torch.save({"epoch": epoch + 1, "arch": "resnet50", "state_dict": net.state_dict(), "optimizer": optimizer.state_dict()}, args.checkpoint)
-            shutil.copyfile(args.checkpoint, "model_latest.pth.tar")
+            os.makedirs(args.save_dir, exist_ok=True)
+            ckpt = args.checkpoint if os.path.isabs(args.checkpoint) else os.path.join(args.save_dir, args.checkpoint)
+            torch.save({"epoch": epoch + 1, "arch": "resnet50", "state_dict": net.state_dict(), "optimizer": optimizer.state_dict()}, ckpt)
+            shutil.copyfile(ckpt, os.path.join(args.save_dir, "model_latest.pth.tar"))
     if distributed:
         dist.destroy_process_group()
 
