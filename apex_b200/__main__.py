@@ -33,13 +33,12 @@ def info() -> dict:
     so = pkg / "_kernels.so"
     out = {"version": __version__, "package": str(pkg), "torch": torch.__version__, "cuda_runtime": torch.version.cuda,
            "kernels_library": str(so) if so.exists() else None, "host_runtime": None, "declared_entry_points": len(_lib._SIGS),
-           "exported_entry_points": None, "experimental_kernels": False, "cuda_available": torch.cuda.is_available(), "devices": [],
+           "exported_entry_points": None, "cuda_available": torch.cuda.is_available(), "devices": [],
            "flags": config.flags()}
     _lib._try_load()
     if _lib._kernels is not None:
         out["host_runtime"] = getattr(_lib._C, "__file__", None)
         out["exported_entry_points"] = sum(hasattr(_lib._kernels, n) for n in _lib._SIGS)
-        out["experimental_kernels"] = hasattr(_lib._kernels, "ab_fmha_fwd")
     elif _lib._load_error is not None:
         out["load_error"] = repr(_lib._load_error)
     if torch.cuda.is_available():
@@ -60,8 +59,7 @@ def main() -> int:
     if d.get("load_error"):
         print(f"  load error: {d['load_error']}")
     else:
-        print(f"  entry points: {d['exported_entry_points']} exported / {d['declared_entry_points']} declared"
-              f"{'  (+ experimental kernels)' if d['experimental_kernels'] else ''}")
+        print(f"  entry points: {d['exported_entry_points']} exported / {d['declared_entry_points']} declared")
     if d["devices"]:
         for g in d["devices"]:
             note = "" if g["sm"] == "100" else "   <- kernels are built for sm_100a only"

@@ -77,9 +77,6 @@ def build_kernels(verbose: bool = True) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h"))
     srcs = sorted(CSRC.glob("*.cu")) + sorted(p for p in CSRC.glob("*.cpp") if p.name != "binding.cpp")
-    if os.environ.get("APEX_B200_EXPERIMENTAL") == "1":  # kernels that have not been validated on hardware yet (csrc/experimental)
-        srcs += sorted((CSRC / "experimental").glob("*.cu"))
-        headers += sorted((CSRC / "experimental").glob("*.cuh"))
     out = PKG / "_kernels.so"
     jobs = max(1, min(len(srcs), int(os.environ.get("MAX_JOBS", os.cpu_count() or 4))))
     with ThreadPoolExecutor(jobs) as ex:

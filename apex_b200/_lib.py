@@ -2,7 +2,7 @@
 
 All kernel launchers return an int (0 = ok, >0 = cudaError_t, <0 = bad argument) and take the stream as the last argument.
 Signatures are declared in ``_SIGS`` with a one-letter-per-argument code so ctypes converts/validates every call:
-  p = pointer (int or None)   i = int32   l = int64   f = float   d = double
+  p = pointer (int or None)   i = int32   l = int64   L = uint64   f = float   d = double
 On a machine with a GPU a missing/broken native library is a hard error (no silent eager fallback); without a GPU the
 pure-PyTorch reference implementations in ``apex_b200.ops.reference`` are used (CPU plumbing config of BASELINE.json).
 """
@@ -15,7 +15,7 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float, "d": ctypes.c_double}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "L": ctypes.c_uint64, "f": ctypes.c_float, "d": ctypes.c_double}
 
 _SIGS: dict[str, str] = {}
 _kernels = None

@@ -1,7 +1,7 @@
 """Functional forms of the attention blocks, with the argument lists of the reference's autograd Functions
 (apex/contrib/multihead_attn/{self,encdec}_multihead_attn_func.py, fast_*_func.py, *_norm_add_func.py, mask_softmax_dropout_func.py).
 The reference hand-writes each backward around its C++ kernels; here every form is the composition the modules use — tcgen05 GEMM projections,
-fused LayerNorm, fused masked softmax — so autograd derives the backward and there is one implementation of the math."""
+fused LayerNorm, the tcgen05 attention kernels (or fused masked softmax on the generic path) — so autograd derives the backward and there is one implementation of the math."""
 from __future__ import annotations
 
 import torch
@@ -18,11 +18,11 @@ def jit_dropout_add(x, residual, prob, is_training):
 
 
 def _split(lin, heads, parts):
-    """[t, b, parts * e] projection with per-head interleaved rows -> ``parts`` tensors [t, b, e]."""
+    """[t, b, parts * e] projection with per-head interleaved rows -> ``parts`` views [t, b, heads, head_dim] (no copies)."""
     t, b, pe = lin.shape
     e = pe // parts
     lin = lin.view(t, b, heads, parts, e // heads)
-    return [lin[:, :, :, i, :].reshape(t, b, e) for i in range(parts)]
+    return [lin[:, :, :, i, :] for i in range(parts)]
 
 
 def _masks(use_time_mask, mask):
@@ -39,6 +39,7 @@ def _self(use_time_mask, is_training, heads, scale, inputs, w_in, w_out, b_in, b
 
 def _encdec(use_time_mask, is_training, heads, scale, inputs_q, inputs_kv, w_q, w_kv, w_out, b_q, b_kv, b_out, mask, dropout_prob):
     q = fused_dense_function(inputs_q, w_q, b_q)
+    q = q.view(q.shape[0], q.shape[1], heads, q.shape[2] // heads)
     k, v = _split(fused_dense_function(inputs_kv, w_kv, b_kv), heads, 2)
     kpm, am = _masks(use_time_mask, mask)
     ctx = _attention(q, k, v, heads, scale, kpm, am, False, dropout_prob, is_training)

@@ -4,8 +4,10 @@ softmax+dropout kernels, optional pre-LayerNorm + residual add + dropout).
 
 Same constructor / forward contract ([time, batch, channel] inputs, ``key_padding_mask`` or ``attn_mask``, additive or boolean masks,
 ``include_norm_add`` pre-LN residual variant, ``impl`` in {"fast", "default"}). On B200 both impls run: input/output projections on
-the tcgen05 GEMM (apex_b200.ops.gemm through fused_dense_function), pre-LN on the fused LayerNorm kernel, the score softmax on the
-scaled-masked-softmax kernel; the two batched score/context products use torch.bmm (cuBLAS, a plain library GEMM).
+the tcgen05 GEMM (apex_b200.ops.gemm through fused_dense_function), pre-LN on the fused LayerNorm kernel, and the attention core
+(scores, key-padding / causal masking, softmax, dropout, context) in ONE tcgen05 / TMEM kernel per direction (contrib/fmha/kernels.py,
+csrc/fmha_{fwd,bwd}_sm100.cu) that reads the packed projection output in place. fp32 inputs, head dims other than 64 / 128 and
+arbitrary (non-causal) time masks compose the generic path: batched GEMM + the fused scaled-masked-softmax kernel + batched GEMM.
 
 Parameter layout is the reference's, so its checkpoints load unchanged: the packed ``in_proj_weight`` ([3 * embed, embed]) is interleaved per
 head — rows ordered [head][q | k | v][head_dim] — and ``in_proj_weight_kv`` likewise [head][k | v][head_dim]; ``separate_qkv_params``
@@ -53,31 +55,54 @@ def fast_mask_softmax_dropout_func(is_training, heads, inputs, pad_mask, mask_ad
     return p.view(bh, sq, sk)
 
 
-def _attention_kernel(q, k, v, heads, scaling):
-    """Opt-in (APEX_B200_FMHA_KERNEL=1) route through the experimental tcgen05 attention kernels for the mask-free, dropout-free case:
-    [t, b, e] -> batch-major [b * t, heads, hd] rows (the layout the kernels' 3-D TMA maps address), and back."""
-    from ..fmha import experimental as X
+_causal_cache: dict = {}
 
-    tq, b, e = q.shape
-    tk, hd = k.shape[0], e // heads
-    rows = [t.transpose(0, 1).reshape(b * n, heads, hd) for t, n in ((q, tq), (k, tk), (v, tk))]
-    out = X.FmhaFunc.apply(rows[0], rows[1], rows[2], None, None, None, None, b, False, float(scaling))
-    return out.view(b, tq, e).transpose(0, 1).contiguous()
+
+def _is_causal_mask(attn_mask: torch.Tensor) -> bool:
+    """True when the time mask is exactly "mask every key after the query" (one device comparison per distinct mask tensor version)."""
+    key = (attn_mask.data_ptr(), tuple(attn_mask.shape), attn_mask._version, attn_mask.dtype)
+    hit = _causal_cache.get(key)
+    if hit is None:
+        tq, tk = attn_mask.shape[-2:]
+        tri = torch.ones(tq, tk, dtype=torch.bool, device=attn_mask.device).triu(1)
+        hit = bool(tq == tk and attn_mask.dim() == 2 and torch.equal(attn_mask.to(torch.bool) if attn_mask.dtype != torch.bool else attn_mask, tri))
+        if len(_causal_cache) > 64:
+            _causal_cache.clear()
+        _causal_cache[key] = hit
+    return hit
+
+
+def _attention_kernel(q, k, v, heads, scaling, key_bias, causal, dropout):
+    """tcgen05 attention (contrib/fmha/kernels.py) on [t, b, heads, hd] views: every (batch, head) pair is one "head" of a single
+    batch whose rows are the time steps — the 3-D TMA maps take the row / head strides as they are, so the packed projection output
+    is consumed in place and the context comes out as [tq, b, e]."""
+    from ..fmha import kernels as K
+
+    tq, b = q.shape[0], q.shape[1]
+    hd = q.shape[-1]
+    rows = [t.flatten(1, 2) for t in (q, k, v)]                                   # [t, b * heads, hd] (a view for the packed layouts)
+    rows = [t if (t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0) else t.contiguous() for t in rows]
+    out = K.FmhaFunc.apply(rows[0], rows[1], rows[2], None, None, None, None, 1, causal, float(scaling), key_bias, float(dropout), heads)
+    return out.view(tq, b, heads * hd)
 
 
 def _attention(q, k, v, heads, scaling, key_padding_mask, attn_mask, mask_additive, dropout, training):
-    """q [tq, b, e]; k, v [tk, b, e] -> [tq, b, e]"""
-    tq, b, e = q.shape
+    """q [tq, b, heads, hd]; k, v [tk, b, heads, hd] (views) -> [tq, b, e]"""
+    tq, b, _, hd = q.shape
     tk = k.shape[0]
-    hd = e // heads
-    if key_padding_mask is None and attn_mask is None:
-        from ..fmha.fmha import _use_kernel
+    e = heads * hd
+    p_drop = float(dropout) if training else 0.0
+    from ..fmha import kernels as K
 
-        if _use_kernel(q, hd, dropout if training else 0.0):
-            return _attention_kernel(q, k, v, heads, scaling)
-    q = q.contiguous().view(tq, b * heads, hd).transpose(0, 1)
-    k = k.contiguous().view(tk, b * heads, hd).transpose(0, 1)
-    v = v.contiguous().view(tk, b * heads, hd).transpose(0, 1)
+    if K.supported(q, hd) and (attn_mask is None or _is_causal_mask(attn_mask)):
+        key_bias = None
+        if key_padding_mask is not None:
+            kp = key_padding_mask.view(b, tk)
+            key_bias = kp.float() if mask_additive else torch.zeros(b, tk, dtype=torch.float32, device=q.device).masked_fill_(kp.to(torch.bool), float("-inf"))
+        return _attention_kernel(q, k, v, heads, scaling, key_bias, attn_mask is not None, p_drop)
+    q = q.reshape(tq, b * heads, hd).transpose(0, 1)
+    k = k.reshape(tk, b * heads, hd).transpose(0, 1)
+    v = v.reshape(tk, b * heads, hd).transpose(0, 1)
     scores = torch.bmm(q, k.transpose(1, 2)) * scaling                 # [b*h, tq, tk]
     x = scores.view(b, heads, tq, tk)
     if attn_mask is not None:                                          # time mask [tq, tk] (e.g. causal): True/1 = masked
@@ -90,7 +115,7 @@ def _attention(q, k, v, heads, scaling, key_padding_mask, attn_mask, mask_additi
         p = scaled_masked_softmax(x, m, 1.0)
     else:
         p = scaled_softmax(x, 1.0)
-    p = F.dropout(p, dropout, training).view(b * heads, tq, tk)
+    p = F.dropout(p, p_drop, p_drop > 0.0).view(b * heads, tq, tk)
     ctx = torch.bmm(p.to(v.dtype), v)                                   # [b*h, tq, hd]
     return ctx.transpose(0, 1).contiguous().view(tq, b, e)
 
@@ -182,12 +207,12 @@ class SelfMultiheadAttn(_MHABase):
         else:
             w, bias = self.in_proj_weight, self.in_proj_bias
         qkv = fused_dense_function(x, w, bias)                          # [t, b, 3e]
+        t, b = qkv.shape[0], qkv.shape[1]
         if self.separate_qkv_params:
-            q, k, v = qkv.chunk(3, dim=-1)
+            q, k, v = (c.view(t, b, self.num_heads, self.head_dim) for c in qkv.chunk(3, dim=-1))
         else:   # packed projection: the reference's per-head interleave [heads, 3, head_dim] (self_multihead_attn_func.py:58-66)
-            t, b = qkv.shape[0], qkv.shape[1]
             qkv = qkv.view(t, b, self.num_heads, 3, self.head_dim)
-            q, k, v = (qkv[:, :, :, i, :].reshape(t, b, self.embed_dim) for i in range(3))
+            q, k, v = (qkv[:, :, :, i, :] for i in range(3))
         ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, self.mask_additive, self.dropout, is_training)
         out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
         return self._post(out, query, is_training), None
@@ -232,7 +257,8 @@ class EncdecMultiheadAttn(_MHABase):
         kv = fused_dense_function(key, self.in_proj_weight_kv, self.in_proj_bias_kv)
         tk, b = kv.shape[0], kv.shape[1]   # per-head interleave [heads, 2, head_dim] of the reference (encdec_multihead_attn_func.py:86-91)
         kv = kv.view(tk, b, self.num_heads, 2, self.head_dim)
-        k, v = (kv[:, :, :, i, :].reshape(tk, b, self.embed_dim) for i in range(2))
+        k, v = (kv[:, :, :, i, :] for i in range(2))
+        q = q.view(q.shape[0], b, self.num_heads, self.head_dim)
         ctx = _attention(q, k, v, self.num_heads, self.scaling, key_padding_mask, attn_mask, False, self.dropout, is_training)
         out = fused_dense_function(ctx, self.out_proj_weight, self.out_proj_bias)
         return self._post(out, query, is_training), None

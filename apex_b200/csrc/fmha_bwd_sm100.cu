@@ -1,6 +1,7 @@
-// EXPERIMENTAL (not part of the default build, not yet validated on hardware): attention backward on tcgen05.
-//   P = exp(scale * Q K^T - lse),  dP = dO V^T,  dS = scale * P o (dP - delta),  delta = rowsum(dO o O)
-//   dV = P^T dO,  dK = dS^T Q,  dQ = dS K
+// Attention backward on tcgen05 (validated on B200 against an fp32 reference: tests/test_gpu_fmha.py).
+//   P = exp(scale * Q K^T + key_bias - lse),  dP = dO V^T,  dS = scale * P o (dP - delta),  delta = rowsum(dO o O)
+//   dV = P^T dO,  dK = dS^T Q,  dQ = dS K        (with dropout: P -> P o mask / (1 - p) in dV, dP -> dP o mask / (1 - p) in dS;
+//   the mask is regenerated from the forward's Philox (seed, offset), fmha_common.cuh)
 // Spec: the backward of reference apex/contrib/csrc/fmha (fmha_dgrad_*: mma.sync, fp16, d = 64, seq <= 512) and of the softmax /
 // batched-GEMM chain in apex/contrib/csrc/multihead_attn.
 //
@@ -32,6 +33,9 @@ struct BwdParams {
   const float* lse; const float* delta;  // [rows_q, heads] fp32: log-sum-exp of the forward (natural log), rowsum(dO o O)
   void* out1; long long out1_row_stride, out1_head_stride;  // dV (DKV only)
   void* out2; long long out2_row_stride, out2_head_stride;  // dK (DKV) or dQ
+  const float* key_bias; long long key_bias_stride; int bias_div;  // bias row = bias_div ? head / bias_div : batch
+          // as in the forward
+  Dropout drop; int has_drop;
 };
 
 template <int D>
@@ -78,6 +82,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   if (ot * TO >= outer_len) return;  // whole CTA exits before any barrier is initialised
   // causal: query i attends keys <= i + diag. Inner tiles that are masked for every row of this CTA are skipped.
   const int diag = k_len - q_len;
+  const int brow = p.bias_div > 0 ? head / p.bias_div : b;
   int j0 = 0, j1 = (inner_len + TI - 1) / TI;
   if (p.causal) {
     if (DKV) { const int q_min = max(0, ot * TO - diag); j0 = min(j1, q_min / TI); }
@@ -180,7 +185,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
     const int oi = ot * TO + row;                            // index of the resident row inside its sequence
     const bool row_ok = oi < outer_len;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float my_lse2 = 0.f, my_delta = 0.f;
+    float my_lse2 = 0.f, my_delta = 0.f, my_bias2 = 0.f;
+    const bool has_bias = p.key_bias != nullptr;
+    if (DKV && has_bias && row_ok) my_bias2 = p.key_bias[(size_t)brow * p.key_bias_stride + oi] * 1.4426950408889634f;
+    const uint32_t bh = (uint32_t)(b * p.heads + head);
     if (!DKV && row_ok) {
       my_lse2 = p.lse[(size_t)(q_row0 + oi) * p.heads + head] * 1.4426950408889634f;
       my_delta = p.delta[(size_t)(q_row0 + oi) * p.heads + head];
@@ -199,6 +207,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         if (tid < TI) val *= 1.4426950408889634f;
         sw[tid] = val;                                        // tid < 64: lse * log2(e); tid >= 64: delta
         asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (has_bias) {  // per-KEY bias of this tile -> the (otherwise unused) statistics buffer
+        float* sw = stat + (jj & 1) * 2 * TI;
+        if (tid < TI) { const int ki = inner0 + tid; sw[tid] = ki < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + ki] * 1.4426950408889634f : 0.f; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&s_full[sb], sph, 220);
       mbar_wait(e_empty, eeph ^ 1, 221);  // the GEMMs of the previous tile have finished reading P' / dS' (first use: passes)
@@ -212,15 +224,28 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           T p8[8], d8[8];
+          uint4 rnd = make_uint4(0, 0, 0, 0);
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const int ii = inner0 + c0 + i + e;
             const int key = DKV ? oi : ii, qi = DKV ? ii : oi;
             const bool ok = key < k_len && qi < q_len && (!p.causal || key <= qi + diag);
             const float l2 = DKV ? st[c0 + i + e] : my_lse2, dl = DKV ? st[TI + c0 + i + e] : my_delta;
-            const float pe = ok ? ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -l2)) : 0.f;
-            p8[e] = from_f<T>(pe);
-            d8[e] = from_f<T>(pe * (__uint_as_float(rd[i + e]) - dl) * p.scale);
+            const float b2 = DKV ? my_bias2 : (has_bias ? st[c0 + i + e] : 0.f);
+            const float pe = ok ? ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, b2 - l2)) : 0.f;
+            float pd = pe, dp = __uint_as_float(rd[i + e]);
+            if (p.has_drop) {
+              if ((e & 1) == 0) {
+                const int ii0 = inner0 + c0 + i + e;
+                rnd = DKV ? philox2x2(p.drop, (uint32_t)(ii0 >> 1), (uint32_t)(oi >> 1), bh) : philox2x2(p.drop, (uint32_t)(oi >> 1), (uint32_t)(ii0 >> 1), bh);
+              }
+              const int comp = DKV ? (e & 1) * 2 + (oi & 1) : (oi & 1) * 2 + (e & 1);
+              const bool keep = philox_pick(rnd, comp) >= p.drop.thresh;
+              pd = keep ? pe * p.drop.rp : 0.f;
+              dp = keep ? dp * p.drop.rp : 0.f;
+            }
+            p8[e] = from_f<T>(pd);
+            d8[e] = from_f<T>(pe * (dp - dl) * p.scale);
           }
           const uint32_t off = sw128_offset(row, c0 + i);
           if (DKV) *reinterpret_cast<uint4*>(pbuf + off) = *reinterpret_cast<const uint4*>(p8);
@@ -277,7 +302,8 @@ AB_API int ab_fmha_bwd(const void* q, const void* k, const void* v, const void* 
                        long long k_row_stride, long long k_head_stride, long long v_row_stride, long long v_head_stride,
                        long long do_row_stride, long long do_head_stride, long long dq_row_stride, long long dq_head_stride,
                        long long dk_row_stride, long long dk_head_stride, long long dv_row_stride, long long dv_head_stride, float scale,
-                       int causal, int dt, cudaStream_t st) {
+                       int causal, const float* key_bias, long long key_bias_stride, int bias_div, float p_drop, unsigned long long seed,
+                       unsigned long long offset, int dt, cudaStream_t st) {
   if (batch <= 0 || heads <= 0 || rows_q <= 0 || rows_k <= 0) return 0;
   if ((d != 64 && d != 128) || (dt != kBF16 && dt != kF16)) return -10;
   if ((q_row_stride | q_head_stride | k_row_stride | k_head_stride | v_row_stride | v_head_stride | do_row_stride | do_head_stride |
@@ -297,6 +323,7 @@ AB_API int ab_fmha_bwd(const void* q, const void* k, const void* v, const void* 
   ab::fmha::BwdParams p;
   p.heads = heads; p.causal = causal; p.is_bf16 = is_bf16; p.cu_seqlens_q = cu_seqlens_q; p.cu_seqlens_k = cu_seqlens_k;
   p.seq_q = max_seq_q; p.seq_k = max_seq_k; p.scale = scale; p.lse = lse; p.delta = delta;
+  p.key_bias = key_bias; p.key_bias_stride = key_bias_stride; p.bias_div = bias_div; p.has_drop = p_drop > 0.f; p.drop = ab::fmha::make_dropout(p_drop, seed, offset);
   ab::fmha::BwdParams pkv = p, pq = p;
   pkv.out1 = dv; pkv.out1_row_stride = dv_row_stride; pkv.out1_head_stride = dv_head_stride;
   pkv.out2 = dk; pkv.out2_row_stride = dk_row_stride; pkv.out2_head_stride = dk_head_stride;

@@ -1,6 +1,6 @@
-// EXPERIMENTAL: pieces shared by the tcgen05 attention forward / backward kernels (not yet validated on hardware).
+// Pieces shared by the tcgen05 attention forward / backward kernels (fmha_fwd_sm100.cu, fmha_bwd_sm100.cu).
 #pragma once
-#include "../gemm_common.cuh"
+#include "gemm_common.cuh"
 
 namespace ab {
 namespace fmha {
@@ -21,6 +21,36 @@ __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2: the softmax
 __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
   const int chunk = (c >> 3) ^ (r & 7);
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + chunk * 16 + (c & 7) * 2);
+}
+
+// ---- dropout: counter-based Philox4x32-7, one call per 2 x 2 block of the (query, key) score matrix so that both the
+// query-per-lane kernels (forward, dQ) and the key-per-lane kernel (dK / dV) get two consecutive elements out of one call.
+// counter = (query >> 1, key >> 1, batch * heads + head, offset), key = seed; component (query & 1) * 2 + (key & 1).
+struct Dropout {
+  uint32_t seed_lo, seed_hi, offset, thresh;  // keep an element iff its random word >= thresh  (thresh = p * 2^32)
+  float rp;                                   // 1 / (1 - p)
+};
+static inline Dropout make_dropout(float p, unsigned long long seed, unsigned long long offset) {
+  Dropout d;
+  d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32); d.offset = (uint32_t)offset;
+  double t = (double)p * 4294967296.0;
+  d.thresh = p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  d.rp = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  return d;
+}
+__device__ __forceinline__ uint4 philox2x2(const Dropout& d, uint32_t q2, uint32_t k2, uint32_t bh) {
+  uint32_t c0 = q2, c1 = k2, c2 = bh, c3 = d.offset, k0 = d.seed_lo, k1 = d.seed_hi;
+#pragma unroll
+  for (int r = 0; r < 7; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t philox_pick(const uint4& r, int comp) {
+  return comp == 0 ? r.x : comp == 1 ? r.y : comp == 2 ? r.z : r.w;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -1,5 +1,5 @@
-// EXPERIMENTAL (not part of the default build, not yet validated on hardware): fused multi-head attention forward on tcgen05.
-//   O = softmax(scale * Q K^T + mask) V      Q, K, V: [rows, heads, d] views (any row / head stride: packed qkv, sbhd, bshd), d in {64, 128}
+// Fused multi-head attention forward on tcgen05 (validated on B200 against an fp32 reference: tests/test_gpu_fmha.py).
+//   O = dropout(softmax(scale * Q K^T + key_bias + causal mask)) V      Q, K, V: [rows, heads, d] views (any row / head stride: packed qkv, sbhd, bshd), d in {64, 128}
 // Spec: reference apex/contrib/csrc/fmha (mma.sync kernels, fp16, d = 64, seq <= 512) and the batched-GEMM + softmax pipeline of
 // apex/contrib/csrc/multihead_attn. Variable-length batches through cu_seqlens, optional causal mask.
 //
@@ -12,6 +12,8 @@
 //           O += P V_j accumulated in TMEM with no rescale; epilogue: O / l -> global, log-sum-exp optional.
 // The extra cost is one more QK^T per tile (tensor time is not the bottleneck of attention at d <= 128; exponentials are, and those
 // are computed once).
+// Optional per-key additive bias [batch, seq_k] (key-padding masks: -inf / -10000 on padded keys) and Philox dropout on P
+// (fmha_common.cuh: the backward regenerates the same mask from (seed, offset)).
 #include "fmha_common.cuh"
 
 namespace ab {
@@ -28,6 +30,9 @@ struct Params {
   float scale;
   void* out; long long out_row_stride, out_head_stride;  // elements
   float* lse;                                            // [batch? packed rows][heads] or null
+  const float* key_bias; long long key_bias_stride; int bias_div;  // bias row = bias_div ? head / bias_div : batch
+       // additive bias per (batch, key), natural-log domain; null => none
+  Dropout drop; int has_drop;
 };
 
 template <int D>
@@ -40,7 +45,8 @@ struct Smem {
   static constexpr int kVOff = kKOff + KV_STAGES * kKV;
   static constexpr int kPOff = kVOff + KV_STAGES * kKV;
   static constexpr int kBarOff = kPOff + kP;
-  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kBiasOff = kBarOff + 256;     // [2][TK] floats: key bias * log2(e) of the current / next tile
+  static constexpr int kTotal = kBiasOff + 2 * TK * 4 + 1024;
 };
 
 template <typename T, int D>
@@ -72,6 +78,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (qt * TQ >= q_len) return;  // whole CTA exits before any barrier is initialised
   // causal: query i attends keys <= i + (k_len - q_len); tiles entirely above the diagonal are skipped
   const int diag = k_len - q_len;
+  const int brow = p.bias_div > 0 ? head / p.bias_div : b;
   int n_kv = (k_len + TK - 1) / TK;
   if (p.causal) { const int last_key = min(k_len - 1, qt * TQ + TQ - 1 + diag); n_kv = last_key < 0 ? 0 : last_key / TK + 1; }
   constexpr uint32_t kTmemCols = 512;
@@ -167,10 +174,19 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool row_ok = qi < q_len;
     const float sl2 = p.scale * 1.4426950408889634f;
     int sb = 0; uint32_t sph = 0;
-    float m = -INFINITY;
+    float m = -INFINITY;                                    // row maximum of t = S * scale * log2(e) + bias * log2(e)
+    float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOff);
+    const bool has_bias = p.key_bias != nullptr;
+    auto stage_bias = [&](int j, int slot) {                // 128 softmax threads: one key each; double buffered, one barrier per tile
+      const int kidx = j * TK + row;
+      bias_s[(slot & 1) * TK + row] = kidx < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + kidx] * 1.4426950408889634f : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     auto key_ok = [&](int kidx) { return kidx < k_len && (!p.causal || kidx <= qi + diag); };
     // ---- pass 1: row maximum
     for (int j = 0; j < n_kv; j++) {
+      if (has_bias) stage_bias(j, j);
+      const float* bj = bias_s + (j & 1) * TK;
       mbar_wait(&s_full[sb], sph, 120);
       tc_fence_after();
 #pragma unroll 1
@@ -179,18 +195,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i++) if (key_ok(j * TK + c0 + i)) m = fmaxf(m, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; i++)
+          if (key_ok(j * TK + c0 + i)) m = fmaxf(m, has_bias ? fmaf(__uint_as_float(r[i]), sl2, bj[c0 + i]) : __uint_as_float(r[i]) * sl2);
       }
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
       if (++sb == 2) { sb = 0; sph ^= 1; }
     }
     if (m == -INFINITY) m = 0.f;  // fully masked row: every p becomes 0
-    // ---- pass 2: P = exp2((S - m) * sl2), l = sum P, P -> shared memory (swizzled), O accumulated by the MMA warp
+    // ---- pass 2: P = exp2(S * sl2 + bias2 - m), l = sum P, P -> shared memory (swizzled), O accumulated by the MMA warp
     float l = 0.f;
     uint32_t peph = 0;
     uint8_t* pbuf = smem + S::kPOff;
+    const uint32_t bh = (uint32_t)(b * p.heads + head);
+    const int comp_row = (qi & 1) * 2;
     for (int j = 0; j < n_kv; j++) {
+      if (has_bias) stage_bias(j, n_kv + j);                  // keeps the (tile & 1) double-buffer parity running across the two passes
+      const float* bj = bias_s + ((n_kv + j) & 1) * TK;
       mbar_wait(&s_full[sb], sph, 121);
       mbar_wait(p_empty, peph ^ 1, 122);  // the previous PV has finished reading the P buffer (first use: passes immediately)
       tc_fence_after();
@@ -202,8 +223,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float e = key_ok(j * TK + c0 + i) ? ex2_approx((__uint_as_float(r[i]) - m) * sl2) : 0.f;
+          const float e = key_ok(j * TK + c0 + i) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, (has_bias ? bj[c0 + i] : 0.f) - m)) : 0.f;
           pv[i] = e; l += e;
+        }
+        if (p.has_drop) {                                   // the row sum keeps every element; only what feeds P V is dropped
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint4 rnd = philox2x2(p.drop, (uint32_t)(qi >> 1), (uint32_t)((j * TK + c0 + i) >> 1), bh);
+            if (philox_pick(rnd, comp_row) < p.drop.thresh) pv[i] = 0.f;
+            if (philox_pick(rnd, comp_row + 1) < p.drop.thresh) pv[i + 1] = 0.f;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -223,7 +252,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
     // ---- epilogue: O / l
     if (n_kv > 0) { mbar_wait(o_full, 0, 123); tc_fence_after(); }
-    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    const float inv_l = l > 0.f ? (p.has_drop ? p.drop.rp : 1.f) / l : 0.f;
     T* orow = reinterpret_cast<T*>(p.out) + (size_t)(q_row0 + qi) * p.out_row_stride + (size_t)head * p.out_head_stride;
 #pragma unroll 1
     for (int c0 = 0; c0 < D; c0 += 32) {
@@ -239,7 +268,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-    if (row_ok && p.lse) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * p.scale + logf(l) : -INFINITY;
+    if (row_ok && p.lse) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * 0.6931471805599453f + logf(l) : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -257,8 +286,9 @@ using ab::fmha::fmha_fwd_kernel; using ab::fmha::make_map3; using ab::fmha::TQ;
 AB_API int ab_fmha_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* cu_seqlens_q, const int* cu_seqlens_k,
                        int batch, int heads, int d, long long rows_q, long long rows_k, int max_seq_q, int seq_k, long long q_row_stride,
                        long long q_head_stride, long long k_row_stride, long long k_head_stride, long long v_row_stride,
-                       long long v_head_stride, long long out_row_stride, long long out_head_stride, float scale, int causal, int dt,
-                       cudaStream_t st) {
+                       long long v_head_stride, long long out_row_stride, long long out_head_stride, float scale, int causal,
+                       const float* key_bias, long long key_bias_stride, int bias_div, float p_drop, unsigned long long seed, unsigned long long offset,
+                       int dt, cudaStream_t st) {
   if (batch <= 0 || heads <= 0 || rows_q <= 0) return 0;
   if ((d != 64 && d != 128) || (dt != kBF16 && dt != kF16)) return -10;
   if ((q_row_stride | q_head_stride | k_row_stride | k_head_stride | v_row_stride | v_head_stride | out_row_stride | out_head_stride) % 8) return -10;
@@ -271,7 +301,9 @@ AB_API int ab_fmha_fwd(const void* q, const void* k, const void* v, void* out, f
   ab::fmha::Params p;
   p.heads = heads; p.d = d; p.causal = causal; p.is_bf16 = is_bf16; p.cu_seqlens_q = cu_seqlens_q; p.cu_seqlens_k = cu_seqlens_k;
   p.seq_q = max_seq_q; p.seq_k = seq_k; p.scale = scale; p.out = out; p.out_row_stride = out_row_stride; p.out_head_stride = out_head_stride;
-  p.lse = lse;
+  p.lse = lse; p.key_bias = key_bias; p.key_bias_stride = key_bias_stride; p.bias_div = bias_div;
+  p.has_drop = p_drop > 0.f;
+  p.drop = ab::fmha::make_dropout(p_drop, seed, offset);
   const dim3 grid((max_seq_q + TQ - 1) / TQ, heads, batch);
 #define FMHA_GO(T, DD)                                                                                              \
   do {                                                                                                              \

@@ -4,7 +4,7 @@
 // everybody's slice has been written everywhere). The grid is deliberately small (<= 32 CTAs): this kernel spins on its peers and
 // is meant to run NEXT TO compute kernels (DDP bucket all-reduce during backward) -- see DESIGN.md section 7.
 // Spec: the NCCL all-reduce the reference's DistributedDataParallel issues per gradient bucket.
-#include "../symm_device.cuh"
+#include "symm_device.cuh"
 
 namespace ab {
 

@@ -6,7 +6,7 @@
 //   op 2  multicast ld_reduce (multimem.ld_reduce.add: the switch returns the sum of every rank's copy; result discarded into a checksum)
 //   op 3  multicast st        (multimem.st: one store lands in every rank's copy)
 // Driver: benchmarks/bench_symm.py (torchrun, CUDA events, max over ranks).
-#include "../symm_device.cuh"
+#include "symm_device.cuh"
 
 namespace ab {
 

@@ -1,7 +1,6 @@
-"""EXPERIMENTAL in-kernel all-reduce through the NVSwitch (csrc/experimental/nvls_allreduce.cu): ``multimem.ld_reduce`` +
-``multimem.st`` on a symmetric staging buffer, epoch barriers on the signal pad, at most 32 CTAs. Not in the default build and not
-validated on hardware yet (``APEX_B200_EXPERIMENTAL=1 python -m apex_b200._build``). Intended user: DistributedDataParallel's bucket
-all-reduce (``fused_collectives=True``), where NCCL remains the default."""
+"""In-kernel all-reduce through the NVSwitch (csrc/nvls_allreduce.cu): ``multimem.ld_reduce`` + ``multimem.st`` on a symmetric
+staging buffer, epoch barriers on the signal pad, at most 32 CTAs. User: DistributedDataParallel's bucket all-reduce
+(``fused_collectives=True``); NCCL remains the default there."""
 from __future__ import annotations
 
 import ctypes

@@ -7,7 +7,6 @@ documents and parses the environment variables the library reads.
 | ``APEX_B200_DIST_NVLS`` | ``auto`` | fused ZeRO step: ``1`` force NVSwitch multimem (NVLS), ``0`` force P2P pull/push, ``auto`` = NVLS from 4 ranks |
 | ``APEX_B200_GEMM_1CTA`` | unset | force the single-CTA tcgen05 GEMM (the 2-CTA ``cta_group::2`` kernel is the default for M, N > 128) |
 | ``APEX_B200_LN_FWD_V`` | ``4`` | LayerNorm forward: 16-byte vectors per thread (tuning knob) |
-| ``APEX_B200_FMHA_KERNEL`` | unset | ``1``: route ``contrib.fmha`` through the EXPERIMENTAL tcgen05 attention kernels when they are in the build (``APEX_B200_EXPERIMENTAL=1`` at build time) |
 | ``TORCH_SCHED_NUM_STREAMS`` (+ ``_DEBUG``, ``_SKIP_GRAPH_IDS``, ``_REUSE_CUDA_EVENT``, ``_DUMP_CODE``) | ``8`` | torchsched analogue (same names as the reference) |
 """
 from __future__ import annotations
@@ -24,12 +23,8 @@ def gemm_force_1cta() -> bool:
     return os.environ.get("APEX_B200_GEMM_1CTA") is not None
 
 
-def fmha_kernel() -> bool:
-    return os.environ.get("APEX_B200_FMHA_KERNEL") == "1"
-
-
 def flags() -> dict:
     """Every knob with its current value (for logging at start-up)."""
     return {"APEX_B200_DIST_NVLS": dist_nvls_policy(), "APEX_B200_GEMM_1CTA": gemm_force_1cta(),
-            "APEX_B200_LN_FWD_V": os.environ.get("APEX_B200_LN_FWD_V", "4"), "APEX_B200_FMHA_KERNEL": fmha_kernel(),
+            "APEX_B200_LN_FWD_V": os.environ.get("APEX_B200_LN_FWD_V", "4"),
             "TORCH_SCHED_NUM_STREAMS": os.environ.get("TORCH_SCHED_NUM_STREAMS", "8")}

@@ -330,47 +330,67 @@ def test_extension_name_modules_dense_and_distopt():
     torch.testing.assert_close(copies[0].float(), ps[0], rtol=1e-2, atol=1e-2)
 
 
-def test_attention_modules_route_through_the_kernel_entry_point_when_opted_in(monkeypatch):
-    """APEX_B200_FMHA_KERNEL=1 plumbing of contrib.fmha / contrib.multihead_attn, with the (GPU-only) kernel call replaced by an SDPA
-    stand-in that honours the same [rows, heads, d] / cu_seqlens contract: layouts, scaling and the batch-major row order must agree."""
-    from apex_b200.contrib.fmha import experimental as X
+def test_attention_modules_route_through_the_kernel_entry_point(monkeypatch):
+    """Default plumbing of contrib.fmha / contrib.multihead_attn into the tcgen05 attention kernels, with the (GPU-only) kernel call replaced
+    by an SDPA stand-in that honours the same [rows, heads, d] / cu_seqlens / key_bias / bias_div contract: layouts, scaling, masks and the
+    (time-major rows, batch x heads as heads) addressing must agree with the generic path."""
     from apex_b200.contrib.fmha import fmha as fm
+    from apex_b200.contrib.fmha import kernels as K
     from apex_b200.contrib.multihead_attn import SelfMultiheadAttn
 
     calls = []
 
-    def stand_in(q, k, v, cu_q, cu_k, max_q, max_k, batch, causal, scale):
-        calls.append((tuple(q.shape), batch, causal))
+    def stand_in(q, k, v, cu_q, cu_k, max_q, max_k, batch, causal, scale, key_bias=None, dropout_p=0.0, bias_div=0):
+        calls.append((tuple(q.shape), batch, causal, key_bias is not None, bias_div))
         rows, h, d = q.shape
         scale = d ** -0.5 if scale is None else scale
         if cu_q is None:
             bounds = [(i * (rows // batch), (i + 1) * (rows // batch), i * (k.shape[0] // batch), (i + 1) * (k.shape[0] // batch)) for i in range(batch)]
         else:
             bounds = [(int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])) for i in range(cu_q.numel() - 1)]
-        out = torch.empty_like(q)
-        for a, b_, c, e in bounds:
+        out = torch.empty(rows, h, d, dtype=q.dtype)
+        for bi, (a, b_, c, e) in enumerate(bounds):
             qq, kk, vv = q[a:b_].transpose(0, 1), k[c:e].transpose(0, 1), v[c:e].transpose(0, 1)
-            out[a:b_] = F.scaled_dot_product_attention(qq, kk, vv, is_causal=causal, scale=scale).transpose(0, 1)
+            mask = None
+            if key_bias is not None:   # [h, 1, tk]: row head // bias_div (or the batch index)
+                rowsel = torch.arange(h) // bias_div if bias_div else torch.full((h,), bi)
+                mask = key_bias[rowsel][:, None, :e - c].to(qq.dtype)
+                if causal:
+                    mask = mask + torch.zeros(b_ - a, e - c).masked_fill_(torch.ones(b_ - a, e - c, dtype=torch.bool).triu(1), float("-inf"))
+            out[a:b_] = F.scaled_dot_product_attention(qq, kk, vv, attn_mask=mask, is_causal=causal and mask is None, scale=scale).transpose(0, 1)
         return out
 
-    monkeypatch.setenv("APEX_B200_FMHA_KERNEL", "1")
-    monkeypatch.setattr(X, "available", lambda: True)
-    monkeypatch.setattr(X.FmhaFunc, "apply", staticmethod(stand_in))
-    monkeypatch.setattr(fm, "_use_kernel", lambda t, d, dropout: d in (64, 128) and dropout == 0.0)   # the real gate also demands CUDA fp16/bf16
+    monkeypatch.setattr(K, "supported", lambda t, d: d in (64, 128))   # the real gate also demands CUDA fp16 / bf16 and the native library
+    monkeypatch.setattr(K.FmhaFunc, "apply", staticmethod(stand_in))
     torch.manual_seed(0)
     lens = [5, 17, 9]
     cu = torch.tensor([0, 5, 22, 31], dtype=torch.int32)
     qkv = torch.randn(31, 3, 2, 64)
     got = fm.fmha_varlen(qkv, cu, max(lens), 0.0, False)
-    monkeypatch.setattr(fm, "_use_kernel", lambda *a: False)
-    torch.testing.assert_close(got, fm.fmha_varlen(qkv, cu, max(lens), 0.0, False), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got, fm._generic_varlen(qkv, cu, max(lens), 0.0, False), rtol=1e-4, atol=1e-5)
+    got_c = fm.fmha_varlen(qkv, cu, max(lens), 0.0, False, causal=True)
+    torch.testing.assert_close(got_c, fm._generic_varlen(qkv, cu, max(lens), 0.0, True), rtol=1e-4, atol=1e-5)
     mha = SelfMultiheadAttn(128, 2, dropout=0.0, bias=True, impl="fast").eval()
     x = torch.randn(7, 3, 128)
-    ref, _ = mha(x, is_training=False)
-    monkeypatch.setattr(fm, "_use_kernel", lambda t, d, dropout: d in (64, 128) and dropout == 0.0)
-    out, _ = mha(x, is_training=False)
-    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-5)
-    assert calls[0] == ((31, 2, 64), None, False) and calls[-1] == ((21, 2, 64), 3, False)
+    kpm = torch.zeros(3, 7, dtype=torch.bool)
+    kpm[1, 5:] = True
+    causal = torch.ones(7, 7, dtype=torch.bool).triu(1)
+    outs = [mha(x, is_training=False)[0], mha(x, key_padding_mask=kpm, is_training=False)[0], mha(x, attn_mask=causal, is_training=False)[0]]
+    monkeypatch.setattr(K, "supported", lambda t, d: False)
+    refs = [mha(x, is_training=False)[0], mha(x, key_padding_mask=kpm, is_training=False)[0], mha(x, attn_mask=causal, is_training=False)[0]]
+    for o, r in zip(outs, refs):
+        torch.testing.assert_close(o, r, rtol=1e-4, atol=1e-5)
+    assert calls[0] == ((31, 2, 64), None, False, False, 0) and calls[1][2] is True
+    assert calls[2] == ((7, 6, 64), 1, False, False, 2) and calls[3] == ((7, 6, 64), 1, False, True, 2) and calls[4] == ((7, 6, 64), 1, True, False, 2)
+
+
+def test_fmha_dropout_mask_reference_has_the_requested_keep_rate():
+    from apex_b200.contrib.fmha import kernels as K
+
+    m = K.dropout_keep_mask(2, 3, 65, 130, 0.25, (1234, 8))
+    assert m.shape == (2, 3, 65, 130) and abs(m.float().mean().item() - 0.75) < 0.02
+    assert not torch.equal(m, K.dropout_keep_mask(2, 3, 65, 130, 0.25, (1234, 12)))
+    assert K.dropout_keep_mask(1, 1, 4, 4, 0.0, (1, 0)).all()
 
 
 def test_syncbatchnorm_follows_torch_batchnorm_semantics_sweep():

@@ -119,8 +119,7 @@ def test_info_cli_reports_the_build():
     d = info()
     assert d["version"] and d["declared_entry_points"] >= 50 and "APEX_B200_DIST_NVLS" in d["flags"]
     if d["kernels_library"]:
-        experimental = 3   # ab_fmha_fwd, ab_fmha_bwd, ab_nvls_allreduce: only in APEX_B200_EXPERIMENTAL=1 builds
-        assert d["exported_entry_points"] >= d["declared_entry_points"] - experimental
+        assert d["exported_entry_points"] == d["declared_entry_points"]
 
 
 def test_dist_harness_fails_fast_with_the_failing_ranks_traceback():

@@ -7,7 +7,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("APEX_B200_UNVERIFIED_TESTS"), reason="opt-in: not yet run on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
