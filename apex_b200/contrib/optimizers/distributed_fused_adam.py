@@ -30,7 +30,7 @@ from ... import _lib
 from ...ops import amp_C
 from ...ops import reference as ref
 
-_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i i i i p p p p f f f f f i i i f p p p i i i p")
+_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p i i i p")
 
 _CHUNK = 2048  # elements handled by one CTA work item in csrc/dist_adam.cu
 _ALIGN = 64    # every parameter starts on a 64-element boundary of the flat space
@@ -95,9 +95,21 @@ class _Segment:
         self.master = torch.zeros(self.local_elems, dtype=dtype, device=dev) if opt.store_params else None
         self.remainders = torch.zeros(self.local_elems, dtype=torch.int16, device=dev) if opt.store_param_remainders else None
         self.reduced = None
-        self.norm_out = torch.zeros(2, dtype=torch.float32, device=dev)
+        # one (local, global) sum-of-squares pair per reduce-scatter launch: row b0 belongs to the launch that started at bucket b0
+        self.norm_out = torch.zeros(self.n_buckets, 2, dtype=torch.float32, device=dev)
+        self.norm_rows: list[int] = []   # rows written since the last zero_grad / step
         self.norm_partials = torch.zeros(1024, dtype=torch.float32, device=dev) if dev.type == "cuda" else None
-        self.synced = False      # reduced shard holds this step's reduce-scattered grads
+        self.bucket_synced = [False] * self.n_buckets   # reduced shard holds this step's reduce-scattered grads of bucket b
+        # overlap_grad_sync bookkeeping: parameters that intersect each bucket, and how many of them still owe a gradient this step
+        self.param_buckets = []
+        self.bucket_nparams = [0] * self.n_buckets
+        for p, off0 in zip(params, self.offsets):
+            bs = range(off0 // self.bucket_elems, (off0 + max(p.numel(), 1) - 1) // self.bucket_elems + 1)
+            self.param_buckets.append(bs)
+            for b in bs:
+                self.bucket_nparams[b] += 1
+        self.bucket_pending = list(self.bucket_nparams)
+        self.cast_params = [p for p in params if (not param_dtype.is_floating_point) or p.dtype != param_dtype]
         self.scales = None
         if getattr(opt, "with_scaled_states", False):
             # per-(parameter x shard) fragment scale factors for the 16-bit state (reference :2693-2774,2833-2860): element i of the
@@ -183,6 +195,23 @@ class _Segment:
                 self.remainders.copy_(lo)
                 del full
 
+    @property
+    def synced(self) -> bool:
+        return all(self.bucket_synced)
+
+    @synced.setter
+    def synced(self, v: bool):
+        self.bucket_synced = [bool(v)] * self.n_buckets
+        if not v:
+            self.norm_rows = []
+            self.bucket_pending = list(self.bucket_nparams)
+
+    def grad_sq(self) -> torch.Tensor:
+        """Global sum of squares of the gradients reduced so far this step (device scalar)."""
+        if len(self.norm_rows) == 1:
+            return self.norm_out[self.norm_rows[0], 1]
+        return self.norm_out[self.norm_rows, 1].sum()
+
     def attach_grads(self):
         for p in self.params:
             p.grad = self.opt._grad_view[id(p)] if p.dtype == self.grad_dtype else None
@@ -250,9 +279,13 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._step_supports_amp_scaling = True
         self._inited = False
         self._sync_enabled = True
+        self._side_stream = None          # overlap_grad_sync: per-bucket reduce-scatter launches run here while backward continues
+        self._hook_handles = []
+        self._overlap_launched = False
         self.last_nvls = False
         self.kernel_launches = 0  # number of csrc/dist_adam.cu launches so far (bench.py reports it)
         self._last_grad_norm = None
+        self._last_norm_rows: dict = {}
         if capturable:
             # graph-capturable: learning rate and step count are device tensors read by the kernel (reference :576-582)
             for group in self.param_groups:
@@ -323,10 +356,60 @@ class DistributedFusedAdam(torch.optim.Optimizer):
 
             self._pad = SignalPad.get(self.distributed_process_group, self.device)
         self._done_ctr = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._done_ctr_side = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._inited = True
+        self._install_overlap_hooks()
         self._collect_grads()  # gradients that already exist (assigned before the first step) are folded in, not dropped
         for seg in self._segments:
             seg.attach_grads()
+
+    # ---- overlap_grad_sync: reduce-scatter every bucket as soon as backward has produced all of its gradients -------------
+    def _install_overlap_hooks(self):
+        """Reference :899-913, :1827-1875: post-accumulate-grad hooks start a bucket's gradient synchronisation on a side stream
+        while backward continues. Here the synchronisation of a bucket is one MODE_RS launch of csrc/dist_adam.cu over that bucket
+        (in-kernel pulls / multimem.ld_reduce, result in the fp32 reduced shard); step() then only runs Adam + the parameter push
+        for everything that was reduced during backward. Every rank must produce gradients in the same order (same model)."""
+        if not (self.overlap_grad_sync and self.device.type == "cuda" and self.distributed_size > 1):
+            return
+        if not hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
+            return
+        for si, seg in enumerate(self._segments):
+            if not seg.fused:
+                continue
+            for pi, p in enumerate(seg.params):
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(si, pi)))
+
+    def _make_hook(self, si: int, pi: int):
+        def hook(param):
+            if not self._sync_enabled:
+                return
+            seg = self._segments[si]
+            g, gv = param.grad, self._grad_view[id(param)]
+            if g is not gv and (g is None or g.data_ptr() != gv.data_ptr()):
+                return   # gradient did not land in the buffer (user-assigned tensor): step() folds it in and syncs then
+            for b in seg.param_buckets[pi]:
+                seg.bucket_pending[b] -= 1
+                if seg.bucket_pending[b] == 0 and not seg.bucket_synced[b]:
+                    self._overlap_sync_bucket(seg, b)
+        return hook
+
+    def _overlap_sync_bucket(self, seg, b: int):
+        import os as _os
+
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._side_stream.wait_stream(cur)          # the gradients of this bucket are complete on the backward stream
+        grid = int(_os.environ.get("APEX_B200_DIST_OVERLAP_CTAS", "64"))
+        with torch.cuda.stream(self._side_stream):
+            self._launch(seg, 1, self.param_groups[seg.group_idx], 1, b, b + 1, grid=grid, done_ctr=self._done_ctr_side)
+        seg.bucket_synced[b] = True
+        self._overlap_launched = True
+
+    def _join_overlap(self):
+        if self._overlap_launched:
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
+            self._overlap_launched = False
 
     def init_param_buffer(self) -> None:
         self.init_params()
@@ -346,6 +429,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     # ---------------------------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.init_params()
+        self._join_overlap()
         for seg in self._segments:
             seg.grad_buf.zero_()
             seg.synced = False
@@ -359,6 +443,8 @@ class DistributedFusedAdam(torch.optim.Optimizer):
 
     @contextlib.contextmanager
     def no_sync(self, greedy_grad_copy: bool = False):
+        """Gradient accumulation: backward passes inside this context only accumulate into the gradient buffer; no bucket is
+        reduce-scattered until a backward pass (or step) outside of it (reference :1474-1506)."""
         old = self._sync_enabled
         self._sync_enabled = False
         try:
@@ -370,20 +456,28 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         """Fold gradients that are not already views of the gradient buffer (user-assigned / dtype-mismatched) into it."""
         for seg in self._segments:
             for p in seg.params:
-                gv = self._grad_view[id(p)]
                 g = p.grad
-                if g is None or (g.data_ptr() == gv.data_ptr() and g.dtype == gv.dtype):
+                if g is None:
                     continue
+                gv = self._grad_view[id(p)]
+                if g is gv or (g.data_ptr() == gv.data_ptr() and g.dtype == gv.dtype):
+                    continue
+                if any(seg.bucket_synced):
+                    raise RuntimeError("a gradient outside the gradient buffer appeared after part of this step's gradients were already "
+                                       "reduce-scattered (overlap_grad_sync); assign gradients before backward or disable the overlap")
                 gv.add_(g.detach().to(gv.dtype))
                 p.grad = gv if p.dtype == seg.grad_dtype else None
-                seg.synced = False
 
     # ---- gradient synchronisation -----------------------------------------------------------------------------------
     def _pre_scale(self):
         return 1.0 / (self.distributed_size * self.redundant_size) if self.average_grad_sync else 1.0
 
-    def _launch(self, seg: _Segment, mode: int, group, step: int):
-        """One csrc/dist_adam.cu launch over every bucket of a segment."""
+    def _launch(self, seg: _Segment, mode: int, group, step: int, b0: int = 0, b1: Optional[int] = None, grid: Optional[int] = None,
+                done_ctr=None):
+        """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them)."""
+        b1 = seg.n_buckets if b1 is None else b1
+        if mode != 2:
+            seg.norm_rows.append(b0)
         D = seg.D
         fused_comm = seg.fused and D > 1
         beta1, beta2 = group["betas"]
@@ -391,7 +485,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             seg.reduced = torch.zeros(seg.local_elems, dtype=torch.float32, device=self.device)
         if fused_comm:
             pad = self._pad
-            epoch = pad.next_epoch()
+            epoch, epoch_ctr = 0, pad.dev_epochs[0:1].data_ptr()   # the epoch lives on the device: graph replays keep counting
             g_arr, p_arr, pads = seg.symm_g.peer_ptr_array(), seg.symm_p.peer_ptr_array(), pad.ptrs
             # NVSwitch multicast moves 16 + 16/D GB per direction per step, plain P2P (D-1)/D * 32 GB: NVLS wins from D = 4 up
             import os as _os
@@ -402,18 +496,20 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             self.last_nvls = bool(nvls)
             rank, world = seg.rank, D
         else:
-            epoch, nvls, mcg, mcp, rank, world = 0, 0, 0, 0, 0, 1
+            epoch, epoch_ctr, nvls, mcg, mcp, rank, world = 0, None, 0, 0, 0, 0, 1
             g_arr = (ctypes.c_uint64 * 8)(seg.grad_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             p_arr = (ctypes.c_uint64 * 8)(seg.param_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             pads = (ctypes.c_uint64 * 8)(0, 0, 0, 0, 0, 0, 0, 0)
-        grid = 148 * (3 if D <= 2 else 2)
+        if grid is None:
+            grid = 148 * (3 if D <= 2 else 2)
         cap = self.capturable
+        done_ctr = self._done_ctr if done_ctr is None else done_ctr
         self.kernel_launches += 1
         _lib.fn("ab_dist_adam_step")(
             mode, nvls, ctypes.addressof(g_arr), ctypes.addressof(p_arr), ctypes.addressof(pads), mcg, mcp,
             _lib.ptr(seg.master), seg.exp_avg.data_ptr(), seg.exp_avg_sq.data_ptr(), _lib.ptr(seg.reduced), seg.bucket_elems,
-            seg.shard_elems, 0, seg.n_buckets, seg.rank, rank, world, epoch, 0, 1, seg.group_idx % 64, self._done_ctr.data_ptr(),
-            seg.norm_partials.data_ptr(), seg.norm_out.data_ptr(), self._grad_scale.data_ptr(), self._pre_scale(),
+            seg.shard_elems, b0, b1, seg.rank, rank, world, epoch, epoch_ctr, 0, 1, seg.group_idx % 64, done_ctr.data_ptr(),
+            seg.norm_partials.data_ptr(), seg.norm_out[b0].data_ptr(), self._grad_scale.data_ptr(), self._pre_scale(),
             0.0 if cap else float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), 0 if cap else int(step),
             1 if self.adam_w_mode else 0, 1 if group["bias_correction"] else 0, float(group["weight_decay"]),
             self._dummy_overflow_buf.data_ptr(), group["lr"].data_ptr() if cap else None, group["step"].data_ptr() if cap else None,
@@ -448,25 +544,42 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         if self.redundant_size > 1:
             dist.all_reduce(seg.reduced, group=self.redundant_process_group)
         sq = (seg.reduced.double() ** 2).sum().float()
-        seg.norm_out[0] = sq
+        seg.norm_out[0, 0] = sq
         tot = sq.clone()
         if D > 1:
             dist.all_reduce(tot, group=self.distributed_process_group)
-        seg.norm_out[1] = tot
+        seg.norm_out[0, 1] = tot
+        seg.norm_rows = [0]
 
     def grad_sync(self) -> None:
         """Make sure every segment's reduced shard holds the reduce-scattered gradients of this step."""
         self.init_params()
         self._collect_grads()
+        self._join_overlap()
         for seg in self._segments:
             if seg.synced:
                 continue
             group = self.param_groups[seg.group_idx]
             if seg.fused:
-                self._launch(seg, 1, group, 1)
+                self._sync_remaining(seg, group)
             else:
                 self._reduce_scatter_generic(seg)
-            seg.synced = True
+                seg.bucket_synced = [True] * seg.n_buckets
+
+    def _sync_remaining(self, seg: _Segment, group):
+        """MODE_RS over every maximal run of buckets that was not reduce-scattered during backward."""
+        b = 0
+        while b < seg.n_buckets:
+            if seg.bucket_synced[b]:
+                b += 1
+                continue
+            e = b
+            while e < seg.n_buckets and not seg.bucket_synced[e]:
+                e += 1
+            self._launch(seg, 1, group, 1, b, e)
+            for k in range(b, e):
+                seg.bucket_synced[k] = True
+            b = e
 
     def param_sync(self) -> None:
         """Parameters are pushed by the step itself on the fused path; the generic path all-gathers inside step()."""
@@ -480,7 +593,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             self.grad_sync()
             tot = torch.zeros([], dtype=torch.float32, device=self.device)
             for seg in self._segments:
-                tot = tot + seg.norm_out[1]
+                tot = tot + seg.grad_sq()
             self._grad_norm = tot.sqrt()
         return self._grad_norm.detach() * self._grad_scale_for_norm()
 
@@ -553,9 +666,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("without store_params the parameter dtype must equal the state dtype")
                 tb = amp_C.TensorTable([[p_in], [seg.exp_avg], [seg.exp_avg_sq], [g], [out_shard]])
                 d = tb.dtypes
-                _lib.fn("ab_mt_dist_adam")(*tb.head(), d[0], d[3], d[4], self._grad_scale.data_ptr(), float(group["lr"]), float(beta1),
-                                           float(beta2), float(group["eps"]), int(step), mode, bc, float(group["weight_decay"]), 0, None,
-                                           None, None, _lib.stream_ptr(self.device))
+                cap = self.capturable   # device lr / step / overflow flag: no host sync, an overflow step is skipped inside the kernel
+                _lib.fn("ab_mt_dist_adam")(*tb.head(), d[0], d[3], d[4], self._grad_scale.data_ptr(), 0.0 if cap else float(group["lr"]),
+                                           float(beta1), float(beta2), float(group["eps"]), 0 if cap else int(step), mode, bc,
+                                           float(group["weight_decay"]), 1 if cap else 0, group["lr"].data_ptr() if cap else None,
+                                           group["step"].data_ptr() if cap else None,
+                                           self._dummy_overflow_buf.data_ptr() if cap else None, _lib.stream_ptr(self.device))
         elif seg.remainders is not None:
             # bf16 parameter + int16 remainder ARE the fp32 master: (hi << 16) + lo with a signed lo (hi was rounded to nearest)
             hi, lo = out_shard.view(torch.int16).to(torch.int32), seg.remainders.to(torch.int32)
@@ -604,15 +720,20 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 loss = closure()
         self.init_params()
         self._collect_grads()
+        self._join_overlap()
 
-        need_two_phase = grad_scaler is not None or self._grad_norm is not None or any(s.synced for s in self._segments)
+        need_two_phase = grad_scaler is not None or self._grad_norm is not None or any(any(s.bucket_synced) for s in self._segments)
         if grad_scaler is not None:
             st = grad_scaler._per_optimizer_states[id(self)]
             if st["stage"] is not torch.amp.grad_scaler.OptState.UNSCALED:
                 self.unscale_grads(grad_scaler=grad_scaler)
             found = sum(v.to(self.device) for v in st["found_inf_per_device"].values())
             self._dummy_overflow_buf.copy_((found > 0).to(torch.int32).reshape(1))
-            if not self.capturable and int(self._dummy_overflow_buf.item()) != 0:
+            # kernels that take the device flag skip the update themselves; the remainder kernel and the CPU routines do not,
+            # so those configurations read the flag on the host even when capturable
+            host_skip = (not self.capturable) or any((not seg.fused) and (seg.remainders is not None or self.device.type != "cuda")
+                                                     for seg in self._segments)
+            if host_skip and int(self._dummy_overflow_buf.item()) != 0:
                 self._finish_step(skipped=True)
                 return loss
         else:
@@ -629,14 +750,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             if seg.fused:
                 if need_two_phase:
                     if not seg.synced:
-                        self._launch(seg, 1, group, step)
+                        self._sync_remaining(seg, group)
                     self._launch(seg, 2, group, step)
                 else:
                     self._launch(seg, 0, group, step)
             else:
                 if not seg.synced:
                     self._reduce_scatter_generic(seg)
-                self._generic_local_step(seg, group, step)
+                self._generic_local_step(seg, group, float(step) if (self.capturable and self.device.type != "cuda") else step)
         self._finish_step(skipped=False)
         return loss
 
@@ -645,13 +766,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         no extra collective). Device tensor; reading it on the host is the only synchronisation."""
         tot = torch.zeros([], dtype=torch.float32, device=self.device)
         for seg in self._segments:
-            tot = tot + seg.norm_out[1]
+            tot = tot + seg.norm_out[self._last_norm_rows.get(id(seg), [0]), 1].sum()
         return tot.sqrt()
 
     def _finish_step(self, skipped: bool):
+        self._last_norm_rows = {id(seg): list(seg.norm_rows) or [0] for seg in self._segments}
         for seg in self._segments:
             seg.synced = False
-            for p in seg.params:  # parameters whose dtype differs from the sync dtype get a cast copy
+            for p in seg.cast_params:  # parameters whose dtype differs from the sync dtype get a cast copy
                 if not seg.param_dtype.is_floating_point:
                     _pack_msb(self._param_view[id(p)], p.data)   # the same byte transport in the other direction
                 elif p.dtype != seg.param_dtype:
@@ -660,97 +782,211 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._grad_norm = None
 
     # ---- checkpointing: world-size independent (v2-style) -----------------------------------------------------------------
+    _CKPT_CHUNK_BYTES = 256 << 20   # full-size staging per gathered piece: the GPU never holds more than this of a gathered state
+
     def _gather_full(self, seg: _Segment, shard: torch.Tensor) -> torch.Tensor:
-        """[local_elems] shard -> full flat [padded] tensor (identical on every rank)."""
+        """[local_elems] shard -> full flat [padded] tensor (identical on every rank). Small layouts / tests only; checkpoints stream
+        through :meth:`_stream_full`."""
+        pieces = []
+        self._stream_full(seg, shard, lambda start, full: pieces.append(full.clone()))
+        return torch.cat(pieces)
+
+    def _stream_full(self, seg: _Segment, shard: torch.Tensor, consume) -> None:
+        """Walk a sharded state bucket-group by bucket-group: all-gather at most ``_CKPT_CHUNK_BYTES`` of the full tensor, hand
+        ``consume(flat_start, full_piece)`` the gathered piece, drop it, continue (reference :3226-3321 streams bucket by bucket too)."""
         D = seg.D
         sh = shard.view(seg.n_buckets, seg.shard_elems)
-        if D == 1:
-            return sh.reshape(-1).clone()
-        raw = sh.contiguous().view(torch.uint8)   # a pure data move: bytes work for every dtype on every backend (NCCL and gloo lack int16)
-        parts = [torch.empty_like(raw) for _ in range(D)]
-        dist.all_gather(parts, raw, group=self.distributed_process_group)
-        return torch.stack([p.view(shard.dtype) for p in parts], dim=1).reshape(-1)
+        per = max(1, self._CKPT_CHUNK_BYTES // max(1, seg.bucket_elems * shard.element_size()))
+        for b0 in range(0, seg.n_buckets, per):
+            b1 = min(seg.n_buckets, b0 + per)
+            piece = sh[b0:b1]
+            if D == 1:
+                full = piece.reshape(-1)
+            else:
+                raw = piece.contiguous().view(torch.uint8)   # a pure data move: bytes work for every dtype on every backend (NCCL and gloo lack int16)
+                parts = [torch.empty_like(raw) for _ in range(D)]
+                dist.all_gather(parts, raw, group=self.distributed_process_group)
+                full = torch.stack([q.view(shard.dtype).view(b1 - b0, seg.shard_elems) for q in parts], dim=1).reshape(-1)
+            consume(b0 * seg.bucket_elems, full)
+
+    def _param_spans(self, seg: _Segment, start: int, n: int):
+        """(param index, offset inside the parameter, offset inside the piece, length) of every parameter intersecting [start, start+n)."""
+        import bisect
+
+        out = []
+        i = max(0, bisect.bisect_right(seg.offsets, start) - 1)
+        end = start + n
+        while i < len(seg.params) and seg.offsets[i] < end:
+            lo, hi = seg.offsets[i], seg.offsets[i] + seg.params[i].numel()
+            a, z = max(lo, start), min(hi, end)
+            if z > a:
+                out.append((i, a - lo, a - start, z - a))
+            i += 1
+        return out
+
+    def _global_step(self):
+        st = self.param_groups[0].get("step", 0) if self.param_groups else 0
+        return int(st.item()) if torch.is_tensor(st) else int(st)
 
     def state_dict(self, *args, **kwargs):
-        """Every rank returns the same dict: per-parameter full-size CPU tensors (param master, exp_avg, exp_avg_sq), independent
-        of world size and bucket layout, so it can be reloaded under a different parallel configuration (reference v2 format,
-        :3059-3327)."""
+        """Every rank returns the same dict in the reference's v2 layout (:3059-3327): ``state["step"]`` plus, per parameter index,
+        full-size CPU tensors ``param`` (fp32 master), ``exp_avg``, ``exp_avg_sq`` — independent of world size and bucket layout, so it
+        reloads under a different parallel configuration (and in the reference). The sharded state is streamed to the host in
+        bounded pieces (double-buffered pinned staging), never materialised at full size on the GPU."""
         self.init_params()
+        self._join_overlap()
         index = {}
         i = 0
         for g in self.param_groups:
             for p in g["params"]:
                 index[id(p)] = i
                 i += 1
-        state = {}
+        step = self._global_step()
+        state = {"step": step}
+        cuda = self.device.type == "cuda"
         for seg in self._segments:
-            if seg.scales is not None:
-                fulls = {k: self._gather_full(seg, seg.load_scaled(k)) for k in ("exp_avg", "exp_avg_sq", "param")}
-            else:
-                fulls = {"exp_avg": self._gather_full(seg, seg.exp_avg), "exp_avg_sq": self._gather_full(seg, seg.exp_avg_sq)}
-            if seg.master is not None and seg.scales is None:
-                fulls["param"] = self._gather_full(seg, seg.master)
-            elif seg.remainders is not None:
-                fulls["param_remainder"] = self._gather_full(seg, seg.remainders)
-            for p, off in zip(seg.params, seg.offsets):
-                n = p.numel()
-                ent = {k: v[off:off + n].view(p.shape).cpu() for k, v in fulls.items()}
-                if "param_remainder" in ent:
-                    # the checkpoint holds the exact fp32 master: (bf16 bits << 16) + signed remainder (reference :3472-3477 does the same)
-                    hi = seg.param_buf[off:off + n].view(torch.int16).to(torch.int32)
-                    lo = fulls["param_remainder"][off:off + n].to(torch.int32)
-                    ent["param"] = ((hi << 16) + lo).view(torch.float32).view(p.shape).cpu()
-                elif "param" not in ent:
-                    ent["param"] = self._param_view[id(p)].detach().float().cpu()
-                ent["step"] = self.param_groups[seg.group_idx].get("step", 0)
+            out_dtype = torch.float32 if seg.scales is not None else seg.dtype
+            ents = []
+            for p in seg.params:
+                ent = {k: torch.zeros(p.shape, dtype=out_dtype) for k in ("param", "exp_avg", "exp_avg_sq")}
+                ent["step"] = step   # extra key (torch.optim style); the reference reads state["step"]
+                ents.append(ent)
                 state[index[id(p)]] = ent
+            stage = [None, None]     # pinned double buffer: the D2H copy of piece i overlaps the gather of piece i + 1
+            events = [None, None]
+            turn = [0]
+
+            def to_host(key, conv=None):
+                def consume(start, full):
+                    if conv is not None:
+                        full = conv(start, full)
+                    k = turn[0] & 1
+                    turn[0] += 1
+                    if cuda:
+                        if events[k] is not None:
+                            events[k].synchronize()
+                            self._drain(stage[k])
+                        if stage[k] is None or stage[k][0].numel() < full.numel() or stage[k][0].dtype != full.dtype:
+                            stage[k] = [torch.empty(full.numel(), dtype=full.dtype).pin_memory(), None]
+                        host = stage[k][0][:full.numel()]
+                        host.copy_(full, non_blocking=True)
+                        events[k] = torch.cuda.Event()
+                        events[k].record()
+                        stage[k][1] = (host, [(ents[pi][key], po, fo, ln) for pi, po, fo, ln in self._param_spans(seg, start, full.numel())])
+                    else:
+                        for pi, po, fo, ln in self._param_spans(seg, start, full.numel()):
+                            ents[pi][key].view(-1)[po:po + ln].copy_(full[fo:fo + ln])
+                return consume
+
+            def flush():
+                for k in (0, 1):
+                    if events[k] is not None:
+                        events[k].synchronize()
+                        self._drain(stage[k])
+                        events[k] = None
+
+            for key, t in (("exp_avg", seg.exp_avg), ("exp_avg_sq", seg.exp_avg_sq)):
+                self._stream_full(seg, seg.load_scaled(key) if seg.scales is not None else t, to_host(key))
+                flush()
+            if seg.scales is not None:
+                self._stream_full(seg, seg.load_scaled("param"), to_host("param"))
+            elif seg.master is not None:
+                self._stream_full(seg, seg.master, to_host("param"))
+            elif seg.remainders is not None:
+                # the checkpoint holds the exact fp32 master: (bf16 bits << 16) + signed remainder (reference :3472-3477 does the same)
+                def rebuild(start, lo):
+                    hi = seg.param_buf[start:start + lo.numel()].view(torch.int16).to(torch.int32)
+                    return ((hi << 16) + lo.to(torch.int32)).view(torch.float32)
+                self._stream_full(seg, seg.remainders, to_host("param", rebuild))
+            else:
+                for p, ent in zip(seg.params, ents):
+                    ent["param"].copy_(self._param_view[id(p)].detach().float())
+            flush()
         groups = []
         for g in self.param_groups:
-            gg = {k: v for k, v in g.items() if k != "params"}
+            gg = {k: (v.item() if torch.is_tensor(v) and v.numel() == 1 else v) for k, v in g.items() if k != "params"}
             gg["params"] = [index[id(p)] for p in g["params"]]
             groups.append(gg)
         return {"state": state, "param_groups": groups, "format": 2}
 
+    @staticmethod
+    def _drain(slot):
+        if slot is None or slot[1] is None:
+            return
+        host, spans = slot[1]
+        for dst, po, fo, ln in spans:
+            dst.view(-1)[po:po + ln].copy_(host[fo:fo + ln])
+        slot[1] = None
+
     def load_state_dict(self, state_dict) -> None:
         self.init_params()
+        self._join_overlap()
         index = {}
         i = 0
+        st = state_dict["state"]
         for g, sg in zip(self.param_groups, state_dict["param_groups"]):
             for k, v in sg.items():
-                if k != "params":
+                if k == "params":
+                    continue
+                if self.capturable and k in ("lr", "step"):
+                    # the kernels hold the ADDRESS of these device tensors (and so does any captured graph): update in place
+                    g[k].copy_(torch.as_tensor(v).reshape(1).to(g[k].dtype))
+                elif k in ("lr", "step") and torch.is_tensor(v):
+                    g[k] = v.item()
+                else:
                     g[k] = v
             for p in g["params"]:
                 index[id(p)] = i
                 i += 1
+        # the reference keeps ONE step counter in state["step"] (:3081, :3427); per-group / per-parameter values are extras of this format
+        step = st.get("step")
+        if step is None:
+            any_ent = next((e for e in st.values() if isinstance(e, dict) and "step" in e), None)
+            step = any_ent["step"] if any_ent is not None else None
+        if step is not None:
+            step = int(step.item()) if torch.is_tensor(step) else int(step)
+            for g in self.param_groups:
+                if self.capturable:
+                    g["step"].fill_(step)
+                else:
+                    g["step"] = step
         for seg in self._segments:
-            fulls = {k: torch.zeros(seg.padded, dtype=torch.float32 if seg.scales is not None else t.dtype, device=self.device)
-                     for k, t in (("exp_avg", seg.exp_avg), ("exp_avg_sq", seg.exp_avg_sq), ("param", seg.master)) if t is not None}
-            pfull = torch.zeros(seg.padded, dtype=torch.float32, device=self.device)
-            for p, off in zip(seg.params, seg.offsets):
-                ent = state_dict["state"][index[id(p)]]
-                n = p.numel()
-                for k in fulls:
-                    fulls[k][off:off + n].copy_(ent[k].reshape(-1).to(self.device, fulls[k].dtype))
-                pfull[off:off + n].copy_(ent["param"].reshape(-1).to(self.device, torch.float32))
+            Sb, B, r = seg.shard_elems, seg.bucket_elems, seg.rank
+            if seg.scales is not None:
+                tmp = {k: torch.zeros(seg.local_elems, dtype=torch.float32, device=self.device) for k in ("exp_avg", "exp_avg_sq", "param")}
+            per = max(1, self._CKPT_CHUNK_BYTES // max(1, B * 4))
+            for b0 in range(0, seg.n_buckets, per):     # bounded staging: one group of buckets of the full fp32 tensor at a time
+                b1 = min(seg.n_buckets, b0 + per)
+                start, n = b0 * B, (b1 - b0) * B
+                spans = self._param_spans(seg, start, n)
+                for key in ("exp_avg", "exp_avg_sq", "param"):
+                    full = torch.zeros(n, dtype=torch.float32, device=self.device)
+                    for pi, po, fo, ln in spans:
+                        src = st[index[id(seg.params[pi])]][key].reshape(-1)[po:po + ln]
+                        full[fo:fo + ln].copy_(src.to(self.device, torch.float32, non_blocking=True))
+                    mine = full.view(b1 - b0, seg.D, Sb)[:, r, :]
+                    if seg.scales is not None:
+                        tmp[key].view(seg.n_buckets, Sb)[b0:b1].copy_(mine)
+                    elif key != "param":
+                        getattr(seg, key).view(seg.n_buckets, Sb)[b0:b1].copy_(mine)
+                    else:
+                        if seg.master is not None:
+                            seg.master.view(seg.n_buckets, Sb)[b0:b1].copy_(mine)
+                        if seg.remainders is not None:
+                            # split the fp32 master with the SAME convention as the step kernel: signed low half, high half = (bits - lo) >> 16
+                            bits = full.view(torch.int32)
+                            lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
+                            seg.remainders.view(seg.n_buckets, Sb)[b0:b1].copy_(lo.view(b1 - b0, seg.D, Sb)[:, r, :].to(torch.int16))
+                            seg.param_buf[start:start + n].view(torch.int16).copy_(((bits - lo) >> 16).to(torch.int16))
+                        elif not seg.param_dtype.is_floating_point:
+                            _pack_msb(full.to(seg.dtype), seg.param_buf[start:start + n])
+                        else:
+                            seg.param_buf[start:start + n].copy_(full.to(seg.param_dtype))
+                    del full
             if seg.scales is not None:
                 for k in ("exp_avg", "exp_avg_sq", "param"):
-                    seg.store_scaled(k, seg.shard_view(fulls[k]).contiguous().view(-1))
-            else:
-                seg.exp_avg.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg"]))
-                seg.exp_avg_sq.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["exp_avg_sq"]))
-                if seg.master is not None:
-                    seg.master.view(seg.n_buckets, seg.shard_elems).copy_(seg.shard_view(fulls["param"]))
-            if seg.remainders is not None:
-                # split the fp32 master with the SAME convention as the step kernel: signed low half, high half = (bits - lo) >> 16
-                bits = pfull.view(torch.int32)
-                lo = ((bits & 0xFFFF) ^ 0x8000) - 0x8000
-                seg.remainders.copy_(seg.shard_view(lo).contiguous().view(-1).to(torch.int16))
-                seg.param_buf.view(torch.int16).copy_(((bits - lo) >> 16).to(torch.int16))
-            elif not seg.param_dtype.is_floating_point:
-                _pack_msb(pfull.to(seg.dtype), seg.param_buf)
-            else:
-                seg.param_buf.copy_(pfull.to(seg.param_dtype))
-            for p in seg.params:
+                    seg.store_scaled(k, tmp[k])
+            for p in seg.cast_params:
                 if not seg.param_dtype.is_floating_point:
                     _pack_msb(self._param_view[id(p)], p.data)
                 elif p.dtype != seg.param_dtype:

@@ -94,6 +94,22 @@ class TensorTable {
       if (universe_[i].grad().defined() != in_table_[i]) return false;
     if (n_ == 0) return true;
     void** ptrs = reinterpret_cast<void**>(host_.data());
+    // Non-gradient slots (parameters, moments, masters): ``p.data = ...``, ``model.half()`` / ``.to()`` or re-homing parameters into a
+    // flat buffer swap the storage behind a cached tensor. A changed address is re-uploaded, a changed dtype / size forces a rebuild
+    // (the reference rebuilds its lists every step, csrc/multi_tensor_apply.cuh:64-102, and cannot go stale).
+    for (int d = 0; d < depth_; d++) {
+      if (grad_of_[d] >= 0) continue;
+      bool changed = false;
+      for (int t = 0; t < n_; t++) {
+        const at::Tensor& x = lists_[d][t];
+        if (dtype_code(x.scalar_type()) != dtypes_[d] || x.numel() != lists_[0][t].numel() || !x.is_non_overlapping_and_dense() ||
+            x.device() != device_)
+          return false;
+        void* p = x.data_ptr();
+        if (ptrs[(size_t)d * n_ + t] != p) { ptrs[(size_t)d * n_ + t] = p; changed = true; }
+      }
+      if (changed) { upload(sizeof(void*) * (size_t)d * n_, sizeof(void*) * (size_t)n_); uploads_++; }
+    }
     for (int d = 0; d < depth_; d++) {
       const int ps = grad_of_[d];
       if (ps < 0) continue;

@@ -36,6 +36,8 @@ struct DistArgs {
   int lay_rank;  // which shard of every bucket this rank owns (== sig.rank on the fused path; sig.world may be 1 when the
                  // collectives are done by NCCL around the kernel and only the layout is sharded)
   Signal sig;
+  uint32_t* epoch_ctr;  // device-resident epoch of this pad channel (graph-replayable): the launch uses *epoch_ctr + 1 and the
+                        // closing CTA stores it back; null => sig.epoch was chosen by the host
   int chan_start, chan_end, norm_slot;
   unsigned int* done_ctr;
   float* norm_partials;  // [gridDim.x]
@@ -86,6 +88,7 @@ __device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
 // before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
 template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
 __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_step_kernel(DistArgs a) {
+  if (a.epoch_ctr) a.sig.epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u;  // every CTA reads it before the closing CTA can store
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
   constexpr int PV = sizeof(TP) * 8 / 16;
   constexpr int NP = NVLS ? 1 : DP;        // gradient sources read per element
@@ -250,7 +253,10 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
       a.norm_out[1] = tot;
     }
   }
-  if (tid == 0) *a.done_ctr = 0u;
+  if (tid == 0) {
+    *a.done_ctr = 0u;
+    if (a.epoch_ctr) *a.epoch_ctr = a.sig.epoch;
+  }
 }
 
 template <typename TG, typename TP, int MODE>
@@ -282,7 +288,7 @@ using namespace ab;
 AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const uint64_t* params, const uint64_t* pads,
                              uint64_t mc_grads, uint64_t mc_params, float* p, float* m, float* v, float* reduced,
                              long long bucket_elems, int shard_elems, int bucket_begin, int bucket_end, int lay_rank, int rank, int world,
-                             unsigned int epoch, int chan_start, int chan_end, int norm_slot, unsigned int* done_ctr,
+                             unsigned int epoch, unsigned int* epoch_ctr, int chan_start, int chan_end, int norm_slot, unsigned int* done_ctr,
                              float* norm_partials, float* norm_out, const float* grad_scale, float pre_scale, float lr, float beta1,
                              float beta2, float eps, int step, int adam_mode, int bias_correction, float decay, const int* noop,
                              const float* lr_ptr, const int* step_ptr,
@@ -298,7 +304,7 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
   a.mc_grads = (const void*)mc_grads; a.mc_params = (void*)mc_params;
   a.p = p; a.m = m; a.v = v; a.reduced = reduced;
   a.bucket_elems = bucket_elems; a.shard_elems = shard_elems; a.bucket_begin = bucket_begin; a.bucket_end = bucket_end;
-  a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch; a.lay_rank = lay_rank;
+  a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch; a.epoch_ctr = world > 1 ? epoch_ctr : nullptr; a.lay_rank = lay_rank;
   a.chan_start = chan_start; a.chan_end = chan_end; a.norm_slot = norm_slot;
   a.done_ctr = done_ctr; a.norm_partials = norm_partials; a.norm_out = norm_out;
   a.grad_scale = grad_scale; a.pre_scale = pre_scale;

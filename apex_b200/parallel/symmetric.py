@@ -284,6 +284,9 @@ class SignalPad:
         self.epoch = 0
         self.device = self.mem.device
         self.done_ctr = torch.zeros(8, dtype=torch.int32, device=self.device)
+        # device-resident epochs, one per channel: kernels that take an ``epoch_ctr`` pointer advance it themselves, so a captured
+        # CUDA graph keeps counting on replay (a host-chosen epoch would be frozen into the graph)
+        self.dev_epochs = torch.zeros(64, dtype=torch.int32, device=self.device)
 
     @classmethod
     def get(cls, group=None, device=None) -> "SignalPad":

@@ -3,18 +3,27 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--config llama3-8b]
 
-One process per GPU (the driver launches N>1 through torch.distributed.run). A "step" is a full ZeRO-2 optimizer step on
-synthetic gradients that already sit in the contiguous gradient buffer: gradient reduce-scatter over the N ranks + Adam on the
-fp32 (param, exp_avg, exp_avg_sq) shard + all-gather of the new bf16 parameters. fp32 state, bf16 grads, bf16 params
-(the configuration BASELINE.md §2 row 4 names). Strong scaling: the parameter set is fixed, each rank owns 1/N of the state.
+One process per GPU (the driver launches N>1 through torch.distributed.run). fp32 optimizer state, bf16 gradients, bf16 parameters
+(the configuration BASELINE.md section 2 row 4 names). Strong scaling: the parameter set is fixed, each rank owns 1/N of the state.
 
-Timing: W untimed warm-up steps, then exactly K steps between two CUDA events on the launching stream, bracketed by
-barrier + synchronize; value = max over ranks of ms/step. The working set (>= 44 GB per GPU at N=8, 128 GB at N=1) is far
-larger than the 126 MB L2, so no L2 flush is needed between iterations. Clocks are sampled with nvidia-smi during the timed
-region. `e2e` repeats the measurement through the public API with, every step, a host->device copy of that step's learning
-rate from pinned memory and a device->host read of one updated parameter (the step's result).
+Both arms run EXACTLY the same per-step sequence through their public API:
 
---impl reference runs the UNMODIFIED reference (baseline/_ref, NCCL + its own kernels) on the same metric and config.
+    opt.zero_grad()                      # re-attaches p.grad = view of the contiguous gradient buffer, zeroes the buffer
+    p.grad.copy_(synthetic) for every p  # stands in for backward: different values on every rank, written in place
+    opt.step()                           # reduce-scatter + Adam on the fp32 shard + all-gather of the new bf16 parameters
+
+* ``value`` / ``ms_per_step``: the metric BASELINE names — the step() call alone, one CUDA-event pair per step on the launching
+  stream, summed over the K timed steps, MAX over ranks.  ``sequence_ms_per_step`` is the whole sequence (zero_grad + refill + step)
+  between one event pair, same K steps.
+* ``e2e``: a real training step through the public API: tokens / labels copied host->device from pinned memory every step, forward
+  + backward of the SAME plain-PyTorch Llama (bench_common.llama_loss, torch.nn.functional only) over these parameters — backward
+  writes the gradients in place into the optimizer's gradient buffer and triggers whatever overlap hooks the optimizer installs —
+  then opt.step(), then a device->host read of the loss.
+The working set (>= 44 GB per GPU at N=8, 128 GB at N=1) is far larger than the 126 MB L2, so no L2 flush is needed between steps.
+Clocks are sampled with nvidia-smi during the timed region.
+
+--impl reference runs the UNMODIFIED reference (baseline/_ref, NCCL + its own kernels); that process imports only torch,
+bench_common and the reference's ``apex`` — nothing from this repo's package.
 """
 from __future__ import annotations
 
@@ -30,12 +39,16 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="llama3-8b")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-seq", type=int, default=1024, help="tokens per sequence of the end-to-end training step")
+    ap.add_argument("--e2e-batch", type=int, default=1, help="sequences per GPU of the end-to-end training step")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: --steps)")
     ap.add_argument("--fused", default="auto", choices=["auto", "off"], help="ours: in-kernel collectives (auto) or the NCCL path (off)")
+    ap.add_argument("--overlap", default="on", choices=["on", "off"], help="ours: overlap_grad_sync hooks during backward (e2e)")
     return ap.parse_args()
 
 
@@ -71,12 +84,13 @@ def main():
             os.environ.setdefault("MASTER_PORT", str(29500 + (os.getpid() % 2000)))
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    from apex_b200.models.llama import make_params, num_params
-    from apex_b200.utils.timing import ClockSampler, measured_peaks
+    from bench_common import ClockSampler, llama_loss, make_params, measured_peaks, num_params, CONFIGS
 
+    K, W = args.steps, max(args.warmup, 3)
     torch.manual_seed(1234)  # identical initial parameters on every rank
     named = make_params(args.config, device=dev, dtype=torch.bfloat16)
     params = [p for _, p in named]
+    P = dict(named)
     n_params = num_params(args.config)
     hyper = dict(lr=1e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
 
@@ -85,8 +99,8 @@ def main():
             from apex_b200.contrib.optimizers import DistributedFusedAdam
 
             opt = DistributedFusedAdam(params, dtype=torch.float32, grad_sync_dtype=torch.bfloat16, param_sync_dtype=torch.bfloat16,
-                                       capturable=True, fused_collectives=("auto" if args.fused == "auto" else False), **hyper)
-            opt.zero_grad()
+                                       capturable=True, fused_collectives=("auto" if args.fused == "auto" else False),
+                                       overlap_grad_sync=(args.overlap == "on"), **hyper)
             capturable = True
         else:
             from apex.contrib.optimizers.distributed_fused_adam import DistributedFusedAdam as RefDFA
@@ -108,99 +122,121 @@ def main():
             return 0
         raise
 
-    # synthetic gradients (different on every rank), written once straight into the contiguous gradient buffer
+    # synthetic gradient source (different on every rank): one pool as large as the largest parameter, copied into p.grad every step
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    for p in params:
-        opt.grad_buffer_view(p).normal_(0.0, 1e-2, generator=gen)
+    pool = torch.empty(max(p.numel() for p in params), device=dev, dtype=torch.bfloat16).normal_(0.0, 1e-2, generator=gen)
 
-    def one_step():
-        if args.impl == "reference":
-            for p in params:  # the reference drops .grad after folding it into the bucket; re-attach the buffer views
-                p.grad = opt.grad_buffer_view(p)
+    def refill():
+        for p in params:
+            g = p.grad if p.grad is not None else opt.grad_buffer_view(p)
+            g.copy_(pool[:p.numel()].view_as(p))
+            if p.grad is None:
+                p.grad = g
+
+    def sequence(ev=None):
+        opt.zero_grad()
+        refill()
+        if ev is not None:
+            ev[0].record()
         opt.step()
+        if ev is not None:
+            ev[1].record()
 
-    def lr_tensor():
-        lr = opt.param_groups[0]["lr"]
-        return lr if torch.is_tensor(lr) else None
-
-    for _ in range(max(args.warmup, 3)):
-        one_step()
+    for _ in range(W):
+        sequence()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
 
+    # ---- (1) the metric: step() alone, one event pair per step; (2) the whole sequence between one pair -- same K steps
     launches0 = getattr(opt, "kernel_launches", 0)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        e0.record()
-        for _ in range(args.steps):
-            one_step()
-        e1.record()
+        s0.record()
+        for i in range(K):
+            sequence(pairs[i])
+        s1.record()
         torch.cuda.synchronize()
     dist.barrier()
-    ms = e0.elapsed_time(e1) / args.steps
     launches = getattr(opt, "kernel_launches", 0) - launches0
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    step_ms = sum(a.elapsed_time(b) for a, b in pairs) / K
+    seq_ms = s0.elapsed_time(s1) / K
+    t = torch.tensor([step_ms, seq_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max, seq_max = float(t[0].item()), float(t[1].item())
 
-    # ---- end to end through the public API: pinned H2D of the step's lr, step, D2H of a result element
+    # ---- end to end through the public API: pinned H2D of tokens / labels, forward + backward (gradients land in the optimizer's
+    # buffer in place, overlap hooks fire), step, D2H of the loss
     e2e = None
     if not args.no_e2e:
-        host_lr = torch.empty(args.steps + 8, dtype=torch.float32).pin_memory()
-        for i in range(host_lr.numel()):
-            host_lr[i] = hyper["lr"] * (1.0 - 1e-3 * i)
-        dev_lr = lr_tensor()
-        scratch = torch.zeros(1, dtype=torch.float32, device=dev)
-        host_out = torch.empty(1, dtype=torch.float32).pin_memory()
-        probe = params[-1].detach().view(-1)
+        Ke = args.e2e_steps or K
+        B, S = args.e2e_batch, args.e2e_seq
+        vocab = CONFIGS[args.config]["vocab"]
+        g2 = torch.Generator().manual_seed(99 + rank)
+        host_tok = torch.randint(0, vocab, (Ke + 3, B, S), generator=g2).pin_memory()
+        host_lab = torch.randint(0, vocab, (Ke + 3, B, S), generator=g2).pin_memory()
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        e2e_launch0 = getattr(opt, "kernel_launches", 0)
+        try:
+            def e2e_step(i):
+                tok = host_tok[i].to(dev, non_blocking=True)
+                lab = host_lab[i].to(dev, non_blocking=True)
+                opt.zero_grad()
+                loss = llama_loss(P, tok, lab, args.config)
+                loss.backward()
+                opt.step()
+                host_loss.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H: the step's loss (synchronises)
+                return float(host_loss[0])
 
-        def e2e_step(i):
-            tgt = dev_lr if dev_lr is not None else scratch
-            tgt.copy_(host_lr[i:i + 1].view(tgt.shape), non_blocking=True)   # H2D: this step's learning rate
-            one_step()
-            host_out.copy_(probe[:1].float(), non_blocking=False)             # D2H: one updated parameter (synchronises)
-            return float(host_out[0])
-
-        for i in range(3):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(args.steps):
-            e2e_step(3 + i)
-        a1.record()
-        torch.cuda.synchronize()
-        te = torch.tensor([a0.elapsed_time(a1) / args.steps], device=dev, dtype=torch.float64)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": float(te.item()), "unit": "ms/step", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4,
-               "inputs": "per-step learning rate from pinned host memory; gradients are device-resident as produced by backward",
-               "lr_on_device": dev_lr is not None}
+            losses = [e2e_step(i) for i in range(3)]
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for i in range(Ke):
+                losses.append(e2e_step(3 + i))
+            a1.record()
+            torch.cuda.synchronize()
+            te = torch.tensor([a0.elapsed_time(a1) / Ke], device=dev, dtype=torch.float64)
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e = {"value": float(te.item()), "unit": "ms/step", "h2d_bytes_per_step": 2 * B * S * 8, "d2h_bytes_per_step": 4,
+                   "steps": Ke, "what": "H2D tokens+labels (pinned) -> zero_grad -> plain-PyTorch Llama forward+backward (gradients written in "
+                   "place into the optimizer's buffer) -> optimizer.step() -> D2H loss", "batch_per_gpu": B, "seq_len": S,
+                   "tokens_per_s": args.gpus * B * S / (float(te.item()) * 1e-3), "loss_first": losses[0], "loss_last": losses[-1],
+                   "gpu_launches": (getattr(opt, "kernel_launches", 0) - e2e_launch0) if args.impl == "ours" else None}
+        except torch.OutOfMemoryError as e:   # noqa: PERF203
+            e2e = {"unavailable": f"out of memory in the end-to-end step: {str(e)[:120]}"}
 
     if rank == 0:
         pk = measured_peaks()
         D = args.gpus
+        nvls = bool(getattr(opt, "last_nvls", False)) if args.impl == "ours" else None
         hbm_bytes = n_params / D * 28.0
-        link_bytes = (D - 1) / D * n_params * 2.0 * 2.0  # per direction: RS pull + AG push
+        S_bytes = n_params * 2.0
+        # bytes per direction per GPU: P2P pulls (D-1)/D of the gradients and pushes (D-1)/D of the parameters in BOTH directions;
+        # through the switch (NVLS) every rank sends its whole gradient buffer once and receives 1/D reduced, and the reverse for parameters
+        link_bytes = 0.0 if D == 1 else ((S_bytes + S_bytes / D) if nvls else 2.0 * (D - 1) / D * S_bytes)
         t_hbm = hbm_bytes / (pk["hbm_gbs"] * 1e9) * 1e3
-        t_link = link_bytes / 770e9 * 1e3
+        t_link = link_bytes / (pk["link_gbs"] * 1e9) * 1e3
         roof = max(t_hbm, t_link)
         cs = clocks.summary()
         out = {
-            "metric": "dist_fused_adam_step_ms", "value": ms_max, "unit": "ms/step", "n_gpus": D, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 grads+params / fp32 optimizer state", "data": "synthetic gradients, random-init weights", "impl": args.impl,
+            "metric": "dist_fused_adam_step_ms", "value": ms_max, "unit": "ms/step", "n_gpus": D, "steps": K,
+            "warmup": W, "ms_per_step": ms_max, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 grads+params / fp32 optimizer state", "data": "synthetic gradients / tokens, random-init weights", "impl": args.impl,
+            "timing": "sum of per-step CUDA-event pairs around optimizer.step(); zero_grad() and the gradient refill run between the pairs "
+                      "(identical in both arms)", "sequence_ms_per_step": seq_max,
             "config": {"model": args.config, "n_params": n_params, "n_tensors": len(params), "parallelism": f"zero2-dp{D}",
-                       "global_batch": None, "seq_len": None, "l2": "working set >> 126 MB L2 (no flush needed)",
-                       "fused_collectives": bool(getattr(opt, "fused_collectives", False)),
-                       "nvls": bool(getattr(opt, "last_nvls", False)) if args.impl == "ours" else None,
+                       "global_batch": D * args.e2e_batch, "seq_len": args.e2e_seq, "l2": "working set >> 126 MB L2 (no flush needed)",
+                       "fused_collectives": bool(getattr(opt, "fused_collectives", False)), "nvls": nvls,
                        "capturable": capturable},
             "clocks": {"sm_mhz": cs["sm_mhz"], "sm_max_mhz": cs["sm_max_mhz"], "reasons": cs["reasons"]},
             "gpu_launches": launches if args.impl == "ours" else None,
-            "roofline": {"t_hbm_ms": t_hbm, "t_link_ms": t_link, "bound_ms": roof, "achieved_frac": roof / ms_max,
-                         "peaks": pk["source"], "link_gbs": 770.0},
+            "roofline": {"t_hbm_ms": t_hbm, "t_link_ms": t_link, "bound_ms": roof, "achieved_frac": min(1.0, roof / ms_max),
+                         "peaks": pk["source"], "link_gbs": pk["link_gbs"], "link_source": pk["link_source"],
+                         "link_bytes_per_direction": link_bytes},
             "params_per_s": n_params / (ms_max * 1e-3),
         }
         if e2e is not None:

@@ -53,6 +53,93 @@ def dist_adam_matches_ddp_adamw(rank, world, device_type, fused, steps=4, clip=F
         torch.testing.assert_close(t, p.detach().float(), rtol=0, atol=0)
 
 
+def dist_adam_overlap_grad_sync(rank, world, device_type):
+    """overlap_grad_sync: the last micro-batch runs outside no_sync(), so post-accumulate-grad hooks reduce-scatter every bucket on the side
+    stream while backward is still running; the result must equal DDP + AdamW with micro-batch accumulation
+    (reference apex/contrib/test/optimizers/test_dist_adam.py:119-300)."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank)
+    ref_model = _model(dev)
+    dist_model = copy.deepcopy(ref_model)
+    ref_opt = torch.optim.AdamW(ref_model.parameters(), lr=3e-3, weight_decay=0.05)
+    opt = DistributedFusedAdam(dist_model.parameters(), lr=3e-3, weight_decay=0.05, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20,
+                               overlap_grad_sync=True)
+    assert opt.fused_collectives
+    g = torch.Generator().manual_seed(100 + rank)
+    for it in range(4):
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        for micro in range(3):
+            x = torch.randn(5, 7, generator=g).to(dev)
+            ref_model(x).pow(2).mean().backward()
+            if micro < 2:
+                with opt.no_sync():
+                    dist_model(x).pow(2).mean().backward()
+            else:
+                dist_model(x).pow(2).mean().backward()
+        assert any(any(seg.bucket_synced) for seg in opt._segments), "no bucket was reduce-scattered during backward"
+        for p in ref_model.parameters():
+            dist.all_reduce(p.grad)
+            p.grad /= world
+        if it % 2:
+            n_ref = torch.nn.utils.clip_grad_norm_(ref_model.parameters(), 0.05)
+            torch.testing.assert_close(opt.clip_grad_norm(0.05).cpu(), n_ref.cpu(), rtol=1e-4, atol=1e-5)
+        ref_opt.step()
+        opt.step()
+        for pr, pd in zip(ref_model.parameters(), dist_model.parameters()):
+            torch.testing.assert_close(pd, pr, rtol=1e-5, atol=1e-5)
+    n_buckets = sum(seg.n_buckets for seg in opt._segments)
+    assert n_buckets > 1 and opt.kernel_launches >= 4 * (n_buckets + 1)
+
+
+def dist_adam_cuda_graph_replays(rank, world, device_type):
+    """capturable=True at D > 1: torch.cuda.graph capture of step() + 10 replays must match an eager twin bit for bit — the collective's
+    epoch lives in device memory, so every replay signals / waits on a fresh value (reference test_dist_adam.py:834)."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(7)
+    shapes = [(257, 33), (4099,), (64, 64)]
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, device=dev).bfloat16()) for s in shapes]  # noqa: E731
+    torch.manual_seed(7)
+    pa = mk()
+    torch.manual_seed(7)
+    pb = mk()
+    kw = dict(lr=1e-2, weight_decay=0.01, device=dev, capturable=True, bucket_cap_mb=0.05, overlap_grad_sync=False)
+    a, b = DistributedFusedAdam(pa, **kw), DistributedFusedAdam(pb, **kw)
+    a.zero_grad()
+    b.zero_grad()
+    gen = torch.Generator(device=dev).manual_seed(50 + rank)
+
+    def new_grads():
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, device=dev, generator=gen).bfloat16()
+            x.grad.copy_(gr)
+            y.grad.copy_(gr)
+
+    for _ in range(2):   # warm-up (allocations, lazy init) outside the capture
+        new_grads()
+        a.step()
+        b.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    new_grads()
+    with torch.cuda.graph(graph):
+        a.step()
+    b.step()        # the capture does not execute: a is one step behind until the first replay
+    graph.replay()
+    for _ in range(10):
+        new_grads()
+        graph.replay()
+        b.step()
+    torch.cuda.synchronize()
+    for x, y in zip(pa, pb):
+        assert torch.equal(x, y)
+    for sa, sb in zip(a._segments, b._segments):
+        assert torch.equal(sa.master, sb.master) and torch.equal(sa.exp_avg_sq, sb.exp_avg_sq)
+    assert int(a.param_groups[0]["step"].item()) == int(b.param_groups[0]["step"].item()) == 14
+
+
 def dist_adam_two_dimensional_grid(rank, world, device_type):
     """distributed x redundant process-group grid (the reference's HSDP-like layout, distributed_fused_adam.py:477-560): state is sharded
     inside each distributed group of 2 and replicated across the redundant groups; 4 ranks must still equal data-parallel AdamW over all 4."""
@@ -152,7 +239,7 @@ def dist_adam_state_dict_reshards(rank, world, device_type, tmpdir):
         # same data, but the solo optimizer sees only rank 0's gradient: feed it the averaged gradient explicitly
         g.set_state(g_state)
     # (numerical continuation is checked in the single-process test; here the contract is: loads without error, same keys)
-    assert set(sd["state"].keys()) == set(range(22))
+    assert set(sd["state"].keys()) == set(range(22)) | {"step"}
     assert sd["state"][0]["exp_avg"].shape == (7, 7)
 
 

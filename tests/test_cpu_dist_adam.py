@@ -27,7 +27,8 @@ def test_single_process_matches_adamw():
     a2 = DistributedFusedAdam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1e-2, weight_decay=0.1, device="cpu", bucket_cap_mb=1.0)
     a2.load_state_dict(sd)  # different bucket layout: state must carry over
     sd2 = a2.state_dict()
-    for k in sd["state"]:
+    assert sd["state"]["step"] == sd2["state"]["step"] == 3   # the reference's v2 layout keeps ONE step counter next to the per-parameter entries
+    for k in (k for k in sd["state"] if k != "step"):
         for name in ("exp_avg", "exp_avg_sq", "param"):
             torch.testing.assert_close(sd["state"][k][name], sd2["state"][k][name])
 
@@ -380,3 +381,41 @@ def test_integer_param_sync_dtype(model_dtype, state_dtype, sync_dtype, tol):
 
 def test_two_ranks_gloo_int32_param_sync():
     run_distributed(cases.dist_adam_matches_ddp_adamw, 2, "cpu", False, 4, False, torch.float32, None, torch.int32, backend="gloo")
+
+
+def test_loads_a_checkpoint_shaped_like_the_reference_v2_state_dict():
+    """The reference's ``_state_dict_v2`` (distributed_fused_adam.py:3059-3327) keeps ONE step counter in state["step"] and per-parameter
+    {param, exp_avg, exp_avg_sq}; no per-group / per-parameter step. Loading it must resume bias correction at that step, and what this
+    implementation writes must carry the same key."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    shapes = [(5, 9), (130,)]
+    ref_like = {"state": {"step": 7}, "param_groups": [{"lr": 1e-2, "bias_correction": True, "betas": (0.9, 0.999), "eps": 1e-8,
+                                                          "weight_decay": 0.0, "params": [0, 1]}]}
+    for i, sh in enumerate(shapes):
+        ref_like["state"][i] = {"param": torch.randn(sh), "exp_avg": torch.randn(sh) * 0.1, "exp_avg_sq": torch.rand(sh) * 0.01}
+    for capturable in (False, True):
+        ps = [torch.nn.Parameter(torch.zeros(sh)) for sh in shapes]
+        qs = [torch.nn.Parameter(ref_like["state"][i]["param"].clone()) for i in range(2)]
+        a = DistributedFusedAdam(ps, lr=5e-1, device="cpu", capturable=capturable)
+        lr_obj = a.param_groups[0]["lr"]
+        a.load_state_dict(ref_like)
+        if capturable:   # the kernels / captured graphs hold the address of these tensors: loaded values are copied in place
+            assert a.param_groups[0]["lr"] is lr_obj and abs(float(lr_obj) - 1e-2) < 1e-9 and int(a.param_groups[0]["step"]) == 7
+        else:
+            assert a.param_groups[0]["step"] == 7 and a.param_groups[0]["lr"] == 1e-2
+        b = torch.optim.AdamW(qs, lr=1e-2, weight_decay=0.0)
+        for i, q in enumerate(qs):
+            b.state[q] = {"step": torch.tensor(7.0), "exp_avg": ref_like["state"][i]["exp_avg"].clone(),
+                          "exp_avg_sq": ref_like["state"][i]["exp_avg_sq"].clone()}
+        a.zero_grad()
+        for p, q in zip(ps, qs):
+            g = torch.randn(p.shape)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        a.step()
+        b.step()
+        for p, q in zip(ps, qs):
+            torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+        out = a.state_dict()
+        assert out["state"]["step"] == 8 and set(out["state"][0]) >= {"param", "exp_avg", "exp_avg_sq"}

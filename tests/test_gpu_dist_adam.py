@@ -132,6 +132,53 @@ def test_two_gpus_grad_scaler(cuda_dev):
     run_distributed(cases.dist_adam_grad_scaler_skips_on_inf, 2, "cuda", backend="nccl")
 
 
+def test_two_gpus_overlap_grad_sync(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_overlap_grad_sync, 2, "cuda", backend="nccl")
+
+
+def test_two_gpus_cuda_graph_capture_of_the_distributed_step(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_cuda_graph_replays, 2, "cuda", backend="nccl")
+
+
+def test_world1_cuda_graph_capture(cuda_dev):
+    """The same capture at world size 1 (always runs on the single-GPU tier)."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(3)
+    pa = [torch.nn.Parameter(torch.randn(513, 40, device=cuda_dev).bfloat16())]
+    pb = [torch.nn.Parameter(pa[0].detach().clone())]
+    a = DistributedFusedAdam(pa, lr=1e-2, capturable=True, bucket_cap_mb=0.05)
+    b = DistributedFusedAdam(pb, lr=1e-2, capturable=True, bucket_cap_mb=0.05)
+    a.zero_grad()
+    b.zero_grad()
+    gen = torch.Generator(device=cuda_dev).manual_seed(9)
+
+    def new_grads():
+        gr = torch.randn(pa[0].shape, device=cuda_dev, generator=gen).bfloat16()
+        pa[0].grad.copy_(gr)
+        pb[0].grad.copy_(gr)
+
+    new_grads(); a.step(); b.step()   # noqa: E702
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    new_grads()
+    with torch.cuda.graph(graph):
+        a.step()
+    b.step()
+    graph.replay()
+    for _ in range(10):
+        new_grads()
+        graph.replay()
+        b.step()
+    torch.cuda.synchronize()
+    assert torch.equal(pa[0], pb[0]) and int(a.param_groups[0]["step"].item()) == 12
+
+
 def test_four_gpus_fused(cuda_dev):
     _need(4)
     from apex_b200.testing.dist_harness import run_distributed

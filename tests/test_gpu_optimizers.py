@@ -49,6 +49,24 @@ def test_fused_adam_table_is_cached(cuda_dev):
     assert tb.uploads == 1  # built once; the grad pointers never moved so nothing was re-uploaded
 
 
+def test_fused_adam_follows_parameters_whose_storage_is_swapped(cuda_dev):
+    """``p.data = ...`` after the first step (re-homing parameters into a flat buffer, ``.to()``): the cached device table must follow the
+    new address instead of updating the old storage."""
+    from apex_b200.optimizers import FusedAdam
+    pa, pb = _params(cuda_dev), _params(cuda_dev)
+    a, b = FusedAdam(pa, lr=5e-3, weight_decay=0.1), torch.optim.AdamW(pb, lr=5e-3, weight_decay=0.1)
+    _drive(a, b, pa, pb, iters=2)
+    flat = torch.cat([p.detach().reshape(-1) for p in pa])
+    off = 0
+    for p in pa:
+        p.data = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    _drive(a, b, pa, pb, iters=3)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 1e-3
+    torch.testing.assert_close(flat, torch.cat([p.detach().reshape(-1) for p in pb]), rtol=1e-3, atol=1e-3)
+
+
 def test_fused_adam_bf16_and_frozen_param(cuda_dev):
     from apex_b200.optimizers import FusedAdam
     pa = _params(cuda_dev, torch.bfloat16)
