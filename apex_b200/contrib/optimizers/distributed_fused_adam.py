@@ -109,6 +109,7 @@ class _Segment:
             for b in bs:
                 self.bucket_nparams[b] += 1
         self.bucket_pending = list(self.bucket_nparams)
+        self.written = [False] * len(params)   # zero_grad(set_to_none=True): the buffer region of parameter i holds this step's gradient
         self.cast_params = [p for p in params if (not param_dtype.is_floating_point) or p.dtype != param_dtype]
         self.scales = None
         if getattr(opt, "with_scaled_states", False):
@@ -205,6 +206,7 @@ class _Segment:
         if not v:
             self.norm_rows = []
             self.bucket_pending = list(self.bucket_nparams)
+            self.written = [False] * len(self.params)
 
     def grad_sq(self) -> torch.Tensor:
         """Global sum of squares of the gradients reduced so far this step (device scalar)."""
@@ -282,6 +284,8 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._side_stream = None          # overlap_grad_sync: per-bucket reduce-scatter launches run here while backward continues
         self._hook_handles = []
         self._overlap_launched = False
+        self._overlap_ok = False
+        self._steal = False    # zero_grad(set_to_none=True) is in effect: gradients arrive as fresh tensors and are copied into the buffer
         self.last_nvls = False
         self.kernel_launches = 0  # number of csrc/dist_adam.cu launches so far (bench.py reports it)
         self._last_grad_norm = None
@@ -369,24 +373,32 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         while backward continues. Here the synchronisation of a bucket is one MODE_RS launch of csrc/dist_adam.cu over that bucket
         (in-kernel pulls / multimem.ld_reduce, result in the fp32 reduced shard); step() then only runs Adam + the parameter push
         for everything that was reduced during backward. Every rank must produce gradients in the same order (same model)."""
-        if not (self.overlap_grad_sync and self.device.type == "cuda" and self.distributed_size > 1):
-            return
         if not hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
             return
+        self._overlap_ok = bool(self.overlap_grad_sync and self.device.type == "cuda" and self.distributed_size > 1)
         for si, seg in enumerate(self._segments):
-            if not seg.fused:
-                continue
             for pi, p in enumerate(seg.params):
                 self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_hook(si, pi)))
 
     def _make_hook(self, si: int, pi: int):
         def hook(param):
-            if not self._sync_enabled:
-                return
             seg = self._segments[si]
             g, gv = param.grad, self._grad_view[id(param)]
-            if g is not gv and (g is None or g.data_ptr() != gv.data_ptr()):
-                return   # gradient did not land in the buffer (user-assigned tensor): step() folds it in and syncs then
+            if g is None:
+                return
+            if g is not gv and g.data_ptr() != gv.data_ptr():
+                if not self._steal:
+                    return   # a user-assigned gradient tensor: step() folds it in and syncs then
+                # zero_grad(set_to_none=True): autograd handed over a fresh gradient tensor instead of accumulating into the (zeroed)
+                # buffer view; ONE copy moves it into the buffer (4 B/element instead of zero + read-modify-write = 8) and frees it
+                if seg.written[pi]:
+                    gv.add_(g)
+                else:
+                    gv.copy_(g)
+                    seg.written[pi] = True
+                param.grad = None
+            if not (self._sync_enabled and self._overlap_ok and seg.fused):
+                return
             for b in seg.param_buckets[pi]:
                 seg.bucket_pending[b] -= 1
                 if seg.bucket_pending[b] == 0 and not seg.bucket_synced[b]:
@@ -428,12 +440,21 @@ class DistributedFusedAdam(torch.optim.Optimizer):
 
     # ---------------------------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False) -> None:
+        """``set_to_none=False`` (reference default, :1551-1598): ``p.grad`` becomes a zeroed view of the contiguous gradient buffer and
+        backward accumulates into it in place. ``set_to_none=True``: ``p.grad = None``; the buffer is NOT zeroed — every gradient that
+        autograd produces is moved into its buffer slot by the post-accumulate hook with a single copy (accumulated from the second
+        micro-batch on), which halves the gradient bookkeeping traffic; slots of parameters that got no gradient are zeroed at step()."""
         self.init_params()
         self._join_overlap()
+        self._steal = bool(set_to_none) and bool(self._hook_handles)
         for seg in self._segments:
-            seg.grad_buf.zero_()
             seg.synced = False
-            seg.attach_grads()
+            if self._steal:
+                for p in seg.params:
+                    p.grad = None
+            else:
+                seg.grad_buf.zero_()
+                seg.attach_grads()
         self._grad_scale.fill_(1.0)
         self._grad_norm = None
 
@@ -455,9 +476,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     def _collect_grads(self):
         """Fold gradients that are not already views of the gradient buffer (user-assigned / dtype-mismatched) into it."""
         for seg in self._segments:
-            for p in seg.params:
+            for pi, p in enumerate(seg.params):
                 g = p.grad
                 if g is None:
+                    if self._steal and not seg.written[pi]:
+                        self._grad_view[id(p)].zero_()   # no gradient this step: the slot must not keep the previous step's values
+                        seg.written[pi] = True
                     continue
                 gv = self._grad_view[id(p)]
                 if g is gv or (g.data_ptr() == gv.data_ptr() and g.dtype == gv.dtype):
@@ -465,16 +489,21 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 if any(seg.bucket_synced):
                     raise RuntimeError("a gradient outside the gradient buffer appeared after part of this step's gradients were already "
                                        "reduce-scattered (overlap_grad_sync); assign gradients before backward or disable the overlap")
-                gv.add_(g.detach().to(gv.dtype))
-                p.grad = gv if p.dtype == seg.grad_dtype else None
+                if self._steal and not seg.written[pi]:
+                    gv.copy_(g.detach())
+                    seg.written[pi] = True
+                else:
+                    gv.add_(g.detach().to(gv.dtype))
+                p.grad = None if self._steal else (gv if p.dtype == seg.grad_dtype else None)
 
     # ---- gradient synchronisation -----------------------------------------------------------------------------------
     def _pre_scale(self):
         return 1.0 / (self.distributed_size * self.redundant_size) if self.average_grad_sync else 1.0
 
     def _launch(self, seg: _Segment, mode: int, group, step: int, b0: int = 0, b1: Optional[int] = None, grid: Optional[int] = None,
-                done_ctr=None):
-        """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them)."""
+                done_ctr=None, lane: int = 0, force_nvls: Optional[bool] = None):
+        """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them). ``lane`` selects an independent set
+        of signal channels / epoch counter / scratch so that two launches can be in flight at once (hybrid NVLS + P2P step)."""
         b1 = seg.n_buckets if b1 is None else b1
         if mode != 2:
             seg.norm_rows.append(b0)
@@ -485,13 +514,15 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             seg.reduced = torch.zeros(seg.local_elems, dtype=torch.float32, device=self.device)
         if fused_comm:
             pad = self._pad
-            epoch, epoch_ctr = 0, pad.dev_epochs[0:1].data_ptr()   # the epoch lives on the device: graph replays keep counting
+            epoch, epoch_ctr = 0, pad.dev_epochs[2 * lane:2 * lane + 1].data_ptr()   # the epoch lives on the device: graph replays keep counting
             g_arr, p_arr, pads = seg.symm_g.peer_ptr_array(), seg.symm_p.peer_ptr_array(), pad.ptrs
             # NVSwitch multicast moves 16 + 16/D GB per direction per step, plain P2P (D-1)/D * 32 GB: NVLS wins from D = 4 up
             import os as _os
 
             pol = _os.environ.get("APEX_B200_DIST_NVLS", "auto")
             nvls = int(seg.symm_g.has_multicast and seg.symm_p.has_multicast and (pol == "1" or (pol == "auto" and D >= 4)))
+            if force_nvls is not None:
+                nvls = int(bool(force_nvls) and seg.symm_g.has_multicast and seg.symm_p.has_multicast)
             mcg, mcp = seg.symm_g.mc_ptr, seg.symm_p.mc_ptr
             self.last_nvls = bool(nvls)
             rank, world = seg.rank, D
@@ -508,12 +539,45 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         _lib.fn("ab_dist_adam_step")(
             mode, nvls, ctypes.addressof(g_arr), ctypes.addressof(p_arr), ctypes.addressof(pads), mcg, mcp,
             _lib.ptr(seg.master), seg.exp_avg.data_ptr(), seg.exp_avg_sq.data_ptr(), _lib.ptr(seg.reduced), seg.bucket_elems,
-            seg.shard_elems, b0, b1, seg.rank, rank, world, epoch, epoch_ctr, 0, 1, seg.group_idx % 64, done_ctr.data_ptr(),
-            seg.norm_partials.data_ptr(), seg.norm_out[b0].data_ptr(), self._grad_scale.data_ptr(), self._pre_scale(),
+            seg.shard_elems, b0, b1, seg.rank, rank, world, epoch, epoch_ctr, 2 * lane, 2 * lane + 1, (seg.group_idx % 32) + 32 * lane,
+            done_ctr.data_ptr(), seg.norm_partials[512 * lane:].data_ptr(), seg.norm_out[b0].data_ptr(), self._grad_scale.data_ptr(), self._pre_scale(),
             0.0 if cap else float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), 0 if cap else int(step),
             1 if self.adam_w_mode else 0, 1 if group["bias_correction"] else 0, float(group["weight_decay"]),
             self._dummy_overflow_buf.data_ptr(), group["lr"].data_ptr() if cap else None, group["step"].data_ptr() if cap else None,
             _lib.dt(seg.grad_dtype), _lib.dt(seg.param_dtype), grid, _lib.stream_ptr(self.device))
+
+    def _hybrid_split(self, seg: _Segment) -> int:
+        """Buckets [0, k) go through the NVSwitch (multimem), [k, n) over plain P2P, as two co-resident kernels: NVLS reduction /
+        multicast tops out below the link rate (the switch engines, not the wires, are the limit), so the P2P kernel uses what is left.
+        ``APEX_B200_DIST_HYBRID`` = fraction of the buckets on the NVLS side (1 = all NVLS, 0 = all P2P; default 1 below 4 ranks)."""
+        import os as _os
+
+        D = seg.D
+        if not (seg.fused and D >= 4 and seg.symm_g.has_multicast and seg.symm_p.has_multicast and seg.n_buckets >= 8):
+            return -1
+        if _os.environ.get("APEX_B200_DIST_NVLS", "auto") not in ("auto",):
+            return -1
+        f = float(_os.environ.get("APEX_B200_DIST_HYBRID", "1.0"))
+        if f >= 1.0 or f <= 0.0:
+            return -1
+        return max(1, min(seg.n_buckets - 1, int(round(seg.n_buckets * f))))
+
+    def _fused_pass(self, seg: _Segment, group, step):
+        """MODE_FUSED over the whole segment: one launch, or the hybrid pair (NVLS lane 0 on the current stream, P2P lane 1 on a forked one)."""
+        k = self._hybrid_split(seg)
+        if k < 0:
+            self._launch(seg, 0, group, step)
+            return
+        if getattr(self, "_lane_stream", None) is None:
+            self._lane_stream = torch.cuda.Stream(device=self.device)
+            self._done_ctr_lane = torch.zeros(4, dtype=torch.int32, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._lane_stream.wait_stream(cur)
+        # one CTA per SM each, launched in the same order on every rank: both grids are resident together, neither can starve the other
+        self._launch(seg, 0, group, step, 0, k, grid=148, lane=0, force_nvls=True)
+        with torch.cuda.stream(self._lane_stream):
+            self._launch(seg, 0, group, step, k, seg.n_buckets, grid=148, done_ctr=self._done_ctr_lane, lane=1, force_nvls=False)
+        cur.wait_stream(self._lane_stream)
 
     def _reduce_scatter_generic(self, seg: _Segment):
         """NCCL / gloo reduce-scatter of every bucket into the fp32 reduced shard (the reference's data path)."""
@@ -753,7 +817,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                         self._sync_remaining(seg, group)
                     self._launch(seg, 2, group, step)
                 else:
-                    self._launch(seg, 0, group, step)
+                    self._fused_pass(seg, group, step)
             else:
                 if not seg.synced:
                     self._reduce_scatter_generic(seg)

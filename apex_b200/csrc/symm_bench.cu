@@ -1,10 +1,11 @@
-// EXPERIMENTAL (not part of the default build, not yet run): bandwidth probes for the symmetric heap -- the "8-GPU P2P bandwidth, NVLS
+// Bandwidth probes for the symmetric heap -- the "8-GPU P2P bandwidth, NVLS
 // multimem bandwidth, barrier latency" unit measurements of SURVEY.md section 7.2 step 5. Each probe moves `bytes` once per launch with
 // 16-byte accesses and `unroll` independent accesses in flight per thread (bytes in flight per SM, not threads, set NVLink bandwidth).
 //   op 0  peer read    local <- peer   (ld.global.L1::no_allocate from the peer mapping)
 //   op 1  peer write   peer  <- local  (st to the peer mapping)
 //   op 2  multicast ld_reduce (multimem.ld_reduce.add: the switch returns the sum of every rank's copy; result discarded into a checksum)
 //   op 3  multicast st        (multimem.st: one store lands in every rank's copy)
+//   op 4  multicast ld_reduce of src -> multimem.st into dst (both directions of every link busy at once: the all-reduce / fused ZeRO pattern)
 // Driver: benchmarks/bench_symm.py (torchrun, CUDA events, max over ranks).
 #include "symm_device.cuh"
 
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(512) symm_bench_kernel(int op, const char* src
     for (int u = 0; u < U; u++) {
       const long long k = i + u * stride;
       if (op == 0) v[u] = ld_peer16(src + k * 16);
-      else if (op == 2) v[u] = multimem_ld_reduce16<float>(src + k * 16);
+      else if (op == 2 || op == 4) v[u] = multimem_ld_reduce16<float>(src + k * 16);
       else v[u] = *reinterpret_cast<const uint4*>(src + k * 16);   // local read feeding a remote / multicast store
     }
 #pragma unroll
@@ -29,15 +30,15 @@ __global__ void __launch_bounds__(512) symm_bench_kernel(int op, const char* src
       const long long k = i + u * stride;
       if (op == 0) *reinterpret_cast<uint4*>(dst + k * 16) = v[u];
       else if (op == 1) st_peer16(dst + k * 16, v[u]);
-      else if (op == 3) multimem_st16(dst + k * 16, v[u]);
+      else if (op == 3 || op == 4) multimem_st16(dst + k * 16, v[u]);
       else { acc.x ^= v[u].x; acc.y ^= v[u].y; acc.z ^= v[u].z; acc.w ^= v[u].w; }
     }
   }
   for (; i < nvec; i += stride) {  // tail
-    uint4 v = (op == 0) ? ld_peer16(src + i * 16) : (op == 2) ? multimem_ld_reduce16<float>(src + i * 16) : *reinterpret_cast<const uint4*>(src + i * 16);
+    uint4 v = (op == 0) ? ld_peer16(src + i * 16) : (op == 2 || op == 4) ? multimem_ld_reduce16<float>(src + i * 16) : *reinterpret_cast<const uint4*>(src + i * 16);
     if (op == 0) *reinterpret_cast<uint4*>(dst + i * 16) = v;
     else if (op == 1) st_peer16(dst + i * 16, v);
-    else if (op == 3) multimem_st16(dst + i * 16, v);
+    else if (op == 3 || op == 4) multimem_st16(dst + i * 16, v);
     else { acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
   }
   if (op == 2 && (acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x5eedf00du) *sink = 1.f;  // keeps the reduce loads alive
@@ -49,7 +50,7 @@ using namespace ab;
 
 // src / dst: device addresses valid in THIS process (local buffer, peer mapping or multicast mapping, as the op requires); bytes % 16 == 0.
 AB_API int ab_symm_bench(int op, const void* src, void* dst, long long bytes, int ctas, int unroll, float* sink, cudaStream_t st) {
-  if (op < 0 || op > 3 || bytes <= 0 || bytes % 16) return -3;
+  if (op < 0 || op > 4 || bytes <= 0 || bytes % 16) return -3;
   if (ctas <= 0) ctas = 148 * 2;
   const long long nvec = bytes / 16;
   const char* s = static_cast<const char*>(src);

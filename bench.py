@@ -182,7 +182,7 @@ def main():
             def e2e_step(i):
                 tok = host_tok[i].to(dev, non_blocking=True)
                 lab = host_lab[i].to(dev, non_blocking=True)
-                opt.zero_grad()
+                opt.zero_grad(set_to_none=True)   # same call in both arms
                 loss = llama_loss(P, tok, lab, args.config)
                 loss.backward()
                 opt.step()
@@ -202,7 +202,7 @@ def main():
             te = torch.tensor([a0.elapsed_time(a1) / Ke], device=dev, dtype=torch.float64)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": float(te.item()), "unit": "ms/step", "h2d_bytes_per_step": 2 * B * S * 8, "d2h_bytes_per_step": 4,
-                   "steps": Ke, "what": "H2D tokens+labels (pinned) -> zero_grad -> plain-PyTorch Llama forward+backward (gradients written in "
+                   "steps": Ke, "what": "H2D tokens+labels (pinned) -> zero_grad(set_to_none=True) -> plain-PyTorch Llama forward+backward (gradients written in "
                    "place into the optimizer's buffer) -> optimizer.step() -> D2H loss", "batch_per_gpu": B, "seq_len": S,
                    "tokens_per_s": args.gpus * B * S / (float(te.item()) * 1e-3), "loss_first": losses[0], "loss_last": losses[-1],
                    "gpu_launches": (getattr(opt, "kernel_launches", 0) - e2e_launch0) if args.impl == "ours" else None}

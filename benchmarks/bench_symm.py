@@ -1,4 +1,4 @@
-"""Symmetric-heap micro-benchmarks (needs the experimental build: APEX_B200_EXPERIMENTAL=1 python -m apex_b200._build).
+"""Symmetric-heap micro-benchmarks.
 
     python -m torch.distributed.run --standalone --local-addr 127.0.0.1 --nproc-per-node N benchmarks/bench_symm.py [--mb 256]
 
@@ -39,7 +39,10 @@ def timed(fn, iters, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mb", type=int, default=256)
-    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ctas", type=int, nargs="*", default=None)
+    ap.add_argument("--unroll", type=int, nargs="*", default=None)
+    ap.add_argument("--write-peaks", action="store_true", help="store the best observed link rate in profiles/results/link_peaks.json")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -49,6 +52,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     nbytes = args.mb << 20
     mem = SymmetricMemory(nbytes, multicast=True, tag="bw")
+    mem2 = SymmetricMemory(nbytes, multicast=True, tag="bw2")
     local_buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     mem.buffer.view(torch.float32).fill_(1.0)
     sink = torch.zeros(1, device=dev)
@@ -56,22 +60,35 @@ def main():
     peer = mem.peer_ptrs[(rank + 1) % world]
     stream = lambda: _lib.stream_ptr(dev)  # noqa: E731
     rows = []
-    probes = [("peer_read", 0, peer, local_buf.data_ptr()), ("peer_write", 1, local_buf.data_ptr(), peer)]
-    if mem.has_multicast:
+    # (name, op, src, dst, bytes moved by this rank's kernel, link bytes per direction on THIS GPU per payload byte)
+    probes = [("peer_read", 0, peer, local_buf.data_ptr(), nbytes, 1.0), ("peer_write", 1, local_buf.data_ptr(), peer, nbytes, 1.0)]
+    if mem.has_multicast and mem2.has_multicast:
         per_rank = nbytes // world // 16 * 16       # every rank reduces / broadcasts its own slice, as the ZeRO kernel does
         off = rank * per_rank
-        probes += [("nvls_ld_reduce", 2, mem.mc_ptr + off, local_buf.data_ptr()), ("nvls_st", 3, local_buf.data_ptr(), mem.mc_ptr + off)]
-    for name, op, src, dst in probes:
-        size = nbytes if op < 2 else nbytes // world // 16 * 16
-        for unroll in (1, 2, 4, 8):
-            ms = timed(lambda: _lib.fn("ab_symm_bench")(op, src, dst, size, 0, unroll, sink.data_ptr(), stream()), args.iters, dev)
-            # NVLS: bytes on this GPU's links = the slice x (world - 1) for ld_reduce (egress, every copy is read) or x 1 for st (egress)
-            rows.append({"op": name, "unroll": unroll, "ms": ms, "payload_GBps": size / ms / 1e6, "world": world})
+        # every rank's ld_reduce pulls its slice out of ALL GPUs: this GPU's egress = world x slice; multimem.st: ingress = world x slice
+        probes += [("nvls_ld_reduce", 2, mem.mc_ptr + off, local_buf.data_ptr(), per_rank, float(world)),
+                   ("nvls_st", 3, local_buf.data_ptr(), mem.mc_ptr + off, per_rank, float(world)),
+                   ("nvls_ld_reduce+st", 4, mem.mc_ptr + off, mem2.mc_ptr + off, per_rank, float(world) + 1.0)]
+    best = {}
+    for name, op, src, dst, size, link_factor in probes:
+        for ctas in (args.ctas or [74, 148, 296, 592]):
+            for unroll in (args.unroll or [2, 8]):
+                ms = timed(lambda: _lib.fn("ab_symm_bench")(op, src, dst, size, ctas, unroll, sink.data_ptr(), stream()), args.iters, dev)
+                link = size * link_factor / ms / 1e6
+                rows.append({"op": name, "ctas": ctas, "unroll": unroll, "ms": ms, "payload_GBps": size / ms / 1e6,
+                             "link_GBps_per_direction": link, "world": world})
+                best[name] = max(best.get(name, 0.0), link)
     ms = timed(lambda: pad.barrier(channel=50), 200, dev)
     rows.append({"op": "barrier", "us": ms * 1e3, "world": world})
     if rank == 0:
         for r in rows:
             print(json.dumps(r))
+        print(json.dumps({"summary": best, "world": world, "mb": args.mb}))
+        if args.write_peaks:
+            out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "results", "link_peaks.json")
+            json.dump({"link_gbs": max(best.values()), "per_op_best_GBps": best, "world": world, "mb": args.mb,
+                       "how": "benchmarks/bench_symm.py: best sustained bytes per direction on one GPU's links over the probes "
+                              "(P2P read / write, multimem.ld_reduce, multimem.st, ld_reduce+st)"}, open(out, "w"), indent=1)
     dist.destroy_process_group()
 
 

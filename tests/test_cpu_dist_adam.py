@@ -419,3 +419,32 @@ def test_loads_a_checkpoint_shaped_like_the_reference_v2_state_dict():
             torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
         out = a.state_dict()
         assert out["state"]["step"] == 8 and set(out["state"][0]) >= {"param", "exp_avg", "exp_avg_sq"}
+
+
+def test_zero_grad_set_to_none_moves_gradients_with_one_copy_and_matches_the_default_mode():
+    """zero_grad(set_to_none=True): gradients arrive as fresh tensors, the post-accumulate hook copies them into the (un-zeroed) buffer and
+    frees them; micro-batch accumulation, a parameter without gradient in some steps and stale buffer contents must all behave like the
+    default mode (zeroed buffer views + in-place accumulation)."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+
+    def run(set_to_none):
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Linear(9, 17), torch.nn.Tanh(), torch.nn.Linear(17, 5))
+        extra = torch.nn.Parameter(torch.randn(33))
+        opt = DistributedFusedAdam(list(m.parameters()) + [extra], lr=1e-2, weight_decay=0.01, device="cpu", bucket_cap_mb=0.001)
+        g = torch.Generator().manual_seed(1)
+        for it in range(5):
+            opt.zero_grad(set_to_none=set_to_none)
+            for micro in range(2):
+                x = torch.randn(4, 9, generator=g)
+                loss = m(x).pow(2).mean()
+                if it % 2 == 0:   # `extra` gets a gradient only every other step
+                    loss = loss + (extra * x.mean()).sum()
+                loss.backward()
+            if set_to_none:
+                assert all(p.grad is None for p in m.parameters())   # consumed by the hook
+            opt.step()
+        return [p.detach().clone() for p in list(m.parameters()) + [extra]]
+
+    for a, b in zip(run(False), run(True)):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
