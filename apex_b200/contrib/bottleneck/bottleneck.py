@@ -1,15 +1,21 @@
 """ResNet bottleneck block with frozen BN folded into per-channel scale/bias, and its spatially (H-) parallel variant.
 Reference: apex/contrib/bottleneck/bottleneck.py:32-1410 over ``fast_bottleneck`` (26 cuDNN-frontend fused graphs, 3.6k lines).
-Convolutions are cuDNN here as in the reference; the scale/bias/ReLU/residual tails are single fused pointwise expressions.
-``SpatialBottleneck`` shards the activation along H over ``spatial_group_size`` ranks and exchanges one-row halos around the 3x3
-convolution through a :mod:`halo_exchangers` transport (peer memory over NVLink by default)."""
+Convolutions are cuDNN here as in the reference; every scale / bias / residual / ReLU tail is ONE hand-written kernel in place over
+the convolution output, and every backward tail (ReLU mask, residual gradient, scaled gradient for cuDNN's dgrad / wgrad, per-channel
+reductions) is one kernel too (contrib/conv_bias_relu -> csrc/conv_epilogue.cu), behind custom autograd Functions.
+``SpatialBottleneck`` shards the activation along H over ``spatial_group_size`` ranks: the one-row halo exchange around the 3x3
+convolution runs on a side stream WHILE the interior rows are convolved; only the two boundary rows wait for the halos. Its backward
+sends the halo-row gradients back to the neighbours the same way, overlapped with the weight gradient (reference
+apex/contrib/bottleneck/bottleneck.py:304-830: three side streams, same split)."""
 from __future__ import annotations
 
 import functools
 
 import torch
-import torch.nn.functional as F
+import torch.nn.functional as F  # noqa: F401  (re-exported for users of the reference's module namespace)
 from torch import nn
+
+from ..conv_bias_relu.conv_bias_relu import _cl, epilogue_bwd, epilogue_fwd, fused_conv_epilogue
 
 
 def kaiming_uniform_(tensor, a=0, mode="fan_in", nonlinearity="leaky_relu"):
@@ -116,22 +122,96 @@ class Bottleneck(nn.Module):
     def _from_nchw(self, x):
         return x.permute(0, 2, 3, 1) if self.explicit_nhwc else x
 
-    def _conv2(self, out):
-        return self.conv2(out)
+    def _conv2(self, out, s2, b2):
+        return fused_conv_epilogue(out, self.conv2.weight, bias=b2, scale=s2, stride=1, padding=1, relu=True)
 
     def forward(self, x):
         x = self._to_nchw(x)
         (s1, b1), (s2, b2), (s3, b3) = self._folded(0, self.bn1), self._folded(1, self.bn2), self._folded(2, self.bn3)
-        out = F.relu(self.conv1(x) * s1.to(x.dtype) + b1.to(x.dtype))
-        out = F.relu(self._conv2(out) * s2.to(x.dtype) + b2.to(x.dtype))
-        out = self.conv3(out) * s3.to(x.dtype) + b3.to(x.dtype)
+        out = fused_conv_epilogue(x, self.conv1.weight, bias=b1, scale=s1, stride=self.conv1.stride, padding=0, relu=True)
+        out = self._conv2(out, s2, b2)
         if self.downsample is None:
             identity = x
-        elif self.w_scale is not None:
-            identity = self.downsample[0](x) * self.w_scale[3].to(x.dtype) + self.w_bias[3].to(x.dtype)
         else:
-            identity = self.downsample(x)
-        return self._from_nchw(F.relu(out + identity))
+            s4, b4 = (self.w_scale[3], self.w_bias[3]) if self.w_scale is not None else self.downsample[1].get_scale_bias()
+            identity = fused_conv_epilogue(x, self.downsample[0].weight, bias=b4, scale=s4, stride=self.downsample[0].stride, padding=0,
+                                           relu=False)
+        out = fused_conv_epilogue(out, self.conv3.weight, bias=b3, scale=s3, z=identity, stride=1, padding=0, relu=True)
+        return self._from_nchw(out)
+
+
+class _SpatialConv3x3(torch.autograd.Function):
+    """relu(conv3x3(x with one-row halos from the H-neighbours) * scale + bias) on an H-shard.
+
+    forward : the halo rows travel on a side stream while cuDNN convolves the rows that do not need them (H padding 0 -> H - 2 output
+              rows); the top / bottom output rows are convolved from 3-row slabs once the halos have landed; one fused epilogue kernel.
+    backward: fused drelu / dscale kernel; dgrad over the halo-extended input; the two halo rows of that gradient belong to the
+              neighbours and are sent back (side stream, overlapped with wgrad), the rows that arrive are added to this shard's edges."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, bias, halo_ex):
+        x, weight = _cl(x), _cl(weight)
+        w = weight.to(x.dtype)
+        cuda = x.is_cuda
+        top_out, btm_out = x[:, :, :1, :].contiguous(), x[:, :, -1:, :].contiguous()
+        if cuda:
+            cur, side = torch.cuda.current_stream(x.device), halo_ex.stream1
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                top_in, btm_in = halo_ex.left_right_halo_exchange(top_out, btm_out)
+        else:
+            top_in, btm_in = halo_ex.left_right_halo_exchange(top_out, btm_out)
+        H = x.shape[2]
+        conv = lambda t: torch.ops.aten.convolution(t, w, None, (1, 1), (0, 1), (1, 1), False, (0, 0), 1)  # noqa: E731
+        inner = conv(x) if H > 2 else None                       # output rows 1 .. H-2 need no halo
+        if cuda:
+            cur.wait_stream(side)
+            top_in.record_stream(cur)
+            btm_in.record_stream(cur)
+        xp = _cl(torch.cat((top_in.to(x.dtype), x, btm_in.to(x.dtype)), dim=2))     # kept for wgrad
+        top = conv(xp[:, :, :3, :]) if H > 1 else None
+        btm = conv(xp[:, :, -3:, :]) if H > 1 else None
+        if H == 1:
+            y = conv(xp)
+        else:
+            y = torch.cat([t for t in (top, inner, btm) if t is not None], dim=2)
+        y = _cl(y)
+        sc32, b32 = scale.detach().reshape(-1).float().contiguous(), bias.detach().reshape(-1).float().contiguous()
+        out = epilogue_fwd(y, sc32, b32, None, None, True, False)
+        ctx.save_for_backward(xp, weight, out, sc32)
+        ctx.halo_ex = halo_ex
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xp, weight, out, sc32 = ctx.saved_tensors
+        halo_ex = ctx.halo_ex
+        need = ctx.needs_input_grad
+        dy, _, _, _ = epilogue_bwd(_cl(dout), out, None, None, sc32, True, False, False, False)
+        w = weight.to(xp.dtype)
+        # dgrad first: its halo rows must leave as early as possible
+        dxp, _, _ = torch.ops.aten.convolution_backward(dy, xp, w, None, (1, 1), (0, 1), (1, 1), False, (0, 0), 1, (True, False, False))
+        g_top, g_btm = dxp[:, :, :1, :].contiguous(), dxp[:, :, -1:, :].contiguous()
+        cuda = dy.is_cuda
+        if cuda:
+            cur, side = torch.cuda.current_stream(dy.device), halo_ex.stream1
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                r_top, r_btm = halo_ex.left_right_halo_exchange(g_top, g_btm)
+        else:
+            r_top, r_btm = halo_ex.left_right_halo_exchange(g_top, g_btm)
+        dw = None
+        if need[1]:
+            _, dw, _ = torch.ops.aten.convolution_backward(dy, xp, w, None, (1, 1), (0, 1), (1, 1), False, (0, 0), 1, (False, True, False))
+            dw = dw.to(weight.dtype)
+        dx = dxp[:, :, 1:-1, :].clone(memory_format=torch.channels_last)
+        if cuda:
+            cur.wait_stream(side)
+            r_top.record_stream(cur)
+            r_btm.record_stream(cur)
+        dx[:, :, :1, :] += r_top.to(dx.dtype)      # the upper neighbour's gradient for the row it borrowed from this shard
+        dx[:, :, -1:, :] += r_btm.to(dx.dtype)
+        return dx, dw, None, None, None
 
 
 class SpatialBottleneck(Bottleneck):
@@ -143,13 +223,8 @@ class SpatialBottleneck(Bottleneck):
         self.spatial_parallel_args = spatial_parallel_args  # (spatial_group_size, spatial_group_rank, spatial_communicator, halo_ex, method)
         self.conv2_nopad_h = None
 
-    def _conv2(self, out):
+    def _conv2(self, out, s2, b2):
         args = self.spatial_parallel_args
         if args is None or args[0] <= 1:
-            return self.conv2(out)
-        halo_ex = args[3]
-        top_out, btm_out = out[:, :, :1, :].contiguous(), out[:, :, -1:, :].contiguous()
-        top_in, btm_in = halo_ex.left_right_halo_exchange(top_out, btm_out)
-        padded = torch.cat((top_in, out, btm_in), dim=2)
-        # halos replace the H padding: pad W only
-        return F.conv2d(padded, self.conv2.weight, None, self.conv2.stride, (0, 1))
+            return super()._conv2(out, s2, b2)
+        return _SpatialConv3x3.apply(out, self.conv2.weight, s2, b2, args[3])

@@ -109,6 +109,7 @@ class _Segment:
             for b in bs:
                 self.bucket_nparams[b] += 1
         self.bucket_pending = list(self.bucket_nparams)
+        self.bucket_stepped = [False] * self.n_buckets  # overlap_step_with_backward: the fused step of bucket b already ran this step
         self.written = [False] * len(params)   # zero_grad(set_to_none=True): the buffer region of parameter i holds this step's gradient
         self.cast_params = [p for p in params if (not param_dtype.is_floating_point) or p.dtype != param_dtype]
         self.scales = None
@@ -206,6 +207,7 @@ class _Segment:
         if not v:
             self.norm_rows = []
             self.bucket_pending = list(self.bucket_nparams)
+            self.bucket_stepped = [False] * self.n_buckets
             self.written = [False] * len(self.params)
 
     def grad_sq(self) -> torch.Tensor:
@@ -241,7 +243,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                  overlap_grad_sync: bool = True, overlap_param_sync: bool = False, bucket_cap_mb: float = 100.0,
                  pipeline_size: int = 2, contiguous_param_buffer: bool = True, contiguous_grad_buffer: bool = True,
                  store_params: bool = True, store_param_remainders: bool = False, with_scaled_states: bool = False,
-                 nccl_ub: bool = False, capturable: bool = False, fused_collectives="auto"):
+                 nccl_ub: bool = False, capturable: bool = False, fused_collectives="auto", overlap_step_with_backward: bool = False):
         if amsgrad:
             raise RuntimeError("DistributedFusedAdam does not support the AMSGrad variant.")
         if with_scaled_states and (dtype not in (torch.float16, torch.bfloat16) or not store_params or store_param_remainders):
@@ -271,6 +273,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self.with_scaled_states = with_scaled_states
         self.nccl_ub = nccl_ub
         self._fused_request = fused_collectives
+        # B200 extension (not in the reference): run the WHOLE step of a bucket (reduce-scatter + Adam + parameter push, one
+        # kernel) from the post-accumulate-grad hook as soon as backward has produced the bucket's gradients, on a side stream, so the
+        # HBM- / link-bound optimizer hides under the tensor-core-bound backward; step() then only joins. The arithmetic is the same
+        # kernel on the same data. Needs the global gradient norm to be irrelevant to the update: no clip_grad_norm, no GradScaler.
+        self.overlap_step_with_backward = bool(overlap_step_with_backward)
+        self._step_bumped = False
         self._param_view, self._grad_view, self._init_values = {}, {}, {}
         self._segments: list[_Segment] = []
         self._grad_scale = torch.ones([], dtype=torch.float32, device=self.device)
@@ -397,25 +405,45 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                     gv.copy_(g)
                     seg.written[pi] = True
                 param.grad = None
-            if not (self._sync_enabled and self._overlap_ok and seg.fused):
+            step_now = self.overlap_step_with_backward and seg.fused and self.device.type == "cuda"
+            if not (self._sync_enabled and seg.fused and (self._overlap_ok or step_now)):
                 return
             for b in seg.param_buckets[pi]:
                 seg.bucket_pending[b] -= 1
-                if seg.bucket_pending[b] == 0 and not seg.bucket_synced[b]:
-                    self._overlap_sync_bucket(seg, b)
+                if seg.bucket_pending[b] == 0 and not seg.bucket_synced[b] and not seg.bucket_stepped[b]:
+                    self._overlap_sync_bucket(seg, b, 0 if step_now else 1)
         return hook
 
-    def _overlap_sync_bucket(self, seg, b: int):
+    def _bump_step(self):
+        """Advance the step counters once per optimizer step (bias correction of every bucket launched for this step uses it)."""
+        if self._step_bumped:
+            return
+        self._step_bumped = True
+        for group in self.param_groups:
+            if self.capturable:
+                group["step"] += (self._dummy_overflow_buf != 1).to(torch.int32)
+            else:
+                group["step"] = group.get("step", 0) + 1
+
+    def _overlap_sync_bucket(self, seg, b: int, mode: int = 1):
         import os as _os
 
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=self.device)
+        group = self.param_groups[seg.group_idx]
+        if mode == 0:
+            if not self._step_bumped:
+                self._dummy_overflow_buf.zero_()
+            self._bump_step()
         cur = torch.cuda.current_stream(self.device)
         self._side_stream.wait_stream(cur)          # the gradients of this bucket are complete on the backward stream
-        grid = int(_os.environ.get("APEX_B200_DIST_OVERLAP_CTAS", "64"))
+        grid = int(_os.environ.get("APEX_B200_DIST_OVERLAP_CTAS", "64" if mode == 1 else "148"))
         with torch.cuda.stream(self._side_stream):
-            self._launch(seg, 1, self.param_groups[seg.group_idx], 1, b, b + 1, grid=grid, done_ctr=self._done_ctr_side)
-        seg.bucket_synced[b] = True
+            self._launch(seg, mode, group, group["step"] if mode == 0 else 1, b, b + 1, grid=grid, done_ctr=self._done_ctr_side)
+        if mode == 0:
+            seg.bucket_stepped[b] = True
+        else:
+            seg.bucket_synced[b] = True
         self._overlap_launched = True
 
     def _join_overlap(self):
@@ -786,6 +814,25 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._collect_grads()
         self._join_overlap()
 
+        if any(any(s.bucket_stepped) for s in self._segments):
+            if grad_scaler is not None or self._grad_norm is not None:
+                raise RuntimeError("overlap_step_with_backward already applied part of this step during backward: it cannot be combined "
+                                   "with clip_grad_norm / grad_norm / GradScaler (construct the optimizer without it)")
+            for seg in self._segments:   # whatever backward did not reach (parameters without a hook firing) steps now
+                group = self.param_groups[seg.group_idx]
+                b = 0
+                while seg.fused and b < seg.n_buckets:
+                    if seg.bucket_stepped[b]:
+                        b += 1
+                        continue
+                    e = b
+                    while e < seg.n_buckets and not seg.bucket_stepped[e]:
+                        e += 1
+                    self._launch(seg, 0, group, group["step"], b, e)
+                    b = e
+            self._finish_step(skipped=False)
+            return loss
+
         need_two_phase = grad_scaler is not None or self._grad_norm is not None or any(any(s.bucket_synced) for s in self._segments)
         if grad_scaler is not None:
             st = grad_scaler._per_optimizer_states[id(self)]
@@ -803,11 +850,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         else:
             self._dummy_overflow_buf.zero_()
 
-        for gi, group in enumerate(self.param_groups):
-            if self.capturable:
-                group["step"] += (self._dummy_overflow_buf != 1).to(torch.int32)
-            else:
-                group["step"] = group.get("step", 0) + 1
+        self._bump_step()
         for seg in self._segments:
             group = self.param_groups[seg.group_idx]
             step = group["step"]
@@ -834,6 +877,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         return tot.sqrt()
 
     def _finish_step(self, skipped: bool):
+        self._step_bumped = False
         self._last_norm_rows = {id(seg): list(seg.norm_rows) or [0] for seg in self._segments}
         for seg in self._segments:
             seg.synced = False
@@ -907,7 +951,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                 i += 1
         step = self._global_step()
         state = {"step": step}
-        cuda = self.device.type == "cuda"
+        cuda = self.device.type == "cuda" and torch.cuda.is_available()
         for seg in self._segments:
             out_dtype = torch.float32 if seg.scales is not None else seg.dtype
             ents = []

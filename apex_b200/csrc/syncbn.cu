@@ -39,6 +39,7 @@ struct BnArgs {
   unsigned int* grid_bar;           // [2]  {arrivals, generation}
   int splits, phases, fuse_relu, is_bwd;
   Signal sig; int channel;          // cross-GPU epoch signalling (sig.world == 1 => local only)
+  uint32_t* epoch_ctr; int xchg_region;  // device-resident epoch (graph-replayable): epoch = *ctr + 1, exchange half = epoch & 1
   PeerPtrs xchg; int xchg_off;      // every rank's exchange buffer (floats): slot [xchg_off + (r*C + c)*3 + k]
 };
 
@@ -111,6 +112,10 @@ __device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float 
 template <typename T, bool IS_BWD, bool NHWC, bool FUSED>
 __global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
   constexpr int V = VecOf<T>::V;
+  if (a.epoch_ctr) {  // every CTA reads the counter here; it is advanced after the grid barrier that precedes the exchange
+    a.sig.epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u;
+    a.xchg_off = (int)(a.sig.epoch & 1u) * a.xchg_region;
+  }
   __shared__ float sm[3][kBnThreads + 8];
   __shared__ int s_last;
   __shared__ float csum[2][kBnThreads / 32][64];  // NHWC: per-warp channel sums of one item
@@ -332,6 +337,7 @@ __global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
       if (blockIdx.x == 0) { __threadfence_system(); signal_all(a.sig, a.channel, tid); }
       wait_all(a.sig, a.channel, tid);
       __syncthreads();
+      if (a.epoch_ctr && blockIdx.x == 0 && tid == 0) *a.epoch_ctr = a.sig.epoch;
     }
     const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + a.xchg_off : nullptr;
     for (int c = blockIdx.x * kBnThreads + tid; c < C; c += gridDim.x * kBnThreads) {
@@ -473,7 +479,7 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
                      float* running_mean, float* running_var, float momentum, float eps, float* grad_w, float* grad_b, float* sum_dy,
                      float* sum_dy_xmu, float* scratch, long long scratch_floats, float* count_total, unsigned int* grid_bar,
                      int fuse_relu, const uint64_t* pads, const uint64_t* xchg, int xchg_off, int rank, int world, unsigned int epoch,
-                     int channel, int dt, cudaStream_t st) {
+                     unsigned int* epoch_ctr, int xchg_region, int sm_margin, int channel, int dt, cudaStream_t st) {
   if (C <= 0 || N <= 0 || HW <= 0) return 0;
   BnArgs a;
   a.x = x; a.dy = dy; a.z = z; a.out = out; a.dz = dz; a.N = N; a.C = C; a.HW = HW; a.nhwc = nhwc;
@@ -495,9 +501,13 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
     a.xchg.p[i] = (xchg && i < world) ? (void*)xchg[i] : nullptr;
   }
   a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch;
+  a.epoch_ctr = world > 1 ? epoch_ctr : nullptr; a.xchg_region = xchg_region;
   const long long per_c = (long long)N * HW;
   // the software grid barrier needs every CTA resident: one 512-thread CTA per SM, minus the NCCL margin when peers are involved
-  int grid = world > 1 ? kNumSMs - kSmMargin : kNumSMs;
+  // (sm_margin < 0 => the default kSmMargin; the reference exposes the same knob: gn_cuda_host_template.cuh:50-61)
+  if (sm_margin < 0) sm_margin = kSmMargin;
+  if (sm_margin > kNumSMs - 8) sm_margin = kNumSMs - 8;
+  int grid = world > 1 ? kNumSMs - sm_margin : kNumSMs;
   const int units = nhwc ? (C + 63) / 64 : C;
   long long splits = (2LL * grid + units - 1) / units;
   const long long min_per_split = nhwc ? 128 : 4096;  // rows / elements: keep every split a few full passes long
@@ -513,7 +523,11 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
   if (phases & 4) { const long long w4 = (total + kBnThreads * 16 - 1) / (kBnThreads * 16); if (w4 > want) want = w4; }
   if (want < grid) grid = (int)want;
   const bool fused = fuse_relu || z != nullptr || dz != nullptr;
-#define BN_GO4(T, B, H, F) syncbn_kernel<T, B, H, F><<<grid, kBnThreads, 0, st>>>(a)
+  // Cooperative launch: the software grid barrier (and the spin on the peers) needs every CTA of the grid resident at once; the
+  // driver guarantees all-or-nothing placement (or fails the launch) instead of this kernel hoping that no other stream holds SMs.
+  void* kargs[] = {(void*)&a};
+  cudaError_t lerr = cudaSuccess;
+#define BN_GO4(T, B, H, F) lerr = cudaLaunchCooperativeKernel((const void*)syncbn_kernel<T, B, H, F>, dim3(grid), dim3(kBnThreads), kargs, 0, st)
 #define BN_GO(T)                                                                                   \
   do {                                                                                             \
     if (is_bwd) { if (nhwc) { if (fused) BN_GO4(T, true, true, true); else BN_GO4(T, true, true, false); }        \
@@ -522,6 +536,7 @@ AB_API int ab_syncbn(int is_bwd, int phases, const void* x, const void* dy, cons
                   else      { if (fused) BN_GO4(T, false, false, true); else BN_GO4(T, false, false, false); } }  \
   } while (0)
   AB_DISPATCH_FLOAT3(dt, T, BN_GO(T));
+  if (lerr != cudaSuccess) return (int)lerr;
   AB_CHECK_LAUNCH();
   return 0;
 }

@@ -20,9 +20,11 @@ import torch
 import torch.distributed as dist
 
 from .. import _lib
+from ..utils import config
 
-_lib.declare("ab_syncbn", "i i p p p p p i i i i p p p p p p p f f p p p p p l p p i p p i i i i i i p")
+_lib.declare("ab_syncbn", "i i p p p p p i i i i p p p p p p p f f p p p p p l p p i p p i i i i p i i i i p")
 
+_BN_CHANNEL = 32  # signal-pad channel (and device epoch counter) owned by SyncBN
 _XCHG_C = 4096  # channels the exchange buffer is sized for (grown on demand)
 
 
@@ -79,17 +81,19 @@ def _call(st: _GroupState, is_bwd, phases, x, dy, z, out, dz, N, C, HW, nhwc, we
           momentum, eps, grad_w, grad_b, sum_dy, sum_dy_xmu, fuse_relu, exchange: bool):
     world = st.world if (exchange and st.world > 1) else 1
     if world > 1:
-        epoch = st.pad.next_epoch()
+        # the epoch (and with it the half of the exchange buffer in use) lives in device memory: the kernel advances it, so a captured
+        # CUDA graph signals / waits on a fresh value at every replay
+        epoch, epoch_ctr = 0, st.pad.dev_epochs[_BN_CHANNEL:_BN_CHANNEL + 1].data_ptr()
         pads, xchg = ctypes.addressof(st.pad.ptrs), ctypes.addressof(st.xchg_ptrs)
-        off = (epoch & 1) * st.region
+        off, region = 0, st.region
         rank = st.rank
     else:
-        epoch, pads, xchg, off, rank = 0, None, None, 0, 0
+        epoch, epoch_ctr, pads, xchg, off, region, rank = 0, None, None, None, 0, 0, 0
     _lib.fn("ab_syncbn")(int(is_bwd), int(phases), x.data_ptr(), _lib.ptr(dy), _lib.ptr(z), _lib.ptr(out), _lib.ptr(dz), N, C, HW, nhwc,
                          _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(var_biased), _lib.ptr(rmean),
                          _lib.ptr(rvar), float(momentum), float(eps), _lib.ptr(grad_w), _lib.ptr(grad_b), _lib.ptr(sum_dy),
                          _lib.ptr(sum_dy_xmu), st.scratch.data_ptr(), st.scratch.numel(), st.count.data_ptr(), st.grid_bar.data_ptr(), int(fuse_relu), pads,
-                         xchg, off, rank, world, epoch, 32, _lib.dt(x), _lib.stream_ptr(x.device))
+                         xchg, off, rank, world, epoch, epoch_ctr, region, config.syncbn_sm_margin(), _BN_CHANNEL, _lib.dt(x), _lib.stream_ptr(x.device))
 
 
 class SyncBatchnormFunction(torch.autograd.Function):

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default: --steps)")
     ap.add_argument("--fused", default="auto", choices=["auto", "off"], help="ours: in-kernel collectives (auto) or the NCCL path (off)")
     ap.add_argument("--overlap", default="on", choices=["on", "off"], help="ours: overlap_grad_sync hooks during backward (e2e)")
+    ap.add_argument("--step-in-backward", default="off", choices=["on", "off"],
+                    help="ours: overlap_step_with_backward=True (each bucket's whole step runs from the gradient hook during backward)")
     return ap.parse_args()
 
 
@@ -100,7 +102,8 @@ def main():
 
             opt = DistributedFusedAdam(params, dtype=torch.float32, grad_sync_dtype=torch.bfloat16, param_sync_dtype=torch.bfloat16,
                                        capturable=True, fused_collectives=("auto" if args.fused == "auto" else False),
-                                       overlap_grad_sync=(args.overlap == "on"), **hyper)
+                                       overlap_grad_sync=(args.overlap == "on"),
+                                       overlap_step_with_backward=(args.step_in_backward == "on"), **hyper)
             capturable = True
         else:
             from apex.contrib.optimizers.distributed_fused_adam import DistributedFusedAdam as RefDFA
@@ -205,7 +208,8 @@ def main():
                    "steps": Ke, "what": "H2D tokens+labels (pinned) -> zero_grad(set_to_none=True) -> plain-PyTorch Llama forward+backward (gradients written in "
                    "place into the optimizer's buffer) -> optimizer.step() -> D2H loss", "batch_per_gpu": B, "seq_len": S,
                    "tokens_per_s": args.gpus * B * S / (float(te.item()) * 1e-3), "loss_first": losses[0], "loss_last": losses[-1],
-                   "gpu_launches": (getattr(opt, "kernel_launches", 0) - e2e_launch0) if args.impl == "ours" else None}
+                   "gpu_launches": (getattr(opt, "kernel_launches", 0) - e2e_launch0) if args.impl == "ours" else None,
+                   "step_in_backward": bool(getattr(opt, "overlap_step_with_backward", False))}
         except torch.OutOfMemoryError as e:   # noqa: PERF203
             e2e = {"unavailable": f"out of memory in the end-to-end step: {str(e)[:120]}"}
 

@@ -59,7 +59,9 @@ def dist_adam_overlap_grad_sync(rank, world, device_type):
     (reference apex/contrib/test/optimizers/test_dist_adam.py:119-300)."""
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank)
-    ref_model = _model(dev)
+    torch.manual_seed(0)
+    # six 48x48 layers: ~14k elements over buckets of 2048 * world elements => several buckets, some parameters straddle two
+    ref_model = torch.nn.Sequential(*[torch.nn.Linear(48, 48) for _ in range(6)]).to(dev)
     dist_model = copy.deepcopy(ref_model)
     ref_opt = torch.optim.AdamW(ref_model.parameters(), lr=3e-3, weight_decay=0.05)
     opt = DistributedFusedAdam(dist_model.parameters(), lr=3e-3, weight_decay=0.05, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20,
@@ -67,10 +69,10 @@ def dist_adam_overlap_grad_sync(rank, world, device_type):
     assert opt.fused_collectives
     g = torch.Generator().manual_seed(100 + rank)
     for it in range(4):
-        opt.zero_grad()
+        opt.zero_grad(set_to_none=bool(it & 1))      # both gradient paths: in-place accumulation and single-copy hand-over
         ref_opt.zero_grad()
         for micro in range(3):
-            x = torch.randn(5, 7, generator=g).to(dev)
+            x = torch.randn(5, 48, generator=g).to(dev)
             ref_model(x).pow(2).mean().backward()
             if micro < 2:
                 with opt.no_sync():
@@ -90,6 +92,38 @@ def dist_adam_overlap_grad_sync(rank, world, device_type):
             torch.testing.assert_close(pd, pr, rtol=1e-5, atol=1e-5)
     n_buckets = sum(seg.n_buckets for seg in opt._segments)
     assert n_buckets > 1 and opt.kernel_launches >= 4 * (n_buckets + 1)
+
+
+def dist_adam_step_in_backward(rank, world, device_type):
+    """overlap_step_with_backward: every bucket's whole step (reduce-scatter + Adam + parameter push) runs from the gradient hook while
+    backward continues; step() only joins. Same kernel on the same data => bit-identical to a twin that steps after backward."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    ma = torch.nn.Sequential(*[torch.nn.Linear(48, 48) for _ in range(6)]).to(dev)
+    mb = copy.deepcopy(ma)
+    kw = dict(lr=3e-3, weight_decay=0.05, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20)
+    a = DistributedFusedAdam(ma.parameters(), overlap_step_with_backward=True, **kw)
+    b = DistributedFusedAdam(mb.parameters(), overlap_grad_sync=False, **kw)
+    g = torch.Generator().manual_seed(100 + rank)
+    for it in range(5):
+        a.zero_grad(set_to_none=bool(it & 1))
+        b.zero_grad()
+        for micro in range(2):
+            x = torch.randn(5, 48, generator=g).to(dev)
+            if micro == 0:
+                with a.no_sync():
+                    ma(x).pow(2).mean().backward()
+            else:
+                ma(x).pow(2).mean().backward()
+            mb(x).pow(2).mean().backward()
+        assert any(any(seg.bucket_stepped) for seg in a._segments), "no bucket stepped during backward"
+        a.step()
+        b.step()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert torch.equal(pa, pb), (it, (pa - pb).abs().max())
+    torch.testing.assert_close(a.last_grad_norm(), b.last_grad_norm(), rtol=1e-5, atol=1e-7)
+    assert a.param_groups[0]["step"] == b.param_groups[0]["step"] == 5
 
 
 def dist_adam_cuda_graph_replays(rank, world, device_type):
@@ -664,11 +698,22 @@ def spatial_bottleneck_matches_full(rank, world, device_type):
     full = Bottleneck(16, 8, 32).to(dev)
     for bn in (full.bn1, full.bn2, full.bn3, full.downsample[1]):
         bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5)
-    x = torch.randn(2, 16, 8 * world, 6, device=dev)
+    x = torch.randn(2, 16, 8 * world, 6, device=dev, requires_grad=True)
     want = full(x)
+    gout = torch.randn_like(want)
+    want.backward(gout)
+    rows = slice(8 * rank, 8 * (rank + 1))
     for make in (lambda: HaloExchangerAllGather(list(range(world)), rank, None), lambda: HaloExchangerSendRecv(list(range(world)), rank)):
         halo_ex = make()
         sp = SpatialBottleneck(16, 8, 32, spatial_parallel_args=(world, rank, None, halo_ex, 1)).to(dev)
         sp.load_state_dict(full.state_dict())
-        got = sp(x[:, :, 8 * rank:8 * (rank + 1)].contiguous())
-        torch.testing.assert_close(got, want[:, :, 8 * rank:8 * (rank + 1)], atol=1e-5, rtol=1e-5)
+        xs = x.detach()[:, :, rows].contiguous().requires_grad_()
+        got = sp(xs)
+        torch.testing.assert_close(got, want.detach()[:, :, rows], atol=1e-5, rtol=1e-5)
+        # backward: the halo-row gradients travel back to the neighbours; weight gradients are partial sums over the H-shards
+        got.backward(gout[:, :, rows].contiguous())
+        torch.testing.assert_close(xs.grad, x.grad[:, :, rows], atol=1e-4, rtol=1e-4)
+        for (n, p), (_, q) in zip(sp.named_parameters(), full.named_parameters()):
+            g = p.grad.clone()
+            dist.all_reduce(g)
+            torch.testing.assert_close(g, q.grad, atol=1e-4, rtol=1e-4, msg=lambda m, n=n: f"{n}: {m}")

@@ -166,3 +166,72 @@ def test_peer_halo_exchange(cuda_dev, world):
     from apex_b200.testing.dist_harness import run_distributed
     from tests import _dist_cases as cases
     run_distributed(cases.peer_halo_exchange_matches_allgather, world, "cuda", backend="nccl")
+
+
+# ---------------------------------------------------------------- fused conv tails (csrc/conv_epilogue.cu)
+@pytest.mark.parametrize("dtype,C_out", [(torch.bfloat16, 64), (torch.float16, 24), (torch.float32, 32), (torch.float16, 13)])
+@pytest.mark.parametrize("variant", ["bias_relu", "bias", "mask", "scale_bias_add_relu"])
+def test_fused_conv_epilogue_forward_backward(cuda_dev, dtype, C_out, variant):
+    import torch.nn.functional as F
+    from apex_b200.contrib.conv_bias_relu.conv_bias_relu import fused_conv_epilogue
+    torch.manual_seed(0)
+    x = torch.randn(3, 16, 14, 10, device=cuda_dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = (torch.randn(C_out, 16, 3, 3, device=cuda_dev) * 0.1).to(dtype).requires_grad_()
+    b = torch.randn(1, C_out, 1, 1, device=cuda_dev).to(dtype).requires_grad_()
+    sc = (torch.rand(C_out, device=cuda_dev) + 0.5).requires_grad_() if variant == "scale_bias_add_relu" else None
+    z = torch.randn(3, C_out, 14, 10, device=cuda_dev).to(dtype).requires_grad_() if variant == "scale_bias_add_relu" else None
+    mask = (torch.rand(3, C_out, 14, 10, device=cuda_dev) > 0.3) if variant == "mask" else None
+    relu = variant != "bias"
+    out = fused_conv_epilogue(x, w, bias=b, scale=sc, z=z, mask=mask, stride=1, padding=1, relu=relu)
+    # fp32 reference of the same op
+    xf, wf, bf = (t.detach().float().requires_grad_() for t in (x, w, b))
+    scf = sc.detach().clone().requires_grad_() if sc is not None else None
+    zf = z.detach().float().requires_grad_() if z is not None else None
+    ref = F.conv2d(xf, wf, None, 1, 1)
+    if scf is not None:
+        ref = ref * scf.view(1, -1, 1, 1)
+    ref = ref + bf
+    if zf is not None:
+        ref = ref + zf
+    if mask is not None:
+        ref = ref * mask
+    if relu:
+        ref = F.relu(ref)
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    torch.testing.assert_close(out.float(), ref, atol=tol * 4, rtol=tol)
+    g = torch.randn_like(out)
+    ins = [t for t in (x, w, b, sc, z) if t is not None]
+    refs = [t for t in (xf, wf, bf, scf, zf) if t is not None]
+    got = torch.autograd.grad(out, ins, g)
+    want = torch.autograd.grad(ref, refs, g.float())
+    for a_, r_, name in zip(got, want, ["x", "w", "b", "scale", "z"][:len(got)] if sc is not None else ["x", "w", "b"]):
+        scale_ = max(1.0, r_.abs().max().item())
+        assert (a_.float() - r_).abs().max().item() <= (5e-4 if dtype == torch.float32 else 6e-2) * scale_, name
+
+
+def test_bottleneck_block_matches_eager_composition(cuda_dev):
+    import torch.nn.functional as F
+    from apex_b200.contrib.bottleneck import Bottleneck
+    torch.manual_seed(0)
+    blk = Bottleneck(32, 16, 64, stride=2).to(cuda_dev).half().to(memory_format=torch.channels_last)
+    for bn in (blk.bn1, blk.bn2, blk.bn3, blk.downsample[1]):
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5)  # noqa: E702
+    x = torch.randn(4, 32, 16, 16, device=cuda_dev).half().contiguous(memory_format=torch.channels_last).requires_grad_()
+    out = blk(x)
+
+    def eager(xx):
+        f = lambda bn: tuple(t.float() for t in bn.get_scale_bias())  # noqa: E731
+        (s1, b1), (s2, b2), (s3, b3), (s4, b4) = f(blk.bn1), f(blk.bn2), f(blk.bn3), f(blk.downsample[1])
+        w = lambda c: c.weight.float()  # noqa: E731
+        o = F.relu(F.conv2d(xx, w(blk.conv1), None, 2) * s1 + b1)
+        o = F.relu(F.conv2d(o, w(blk.conv2), None, 1, 1) * s2 + b2)
+        o = F.conv2d(o, w(blk.conv3)) * s3 + b3
+        return F.relu(o + F.conv2d(xx, w(blk.downsample[0]), None, 2) * s4 + b4)
+
+    xf = x.detach().float().requires_grad_()
+    ref = eager(xf)
+    torch.testing.assert_close(out.float(), ref, atol=5e-2, rtol=5e-2)
+    g = torch.randn_like(out)
+    (gx,) = torch.autograd.grad(out, x, g)
+    (rx,) = torch.autograd.grad(ref, xf, g.float())
+    assert (gx.float() - rx).abs().max().item() <= 5e-2 * max(1.0, rx.abs().max().item())

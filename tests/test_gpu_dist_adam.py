@@ -139,6 +139,35 @@ def test_two_gpus_overlap_grad_sync(cuda_dev):
     run_distributed(cases.dist_adam_overlap_grad_sync, 2, "cuda", backend="nccl")
 
 
+def test_two_gpus_step_in_backward(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_step_in_backward, 2, "cuda", backend="nccl")
+
+
+def test_world1_step_in_backward_matches_step_after_backward(cuda_dev):
+    import copy
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    ma = torch.nn.Sequential(*[torch.nn.Linear(64, 64) for _ in range(5)]).to(cuda_dev, torch.bfloat16)
+    mb = copy.deepcopy(ma)
+    a = DistributedFusedAdam(ma.parameters(), lr=1e-2, bucket_cap_mb=0.01, overlap_step_with_backward=True, capturable=True)
+    b = DistributedFusedAdam(mb.parameters(), lr=1e-2, bucket_cap_mb=0.01, capturable=True)
+    for it in range(4):
+        a.zero_grad(set_to_none=True)
+        b.zero_grad()
+        x = torch.randn(16, 64, device=cuda_dev, dtype=torch.bfloat16)
+        ma(x).float().pow(2).mean().backward()
+        mb(x).float().pow(2).mean().backward()
+        assert sum(sum(seg.bucket_stepped) for seg in a._segments) > 1
+        a.step()
+        b.step()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.equal(pa, pb)
+    assert int(a.param_groups[0]["step"]) == 4
+
+
 def test_two_gpus_cuda_graph_capture_of_the_distributed_step(cuda_dev):
     _need(2)
     from apex_b200.testing.dist_harness import run_distributed
