@@ -26,6 +26,8 @@ struct Params {
   int epi;
   float alpha;                     // accumulator scale applied before the epilogue op
   const float* scale_a; const float* scale_b;  // optional DEVICE scalars multiplied into alpha (fp8 dequantisation scales: no host sync)
+  float* colsum;                   // optional fp32 [N], zero on entry: += column sums of the values this GEMM stores (fused bias gradient:
+                                   // the reference's EPILOGUE_DGELU_BGRAD / BGRADB, csrc/fused_dense_cuda.cu:595,829)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -161,11 +163,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
     tmem_ld_wait();
     const int col0 = n_blk * BN + c0;
+    float v[32];
+    const bool full = (col0 + 32 <= p.N);
     if (row_ok && col0 < p.N) {
-      float v[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) * alpha;
-      const bool full = (col0 + 32 <= p.N);
       if (p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RELU || p.epi == EPI_BIAS_SIGMOID) {
         const TOut* b = reinterpret_cast<const TOut*>(p.bias) + col0;
         if (full && aligned16(b)) {
@@ -244,6 +246,24 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_bas
 #pragma unroll
         for (int j = 0; j < 32; j++) if (col0 + j < p.N) drow[col0 + j] = from_f<TOut>(v[j]);
       }
+    }
+    if (p.colsum && col0 < p.N) {   // warp-uniform
+      // Fused bias gradient: column sums of this 32-row x 32-column block. Recursive-halving transpose-reduce: after the step with
+      // stride s every lane keeps the s columns whose index agrees with its lane bit, so 31 shuffles leave column `lane` on lane `lane`.
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int j = 0; j < 32; j++) if (!row_ok || (!full && col0 + j >= p.N)) v[j] = 0.f;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < s; j++) {
+          const float send = up ? v[j] : v[j + s];
+          const float keep = up ? v[j + s] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, v[0]);
     }
   }
 }

@@ -13,7 +13,8 @@
 //   EPI_NONE       plain store                               (dgrad, :1104-1129)
 //   EPI_BIAS       + bias[N]                                 (EPILOGUE_BIAS, :81)
 //   EPI_BIAS_GELU  + bias, GELU; pre-activation saved to aux (EPILOGUE_GELU_AUX_BIAS, :315,336)
-//   EPI_DGELU      * gelu'(aux)                              (EPILOGUE_DGELU_BGRAD, :829; the bias-grad is a separate reduction)
+//   EPI_DGELU      * gelu'(aux)                              (EPILOGUE_DGELU_BGRAD, :829)
+//   any epilogue + Params::colsum: the bias gradient (column sums of the stored tile) accumulated from the epilogue registers
 //   EPI_ACCUM      + C (beta = 1), fp32 or 16-bit main-grad  (fused_weight_gradient_dense_cuda.cu:42-49)
 //   EPI_BIAS_RELU / EPI_BIAS_SIGMOID / EPI_RELU / EPI_SIGMOID (mlp_cuda.cu:95-119,271-405)
 #include "gemm_common.cuh"
@@ -370,9 +371,32 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D row-major [rows, cols] 16-bit tensor with leading dimension ld (elements); box = {box_cols (inner), box_rows}.
+// Descriptor cache: a training loop issues the same GEMMs (same pointers, shapes, boxes) every step, and cuTensorMapEncodeTiled is a
+// driver call (~1-2 us each, two per GEMM). Small direct-mapped cache keyed by everything that goes into the descriptor.
+struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_cols, box_rows; int fmt, esize; };
+struct MapSlot { MapKey k; CUtensorMap m; bool valid; };
+static inline bool key_eq(const MapKey& a, const MapKey& b) {
+  return a.ptr == b.ptr && a.rows == b.rows && a.cols == b.cols && a.ld == b.ld && a.box_cols == b.box_cols && a.box_rows == b.box_rows &&
+         a.fmt == b.fmt && a.esize == b.esize;
+}
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                             uint32_t box_rows, int esize);
 static int make_map(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                     uint32_t box_rows, int esize = 2) {
+  constexpr int kSlots = 256;
+  static thread_local MapSlot cache[kSlots];   // thread_local: the autograd engine calls from its own threads, no locking needed
+  const MapKey k{ptr, rows, cols, ld, box_cols, box_rows, is_bf16, esize};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols << 17) ^ (ld << 3) ^ box_rows ^ ((uint64_t)box_cols << 9);
+  MapSlot& slot = cache[(h >> 32) % kSlots];
+  if (slot.valid && key_eq(slot.k, k)) { *m = slot.m; return 0; }
+  const int rc = make_map_uncached(m, ptr, is_bf16, rows, cols, ld, box_cols, box_rows, esize);
+  if (rc == 0) { slot.k = k; slot.m = *m; slot.valid = true; }
+  return rc;
+}
+
+// 2-D row-major [rows, cols] 16-bit tensor with leading dimension ld (elements); box = {box_cols (inner), box_rows}.
+static int make_map_uncached(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                             uint32_t box_rows, int esize) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1001;
   bind_primary_context_once();
@@ -433,7 +457,7 @@ using namespace ab::gemm;
 // 16-byte aligned bases.
 AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd,
                         int a_mn_major, int b_mn_major, int dt_in, int dt_out, int epi, const void* bias, void* aux, long long ldaux,
-                        const void* C, long long ldc, int sms, cudaStream_t st) {
+                        const void* C, long long ldc, float* colsum, int sms, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (dt_in != kBF16 && dt_in != kF16) return -10;
   const int is_bf16 = dt_in == kBF16;
@@ -451,6 +475,7 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
   p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f; p.scale_a = nullptr; p.scale_b = nullptr;
+  p.colsum = colsum;
   if (sms <= 0) sms = kNumSMs;
 #define GEMM_GO(T)                                                                      \
   if (use2) return launch2<T, 6>(ma, mb, p, is_bf16, sms, st);                          \
@@ -479,7 +504,7 @@ AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int 
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = nullptr; p.ldc = 0;
-  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b;
+  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b; p.colsum = nullptr;
   if (sms <= 0) sms = kNumSMs;
   if (dt_out == kBF16) return launch2<bf16, 6, true>(ma, mb, p, fmt, sms, st);
   if (dt_out == kF16) return launch2<f16, 6, true>(ma, mb, p, fmt, sms, st);

@@ -76,8 +76,8 @@ class FusedDenseGeluDenseFunc(torch.autograd.Function):
         dy = _2d(grad_output)
         dw2 = G.linear_wgrad(dy, output1)
         db2 = G.colsum(dy)
-        d_gelu_in = G.linear_dgrad(dy, weight2.contiguous(), dgelu_aux=gelu_in)   # dgrad2 fused with gelu'
-        db1 = G.colsum(d_gelu_in)
+        # dgrad2 fused with gelu' AND with the bias-1 gradient (column sums out of the same epilogue registers)
+        d_gelu_in, db1 = G.linear_dgrad(dy, weight2.contiguous(), dgelu_aux=gelu_in, want_colsum=True)
         dw1 = G.linear_wgrad(d_gelu_in, x)
         dx = G.linear_dgrad(d_gelu_in, weight1.contiguous()) if ctx.needs_input_grad[0] else None
         return (dx.view(ctx.in_shape) if dx is not None else None), dw1, db1, dw2, db2

@@ -10,7 +10,7 @@ import torch
 
 from .. import _lib
 
-_lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l i p")
+_lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l p i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
 _lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f p p i p")
 _lib.declare("ab_fp8_quantize", "p p l p p i i p")
@@ -28,8 +28,9 @@ def _native_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_dtype=None, epi: int = EPI_NONE,
          bias: torch.Tensor | None = None, aux: torch.Tensor | None = None, c: torch.Tensor | None = None,
-         out: torch.Tensor | None = None, sms: int = 0) -> torch.Tensor | None:
+         out: torch.Tensor | None = None, sms: int = 0, colsum_out: torch.Tensor | None = None) -> torch.Tensor | None:
     """a: [M,K] (a_mn=False) or [K,M] (a_mn=True), row-major with unit inner stride; b: [N,K] or [K,N] likewise.
+    ``colsum_out``: fp32 [N], zero on entry — the column sums of D (a bias gradient) are accumulated into it by the epilogue.
     Returns D [M,N], or None if the native kernel cannot take this problem (caller falls back)."""
     if not _native_ok(a, b):
         return None
@@ -47,7 +48,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         rc_ok = True
         _lib.fn("ab_gemm_bf16")(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
                                 int(b_mn), _lib.dt(a), _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux),
-                                aux.stride(0) if aux is not None else 0, _lib.ptr(c), c.stride(0) if c is not None else 0, int(sms),
+                                aux.stride(0) if aux is not None else 0, _lib.ptr(c), c.stride(0) if c is not None else 0, _lib.ptr(colsum_out), int(sms),
                                 _lib.stream_ptr(a.device))
     except RuntimeError as e:
         if "bad argument (-10)" in str(e):
@@ -94,18 +95,20 @@ def linear_fwd(x, w, bias=None, epi=None, aux=None, out_dtype=None):
     return y
 
 
-def linear_dgrad(dy, w, dgelu_aux=None):
-    """dx = dy @ W  (optionally fused with * gelu'(aux))."""
-    dx = gemm(dy, w, b_mn=True, epi=EPI_DGELU if dgelu_aux is not None else EPI_NONE, aux=dgelu_aux)
+def linear_dgrad(dy, w, dgelu_aux=None, want_colsum: bool = False):
+    """dx = dy @ W  (optionally fused with * gelu'(aux)). ``want_colsum``: also return the column sums of dx (the bias gradient of the
+    layer below), accumulated by the same kernel's epilogue — no second pass over dx."""
+    cs = torch.zeros(w.shape[1], dtype=torch.float32, device=dy.device) if (want_colsum and _native_ok(dy, w)) else None
+    dx = gemm(dy, w, b_mn=True, epi=EPI_DGELU if dgelu_aux is not None else EPI_NONE, aux=dgelu_aux, colsum_out=cs)
     if dx is not None:
-        return dx
+        return (dx, cs.to(dx.dtype)) if want_colsum else dx
     dx = torch.matmul(dy, w)
     if dgelu_aux is not None:
         a = dgelu_aux.float()
         cdf = 0.5 * (1 + torch.erf(a * 0.7071067811865476))
         pdf = torch.exp(-0.5 * a * a) * 0.3989422804014327
         dx = (dx.float() * (cdf + a * pdf)).to(dy.dtype)
-    return dx
+    return (dx, colsum(dx)) if want_colsum else dx
 
 
 def linear_wgrad(dy, x, accum_into: torch.Tensor | None = None, out_dtype=None):

@@ -181,3 +181,23 @@ def test_fp8_quantize_kernel(cuda_dev, dtype):
     assert out is not None
     want = (q.float() @ w8.float().t()) * inv * winv
     torch.testing.assert_close(out, want, atol=2e-2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 256), (300, 200, 136), (8192, 4096, 1024)])
+def test_dgrad_epilogue_accumulates_the_bias_gradient(cuda_dev, M, N, K):
+    """EPI_DGELU / EPI_NONE + colsum: the column sums of the stored tile come out of the epilogue registers (fused BGRAD)."""
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    dy = torch.randn(M, K, device=cuda_dev, dtype=torch.bfloat16)
+    w = (torch.randn(K, N, device=cuda_dev) * 0.05).to(torch.bfloat16)
+    aux = torch.randn(M, N, device=cuda_dev, dtype=torch.bfloat16)
+    for use_aux in (False, True):
+        dx, cs = G.linear_dgrad(dy, w, dgelu_aux=aux if use_aux else None, want_colsum=True)
+        ref = dy.float() @ w.float()
+        if use_aux:
+            a = aux.float()
+            ref = ref * (0.5 * (1 + torch.erf(a * 0.7071067811865476)) + a * torch.exp(-0.5 * a * a) * 0.3989422804014327)
+        torch.testing.assert_close(dx.float(), ref, atol=3e-2, rtol=3e-2)
+        want = ref.sum(0)
+        err = (cs.float() - want).abs().max().item()
+        assert err <= 2e-2 * max(1.0, want.abs().max().item()), (use_aux, err)
