@@ -30,7 +30,7 @@ from ... import _lib
 from ...ops import amp_C
 from ...ops import reference as ref
 
-_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p i i i p")
+_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p p p i i i i p")
 
 _CHUNK = 2048  # elements handled by one CTA work item in csrc/dist_adam.cu
 _ALIGN = 64    # every parameter starts on a 64-element boundary of the flat space
@@ -112,6 +112,25 @@ class _Segment:
         self.bucket_stepped = [False] * self.n_buckets  # overlap_step_with_backward: the fused step of bucket b already ran this step
         self.written = [False] * len(params)   # zero_grad(set_to_none=True): the buffer region of parameter i holds this step's gradient
         self.cast_params = [p for p in params if (not param_dtype.is_floating_point) or p.dtype != param_dtype]
+        # overlap_param_sync: per-(bucket, rank) ready flags in memory every rank can write (symmetric heap), local chunk counters
+        self.region = None
+        self.ready_ptrs = None
+        if self.fused and getattr(opt, "overlap_param_sync", False) and dev.type == "cuda":
+            from ...parallel import param_sync as _ps
+
+            nb = self.n_buckets * 8 * 4
+            if D > 1:
+                from ...parallel.symmetric import SymmetricMemory
+
+                self.symm_flags = SymmetricMemory(nb, group=opt.distributed_process_group, device=dev, multicast=False, tag=f"f{group_idx}")
+                self.ready_ptrs = self.symm_flags.peer_ptr_array()
+                flags_ptr = self.symm_flags.local_ptr
+            else:
+                self.flags = torch.zeros(self.n_buckets * 8, dtype=torch.int32, device=dev)
+                self.ready_ptrs = (ctypes.c_uint64 * 8)(self.flags.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
+                flags_ptr = self.flags.data_ptr()
+            self.bucket_ctr = torch.zeros(self.n_buckets, dtype=torch.int32, device=dev)
+            self.region = _ps.register(_ps.Region(self.param_buf, flags_ptr, D, self.bucket_elems))
         self.scales = None
         if getattr(opt, "with_scaled_states", False):
             # per-(parameter x shard) fragment scale factors for the 16-bit state (reference :2693-2774,2833-2860): element i of the
@@ -292,6 +311,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._side_stream = None          # overlap_grad_sync: per-bucket reduce-scatter launches run here while backward continues
         self._hook_handles = []
         self._overlap_launched = False
+        self._push_in_flight = False
         self._overlap_ok = False
         self._steal = False    # zero_grad(set_to_none=True) is in effect: gradients arrive as fresh tensors and are copied into the buffer
         self.last_nvls = False
@@ -451,6 +471,15 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
             self._overlap_launched = False
 
+    def _join_push(self):
+        """Wait for an in-flight parameter push (overlap_param_sync) on the current stream."""
+        if self._push_in_flight:
+            torch.cuda.current_stream(self.device).wait_stream(self._side_stream)
+            self._push_in_flight = False
+            for seg in self._segments:
+                if seg.region is not None:
+                    seg.region.in_flight = False
+
     def init_param_buffer(self) -> None:
         self.init_params()
 
@@ -529,7 +558,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         return 1.0 / (self.distributed_size * self.redundant_size) if self.average_grad_sync else 1.0
 
     def _launch(self, seg: _Segment, mode: int, group, step: int, b0: int = 0, b1: Optional[int] = None, grid: Optional[int] = None,
-                done_ctr=None, lane: int = 0, force_nvls: Optional[bool] = None):
+                done_ctr=None, lane: int = 0, force_nvls: Optional[bool] = None, publish: bool = False):
         """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them). ``lane`` selects an independent set
         of signal channels / epoch counter / scratch so that two launches can be in flight at once (hybrid NVLS + P2P step)."""
         b1 = seg.n_buckets if b1 is None else b1
@@ -572,6 +601,9 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             0.0 if cap else float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), 0 if cap else int(step),
             1 if self.adam_w_mode else 0, 1 if group["bias_correction"] else 0, float(group["weight_decay"]),
             self._dummy_overflow_buf.data_ptr(), group["lr"].data_ptr() if cap else None, group["step"].data_ptr() if cap else None,
+            ctypes.addressof(seg.ready_ptrs) if (publish and seg.region is not None) else None,
+            seg.bucket_ctr.data_ptr() if (publish and seg.region is not None) else None,
+            (seg.region.epoch & 0x7FFFFFFF) if (publish and seg.region is not None) else 0,
             _lib.dt(seg.grad_dtype), _lib.dt(seg.param_dtype), grid, _lib.stream_ptr(self.device))
 
     def _hybrid_split(self, seg: _Segment) -> int:
@@ -606,6 +638,23 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         with torch.cuda.stream(self._lane_stream):
             self._launch(seg, 0, group, step, k, seg.n_buckets, grid=148, done_ctr=self._done_ctr_lane, lane=1, force_nvls=False)
         cur.wait_stream(self._lane_stream)
+
+    def _push_async(self, seg: _Segment, mode: int, group, step):
+        """overlap_param_sync: the kernel that updates and pushes the parameters runs on the side stream with a small grid (the
+        all-gather is link-bound: a few dozen CTAs saturate it and the rest of the GPU stays free for the next forward); it releases a
+        ready flag per (bucket, rank). step() returns at once — consumers synchronise per weight tile / per bucket (parallel/param_sync.py)."""
+        import os as _os
+
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._side_stream.wait_stream(cur)
+        seg.region.epoch += 1
+        seg.region.in_flight = True
+        grid = int(_os.environ.get("APEX_B200_DIST_PARAM_SYNC_CTAS", "48"))
+        with torch.cuda.stream(self._side_stream):
+            self._launch(seg, mode, group, step, grid=grid, done_ctr=self._done_ctr_side, publish=True)
+        self._push_in_flight = True
 
     def _reduce_scatter_generic(self, seg: _Segment):
         """NCCL / gloo reduce-scatter of every bucket into the fp32 reduced shard (the reference's data path)."""
@@ -674,8 +723,11 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             b = e
 
     def param_sync(self) -> None:
-        """Parameters are pushed by the step itself on the fused path; the generic path all-gathers inside step()."""
-        return
+        """Parameters are pushed by the step itself (fused path) or all-gathered inside step() (generic path). With
+        ``overlap_param_sync=True`` the push may still be in flight when step() returns: this joins it (flag-aware GEMMs and the
+        hooks of ``parallel.param_sync.attach_param_sync_hooks`` do not need it — they wait per tile / per bucket)."""
+        self._join_overlap()
+        self._join_push()
 
     def grad_norm(self, parameters=None, norm_type: float = 2.0, force: bool = False) -> torch.Tensor:
         """L2 norm of the (averaged, still loss-scaled) gradients over all ranks; cached until the next zero_grad/step."""
@@ -813,6 +865,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self.init_params()
         self._collect_grads()
         self._join_overlap()
+        self._join_push()     # the previous step's parameter push (overlap_param_sync), if a consumer has not joined it already
 
         if any(any(s.bucket_stepped) for s in self._segments):
             if grad_scaler is not None or self._grad_norm is not None:
@@ -855,9 +908,17 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             group = self.param_groups[seg.group_idx]
             step = group["step"]
             if seg.fused:
-                if need_two_phase:
+                if seg.region is not None:
+                    # overlap_param_sync: reduce-scatter now (whatever backward did not already overlap), then Adam + push on the side
+                    # stream; the gradient buffer is free again as soon as the reduce-scatter is done, so the next zero_grad / backward
+                    # does not have to wait for the parameter push
                     if not seg.synced:
                         self._sync_remaining(seg, group)
+                    self._push_async(seg, 2, group, step)
+                    continue
+                if need_two_phase and not seg.synced:
+                    self._sync_remaining(seg, group)
+                if need_two_phase:
                     self._launch(seg, 2, group, step)
                 else:
                     self._fused_pass(seg, group, step)
@@ -879,6 +940,8 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     def _finish_step(self, skipped: bool):
         self._step_bumped = False
         self._last_norm_rows = {id(seg): list(seg.norm_rows) or [0] for seg in self._segments}
+        if any(seg.cast_params and seg.region is not None and seg.region.in_flight for seg in self._segments):
+            self._join_push()   # the cast copies below read the gathered buffer
         for seg in self._segments:
             seg.synced = False
             for p in seg.cast_params:  # parameters whose dtype differs from the sync dtype get a cast copy
@@ -943,6 +1006,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         bounded pieces (double-buffered pinned staging), never materialised at full size on the GPU."""
         self.init_params()
         self._join_overlap()
+        self._join_push()
         index = {}
         i = 0
         for g in self.param_groups:
@@ -1029,6 +1093,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     def load_state_dict(self, state_dict) -> None:
         self.init_params()
         self._join_overlap()
+        self._join_push()
         index = {}
         i = 0
         st = state_dict["state"]

@@ -50,6 +50,12 @@ struct DistArgs {
   const float* lr_ptr;   // capturable: learning rate and step count live on the device
   const int* step_ptr;
   int bias_correction;
+  // overlap_param_sync (all-gather fused into the consuming GEMM): when every chunk of this rank's shard of bucket b has been pushed,
+  // `ready_epoch` is released into slot [b][rank] of EVERY rank's flag array; consumers (csrc/gemm_sm100.cu TMA producer, or a
+  // cuStreamWaitValue32) acquire the D slots of the buckets that hold the weight tile they are about to load.
+  PeerPtrs ready;          // every rank's flag array [n_buckets][kMaxPeers] uint32 (null => feature off)
+  uint32_t* bucket_ctr;    // local [n_buckets] chunk counters, zero between launches
+  uint32_t ready_epoch;
 };
 
 template <typename T> __device__ __forceinline__ void unpack8(const uint4* raw, float (&f)[8]) {
@@ -208,7 +214,29 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
           }
         }
       }
+      if (MODE != MODE_RS && a.bucket_ctr != nullptr) {
+        // this CTA's pushes of the iteration are issued; thread 0 orders them (cumulatively, through the barrier) before the counters
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence_system();
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            if (!on[u]) continue;
+            const int b = (int)((cb + (long long)u * gridDim.x) / cpb);
+            if (atomicAdd(a.bucket_ctr + b, 1u) + 1u == (unsigned)cpb) {
+              a.bucket_ctr[b] = 0u;
+              __threadfence_system();
+              for (int r = 0; r < D; r++)
+                st_release_sys(reinterpret_cast<uint32_t*>(a.ready.p[r]) + (size_t)b * kMaxPeers + rank, a.ready_epoch);
+            }
+          }
+        }
+      }
     }
+  } else if (a.bucket_ctr != nullptr && blockIdx.x == 0 && tid == 0) {
+    // skipped step (overflow): the parameters are unchanged and therefore already "ready"
+    for (int b = a.bucket_begin; b < a.bucket_end; b++)
+      for (int r = 0; r < D; r++) st_release_sys(reinterpret_cast<uint32_t*>(a.ready.p[r]) + (size_t)b * kMaxPeers + rank, a.ready_epoch);
   }
 
   // ---- epilogue: per-CTA norm partial, then the last CTA to finish closes the collective
@@ -291,8 +319,8 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
                              unsigned int epoch, unsigned int* epoch_ctr, int chan_start, int chan_end, int norm_slot, unsigned int* done_ctr,
                              float* norm_partials, float* norm_out, const float* grad_scale, float pre_scale, float lr, float beta1,
                              float beta2, float eps, int step, int adam_mode, int bias_correction, float decay, const int* noop,
-                             const float* lr_ptr, const int* step_ptr,
-                             int dt_g, int dt_p, int grid, cudaStream_t st) {
+                             const float* lr_ptr, const int* step_ptr, const uint64_t* ready, unsigned int* bucket_ctr,
+                             unsigned int ready_epoch, int dt_g, int dt_p, int grid, cudaStream_t st) {
   if (world < 1 || world > kMaxPeers) return -3;
   if (shard_elems % kDChunk != 0) return -4;
   DistArgs a;
@@ -300,7 +328,9 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
     a.grads.p[i] = i < world && grads ? (void*)grads[i] : nullptr;
     a.params.p[i] = i < world && params ? (void*)params[i] : nullptr;
     a.sig.pads.p[i] = i < world && pads ? (void*)pads[i] : nullptr;
+    a.ready.p[i] = i < world && ready ? (void*)ready[i] : nullptr;
   }
+  a.bucket_ctr = ready ? bucket_ctr : nullptr; a.ready_epoch = ready_epoch;
   a.mc_grads = (const void*)mc_grads; a.mc_params = (void*)mc_params;
   a.p = p; a.m = m; a.v = v; a.reduced = reduced;
   a.bucket_elems = bucket_elems; a.shard_elems = shard_elems; a.bucket_begin = bucket_begin; a.bucket_end = bucket_end;

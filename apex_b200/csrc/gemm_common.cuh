@@ -26,6 +26,13 @@ struct Params {
   int epi;
   float alpha;                     // accumulator scale applied before the epilogue op
   const float* scale_a; const float* scale_b;  // optional DEVICE scalars multiplied into alpha (fp8 dequantisation scales: no host sync)
+  // All-gather fused into the GEMM: B is a weight living in a ZeRO parameter buffer whose buckets are still being
+  // pushed by the optimizer-step kernels of the D ranks (csrc/dist_adam.cu). Before the TMA producer loads a B tile it acquires the
+  // ready flags [bucket][rank] of the buckets that hold the tile's rows; tiles whose buckets have landed start while later buckets are
+  // still on the wire. Null => B is plain memory.
+  const uint32_t* ready_flags; uint32_t ready_epoch; int ready_world;
+  long long ready_w_off;           // element offset of B's first element inside the parameter buffer
+  long long ready_bucket_elems;
   float* colsum;                   // optional fp32 [N], zero on entry: += column sums of the values this GEMM stores (fused bias gradient:
                                    // the reference's EPILOGUE_DGELU_BGRAD / BGRADB, csrc/fused_dense_cuda.cu:595,829)
 };
@@ -61,6 +68,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Spin (bounded: traps after ~10 s) until every rank has released `epoch` for buckets [b_lo, b_hi]; then order the generic-proxy acquire
+// before the async-proxy (TMA) reads of the data those flags guard.
+__device__ __forceinline__ void acquire_buckets(const uint32_t* flags, uint32_t epoch, int world, int b_lo, int b_hi) {
+  for (int b = b_lo; b <= b_hi; b++) {
+    for (int r = 0; r < world; r++) {
+      const uint32_t* slot = flags + (size_t)b * 8 + r;
+      uint32_t v;
+      long long t0 = clock64();
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 20000000000LL) { printf("apex_b200 gemm: weight bucket %d of rank %d never became ready (epoch %u)\n", b, r, epoch); __trap(); }
+        __nanosleep(128);
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
+        if (p.ready_flags) {   // B rows [n0, n1) x all of K: contiguous in the parameter buffer (K-major weight, ldb == K)
+          const long long n0 = (long long)n_blk * BN, n1 = min((long long)p.N, n0 + BN);
+          acquire_buckets(p.ready_flags, p.ready_epoch, p.ready_world, (int)((p.ready_w_off + n0 * p.K) / p.ready_bucket_elems),
+                          (int)((p.ready_w_off + n1 * p.K - 1) / p.ready_bucket_elems));
+        }
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = smem + stage * S::kStage;
@@ -268,6 +273,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         int m_blk, n_blk; tile_coords(t, num_m, num_n, m_blk, n_blk);
         const int m0 = m_blk * 2 * BM + (int)cta * BM;         // this CTA's A rows
         const int n0 = n_blk * BN2 + (int)cta * (BN2 / 2);     // this CTA's half of B
+        if (p.ready_flags && n0 < p.N) {
+          const long long r1 = min((long long)p.N, (long long)n0 + BN2 / 2);
+          acquire_buckets(p.ready_flags, p.ready_epoch, p.ready_world, (int)((p.ready_w_off + (long long)n0 * p.K) / p.ready_bucket_elems),
+                          (int)((p.ready_w_off + r1 * p.K - 1) / p.ready_bucket_elems));
+        }
         for (int kb = 0; kb < num_k; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 11);
           uint8_t* sa = smem + stage * S::kStage;
@@ -457,7 +467,8 @@ using namespace ab::gemm;
 // 16-byte aligned bases.
 AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd,
                         int a_mn_major, int b_mn_major, int dt_in, int dt_out, int epi, const void* bias, void* aux, long long ldaux,
-                        const void* C, long long ldc, float* colsum, int sms, cudaStream_t st) {
+                        const void* C, long long ldc, float* colsum, const void* ready_flags, unsigned int ready_epoch, int ready_world,
+                        long long ready_w_off, long long ready_bucket_elems, int sms, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (dt_in != kBF16 && dt_in != kF16) return -10;
   const int is_bf16 = dt_in == kBF16;
@@ -476,6 +487,11 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
   p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f; p.scale_a = nullptr; p.scale_b = nullptr;
   p.colsum = colsum;
+  // flag-guarded B: only the forward layout (K-major weight, dense rows) maps tile rows to a contiguous range of the parameter buffer
+  const bool guarded = ready_flags != nullptr && !b_mn_major && ldb == K && ready_bucket_elems > 0;
+  p.ready_flags = guarded ? (const uint32_t*)ready_flags : nullptr; p.ready_epoch = ready_epoch; p.ready_world = ready_world;
+  p.ready_w_off = ready_w_off; p.ready_bucket_elems = ready_bucket_elems;
+  if (ready_flags != nullptr && !guarded) return -11;   // the caller must wait for the whole buffer instead
   if (sms <= 0) sms = kNumSMs;
 #define GEMM_GO(T)                                                                      \
   if (use2) return launch2<T, 6>(ma, mb, p, is_bf16, sms, st);                          \
@@ -504,7 +520,7 @@ AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int 
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = nullptr; p.ldc = 0;
-  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b; p.colsum = nullptr;
+  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b; p.colsum = nullptr; p.ready_flags = nullptr;
   if (sms <= 0) sms = kNumSMs;
   if (dt_out == kBF16) return launch2<bf16, 6, true>(ma, mb, p, fmt, sms, st);
   if (dt_out == kF16) return launch2<f16, 6, true>(ma, mb, p, fmt, sms, st);
@@ -544,4 +560,20 @@ AB_API int ab_colsum(const void* x, void* out, float* ws, int M, int N, long lon
                      colsum_final<T><<<(N + 255) / 256, 256, 0, st>>>(ws, (T*)out, N, parts));
   AB_CHECK_LAUNCH();
   return 0;
+}
+
+// Stream-ordered wait (no kernel, no spinning SM): work enqueued on `st` after this call starts only once the 32-bit word at `addr`
+// (device memory, e.g. a bucket-ready flag written by a peer's step kernel) is >= value. Used for consumers that are not flag-aware.
+typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+AB_API int ab_stream_wait_geq(const void* addr, unsigned int value, cudaStream_t st) {
+  static StreamWaitFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return -1001;
+    fn = reinterpret_cast<StreamWaitFn>(f);
+  }
+  bind_primary_context_once();
+  CUresult r = fn((CUstream)st, (CUdeviceptr)(uintptr_t)addr, value, CU_STREAM_WAIT_VALUE_GEQ);
+  return r == CUDA_SUCCESS ? 0 : -(2000 + (int)r);
 }

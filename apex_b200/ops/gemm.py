@@ -9,8 +9,9 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
+from ..parallel import param_sync as _param_sync
 
-_lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l p i p")
+_lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l p p i i l l i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
 _lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f p p i p")
 _lib.declare("ab_fp8_quantize", "p p l p p i i p")
@@ -18,7 +19,7 @@ _lib.declare("ab_fp8_quantize", "p p l p p i i p")
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_ACCUM, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_RELU, EPI_SIGMOID = range(9)
 
 _ws: dict = {}
-stats = {"native": 0, "fallback": 0}
+stats = {"native": 0, "fallback": 0, "guarded": 0}
 
 
 def _native_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
@@ -33,6 +34,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     ``colsum_out``: fp32 [N], zero on entry — the column sums of D (a bias gradient) are accumulated into it by the epilogue.
     Returns D [M,N], or None if the native kernel cannot take this problem (caller falls back)."""
     if not _native_ok(a, b):
+        if _param_sync._regions:   # the caller's library fallback reads the operands as a whole
+            _param_sync.wait(a)
+            _param_sync.wait(b)
         return None
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
@@ -44,11 +48,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         assert c.dtype == out.dtype and c.stride(1) == 1
     if bias is not None and bias.dtype != out.dtype:
         bias = bias.to(out.dtype)
+    # B inside a parameter buffer whose all-gather is still in flight (overlap_param_sync): guard it tile by tile inside the kernel when
+    # the layout allows (forward: K-major dense weight), else make the stream wait for the buckets under it
+    guard = (None, 0, 0, 0, 0)
+    if _param_sync._regions:
+        hit = _param_sync.lookup(b)
+        if hit is not None:
+            region, g = hit
+            if (not b_mn) and b.stride(0) == K and b.is_contiguous():
+                guard = g
+                stats["guarded"] += 1
+            else:
+                region.wait(b)
+        if _param_sync.find(a) is not None:
+            _param_sync.wait(a)
     try:
         rc_ok = True
         _lib.fn("ab_gemm_bf16")(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
                                 int(b_mn), _lib.dt(a), _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux),
-                                aux.stride(0) if aux is not None else 0, _lib.ptr(c), c.stride(0) if c is not None else 0, _lib.ptr(colsum_out), int(sms),
+                                aux.stride(0) if aux is not None else 0, _lib.ptr(c), c.stride(0) if c is not None else 0, _lib.ptr(colsum_out), guard[0], int(guard[1]), int(guard[2]), int(guard[3]), int(guard[4]), int(sms),
                                 _lib.stream_ptr(a.device))
     except RuntimeError as e:
         if "bad argument (-10)" in str(e):

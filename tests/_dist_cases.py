@@ -126,6 +126,42 @@ def dist_adam_step_in_backward(rank, world, device_type):
     assert a.param_groups[0]["step"] == b.param_groups[0]["step"] == 5
 
 
+def dist_adam_overlap_param_sync(rank, world, device_type):
+    """overlap_param_sync: step() returns while Adam + the parameter push run on the side stream; the FusedDense forward that follows
+    acquires per-bucket ready flags inside its GEMM kernels (weights) and through stream-ordered waits (biases, via the module hooks).
+    Must equal a twin that joins everything inside step()."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    from apex_b200.fused_dense import FusedDense
+    from apex_b200.ops import gemm as G
+    from apex_b200.parallel.param_sync import attach_param_sync_hooks
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(FusedDense(256, 512), torch.nn.GELU(), FusedDense(512, 256), torch.nn.LayerNorm(256)).to(dev, torch.bfloat16)  # noqa: E731
+    ma = mk()
+    mb = copy.deepcopy(ma)
+    kw = dict(lr=1e-2, weight_decay=0.01, device=dev, bucket_cap_mb=0.1)
+    a = DistributedFusedAdam(ma.parameters(), overlap_param_sync=True, **kw)
+    b = DistributedFusedAdam(mb.parameters(), overlap_grad_sync=False, **kw)
+    attach_param_sync_hooks(ma)
+    g = torch.Generator().manual_seed(100 + rank)
+    guarded0 = G.stats["guarded"]
+    for it in range(5):
+        x = torch.randn(64, 256, generator=g).to(dev, torch.bfloat16)
+        a.zero_grad()
+        b.zero_grad()
+        ya = ma(x)                     # reads weights that the previous step may still be pushing
+        yb = mb(x)
+        assert torch.equal(ya, yb), (it, (ya.float() - yb.float()).abs().max())
+        ya.float().pow(2).mean().backward()
+        yb.float().pow(2).mean().backward()
+        a.step()
+        b.step()
+    a.param_sync()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.equal(pa, pb)
+    assert G.stats["guarded"] - guarded0 >= 4, "the forward GEMMs never saw an in-flight parameter buffer"
+
+
 def dist_adam_cuda_graph_replays(rank, world, device_type):
     """capturable=True at D > 1: torch.cuda.graph capture of step() + 10 replays must match an eager twin bit for bit — the collective's
     epoch lives in device memory, so every replay signals / waits on a fresh value (reference test_dist_adam.py:834)."""

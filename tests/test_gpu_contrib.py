@@ -196,9 +196,14 @@ def test_fused_conv_epilogue_forward_backward(cuda_dev, dtype, C_out, variant):
     if mask is not None:
         ref = ref * mask
     if relu:
-        ref = F.relu(ref)
+        # the ReLU decision is taken from the kernel's own (16-bit) output so that elements within rounding distance of zero do not flip
+        # between the two computations; everything else of the reference is fp32
+        fwd_ref = F.relu(ref)
+        ref = ref * (out.detach().float() > 0)
+    else:
+        fwd_ref = ref
     tol = 2e-5 if dtype == torch.float32 else 3e-2
-    torch.testing.assert_close(out.float(), ref, atol=tol * 4, rtol=tol)
+    torch.testing.assert_close(out.float(), fwd_ref, atol=tol * 4, rtol=tol)
     g = torch.randn_like(out)
     ins = [t for t in (x, w, b, sc, z) if t is not None]
     refs = [t for t in (xf, wf, bf, scf, zf) if t is not None]

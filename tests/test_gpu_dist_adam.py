@@ -139,6 +139,43 @@ def test_two_gpus_overlap_grad_sync(cuda_dev):
     run_distributed(cases.dist_adam_overlap_grad_sync, 2, "cuda", backend="nccl")
 
 
+def test_two_gpus_overlap_param_sync_into_fused_dense(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_adam_overlap_param_sync, 2, "cuda", backend="nccl")
+
+
+def test_world1_overlap_param_sync_into_fused_dense(cuda_dev):
+    """Same protocol at world size 1 (flags written and acquired on one GPU; the push runs on the side stream)."""
+    import copy
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    from apex_b200.fused_dense import FusedDense
+    from apex_b200.ops import gemm as G
+    from apex_b200.parallel.param_sync import attach_param_sync_hooks
+    torch.manual_seed(0)
+    ma = torch.nn.Sequential(FusedDense(512, 1024), torch.nn.GELU(), FusedDense(1024, 512), torch.nn.LayerNorm(512)).to(cuda_dev, torch.bfloat16)
+    mb = copy.deepcopy(ma)
+    a = DistributedFusedAdam(ma.parameters(), lr=1e-2, bucket_cap_mb=0.25, overlap_param_sync=True)
+    b = DistributedFusedAdam(mb.parameters(), lr=1e-2, bucket_cap_mb=0.25)
+    attach_param_sync_hooks(ma)
+    guarded0 = G.stats["guarded"]
+    for it in range(5):
+        x = torch.randn(256, 512, device=cuda_dev, dtype=torch.bfloat16)
+        a.zero_grad()
+        b.zero_grad()
+        ya, yb = ma(x), mb(x)
+        assert torch.equal(ya, yb), it
+        ya.float().pow(2).mean().backward()
+        yb.float().pow(2).mean().backward()
+        a.step()
+        b.step()
+    a.param_sync()
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.equal(pa, pb)
+    assert G.stats["guarded"] - guarded0 >= 4
+
+
 def test_two_gpus_step_in_backward(cuda_dev):
     _need(2)
     from apex_b200.testing.dist_harness import run_distributed
