@@ -30,7 +30,8 @@ from ... import _lib
 from ...ops import amp_C
 from ...ops import reference as ref
 
-_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p p p i i i i p")
+_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p p p i i p i i i i p")
+_lib.declare("ab_symm_gate", "p i i p i p")
 
 _CHUNK = 2048  # elements handled by one CTA work item in csrc/dist_adam.cu
 _ALIGN = 64    # every parameter starts on a 64-element boundary of the flat space
@@ -61,10 +62,13 @@ class _Segment:
         self.dtype, self.grad_dtype, self.param_dtype = dtype, grad_dtype, param_dtype
         D, rank = opt.distributed_size, opt.distributed_rank
         self.D, self.rank = D, rank
+        # world size 1: every parameter starts on a chunk boundary so that the step kernel can read a parameter's gradient in place
+        # (one source per chunk, see ``direct``); sharded layouts pack at 64 elements
+        align = _CHUNK if D == 1 else _ALIGN
         off, self.offsets = 0, []
         for p in params:
             self.offsets.append(off)
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            off += (p.numel() + align - 1) // align * align
         self.numel = off
         gran = D * _CHUNK
         esize = max(torch.empty((), dtype=grad_dtype).element_size(), torch.empty((), dtype=param_dtype).element_size())
@@ -111,6 +115,11 @@ class _Segment:
         self.bucket_pending = list(self.bucket_nparams)
         self.bucket_stepped = [False] * self.n_buckets  # overlap_step_with_backward: the fused step of bucket b already ran this step
         self.written = [False] * len(params)   # zero_grad(set_to_none=True): the buffer region of parameter i holds this step's gradient
+        # world size 1, zero_grad(set_to_none=True): gradients that autograd hands over are not even copied — the step kernel reads them
+        # where they are (csrc/dist_adam.cu src_tab); ``live`` keeps them alive until the step has consumed them
+        self.live = [None] * len(params)
+        self.src_tab_host = None
+        self.src_tab_dev = None
         self.cast_params = [p for p in params if (not param_dtype.is_floating_point) or p.dtype != param_dtype]
         # overlap_param_sync: per-(bucket, rank) ready flags in memory every rank can write (symmetric heap), local chunk counters
         self.region = None
@@ -228,6 +237,29 @@ class _Segment:
             self.bucket_pending = list(self.bucket_nparams)
             self.bucket_stepped = [False] * self.n_buckets
             self.written = [False] * len(self.params)
+            self.live = [None] * len(self.params)
+
+    def direct_ok(self, g: torch.Tensor) -> bool:
+        return (self.D == 1 and self.fused and g.is_cuda and g.dtype == self.grad_dtype and g.is_contiguous() and g.numel() % 8 == 0
+                and g.data_ptr() % 16 == 0 and not self.opt.overlap_step_with_backward)
+
+    def source_table(self):
+        """Device table for this step's launch, or (None, 0) when every gradient sits in the contiguous buffer."""
+        if not any(t is not None for t in self.live):
+            return None, 0
+        n = len(self.params)
+        if self.src_tab_host is None:
+            self.src_tab_host = torch.empty(n, 3, dtype=torch.int64).pin_memory()
+            self.src_tab_dev = torch.empty(n, 3, dtype=torch.int64, device=self.opt.device)
+        rows = []
+        esz = self.grad_buf.element_size()
+        base = self.grad_buf.data_ptr()
+        for i, p in enumerate(self.params):
+            t = self.live[i]
+            rows.append((self.offsets[i] // _CHUNK, t.data_ptr() if t is not None else base + self.offsets[i] * esz, p.numel()))
+        self.src_tab_host.copy_(torch.tensor(rows, dtype=torch.int64))
+        self.src_tab_dev.copy_(self.src_tab_host, non_blocking=True)
+        return self.src_tab_dev.data_ptr(), n
 
     def grad_sq(self) -> torch.Tensor:
         """Global sum of squares of the gradients reduced so far this step (device scalar)."""
@@ -419,8 +451,13 @@ class DistributedFusedAdam(torch.optim.Optimizer):
                     return   # a user-assigned gradient tensor: step() folds it in and syncs then
                 # zero_grad(set_to_none=True): autograd handed over a fresh gradient tensor instead of accumulating into the (zeroed)
                 # buffer view; ONE copy moves it into the buffer (4 B/element instead of zero + read-modify-write = 8) and frees it
-                if seg.written[pi]:
+                if seg.live[pi] is not None:
+                    seg.live[pi].add_(g)                 # later micro-batch: accumulate into the tensor the kernel will read
+                elif seg.written[pi]:
                     gv.add_(g)
+                elif seg.direct_ok(g):
+                    seg.live[pi] = g                     # world size 1: no copy at all, the step kernel reads it in place
+                    seg.written[pi] = True
                 else:
                     gv.copy_(g)
                     seg.written[pi] = True
@@ -459,7 +496,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self._side_stream.wait_stream(cur)          # the gradients of this bucket are complete on the backward stream
         grid = int(_os.environ.get("APEX_B200_DIST_OVERLAP_CTAS", "64" if mode == 1 else "148"))
         with torch.cuda.stream(self._side_stream):
-            self._launch(seg, mode, group, group["step"] if mode == 0 else 1, b, b + 1, grid=grid, done_ctr=self._done_ctr_side)
+            self._launch(seg, mode, group, group["step"] if mode == 0 else 1, b, b + 1, grid=grid, done_ctr=self._done_ctr_side, gate=True)
         if mode == 0:
             seg.bucket_stepped[b] = True
         else:
@@ -558,7 +595,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         return 1.0 / (self.distributed_size * self.redundant_size) if self.average_grad_sync else 1.0
 
     def _launch(self, seg: _Segment, mode: int, group, step: int, b0: int = 0, b1: Optional[int] = None, grid: Optional[int] = None,
-                done_ctr=None, lane: int = 0, force_nvls: Optional[bool] = None, publish: bool = False):
+                done_ctr=None, lane: int = 0, force_nvls: Optional[bool] = None, publish: bool = False, gate: bool = False):
         """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them). ``lane`` selects an independent set
         of signal channels / epoch counter / scratch so that two launches can be in flight at once (hybrid NVLS + P2P step)."""
         b1 = seg.n_buckets if b1 is None else b1
@@ -588,10 +625,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             g_arr = (ctypes.c_uint64 * 8)(seg.grad_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             p_arr = (ctypes.c_uint64 * 8)(seg.param_buf.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
             pads = (ctypes.c_uint64 * 8)(0, 0, 0, 0, 0, 0, 0, 0)
+        src_tab, src_n = (seg.source_table() if (D == 1 and mode != 2) else (None, 0))
         if grid is None:
             grid = 148 * (3 if D <= 2 else 2)
         cap = self.capturable
         done_ctr = self._done_ctr if done_ctr is None else done_ctr
+        gate = bool(gate and fused_comm and mode != 2)
+        if gate:   # the cross-rank start barrier as a 1-warp kernel in front (launches that overlap with backward)
+            _lib.fn("ab_symm_gate")(ctypes.addressof(pads), rank, world, epoch_ctr, 2 * lane, _lib.stream_ptr(self.device))
         self.kernel_launches += 1
         _lib.fn("ab_dist_adam_step")(
             mode, nvls, ctypes.addressof(g_arr), ctypes.addressof(p_arr), ctypes.addressof(pads), mcg, mcp,
@@ -603,7 +644,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
             self._dummy_overflow_buf.data_ptr(), group["lr"].data_ptr() if cap else None, group["step"].data_ptr() if cap else None,
             ctypes.addressof(seg.ready_ptrs) if (publish and seg.region is not None) else None,
             seg.bucket_ctr.data_ptr() if (publish and seg.region is not None) else None,
-            (seg.region.epoch & 0x7FFFFFFF) if (publish and seg.region is not None) else 0,
+            (seg.region.epoch & 0x7FFFFFFF) if (publish and seg.region is not None) else 0, int(gate), src_tab, src_n,
             _lib.dt(seg.grad_dtype), _lib.dt(seg.param_dtype), grid, _lib.stream_ptr(self.device))
 
     def _hybrid_split(self, seg: _Segment) -> int:

@@ -56,6 +56,11 @@ struct DistArgs {
   PeerPtrs ready;          // every rank's flag array [n_buckets][kMaxPeers] uint32 (null => feature off)
   uint32_t* bucket_ctr;    // local [n_buckets] chunk counters, zero between launches
   uint32_t ready_epoch;
+  // world == 1 only: gradients read in place from wherever autograd left them (no copy into the contiguous buffer). Table of
+  // {first chunk of the parameter in the flat space, gradient address, numel} sorted by chunk; every parameter starts on a chunk
+  // boundary in this layout, so a chunk has exactly one source. Null => the contiguous buffer.
+  const long long* src_tab; int src_n;
+  int skip_start;          // the start barrier already ran as a 1-CTA gate kernel in front of this launch (ab_symm_gate)
 };
 
 template <typename T> __device__ __forceinline__ void unpack8(const uint4* raw, float (&f)[8]) {
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   const int tid = threadIdx.x;
   const int D = a.sig.world, rank = a.sig.rank;
 
-  if (MODE != MODE_ADAM && D > 1) {
+  if (MODE != MODE_ADAM && D > 1 && !a.skip_start) {
     if (blockIdx.x == 0) signal_all(a.sig, a.chan_start, tid);
     wait_all(a.sig, a.chan_start, tid);
     __syncthreads();
@@ -151,6 +156,18 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
 #pragma unroll
               for (int q = 0; q < GV; q++)
                 raw[u][0][q] = multimem_ld_reduce16<TG>(reinterpret_cast<const char*>(a.mc_grads) + flat[u] * sizeof(TG) + q * 16);
+            } else if (DP == 1 && a.src_tab != nullptr) {
+              const long long fc = (flat[u] - tid * 8) / kDChunk;
+              int lo = 0, hi = a.src_n - 1;
+              while (lo < hi) {   // uniform across the CTA: broadcast loads out of L1
+                const int mid = (lo + hi + 1) >> 1;
+                if (__ldg(a.src_tab + 3 * mid) <= fc) lo = mid; else hi = mid - 1;
+              }
+              const char* base = reinterpret_cast<const char*>(__ldg(a.src_tab + 3 * lo + 1));
+              const long long e = (fc - __ldg(a.src_tab + 3 * lo)) * kDChunk + tid * 8;
+              const bool ok = base != nullptr && e + 8 <= __ldg(a.src_tab + 3 * lo + 2);
+#pragma unroll
+              for (int q = 0; q < GV; q++) raw[u][0][q] = ok ? ld_peer16(base + e * sizeof(TG) + q * 16) : make_uint4(0, 0, 0, 0);
             } else {
 #pragma unroll
               for (int p = 0; p < DP; p++) {
@@ -320,7 +337,8 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
                              float* norm_partials, float* norm_out, const float* grad_scale, float pre_scale, float lr, float beta1,
                              float beta2, float eps, int step, int adam_mode, int bias_correction, float decay, const int* noop,
                              const float* lr_ptr, const int* step_ptr, const uint64_t* ready, unsigned int* bucket_ctr,
-                             unsigned int ready_epoch, int dt_g, int dt_p, int grid, cudaStream_t st) {
+                             unsigned int ready_epoch, int skip_start, const long long* src_tab, int src_n, int dt_g, int dt_p, int grid,
+                             cudaStream_t st) {
   if (world < 1 || world > kMaxPeers) return -3;
   if (shard_elems % kDChunk != 0) return -4;
   DistArgs a;
@@ -330,7 +348,8 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
     a.sig.pads.p[i] = i < world && pads ? (void*)pads[i] : nullptr;
     a.ready.p[i] = i < world && ready ? (void*)ready[i] : nullptr;
   }
-  a.bucket_ctr = ready ? bucket_ctr : nullptr; a.ready_epoch = ready_epoch;
+  a.bucket_ctr = ready ? bucket_ctr : nullptr; a.ready_epoch = ready_epoch; a.skip_start = skip_start;
+  a.src_tab = (world == 1 && src_n > 0) ? src_tab : nullptr; a.src_n = src_n;
   a.mc_grads = (const void*)mc_grads; a.mc_params = (void*)mc_params;
   a.p = p; a.m = m; a.v = v; a.reduced = reduced;
   a.bucket_elems = bucket_elems; a.shard_elems = shard_elems; a.bucket_begin = bucket_begin; a.bucket_end = bucket_end;
@@ -368,6 +387,24 @@ AB_API int ab_symm_barrier(const uint64_t* pads, int rank, int world, unsigned i
   for (int i = 0; i < kMaxPeers; i++) s.pads.p[i] = i < world ? (void*)pads[i] : nullptr;
   s.rank = rank; s.world = world; s.epoch = epoch;
   symm_barrier_kernel<<<1, 32, 0, st>>>(s, channel);
+  AB_CHECK_LAUNCH();
+  return 0;
+}
+
+// Start barrier of a collective as its own 1-warp kernel: while this rank waits for its peers (which may still be busy with their backward
+// pass) only one warp is parked on the GPU instead of a whole grid of spinning CTAs; the collective kernel launched behind it on the same
+// stream skips its own start barrier. Uses epoch = *epoch_ctr + 1 like the kernel that follows (which is the one that stores it back).
+__global__ void symm_gate_kernel(Signal s, const uint32_t* epoch_ctr, int channel) {
+  s.epoch = *reinterpret_cast<const volatile uint32_t*>(epoch_ctr) + 1u;
+  signal_all(s, channel, threadIdx.x);
+  wait_all(s, channel, threadIdx.x);
+}
+AB_API int ab_symm_gate(const uint64_t* pads, int rank, int world, const unsigned int* epoch_ctr, int channel, cudaStream_t st) {
+  if (world <= 1) return 0;
+  Signal s;
+  for (int i = 0; i < kMaxPeers; i++) s.pads.p[i] = i < world ? (void*)pads[i] : nullptr;
+  s.rank = rank; s.world = world; s.epoch = 0;
+  symm_gate_kernel<<<1, 32, 0, st>>>(s, epoch_ctr, channel);
   AB_CHECK_LAUNCH();
   return 0;
 }
