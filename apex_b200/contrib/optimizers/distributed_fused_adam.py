@@ -599,12 +599,12 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         """One csrc/dist_adam.cu launch over buckets [b0, b1) of a segment (default: all of them). ``lane`` selects an independent set
         of signal channels / epoch counter / scratch so that two launches can be in flight at once (hybrid NVLS + P2P step)."""
         b1 = seg.n_buckets if b1 is None else b1
-        if mode != 2:
+        if mode in (0, 1):
             seg.norm_rows.append(b0)
         D = seg.D
         fused_comm = seg.fused and D > 1
         beta1, beta2 = group["betas"]
-        if seg.reduced is None and mode in (1, 2):
+        if seg.reduced is None and mode in (1, 2, 3):
             seg.reduced = torch.zeros(seg.local_elems, dtype=torch.float32, device=self.device)
         if fused_comm:
             pad = self._pad

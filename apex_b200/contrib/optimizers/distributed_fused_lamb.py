@@ -8,8 +8,13 @@ symmetric-heap layout of :class:`DistributedFusedAdam`:
   1. gradient reduce-scatter + global gradient norm: the in-kernel collective (``MODE_RS`` of csrc/dist_adam.cu) or NCCL/gloo;
   2. LAMB stage 1 on this rank's shard with the multi-tensor kernel over the (parameter ∩ shard) FRAGMENTS — it also emits the
      per-fragment sums of squares of p and of the update; fragment sums are scattered to per-parameter slots and all-reduced
-     (one small vector) to obtain the per-tensor trust ratios;
-  3. LAMB stage 2 on the fragments, cast to the parameter dtype, all-gather of the parameter buckets.
+     (one small vector: through the NVSwitch with ``multimem.ld_reduce`` / ``multimem.st`` when the group has multicast, csrc/
+     nvls_allreduce.cu) to obtain the per-tensor trust ratios;
+  3. LAMB stage 2 on the fragments; the all-gather is ``MODE_PUSH`` of csrc/dist_adam.cu: the fp32 shard is cast and pushed into
+     every rank's parameter buffer by one kernel (P2P stores or ``multimem.st``) — no NCCL call and no separate cast pass.
+On CUDA the whole step is free of host synchronisation (reference :1078-1094): overflow (non-finite global norm or GradScaler
+found_inf) becomes a device flag that the stage kernels honour, the applied-update counter used for bias correction lives on the
+device, loss-unscaling is folded into stage 1 through the device ``_grad_scale``, and the per-segment tensor tables are built once.
 Knobs of the reference that only shaped its NCCL pipeline (dwu_num_blocks/chunks/rs_pg/ar_pg/ag_pg, full_ar, ...) are accepted and
 ignored; ``clip_after_ar`` semantics (clip by the GLOBAL norm) is what is implemented; ``e5m2_allgather`` is available through
 ``param_sync_dtype=torch.float8_e5m2`` style casting of the gathered bucket.
@@ -44,6 +49,9 @@ class DistributedFusedLAMB(DistributedFusedAdam):
         self.max_grad_norm = max_grad_norm
         self.use_nvlamb = use_nvlamb
         self._frag_cache: dict = {}
+        self._lamb_cache: dict = {}
+        self._lamb_ar = None
+        self._applied_steps = None   # device int32: updates that were actually applied (bias correction on the CUDA path)
         self._global_scale = None
         self._is_accumulation_step = False
         self._last_step = False
@@ -78,6 +86,11 @@ class DistributedFusedLAMB(DistributedFusedAdam):
         self._frag_cache[id(seg)] = out
         return out
 
+    def _global_step(self):
+        if self._applied_steps is not None:
+            return int(self._applied_steps.item())
+        return super()._global_step()
+
     @torch.no_grad()
     def step(self, closure=None, *, grad_scaler=None):
         loss = None
@@ -92,25 +105,107 @@ class DistributedFusedLAMB(DistributedFusedAdam):
             self._grad_scale *= (gs.detach().to(self.device, torch.float32).reshape([]).reciprocal() if torch.is_tensor(gs) else 1.0 / float(gs))
         # global gradient norm (already unscaled through _grad_scale)
         gnorm = self.grad_norm()
+        device_flow = self.device.type == "cuda" and all(seg.fused for seg in self._segments)
+        found = None
         if grad_scaler is not None:
             st = grad_scaler._per_optimizer_states[id(self)]
             if st["stage"] is not torch.amp.grad_scaler.OptState.UNSCALED:
                 self.unscale_grads(grad_scaler=grad_scaler)
                 gnorm = self.grad_norm()
-            found = sum(v.to(self.device) for v in st["found_inf_per_device"].values())
-            if bool(found.item() > 0):
+            found = sum(v.to(self.device) for v in st["found_inf_per_device"].values()) > 0
+        if device_flow:
+            # no host synchronisation: the stage kernels skip on the device flag; the bias-correction step counts applied updates only
+            bad = torch.logical_not(torch.isfinite(gnorm))
+            if found is not None:
+                bad = torch.logical_or(bad, found.reshape([]))
+            self._dummy_overflow_buf.copy_(bad.to(torch.int32).reshape(1))
+            if self._applied_steps is None:
+                start = self.param_groups[0].get("step", 0)
+                self._applied_steps = torch.full((1,), int(start), dtype=torch.int32, device=self.device)
+            self._applied_steps += (self._dummy_overflow_buf == 0).to(torch.int32)
+            for group in self.param_groups:
+                group["step"] = group.get("step", 0) + 1     # host-side upper bound; the exact value is the device counter
+        else:
+            if (found is not None and bool(found.item())) or not bool(torch.isfinite(gnorm)):
                 self._finish_step(skipped=True)
                 return loss
-        elif not bool(torch.isfinite(gnorm)):
-            self._finish_step(skipped=True)
-            return loss
-        for group in self.param_groups:
-            group["step"] = group.get("step", 0) + 1
+            for group in self.param_groups:
+                group["step"] = group.get("step", 0) + 1
         for seg in self._segments:
             group = self.param_groups[seg.group_idx]
-            self._lamb_segment(seg, group, gnorm)
+            if device_flow:
+                self._lamb_segment_device(seg, group, gnorm)
+            else:
+                self._lamb_segment(seg, group, gnorm)
         self._finish_step(skipped=False)
         return loss
+
+    def load_state_dict(self, state_dict) -> None:
+        super().load_state_dict(state_dict)
+        if self._applied_steps is not None:
+            self._applied_steps.fill_(int(self.param_groups[0].get("step", 0)))
+
+    def _allreduce_small(self, t: torch.Tensor):
+        """Sum a small fp32 vector over the ZeRO group: NVSwitch multimem all-reduce when available, else NCCL."""
+        if self.distributed_size == 1:
+            return
+        if self._lamb_ar is None:
+            self._lamb_ar = False
+            try:
+                from ...parallel import nvls_allreduce as N
+
+                if N.available(self.distributed_process_group):
+                    self._lamb_ar = N.NvlsAllReduce(self.distributed_process_group, self.device, 1 << 20)
+            except Exception:  # noqa: BLE001  (no multicast on this group / fabric)
+                self._lamb_ar = False
+        flat = t.view(-1)
+        if self._lamb_ar and flat.numel() * 4 <= (1 << 20) - 4096:
+            self._lamb_ar.allreduce_(flat)
+        else:
+            dist.all_reduce(t, group=self.distributed_process_group)
+
+    def _lamb_segment_device(self, seg: _Segment, group, gnorm):
+        """CUDA path: stage 1 -> trust-ratio sums through the switch -> stage 2 -> in-kernel cast + push (MODE_PUSH). No host sync, no
+        per-step list building, no separate unscale / cast passes."""
+        dev = self.device
+        c = self._lamb_cache.get(id(seg))
+        if c is None:
+            frags = self._fragments(seg)
+            c = {"frags": frags, "nparam": len(seg.params)}
+            if frags:
+                g_l = [seg.reduced[s:s + n] for _, s, n in frags]
+                p_l = [seg.master[s:s + n] for _, s, n in frags]
+                m_l = [seg.exp_avg[s:s + n] for _, s, n in frags]
+                v_l = [seg.exp_avg_sq[s:s + n] for _, s, n in frags]
+                c["tb"] = amp_C.TensorTable([g_l, p_l, m_l, v_l])
+                c["idx"] = torch.tensor([pi for pi, _, _ in frags], device=dev, dtype=torch.long)
+                c["pn"] = torch.empty(len(frags), dtype=torch.float32, device=dev)
+                c["un"] = torch.empty(len(frags), dtype=torch.float32, device=dev)
+            c["sq"] = torch.zeros(2, c["nparam"], dtype=torch.float32, device=dev)
+            self._lamb_cache[id(seg)] = c
+        beta1, beta2 = group["betas"]
+        beta3 = 1.0 - beta1 if self.grad_averaging else 1.0
+        mode = 1 if self.adam_w_mode else 0
+        bc = 1 if group["bias_correction"] else 0
+        sq = c["sq"].zero_()
+        s_ = _lib.stream_ptr(dev)
+        noop = self._dummy_overflow_buf.data_ptr()
+        gn = gnorm.reshape(1)
+        if c["frags"]:
+            tb, d = c["tb"], c["tb"].dtypes
+            pp, pu = amp_C._partials(dev, tb.total_chunks, 1), amp_C._partials(dev, tb.total_chunks, 2)
+            _lib.fn("ab_mt_lamb_stage1")(*tb.head(), d[0], d[1], 0, float(beta1), float(beta2), float(beta3), 0, bc, float(group["eps"]), mode,
+                                         float(group["weight_decay"]), None, gn.data_ptr(), float(self.max_grad_norm), None, 1,
+                                         self._applied_steps.data_ptr(), self._grad_scale.data_ptr(), noop, pp.data_ptr(), pu.data_ptr(),
+                                         c["pn"].data_ptr(), c["un"].data_ptr(), 0, s_)
+            sq[0].index_add_(0, c["idx"], c["pn"] * c["pn"])
+            sq[1].index_add_(0, c["idx"], c["un"] * c["un"])
+        self._allreduce_small(sq)
+        if c["frags"]:
+            pn_f, un_f = sq[0].sqrt()[c["idx"]].contiguous(), sq[1].sqrt()[c["idx"]].contiguous()
+            _lib.fn("ab_mt_lamb_stage2")(*tb.head(), d[0], d[1], pn_f.data_ptr(), un_f.data_ptr(), float(group["lr"]), None,
+                                         float(group["weight_decay"]), None, int(bool(self.use_nvlamb)), 1, noop, 0, 0, s_)
+        self._launch(seg, 3, group, 1)    # MODE_PUSH: master shard -> parameter dtype -> every rank's parameter buffer
 
     def _lamb_segment(self, seg: _Segment, group, gnorm):
         frags = self._fragments(seg)

@@ -6,6 +6,8 @@
 //   MODE_RS    : reduce-scatter + norm only (writes the fp32 reduced shard) — used when the update needs the global norm
 //                first (clipping / GradScaler), and per bucket while backward is still running (overlap_grad_sync).
 //   MODE_ADAM  : Adam on the reduced shard + all-gather push.
+//   MODE_PUSH  : all-gather only: cast this rank's fp32 shard to the parameter dtype and push it to every rank (the in-kernel
+//                all-gather of optimizers whose update runs in other kernels: DistributedFusedLAMB).
 //
 // Replaces the reference pipeline: _grad_copy into buckets (distributed_fused_adam.py:1600-1666) -> NCCL
 // reduce_scatter_tensor (:1929-1947) -> multi_tensor_l2norm (:2216) -> DistAdamFunctor (multi_tensor_distopt_adam_kernel.cu:84-168)
@@ -22,7 +24,7 @@ namespace ab {
 constexpr int kDChunk = 2048;   // elements per CTA work item (256 threads x 8)
 constexpr int kDThreads = 256;
 
-enum { MODE_FUSED = 0, MODE_RS = 1, MODE_ADAM = 2 };
+enum { MODE_FUSED = 0, MODE_RS = 1, MODE_ADAM = 2, MODE_PUSH = 3 };
 
 struct DistArgs {
   PeerPtrs grads;    // every rank's full gradient buffer (TG) as mapped here
@@ -103,18 +105,20 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
   constexpr int PV = sizeof(TP) * 8 / 16;
   constexpr int NP = NVLS ? 1 : DP;        // gradient sources read per element
+  constexpr bool kReads = MODE == MODE_FUSED || MODE == MODE_RS;      // pulls / reduces gradients (start barrier, norm)
+  constexpr bool kUpdates = MODE == MODE_FUSED || MODE == MODE_ADAM;  // applies Adam to (p, m, v)
   __shared__ float red[40];
   __shared__ int s_last;
   const int tid = threadIdx.x;
   const int D = a.sig.world, rank = a.sig.rank;
 
-  if (MODE != MODE_ADAM && D > 1 && !a.skip_start) {
+  if (kReads && D > 1 && !a.skip_start) {
     if (blockIdx.x == 0) signal_all(a.sig, a.chan_start, tid);
     wait_all(a.sig, a.chan_start, tid);
     __syncthreads();
   }
 
-  const bool skip = (MODE != MODE_RS) && a.noop != nullptr && *a.noop != 0;
+  const bool skip = kUpdates && a.noop != nullptr && *a.noop != 0;
   AdamScalars h{1.f, a.lr, a.bc1, a.bc2, a.beta1, a.beta2, a.eps, a.decay, a.mode};
   if (MODE != MODE_RS) {
     if (a.grad_scale) h.gs = *a.grad_scale;
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
       if (MODE == MODE_ADAM) {
 #pragma unroll
         for (int u = 0; u < U; u++) if (on[u]) ld8(a.reduced + local[u], red_in[u]);
-      } else {
+      } else if (kReads) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (on[u]) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
         if (MODE == MODE_ADAM) {
 #pragma unroll
           for (int i = 0; i < 8; i++) g[i] = red_in[u][i];
-        } else {
+        } else if (kReads) {
 #pragma unroll
           for (int i = 0; i < 8; i++) g[i] = 0.f;
 #pragma unroll
@@ -207,10 +211,14 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
         if (MODE == MODE_RS) {
           st8(a.reduced + local[u], g);
         } else {
-          float p[8], m[8], v[8];
-          ld8(a.p + local[u], p); ld8(a.m + local[u], m); ld8(a.v + local[u], v);
-          adam8(p, m, v, g, h);
-          st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v);
+          float p[8];
+          ld8(a.p + local[u], p);
+          if (kUpdates) {
+            float m[8], v[8];
+            ld8(a.m + local[u], m); ld8(a.v + local[u], v);
+            adam8(p, m, v, g, h);
+            st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v);
+          }
           uint4 out[PV];
           {
             TP* e = reinterpret_cast<TP*>(out);
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   }
 
   // ---- epilogue: per-CTA norm partial, then the last CTA to finish closes the collective
-  if (MODE != MODE_ADAM) {
+  if (kReads) {
     const float s = block_sum(nsq, red);
     if (tid == 0) a.norm_partials[blockIdx.x] = s;
   }
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
-  if (MODE != MODE_ADAM) {
+  if (kReads) {
     float s = 0.f;
     for (int k = tid; k < (int)gridDim.x; k += kDThreads) s += __ldcg(a.norm_partials + k);
     s = block_sum(s, red);
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
     signal_all(a.sig, a.chan_end, tid);
     wait_all(a.sig, a.chan_end, tid);
     __syncthreads();
-    if (MODE != MODE_ADAM && tid == 0) {
+    if (kReads && tid == 0) {
       const float* scratch = reinterpret_cast<const float*>(reinterpret_cast<const uint32_t*>(a.sig.pads.p[rank]) + kPadChannels * kMaxPeers);
       float tot = 0.f;
       for (int r = 0; r < D; r++) tot += ld_relaxed_sys_f32(scratch + a.norm_slot * kMaxPeers + r);
@@ -322,6 +330,7 @@ template <typename TG, typename TP>
 int dist_launch(const DistArgs& a, int mode, int nvls, int grid, cudaStream_t st) {
   if (mode == MODE_FUSED) return dist_launch_mode<TG, TP, MODE_FUSED>(a, nvls, grid, st);
   if (mode == MODE_RS) return dist_launch_mode<TG, TP, MODE_RS>(a, nvls, grid, st);
+  if (mode == MODE_PUSH) return dist_launch_mode<TG, TP, MODE_PUSH>(a, nvls, grid, st);
   return dist_launch_mode<TG, TP, MODE_ADAM>(a, nvls, grid, st);
 }
 
@@ -368,7 +377,7 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
   const long long chunks = (long long)(bucket_end - bucket_begin) * (shard_elems / kDChunk);
   if (chunks <= 0) return 0;
   if (chunks < grid) grid = (int)chunks;
-  const bool use_nvls = nvls && world > 1 && ((mode == MODE_ADAM) || mc_grads) && ((mode == MODE_RS) || mc_params);
+  const bool use_nvls = nvls && world > 1 && ((mode == MODE_ADAM || mode == MODE_PUSH) || mc_grads) && ((mode == MODE_RS) || mc_params);
 #define DPAIR(TG, TP) return dist_launch<TG, TP>(a, mode, use_nvls ? 1 : 0, grid, st)
   if (dt_g == kBF16 && dt_p == kBF16) DPAIR(bf16, bf16);
   if (dt_g == kF16 && dt_p == kF16) DPAIR(f16, f16);

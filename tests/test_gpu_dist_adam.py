@@ -296,3 +296,41 @@ def test_eight_gpus_fused(cuda_dev):
     from apex_b200.testing.dist_harness import run_distributed
     from tests import _dist_cases as cases
     run_distributed(cases.dist_adam_matches_ddp_adamw, 8, "cuda", True, 3, True, backend="nccl")
+
+
+# ---------------------------------------------------------------- DistributedFusedLAMB: device flow (stage kernels + MODE_PUSH + NVLS sums)
+def test_world1_dist_lamb_matches_fused_lamb_and_skips_overflow_on_the_device(cuda_dev):
+    import copy
+    from apex_b200.contrib.optimizers import DistributedFusedLAMB
+    from apex_b200.optimizers import FusedLAMB
+    torch.manual_seed(0)
+    ref_model = torch.nn.Sequential(*[torch.nn.Linear(40, 40) for _ in range(4)]).to(cuda_dev)
+    dist_model = copy.deepcopy(ref_model)
+    ref_opt = FusedLAMB(ref_model.parameters(), lr=2e-2, weight_decay=0.01, max_grad_norm=0.5, eps=1e-6)
+    opt = DistributedFusedLAMB(dist_model.parameters(), lr=2e-2, weight_decay=0.01, max_grad_norm=0.5, eps=1e-6, bucket_cap_mb=0.01)
+    for it in range(4):
+        opt.zero_grad()
+        ref_opt.zero_grad()
+        x = torch.randn(8, 40, device=cuda_dev)
+        ref_model(x).pow(2).mean().backward()
+        dist_model(x).pow(2).mean().backward()
+        if it == 2:   # overflow step: must be skipped without reading the flag on the host, bias correction must not advance
+            before = [p.detach().clone() for p in dist_model.parameters()]
+            next(dist_model.parameters()).grad.view(-1)[0] = float("inf")
+            opt.step()
+            for p, q in zip(dist_model.parameters(), before):
+                assert torch.equal(p, q)
+            assert int(opt._applied_steps.item()) == 2
+            continue
+        ref_opt.step()
+        opt.step()
+        for pr, pd in zip(ref_model.parameters(), dist_model.parameters()):
+            torch.testing.assert_close(pd, pr, rtol=2e-4, atol=2e-5)
+    assert opt.state_dict()["state"]["step"] == 3
+
+
+def test_two_gpus_dist_lamb(cuda_dev):
+    _need(2)
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.dist_lamb_matches_fused_lamb, 2, "cuda", backend="nccl")
