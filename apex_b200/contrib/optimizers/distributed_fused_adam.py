@@ -256,7 +256,10 @@ class _Segment:
         base = self.grad_buf.data_ptr()
         for i, p in enumerate(self.params):
             t = self.live[i]
-            rows.append((self.offsets[i] // _CHUNK, t.data_ptr() if t is not None else base + self.offsets[i] * esz, p.numel()))
+            if t is not None:
+                rows.append((self.offsets[i] // _CHUNK, t.data_ptr(), p.numel()))
+            else:   # buffer slot: padded (and zero beyond the parameter) up to the next chunk boundary, so whole vectors are valid
+                rows.append((self.offsets[i] // _CHUNK, base + self.offsets[i] * esz, (p.numel() + _CHUNK - 1) // _CHUNK * _CHUNK))
         self.src_tab_host.copy_(torch.tensor(rows, dtype=torch.int64))
         self.src_tab_dev.copy_(self.src_tab_host, non_blocking=True)
         return self.src_tab_dev.data_ptr(), n

@@ -100,8 +100,9 @@ __device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
 // DP: compile-time bound on the number of peers looped over (1, 2, 4, 8); U: chunks whose remote gradient loads are issued
 // before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
 template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
-__global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_step_kernel(DistArgs a) {
-  if (a.epoch_ctr) a.sig.epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u;  // every CTA reads it before the closing CTA can store
+__global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_step_kernel(const __grid_constant__ DistArgs a) {
+  // every CTA reads the counter before the closing CTA can store it back; `a` itself stays read-only (constant bank, no stack copy)
+  const uint32_t epoch = a.epoch_ctr ? *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u : a.sig.epoch;
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
   constexpr int PV = sizeof(TP) * 8 / 16;
   constexpr int NP = NVLS ? 1 : DP;        // gradient sources read per element
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   const int D = a.sig.world, rank = a.sig.rank;
 
   if (kReads && D > 1 && !a.skip_start) {
-    if (blockIdx.x == 0) signal_all(a.sig, a.chan_start, tid);
-    wait_all(a.sig, a.chan_start, tid);
+    if (blockIdx.x == 0) signal_all_e(a.sig, epoch, a.chan_start, tid);
+    wait_all_e(a.sig, epoch, a.chan_start, tid);
     __syncthreads();
   }
 
@@ -296,8 +297,8 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
     }
   }
   if (D > 1) {
-    signal_all(a.sig, a.chan_end, tid);
-    wait_all(a.sig, a.chan_end, tid);
+    signal_all_e(a.sig, epoch, a.chan_end, tid);
+    wait_all_e(a.sig, epoch, a.chan_end, tid);
     __syncthreads();
     if (kReads && tid == 0) {
       const float* scratch = reinterpret_cast<const float*>(reinterpret_cast<const uint32_t*>(a.sig.pads.p[rank]) + kPadChannels * kMaxPeers);
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_st
   }
   if (tid == 0) {
     *a.done_ctr = 0u;
-    if (a.epoch_ctr) *a.epoch_ctr = a.sig.epoch;
+    if (a.epoch_ctr) *a.epoch_ctr = epoch;
   }
 }
 

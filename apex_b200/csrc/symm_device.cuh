@@ -98,4 +98,23 @@ __device__ __forceinline__ void wait_all(const Signal& s, int channel, int t) {
   }
 }
 
+// Variants that take the epoch separately: kernels that derive it from a device counter keep their argument struct read-only (a
+// modified __grid_constant__ / by-value parameter is copied to the stack and every later access goes through local memory).
+__device__ __forceinline__ void signal_all_e(const Signal& s, uint32_t epoch, int channel, int t) {
+  if (t < s.world) {
+    uint32_t* slot = reinterpret_cast<uint32_t*>(s.pads.p[t]) + channel * kMaxPeers + s.rank;
+    st_release_sys(slot, epoch);
+  }
+}
+__device__ __forceinline__ void wait_all_e(const Signal& s, uint32_t epoch, int channel, int t) {
+  if (t < s.world) {
+    const uint32_t* slot = reinterpret_cast<const uint32_t*>(s.pads.p[s.rank]) + channel * kMaxPeers + t;
+    long long t0 = clock64();
+    while ((int)(ld_acquire_sys(slot) - epoch) < 0) {
+      if (clock64() - t0 > 20000000000LL) { printf("apex_b200: peer %d never signalled channel %d (epoch %u)\n", t, channel, epoch); __trap(); }
+      __nanosleep(64);
+    }
+  }
+}
+
 }  // namespace ab

@@ -91,7 +91,7 @@ __device__ __forceinline__ float masked_grad(const BnArgs& a, bool fuse_relu, fl
 }
 
 // this rank's merged per-channel value -> local `merged` and every peer's exchange slot; bwd also emits grad_w / grad_b
-__device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float v1, float v2) {
+__device__ __forceinline__ void publish(const BnArgs& a, int xchg_off, int c, float v0, float v1, float v2) {
   if (a.is_bwd) {
     if (a.grad_w) a.grad_w[c] = v1 * a.invstd[c];
     if (a.grad_b) a.grad_b[c] = v0;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float 
   const int D = a.sig.world;
   if (D > 1) {
     for (int r = 0; r < D; r++) {
-      float* dst = reinterpret_cast<float*>(a.xchg.p[r]) + a.xchg_off + ((size_t)a.sig.rank * a.C + c) * 3;
+      float* dst = reinterpret_cast<float*>(a.xchg.p[r]) + xchg_off + ((size_t)a.sig.rank * a.C + c) * 3;
       st_relaxed_sys_f32(dst, v0); st_relaxed_sys_f32(dst + 1, v1); st_relaxed_sys_f32(dst + 2, v2);
     }
   }
@@ -110,12 +110,11 @@ __device__ __forceinline__ void publish(const BnArgs& a, int c, float v0, float 
 // IS_BWD / NHWC / FUSED (residual add and/or ReLU present) are compile-time: every instantiation carries only its own inner loops
 // (the runtime-flag version was 13.7k SASS instructions at 114 registers and stalled on instruction fetch for small layers).
 template <typename T, bool IS_BWD, bool NHWC, bool FUSED>
-__global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
+__global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(const __grid_constant__ BnArgs a) {
   constexpr int V = VecOf<T>::V;
-  if (a.epoch_ctr) {  // every CTA reads the counter here; it is advanced after the grid barrier that precedes the exchange
-    a.sig.epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u;
-    a.xchg_off = (int)(a.sig.epoch & 1u) * a.xchg_region;
-  }
+  // every CTA reads the counter here; it is advanced after the grid barrier that precedes the exchange. `a` stays read-only.
+  const uint32_t epoch = a.epoch_ctr ? *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u : a.sig.epoch;
+  const int xchg_off = a.epoch_ctr ? (int)(epoch & 1u) * a.xchg_region : a.xchg_off;
   __shared__ float sm[3][kBnThreads + 8];
   __shared__ int s_last;
   __shared__ float csum[2][kBnThreads / 32][64];  // NHWC: per-warp channel sums of one item
@@ -207,12 +206,12 @@ __global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
               for (int q = lane; q < S; q += 32) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) w = wf_merge(w, wf_shfl_xor(w, o));
-              if (lane == 0) publish(a, c, w.mean, w.m2, w.n);
+              if (lane == 0) publish(a, xchg_off, c, w.mean, w.m2, w.n);
             } else {
               float s0 = 0.f, s1 = 0.f;
               for (int q = lane; q < S; q += 32) { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
               s0 = warp_sum(s0); s1 = warp_sum(s1);
-              if (lane == 0) publish(a, c, s0, s1, (float)per_c);
+              if (lane == 0) publish(a, xchg_off, c, s0, s1, (float)per_c);
             }
             if (lane == 0) { a.unit_ctr[c] = 0u; __threadfence_system(); }
           }
@@ -312,13 +311,13 @@ __global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
               for (int q = lane; q < S; q += 32) w = wf_merge(w, Wf{__ldcg(base + q * 3), __ldcg(base + q * 3 + 1), __ldcg(base + q * 3 + 2)});
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) w = wf_merge(w, wf_shfl_xor(w, o));
-              if (lane == 0) publish(a, c, w.mean, w.m2, w.n);
+              if (lane == 0) publish(a, xchg_off, c, w.mean, w.m2, w.n);
             } else {
               float s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
               for (int q = lane; q < S; q += 32) { s0 += __ldcg(base + q * 3); s1 += __ldcg(base + q * 3 + 1); }
               s0 = warp_sum(s0); s1 = warp_sum(s1);
-              if (lane == 0) publish(a, c, s0, s1, (float)per_c);
+              if (lane == 0) publish(a, xchg_off, c, s0, s1, (float)per_c);
             }
           }
           __threadfence_system();
@@ -334,12 +333,12 @@ __global__ void __launch_bounds__(kBnThreads, 1) syncbn_kernel(BnArgs a) {
   if (a.phases & 2) {
     const int D = a.sig.world, rank = a.sig.rank;
     if (D > 1) {
-      if (blockIdx.x == 0) { __threadfence_system(); signal_all(a.sig, a.channel, tid); }
-      wait_all(a.sig, a.channel, tid);
+      if (blockIdx.x == 0) { __threadfence_system(); signal_all_e(a.sig, epoch, a.channel, tid); }
+      wait_all_e(a.sig, epoch, a.channel, tid);
       __syncthreads();
-      if (a.epoch_ctr && blockIdx.x == 0 && tid == 0) *a.epoch_ctr = a.sig.epoch;
+      if (a.epoch_ctr && blockIdx.x == 0 && tid == 0) *a.epoch_ctr = epoch;
     }
-    const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + a.xchg_off : nullptr;
+    const float* mine = D > 1 ? reinterpret_cast<const float*>(a.xchg.p[rank]) + xchg_off : nullptr;
     for (int c = blockIdx.x * kBnThreads + tid; c < C; c += gridDim.x * kBnThreads) {
       if (!IS_BWD) {
         Wf w{0.f, 0.f, 0.f};

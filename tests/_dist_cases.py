@@ -141,7 +141,9 @@ def dist_adam_overlap_param_sync(rank, world, device_type):
     mb = copy.deepcopy(ma)
     kw = dict(lr=1e-2, weight_decay=0.01, device=dev, bucket_cap_mb=0.1)
     a = DistributedFusedAdam(ma.parameters(), overlap_param_sync=True, **kw)
-    b = DistributedFusedAdam(mb.parameters(), overlap_grad_sync=False, **kw)
+    # the twin gets its own process group => its own signal pad / epoch counters: its step kernels run on the main stream WHILE a's
+    # parameter push is still in flight on the side stream (one optimizer never overlaps two of its own collectives)
+    b = DistributedFusedAdam(mb.parameters(), overlap_grad_sync=False, process_group=dist.new_group(list(range(world))), **kw)
     attach_param_sync_hooks(ma)
     g = torch.Generator().manual_seed(100 + rank)
     guarded0 = G.stats["guarded"]
@@ -207,7 +209,7 @@ def dist_adam_cuda_graph_replays(rank, world, device_type):
         assert torch.equal(x, y)
     for sa, sb in zip(a._segments, b._segments):
         assert torch.equal(sa.master, sb.master) and torch.equal(sa.exp_avg_sq, sb.exp_avg_sq)
-    assert int(a.param_groups[0]["step"].item()) == int(b.param_groups[0]["step"].item()) == 14
+    assert int(a.param_groups[0]["step"].item()) == int(b.param_groups[0]["step"].item()) == 13
 
 
 def dist_adam_two_dimensional_grid(rank, world, device_type):
@@ -362,7 +364,9 @@ def dist_adam_grad_scaler_skips_on_inf(rank, world, device_type):
     from apex_b200.contrib.optimizers import DistributedFusedAdam
     dev = torch.device("cuda", rank)
     model = _model(dev)
-    opt = DistributedFusedAdam(model.parameters(), lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20)
+    # overlap_grad_sync=False: the test plants the inf AFTER backward; with the overlap the bucket may already have been reduce-scattered
+    # by then (as in the reference, gradients must not be edited behind the hooks' back)
+    opt = DistributedFusedAdam(model.parameters(), lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20, overlap_grad_sync=False)
     scaler = torch.amp.GradScaler("cuda", init_scale=128.0)
     x = torch.randn(5, 7, device=dev)
     before = [p.detach().clone() for p in model.parameters()]
@@ -406,6 +410,26 @@ def dist_lamb_matches_fused_lamb(rank, world, device_type):
         opt.step()
         for pr, pd in zip(ref_model.parameters(), dist_model.parameters()):
             torch.testing.assert_close(pd, pr, rtol=2e-4, atol=2e-5)
+
+
+def nccl_p2p_native_exchange(rank, world, device_type):
+    """contrib.nccl_p2p over its own ncclComm (csrc/nccl_p2p.cpp): a real unique id broadcast from rank 0, grouped send / recv on the current
+    stream, open-chain ends zeroed; compared with the values the neighbours hold."""
+    from apex_b200.contrib.nccl_p2p import nccl_p2p as P
+    dev = torch.device("cuda", rank)
+    uid = P.get_unique_nccl_id(1).to(dev)
+    dist.broadcast(uid, src=0)
+    handle = P.init_nccl_comm(uid, rank, world)
+    assert P._groups[handle][1] is not None, "the native communicator was not built"
+    for shape, dtype in (((2, 8, 1, 16), torch.float16), ((3, 5, 7), torch.float32)):
+        lo_out = torch.full(shape, float(10 * rank + 1), device=dev, dtype=dtype)
+        hi_out = torch.full(shape, float(10 * rank + 2), device=dev, dtype=dtype)
+        lo_in, hi_in = P.left_right_halo_exchange(handle, rank == 0, rank == world - 1, lo_out, hi_out)
+        want_lo = 0.0 if rank == 0 else float(10 * (rank - 1) + 2)           # the left neighbour's right-going halo
+        want_hi = 0.0 if rank == world - 1 else float(10 * (rank + 1) + 1)
+        torch.testing.assert_close(lo_in, torch.full_like(lo_in, want_lo))
+        torch.testing.assert_close(hi_in, torch.full_like(hi_in, want_hi))
+    P.destroy_nccl_comm(handle)
 
 
 def peer_halo_exchange_matches_allgather(rank, world, device_type):

@@ -159,6 +159,22 @@ def test_self_multihead_attn(cuda_dev):
     torch.testing.assert_close(out, r, atol=2e-4, rtol=2e-4)
 
 
+def test_nccl_p2p_native_communicator(cuda_dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.nccl_p2p_native_exchange, 2, "cuda", backend="nccl")
+
+
+def test_spatial_bottleneck_two_gpus(cuda_dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.spatial_bottleneck_matches_full, 2, "cuda", backend="nccl")
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_peer_halo_exchange(cuda_dev, world):
     if torch.cuda.device_count() < world:
