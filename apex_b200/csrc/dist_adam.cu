@@ -100,7 +100,7 @@ __device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
 // DP: compile-time bound on the number of peers looped over (1, 2, 4, 8); U: chunks whose remote gradient loads are issued
 // before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
 template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
-__global__ void __launch_bounds__(kDThreads, (!NVLS && DP <= 2) ? 3 : 2) dist_step_kernel(const __grid_constant__ DistArgs a) {
+__global__ void __launch_bounds__(kDThreads, (!NVLS && DP == 1) ? 3 : 2) dist_step_kernel(const __grid_constant__ DistArgs a) {
   // every CTA reads the counter before the closing CTA can store it back; `a` itself stays read-only (constant bank, no stack copy)
   const uint32_t epoch = a.epoch_ctr ? *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u : a.sig.epoch;
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
