@@ -758,6 +758,8 @@ def spatial_bottleneck_matches_full(rank, world, device_type):
     full = Bottleneck(16, 8, 32).to(dev)
     for bn in (full.bn1, full.bn2, full.bn3, full.downsample[1]):
         bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5)
+    # cuDNN picks TF32 / different algorithms for the full image and for the shards: compare at TF32 resolution on CUDA
+    tol = 1e-5 if device_type == "cpu" else 1e-2
     x = torch.randn(2, 16, 8 * world, 6, device=dev, requires_grad=True)
     want = full(x)
     gout = torch.randn_like(want)
@@ -769,11 +771,11 @@ def spatial_bottleneck_matches_full(rank, world, device_type):
         sp.load_state_dict(full.state_dict())
         xs = x.detach()[:, :, rows].contiguous().requires_grad_()
         got = sp(xs)
-        torch.testing.assert_close(got, want.detach()[:, :, rows], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(got, want.detach()[:, :, rows], atol=tol, rtol=tol)
         # backward: the halo-row gradients travel back to the neighbours; weight gradients are partial sums over the H-shards
         got.backward(gout[:, :, rows].contiguous())
-        torch.testing.assert_close(xs.grad, x.grad[:, :, rows], atol=1e-4, rtol=1e-4)
+        torch.testing.assert_close(xs.grad, x.grad[:, :, rows], atol=10 * tol, rtol=10 * tol)
         for (n, p), (_, q) in zip(sp.named_parameters(), full.named_parameters()):
             g = p.grad.clone()
             dist.all_reduce(g)
-            torch.testing.assert_close(g, q.grad, atol=1e-4, rtol=1e-4, msg=lambda m, n=n: f"{n}: {m}")
+            torch.testing.assert_close(g, q.grad, atol=10 * tol, rtol=10 * tol, msg=lambda m, n=n: f"{n}: {m}")
