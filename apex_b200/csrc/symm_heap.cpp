@@ -206,3 +206,70 @@ AB_API int ab_ipc_close(uint64_t ptr) { return (int)cudaIpcCloseMemHandle((void*
 AB_API int ab_ipc_free(uint64_t ptr) { return (int)cudaFree((void*)ptr); }
 
 AB_API int ab_close_fd(int fd) { return close(fd); }
+
+// ---- pluggable allocator over the shareable heap -----------------------------------------------------------------------
+// torch.cuda.memory.CUDAPluggableAllocator(<this library>, "ab_symm_pool_malloc", "ab_symm_pool_free") -> torch.cuda.MemPool: every
+// tensor allocated inside the pool lives in a shareable VMM allocation, so it can be peer-mapped (and multicast-bound) AFTER the fact
+// with ab_symm_pool_export + ab_symm_import on the peers. The reference's counterpart wraps ncclMemAlloc / ncclMemFree
+// (apex/contrib/csrc/nccl_allocator/NCCLAllocator.cpp:17-38) so that NCCL can register user buffers; here the consumers are this
+// library's own in-kernel collectives.
+#include <map>
+#include <mutex>
+
+namespace {
+struct PoolBlock { CUmemGenericAllocationHandle h; size_t bytes; int device; };
+std::map<uintptr_t, PoolBlock> g_pool;   // base address -> block
+std::mutex g_pool_mu;
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) void* ab_symm_pool_malloc(ssize_t size, int device, cudaStream_t) {
+  if (size <= 0) return nullptr;
+  uint64_t gran = 0;
+  if (ab_symm_granularity(device, 1, &gran) != 0 || gran == 0) return nullptr;
+  const uint64_t bytes = ((uint64_t)size + gran - 1) / gran * gran;
+  uint64_t h = 0, p = 0;
+  int fd = -1;
+  if (ab_symm_alloc(device, bytes, gran, &h, &p, &fd) != 0) return nullptr;
+  if (fd >= 0) close(fd);   // re-exported on demand (ab_symm_pool_export)
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool[(uintptr_t)p] = PoolBlock{(CUmemGenericAllocationHandle)h, (size_t)bytes, device};
+  return (void*)(uintptr_t)p;
+}
+
+extern "C" __attribute__((visibility("default"))) void ab_symm_pool_free(void* ptr, ssize_t, int, cudaStream_t) {
+  PoolBlock b;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool.find((uintptr_t)ptr);
+    if (it == g_pool.end()) return;
+    b = it->second;
+    g_pool.erase(it);
+  }
+  ab_symm_free((uint64_t)b.h, (uint64_t)(uintptr_t)ptr, (uint64_t)b.bytes);
+}
+
+// Block that contains `ptr`: base address, size, and a fresh POSIX fd of its physical allocation (the caller closes it after its peers
+// have imported it). Returns -3 when the pointer does not belong to the pool.
+AB_API int ab_symm_pool_export(const void* ptr, uint64_t* base_out, uint64_t* bytes_out, int* fd_out) {
+  DRV(cuMemExportToShareableHandle);
+  PoolBlock b;
+  uintptr_t base = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool.upper_bound((uintptr_t)ptr);
+    if (it == g_pool.begin()) return -3;
+    --it;
+    if ((uintptr_t)ptr >= it->first + it->second.bytes) return -3;
+    base = it->first;
+    b = it->second;
+  }
+  int fd = -1;
+  CK(p_cuMemExportToShareableHandle(&fd, b.h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *base_out = (uint64_t)base; *bytes_out = (uint64_t)b.bytes; *fd_out = fd;
+  return 0;
+}
+
+AB_API int ab_symm_pool_blocks() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  return (int)g_pool.size();
+}

@@ -432,6 +432,31 @@ def nccl_p2p_native_exchange(rank, world, device_type):
     P.destroy_nccl_comm(handle)
 
 
+def symmetric_pool_peer_map(rank, world, device_type):
+    """Tensors allocated through the library's pluggable allocator (torch.cuda.MemPool) are peer-mapped after the fact: every rank reads the
+    others' tensors through the returned addresses (NVLink P2P loads issued by an ordinary torch copy from the aliased pointer)."""
+    from apex_b200.contrib.nccl_allocator import nccl_allocator as A
+    from apex_b200.parallel.symmetric import _tensor_from_ptr
+    dev = torch.device("cuda", rank)
+    with A.symmetric_mem():
+        _pad = torch.empty(1000, device=dev)                       # noqa: F841  (an unrelated allocation in front)
+        t = torch.full((3, 257), float(rank + 1), device=dev)
+    torch.cuda.synchronize()
+    ptrs = A.peer_map(t, None)
+    assert len(ptrs) == world and ptrs[rank] == t.data_ptr()
+    dist.barrier()
+    for r in range(world):
+        alias = _tensor_from_ptr(ptrs[r], t.numel() * 4, dev, None).view(torch.float32).view(3, 257)
+        torch.testing.assert_close(alias.clone(), torch.full((3, 257), float(r + 1), device=dev))
+    dist.barrier()
+    t.mul_(2)                                                      # writes are visible through the peers' mappings
+    torch.cuda.synchronize()
+    dist.barrier()
+    alias = _tensor_from_ptr(ptrs[(rank + 1) % world], t.numel() * 4, dev, None).view(torch.float32)
+    assert float(alias[0]) == 2.0 * ((rank + 1) % world + 1)
+    dist.barrier()
+
+
 def peer_halo_exchange_matches_allgather(rank, world, device_type):
     """PeerHaloExchanger1d (one fused P2P kernel) against halos built from an all-gather of the interiors; NCHW, channels-last and
     explicit NHWC, H- and W-split, fp16 and fp32, repeated to exercise the parity double-buffering."""

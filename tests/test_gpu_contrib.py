@@ -159,6 +159,34 @@ def test_self_multihead_attn(cuda_dev):
     torch.testing.assert_close(out, r, atol=2e-4, rtol=2e-4)
 
 
+def test_symmetric_pluggable_allocator_pool(cuda_dev):
+    """torch.cuda.MemPool over csrc/symm_heap.cpp ab_symm_pool_malloc / _free: allocations come from shareable VMM blocks."""
+    import ctypes
+    from apex_b200 import _lib
+    from apex_b200.contrib.nccl_allocator import nccl_allocator as A
+    blocks = _lib.raw_fn("ab_symm_pool_blocks", ctypes.c_int, [])
+    n0 = blocks()
+    with A.symmetric_mem():
+        a = torch.randn(1 << 20, device=cuda_dev)
+        b = torch.randn(1 << 20, device=cuda_dev)
+    assert blocks() > n0
+    torch.testing.assert_close((a + b).sum(), a.sum() + b.sum(), rtol=1e-4, atol=1e-2)
+    base, nbytes, fd = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_int(-1)
+    _lib.declare("ab_symm_pool_export", "p p p p")
+    _lib.fn("ab_symm_pool_export")(a.data_ptr(), ctypes.addressof(base), ctypes.addressof(nbytes), ctypes.addressof(fd))
+    assert base.value <= a.data_ptr() < base.value + nbytes.value and fd.value >= 0
+    import os
+    os.close(fd.value)
+
+
+def test_symmetric_pool_peer_map_two_gpus(cuda_dev):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from apex_b200.testing.dist_harness import run_distributed
+    from tests import _dist_cases as cases
+    run_distributed(cases.symmetric_pool_peer_map, 2, "cuda", backend="nccl")
+
+
 def test_nccl_p2p_native_communicator(cuda_dev):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
