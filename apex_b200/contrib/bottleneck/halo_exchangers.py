@@ -82,11 +82,11 @@ class HaloExchangerPeer(HaloExchanger):
             tx[self.wrap_around_left_rank_in_group][1].copy_(left_output_halo)
         if not self.right_zero:
             tx[self.wrap_around_right_rank_in_group][0].copy_(right_output_halo)
-        self.pad.barrier(channel=42)
+        self.pad.barrier(channel=46)
         mine = tx[self.rank_in_group]
         left_input_halo.zero_() if self.left_zero else left_input_halo.copy_(mine[0])
         right_input_halo.zero_() if self.right_zero else right_input_halo.copy_(mine[1])
-        self.pad.barrier(channel=43)
+        self.pad.barrier(channel=47)
         if not inplace:
             return left_input_halo, right_input_halo
 

@@ -13,7 +13,7 @@ import ctypes
 from ... import _lib
 from ...parallel.symmetric import SignalPad
 
-_lib.declare("ab_halo_exchange_1d", "p i p p p p p p p i i i i i i i p i p")
+_lib.declare("ab_halo_exchange_1d", "p i p p p p p p p i i i i i i i p l p i p")
 
 
 class PeerHaloExchanger1d:
@@ -67,8 +67,10 @@ class PeerHaloExchanger1d:
             tx = self.peer_pool.allocate_peer_tensors([2, 2, low_out.numel()], y.dtype, False, False)
             self._tx = st = (key, tx, torch.zeros(1, dtype=torch.int32, device=y.device), [0])
         _, tx, ticket, it = st
-        par = it[0] & 1
-        it[0] += 1
+        # the epoch — and with it the parity of the double-buffered transfer slabs — lives in device memory (pad.dev_epochs[42]): the
+        # kernel advances it, so the exchange can be captured in a CUDA graph and replayed
+        par = 0
+        parity_stride = (tx[0][1].data_ptr() - tx[0][0].data_ptr())
         # innermost-last ordering of the slab dims so that 16-byte vectors run along the unit-stride dim
         order = sorted(range(4), key=lambda d: (-low_out.stride(d), d))
         base = y.untyped_storage().data_ptr()
@@ -80,5 +82,6 @@ class PeerHaloExchanger1d:
         me, lo, hi = self.peer_rank, self.low_neighbor, self.high_neighbor
         _lib.fn("ab_halo_exchange_1d")(base, es, ctypes.addressof(meta), tx[lo][par].data_ptr(), tx[hi][par].data_ptr(),
                                        tx[me][par].data_ptr(), pads[lo], pads[hi], pads[me], me, lo, hi, int(not self.low_zero),
-                                       int(not self.high_zero), 42, self.pad.next_epoch(), ticket.data_ptr(), int(numSM),
+                                       int(not self.high_zero), 42, 0, self.pad.dev_epochs[42:43].data_ptr(), parity_stride,
+                                       ticket.data_ptr(), int(numSM),
                                        _lib.stream_ptr(y.device))

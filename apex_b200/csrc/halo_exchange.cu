@@ -19,6 +19,9 @@ struct HaloArgs {
   int rank, rank_low, rank_high, has_low, has_high, channel;
   uint32_t epoch;
   unsigned int* ticket;
+  // device-resident epoch (graph-replayable): epoch = *epoch_ctr + 1; the transfer buffers are double-buffered by the epoch's parity
+  // (tx_* point at parity 0, parity 1 lies `parity_stride` bytes further); the CTA that signals the neighbours stores the epoch back
+  uint32_t* epoch_ctr; long long parity_stride;
 };
 
 template <typename E>
@@ -32,9 +35,12 @@ __device__ __forceinline__ long long slab_index(const HaloArgs& a, long long i, 
 }
 
 template <typename E, typename VT>
-__global__ void __launch_bounds__(256) halo_kernel(HaloArgs a) {
+__global__ void __launch_bounds__(256) halo_kernel(const __grid_constant__ HaloArgs a) {
   constexpr int VEC = sizeof(VT) / sizeof(E);
   __shared__ int s_last;
+  const uint32_t epoch = a.epoch_ctr ? *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u : a.epoch;
+  const long long poff = a.epoch_ctr ? (long long)(epoch & 1u) * a.parity_stride : 0;
+  char* const tx_low = a.tx_low + poff; char* const tx_high = a.tx_high + poff; char* const tx_mine = a.tx_mine + poff;
   const long long nvec = a.slab / VEC;
   const long long gstride = (long long)gridDim.x * 256;
   const E* y = reinterpret_cast<const E*>(a.y);
@@ -43,11 +49,11 @@ __global__ void __launch_bounds__(256) halo_kernel(HaloArgs a) {
     const long long o = slab_index<E>(a, i, VEC);
     if (a.has_low) {
       const VT v = *reinterpret_cast<const VT*>(y + a.off[0] + o);
-      *reinterpret_cast<VT*>(a.tx_low + (a.slab + i * VEC) * sizeof(E)) = v;
+      *reinterpret_cast<VT*>(tx_low + (a.slab + i * VEC) * sizeof(E)) = v;
     }
     if (a.has_high) {
       const VT v = *reinterpret_cast<const VT*>(y + a.off[2] + o);
-      *reinterpret_cast<VT*>(a.tx_high + (i * VEC) * sizeof(E)) = v;
+      *reinterpret_cast<VT*>(tx_high + (i * VEC) * sizeof(E)) = v;
     }
   }
   // ---- the last CTA to finish its pushes tells the neighbours
@@ -57,9 +63,10 @@ __global__ void __launch_bounds__(256) halo_kernel(HaloArgs a) {
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence_system();
-    if (a.has_low) st_release_sys(a.pad_low + a.channel * kMaxPeers + a.rank, a.epoch);
-    if (a.has_high) st_release_sys(a.pad_high + a.channel * kMaxPeers + a.rank, a.epoch);
+    if (a.has_low) st_release_sys(a.pad_low + a.channel * kMaxPeers + a.rank, epoch);
+    if (a.has_high) st_release_sys(a.pad_high + a.channel * kMaxPeers + a.rank, epoch);
     *a.ticket = 0u;
+    if (a.epoch_ctr) *a.epoch_ctr = epoch;   // every CTA has read it (all tickets are in)
   }
   // ---- wait for the neighbours' pushes into my buffer
   if (threadIdx.x < 2) {
@@ -67,8 +74,8 @@ __global__ void __launch_bounds__(256) halo_kernel(HaloArgs a) {
     if (need) {
       const uint32_t* slot = a.pad_mine + a.channel * kMaxPeers + (threadIdx.x == 0 ? a.rank_low : a.rank_high);
       long long t0 = clock64();
-      while ((int)(ld_acquire_sys(slot) - a.epoch) < 0) {
-        if (clock64() - t0 > 20000000000LL) { printf("apex_b200 halo: neighbour never signalled (epoch %u)\n", a.epoch); __trap(); }
+      while ((int)(ld_acquire_sys(slot) - epoch) < 0) {
+        if (clock64() - t0 > 20000000000LL) { printf("apex_b200 halo: neighbour never signalled (epoch %u)\n", epoch); __trap(); }
         __nanosleep(64);
       }
     }
@@ -79,8 +86,8 @@ __global__ void __launch_bounds__(256) halo_kernel(HaloArgs a) {
   VT zero; memset(&zero, 0, sizeof(VT));
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += gstride) {
     const long long o = slab_index<E>(a, i, VEC);
-    const VT lo = a.has_low ? __ldcg(reinterpret_cast<const VT*>(a.tx_mine + (i * VEC) * sizeof(E))) : zero;
-    const VT hi = a.has_high ? __ldcg(reinterpret_cast<const VT*>(a.tx_mine + (a.slab + i * VEC) * sizeof(E))) : zero;
+    const VT lo = a.has_low ? __ldcg(reinterpret_cast<const VT*>(tx_mine + (i * VEC) * sizeof(E))) : zero;
+    const VT hi = a.has_high ? __ldcg(reinterpret_cast<const VT*>(tx_mine + (a.slab + i * VEC) * sizeof(E))) : zero;
     *reinterpret_cast<VT*>(yw + a.off[1] + o) = lo;
     *reinterpret_cast<VT*>(yw + a.off[3] + o) = hi;
   }
@@ -93,7 +100,8 @@ using namespace ab;
 // meta: 4 slab extents, 4 strides, 4 offsets (low_out, low_in, high_out, high_in) as int64, strides/offsets in elements.
 AB_API int ab_halo_exchange_1d(void* y, int esize, const long long* meta, void* tx_low, void* tx_high, void* tx_mine, void* pad_low,
                                void* pad_high, void* pad_mine, int rank, int rank_low, int rank_high, int has_low, int has_high,
-                               int channel, unsigned int epoch, void* ticket, int max_ctas, cudaStream_t s) {
+                               int channel, unsigned int epoch, unsigned int* epoch_ctr, long long parity_stride, void* ticket, int max_ctas,
+                               cudaStream_t s) {
   HaloArgs a;
   a.y = (char*)y;
   a.slab = 1;
@@ -101,7 +109,7 @@ AB_API int ab_halo_exchange_1d(void* y, int esize, const long long* meta, void* 
   a.tx_low = (char*)tx_low; a.tx_high = (char*)tx_high; a.tx_mine = (char*)tx_mine;
   a.pad_low = (uint32_t*)pad_low; a.pad_high = (uint32_t*)pad_high; a.pad_mine = (uint32_t*)pad_mine;
   a.rank = rank; a.rank_low = rank_low; a.rank_high = rank_high; a.has_low = has_low; a.has_high = has_high;
-  a.channel = channel; a.epoch = epoch; a.ticket = (unsigned int*)ticket;
+  a.channel = channel; a.epoch = epoch; a.ticket = (unsigned int*)ticket; a.epoch_ctr = epoch_ctr; a.parity_stride = parity_stride;
   if (a.slab <= 0) return 0;
   if (esize != 2 && esize != 4) return -2;
   const int V = 16 / esize;
