@@ -18,6 +18,7 @@
 // Cross-rank ordering uses epoch signals (symm_device.cuh): start = "my grads are final and my params buffer may be
 // overwritten"; end = "I no longer read your grads and everything I pushed into your params is visible".
 #include "symm_device.cuh"
+#include <cstdlib>
 
 namespace ab {
 
@@ -88,6 +89,17 @@ __device__ __forceinline__ void adam8(float (&p)[8], float (&m)[8], float (&v)[8
     p[i] -= h.lr * upd;
   }
 }
+// evict-first variants: optimizer state is touched exactly once per step, keeping it in L2 only displaces lines that are about to be written
+__device__ __forceinline__ void ld8_cs(const float* src, float (&d)[8]) {
+  float4 a, b;
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src));
+  asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 4));
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st8_cs(float* dst, const float (&d)[8]) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(d[0]), "f"(d[1]), "f"(d[2]), "f"(d[3]) : "memory");
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(d[4]), "f"(d[5]), "f"(d[6]), "f"(d[7]) : "memory");
+}
 __device__ __forceinline__ void ld8(const float* src, float (&d)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
   d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
@@ -99,8 +111,9 @@ __device__ __forceinline__ void st8(float* dst, const float (&d)[8]) {
 
 // DP: compile-time bound on the number of peers looped over (1, 2, 4, 8); U: chunks whose remote gradient loads are issued
 // before any of them is consumed (NVLink round trips are ~2-4 us: bytes in flight per SM, not threads, set the bandwidth).
-template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U>
-__global__ void __launch_bounds__(kDThreads, (!NVLS && DP == 1) ? 3 : 2) dist_step_kernel(const __grid_constant__ DistArgs a) {
+// MB: minimum resident CTAs per SM the register budget is set for; CS: evict-first loads / stores of the optimizer state.
+template <typename TG, typename TP, int MODE, bool NVLS, int DP, int U, int MB = ((!NVLS && DP == 1) ? 3 : 2), bool CS = false>
+__global__ void __launch_bounds__(kDThreads, MB) dist_step_kernel(const __grid_constant__ DistArgs a) {
   // every CTA reads the counter before the closing CTA can store it back; `a` itself stays read-only (constant bank, no stack copy)
   const uint32_t epoch = a.epoch_ctr ? *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr) + 1u : a.sig.epoch;
   constexpr int GV = sizeof(TG) * 8 / 16;  // 16-byte vectors per 8 gradient elements
@@ -213,12 +226,13 @@ __global__ void __launch_bounds__(kDThreads, (!NVLS && DP == 1) ? 3 : 2) dist_st
           st8(a.reduced + local[u], g);
         } else {
           float p[8];
-          ld8(a.p + local[u], p);
+          if (CS) ld8_cs(a.p + local[u], p); else ld8(a.p + local[u], p);
           if (kUpdates) {
             float m[8], v[8];
-            ld8(a.m + local[u], m); ld8(a.v + local[u], v);
+            if (CS) { ld8_cs(a.m + local[u], m); ld8_cs(a.v + local[u], v); } else { ld8(a.m + local[u], m); ld8(a.v + local[u], v); }
             adam8(p, m, v, g, h);
-            st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v);
+            if (CS) { st8_cs(a.p + local[u], p); st8_cs(a.m + local[u], m); st8_cs(a.v + local[u], v); }
+            else { st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v); }
           }
           uint4 out[PV];
           {
@@ -318,7 +332,20 @@ int dist_launch_mode(const DistArgs& a, int nvls, int grid, cudaStream_t st) {
   const int D = a.sig.world;
 #define DGO(N, DPV, UV) dist_step_kernel<TG, TP, MODE, N, DPV, UV><<<grid, kDThreads, 0, st>>>(a)
   if (nvls) DGO(true, 1, 8);
-  else if (D <= 1) DGO(false, 1, 2);
+  else if (D <= 1) {
+    // tuning knob for the single-GPU instantiation (APEX_B200_DIST_W1: 0 = default); see DESIGN.md for the A/B table
+    static const int variant = getenv("APEX_B200_DIST_W1") ? atoi(getenv("APEX_B200_DIST_W1")) : 0;
+#define DGW(UV, MBV, CSV) dist_step_kernel<TG, TP, MODE, false, 1, UV, MBV, CSV><<<grid, kDThreads, 0, st>>>(a)
+    switch (variant) {
+      case 1: DGW(4, 2, false); break;
+      case 2: DGW(2, 4, false); break;
+      case 3: DGW(2, 3, true); break;
+      case 4: DGW(4, 2, true); break;
+      case 5: DGW(1, 4, true); break;
+      default: DGW(2, 3, false); break;
+    }
+#undef DGW
+  }
   else if (D == 2) DGO(false, 2, 4);
   else if (D <= 4) DGO(false, 4, 2);
   else DGO(false, 8, 2);

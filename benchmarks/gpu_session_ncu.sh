@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu --set full captures (one GPU, one kernel instance per capture) of the named hot kernels; exports CSV on the box, keeps no .ncu-rep.
 mkdir -p gpurun_out/ncu
-NCU="ncu --set full --clock-control none --import-source on -f"
+NCU="ncu --set full --clock-control none --import-source on --kernel-name-base demangled -f"
 cap() {  # name target kernel-regex skip
   name=$1; target=$2; rx=$3; skip=${4:-2}
   timeout 240 $NCU -k "regex:$rx" -s $skip -c 1 -o gpurun_out/ncu/$name python benchmarks/profile_targets.py $target > gpurun_out/ncu/$name.log 2>&1
