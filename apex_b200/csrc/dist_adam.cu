@@ -336,13 +336,13 @@ int dist_launch_mode(const DistArgs& a, int nvls, int grid, cudaStream_t st) {
     // tuning knob for the single-GPU instantiation (APEX_B200_DIST_W1: 0 = default); see DESIGN.md for the A/B table
     static const int variant = getenv("APEX_B200_DIST_W1") ? atoi(getenv("APEX_B200_DIST_W1")) : 0;
 #define DGW(UV, MBV, CSV) dist_step_kernel<TG, TP, MODE, false, 1, UV, MBV, CSV><<<grid, kDThreads, 0, st>>>(a)
-    switch (variant) {
+    switch (variant) {   // A/B on B200 (gpurun_out/w1_variants.jsonl): U = 2 with 4 resident CTAs per SM and a 6-per-SM grid is the fastest
       case 1: DGW(4, 2, false); break;
-      case 2: DGW(2, 4, false); break;
+      case 2: DGW(2, 3, false); break;
       case 3: DGW(2, 3, true); break;
       case 4: DGW(4, 2, true); break;
       case 5: DGW(1, 4, true); break;
-      default: DGW(2, 3, false); break;
+      default: DGW(2, 4, false); break;
     }
 #undef DGW
   }

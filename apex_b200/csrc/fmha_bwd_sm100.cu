@@ -14,7 +14,8 @@
 // The two are the same program with the operand roles exchanged ("X" = resident pair, "Y" = streamed pair):
 //   S' = X1 Y1^T,  dP' = X2 Y2^T,  [out1 += P' Y2],  out2 += dS' Y1
 // S and dP are recomputed in both (one extra pair of QK-sized GEMMs) instead of a dQ reduction through global atomics.
-// Warp roles as in the forward kernel: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM allocation, warps 4-7 element-wise + epilogue.
+// Warp roles as in the forward kernel: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM allocation, warps 4-11 element-wise + epilogue (two
+// threads per resident row: warps w and w + 4 share a TMEM lane quarter and take one 32-column half of every 64-column tile each).
 // TMEM columns: S'[2] at 0 / 64, dP'[2] at 128 / 192, out1 at 256, out2 at 384 (fp32, 128 lanes).
 #include "fmha_common.cuh"
 
@@ -53,7 +54,7 @@ struct BwdSmem {
 };
 
 template <typename T, int D, bool DKV>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
                 const __grid_constant__ CUtensorMap map_y1, const __grid_constant__ CUtensorMap map_y2, BwdParams p) {
   using S = BwdSmem<D>;
@@ -95,8 +96,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1);
     for (int s = 0; s < Y_STAGES; s++) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&s_full[a], 1); mbar_init(&s_empty[a], 128); }
-    mbar_init(e_full, 128); mbar_init(e_empty, 1); mbar_init(o_full, 1);
+    for (int a = 0; a < 2; a++) { mbar_init(&s_full[a], 1); mbar_init(&s_empty[a], 256); }
+    mbar_init(e_full, 256); mbar_init(e_empty, 1); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
@@ -181,7 +182,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================================= element-wise: thread <-> resident row (= TMEM lane)
-    const int qd = warp - 4, row = qd * 32 + lane, tid = threadIdx.x - 128;
+    const int qd = (warp - 4) & 3, half = (warp - 4) >> 2, row = qd * 32 + lane, tid = threadIdx.x - 128;   // tid in [0, 256)
     const int oi = ot * TO + row;                            // index of the resident row inside its sequence
     const bool row_ok = oi < outer_len;
     const float sl2 = p.scale * 1.4426950408889634f;
@@ -201,22 +202,24 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
       const float* st = stat + (jj & 1) * 2 * TI;
       if (DKV) {  // per-QUERY statistics of this tile -> shared memory (read as broadcasts below); buffers alternate
         float* sw = stat + (jj & 1) * 2 * TI;
-        const int qi = inner0 + (tid & (TI - 1));
-        const float* src = tid < TI ? p.lse : p.delta;
-        float val = qi < q_len ? src[(size_t)(q_row0 + qi) * p.heads + head] : 0.f;
-        if (tid < TI) val *= 1.4426950408889634f;
-        sw[tid] = val;                                        // tid < 64: lse * log2(e); tid >= 64: delta
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid < 2 * TI) {
+          const int qi = inner0 + (tid & (TI - 1));
+          const float* src = tid < TI ? p.lse : p.delta;
+          float val = qi < q_len ? src[(size_t)(q_row0 + qi) * p.heads + head] : 0.f;
+          if (tid < TI) val *= 1.4426950408889634f;
+          sw[tid] = val;                                      // tid < 64: lse * log2(e); 64 <= tid < 128: delta
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       } else if (has_bias) {  // per-KEY bias of this tile -> the (otherwise unused) statistics buffer
         float* sw = stat + (jj & 1) * 2 * TI;
         if (tid < TI) { const int ki = inner0 + tid; sw[tid] = ki < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + ki] * 1.4426950408889634f : 0.f; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(&s_full[sb], sph, 220);
       mbar_wait(e_empty, eeph ^ 1, 221);  // the GEMMs of the previous tile have finished reading P' / dS' (first use: passes)
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TI; c0 += 32) {
+      for (int c0 = half * (TI / 2); c0 < (half + 1) * (TI / 2); c0 += 32) {
         uint32_t rs[32], rd[32];
         tmem_ld32(tmem_s + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sb * TI + c0), rs);
         tmem_ld32(tmem_dp + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sb * TI + c0), rd);
@@ -268,7 +271,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
                            : reinterpret_cast<T*>(p.out2) + grow * p.out2_row_stride + (size_t)head * p.out2_head_stride;
       const uint32_t tm = which == 0 ? tmem_o1 : tmem_o2;
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
+      for (int c0 = half * (D / 2); c0 < (half + 1) * (D / 2); c0 += 32) {
         uint32_t r[32];
         if (n > 0) { tmem_ld32(tm + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, r); tmem_ld_wait(); }
         if (row_ok) {
@@ -338,8 +341,8 @@ AB_API int ab_fmha_bwd(const void* q, const void* k, const void* v, const void* 
     if (e != cudaSuccess) return (int)e;                                                                                     \
     e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, ab::fmha::BwdSmem<DD>::kTotal);                \
     if (e != cudaSuccess) return (int)e;                                                                                     \
-    kkv<<<grid_kv, 256, ab::fmha::BwdSmem<DD>::kTotal, st>>>(mk_o, mv_o, mq_i, mdo_i, pkv);   /* X = (K, V), Y = (Q, dO) */     \
-    kq<<<grid_q, 256, ab::fmha::BwdSmem<DD>::kTotal, st>>>(mq_o, mdo_o, mk_i, mv_i, pq);      /* X = (Q, dO), Y = (K, V) */     \
+    kkv<<<grid_kv, 384, ab::fmha::BwdSmem<DD>::kTotal, st>>>(mk_o, mv_o, mq_i, mdo_i, pkv);   /* X = (K, V), Y = (Q, dO) */     \
+    kq<<<grid_q, 384, ab::fmha::BwdSmem<DD>::kTotal, st>>>(mq_o, mdo_o, mk_i, mv_i, pq);      /* X = (Q, dO), Y = (K, V) */     \
   } while (0)
   if (is_bf16) { if (d == 64) FMHA_BWD_GO(bf16, 64); else FMHA_BWD_GO(bf16, 128); }
   else { if (d == 64) FMHA_BWD_GO(f16, 64); else FMHA_BWD_GO(f16, 128); }

@@ -3,8 +3,10 @@
 // Spec: reference apex/contrib/csrc/fmha (mma.sync kernels, fp16, d = 64, seq <= 512) and the batched-GEMM + softmax pipeline of
 // apex/contrib/csrc/multihead_attn. Variable-length batches through cu_seqlens, optional causal mask.
 //
-// One CTA per (128-query tile, head, sequence). Warp roles as in gemm_sm100.cu: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
-// allocation, warps 4-7 softmax (one query row per thread = one TMEM lane).
+// One CTA per (128-query tile, head, sequence), 12 warps. Warp roles as in gemm_sm100.cu: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
+// allocation, warps 4-11 softmax: TWO threads per query row (= TMEM lane; warps w and w + 4 share a lane quarter and take one 64-key
+// half of every tile each) — the softmax is instruction-issue bound, eight warps hide the TMEM-load / MUFU latencies that four could
+// not (ncu: 38 % issue utilisation with four). P is double buffered so the softmax of tile j + 1 overlaps the P V of tile j.
 // TWO PASSES over the keys instead of online-softmax rescaling (rescaling the TMEM accumulator costs a TMEM load + store per tile):
 //   pass 1  S = Q K_j^T (TMEM, double buffered) -> row maximum only (no exponentials)
 //   pass 2  S recomputed (K tiles come from L2), P = exp2((S - m) * scale * log2e) written as bf16/fp16 into shared memory in the
@@ -43,14 +45,14 @@ struct Smem {
   static constexpr int kQOff = 0;
   static constexpr int kKOff = kQ;
   static constexpr int kVOff = kKOff + KV_STAGES * kKV;
-  static constexpr int kPOff = kVOff + KV_STAGES * kKV;
-  static constexpr int kBarOff = kPOff + kP;
+  static constexpr int kPOff = kVOff + KV_STAGES * kKV;   // two P buffers
+  static constexpr int kBarOff = kPOff + 2 * kP;
   static constexpr int kBiasOff = kBarOff + 256;     // [2][TK] floats: key bias * log2(e) of the current / next tile
   static constexpr int kTotal = kBiasOff + 2 * TK * 4 + 1024;
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                 ab::fmha::Params p) {
   using S = Smem<D>;
@@ -64,9 +66,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* v_empty = v_full + KV_STAGES;
   uint64_t* s_full = v_empty + KV_STAGES;         // 2
   uint64_t* s_empty = s_full + 2;                 // 2
-  uint64_t* p_full = s_empty + 2;                 // 1
-  uint64_t* p_empty = p_full + 1;                 // 1
-  uint64_t* o_full = p_empty + 1;                 // 1
+  uint64_t* p_full = s_empty + 2;                 // 2
+  uint64_t* p_empty = p_full + 2;                 // 2
+  uint64_t* o_full = p_empty + 2;                 // 1
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,8 +89,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; s++) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&s_full[a], 1); mbar_init(&s_empty[a], 128); }
-    mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    for (int a = 0; a < 2; a++) { mbar_init(&s_full[a], 1); mbar_init(&s_empty[a], 256); mbar_init(&p_full[a], 256); mbar_init(&p_empty[a], 1); }
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
@@ -125,7 +127,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t idesc_o = make_idesc(p.is_bf16, 0, 1, TQ, D);    // O = P V   : P K-major (keys contiguous), V MN-major (d contiguous)
     const uint32_t q_addr = smem_u32(smem + S::kQOff), p_addr = smem_u32(smem + S::kPOff);
     if (n_kv > 0) mbar_wait(q_full, 0, 110);
-    int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0; int sb = 0; uint32_t sph = 0; uint32_t pph = 0;
+    int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0; int sb = 0; uint32_t sph = 0; uint32_t pph[2] = {0, 0};
     auto issue_s = [&]() {  // S[sb] = Q K[ks]^T
       mbar_wait(&k_full[ks], kph, 111);
       mbar_wait(&s_empty[sb], sph ^ 1, 112);
@@ -148,28 +150,30 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (n_kv > 0) issue_s();                             // pass 2, tile 0
     for (int j = 0; j < n_kv; j++) {
       if (j + 1 < n_kv) issue_s();                       // S of the next tile overlaps the softmax of this one
-      mbar_wait(p_full, pph, 113);
+      const int pb = j & 1;
+      mbar_wait(&p_full[pb], pph[pb], 113);
       mbar_wait(&v_full[vs], vph, 114);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t v_addr = smem_u32(smem + S::kVOff + vs * S::kKV);
 #pragma unroll
         for (int k = 0; k < TK / UMMA_K; k++) {
-          const uint64_t adesc = make_desc(p_addr + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t adesc = make_desc(p_addr + pb * S::kP + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024);
           const uint64_t bdesc = make_desc(v_addr + k * 2048, TK * 128, 1024);  // 16 key rows x 128 B per step; d blocks TK*128 B apart
           umma_f16(tmem_o, adesc, bdesc, idesc_o, (j | k) ? 1u : 0u);
         }
         umma_commit(&v_empty[vs]);
-        umma_commit(p_empty);
+        umma_commit(&p_empty[pb]);
         if (j == n_kv - 1) umma_commit(o_full);
       }
       __syncwarp();
-      pph ^= 1;
+      pph[pb] ^= 1;
       if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================================= softmax / epilogue: thread <-> query row
-    const int q = warp - 4, row = q * 32 + lane;            // TMEM lane == row of the tile
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;   // lane quarter (== warp % 4) and which 64-key half of every tile
+    const int row = q * 32 + lane;                          // TMEM lane == row of the tile
     const int qi = qt * TQ + row;                           // index inside the sequence
     const bool row_ok = qi < q_len;
     const float sl2 = p.scale * 1.4426950408889634f;
@@ -177,10 +181,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     float m = -INFINITY;                                    // row maximum of t = S * scale * log2(e) + bias * log2(e)
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOff);
     const bool has_bias = p.key_bias != nullptr;
-    auto stage_bias = [&](int j, int slot) {                // 128 softmax threads: one key each; double buffered, one barrier per tile
+    auto stage_bias = [&](int j, int slot) {                // the 128 threads of one half stage one key each; double buffered, one barrier per tile
       const int kidx = j * TK + row;
-      bias_s[(slot & 1) * TK + row] = kidx < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + kidx] * 1.4426950408889634f : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (half == 0) bias_s[(slot & 1) * TK + row] = kidx < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + kidx] * 1.4426950408889634f : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     auto key_ok = [&](int kidx) { return kidx < k_len && (!p.causal || kidx <= qi + diag); };
     // ---- pass 1: row maximum
@@ -190,7 +194,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait(&s_full[sb], sph, 120);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TK; c0 += 32) {
+      for (int c0 = half * (TK / 2); c0 < (half + 1) * (TK / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
         tmem_ld_wait();
@@ -202,21 +206,28 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_arrive(&s_empty[sb]);
       if (++sb == 2) { sb = 0; sph ^= 1; }
     }
+    // the two threads of a row combine their partial maxima through the (still unused) first P buffer
+    float* xch = reinterpret_cast<float*>(smem + S::kPOff);
+    xch[half * TQ + row] = m;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    m = fmaxf(xch[row], xch[TQ + row]);
+    asm volatile("bar.sync 2, 256;" ::: "memory");    // nobody overwrites the exchange area (P tile 0) before everybody has read it
     if (m == -INFINITY) m = 0.f;  // fully masked row: every p becomes 0
     // ---- pass 2: P = exp2(S * sl2 + bias2 - m), l = sum P, P -> shared memory (swizzled), O accumulated by the MMA warp
     float l = 0.f;
-    uint32_t peph = 0;
-    uint8_t* pbuf = smem + S::kPOff;
+    uint32_t peph[2] = {0, 0};
     const uint32_t bh = (uint32_t)(b * p.heads + head);
     const int comp_row = (qi & 1) * 2;
     for (int j = 0; j < n_kv; j++) {
       if (has_bias) stage_bias(j, n_kv + j);                  // keeps the (tile & 1) double-buffer parity running across the two passes
       const float* bj = bias_s + ((n_kv + j) & 1) * TK;
+      const int pb = j & 1;
+      uint8_t* pbuf = smem + S::kPOff + pb * S::kP;
       mbar_wait(&s_full[sb], sph, 121);
-      mbar_wait(p_empty, peph ^ 1, 122);  // the previous PV has finished reading the P buffer (first use: passes immediately)
+      mbar_wait(&p_empty[pb], peph[pb] ^ 1, 122);  // the PV that last read this P buffer has finished (first use: passes immediately)
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TK; c0 += 32) {
+      for (int c0 = half * (TK / 2); c0 < (half + 1) * (TK / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
         tmem_ld_wait();
@@ -245,17 +256,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       tc_fence_before();
       fence_proxy_async();          // generic-proxy stores to shared memory -> visible to the tensor-core (async) proxy
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[pb]);
       mbar_arrive(&s_empty[sb]);
-      peph ^= 1;
+      peph[pb] ^= 1;
       if (++sb == 2) { sb = 0; sph ^= 1; }
     }
     // ---- epilogue: O / l
     if (n_kv > 0) { mbar_wait(o_full, 0, 123); tc_fence_after(); }
+    // every MMA has completed: the P buffers are free again; the two threads of a row add their partial row sums through one of them
+    xch[half * TQ + row] = l;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    l = xch[row] + xch[TQ + row];
     const float inv_l = l > 0.f ? (p.has_drop ? p.drop.rp : 1.f) / l : 0.f;
     T* orow = reinterpret_cast<T*>(p.out) + (size_t)(q_row0 + qi) * p.out_row_stride + (size_t)head * p.out_head_stride;
 #pragma unroll 1
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = half * (D / 2); c0 < (half + 1) * (D / 2); c0 += 32) {
       uint32_t r[32];
       if (n_kv > 0) { tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r); tmem_ld_wait(); }
       if (row_ok) {
@@ -268,7 +283,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
     }
-    if (row_ok && p.lse) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * 0.6931471805599453f + logf(l) : -INFINITY;
+    if (row_ok && p.lse && half == 0) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * 0.6931471805599453f + logf(l) : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -310,7 +325,7 @@ AB_API int ab_fmha_fwd(const void* q, const void* k, const void* v, void* out, f
     auto kern = fmha_fwd_kernel<T, DD>;                                                                             \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ab::fmha::Smem<DD>::kTotal);      \
     if (e != cudaSuccess) return (int)e;                                                                            \
-    kern<<<grid, 256, ab::fmha::Smem<DD>::kTotal, st>>>(mq, mk, mv, p);                                                       \
+    kern<<<grid, 384, ab::fmha::Smem<DD>::kTotal, st>>>(mq, mk, mv, p);                                                       \
   } while (0)
   if (is_bf16) { if (d == 64) FMHA_GO(bf16, 64); else FMHA_GO(bf16, 128); }
   else { if (d == 64) FMHA_GO(f16, 64); else FMHA_GO(f16, 128); }

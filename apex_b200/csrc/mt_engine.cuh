@@ -2,6 +2,7 @@
 // host runtime), one persistent launch walks every chunk of every tensor. Replaces the reference's by-value 4 KB kernel
 // argument struct + one launch per <=110/64/48/36 tensors (reference: csrc/multi_tensor_apply.cuh:13-103).
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include <tuple>
 
@@ -135,7 +136,9 @@ __global__ void __launch_bounds__(kMTThreads, 3) mt_kernel(MTTable tb, Op op) {
 }
 
 inline int mt_grid(int total_chunks) {
-  int g = kNumSMs * 3;
+  // CTAs per SM of the persistent grid. 3 = the resident count; a finer grid (6, 8) lets the block scheduler even out the two dies.
+  static const int mult = getenv("APEX_B200_MT_GRID_MULT") ? atoi(getenv("APEX_B200_MT_GRID_MULT")) : 3;
+  int g = kNumSMs * (mult > 0 ? mult : 3);
   return total_chunks < g ? (total_chunks > 0 ? total_chunks : 1) : g;
 }
 

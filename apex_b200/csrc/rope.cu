@@ -31,8 +31,11 @@ __device__ __forceinline__ float ld_cs(const void* p, int dt, long long i) {
   return __bfloat162float(reinterpret_cast<const bf16*>(p)[i]);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) rope_kernel(RopeArgs a) {
+// VEC: unit element stride on both sides, every stride / offset a multiple of 8 elements, rotary half a multiple of 8: a work item is
+// 8 consecutive dims of the first half and the matching 8 of the second half (two 16-byte loads, two 16-byte stores, one integer
+// division) — the scalar version (2-byte accesses, a division per pair) was instruction-issue bound at 16 % of HBM (profiles/rope_fwd.md).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) rope_kernel(const __grid_constant__ RopeArgs a) {
   extern __shared__ float sc[];  // cos[nsc], sin[nsc]
   const int nsc = (a.mode == ROPE_2D) ? a.d : a.r;
   float* cs = sc;
@@ -74,6 +77,35 @@ __global__ void __launch_bounds__(256) rope_kernel(RopeArgs a) {
     const int r = (a.mode == ROPE_2D) ? a.d / 2 : a.r;
     const int hr = r / 2;
     const int pairs_per_head = parts * hr;
+    if (VEC) {
+      constexpr int V = 16 / sizeof(T);          // elements per 16-byte vector (8 for 16-bit types, 4 for fp32)
+      const int vp = hr / V, per_head = parts * vp;
+      for (int j = threadIdx.x; j < a.h * per_head; j += blockDim.x) {
+        const int head = j / per_head, jj = j - head * per_head;
+        const int part = jj / vp, i = (jj - part * vp) * V;
+        const int base = part * r;
+        const long long xi = xoff + head * a.xs_h + base + i, oi = ooff + head * a.os_h + base + i;
+        float v0[V], v1[V], o0[V], o1[V];
+        load_vec<T, V>(v0, x + xi);
+        load_vec<T, V>(v1, x + xi + hr);
+#pragma unroll
+        for (int e = 0; e < V; e++) {
+          const float c0 = cs[base + i + e], c1 = cs[base + i + e + hr], s0 = sn[base + i + e], s1 = sn[base + i + e + hr];
+          if (!a.is_bwd) { o0[e] = v0[e] * c0 - v1[e] * s0; o1[e] = v1[e] * c1 + v0[e] * s1; }
+          else { o0[e] = v0[e] * c0 + v1[e] * s1; o1[e] = v1[e] * c1 - v0[e] * s0; }
+        }
+        store_vec<T, V>(out + oi, o0);
+        store_vec<T, V>(out + oi + hr, o1);
+      }
+      if (a.mode != ROPE_2D && a.d > a.r) {  // pass-through tail, 16 bytes at a time
+        const int tv = (a.d - a.r) / V;
+        for (int j = threadIdx.x; j < a.h * tv; j += blockDim.x) {
+          const int head = j / tv, i = a.r + (j - head * tv) * V;
+          *reinterpret_cast<uint4*>(out + ooff + head * a.os_h + i) = *reinterpret_cast<const uint4*>(x + xoff + head * a.xs_h + i);
+        }
+      }
+      continue;
+    }
     for (int j = threadIdx.x; j < a.h * pairs_per_head; j += blockDim.x) {
       const int head = j / pairs_per_head, jj = j - head * pairs_per_head;
       const int part = jj / hr, i = jj - part * hr;
@@ -115,7 +147,13 @@ AB_API int ab_rope(const void* x, void* out, int mode, int is_bwd, int cached, i
   const int nsc = (mode == ROPE_2D) ? d : r;
   const int grid = n_tokens < kNumSMs * 8 ? n_tokens : kNumSMs * 8;
   const size_t smem = sizeof(float) * 2 * (size_t)nsc;
-  AB_DISPATCH_FLOAT3(dt, T, rope_kernel<T><<<grid, 256, smem, st>>>(a));
+  const int esz = dt == kF32 ? 4 : 2, V = 16 / esz;
+  const int rr = (mode == ROPE_2D) ? d / 2 : r;
+  auto m8 = [&](long long v) { return v % V == 0; };
+  const bool vec = xsd == 1 && osd == 1 && (rr / 2) % V == 0 && rr % 2 == 0 && (d - r) % V == 0 && m8(xs0) && m8(xs1) && m8(xsh) && m8(os0) &&
+                   m8(os1) && m8(osh) && m8(xs_b2) && m8(xs_ih) && m8(xs_iw) && m8(os_b2) && m8(os_seq) && aligned16(x) && aligned16(out);
+  if (vec) { AB_DISPATCH_FLOAT3(dt, T, (rope_kernel<T, true><<<grid, 256, smem, st>>>(a))); }
+  else { AB_DISPATCH_FLOAT3(dt, T, (rope_kernel<T, false><<<grid, 256, smem, st>>>(a))); }
   AB_CHECK_LAUNCH();
   return 0;
 }
