@@ -156,6 +156,7 @@ declare("ab_mt_axpby", _T + " i i i f f i p p")
 declare("ab_mt_norm", _T + " i p p p p p p i i f f p")
 declare("ab_mt_l2norm_scale", _T + " i i f p p p p p")
 declare("ab_mt_adam", _T + " i i f f f f i i i f i p p p p p")
+declare("ab_mt_adam_swa", _T + " i i f f f f i i i i f f f p p")
 declare("ab_mt_adagrad", _T + " i f f i f p")
 declare("ab_mt_sgd", _T + " i i i f f f f i i i f p p")
 declare("ab_mt_novograd", _T + " i f f f f i i f i i p p")

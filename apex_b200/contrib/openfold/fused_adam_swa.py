@@ -1,4 +1,4 @@
-"""FusedAdamSWA: Adam on fp32 params + bf16 compute copy + stochastic-weight-average update in two persistent launches.
+"""FusedAdamSWA: Adam on fp32 params + bf16 compute copy + stochastic-weight-average update in ONE persistent launch (csrc/mt_optim.cu AdamSwaOp).
 Reference: apex/contrib/openfold_triton/fused_adam_swa.py:209-400 (one Triton multi-tensor kernel over pointer tables)."""
 from __future__ import annotations
 
@@ -79,24 +79,35 @@ class FusedAdamSWA(Optimizer):
                 st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32), torch.zeros_like(p, dtype=torch.float32)
         # gradients come from the bf16 compute copies (OpenFold runs fwd/bwd on them)
         grads = [(c.grad if c.grad is not None else p.grad) for p, c in zip(params, cparams)]
-        if grad_clip_scale is not None:
-            grads = [g * grad_clip_scale for g in grads]
-        lists = [grads, params, [self.state[p]["exp_avg"] for p in params], [self.state[p]["exp_avg_sq"] for p in params]]
+        exp_avg, exp_avg_sq = [self.state[p]["exp_avg"] for p in params], [self.state[p]["exp_avg_sq"] for p in params]
         beta1, beta2 = group["betas"]
         mode = 1 if self.adam_math_mode == AdamMathType.ApexAdamW else 0
-        cuda = params[0].is_cuda
-        if cuda:
-            amp_C.multi_tensor_adam(65536, None, lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode,
-                                    int(group["bias_correction"]), group["weight_decay"])
-        else:
-            ref.multi_tensor_adam(lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode, int(group["bias_correction"]),
-                                  group["weight_decay"])
-        # SWA: first step copies, later steps swa += (1 - decay) * (p - swa); then the bf16 compute copy
+        # SWA: the first step copies, later steps swa = decay * swa + (1 - decay) * p
         n = self.swa_param_groups[0]["n_averaged"]
         a, b = (0.0, 1.0) if n == 0 else (self.swa_decay_rate, 1.0 - self.swa_decay_rate)
-        noop = torch.zeros(1, dtype=torch.int32, device=params[0].device)
-        amp_C.multi_tensor_axpby(65536, noop, [sparams, params, sparams], a, b, -1)
-        amp_C.multi_tensor_scale(65536, noop, [params, cparams], 1.0)
+        cuda = params[0].is_cuda
+        if cuda and all(p.dtype == torch.float32 for p in params) and all(s_.dtype == torch.float32 for s_ in sparams):
+            # ONE persistent launch: Adam + SWA + compute copy (+ the clip factor read from the device), csrc/mt_optim.cu AdamSwaOp
+            clip = None
+            if grad_clip_scale is not None:
+                clip = (grad_clip_scale if torch.is_tensor(grad_clip_scale) else torch.tensor(float(grad_clip_scale)))
+                clip = clip.to(params[0].device, torch.float32).reshape(1)
+            amp_C.multi_tensor_adam_swa(65536, [grads, params, exp_avg, exp_avg_sq, sparams, cparams], group["lr"], beta1, beta2, group["eps"],
+                                        group["step"], mode, int(self.adam_math_mode == AdamMathType.PyTorchAdam), int(group["bias_correction"]),
+                                        group["weight_decay"], a, b, clip)
+        else:
+            if grad_clip_scale is not None:
+                grads = [g * grad_clip_scale for g in grads]
+            lists = [grads, params, exp_avg, exp_avg_sq]
+            if cuda:
+                amp_C.multi_tensor_adam(65536, None, lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode,
+                                        int(group["bias_correction"]), group["weight_decay"])
+            else:
+                ref.multi_tensor_adam(lists, group["lr"], beta1, beta2, group["eps"], group["step"], mode, int(group["bias_correction"]),
+                                      group["weight_decay"])
+            noop = torch.zeros(1, dtype=torch.int32, device=params[0].device)
+            amp_C.multi_tensor_axpby(65536, noop, [sparams, params, sparams], a, b, -1)
+            amp_C.multi_tensor_scale(65536, noop, [params, cparams], 1.0)
         self.swa_param_groups[0]["n_averaged"] = n + 1
         if self.set_grad_none:
             for c in cparams:

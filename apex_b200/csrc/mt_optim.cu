@@ -57,6 +57,40 @@ struct AdamOp {
   __device__ void end(const Ctx&, int, int, float (&)[2], float*) const {}
 };
 
+// ---------------------------------------------------------------- Adam + stochastic weight average + low-precision compute copy in ONE pass
+// slots: 0 g (bf16/fp16/fp32), 1 p (fp32), 2 m, 3 v, 4 swa (fp32), 5 compute copy (16-bit). Reference: the single Triton multi-tensor kernel of
+// apex/contrib/openfold_triton/fused_adam_swa.py:209-400 (Adam math modes, swa = decay * swa + (1 - decay) * p, bf16 copy, clip scale).
+struct AdamSwaOp {
+  static constexpr unsigned kRead = 0b011111u, kWrite = 0b111110u;
+  static constexpr int kAcc = 0;
+  using Ctx = NoCtx2;
+  float beta1, beta2, eps, decay, lr, bc1, bc2, swa_a, swa_b; int mode;  // mode 0: L2 (ApexAdam / PyTorchAdam), 1: decoupled (ApexAdamW)
+  int torch_math;           // PyTorchAdam: denom = sqrt(v) / sqrt(bc2) + eps, step size lr / bc1 (same value, different rounding order)
+  const float* clip_scale;  // optional device scalar multiplied into every gradient
+  __device__ bool skip() const { return false; }
+  __device__ Ctx begin(int) const { return Ctx{}; }
+  template <int D, int V>
+  __device__ __forceinline__ void apply(float (&r)[D][V], const Ctx&, float (&)[2], int) const {
+    const float gs = clip_scale ? *clip_scale : 1.f;
+#pragma unroll
+    for (int j = 0; j < V; j++) {
+      float g = r[0][j] * gs, p = r[1][j], m = r[2][j], v = r[3][j];
+      if (mode == 0) g += decay * p;
+      m = beta1 * m + (1.f - beta1) * g;
+      v = beta2 * v + (1.f - beta2) * g * g;
+      float upd;
+      if (torch_math) upd = (m / bc1) / (sqrtf(v) / sqrtf(bc2) + eps);
+      else upd = (m / bc1) / (sqrtf(v / bc2) + eps);
+      if (mode != 0) upd += decay * p;
+      p -= lr * upd;
+      r[1][j] = p; r[2][j] = m; r[3][j] = v;
+      r[4][j] = swa_a * r[4][j] + swa_b * p;
+      r[5][j] = p;
+    }
+  }
+  __device__ void end(const Ctx&, int, int, float (&)[2], float*) const {}
+};
+
 // ---------------------------------------------------------------- Adagrad: slots g,p,h
 struct AdagradOp {
   static constexpr unsigned kRead = 0b111u, kWrite = 0b110u;
@@ -195,6 +229,21 @@ AB_API int ab_mt_adam(void* arena, int n, int depth, int total_chunks, int chunk
   } else if (depth == 5) {
     if (capturable) ADAM_GO(true, true, TG, TP, float, float, float) else ADAM_GO(true, false, TG, TP, float, float, float)
   }
+  return -2;
+}
+
+// [g, p, m, v, swa, compute]: dt_g for g, dt_c for the compute copy; p / m / v / swa fp32.
+AB_API int ab_mt_adam_swa(void* arena, int n, int depth, int total_chunks, int chunk, int dt_g, int dt_c, float lr, float beta1, float beta2,
+                          float eps, int step, int mode, int torch_math, int bias_correction, float decay, float swa_a, float swa_b,
+                          const float* clip_scale, cudaStream_t st) {
+  if (depth != 6) return -2;
+  float bc1 = 1.f, bc2 = 1.f;
+  if (bias_correction) {
+    bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+  }
+  AdamSwaOp op{beta1, beta2, eps, decay, lr, bc1, bc2, swa_a, swa_b, mode, torch_math, clip_scale};
+  AB_DISPATCH_FLOAT3(dt_g, TG, AB_DISPATCH_FLOAT3(dt_c, TC, return (mt_launch<4, AdamSwaOp, TG, float, float, float, float, TC>(TB, op, st))));
   return -2;
 }
 

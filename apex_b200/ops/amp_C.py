@@ -233,6 +233,18 @@ def multi_tensor_adam_capturable(chunk_size, noop_flag, tensor_lists, lr, beta1,
 multi_tensor_adam_capturable_master = multi_tensor_adam_capturable  # 5 lists: [g, p, m, v, p_master]
 
 
+def multi_tensor_adam_swa(chunk_size, tensor_lists, lr, beta1, beta2, eps, step, mode, torch_math, bias_correction, weight_decay, swa_a, swa_b,
+                          clip_scale=None):
+    """[g, p, m, v, swa, compute]: Adam on the fp32 parameters, swa = swa_a * swa + swa_b * p and the low-precision compute copy, one
+    persistent launch (csrc/mt_optim.cu AdamSwaOp). ``clip_scale``: optional 1-element device tensor multiplied into the gradients."""
+    if _empty(tensor_lists):
+        return
+    tb = _table(tensor_lists, chunk_size)
+    d = tb.dtypes
+    _lib.fn("ab_mt_adam_swa")(*tb.head(), d[0], d[5], float(lr), float(beta1), float(beta2), float(eps), int(step), int(mode), int(torch_math),
+                              int(bias_correction), float(weight_decay), float(swa_a), float(swa_b), _lib.ptr(clip_scale), _s(tb))
+
+
 def multi_tensor_adagrad(chunk_size, noop_flag, tensor_lists, lr, eps, mode, weight_decay):
     if _empty(tensor_lists):
         return

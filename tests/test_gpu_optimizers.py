@@ -145,3 +145,41 @@ def test_mixed_precision_lamb(cuda_dev):
     for p in pa:
         p.grad = torch.randn_like(p)
     opt.step()
+
+
+@pytest.mark.parametrize("mode", ["PyTorchAdam", "ApexAdamW"])
+def test_fused_adam_swa_single_launch(cuda_dev, mode):
+    """openfold FusedAdamSWA: Adam + SWA average + bf16 compute copy (+ clip factor) in one multi-tensor launch vs a plain torch oracle."""
+    from apex_b200.contrib.openfold.fused_adam_swa import AdamMathType, FusedAdamSWA
+    torch.manual_seed(0)
+    shapes = [(257, 33), (4099,), (64, 64)]
+    p32 = [torch.nn.Parameter(torch.randn(s, device=cuda_dev)) for s in shapes]
+    pbf = [torch.nn.Parameter(p.detach().bfloat16()) for p in p32]
+    swa = [torch.nn.Parameter(p.detach().clone()) for p in p32]
+    ref_p = [p.detach().clone() for p in p32]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    ref_swa = [p.clone() for p in ref_p]
+    decay, lr, b1, b2, eps, wd = 0.9, 1e-2, 0.9, 0.999, 1e-8, 0.01
+    opt = FusedAdamSWA(p32, pbf, swa, decay, lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd, adam_math_mode=AdamMathType[mode])
+    for step in range(1, 5):
+        clip = 0.5 if step == 3 else None
+        for c in pbf:
+            c.grad = torch.randn_like(c)
+        grads = [c.grad.float() * (clip or 1.0) for c in pbf]
+        opt.step(grad_clip_scale=clip)
+        for i, g in enumerate(grads):
+            p = ref_p[i]
+            if mode == "PyTorchAdam":
+                g = g + wd * p
+            ref_m[i] = b1 * ref_m[i] + (1 - b1) * g
+            ref_v[i] = b2 * ref_v[i] + (1 - b2) * g * g
+            upd = (ref_m[i] / (1 - b1 ** step)) / ((ref_v[i] / (1 - b2 ** step)).sqrt() + eps)
+            if mode == "ApexAdamW":
+                upd = upd + wd * p
+            ref_p[i] = p - lr * upd
+            ref_swa[i] = ref_p[i].clone() if step == 1 else decay * ref_swa[i] + (1 - decay) * ref_p[i]
+        for i in range(len(shapes)):
+            torch.testing.assert_close(p32[i].detach(), ref_p[i], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(swa[i].detach(), ref_swa[i], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(pbf[i].detach().float(), ref_p[i].bfloat16().float(), rtol=0, atol=0)
