@@ -15,6 +15,7 @@ from ... import _lib
 _lib.declare("ab_group_norm", "i p p p p p i p p p p p l p i i i i i f i i p")
 
 _lib.declare("ab_group_norm_small", "i p p p p p i p p p p p p i i i i f i i p")
+_lib.declare("ab_group_norm_stream", "i p p p p p i p p p p p i i i i f i i p")
 
 _MAX_N = 8192  # per-image arrival counters / ready flags live in a fixed control buffer
 
@@ -62,8 +63,26 @@ def _small_ok(is_bwd, HW, C, G, dtype):
     return r
 
 
+def _stream_min_bytes(is_bwd: bool) -> int:
+    """Activation size from which the two-pass streaming kernels (csrc/group_norm_stream.cu) replace the slab-per-group kernels: measured
+    cross-over on B200 (benchmarks/bench_group_norm.py), overridable with APEX_B200_GN_STREAM_MIN_MB (0 = always, large = never)."""
+    import os
+
+    v = os.environ.get("APEX_B200_GN_STREAM_MIN_MB")
+    if v is not None:
+        return int(float(v) * 1e6)
+    return int((9 if is_bwd else 14) * 1e6)
+
+
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
+    if G <= 64 and x.numel() * x.element_size() >= _stream_min_bytes(is_bwd):
+        st = _scratch(x.device, N * C * 2 + 64)
+        w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
+        _lib.fn("ab_group_norm_stream")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
+                                        rstd.data_ptr(), _lib.ptr(dg), _lib.ptr(db), st[0].data_ptr(), N, H * W, C, G, float(eps), int(silu),
+                                        _lib.dt(x), _lib.stream_ptr(x.device))
+        return
     if _small_ok(is_bwd, H * W, C, G, x.dtype):
         st = _scratch(x.device, N * C * 2 + 64)
         w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)

@@ -34,3 +34,14 @@ def test_group_norm(cuda_dev, N, C, H, W, G, dtype, act):
     sc = (N * H * W) ** 0.5
     torch.testing.assert_close(gn.weight.grad.float(), wr.grad, atol=bt * sc, rtol=bt)
     torch.testing.assert_close(gn.bias.grad.float(), br.grad, atol=bt * sc, rtol=bt)
+
+
+@pytest.mark.parametrize("N,C,H,W,G", [(2, 320, 64, 64, 32), (1, 640, 16, 16, 16), (3, 96, 7, 5, 8), (2, 2560, 16, 16, 32), (1, 42 * 4, 9, 9, 4),
+                                       (2, 960, 64, 64, 16)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("act", ["", "silu"])
+def test_group_norm_streaming_path(cuda_dev, N, C, H, W, G, dtype, act, monkeypatch):
+    """csrc/group_norm_stream.cu (two streaming passes per direction; the default for large activations) forced on every shape:
+    channel vectors that straddle groups (C / G = 60, 42), odd spatial sizes, the scalar fallback (C % 8 != 0 handled by V = 1)."""
+    monkeypatch.setenv("APEX_B200_GN_STREAM_MIN_MB", "0")
+    test_group_norm(cuda_dev, N, C, H, W, G, dtype, act)
