@@ -144,11 +144,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a_format [7,10), b_format [10,13),
 // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
 // `is_bf16` doubles as the operand format code: kind::f16 0 = F16, 1 = BF16; kind::f8f6f4 0 = E4M3, 1 = E5M2.
-__host__ __device__ inline uint32_t make_idesc(int is_bf16, int a_mn, int b_mn, int m, int n) {
+// Bit 0 of the code is A's format, bit 1 set means "B's format differs from A's" (fp8 backward: E5M2 gradients x E4M3 weights / activations).
+__host__ __device__ inline uint32_t make_idesc(int fmt, int a_mn, int b_mn, int m, int n) {
   uint32_t d = 0;
+  const uint32_t fa = (uint32_t)(fmt & 1), fb = ((fmt >> 1) & 1) ? (fa ^ 1u) : fa;
   d |= 1u << 4;
-  d |= (uint32_t)(is_bf16 ? 1 : 0) << 7;
-  d |= (uint32_t)(is_bf16 ? 1 : 0) << 10;
+  d |= fa << 7;
+  d |= fb << 10;
   d |= (uint32_t)(a_mn ? 1 : 0) << 15;
   d |= (uint32_t)(b_mn ? 1 : 0) << 16;
   d |= (uint32_t)(n >> 3) << 17;

@@ -502,17 +502,18 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   return -1;
 }
 
-// D[M,N] (dt_out) = alpha * A B^T with A [M,K], B [N,K] row-major 8-bit floats (dt_in: kE4M3 or kE5M2, both operands the same type),
+// D[M,N] (dt_out) = alpha * A B^T with A [M,K] (dt_in), B [N,K] (dt_b) row-major 8-bit floats (kE4M3 / kE5M2, may differ),
 // fp32 accumulation in TMEM (tcgen05.mma.kind::f8f6f4, cta_group::2). K, lda, ldb must be multiples of 16 (TMA 16-byte rule).
 // scale_a / scale_b: optional device floats multiplied into alpha in the epilogue (per-tensor dequantisation scales).
 AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd, int dt_in,
-                       int dt_out, int epi, const void* bias, void* aux, long long ldaux, float alpha, const float* scale_a, const float* scale_b,
+                       int dt_b, int dt_out, int epi, const void* bias, void* aux, long long ldaux, float alpha, const float* scale_a, const float* scale_b,
                        int sms, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (dt_in != kE4M3 && dt_in != kE5M2) return -10;
+  if (dt_b != kE4M3 && dt_b != kE5M2) return -10;
   if ((K % 16) || (lda % 16) || (ldb % 16) || !aligned16(A) || !aligned16(B)) return -10;
   if (epi == EPI_ACCUM) return -10;
-  const int fmt = dt_in == kE5M2 ? 1 : 0;
+  const int fmt = (dt_in == kE5M2 ? 1 : 0) | (dt_b != dt_in ? 2 : 0);   // bit 0: A is E5M2; bit 1: B has the other 8-bit format
   CUtensorMap ma, mb;
   int rc = make_map(&ma, A, fmt, M, K, lda, 2 * BK, BM, 1);
   if (rc) return rc;

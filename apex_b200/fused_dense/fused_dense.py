@@ -100,25 +100,44 @@ def fused_dense_gelu_dense_function(input, weight1, bias1, weight2, bias2):
 
 
 class FusedDenseFP8Func(torch.autograd.Function):
-    """Linear with an fp8 (E4M3, per-tensor dynamic scales) forward GEMM on the tcgen05 kind::f8f6f4 path; dgrad / wgrad stay 16-bit
-    (BASELINE.md row 3 'bf16 / fp8 FFN block' -- the reference has no fp8 path at all)."""
+    """Linear with fp8 GEMMs on the tcgen05 kind::f8f6f4 path (per-tensor dynamic scales). Forward: E4M3 x E4M3. ``fp8_backward=True``
+    also runs dgrad and wgrad in fp8 (E5M2 gradient x E4M3 weight / activation): the activation is saved as its TRANSPOSED fp8 copy (half the
+    bytes of the 16-bit tensor) produced by the same pass that quantises it for the forward. Default: 16-bit dgrad / wgrad.
+    (BASELINE.md row 3 'bf16 / fp8 FFN block' -- the reference has no fp8 path at all.)"""
 
     @staticmethod
-    def forward(ctx, input, weight, bias):
+    def forward(ctx, input, weight, bias, fp8_backward=False):
         x = _2d(input)
-        ctx.save_for_backward(x, weight)
         ctx.in_shape, ctx.has_bias = input.shape, bias is not None
+        ctx.fp8_bwd = bool(fp8_backward) and x.is_cuda and x.shape[0] % 16 == 0 and x.shape[1] % 16 == 0 and weight.shape[0] % 16 == 0
+        if ctx.fp8_bwd:
+            x8, xt8, sx = G.quantize_fp8_dual(x)
+            w8, sw = G._quantize_weight_cached(weight.contiguous())
+            y = G.gemm_fp8(x8, w8, 1.0, scale_a=sx, scale_b=sw, out_dtype=x.dtype, epi=G.EPI_BIAS if bias is not None else G.EPI_NONE, bias=bias)
+            if y is not None:
+                ctx.save_for_backward(xt8, sx, weight)
+                return y.view(*input.shape[:-1], weight.shape[0])
+            ctx.fp8_bwd = False
+        ctx.save_for_backward(x, weight)
         y = G.linear_fwd_fp8(x, weight.contiguous(), bias)
         return y.view(*input.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, grad_output):
-        x, weight = ctx.saved_tensors
         dy = _2d(grad_output)
+        if ctx.fp8_bwd:
+            xt8, sx, weight = ctx.saved_tensors
+            r = G.linear_bwd_fp8(dy.contiguous(), weight.contiguous(), xt8, sx, need_dx=ctx.needs_input_grad[0])
+            if r is None:
+                raise RuntimeError("fp8 backward: shapes must be multiples of 16 (checked in forward)")
+            dx, dw = r
+            db = G.colsum(dy) if ctx.has_bias else None
+            return (dx.view(ctx.in_shape) if dx is not None else None), dw, db, None
+        x, weight = ctx.saved_tensors
         dx = G.linear_dgrad(dy, weight.contiguous()) if ctx.needs_input_grad[0] else None
         dw = G.linear_wgrad(dy, x)
         db = G.colsum(dy) if ctx.has_bias else None
-        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db, None
 
 
 class FusedDenseGeluDenseFP8Func(FusedDenseGeluDenseFunc):
@@ -142,10 +161,10 @@ def fused_dense_gelu_dense_fp8_function(input, weight1, bias1, weight2, bias2):
         return FusedDenseGeluDenseFP8Func.apply(*args)
 
 
-def fused_dense_fp8_function(input, weight, bias=None):
+def fused_dense_fp8_function(input, weight, bias=None, fp8_backward=False):
     args = _cast_if_autocast_enabled(input, weight, bias)
     with torch.amp.autocast("cuda", enabled=False):
-        return FusedDenseFP8Func.apply(*args)
+        return FusedDenseFP8Func.apply(*args, fp8_backward)
 
 
 class FusedDense(nn.Module):

@@ -13,7 +13,8 @@ from ..parallel import param_sync as _param_sync
 
 _lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l p p i i l l i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
-_lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i p p l f p p i p")
+_lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i i p p l f p p i p")
+_lib.declare("ab_fp8_quantize_dual", "p p p i i p p i i p")
 _lib.declare("ab_fp8_quantize", "p p l p p i i p")
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_DGELU, EPI_ACCUM, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_RELU, EPI_SIGMOID = range(9)
@@ -173,10 +174,10 @@ def quantize_fp8(x: torch.Tensor, dtype=None):
 def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, scale_a: torch.Tensor | None = None,
              scale_b: torch.Tensor | None = None, out_dtype=torch.bfloat16, epi: int = EPI_NONE, bias: torch.Tensor | None = None,
              aux: torch.Tensor | None = None, out: torch.Tensor | None = None):
-    """D [M, N] = alpha * scale_a * scale_b * a8 [M, K] @ b8 [N, K]^T for 8-bit float operands (both K-major, same format);
+    """D [M, N] = alpha * scale_a * scale_b * a8 [M, K] @ b8 [N, K]^T for 8-bit float operands (both K-major; E4M3 / E5M2 may be mixed);
     ``scale_a`` / ``scale_b`` are optional 1-element fp32 DEVICE tensors (the dequantisation scales of :func:`quantize_fp8`).
     Returns None when the native kernel cannot take the problem (K or a leading dimension not a multiple of 16, CPU tensors)."""
-    if not (a8.is_cuda and _lib.available() and a8.dtype in _F8 and a8.dtype == b8.dtype and a8.dim() == 2 and b8.dim() == 2
+    if not (a8.is_cuda and _lib.available() and a8.dtype in _F8 and b8.dtype in _F8 and a8.dim() == 2 and b8.dim() == 2
             and a8.stride(1) == 1 and b8.stride(1) == 1):
         return None
     M, K = a8.shape
@@ -189,13 +190,73 @@ def gemm_fp8(a8: torch.Tensor, b8: torch.Tensor, alpha: float = 1.0, *, scale_a:
     if bias is not None and bias.dtype != out.dtype:
         bias = bias.to(out.dtype)
     _lib.fn("ab_gemm_fp8")(a8.data_ptr(), b8.data_ptr(), out.data_ptr(), M, N, K, a8.stride(0), b8.stride(0), out.stride(0), _lib.dt(a8),
-                           _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, float(alpha),
+                           _lib.dt(b8), _lib.dt(out), int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, float(alpha),
                            _lib.ptr(scale_a), _lib.ptr(scale_b), 0, _lib.stream_ptr(a8.device))
     stats["native"] += 1
     return out
 
 
+def quantize_fp8_dual(x: torch.Tensor, dtype=None, want_q: bool = True, want_t: bool = True):
+    """One read of a 2-D tensor -> (q [R, C] or None, qt [C, R] or None, inv_scale): the fp8 copy and / or its TRANSPOSE with one shared
+    per-tensor scale (csrc/fp8_quant.cu quant_dual_kernel). The transposed copies are what the fp8 backward GEMMs consume: 8-bit tcgen05
+    operands are K-major only, dgrad reduces over the output features and wgrad over the tokens."""
+    dtype = dtype or torch.float8_e4m3fn
+    R, C = x.shape
+    if x.is_cuda and _lib.available() and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        xc = x.detach().contiguous()
+        q = torch.empty(R, C, dtype=dtype, device=x.device) if want_q else None
+        qt = torch.empty(C, R, dtype=dtype, device=x.device) if want_t else None
+        inv = torch.empty(1, dtype=torch.float32, device=x.device)
+        scr = _q_scratch.get(x.device)
+        if scr is None:
+            scr = _q_scratch[x.device] = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.fn("ab_fp8_quantize_dual")(xc.data_ptr(), _lib.ptr(q), _lib.ptr(qt), R, C, scr.data_ptr(), inv.data_ptr(), _lib.dt(xc),
+                                        _lib.dt(dtype), _lib.stream_ptr(x.device))
+        return q, qt, inv
+    amax = x.detach().abs().amax().float().clamp_min(1e-12)
+    scale = torch.finfo(dtype).max / amax
+    q = (x.float() * scale).to(dtype)
+    return (q if want_q else None), (q.t().contiguous() if want_t else None), (1.0 / scale).reshape(1)
+
+
 _wq_cache: dict = {}
+_wqt_cache: dict = {}
+
+
+def _quantize_weight_t_cached(w: torch.Tensor):
+    """Transposed E4M3 copy of a weight [N, K] -> [K, N] for the fp8 dgrad, cached per (storage, version) like the forward copy."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _wqt_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1], hit[2]
+    _, wt8, sw = quantize_fp8_dual(w, want_q=False, want_t=True)
+    if len(_wqt_cache) > 256:
+        _wqt_cache.clear()
+    _wqt_cache[key] = (w._version, wt8, sw)
+    return wt8, sw
+
+
+def linear_bwd_fp8(dy: torch.Tensor, w: torch.Tensor, xt8: torch.Tensor, sx: torch.Tensor, need_dx: bool = True, out_dtype=None):
+    """fp8 backward of y = x W^T: the gradient is quantised ONCE to E5M2 (plain + transposed copy, one read), then
+    dx = dy8 [M, N] @ Wt8 [K, N]^T  and  dW = dyt8 [N, M] @ xt8 [K, M]^T on the kind::f8f6f4 GEMM (E5M2 x E4M3 operands, fp32 accumulation in
+    TMEM, per-tensor dequantisation scales applied in the epilogue). Returns (dx or None, dw) or None when the shapes do not fit
+    (every reduction / leading dimension must be a multiple of 16)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    if not (dy.is_cuda and _lib.available() and _F8 and M % 16 == 0 and N % 16 == 0 and K % 16 == 0):
+        return None
+    out_dtype = out_dtype or dy.dtype
+    dy8, dyt8, sdy = quantize_fp8_dual(dy, torch.float8_e5m2, want_q=need_dx, want_t=True)
+    dx = None
+    if need_dx:
+        wt8, sw = _quantize_weight_t_cached(w)
+        dx = gemm_fp8(dy8, wt8, 1.0, scale_a=sdy, scale_b=sw, out_dtype=out_dtype)
+        if dx is None:
+            return None
+    dw = gemm_fp8(dyt8, xt8, 1.0, scale_a=sdy, scale_b=sx, out_dtype=w.dtype)
+    if dw is None:
+        return None
+    return dx, dw
 
 
 def _quantize_weight_cached(w: torch.Tensor):

@@ -201,3 +201,46 @@ def test_dgrad_epilogue_accumulates_the_bias_gradient(cuda_dev, M, N, K):
         want = ref.sum(0)
         err = (cs.float() - want).abs().max().item()
         assert err <= 2e-2 * max(1.0, want.abs().max().item()), (use_aux, err)
+
+
+@pytest.mark.parametrize("R,C", [(256, 512), (130, 70), (64, 4096)])
+@pytest.mark.parametrize("fmt", ["e4m3", "e5m2"])
+def test_fp8_quantize_dual_matches_the_plain_kernel_and_its_transpose(cuda_dev, R, C, fmt):
+    from apex_b200.ops import gemm as G
+    dt = torch.float8_e4m3fn if fmt == "e4m3" else torch.float8_e5m2
+    torch.manual_seed(0)
+    x = (torch.randn(R, C, device=cuda_dev) * 3).bfloat16()
+    q0, s0 = G.quantize_fp8(x, dt)
+    q, qt, s = G.quantize_fp8_dual(x, dt)
+    torch.testing.assert_close(s, s0)
+    assert torch.equal(q.view(torch.uint8), q0.view(torch.uint8))
+    assert torch.equal(qt.view(torch.uint8), q0.view(torch.uint8).t().contiguous())
+
+
+def test_mixed_format_fp8_gemm_e5m2_times_e4m3(cuda_dev):
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    a = torch.randn(256, 512, device=cuda_dev).bfloat16()
+    b = torch.randn(384, 512, device=cuda_dev).bfloat16()
+    a8, sa = G.quantize_fp8(a, torch.float8_e5m2)
+    b8, sb = G.quantize_fp8(b, torch.float8_e4m3fn)
+    out = G.gemm_fp8(a8, b8, 1.0, scale_a=sa, scale_b=sb, out_dtype=torch.float32)
+    ref = (a8.float() * sa) @ (b8.float() * sb).t()
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-2)      # exact products of the dequantised operands, fp32 accumulation order aside
+
+
+def test_fused_dense_fp8_backward_close_to_bf16(cuda_dev):
+    """fp8_backward=True: dgrad (E5M2 dy x E4M3 W^T) and wgrad (E5M2 dy^T x E4M3 x^T) on the fp8 GEMM vs the 16-bit backward."""
+    from apex_b200.fused_dense import fused_dense_fp8_function, fused_dense_function
+    torch.manual_seed(0)
+    x = torch.randn(512, 1024, device=cuda_dev).bfloat16().requires_grad_()
+    w = (torch.randn(768, 1024, device=cuda_dev) * 0.03).bfloat16().requires_grad_()
+    b = torch.randn(768, device=cuda_dev).bfloat16().requires_grad_()
+    dy = torch.randn(512, 768, device=cuda_dev).bfloat16()
+    y8 = fused_dense_fp8_function(x, w, b, fp8_backward=True)
+    g8 = torch.autograd.grad(y8, (x, w, b), dy)
+    y16 = fused_dense_function(x, w, b)
+    g16 = torch.autograd.grad(y16, (x, w, b), dy)
+    for a_, r_, name in zip(g8, g16, ("dx", "dw", "db")):
+        err = (a_.float() - r_.float()).norm() / r_.float().norm()
+        assert err < (0.08 if name != "db" else 1e-2), (name, float(err))
