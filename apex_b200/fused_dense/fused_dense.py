@@ -142,23 +142,56 @@ class FusedDenseFP8Func(torch.autograd.Function):
 
 class FusedDenseGeluDenseFP8Func(FusedDenseGeluDenseFunc):
     """Dense -> GELU -> Dense with both forward GEMMs on the fp8 path (bias + GELU (+aux) and bias epilogues fused as in the 16-bit
-    version); the backward is inherited unchanged (16-bit dgrad / wgrad on the saved activations)."""
+    version). ``fp8_backward=False``: the backward is inherited (16-bit dgrad / wgrad on the saved activations). ``fp8_backward=True``: all
+    four backward GEMMs run in fp8 (E5M2 gradients x E4M3 weights / activations; dgrad-2 keeps its fused gelu' epilogue), the block input and
+    the hidden activation are saved as transposed fp8 copies made by the forward's own quantisation passes."""
 
     @staticmethod
-    def forward(ctx, input, weight1, bias1, weight2, bias2):
+    def forward(ctx, input, weight1, bias1, weight2, bias2, fp8_backward=False):
         x = _2d(input)
         gelu_in = torch.empty(x.shape[0], weight1.shape[0], dtype=x.dtype, device=x.device)
+        ctx.in_shape = input.shape
+        M, K, H, N = x.shape[0], x.shape[1], weight1.shape[0], weight2.shape[0]
+        ctx.fp8_bwd = bool(fp8_backward) and x.is_cuda and all(v % 16 == 0 for v in (M, K, H, N))
+        if ctx.fp8_bwd:
+            x8, xt8, sx = G.quantize_fp8_dual(x)
+            w18, sw1 = G._quantize_weight_cached(weight1.contiguous())
+            output1 = G.gemm_fp8(x8, w18, 1.0, scale_a=sx, scale_b=sw1, out_dtype=x.dtype, epi=G.EPI_BIAS_GELU, bias=bias1, aux=gelu_in)
+            if output1 is not None:
+                h8, ht8, sh = G.quantize_fp8_dual(output1)
+                w28, sw2 = G._quantize_weight_cached(weight2.contiguous())
+                output2 = G.gemm_fp8(h8, w28, 1.0, scale_a=sh, scale_b=sw2, out_dtype=x.dtype, epi=G.EPI_BIAS, bias=bias2)
+                if output2 is not None:
+                    ctx.save_for_backward(xt8, sx, ht8, sh, gelu_in, weight1, weight2)
+                    return output2.view(*input.shape[:-1], N)
+            ctx.fp8_bwd = False
         output1 = G.linear_fwd_fp8(x, weight1.contiguous(), bias1, epi=G.EPI_BIAS_GELU, aux=gelu_in)
         output2 = G.linear_fwd_fp8(output1, weight2.contiguous(), bias2)
         ctx.save_for_backward(x, weight1, weight2, gelu_in, output1)
-        ctx.in_shape = input.shape
         return output2.view(*input.shape[:-1], weight2.shape[0])
 
+    @staticmethod
+    def backward(ctx, grad_output):
+        if not ctx.fp8_bwd:
+            return FusedDenseGeluDenseFunc.backward(ctx, grad_output) + (None,)
+        xt8, sx, ht8, sh, gelu_in, weight1, weight2 = ctx.saved_tensors
+        dy = _2d(grad_output).contiguous()
+        db2 = G.colsum(dy)
+        dy8, dyt8, sdy = G.quantize_fp8_dual(dy, torch.float8_e5m2)
+        w2t8, sw2 = G._quantize_weight_t_cached(weight2.contiguous())
+        # dgrad 2 fused with gelu'(aux); wgrad 2 on the transposed copies
+        d_gelu_in = G.gemm_fp8(dy8, w2t8, 1.0, scale_a=sdy, scale_b=sw2, out_dtype=dy.dtype, epi=G.EPI_DGELU, aux=gelu_in)
+        dw2 = G.gemm_fp8(dyt8, ht8, 1.0, scale_a=sdy, scale_b=sh, out_dtype=weight2.dtype)
+        db1 = G.colsum(d_gelu_in)
+        r = G.linear_bwd_fp8(d_gelu_in, weight1.contiguous(), xt8, sx, need_dx=ctx.needs_input_grad[0])
+        dx, dw1 = r
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw1, db1, dw2, db2, None
 
-def fused_dense_gelu_dense_fp8_function(input, weight1, bias1, weight2, bias2):
+
+def fused_dense_gelu_dense_fp8_function(input, weight1, bias1, weight2, bias2, fp8_backward=False):
     args = _cast_if_autocast_enabled(input, weight1, bias1, weight2, bias2)
     with torch.amp.autocast("cuda", enabled=False):
-        return FusedDenseGeluDenseFP8Func.apply(*args)
+        return FusedDenseGeluDenseFP8Func.apply(*args, fp8_backward)
 
 
 def fused_dense_fp8_function(input, weight, bias=None, fp8_backward=False):

@@ -52,6 +52,8 @@ def main():
         row["fwd_bf16_ms"] = round(time_fn(lambda: blk(xin), warmup=3, iters=10)[0], 4)
     row["fwd_bwd_fp8_ms"] = round(time_fn(lambda: f8().backward(dout), warmup=3, iters=10)[0], 4)
     row["fwd_bwd_bf16_ms"] = round(time_fn(lambda: blk(xin).backward(dout), warmup=3, iters=10)[0], 4)
+    f8b = lambda: fused_dense_gelu_dense_fp8_function(xin, blk.weight1, blk.bias1, blk.weight2, blk.bias2, True)  # noqa: E731  fp8 dgrad / wgrad too
+    row["fwd_bwd_all_fp8_ms"] = round(time_fn(lambda: f8b().backward(dout), warmup=3, iters=10)[0], 4)
     y8, y16 = f8().float(), blk(xin).float()
     row["fp8_vs_bf16_rel_err"] = float((y8 - y16).norm() / y16.norm())
     out.append(row)

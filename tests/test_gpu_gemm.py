@@ -244,3 +244,22 @@ def test_fused_dense_fp8_backward_close_to_bf16(cuda_dev):
     for a_, r_, name in zip(g8, g16, ("dx", "dw", "db")):
         err = (a_.float() - r_.float()).norm() / r_.float().norm()
         assert err < (0.08 if name != "db" else 1e-2), (name, float(err))
+
+
+def test_ffn_block_fp8_backward_close_to_bf16(cuda_dev):
+    from apex_b200.fused_dense import fused_dense_gelu_dense_fp8_function, fused_dense_gelu_dense_function
+    torch.manual_seed(0)
+    x = torch.randn(256, 512, device=cuda_dev).bfloat16().requires_grad_()
+    w1 = (torch.randn(1024, 512, device=cuda_dev) * 0.04).bfloat16().requires_grad_()
+    b1 = (torch.randn(1024, device=cuda_dev) * 0.1).bfloat16().requires_grad_()
+    w2 = (torch.randn(512, 1024, device=cuda_dev) * 0.03).bfloat16().requires_grad_()
+    b2 = (torch.randn(512, device=cuda_dev) * 0.1).bfloat16().requires_grad_()
+    dy = torch.randn(256, 512, device=cuda_dev).bfloat16()
+    y8 = fused_dense_gelu_dense_fp8_function(x, w1, b1, w2, b2, fp8_backward=True)
+    g8 = torch.autograd.grad(y8, (x, w1, b1, w2, b2), dy)
+    y16 = fused_dense_gelu_dense_function(x, w1, b1, w2, b2)
+    g16 = torch.autograd.grad(y16, (x, w1, b1, w2, b2), dy)
+    assert (y8.float() - y16.float()).norm() / y16.float().norm() < 0.08
+    for a_, r_, name in zip(g8, g16, ("dx", "dw1", "db1", "dw2", "db2")):
+        err = (a_.float() - r_.float()).norm() / r_.float().norm()
+        assert err < 0.12, (name, float(err))
