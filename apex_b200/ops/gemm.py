@@ -23,6 +23,20 @@ _ws: dict = {}
 stats = {"native": 0, "fallback": 0, "guarded": 0}
 
 
+_warned: set = set()
+
+
+def _note_fallback(why: str) -> None:
+    """The tcgen05 kernel takes bf16 / fp16 operands with 8-element-aligned extents; everything else is a plain library GEMM (cuBLAS via
+    torch), as the module docstring says. Counted in ``stats`` and reported once per reason so that it is never silent."""
+    stats["fallback"] += 1
+    if why not in _warned:
+        _warned.add(why)
+        import warnings
+
+        warnings.warn(f"apex_b200.ops.gemm: library (cuBLAS) GEMM used instead of the tcgen05 kernel: {why}", stacklevel=3)
+
+
 def _native_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
     return (a.is_cuda and a.dtype in (torch.bfloat16, torch.float16) and a.dtype == b.dtype and _lib.available()
             and a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1)
@@ -38,6 +52,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if _param_sync._regions:   # the caller's library fallback reads the operands as a whole
             _param_sync.wait(a)
             _param_sync.wait(b)
+        if a.is_cuda:
+            _note_fallback(f"{a.dtype} operands" if a.dtype not in (torch.bfloat16, torch.float16) else "non-unit inner stride / mixed dtypes")
         return None
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
@@ -75,7 +91,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         else:
             raise
     if not rc_ok:
-        stats["fallback"] += 1
+        _note_fallback(f"extents / leading dimensions not multiples of 8 (M={M}, N={N}, K={K})")
         return None
     stats["native"] += 1
     return out
