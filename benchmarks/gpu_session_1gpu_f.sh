@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_group_norm.py tests/test_gpu_optimizers.py tests/test_gpu_contrib.py tests/test_gpu_gemm.py -m gpu -q -x 2>&1 | tail -6 | cut -c1-300
+echo "== fp8 FFN"; timeout 300 python benchmarks/bench_gemm_fp8.py 2>&1 | tail -1 | cut -c1-600
 for MB in 0 100000; do
   echo "== group norm bench, stream threshold $MB MB"
   APEX_B200_GN_STREAM_MIN_MB=$MB timeout 600 python benchmarks/bench_group_norm.py 2>&1 | grep "^{" > gpurun_out/bench_group_norm_thr$MB.json
