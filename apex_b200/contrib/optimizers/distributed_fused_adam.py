@@ -30,7 +30,7 @@ from ... import _lib
 from ...ops import amp_C
 from ...ops import reference as ref
 
-_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p p p i i p i i i i p")
+_lib.declare("ab_dist_adam_step", "i i p p p l l p p p p p l i i i i i i i p i i i p p p p f f f f f i i i f p p p p p i i p i i i i p")
 _lib.declare("ab_symm_gate", "p i i p i p")
 
 _CHUNK = 2048  # elements handled by one CTA work item in csrc/dist_adam.cu
@@ -386,7 +386,9 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         pairs = {(torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16), (torch.float32, torch.float32),
                  (torch.bfloat16, torch.float32), (torch.float16, torch.float32), (torch.float32, torch.bfloat16),
                  (torch.float32, torch.float16)}
-        return (self.fused_collectives and not self.with_scaled_states and dtype == torch.float32 and self.store_params and grad_dtype in f and param_dtype in f
+        # fp32 master weights, or (store_param_remainders) bf16 parameters + int16 remainders reassembled inside the kernel
+        master_ok = self.store_params or (self.store_param_remainders and param_dtype == torch.bfloat16)
+        return (self.fused_collectives and not self.with_scaled_states and dtype == torch.float32 and master_ok and grad_dtype in f and param_dtype in f
                 and (grad_dtype, param_dtype) in pairs)
 
     def init_params(self, params: Optional[Iterable[torch.nn.Parameter]] = None, dtype: Optional[torch.dtype] = None,
@@ -639,7 +641,7 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         self.kernel_launches += 1
         _lib.fn("ab_dist_adam_step")(
             mode, nvls, ctypes.addressof(g_arr), ctypes.addressof(p_arr), ctypes.addressof(pads), mcg, mcp,
-            _lib.ptr(seg.master), seg.exp_avg.data_ptr(), seg.exp_avg_sq.data_ptr(), _lib.ptr(seg.reduced), seg.bucket_elems,
+            _lib.ptr(seg.master), _lib.ptr(seg.remainders), seg.exp_avg.data_ptr(), seg.exp_avg_sq.data_ptr(), _lib.ptr(seg.reduced), seg.bucket_elems,
             seg.shard_elems, b0, b1, seg.rank, rank, world, epoch, epoch_ctr, 2 * lane, 2 * lane + 1, (seg.group_idx % 32) + 32 * lane,
             done_ctr.data_ptr(), seg.norm_partials[512 * lane:].data_ptr(), seg.norm_out[b0].data_ptr(), self._grad_scale.data_ptr(), self._pre_scale(),
             0.0 if cap else float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), 0 if cap else int(step),

@@ -33,6 +33,8 @@ struct DistArgs {
   const void* mc_grads;  // multicast alias of the gradient buffers (NVLS) or null
   void* mc_params;       // multicast alias of the parameter buffers or null
   float* p; float* m; float* v;  // local fp32 shards
+  short* rem;                    // store_param_remainders: p == null, the fp32 master is (this rank's bf16 parameter << 16) + signed int16
+                                 // remainder (reference multi_tensor_distopt_adam_kernel.cu:319-429); halves the master-weight traffic
   float* reduced;                // local fp32 reduced-gradient shard (MODE_RS out / MODE_ADAM in)
   long long bucket_elems;
   int shard_elems, bucket_begin, bucket_end;
@@ -226,16 +228,43 @@ __global__ void __launch_bounds__(kDThreads, MB) dist_step_kernel(const __grid_c
           st8(a.reduced + local[u], g);
         } else {
           float p[8];
-          if (CS) ld8_cs(a.p + local[u], p); else ld8(a.p + local[u], p);
+          bool use_rem = false;
+          if constexpr (sizeof(TP) == 2) use_rem = a.rem != nullptr;
+          if (use_rem) {   // fp32 master = bf16 parameter bits (this rank's copy of its own shard) : int16 remainder
+            const uint4 hraw = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a.params.p[rank]) + flat[u] * 2);
+            const uint4 lraw = *reinterpret_cast<const uint4*>(a.rem + local[u]);
+            const unsigned short* hh = reinterpret_cast<const unsigned short*>(&hraw);
+            const short* ll = reinterpret_cast<const short*>(&lraw);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              int hi = (int)(short)hh[i];
+              const int lo = (int)ll[i];
+              if (lo < 0) hi -= 1;   // undo the round-to-nearest carry of the split
+              p[i] = __uint_as_float(((unsigned)(hi & 0xffff) << 16) | (unsigned)(lo & 0xffff));
+            }
+          } else if (CS) ld8_cs(a.p + local[u], p); else ld8(a.p + local[u], p);
           if (kUpdates) {
             float m[8], v[8];
             if (CS) { ld8_cs(a.m + local[u], m); ld8_cs(a.v + local[u], v); } else { ld8(a.m + local[u], m); ld8(a.v + local[u], v); }
             adam8(p, m, v, g, h);
-            if (CS) { st8_cs(a.p + local[u], p); st8_cs(a.m + local[u], m); st8_cs(a.v + local[u], v); }
-            else { st8(a.p + local[u], p); st8(a.m + local[u], m); st8(a.v + local[u], v); }
+            if (!use_rem) { if (CS) st8_cs(a.p + local[u], p); else st8(a.p + local[u], p); }
+            if (CS) { st8_cs(a.m + local[u], m); st8_cs(a.v + local[u], v); } else { st8(a.m + local[u], m); st8(a.v + local[u], v); }
           }
           uint4 out[PV];
-          {
+          if (use_rem) {   // split the updated master: signed low half stays local, the (carry-adjusted) high half IS the bf16 parameter
+            uint4 lo8;
+            short* lo = reinterpret_cast<short*>(&lo8);
+            unsigned short* e = reinterpret_cast<unsigned short*>(out);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const unsigned uu = __float_as_uint(p[i]);
+              const int nlo = (int)(short)(uu & 0xffffu);
+              int nhi = (int)(short)(uu >> 16);
+              if (nlo < 0) nhi += 1;
+              lo[i] = (short)nlo; e[i] = (unsigned short)nhi;
+            }
+            if (kUpdates) *reinterpret_cast<uint4*>(a.rem + local[u]) = lo8;
+          } else {
             TP* e = reinterpret_cast<TP*>(out);
 #pragma unroll
             for (int i = 0; i < 8; i++) e[i] = from_f<TP>(p[i]);
@@ -368,7 +397,7 @@ using namespace ab;
 
 // grads/params/pads: arrays of `world` pointers (this process's mappings of every rank's buffers).
 AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const uint64_t* params, const uint64_t* pads,
-                             uint64_t mc_grads, uint64_t mc_params, float* p, float* m, float* v, float* reduced,
+                             uint64_t mc_grads, uint64_t mc_params, float* p, short* rem, float* m, float* v, float* reduced,
                              long long bucket_elems, int shard_elems, int bucket_begin, int bucket_end, int lay_rank, int rank, int world,
                              unsigned int epoch, unsigned int* epoch_ctr, int chan_start, int chan_end, int norm_slot, unsigned int* done_ctr,
                              float* norm_partials, float* norm_out, const float* grad_scale, float pre_scale, float lr, float beta1,
@@ -388,7 +417,8 @@ AB_API int ab_dist_adam_step(int mode, int nvls, const uint64_t* grads, const ui
   a.bucket_ctr = ready ? bucket_ctr : nullptr; a.ready_epoch = ready_epoch; a.skip_start = skip_start;
   a.src_tab = (world == 1 && src_n > 0) ? src_tab : nullptr; a.src_n = src_n;
   a.mc_grads = (const void*)mc_grads; a.mc_params = (void*)mc_params;
-  a.p = p; a.m = m; a.v = v; a.reduced = reduced;
+  a.p = p; a.rem = (p == nullptr && dt_p == kBF16) ? rem : nullptr; a.m = m; a.v = v; a.reduced = reduced;
+  if (p == nullptr && a.rem == nullptr) return -5;
   a.bucket_elems = bucket_elems; a.shard_elems = shard_elems; a.bucket_begin = bucket_begin; a.bucket_end = bucket_end;
   a.sig.rank = rank; a.sig.world = world; a.sig.epoch = epoch; a.epoch_ctr = world > 1 ? epoch_ctr : nullptr; a.lay_rank = lay_rank;
   a.chan_start = chan_start; a.chan_end = chan_end; a.norm_slot = norm_slot;
