@@ -16,6 +16,7 @@ namespace ab {
 
 constexpr int kGsT = 256;
 constexpr int kGsMaxG = 64;
+constexpr int kGsU = 4;      // rows in flight per thread
 
 struct GnsArgs {
   const void* x; const void* dy; void* out;
@@ -70,21 +71,31 @@ __global__ void __launch_bounds__(kGsT) gns_stats(const __grid_constant__ GnsArg
       }
     }
     if (on) {
-      for (int r = blockIdx.x * rpc + tr; r < a.HW; r += gridDim.x * rpc) {
-        const size_t off = (size_t)r * a.C + c0;
-        float xv[V];
-        gs_load<T, V>(xv, x + off);
-        if (!BWD) {
+      const int step = gridDim.x * rpc;
+      for (int r0 = blockIdx.x * rpc + tr; r0 < a.HW; r0 += kGsU * step) {
+        float xv[kGsU][V], g[kGsU][V];
 #pragma unroll
-          for (int j = 0; j < V; j++) { s1[j] += xv[j]; s2[j] = fmaf(xv[j], xv[j], s2[j]); }
-        } else {
-          float g[V];
-          gs_load<T, V>(g, dy + off);
+        for (int u = 0; u < kGsU; u++) {   // kGsU independent rows in flight per thread
+          const int r = r0 + u * step;
+          if (r < a.HW) {
+            const size_t off = (size_t)r * a.C + c0;
+            gs_load<T, V>(xv[u], x + off);
+            if (BWD) gs_load<T, V>(g[u], dy + off);
+          }
+        }
 #pragma unroll
-          for (int j = 0; j < V; j++) {
-            float gj = g[j];
-            if (SILU) { const float z = fmaf(xv[j], A[j], B[j]), sg = sigmoid_f(z); gj *= sg * (1.f + z * (1.f - sg)); }
-            s1[j] += gj; s2[j] = fmaf(gj, xv[j], s2[j]);
+        for (int u = 0; u < kGsU; u++) {
+          if (r0 + u * step >= a.HW) continue;
+          if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < V; j++) { s1[j] += xv[u][j]; s2[j] = fmaf(xv[u][j], xv[u][j], s2[j]); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+              float gj = g[u][j];
+              if (SILU) { const float z = fmaf(xv[u][j], A[j], B[j]), sg = sigmoid_f(z); gj *= sg * (1.f + z * (1.f - sg)); }
+              s1[j] += gj; s2[j] = fmaf(gj, xv[u][j], s2[j]);
+            }
           }
         }
       }
@@ -142,17 +153,22 @@ __global__ void __launch_bounds__(kGsT) gns_fwd_apply(const __grid_constant__ Gn
       const float ga = a.gamma ? ldw<T>(a.gamma, c0 + j, a.w_fp32) : 1.f, be = a.beta ? ldw<T>(a.beta, c0 + j, a.w_fp32) : 0.f;
       A[j] = s_rstd[g] * ga; B[j] = be - s_mean[g] * A[j];
     }
-    for (int r = blockIdx.x * rpc + tr; r < a.HW; r += gridDim.x * rpc) {
-      const size_t off = (size_t)r * a.C + c0;
-      float v[V];
-      gs_load<T, V>(v, x + off);
+    const int step = gridDim.x * rpc;
+    for (int r0 = blockIdx.x * rpc + tr; r0 < a.HW; r0 += kGsU * step) {
+      float v[kGsU][V];
 #pragma unroll
-      for (int j = 0; j < V; j++) {
-        float z = fmaf(v[j], A[j], B[j]);
-        if (SILU) z *= sigmoid_f(z);
-        v[j] = z;
+      for (int u = 0; u < kGsU; u++) if (r0 + u * step < a.HW) gs_load<T, V>(v[u], x + (size_t)(r0 + u * step) * a.C + c0);
+#pragma unroll
+      for (int u = 0; u < kGsU; u++) {
+        if (r0 + u * step >= a.HW) continue;
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          float z = fmaf(v[u][j], A[j], B[j]);
+          if (SILU) z *= sigmoid_f(z);
+          v[u][j] = z;
+        }
+        gs_store<T, V>(y + (size_t)(r0 + u * step) * a.C + c0, v[u]);
       }
-      gs_store<T, V>(y + off, v);
     }
   }
 }
@@ -213,18 +229,28 @@ __global__ void __launch_bounds__(kGsT) gns_bwd_apply(const __grid_constant__ Gn
       P[j] = s_rstd[g] * ga; Q[j] = s_q[g]; R[j] = s_r[g];
       A[j] = P[j]; B[j] = be - s_mean[g] * P[j];
     }
-    for (int r = blockIdx.x * rpc + tr; r < a.HW; r += gridDim.x * rpc) {
-      const size_t off = (size_t)r * a.C + c0;
-      float xv[V], g[V];
-      gs_load<T, V>(xv, x + off);
-      gs_load<T, V>(g, dy + off);
+    const int step = gridDim.x * rpc;
+    for (int r0 = blockIdx.x * rpc + tr; r0 < a.HW; r0 += 2 * step) {
+      float xv[2][V], g[2][V];
 #pragma unroll
-      for (int j = 0; j < V; j++) {
-        float gj = g[j];
-        if (SILU) { const float z = fmaf(xv[j], A[j], B[j]), sg = sigmoid_f(z); gj *= sg * (1.f + z * (1.f - sg)); }
-        g[j] = fmaf(gj, P[j], fmaf(xv[j], Q[j], R[j]));
+      for (int u = 0; u < 2; u++) {
+        if (r0 + u * step < a.HW) {
+          const size_t off = (size_t)(r0 + u * step) * a.C + c0;
+          gs_load<T, V>(xv[u], x + off);
+          gs_load<T, V>(g[u], dy + off);
+        }
       }
-      gs_store<T, V>(dx + off, g);
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (r0 + u * step >= a.HW) continue;
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+          float gj = g[u][j];
+          if (SILU) { const float z = fmaf(xv[u][j], A[j], B[j]), sg = sigmoid_f(z); gj *= sg * (1.f + z * (1.f - sg)); }
+          g[u][j] = fmaf(gj, P[j], fmaf(xv[u][j], Q[j], R[j]));
+        }
+        gs_store<T, V>(dx + (size_t)(r0 + u * step) * a.C + c0, g[u]);
+      }
     }
   }
 }
@@ -232,10 +258,13 @@ __global__ void __launch_bounds__(kGsT) gns_bwd_apply(const __grid_constant__ Gn
 template <typename T, int V>
 static int gns_launch(const GnsArgs& a, int is_bwd, cudaStream_t st) {
   const int cols = gs_cols(a.C / V), rpc = kGsT / cols;
-  long long blocks = ((long long)a.HW + rpc - 1) / rpc;
-  long long cap = (long long)kNumSMs * 8 / (a.N > 0 ? a.N : 1);
+  // every CTA issues 2 * C atomics at the end of pass 1 whatever it has read: give it >= 32 row-iterations (x kGsU rows) when the image
+  // is large enough, while keeping ~4 CTAs per SM over the whole batch for bandwidth
+  long long blocks = ((long long)a.HW + (long long)rpc * 8 - 1) / ((long long)rpc * 8);
+  long long cap = (long long)kNumSMs * 4 / (a.N > 0 ? a.N : 1);
   if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   const dim3 grid((unsigned)blocks, (unsigned)a.N);
   cudaError_t e = cudaMemsetAsync(a.chan, 0, sizeof(float) * 2 * (size_t)a.N * a.C, st);
   if (e != cudaSuccess) return (int)e;
