@@ -63,20 +63,25 @@ def _small_ok(is_bwd, HW, C, G, dtype):
     return r
 
 
-def _stream_min_bytes(is_bwd: bool) -> int:
-    """Activation size from which the two-pass streaming kernels (csrc/group_norm_stream.cu) replace the slab-per-group kernels: measured
-    cross-over on B200 (benchmarks/bench_group_norm.py), overridable with APEX_B200_GN_STREAM_MIN_MB (0 = always, large = never)."""
+def _use_stream(is_bwd: bool, x, G: int) -> bool:
+    """Two-pass streaming kernels (csrc/group_norm_stream.cu) instead of the slab-per-group kernels. Measured on B200
+    (profiles/results/bench_group_norm_thr{0,100000}.json): they only win in the BACKWARD pass once an (image, group) slab exceeds
+    ~300 KB (the slab kernels then need clusters of 8 latency-bound CTAs); the forward never wins. APEX_B200_GN_STREAM_MIN_MB (total
+    activation MB; 0 = always, large = never) overrides the rule for A/B runs."""
     import os
 
+    if G > 64:
+        return False
     v = os.environ.get("APEX_B200_GN_STREAM_MIN_MB")
     if v is not None:
-        return int(float(v) * 1e6)
-    return int((40 if is_bwd else 1e6) * 1e6)   # measured (gpurun_out/bench_group_norm_thr*.json): the streaming backward wins from ~40 MB, the forward never did
+        return x.numel() * x.element_size() >= float(v) * 1e6
+    N, C, H, W = x.shape
+    return bool(is_bwd) and H * W * (C // G) * x.element_size() >= 300 * 1024
 
 
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
-    if G <= 64 and x.numel() * x.element_size() >= _stream_min_bytes(is_bwd):
+    if _use_stream(is_bwd, x, G):
         st = _scratch(x.device, N * C * 2 + 64)
         w_fp32 = int(w is not None and w.dtype == torch.float32 and x.dtype != torch.float32)
         _lib.fn("ab_group_norm_stream")(int(is_bwd), x.data_ptr(), _lib.ptr(dy), out.data_ptr(), _lib.ptr(w), _lib.ptr(b), w_fp32, mean.data_ptr(),
