@@ -215,6 +215,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         if (tid < TI) { const int ki = inner0 + tid; sw[tid] = ki < k_len ? p.key_bias[(size_t)brow * p.key_bias_stride + ki] * 1.4426950408889634f : 0.f; }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      // does this (outer tile, inner tile) pair contain ANY masked (query, key) combination?
+      const int key_lo = DKV ? ot * TO : inner0, key_hi = DKV ? ot * TO + TO - 1 : inner0 + TI - 1;
+      const int q_lo = DKV ? inner0 : ot * TO, q_hi = DKV ? inner0 + TI - 1 : ot * TO + TO - 1;
+      (void)key_lo;
+      const bool masked = key_hi >= k_len || q_hi >= q_len || (p.causal && key_hi > q_lo + diag);
       mbar_wait(&s_full[sb], sph, 220);
       mbar_wait(e_empty, eeph ^ 1, 221);  // the GEMMs of the previous tile have finished reading P' / dS' (first use: passes)
       tc_fence_after();
@@ -224,6 +229,24 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
         tmem_ld32(tmem_s + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sb * TI + c0), rs);
         tmem_ld32(tmem_dp + ((uint32_t)(qd * 32) << 16) + (uint32_t)(sb * TI + c0), rd);
         tmem_ld_wait();
+        if (!masked && !p.has_drop && !has_bias) {
+          // interior tile, no dropout: no per-element predicates or index arithmetic (they were half of the issued instructions)
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float pe8[8], ds8[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const float l2 = DKV ? st[c0 + i + e] : my_lse2, dl = DKV ? st[TI + c0 + i + e] : my_delta;
+              const float pe = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -l2));
+              pe8[e] = pe;
+              ds8[e] = pe * (__uint_as_float(rd[i + e]) - dl) * p.scale;
+            }
+            const uint32_t off = sw128_offset(row, c0 + i);
+            if (DKV) *reinterpret_cast<uint4*>(pbuf + off) = make_uint4(pack2<T>(pe8[0], pe8[1]), pack2<T>(pe8[2], pe8[3]), pack2<T>(pe8[4], pe8[5]), pack2<T>(pe8[6], pe8[7]));
+            *reinterpret_cast<uint4*>(dsbuf + off) = make_uint4(pack2<T>(ds8[0], ds8[1]), pack2<T>(ds8[2], ds8[3]), pack2<T>(ds8[4], ds8[5]), pack2<T>(ds8[6], ds8[7]));
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           T p8[8], d8[8];

@@ -17,6 +17,19 @@ __device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2: the softmax
   return y;
 }
 
+// two floats -> one packed 16-bit pair (low half = first argument), a single cvt instruction
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // byte offset of element (row r, col c) inside a [rows x 64 cols] 16-bit block in the SWIZZLE_128B K-major layout
 __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
   const int chunk = (c >> 3) ^ (r & 7);

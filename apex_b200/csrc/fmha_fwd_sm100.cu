@@ -187,20 +187,35 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       asm volatile("bar.sync 1, 256;" ::: "memory");
     };
     auto key_ok = [&](int kidx) { return kidx < k_len && (!p.causal || kidx <= qi + diag); };
+    // does key tile j contain a key that is masked for ANY row of this query tile (sequence tail, or the causal diagonal)?
+    auto tile_masked = [&](int j) { return (j + 1) * TK > k_len || (p.causal && (j + 1) * TK - 1 > qt * TQ + diag); };
     // ---- pass 1: row maximum
     for (int j = 0; j < n_kv; j++) {
       if (has_bias) stage_bias(j, j);
       const float* bj = bias_s + (j & 1) * TK;
       mbar_wait(&s_full[sb], sph, 120);
       tc_fence_after();
+      // interior tiles (every key valid for every row of this query tile) skip the per-element predicates: they were half of the
+      // instructions the softmax warps issued (ncu: ISETP 25 %, FSEL 9 %, index adds 9 %)
+      const bool masked = tile_masked(j);
 #pragma unroll 1
       for (int c0 = half * (TK / 2); c0 < (half + 1) * (TK / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
         tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains instead of one 32-deep dependent one
+        if (!masked && !has_bias) {   // raw maximum, scaled once (scale > 0)
 #pragma unroll
-        for (int i = 0; i < 32; i++)
-          if (key_ok(j * TK + c0 + i)) m = fmaxf(m, has_bias ? fmaf(__uint_as_float(r[i]), sl2, bj[c0 + i]) : __uint_as_float(r[i]) * sl2);
+          for (int i = 0; i < 32; i++) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+          m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float t = has_bias ? fmaf(__uint_as_float(r[i]), sl2, bj[c0 + i]) : __uint_as_float(r[i]) * sl2;
+            if (!masked || key_ok(j * TK + c0 + i)) m4[i & 3] = fmaxf(m4[i & 3], t);
+          }
+          m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
       }
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
@@ -223,6 +238,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const float* bj = bias_s + ((n_kv + j) & 1) * TK;
       const int pb = j & 1;
       uint8_t* pbuf = smem + S::kPOff + pb * S::kP;
+      const bool masked = tile_masked(j);
       mbar_wait(&s_full[sb], sph, 121);
       mbar_wait(&p_empty[pb], peph[pb] ^ 1, 122);  // the PV that last read this P buffer has finished (first use: passes immediately)
       tc_fence_after();
@@ -232,11 +248,19 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
         tmem_ld_wait();
         float pv[32];
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!masked && !has_bias) {
+          const float nm = -m;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float e = key_ok(j * TK + c0 + i) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, (has_bias ? bj[c0 + i] : 0.f) - m)) : 0.f;
-          pv[i] = e; l += e;
+          for (int i = 0; i < 32; i++) { const float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, nm)); pv[i] = e; l4[i & 3] += e; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float e = (!masked || key_ok(j * TK + c0 + i)) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, (has_bias ? bj[c0 + i] : 0.f) - m)) : 0.f;
+            pv[i] = e; l4[i & 3] += e;
+          }
         }
+        l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         if (p.has_drop) {                                   // the row sum keeps every element; only what feeds P V is dropped
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
@@ -247,11 +271,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          T h8[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) h8[e] = from_f<T>(pv[i + e]);
+          uint4 h8;   // one cvt.rn.{bf16x2,f16x2}.f32 per pair
+          h8.x = pack2<T>(pv[i], pv[i + 1]); h8.y = pack2<T>(pv[i + 2], pv[i + 3]);
+          h8.z = pack2<T>(pv[i + 4], pv[i + 5]); h8.w = pack2<T>(pv[i + 6], pv[i + 7]);
           const int c = c0 + i;
-          *reinterpret_cast<uint4*>(pbuf + (c >> 6) * (TQ * 128) + sw128_offset(row, c & 63)) = *reinterpret_cast<const uint4*>(h8);
+          *reinterpret_cast<uint4*>(pbuf + (c >> 6) * (TQ * 128) + sw128_offset(row, c & 63)) = h8;
         }
       }
       tc_fence_before();
