@@ -42,6 +42,9 @@ class ASP:
         cls.__model, cls.__verbosity, cls.__allow_permutation = model, verbosity, allow_permutation
         cls.__sparse_parameters = []
         cls.__permuted = False
+        from .permutation_lib import Permutation
+
+        Permutation.set_permutation_params_from_asp(None, None)
         if isinstance(mask_calculator, str):
             cls.__calculate_mask = lambda p: create_mask(p, mask_calculator).bool()
         else:
@@ -112,6 +115,7 @@ class ASP:
             # search + apply function-preserving channel permutations once, before the first masks (reference asp.py:314-345)
             from .permutation_lib import Permutation
 
+            Permutation.set_permutation_params_from_asp(cls.__model, cls.__sparse_parameters, None, cls.__verbosity)
             Permutation.permute_model(cls.__model, dump_fx_graph=cls.__save_permutation_graph,
                                       save_dumped_fx_graph=(cls.__permutation_output_dir + "/model_offline_permutation_graph.json"
                                                             if cls.__save_permutation_graph else None),

@@ -1,12 +1,23 @@
 """Function-preserving channel permutations for 2:4 sparsity. Reference: apex/contrib/sparsity/permutation_lib.py (2,068 LoC:
-torch.fx trace -> sibling / parent / child groups -> search -> permute C of consumers and K of producers, plus BN / bias).
+torch.fx trace -> per-node C/K permutation flags -> sibling / coparent groups -> search -> permute C of the children and K of the
+parents, BatchNorm / bias / module attributes in between; behaviour pinned by apex/contrib/sparsity/test/test_permutation_application.py).
 
-Same idea, compact: the model is symbolically traced; for every prunable consumer (Linear / Conv whose INPUT-channel dim gets the
-2:4 pattern) we walk back through channel-preserving nodes (activations, dropout, BatchNorm / LayerNorm-free elementwise ops) to
-the layer(s) that PRODUCE those channels. Consumers that share a producer are siblings: their weights are stacked row-wise and one
-permutation is searched for the group (csrc/perm_search.cu). The permutation is applied to the consumers' input channels, and the
-inverse bookkeeping (output channels of the producer: weight rows, bias, BatchNorm affine + running stats in between) keeps the
-network function unchanged. Anything the walk cannot prove safe (residual adds, reshapes, graph inputs) is left alone."""
+Design here: CHANNEL SPACES. The model is symbolically traced and every tensor value in the graph is assigned to a *channel space*
+(union-find): the set of values whose channel axis must be permuted together for the network function to stay the same.
+  * Linear / Conv / Embedding / MultiheadAttention.out_proj open a new space for their output (they are its PRODUCERS: weight rows,
+    bias) and are CONSUMERS of their input's space (weight columns = the dim that gets the 2:4 pattern).
+  * elementwise ops (add, mul, residual joins, activations, pooling, dropout) merge / pass through spaces; BatchNorm, InstanceNorm,
+    channel LayerNorm, depthwise convolutions and broadcast module attributes are pass-through nodes whose per-channel tensors ride
+    along with the space.
+  * flatten after a convolution keeps the space but records that every channel now covers `rep` consecutive columns of the next
+    Linear (the reference's replicate_sequence case).
+  * anything that mixes or exposes channel order (graph inputs and outputs, reshapes, matmuls, grouped convolutions, GroupNorm,
+    LocalResponseNorm, concatenation, slicing, unknown modules and functions) FREEZES the spaces it touches.
+Every unfrozen space with at least one prunable consumer is one search problem: the consumers' weights are stacked row-wise (the
+reference's sibling group), one permutation is searched (csrc/perm_search.cu), applied to every consumer's input-channel dim and to
+every producer / pass-through tensor's channel dim (the reference's coparent group + K_passthru chain). Residual networks and
+transformer blocks therefore come out as ONE space for the residual stream and one per hidden FFN / bottleneck width, instead of
+being skipped."""
 from __future__ import annotations
 
 import operator
@@ -17,16 +28,100 @@ import torch.nn.functional as F
 
 from .permutation_search import accelerated_search_for_good_permutation, sum_after_2_to_4
 
-_PASS_MODULES = (nn.ReLU, nn.ReLU6, nn.GELU, nn.SiLU, nn.Sigmoid, nn.Tanh, nn.Dropout, nn.Dropout2d, nn.Identity, nn.LeakyReLU, nn.Hardswish,
-                 nn.MaxPool2d, nn.AvgPool2d, nn.AdaptiveAvgPool2d)
-_BN_MODULES = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)
-_PASS_FUNCS = (F.relu, F.gelu, F.silu, F.dropout, torch.relu, torch.sigmoid, torch.tanh, F.leaky_relu, F.hardswish)
-_PRUNABLE = (nn.Linear, nn.Conv1d, nn.Conv2d)
+_PRUNABLE = (nn.Linear, nn.Conv1d, nn.Conv2d, nn.Conv3d)
+_CONVS = (nn.Conv1d, nn.Conv2d, nn.Conv3d)
+_CONV_T = (nn.ConvTranspose1d, nn.ConvTranspose2d, nn.ConvTranspose3d)
+_BN_MODULES = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.SyncBatchNorm, nn.InstanceNorm1d, nn.InstanceNorm2d, nn.InstanceNorm3d)
+_PASS_MODULES = (nn.ReLU, nn.ReLU6, nn.GELU, nn.SiLU, nn.Sigmoid, nn.Tanh, nn.Dropout, nn.Identity, nn.LeakyReLU, nn.Hardswish, nn.Hardsigmoid,
+                 nn.Hardtanh, nn.ELU, nn.SELU, nn.CELU, nn.Mish, nn.Softplus, nn.Softsign)
+# modules that act on the trailing (spatial) dims only: channel-preserving for N,C,spatial... values, not for channels-last ones
+_SPATIAL_MODULES = (nn.Dropout1d, nn.Dropout2d, nn.Dropout3d, nn.MaxPool1d, nn.MaxPool2d, nn.MaxPool3d, nn.AvgPool1d, nn.AvgPool2d, nn.AvgPool3d,
+                    nn.AdaptiveAvgPool1d, nn.AdaptiveAvgPool2d, nn.AdaptiveAvgPool3d, nn.AdaptiveMaxPool1d, nn.AdaptiveMaxPool2d,
+                    nn.AdaptiveMaxPool3d, nn.Upsample, nn.ZeroPad2d, nn.ReflectionPad2d, nn.ReplicationPad2d)
+_UNARY_FUNCS = {F.relu, F.relu6, F.gelu, F.silu, F.dropout, F.leaky_relu, F.hardswish, F.hardsigmoid, F.hardtanh, F.elu, F.selu, F.mish,
+                F.softplus, F.sigmoid, F.tanh, torch.relu, torch.sigmoid, torch.tanh, torch.abs, torch.neg, torch.exp, torch.sqrt, torch.rsqrt,
+                torch.square, torch.clamp, torch.clone, operator.neg}
+_SPATIAL_FUNCS = {F.max_pool2d, F.avg_pool2d, F.adaptive_avg_pool2d, F.max_pool1d, F.avg_pool1d, F.adaptive_avg_pool1d, F.interpolate}
+_BINARY_FUNCS = {operator.add, operator.iadd, operator.sub, operator.isub, operator.mul, operator.imul, operator.truediv, operator.itruediv,
+                 torch.add, torch.sub, torch.mul, torch.div, torch.maximum, torch.minimum}
+_UNARY_METHODS = {"contiguous", "clone", "detach", "float", "half", "bfloat16", "to", "type", "relu", "sigmoid", "tanh", "clamp", "abs", "neg",
+                  "exp", "sqrt", "rsqrt", "square", "pow", "cuda", "cpu", "relu_", "clamp_", "type_as", "requires_grad_"}
+_BINARY_METHODS = {"add", "add_", "sub", "sub_", "mul", "mul_", "div", "div_"}
+_NON_TENSOR_METHODS = {"size", "dim", "numel", "shape", "ndimension"}
+_FLATTEN_FUNCS = {torch.flatten}
+
+
+def _is_pool_to_1(m):
+    if isinstance(m, (nn.AdaptiveAvgPool1d, nn.AdaptiveAvgPool2d, nn.AdaptiveAvgPool3d, nn.AdaptiveMaxPool1d, nn.AdaptiveMaxPool2d, nn.AdaptiveMaxPool3d)):
+        o = m.output_size
+        return all(v == 1 for v in (o if isinstance(o, (tuple, list)) else (o,)))
+    return False
+
+
+class _Space:
+    """One channel space (union-find node). ``consumers``: (module, attr, dim, rep, prunable) -- tensors permuted along their INPUT
+    channel dim; ``riders``: (owner, attr, dim) -- producer weights / biases / norm statistics / broadcast attributes permuted along
+    their channel dim."""
+
+    __slots__ = ("parent", "frozen", "why", "consumers", "riders")
+
+    def __init__(self):
+        self.parent, self.frozen, self.why, self.consumers, self.riders = self, False, "", [], []
+
+    def find(self):
+        s = self
+        while s.parent is not s:
+            s.parent = s.parent.parent
+            s = s.parent
+        return s
+
+    def freeze(self, why):
+        r = self.find()
+        if not r.frozen:
+            r.frozen, r.why = True, why
+
+    def union(self, other):
+        a, b = self.find(), other.find()
+        if a is b:
+            return a
+        b.parent = a
+        a.consumers += b.consumers
+        a.riders += b.riders
+        if b.frozen and not a.frozen:
+            a.frozen, a.why = True, b.why
+        b.consumers, b.riders = [], []
+        return a
+
+
+class _Val:
+    """A traced tensor value: its channel space, where the channel axis is (1: N,C,spatial...; -1: last dim), the tensor rank when it is
+    known (conv outputs), whether the spatial extent is known to be 1, and how many flattened columns each channel covers."""
+
+    __slots__ = ("space", "axis", "rank", "spatial1", "rep")
+
+    def __init__(self, space, axis, rank=None, spatial1=False, rep=1):
+        self.space, self.axis, self.rank, self.spatial1, self.rep = space, axis, rank, spatial1, rep
+
+    def like(self, **kw):
+        v = _Val(self.space, self.axis, self.rank, self.spatial1, self.rep)
+        for k, x in kw.items():
+            setattr(v, k, x)
+        return v
+
+
+def _expand(perm, rep):
+    """Channel permutation -> column permutation when each channel covers `rep` consecutive columns (reference: replicate_sequence)."""
+    p = torch.as_tensor(perm).long()
+    if rep == 1:
+        return p
+    return (p.view(-1, 1) * rep + torch.arange(rep).view(1, -1)).reshape(-1)
 
 
 class Permutation:
     __verbosity = 0
     __seed = 1
+    __stats = {"C": 0, "K": 0}
+    __sparse_parameters = None
     search_options = {"strategy": "exhaustive", "stripe_group_size": 8, "escape_attempts": 100}
 
     @classmethod
@@ -41,8 +136,8 @@ class Permutation:
 
     @classmethod
     def set_tcpstore_port(cls, tcpstore_port):
-        """The reference synchronises permutations through a TCPStore on this port; here every rank runs the same seeded search, so the
-        port is only recorded."""
+        """The reference synchronises permutations through a TCPStore on this port; here rank 0's result is broadcast over the default
+        process group when one exists (sync_permutation), so the port is only recorded."""
         cls.__tcpstore_port = tcpstore_port
 
     @classmethod
@@ -53,174 +148,451 @@ class Permutation:
 
     @classmethod
     def set_permutation_params_from_asp(cls, model, sparse_parameters, all_parameters=None, verbosity=0):
-        """Hand-over of the ASP state (reference: called from ASP.init_model_for_pruning); the graph search works from the model alone."""
-        cls.__model, cls.__sparse_parameters, cls.__verbosity = model, sparse_parameters, verbosity
+        """Hand-over of the ASP state (reference: called from ASP.init_model_for_pruning). When set, only consumers whose weight ASP will
+        actually prune drive the search (the reference's one_sparse_sibling case); the others are still permuted along."""
+        cls.__model, cls.__verbosity = model, verbosity
+        cls.__sparse_parameters = [p for (_, _, _, p, *_rest) in sparse_parameters] if sparse_parameters is not None else None
+
+    @classmethod
+    def get_permutation_stats(cls):
+        """(tensors permuted along C, tensors permuted along K) by the last permute_model (reference :331)."""
+        return cls.__stats["C"], cls.__stats["K"]
 
     # ------------------------------------------------------------------------------------------------- parameter surgery
     @staticmethod
-    def apply_permutation_in_C_dim(module, perm):
-        """Permute the input channels (dim 1 of the weight) of a Linear / Conv."""
-        idx = torch.as_tensor(perm, device=module.weight.device).long()
+    def _permute_tensor(t, dim, idx):
         with torch.no_grad():
-            module.weight.copy_(module.weight.index_select(1, idx))
+            t.copy_(t.index_select(dim, idx.to(t.device)))
 
-    @staticmethod
-    def apply_permutation_in_K_dim(module, perm):
+    @classmethod
+    def apply_permutation_in_C_dim(cls, module, perm, attr="weight", dim=1, rep=1):
+        """Permute the input channels of a Linear / Conv (dim 1 of the weight; each channel covering `rep` columns after a flatten)."""
+        cls._permute_tensor(getattr(module, attr), dim, _expand(perm, rep))
+
+    @classmethod
+    def apply_permutation_in_K_dim(cls, module, perm):
         """Permute the output channels of a producer: weight rows + bias; BatchNorm: affine parameters and running statistics."""
-        with torch.no_grad():
-            for name in ("weight", "bias", "running_mean", "running_var"):
-                t = getattr(module, name, None)
-                if t is not None and t.dim() >= 1:
-                    t.copy_(t.index_select(0, torch.as_tensor(perm, device=t.device).long()))
+        idx = torch.as_tensor(perm).long()
+        for name in ("weight", "bias", "running_mean", "running_var"):
+            t = getattr(module, name, None)
+            if t is not None and t.dim() >= 1:
+                cls._permute_tensor(t, 0, idx)
 
     # ------------------------------------------------------------------------------------------------------ graph analysis
     @classmethod
-    def build_groups(cls, model):
-        """-> list of (consumers [modules], producers [modules], in-between BatchNorms [modules])."""
+    def build_spaces(cls, model):
+        """Trace `model` and return the list of root :class:`_Space` objects (frozen ones included, for reporting)."""
         import torch.fx as fx
 
         gm = fx.symbolic_trace(model)
         mods = dict(gm.named_modules())
+        vals: dict = {}
+        spaces: list = []
+        first_use: dict = {}   # id(module) -> (input space, output space): a module called twice ties both call sites together
 
-        def producers_of(node, bns, seen):
-            """Walk up from `node`; returns the list of producer modules, or None if the path is not provably channel-preserving."""
-            if node in seen:
-                return []
-            seen.add(node)
-            if node.op == "call_module":
-                m = mods[node.target]
-                if isinstance(m, _PRUNABLE):
-                    if isinstance(m, (nn.Conv1d, nn.Conv2d)) and m.groups != 1:
-                        return None
-                    return [(node, m)]
-                if isinstance(m, _BN_MODULES):
-                    bns.append(m)
-                    return producers_of(node.args[0], bns, seen)
-                if isinstance(m, _PASS_MODULES):
-                    return producers_of(node.args[0], bns, seen)
-                return None
-            if node.op == "call_function" and node.target in _PASS_FUNCS:
-                return producers_of(node.args[0], bns, seen)
-            if node.op == "call_function" and node.target in (operator.add, torch.add):
-                out = []
-                for a in node.args[:2]:
-                    if not isinstance(a, fx.Node):
-                        continue
-                    r = producers_of(a, bns, seen)
-                    if r is None:
-                        return None
-                    out += r
-                return out
-            return None
+        def reuse(m, src_space, out_space):
+            prev = first_use.get(id(m))
+            if prev is None:
+                first_use[id(m)] = (src_space, out_space)
+                return False
+            if src_space is not None and prev[0] is not None:
+                prev[0].union(src_space)
+            if out_space is not None and prev[1] is not None:
+                prev[1].union(out_space)
+            return True
 
-        # consumer -> (producer nodes, bns); then merge consumers that share any producer (siblings)
-        info = []
-        for node in gm.graph.nodes:
-            if node.op == "call_module" and isinstance(mods[node.target], _PRUNABLE):
-                m = mods[node.target]
-                if isinstance(m, (nn.Conv1d, nn.Conv2d)) and m.groups != 1:
+        def new_space(frozen_why=None):
+            s = _Space()
+            spaces.append(s)
+            if frozen_why:
+                s.freeze(frozen_why)
+            return s
+
+        def tensor_args(node):
+            out = []
+
+            def visit(a):
+                if isinstance(a, fx.Node):
+                    out.append(a)
+                elif isinstance(a, (tuple, list)):
+                    for x in a:
+                        visit(x)
+                elif isinstance(a, dict):
+                    for x in a.values():
+                        visit(x)
+
+            visit(node.args)
+            visit(node.kwargs)
+            return out
+
+        def freeze_inputs(node, why):
+            for a in tensor_args(node):
+                v = vals.get(a)
+                if isinstance(v, _Val):
+                    v.space.freeze(why)
+                elif isinstance(v, tuple):
+                    for x in v:
+                        if isinstance(x, _Val):
+                            x.space.freeze(why)
+
+        def opaque(node, why):
+            freeze_inputs(node, why)
+            vals[node] = _Val(new_space(why), None)
+
+        def fetch_attr(target):
+            obj = gm
+            for part in target.split("."):
+                obj = getattr(obj, part)
+            return obj
+
+        def attr_owner(target):
+            parts = target.split(".")
+            obj = gm
+            for part in parts[:-1]:
+                obj = getattr(obj, part)
+            real = model
+            try:
+                for part in parts[:-1]:
+                    real = getattr(real, part)
+            except AttributeError:
+                real = obj
+            return real, parts[-1]
+
+        def join(node, operands, why):
+            """Elementwise combination of tensor operands (some may be raw get_attr tensors riding on another operand's space)."""
+            tvals = [vals.get(a) for a in operands if isinstance(a, fx.Node)]
+            real = [v for v in tvals if isinstance(v, _Val)]
+            attrs = [a for a in operands if isinstance(a, fx.Node) and a.op == "get_attr"]
+            if not real:
+                return opaque(node, why)
+            base = real[0]
+            for v in real[1:]:
+                if v.axis != base.axis or v.rep != base.rep:
+                    base.space.freeze("elementwise operands with different layouts")
+                    v.space.freeze("elementwise operands with different layouts")
+                base.space.union(v.space)
+            for a in attrs:
+                t = fetch_attr(a.target)
+                if not torch.is_tensor(t) or t.numel() == 1:
                     continue
-                bns: list = []
-                prods = producers_of(node.args[0], bns, set())
-                if prods:
-                    info.append((m, prods, bns))
-        # every user path of a producer must end in consumers of the same group, otherwise permuting its outputs changes the function
-        consumer_inputs = {}
-        for m, prods, bns in info:
-            for pn, pm in prods:
-                consumer_inputs.setdefault(pn, []).append(m)
-
-        def escapes(pn):
-            """True if the producer's output reaches anything other than pass-through nodes and prunable consumers."""
-            stack, seen = list(pn.users), set()
-            while stack:
-                u = stack.pop()
-                if u in seen:
-                    continue
-                seen.add(u)
-                if u.op == "call_module":
-                    mm = mods[u.target]
-                    if isinstance(mm, _PRUNABLE):
-                        if isinstance(mm, (nn.Conv1d, nn.Conv2d)) and mm.groups != 1:
-                            return True
-                        continue
-                    if isinstance(mm, _PASS_MODULES + _BN_MODULES):
-                        stack += list(u.users)
-                        continue
-                    return True
-                if u.op == "call_function" and (u.target in _PASS_FUNCS or u.target in (operator.add, torch.add)):
-                    stack += list(u.users)
-                    continue
-                return True
-            return False
-
-        # union-find over consumers sharing producers
-        parent = list(range(len(info)))
-
-        def find(i):
-            while parent[i] != i:
-                parent[i] = parent[parent[i]]
-                i = parent[i]
-            return i
-
-        owner = {}
-        for i, (m, prods, bns) in enumerate(info):
-            for pn, pm in prods:
-                if pn in owner:
-                    parent[find(i)] = find(owner[pn])
+                owner, name = attr_owner(a.target)
+                if base.axis == -1:
+                    dim = t.dim() - 1
+                elif base.axis == 1 and base.rank is not None:
+                    dim = t.dim() - (base.rank - 1)
                 else:
-                    owner[pn] = i
-        groups = {}
-        for i, (m, prods, bns) in enumerate(info):
-            g = groups.setdefault(find(i), ([], {}, []))
-            g[0].append(m)
-            for pn, pm in prods:
-                g[1][pn] = pm
-            for b in bns:
-                if all(b is not x for x in g[2]):
-                    g[2].append(b)
-        out = []
-        for cons, prods, bns in groups.values():
-            if any(escapes(pn) for pn in prods):
+                    dim = None
+                if dim is None or dim < 0:
+                    base.space.freeze(f"attribute {a.target} broadcasts ambiguously")
+                    continue
+                if t.shape[dim] == 1:
+                    continue
+                base.space.find().riders.append((owner, name, dim, a.target))
+            vals[node] = base.like(spatial1=all(v.spatial1 for v in real))
+
+        for node in gm.graph.nodes:
+            if node.op == "placeholder":
+                vals[node] = _Val(new_space("graph input"), None)
+            elif node.op == "get_attr":
+                vals[node] = None   # handled where it is used (join); anywhere else the user freezes its other operands
+            elif node.op == "output":
+                freeze_inputs(node, "graph output")
+            elif node.op == "call_module":
+                m = mods[node.target]
+                src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
+                if isinstance(m, _CONVS + (nn.Linear,)):
+                    is_conv = isinstance(m, _CONVS)
+                    cin = m.in_channels if is_conv else m.in_features
+                    cout = m.out_channels if is_conv else m.out_features
+                    groups = m.groups if is_conv else 1
+                    rank = (m.weight.dim() if is_conv else None)
+                    if not isinstance(src, _Val):
+                        opaque(node, "consumer of a non-tensor")
+                        continue
+                    if groups == 1:
+                        want_axis = 1 if is_conv else -1
+                        ok = src.axis == want_axis or (not is_conv and src.axis == "flat")
+                        if not ok and src.axis is not None:
+                            src.space.freeze(f"{node.target}: channel axis mismatch")
+                        rep = src.rep if src.axis == "flat" else 1
+                        out = new_space()
+                        if not reuse(m, src.space, out):
+                            src.space.find().consumers.append((m, "weight", 1, rep, True, node.target, cin))
+                            out.riders.append((m, "weight", 0, node.target))
+                            if m.bias is not None:
+                                out.riders.append((m, "bias", 0, node.target))
+                        vals[node] = _Val(out, 1 if is_conv else -1, rank)
+                    elif groups == cin and cout == cin:   # depthwise: per-channel filter, channels pass straight through
+                        if not reuse(m, src.space, None):
+                            src.space.find().riders.append((m, "weight", 0, node.target))
+                            if m.bias is not None:
+                                src.space.find().riders.append((m, "bias", 0, node.target))
+                        vals[node] = src.like(spatial1=False)
+                    else:
+                        opaque(node, f"grouped convolution {node.target}")
+                elif isinstance(m, _CONV_T):
+                    if not isinstance(src, _Val) or m.groups != 1:
+                        opaque(node, f"transposed convolution {node.target}")
+                        continue
+                    out = new_space()
+                    if not reuse(m, src.space, out):
+                        src.space.find().consumers.append((m, "weight", 0, 1, False, node.target, m.in_channels))
+                        out.riders.append((m, "weight", 1, node.target))
+                        if m.bias is not None:
+                            out.riders.append((m, "bias", 0, node.target))
+                    vals[node] = _Val(out, 1, m.weight.dim())
+                elif isinstance(m, nn.Embedding):
+                    out = new_space()
+                    if not reuse(m, None, out):
+                        out.riders.append((m, "weight", 1, node.target))
+                    vals[node] = _Val(out, -1)
+                elif isinstance(m, _BN_MODULES):
+                    if not isinstance(src, _Val) or src.axis not in (1, -1):
+                        opaque(node, f"normalisation {node.target} on an unknown layout")
+                        continue
+                    if src.axis == -1 and not isinstance(m, nn.BatchNorm1d):
+                        opaque(node, f"normalisation {node.target} on a channels-last value")
+                        continue
+                    lazy = (nn.parameter.UninitializedParameter, nn.parameter.UninitializedBuffer)
+                    for name in ("weight", "bias", "running_mean", "running_var"):
+                        t = getattr(m, name, None)
+                        if isinstance(t, lazy):
+                            src.space.freeze(f"lazy module {node.target} is not materialised")
+                        elif torch.is_tensor(t) and t.dim() == 1:
+                            src.space.find().riders.append((m, name, 0, node.target))
+                    vals[node] = src.like()
+                elif isinstance(m, nn.LayerNorm):
+                    if not isinstance(src, _Val):
+                        opaque(node, "LayerNorm of a non-tensor")
+                        continue
+                    k = len(m.normalized_shape)
+                    if src.axis == -1:    # the channel axis is the last normalised dim: equivariant once gamma / beta are permuted
+                        for name in ("weight", "bias"):
+                            if getattr(m, name, None) is not None:
+                                src.space.find().riders.append((m, name, k - 1, node.target))
+                        vals[node] = src.like()
+                    elif src.axis == 1 and src.rank is not None:
+                        if k == src.rank - 1:   # normalises over [C, spatial...]
+                            for name in ("weight", "bias"):
+                                if getattr(m, name, None) is not None:
+                                    src.space.find().riders.append((m, name, 0, node.target))
+                            vals[node] = src.like()
+                        elif k < src.rank - 1:  # spatial dims only: channels are untouched
+                            vals[node] = src.like()
+                        else:
+                            opaque(node, f"LayerNorm {node.target} covers the batch dim")
+                    else:
+                        opaque(node, f"LayerNorm {node.target} on an unknown layout")
+                elif isinstance(m, nn.GroupNorm):
+                    if isinstance(src, _Val) and src.axis == 1 and m.num_groups in (1, m.num_channels):
+                        for name in ("weight", "bias"):
+                            if getattr(m, name, None) is not None:
+                                src.space.find().riders.append((m, name, 0, node.target))
+                        vals[node] = src.like()
+                    else:
+                        opaque(node, f"GroupNorm {node.target} ties channels into groups")
+                elif isinstance(m, nn.Flatten):
+                    if isinstance(src, _Val) and src.axis == 1 and m.start_dim == 1 and m.end_dim in (-1, (src.rank or 0) - 1):
+                        vals[node] = src.like(axis="flat", rep=1 if src.spatial1 else None)
+                    else:
+                        opaque(node, f"flatten {node.target}")
+                elif isinstance(m, nn.MultiheadAttention):
+                    qkv = list(node.args[:3]) + [node.kwargs.get(k) for k in ("query", "key", "value")]
+                    ins = [vals.get(a) for a in qkv if isinstance(a, fx.Node)]
+                    if len(ins) != 3 or not all(isinstance(v, _Val) and v.axis == -1 for v in ins) or not m._qkv_same_embed_dim:
+                        opaque(node, f"MultiheadAttention {node.target} with an unsupported input layout")
+                        continue
+                    sp = ins[0].space     # q, k and v share in_proj_weight's columns: one permutation for all three inputs
+                    for v in ins[1:]:
+                        sp.union(v.space)
+                    out = new_space()
+                    if not reuse(m, sp, out):
+                        sp.find().consumers.append((m, "in_proj_weight", 1, 1, True, node.target, m.embed_dim))
+                        out.riders.append((m.out_proj, "weight", 0, node.target + ".out_proj"))
+                        if m.out_proj.bias is not None:
+                            out.riders.append((m.out_proj, "bias", 0, node.target + ".out_proj"))
+                    vals[node] = (_Val(out, -1), None)
+                elif isinstance(m, _PASS_MODULES):
+                    if isinstance(src, _Val):
+                        vals[node] = src.like()
+                    else:
+                        opaque(node, "pass-through of a non-tensor")
+                elif isinstance(m, _SPATIAL_MODULES):
+                    if isinstance(src, _Val) and src.axis == 1:
+                        vals[node] = src.like(spatial1=src.spatial1 or _is_pool_to_1(m))
+                    else:
+                        opaque(node, f"spatial module {node.target} on a value whose channel axis is not dim 1")
+                else:
+                    opaque(node, f"unknown module type {type(m).__name__} at {node.target}")
+            elif node.op == "call_function":
+                tgt = node.target
+                if tgt is operator.getitem:
+                    base = vals.get(node.args[0])
+                    if isinstance(base, tuple) and isinstance(node.args[1], int) and node.args[1] < len(base):
+                        vals[node] = base[node.args[1]]
+                    elif isinstance(base, _Val):
+                        opaque(node, "tensor slicing")
+                    else:
+                        vals[node] = None
+                elif tgt is getattr:
+                    vals[node] = None   # x.shape and friends
+                elif tgt in _UNARY_FUNCS:
+                    src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
+                    if isinstance(src, _Val):
+                        vals[node] = src.like()
+                    else:
+                        opaque(node, "elementwise function of a non-tensor")
+                elif tgt in _SPATIAL_FUNCS:
+                    src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
+                    if isinstance(src, _Val) and src.axis == 1:
+                        osz = node.kwargs.get("output_size", node.args[1] if len(node.args) > 1 else None)
+                        to1 = tgt in (F.adaptive_avg_pool2d, F.adaptive_avg_pool1d) and osz in (1, (1, 1), (1,), [1, 1], [1])
+                        vals[node] = src.like(spatial1=src.spatial1 or to1)
+                    else:
+                        opaque(node, f"spatial function {tgt.__name__} on a value whose channel axis is not dim 1")
+                elif tgt in _BINARY_FUNCS:
+                    join(node, list(node.args[:2]), f"binary {getattr(tgt, '__name__', tgt)}")
+                elif tgt in _FLATTEN_FUNCS:
+                    src = vals.get(node.args[0])
+                    start = node.kwargs.get("start_dim", node.args[1] if len(node.args) > 1 else 0)
+                    end = node.kwargs.get("end_dim", node.args[2] if len(node.args) > 2 else -1)
+                    if isinstance(src, _Val) and src.axis == 1 and start == 1 and end in (-1, (src.rank or 0) - 1):
+                        vals[node] = src.like(axis="flat", rep=1 if src.spatial1 else None)
+                    else:
+                        opaque(node, "flatten")
+                else:
+                    opaque(node, f"function {getattr(tgt, '__name__', tgt)}")
+            elif node.op == "call_method":
+                name = node.target
+                src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
+                if name in _NON_TENSOR_METHODS:
+                    vals[node] = None
+                elif name in _UNARY_METHODS and isinstance(src, _Val):
+                    vals[node] = src.like()
+                elif name in _BINARY_METHODS:
+                    join(node, list(node.args[:2]), f"method {name}")
+                elif name == "flatten" and isinstance(src, _Val) and src.axis == 1 and (node.args[1:] or (None,))[0] == 1 and len(node.args) <= 2:
+                    vals[node] = src.like(axis="flat", rep=1 if src.spatial1 else None)
+                elif name in ("view", "reshape") and isinstance(src, _Val) and src.axis == 1 and len(node.args) == 3 and node.args[2] == -1 \
+                        and isinstance(node.args[1], fx.Node) and node.args[1].op == "call_method" and node.args[1].target == "size":
+                    vals[node] = src.like(axis="flat", rep=1 if src.spatial1 else None)   # x.view(x.size(0), -1)
+                else:
+                    opaque(node, f"method {name}")
+
+        return [s for s in spaces if s.find() is s]
+
+    @staticmethod
+    def _space_size(space):
+        for owner, name, dim, _ in space.riders:
+            return getattr(owner, name).shape[dim]
+        return None
+
+    @classmethod
+    def _validate(cls, space):
+        """-> (ok, C, [resolved consumers]); every tensor's channel dim must agree with the space size."""
+        C = cls._space_size(space)
+        if C is None or C % 4 != 0:
+            return False, C, []
+        for owner, name, dim, _ in space.riders:
+            t = getattr(owner, name, None)
+            if t is None or t.shape[dim] != C:
+                return False, C, []
+        cons = []
+        for m, attr, dim, rep, prunable, where, cin in space.consumers:
+            w = getattr(m, attr)
+            if rep is None:   # flattened [C, spatial...]: each channel covers in_features / C consecutive columns
+                if w.shape[dim] % C != 0:
+                    return False, C, []
+                rep = w.shape[dim] // C
+            if w.shape[dim] != C * rep:
+                return False, C, []
+            cons.append((m, attr, dim, rep, prunable, where))
+        return True, C, cons
+
+    @classmethod
+    def _search_matrix(cls, cons):
+        """Stack the prunable consumers' weights into [rows, C] (spatial taps and flattened repeats folded into rows)."""
+        sparse = cls.__sparse_parameters
+        mats = []
+        for m, attr, dim, rep, prunable, _ in cons:
+            w = getattr(m, attr)
+            if not prunable or (sparse is not None and not any(w is p for p in sparse)):
                 continue
-            C = cons[0].weight.shape[1]
-            if any(c.weight.shape[1] != C for c in cons) or any(p.weight.shape[0] != C for p in prods.values()) or C % 4 != 0:
-                continue
-            out.append((cons, list(prods.values()), bns))
-        return out
+            w2 = w.detach().movedim(dim, -1).reshape(-1, w.shape[dim]).float()    # [rows, C * rep], channel-major columns
+            if rep > 1:
+                w2 = w2.reshape(-1, w2.shape[1] // rep, rep).permute(0, 2, 1).reshape(-1, w2.shape[1] // rep)
+            mats.append(w2)
+        return torch.cat(mats, 0) if mats else None
+
+    @staticmethod
+    def sync_permutation(perm, device=None):
+        """Every rank applies rank 0's permutation (reference: sync_permutations through a TCPStore :1026-1090)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return perm
+        dev = device if dist.get_backend() == "nccl" else "cpu"
+        t = torch.as_tensor(perm, dtype=torch.int64, device=dev)
+        dist.broadcast(t, 0)
+        return [int(i) for i in t.cpu()]
 
     # -------------------------------------------------------------------------------------------------------------- driver
     @classmethod
     def permute_model(cls, model, dump_fx_graph=False, save_dumped_fx_graph=None, verbosity=0):
-        """Search and apply a permutation for every safe sibling group; returns [(consumer names..., magnitude before, after)]."""
+        """Search and apply a permutation for every unfrozen channel space; returns [(n consumers, magnitude before, after)]."""
         cls.__verbosity = verbosity
+        cls.__stats = {"C": 0, "K": 0}
         try:
-            groups = cls.build_groups(model)
+            roots = cls.build_spaces(model)
         except Exception as e:  # untraceable model: leave it unpermuted, like the reference does on trace failure
             if verbosity:
                 print(f"[permutation_lib] model is not fx-traceable ({type(e).__name__}: {e}); skipping channel permutations")
             return []
-        report = []
-        names = {m: n for n, m in model.named_modules()}
-        dumped = []
-        for cons, prods, bns in groups:
-            mats = [c.weight.detach().reshape(c.weight.shape[0], c.weight.shape[1], -1).permute(0, 2, 1).reshape(-1, c.weight.shape[1]) for c in cons]
-            stacked = torch.cat(mats, 0).float()
-            before = float(sum_after_2_to_4(stacked))
-            perm = accelerated_search_for_good_permutation(stacked, cls.search_options, verbosity)
-            after = float(sum_after_2_to_4(stacked[:, torch.as_tensor(perm, device=stacked.device)]))
-            if after <= before:
+        report, dumped = [], []
+        for space in roots:
+            if space.frozen or not space.consumers:
+                if verbosity and space.consumers:
+                    print(f"[permutation_lib] skipping a space with {len(space.consumers)} consumer(s): {space.why}")
+                dumped.append({"skipped": space.why or "no consumers", "consumers": [c[5] for c in space.consumers]})
                 continue
-            for c in cons:
-                cls.apply_permutation_in_C_dim(c, perm)
-            for p in prods + bns:
-                cls.apply_permutation_in_K_dim(p, perm)
+            ok, C, cons = cls._validate(space)
+            if not ok:
+                dumped.append({"skipped": f"dimension mismatch (C = {C})", "consumers": [c[5] for c in space.consumers]})
+                continue
+            stacked = cls._search_matrix(cons)
+            if stacked is None:
+                dumped.append({"skipped": "no prunable consumer", "consumers": [c[5] for c in cons]})
+                continue
+            before = float(sum_after_2_to_4(stacked))
+            cls.reset_seed()
+            perm = accelerated_search_for_good_permutation(stacked, cls.search_options, verbosity)
+            perm = cls.sync_permutation([int(i) for i in perm], stacked.device)
+            idx = torch.as_tensor(perm, device=stacked.device)
+            after = float(sum_after_2_to_4(stacked[:, idx]))
+            if after <= before:
+                dumped.append({"skipped": "no improvement", "consumers": [c[5] for c in cons]})
+                continue
+            seen = set()
+            for m, attr, dim, rep, _, _ in cons:
+                if (id(getattr(m, attr)), dim) in seen:
+                    continue
+                seen.add((id(getattr(m, attr)), dim))
+                cls.apply_permutation_in_C_dim(m, perm, attr, dim, rep)
+                cls.__stats["C"] += 1
+            seen = set()
+            for owner, name, dim, _ in space.riders:
+                t = getattr(owner, name)
+                if id(t) in seen:      # a module reused at several call sites rides once
+                    continue
+                seen.add(id(t))
+                cls._permute_tensor(t, dim, idx.long())
+                cls.__stats["K"] += 1
             report.append((len(cons), before, after))
-            dumped.append({"consumers": [names.get(c, "?") for c in cons], "producers": [names.get(m, "?") for m in prods],
-                           "norms": [names.get(m, "?") for m in bns], "permutation": [int(i) for i in perm], "kept_magnitude_before": before,
-                           "kept_magnitude_after": after})
+            dumped.append({"consumers": [c[5] for c in cons], "riders": sorted({f"{r[3]}.{r[1]}" for r in space.riders}), "channels": C,
+                           "permutation": perm, "kept_magnitude_before": before, "kept_magnitude_after": after})
             if verbosity:
-                print(f"[permutation_lib] group of {len(cons)} consumer(s): kept magnitude {before:.3f} -> {after:.3f}")
+                print(f"[permutation_lib] space of {C} channels, {len(cons)} consumer(s), {len(seen)} rider tensor(s): kept magnitude "
+                      f"{before:.3f} -> {after:.3f}")
         if dump_fx_graph and save_dumped_fx_graph:   # what was permuted and how, for offline inspection (the reference dumps its annotated fx graph)
             import json
 

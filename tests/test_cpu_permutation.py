@@ -1,0 +1,182 @@
+"""Channel-permutation graph analysis (contrib/sparsity/permutation_lib.py): every network family below must compute the same function
+after permute_model, and the number of tensors permuted along C / K must match what the graph allows. Modelled on the reference's
+apex/contrib/sparsity/test/test_permutation_application.py (simple_convs x normalisations, forks / joins, grouped and depthwise convs,
+module attributes, MHA, concat, flatten, trace failure)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from apex_b200.contrib.sparsity.permutation_lib import Permutation as P
+
+
+@pytest.fixture(autouse=True)
+def _fast_search():
+    old = P.search_options
+    P.search_options = {"strategy": "exhaustive", "stripe_group_size": 8, "escape_attempts": 1}
+    P.set_permutation_params_from_asp(None, None)
+    yield
+    P.search_options = old
+    P.set_permutation_params_from_asp(None, None)
+
+
+def _check(model, x, exp=None, min_groups=0):
+    torch.manual_seed(0)
+    model.eval()
+    for mod in model.modules():      # non-trivial affine parameters / statistics so that a missed rider shows up in the output
+        if isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm, nn.InstanceNorm2d, nn.GroupNorm)):
+            for n in ("weight", "bias", "running_mean"):
+                t = getattr(mod, n, None)
+                if t is not None:
+                    t.data.normal_()
+    y0 = model(x).detach().clone()
+    rep = P.permute_model(model)
+    torch.testing.assert_close(model(x).detach(), y0, atol=2e-5, rtol=1e-4)
+    assert len(rep) >= min_groups and all(after > before for _, before, after in rep)
+    if exp is not None:
+        assert P.get_permutation_stats() == exp
+    return rep
+
+
+class _Convs(nn.Module):
+    def __init__(self, norm):
+        super().__init__()
+        layers = []
+        for _ in range(3):
+            layers.append(nn.Conv2d(16, 16, 3, padding=1))
+            norm_layer = {"bn": lambda: nn.BatchNorm2d(16), "gn": lambda: nn.GroupNorm(4, 16), "in": lambda: nn.InstanceNorm2d(16, affine=True),
+                          "ln3": lambda: nn.LayerNorm([16, 7, 7]), "ln1": lambda: nn.LayerNorm(7), "lrn": lambda: nn.LocalResponseNorm(16),
+                          "none": lambda: None}[norm]()
+            if norm_layer is not None:
+                layers.append(norm_layer)
+            layers.append(nn.ReLU())
+        layers.append(nn.Conv2d(16, 8, 1))
+        self.s = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.s(x)
+
+
+@pytest.mark.parametrize("norm,exp", [("none", (3, 6)), ("bn", (3, 18)), ("in", (3, 12)), ("ln3", (3, 12)), ("ln1", (3, 6)), ("gn", (0, 0)),
+                                      ("lrn", (0, 0))])
+def test_conv_stacks_with_normalisations(norm, exp):
+    _check(_Convs(norm), torch.randn(4, 16, 7, 7), exp)
+
+
+def test_residual_block_is_one_space_for_the_stream():
+    class Res(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem, self.bn0 = nn.Conv2d(3, 32, 3, padding=1), nn.BatchNorm2d(32)
+            self.c1, self.b1 = nn.Conv2d(32, 16, 1), nn.BatchNorm2d(16)
+            self.c2, self.b2 = nn.Conv2d(16, 16, 3, padding=1), nn.BatchNorm2d(16)
+            self.c3, self.b3 = nn.Conv2d(16, 32, 1), nn.BatchNorm2d(32)
+            self.pool, self.fc = nn.AdaptiveAvgPool2d(1), nn.Linear(32, 10)
+
+        def forward(self, x):
+            x = F.relu(self.bn0(self.stem(x)))
+            y = F.relu(self.b1(self.c1(x)))
+            y = F.relu(self.b2(self.c2(y)))
+            x = F.relu(x + self.b3(self.c3(y)))
+            return self.fc(torch.flatten(self.pool(x), 1))
+
+    rep = _check(Res(), torch.randn(2, 3, 8, 8), min_groups=3)
+    assert sorted(r[0] for r in rep) == [1, 1, 2]     # the stream has two consumers (c1 and fc); the two 16-wide spaces one each
+
+
+def test_transformer_block_with_mha():
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb, self.ln1, self.att = nn.Linear(8, 32), nn.LayerNorm(32), nn.MultiheadAttention(32, 4, batch_first=True)
+            self.ln2, self.f1, self.f2, self.head = nn.LayerNorm(32), nn.Linear(32, 64), nn.Linear(64, 32), nn.Linear(32, 5)
+
+        def forward(self, x):
+            h = self.emb(x)
+            a = self.ln1(h)
+            a, _ = self.att(a, a, a)
+            h = h + a
+            h = h + self.f2(F.gelu(self.f1(self.ln2(h))))
+            return self.head(h)
+
+    # stream: in_proj_weight, f1, head along C; emb / out_proj / f2 weight + bias and both LayerNorms along K; hidden: f2 along C, f1 along K
+    _check(Block(), torch.randn(2, 6, 8), (4, 12), min_groups=2)
+
+
+def test_flatten_after_conv_permutes_blocks_of_columns():
+    class Fl(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c, self.f = nn.Conv2d(16, 64, 1), nn.Linear(64 * 9, 16)
+
+        def forward(self, x):
+            return self.f(torch.flatten(self.c(x), start_dim=1))
+
+    _check(Fl(), torch.randn(4, 16, 3, 3), (1, 2), min_groups=1)
+
+
+@pytest.mark.parametrize("groups,exp", [(32, (1, 4)), (4, (0, 0))])
+def test_depthwise_passes_through_and_grouped_freezes(groups, exp):
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.d, self.b = nn.Conv2d(8, 32, 1), nn.Conv2d(32, 32, 3, padding=1, groups=groups), nn.Conv2d(32, 16, 1)
+
+        def forward(self, x):
+            return self.b(F.relu(self.d(self.a(x))))
+
+    _check(M(), torch.randn(2, 8, 5, 5), exp)
+
+
+def test_broadcast_module_attribute_rides_along():
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.g, self.b = nn.Conv2d(8, 32, 1), nn.Parameter(torch.randn(1, 32, 1, 1)), nn.Conv2d(32, 16, 1)
+
+        def forward(self, x):
+            return self.b(self.a(x) * self.g)
+
+    _check(M(), torch.randn(2, 8, 5, 5), (1, 3))
+
+
+def test_concat_and_untraceable_models_are_left_alone():
+    class Cat(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = nn.Conv2d(8, 16, 1), nn.Conv2d(8, 16, 1), nn.Conv2d(32, 16, 1)
+
+        def forward(self, x):
+            return self.c(torch.cat([self.a(x), self.b(x)], 1))
+
+    class Branchy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(8, 8)
+
+        def forward(self, x):
+            return self.a(x) if x.sum() > 0 else x
+
+    _check(Cat(), torch.randn(2, 8, 5, 5), (0, 0))
+    _check(Branchy(), torch.randn(3, 8), (0, 0))
+
+
+def test_module_called_twice_ties_its_spaces():
+    class Sh(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.m, self.o = nn.Linear(8, 32), nn.Linear(32, 32), nn.Linear(32, 4)
+
+        def forward(self, x):
+            return self.o(F.relu(self.m(F.relu(self.m(F.relu(self.a(x)))))))
+
+    _check(Sh(), torch.randn(3, 8), (2, 4), min_groups=1)
+
+
+def test_only_asp_sparse_consumers_drive_the_search():
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 8))
+    P.set_permutation_params_from_asp(model, [])     # ASP prunes nothing: nothing to search for
+    assert P.permute_model(model) == []
+    P.set_permutation_params_from_asp(model, [("2", model[2], "weight", model[2].weight, None, None)])
+    assert len(P.permute_model(model)) == 1
