@@ -23,6 +23,7 @@ struct Params {
   void* aux; long long ldaux;      // [M, N] pre-activation (dtype of D): written by BIAS_GELU, read by DGELU
   const void* C; long long ldc;    // accumulate source (EPI_ACCUM), same dtype as D
   int a_mn_major, b_mn_major;
+  int a_mn3, b_mn3;                // MN-major operand staged by ONE 3-D TMA box per stage (extent % 128-byte row == 0) instead of 2 / 4 2-D boxes
   int epi;
   float alpha;                     // accumulator scale applied before the epilogue op
   const float* scale_a; const float* scale_b;  // optional DEVICE scalars multiplied into alpha (fp8 dequantisation scales: no host sync)
@@ -132,22 +133,27 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte swizzle atoms, 8-row period); 1 = SWIZZLE_128B_BASE32B (32-byte atoms, 4-row period) -- the only
+// layout the tensor core accepts for MN-major 32-bit (tf32) operands; its TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a_format [7,10), b_format [10,13),
 // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
 // `is_bf16` doubles as the operand format code: kind::f16 0 = F16, 1 = BF16; kind::f8f6f4 0 = E4M3, 1 = E5M2.
 // Bit 0 of the code is A's format, bit 1 set means "B's format differs from A's" (fp8 backward: E5M2 gradients x E4M3 weights / activations).
+// fmt == kFmtTF32: both operands are fp32 words read as TF32 (kind::tf32 format code 2).
+constexpr int kFmtTF32 = 8;
 __host__ __device__ inline uint32_t make_idesc(int fmt, int a_mn, int b_mn, int m, int n) {
   uint32_t d = 0;
-  const uint32_t fa = (uint32_t)(fmt & 1), fb = ((fmt >> 1) & 1) ? (fa ^ 1u) : fa;
+  uint32_t fa = (uint32_t)(fmt & 1), fb = ((fmt >> 1) & 1) ? (fa ^ 1u) : fa;
+  if (fmt == kFmtTF32) fa = fb = 2u;
   d |= 1u << 4;
   d |= fa << 7;
   d |= fb << 10;

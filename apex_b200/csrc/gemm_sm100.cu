@@ -197,6 +197,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
   asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D variant: an MN-major operand viewed as {128-byte row of MN elements, k, MN block}; one box {row, BKE k-rows, all of the CTA's MN
+// blocks} lands in shared memory block after block -- the same image the 2-D boxes build, with one instruction instead of 2 / 4.
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -210,6 +217,10 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
 }
 __device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
@@ -227,9 +238,14 @@ struct Smem2 {
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 
-// F8: operands are 8-bit floats (E4M3 / E5M2, K-major only): a 128-byte swizzle row holds 128 elements, one tcgen05.mma.kind::f8f6f4
-// covers K = 32 -- every BYTE offset (stage sizes, descriptor steps) is identical to the 16-bit case, only element counts double.
-template <typename TOut, int KSTAGES, bool F8>
+// KIND selects the operand element size; every BYTE quantity (128-byte swizzle rows, 16 KB per operand per stage, 32 bytes of K per MMA,
+// four MMAs per k-block) is the same for all three, only the element counts differ:
+//   KIND_16 : bf16 / fp16, kind::f16,     64 k-elements per block, K = 16 per MMA
+//   KIND_8  : E4M3 / E5M2, kind::f8f6f4, 128 k-elements per block, K = 32 per MMA (K-major operands only)
+//   KIND_32 : fp32 words read as TF32, kind::tf32, 32 k-elements per block, K = 8 per MMA
+// MN-major operands are staged as boxes of {one 128-byte row of MN elements, BKE k-rows}: 64 / 32 elements wide for 16-bit / tf32.
+constexpr int KIND_16 = 0, KIND_8 = 1, KIND_32 = 2;
+template <typename TOut, int KSTAGES, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params p, int is_bf16) {
   using S = Smem2<KSTAGES>;
@@ -247,7 +263,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   const bool leader = cta == 0;
   const int num_m = (p.M + 2 * BM - 1) / (2 * BM), num_n = (p.N + BN2 - 1) / BN2;
   const int num_tiles = num_m * num_n;
-  constexpr int BKE = F8 ? 2 * BK : BK;  // elements per k-block (128 bytes per row either way)
+  constexpr int ESZ = KIND == KIND_16 ? 2 : (KIND == KIND_8 ? 1 : 4);
+  constexpr int BKE = 128 / ESZ;         // k-elements per block (128 bytes per K-major row)
+  constexpr int MNB = 128 / ESZ;         // MN-elements per 128-byte row of an MN-major box
+  constexpr int kMnBoxBytes = BKE * 128; // one MN-major box: BKE k-rows of 128 bytes
   const int num_k = (p.K + BKE - 1) / BKE;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   constexpr uint32_t kTmemCols = 2 * BN2;
@@ -284,14 +303,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           uint8_t* sb = sa + S::kABytes;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * S::kStage);  // bytes of both CTAs land on the leader's barrier
           if (!p.a_mn_major) tma_load_2d_2sm(sa, &map_a, &full_bar[stage], kb * BKE, m0);
+          else if (p.a_mn3) tma_load_3d_2sm(sa, &map_a, &full_bar[stage], 0, kb * BKE, m0 / MNB);
           else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; i++) tma_load_2d_2sm(sa + i * (BK * 128), &map_a, &full_bar[stage], m0 + i * 64, kb * BK);
+            for (int i = 0; i < BM / MNB; i++) tma_load_2d_2sm(sa + i * kMnBoxBytes, &map_a, &full_bar[stage], m0 + i * MNB, kb * BKE);
           }
           if (!p.b_mn_major) tma_load_2d_2sm(sb, &map_b, &full_bar[stage], kb * BKE, n0);
+          else if (p.b_mn3) tma_load_3d_2sm(sb, &map_b, &full_bar[stage], 0, kb * BKE, n0 / MNB);
           else {
 #pragma unroll
-            for (int i = 0; i < (BN2 / 2) / 64; i++) tma_load_2d_2sm(sb + i * (BK * 128), &map_b, &full_bar[stage], n0 + i * 64, kb * BK);
+            for (int i = 0; i < (BN2 / 2) / MNB; i++) tma_load_2d_2sm(sb + i * kMnBoxBytes, &map_b, &full_bar[stage], n0 + i * MNB, kb * BKE);
           }
           if (++stage == KSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -302,9 +323,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (leader) {
       const uint32_t idesc = make_idesc(is_bf16, p.a_mn_major, p.b_mn_major, 2 * BM, BN2);
       const uint32_t smem0 = smem_u32(smem);
-      const uint64_t a0 = p.a_mn_major ? make_desc(smem0, BK * 128, 1024) : make_desc(smem0, 16, 1024);
-      const uint64_t b0 = p.b_mn_major ? make_desc(smem0 + S::kABytes, BK * 128, 1024) : make_desc(smem0 + S::kABytes, 16, 1024);
-      const uint32_t a_step = p.a_mn_major ? (2048u >> 4) : (32u >> 4), b_step = p.b_mn_major ? (2048u >> 4) : (32u >> 4);
+      // MN-major: boxes kMnBoxBytes apart along MN (LBO), 8-k-row atoms 1024 B apart (SBO); one MMA covers 32 / ESZ k-rows
+      constexpr uint32_t kMnStep = (32u / ESZ) * 128u;
+      // 32-bit MN-major operands: 32-byte swizzle atoms with a 4-row period (SWIZZLE_128B_BASE32B), so k-row groups are 512 B apart
+      constexpr uint32_t kMnLayout = KIND == KIND_32 ? 1u : 2u, kMnSbo = KIND == KIND_32 ? 512u : 1024u;
+      constexpr uint32_t lbo = kMnBoxBytes, sbo = kMnSbo, mstep = kMnStep;
+      const uint64_t a0 = p.a_mn_major ? make_desc(smem0, lbo, sbo, kMnLayout) : make_desc(smem0, 16, 1024);
+      const uint64_t b0 = p.b_mn_major ? make_desc(smem0 + S::kABytes, lbo, sbo, kMnLayout) : make_desc(smem0 + S::kABytes, 16, 1024);
+      const uint32_t a_step = p.a_mn_major ? (mstep >> 4) : (32u >> 4), b_step = p.b_mn_major ? (mstep >> 4) : (32u >> 4);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -318,7 +344,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const uint64_t ad = a0 + (uint32_t)(stage * (S::kStage >> 4)), bd = b0 + (uint32_t)(stage * (S::kStage >> 4));
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; k++)
-              if (F8) umma_f8_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (KIND == KIND_8) umma_f8_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
+              else if (KIND == KIND_32) umma_tf32_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
               else umma_f16_2sm(tmem_d, ad + k * a_step, bd + k * b_step, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2sm(&empty_bar[stage]);
             if (kb == num_k - 1) umma_commit_2sm(&tmem_full[acc]);
@@ -383,30 +410,31 @@ static EncodeTiledFn encode_fn() {
 
 // Descriptor cache: a training loop issues the same GEMMs (same pointers, shapes, boxes) every step, and cuTensorMapEncodeTiled is a
 // driver call (~1-2 us each, two per GEMM). Small direct-mapped cache keyed by everything that goes into the descriptor.
-struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_cols, box_rows; int fmt, esize; };
+struct MapKey { const void* ptr; uint64_t rows, cols, ld; uint32_t box_cols, box_rows; int fmt, esize, atom32; };
 struct MapSlot { MapKey k; CUtensorMap m; bool valid; };
 static inline bool key_eq(const MapKey& a, const MapKey& b) {
   return a.ptr == b.ptr && a.rows == b.rows && a.cols == b.cols && a.ld == b.ld && a.box_cols == b.box_cols && a.box_rows == b.box_rows &&
-         a.fmt == b.fmt && a.esize == b.esize;
+         a.fmt == b.fmt && a.esize == b.esize && a.atom32 == b.atom32;
 }
 static int make_map_uncached(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                             uint32_t box_rows, int esize);
+                             uint32_t box_rows, int esize, int atom32);
+// atom32: SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B (MN-major tf32 operands, see make_desc)
 static int make_map(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                    uint32_t box_rows, int esize = 2) {
+                    uint32_t box_rows, int esize = 2, int atom32 = 0) {
   constexpr int kSlots = 256;
   static thread_local MapSlot cache[kSlots];   // thread_local: the autograd engine calls from its own threads, no locking needed
-  const MapKey k{ptr, rows, cols, ld, box_cols, box_rows, is_bf16, esize};
+  const MapKey k{ptr, rows, cols, ld, box_cols, box_rows, is_bf16, esize, atom32};
   uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols << 17) ^ (ld << 3) ^ box_rows ^ ((uint64_t)box_cols << 9);
   MapSlot& slot = cache[(h >> 32) % kSlots];
   if (slot.valid && key_eq(slot.k, k)) { *m = slot.m; return 0; }
-  const int rc = make_map_uncached(m, ptr, is_bf16, rows, cols, ld, box_cols, box_rows, esize);
+  const int rc = make_map_uncached(m, ptr, is_bf16, rows, cols, ld, box_cols, box_rows, esize, atom32);
   if (rc == 0) { slot.k = k; slot.m = *m; slot.valid = true; }
   return rc;
 }
 
 // 2-D row-major [rows, cols] 16-bit tensor with leading dimension ld (elements); box = {box_cols (inner), box_rows}.
 static int make_map_uncached(CUtensorMap* m, const void* ptr, int is_bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
-                             uint32_t box_rows, int esize) {
+                             uint32_t box_rows, int esize, int atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1001;
   bind_primary_context_once();
@@ -414,10 +442,36 @@ static int make_map_uncached(CUtensorMap* m, const void* ptr, int is_bf16, uint6
   cuuint64_t strides[1] = {ld * (cuuint64_t)esize};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2, const_cast<void*>(ptr), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(m, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(2000 + (int)r);
+}
+
+// MN-major operand [k_rows, mn_cols] (row-major, leading dim ld) as a 3-D tensor {mnb (one 128-byte row), k_rows, mn_cols / mnb}
+// with box {mnb, box_k, nblk}; requires mn_cols % mnb == 0. Cached like the 2-D maps (box_cols carries nblk << 16 | mnb).
+static int make_map3(CUtensorMap* m, const void* ptr, int fmt, uint64_t k_rows, uint64_t mn_cols, uint64_t ld, uint32_t mnb, uint32_t box_k,
+                     uint32_t nblk, int esize, int atom32) {
+  constexpr int kSlots = 64;
+  static thread_local MapSlot cache[kSlots];
+  const MapKey k{ptr, k_rows, mn_cols, ld, (nblk << 16) | mnb, box_k, fmt, esize, atom32 | 2};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull ^ (k_rows * 0xC2B2AE3D27D4EB4Full) ^ (mn_cols << 17) ^ (ld << 3) ^ box_k;
+  MapSlot& slot = cache[(h >> 32) % kSlots];
+  if (slot.valid && key_eq(slot.k, k)) { *m = slot.m; return 0; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1001;
+  bind_primary_context_once();
+  cuuint64_t dims[3] = {mnb, k_rows, mn_cols / mnb};
+  cuuint64_t strides[2] = {ld * (cuuint64_t)esize, (cuuint64_t)mnb * esize};
+  cuuint32_t box[3] = {mnb, box_k, nblk};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : ((fmt & 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  CUresult r = fn(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -(2000 + (int)r);
+  slot.k = k; slot.m = *m; slot.valid = true;
+  return 0;
 }
 
 template <typename TOut, int BN, int KSTAGES>
@@ -437,11 +491,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p,
   return (int)e;
 }
 
-template <typename TOut, int KSTAGES, bool F8 = false>
+template <typename TOut, int KSTAGES, int KIND = KIND_16>
 static int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int is_bf16, int sms, cudaStream_t st) {
   using S = Smem2<KSTAGES>;
   static bool attr_done = false;
-  auto kern = gemm2_kernel<TOut, KSTAGES, F8>;
+  auto kern = gemm2_kernel<TOut, KSTAGES, KIND>;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) return (int)e;
@@ -477,15 +531,22 @@ AB_API int ab_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int
   const int BN = (N >= 192 || N > 128) ? 256 : 128;
   CUtensorMap ma, mb;
   int rc;
-  if (!a_mn_major) rc = make_map(&ma, A, is_bf16, M, K, lda, BK, BM); else rc = make_map(&ma, A, is_bf16, K, M, lda, 64, BK);
-  if (rc) return rc;
   // 2-CTA (SM pair) kernel for anything with at least one full 256 x 256 tile; the single-CTA kernel for small / skinny problems
   const bool use2 = (M > 128) && (N > 128) && (getenv("APEX_B200_GEMM_1CTA") == nullptr);
-  if (!b_mn_major) rc = make_map(&mb, B, is_bf16, N, K, ldb, BK, use2 ? BN2 / 2 : BN); else rc = make_map(&mb, B, is_bf16, K, N, ldb, 64, BK);
+  static const bool no3d = getenv("APEX_B200_GEMM_NO3D") != nullptr;
+  const bool a3 = use2 && a_mn_major && (M % 64 == 0) && !no3d, b3 = use2 && b_mn_major && (N % 64 == 0) && !no3d;
+  if (!a_mn_major) rc = make_map(&ma, A, is_bf16, M, K, lda, BK, BM);
+  else if (a3) rc = make_map3(&ma, A, is_bf16, K, M, lda, 64, BK, BM / 64, 2, 0);
+  else rc = make_map(&ma, A, is_bf16, K, M, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_map(&mb, B, is_bf16, N, K, ldb, BK, use2 ? BN2 / 2 : BN);
+  else if (b3) rc = make_map3(&mb, B, is_bf16, K, N, ldb, 64, BK, (BN2 / 2) / 64, 2, 0);
+  else rc = make_map(&mb, B, is_bf16, K, N, ldb, 64, BK);
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
   p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f; p.scale_a = nullptr; p.scale_b = nullptr;
+  p.a_mn3 = a3; p.b_mn3 = b3;
   p.colsum = colsum;
   // flag-guarded B: only the forward layout (K-major weight, dense rows) maps tile rows to a contiguous range of the parameter buffer
   const bool guarded = ready_flags != nullptr && !b_mn_major && ldb == K && ready_bucket_elems > 0;
@@ -521,12 +582,45 @@ AB_API int ab_gemm_fp8(const void* A, const void* B, void* D, int M, int N, int 
   if (rc) return rc;
   Params p;
   p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = nullptr; p.ldc = 0;
-  p.a_mn_major = 0; p.b_mn_major = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b; p.colsum = nullptr; p.ready_flags = nullptr;
+  p.a_mn_major = 0; p.b_mn_major = 0; p.a_mn3 = 0; p.b_mn3 = 0; p.epi = epi; p.alpha = alpha; p.scale_a = scale_a; p.scale_b = scale_b; p.colsum = nullptr; p.ready_flags = nullptr;
   if (sms <= 0) sms = kNumSMs;
-  if (dt_out == kBF16) return launch2<bf16, 6, true>(ma, mb, p, fmt, sms, st);
-  if (dt_out == kF16) return launch2<f16, 6, true>(ma, mb, p, fmt, sms, st);
-  if (dt_out == kF32) return launch2<float, 6, true>(ma, mb, p, fmt, sms, st);
+  if (dt_out == kBF16) return launch2<bf16, 6, KIND_8>(ma, mb, p, fmt, sms, st);
+  if (dt_out == kF16) return launch2<f16, 6, KIND_8>(ma, mb, p, fmt, sms, st);
+  if (dt_out == kF32) return launch2<float, 6, KIND_8>(ma, mb, p, fmt, sms, st);
   return -1;
+}
+
+// D[M,N] (fp32) = op(A) op(B) with fp32 operands multiplied as TF32 (tcgen05.mma.kind::tf32: 10-bit mantissa products, fp32 accumulation
+// in TMEM) -- the tensor-core path for fp32 layers when the caller allows TF32 (torch.backends.cuda.matmul.allow_tf32 /
+// float32_matmul_precision != "highest"); IEEE fp32 products have no tensor-core instruction and stay a library SGEMM.
+// Operand layouts as in ab_gemm_bf16. Requirements (else -10): inner extents and leading dims multiples of 4 elements, 16-byte bases.
+AB_API int ab_gemm_tf32(const void* A, const void* B, void* D, int M, int N, int K, long long lda, long long ldb, long long ldd,
+                        int a_mn_major, int b_mn_major, int epi, const void* bias, void* aux, long long ldaux, const void* C, long long ldc,
+                        float* colsum, int sms, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 4) || (ldb % 4) || !aligned16(A) || !aligned16(B)) return -10;
+  if ((!a_mn_major && (K % 4)) || (a_mn_major && (M % 4)) || (!b_mn_major && (K % 4)) || (b_mn_major && (N % 4))) return -10;
+  constexpr int BKE = 32, MNB = 32;
+  CUtensorMap ma, mb;
+  int rc;
+  static const bool no3d = getenv("APEX_B200_GEMM_NO3D") != nullptr;
+  const bool a3 = a_mn_major && (M % MNB == 0) && !no3d, b3 = b_mn_major && (N % MNB == 0) && !no3d;
+  if (!a_mn_major) rc = make_map(&ma, A, kFmtTF32, M, K, lda, BKE, BM, 4);
+  else if (a3) rc = make_map3(&ma, A, kFmtTF32, K, M, lda, MNB, BKE, BM / MNB, 4, 1);
+  else rc = make_map(&ma, A, kFmtTF32, K, M, lda, MNB, BKE, 4, 1);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_map(&mb, B, kFmtTF32, N, K, ldb, BKE, BN2 / 2, 4);
+  else if (b3) rc = make_map3(&mb, B, kFmtTF32, K, N, ldb, MNB, BKE, (BN2 / 2) / MNB, 4, 1);
+  else rc = make_map(&mb, B, kFmtTF32, K, N, ldb, MNB, BKE, 4, 1);
+  if (rc) return rc;
+  Params p;
+  p.M = M; p.N = N; p.K = K; p.D = D; p.ldd = ldd; p.bias = bias; p.aux = aux; p.ldaux = ldaux; p.C = C; p.ldc = ldc;
+  p.a_mn_major = a_mn_major; p.b_mn_major = b_mn_major; p.epi = epi; p.alpha = 1.f; p.scale_a = nullptr; p.scale_b = nullptr;
+  p.a_mn3 = a3; p.b_mn3 = b3;
+  p.colsum = colsum; p.ready_flags = nullptr; p.ready_epoch = 0; p.ready_world = 0; p.ready_w_off = 0; p.ready_bucket_elems = 0;
+ 
+  if (sms <= 0) sms = kNumSMs;
+  return launch2<float, 6, KIND_32>(ma, mb, p, kFmtTF32, sms, st);
 }
 
 // Column sums of a row-major [M, N] matrix (bias gradients): out[n] = sum_m x[m, n]. fp32 accumulation, deterministic.

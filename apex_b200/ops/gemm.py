@@ -2,7 +2,11 @@
 
 ``linear_*`` helpers express the three GEMMs of a linear layer (forward, dgrad, wgrad) without materialising transposes:
 the kernel reads either operand K-major or MN-major straight from its row-major storage.
-Shapes the kernel does not take (fp32/fp64 operands, inner extents that are not multiples of 8) go to cuBLAS via torch.
+fp32 operands run on the same kernel as TF32 (tcgen05.mma.kind::tf32, fp32 accumulation) when the caller allows TF32 products
+(``torch.backends.cuda.matmul.allow_tf32`` / ``torch.set_float32_matmul_precision("high")``, or APEX_B200_TF32=1); with IEEE fp32
+products requested (torch's default) there is no tensor-core instruction to use and the GEMM is a library SGEMM, like the reference's
+(csrc/fused_dense_cuda.cu:29-30, CUBLAS_COMPUTE_32F). fp64 and extents the kernel does not take (inner extents that are not multiples of
+16 bytes) also go to cuBLAS via torch; every such call is counted in ``stats["fallback"]`` and warned about once per reason.
 """
 from __future__ import annotations
 
@@ -12,6 +16,7 @@ from .. import _lib
 from ..parallel import param_sync as _param_sync
 
 _lib.declare("ab_gemm_bf16", "p p p i i i l l l i i i i i p p l p l p p i i l l i p")
+_lib.declare("ab_gemm_tf32", "p p p i i i l l l i i i p p l p l p i p")
 _lib.declare("ab_colsum", "p p p i i l i p")
 _lib.declare("ab_gemm_fp8", "p p p i i i l l l i i i i p p l f p p i p")
 _lib.declare("ab_fp8_quantize_dual", "p p p i i p p i i p")
@@ -37,9 +42,20 @@ def _note_fallback(why: str) -> None:
         warnings.warn(f"apex_b200.ops.gemm: library (cuBLAS) GEMM used instead of the tcgen05 kernel: {why}", stacklevel=3)
 
 
+def tf32_allowed() -> bool:
+    """fp32 operands may be multiplied as TF32: torch's own switch, overridable with APEX_B200_TF32=0/1."""
+    import os
+
+    env = os.environ.get("APEX_B200_TF32")
+    if env is not None:
+        return env not in ("0", "", "false", "False")
+    return bool(torch.backends.cuda.matmul.allow_tf32)
+
+
 def _native_ok(a: torch.Tensor, b: torch.Tensor) -> bool:
-    return (a.is_cuda and a.dtype in (torch.bfloat16, torch.float16) and a.dtype == b.dtype and _lib.available()
-            and a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1)
+    if not (a.is_cuda and a.dtype == b.dtype and _lib.available() and a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1):
+        return False
+    return a.dtype in (torch.bfloat16, torch.float16) or (a.dtype == torch.float32 and tf32_allowed())
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out_dtype=None, epi: int = EPI_NONE,
@@ -53,7 +69,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
             _param_sync.wait(a)
             _param_sync.wait(b)
         if a.is_cuda:
-            _note_fallback(f"{a.dtype} operands" if a.dtype not in (torch.bfloat16, torch.float16) else "non-unit inner stride / mixed dtypes")
+            if a.dtype == torch.float32 and b.dtype == torch.float32 and not tf32_allowed():
+                _note_fallback("fp32 operands with IEEE fp32 products requested (allow_tf32 is off): library SGEMM")
+            else:
+                _note_fallback(f"{a.dtype} operands" if a.dtype not in (torch.bfloat16, torch.float16, torch.float32)
+                               else "non-unit inner stride / mixed dtypes")
         return None
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
@@ -79,6 +99,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                 region.wait(b)
         if _param_sync.find(a) is not None:
             _param_sync.wait(a)
+    if a.dtype == torch.float32:
+        return _gemm_tf32(a, b, a_mn, b_mn, M, N, K, out, epi, bias, aux, c, colsum_out, sms)
     try:
         rc_ok = True
         _lib.fn("ab_gemm_bf16")(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
@@ -94,6 +116,28 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         _note_fallback(f"extents / leading dimensions not multiples of 8 (M={M}, N={N}, K={K})")
         return None
     stats["native"] += 1
+    return out
+
+
+def _gemm_tf32(a, b, a_mn, b_mn, M, N, K, out, epi, bias, aux, c, colsum_out, sms):
+    """fp32 operands on tcgen05.mma.kind::tf32; fp32 output / bias / aux / accumulate source."""
+    if out.dtype != torch.float32 or (aux is not None and aux.dtype != torch.float32):
+        _note_fallback("tf32 GEMM with a non-fp32 output")
+        return None
+    if _param_sync._regions:
+        _param_sync.wait(a)
+        _param_sync.wait(b)
+    try:
+        _lib.fn("ab_gemm_tf32")(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn),
+                                int(epi), _lib.ptr(bias), _lib.ptr(aux), aux.stride(0) if aux is not None else 0, _lib.ptr(c),
+                                c.stride(0) if c is not None else 0, _lib.ptr(colsum_out), int(sms), _lib.stream_ptr(a.device))
+    except RuntimeError as e:
+        if "bad argument (-10)" not in str(e):
+            raise
+        _note_fallback(f"fp32 extents / leading dimensions not multiples of 4 (M={M}, N={N}, K={K})")
+        return None
+    stats["native"] += 1
+    stats["tf32"] = stats.get("tf32", 0) + 1
     return out
 
 

@@ -263,3 +263,88 @@ def test_ffn_block_fp8_backward_close_to_bf16(cuda_dev):
     for a_, r_, name in zip(g8, g16, ("dx", "dw1", "db1", "dw2", "db2")):
         err = (a_.float() - r_.float()).norm() / r_.float().norm()
         assert err < 0.12, (name, float(err))
+
+
+# ---- fp32 operands as TF32 (tcgen05.mma.kind::tf32) -------------------------------------------------------------------------
+@pytest.fixture
+def allow_tf32():
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1536, 3072, 1024), (200, 328, 136), (4, 4, 4), (1000, 1000, 1000), (260, 516, 36)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_tf32_layouts(cuda_dev, allow_tf32, M, N, K, a_mn, b_mn):
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=cuda_dev)
+    B = torch.randn(N, K, device=cuda_dev)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    before = G.stats.get("tf32", 0)
+    d = G.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    assert d is not None and d.dtype == torch.float32, "tf32 GEMM refused an aligned fp32 problem"
+    assert G.stats.get("tf32", 0) == before + 1
+    ref = (A.double() @ B.double().t()).float()
+    assert _rel(d, ref) < 1.5e-3, _rel(d, ref)      # 10-bit mantissa products (truncated operands), fp32 accumulation
+    # the operands rounded to TF32 by hand must reproduce the kernel far more closely: the only error left is accumulation order
+    trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    rna = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    errs = [_rel(d, (f(A).double() @ f(B).double().t()).float()) for f in (trunc, rna)]
+    assert min(errs) < 1e-5, errs
+
+
+def test_gemm_tf32_epilogues(cuda_dev, allow_tf32):
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(1)
+    M, N, K = 520, 392, 264
+    x, w, bias = torch.randn(M, K, device=cuda_dev), torch.randn(N, K, device=cuda_dev) * 0.05, torch.randn(N, device=cuda_dev)
+    y = G.linear_fwd(x, w, bias)
+    assert _rel(y, x @ w.t() + bias) < 2e-3
+    aux = torch.empty(M, N, device=cuda_dev)
+    h = G.linear_fwd(x, w, bias, epi=G.EPI_BIAS_GELU, aux=aux)
+    pre = x.double() @ w.double().t() + bias.double()
+    assert _rel(aux, pre.float()) < 2e-3 and _rel(h, F.gelu(pre).float()) < 2e-3
+    dy = torch.randn(M, N, device=cuda_dev)
+    dx, db = G.linear_dgrad(dy, w, want_colsum=True)
+    assert _rel(dx, dy @ w) < 2e-3 and _rel(db, (dy @ w).sum(0)) < 2e-3
+    acc = torch.randn(N, K, device=cuda_dev)
+    ref = acc.double() + dy.double().t() @ x.double()
+    G.linear_wgrad(dy, x, accum_into=acc)
+    assert _rel(acc, ref.float()) < 2e-3
+
+
+def test_fused_dense_fp32_runs_on_the_tf32_kernel_when_allowed(cuda_dev, allow_tf32):
+    from apex_b200.fused_dense import FusedDenseGeluDense
+    from apex_b200.ops import gemm as G
+    torch.manual_seed(0)
+    g = FusedDenseGeluDense(512, 1024, 256).to(cuda_dev)
+    x = torch.randn(384, 512, device=cuda_dev, requires_grad=True)
+    xr = x.detach().double().requires_grad_(True)
+    ps = {n: p.detach().double().requires_grad_(True) for n, p in g.named_parameters()}
+    fb, t0 = G.stats["fallback"], G.stats.get("tf32", 0)
+    out = g(x)
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    assert G.stats["fallback"] == fb and G.stats.get("tf32", 0) >= t0 + 6      # 2 forward, 2 dgrad, 2 wgrad GEMMs, no library call
+    out_ref = F.linear(F.gelu(F.linear(xr, ps["weight1"], ps["bias1"])), ps["weight2"], ps["bias2"])
+    out_ref.backward(dy.double())
+    assert _rel(out, out_ref) < 3e-3 and _rel(x.grad, xr.grad) < 3e-3
+    for n, p in g.named_parameters():
+        assert _rel(p.grad, ps[n].grad) < 3e-3, n
+
+
+def test_fp32_without_tf32_is_an_announced_library_gemm(cuda_dev):
+    from apex_b200.ops import gemm as G
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        fb = G.stats["fallback"]
+        x, w = torch.randn(64, 64, device=cuda_dev), torch.randn(64, 64, device=cuda_dev)
+        y = G.linear_fwd(x, w)
+        assert G.stats["fallback"] == fb + 1
+        torch.testing.assert_close(y, x @ w.t())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
