@@ -1,5 +1,6 @@
 // apex_b200 — shared device utilities for the sm_100a kernels (torch-free; C ABI launchers live in the .cu files).
 #pragma once
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -33,28 +34,42 @@ template <> __device__ __forceinline__ double from_f<double>(float v) { return (
 // ---- V-element vector access (V*sizeof(T) is 16 or 32 bytes; issued as 16-byte LDG/STG) -------------------------
 template <typename T, int V> struct alignas(sizeof(T) * V > 16 ? 16 : sizeof(T) * V) Pack { T v[V]; };
 
+// V elements of type T packed in 32-bit words -> fp32. bf16 by hand: (w << 16) and (w & 0xffff0000) are ONE instruction per element; the
+// library conversion of the high half of a word compiles to a PRMT plus a shift, and the 16-bit row kernels are issue-bound before
+// they are byte-bound (LayerNorm forward: 19 issued instructions per element, profiles/ln_fwd_now.md).
+template <typename T, int V> __device__ __forceinline__ void words_to_float(const uint32_t* w, float (&r)[V]) {
+  if constexpr (std::is_same<T, bf16>::value && V % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < V / 2; q++) { r[2 * q] = __uint_as_float(w[q] << 16); r[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+  } else if constexpr (std::is_same<T, f16>::value && V % 2 == 0) {
+#pragma unroll
+    for (int q = 0; q < V / 2; q++) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+      r[2 * q] = t.x; r[2 * q + 1] = t.y;
+    }
+  } else {
+    const T* e = reinterpret_cast<const T*>(w);
+#pragma unroll
+    for (int i = 0; i < V; i++) r[i] = to_f<T>(e[i]);
+  }
+}
+
 template <typename T, int V>
 __device__ __forceinline__ void load_vec(float (&r)[V], const T* __restrict__ p) {
   constexpr int BYTES = sizeof(T) * V;
   static_assert(BYTES % 16 == 0 || BYTES == 8 || BYTES == 4, "vector width");
   if constexpr (BYTES == 4) {
     uint32_t raw = *reinterpret_cast<const uint32_t*>(p);
-    const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < V; i++) r[i] = to_f<T>(e[i]);
+    words_to_float<T, V>(&raw, r);
   } else if constexpr (BYTES == 8) {
     uint2 raw = *reinterpret_cast<const uint2*>(p);
-    const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-    for (int i = 0; i < V; i++) r[i] = to_f<T>(e[i]);
+    words_to_float<T, V>(reinterpret_cast<const uint32_t*>(&raw), r);
   } else {
     constexpr int N16 = BYTES / 16;
     uint4 raw[N16];
 #pragma unroll
     for (int i = 0; i < N16; i++) raw[i] = reinterpret_cast<const uint4*>(p)[i];
-    const T* e = reinterpret_cast<const T*>(raw);
-#pragma unroll
-    for (int i = 0; i < V; i++) r[i] = to_f<T>(e[i]);
+    words_to_float<T, V>(reinterpret_cast<const uint32_t*>(raw), r);
   }
 }
 

@@ -69,9 +69,7 @@ struct DistArgs {
 };
 
 template <typename T> __device__ __forceinline__ void unpack8(const uint4* raw, float (&f)[8]) {
-  const T* e = reinterpret_cast<const T*>(raw);
-#pragma unroll
-  for (int i = 0; i < 8; i++) f[i] = to_f<T>(e[i]);
+  words_to_float<T, 8>(reinterpret_cast<const uint32_t*>(raw), f);
 }
 
 __device__ __forceinline__ float lerp_f(float t, float x, float y) { return fmaf(t, y, fmaf(-t, x, x)); }

@@ -73,33 +73,10 @@ struct RowReducer {
 };
 
 template <typename T> __device__ __forceinline__ void unpack16(const uint4& raw, float (&r)[16 / sizeof(T)]) {
-  const T* e = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-  for (int i = 0; i < (int)(16 / sizeof(T)); i++) r[i] = to_f<T>(e[i]);
+  words_to_float<T, (int)(16 / sizeof(T))>(reinterpret_cast<const uint32_t*>(&raw), r);
 }
 
-// N elements of type T packed in 32-bit words -> fp32. bf16 by hand: (w << 16) and (w & 0xffff0000) are one instruction per element
-// (the library conversion of the high half is a PRMT + a shift); these kernels are issue-bound, not byte-bound, at 16 bits.
-template <typename T, int N> __device__ __forceinline__ void decode_words(const uint32_t* w, float (&f)[N]) {
-  if constexpr (sizeof(T) == 4) {
-#pragma unroll
-    for (int i = 0; i < N; i++) f[i] = __uint_as_float(w[i]);
-  } else if constexpr (sizeof(T) == 2 && N % 2 == 0) {
-#pragma unroll
-    for (int q = 0; q < N / 2; q++) {
-      if constexpr (std::is_same<T, bf16>::value) {
-        f[2 * q] = __uint_as_float(w[q] << 16); f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-      } else {
-        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
-        f[2 * q] = t.x; f[2 * q + 1] = t.y;
-      }
-    }
-  } else {
-    const T* e = reinterpret_cast<const T*>(w);
-#pragma unroll
-    for (int i = 0; i < N; i++) f[i] = to_f<T>(e[i]);
-  }
-}
+template <typename T, int N> __device__ __forceinline__ void decode_words(const uint32_t* w, float (&f)[N]) { words_to_float<T, N>(w, f); }
 __device__ __forceinline__ float rsqrt_fast(float v) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }  // v = var + eps > 0, never denormal
 
 struct NormCfg { int tpr, maxv, threads, rows_per_cta; bool ok; };
