@@ -79,6 +79,21 @@ def _use_stream(is_bwd: bool, x, G: int) -> bool:
     return bool(is_bwd) and H * W * (C // G) * x.element_size() >= 300 * 1024
 
 
+def _native_bwd(x, dy, weight, bias, mean, rstd, G, eps, silu):
+    """-> (dx, dgamma, dbeta). The slab / persistent kernels' last CTA writes dgamma / dbeta in the parameters' own dtype (no cast kernels:
+    the small shapes are launch-bound); the streaming kernels accumulate with fp32 atomics and are cast afterwards."""
+    dx = torch.empty_like(x)
+    C = x.shape[1]
+    fp32_out = _use_stream(True, x, G) or weight.dtype != bias.dtype
+    dt = torch.float32 if fp32_out else weight.dtype
+    dg = torch.empty(C, dtype=dt, device=x.device)
+    db = torch.empty(C, dtype=dt, device=x.device)
+    _launch(True, x, dy, dx, weight, bias, mean, rstd, dg, db, G, eps, silu)
+    if fp32_out:
+        dg, db = dg.to(weight.dtype), db.to(bias.dtype)
+    return dx, dg, db
+
+
 def _launch(is_bwd, x, dy, out, w, b, mean, rstd, dg, db, G, eps, silu):
     N, C, H, W = x.shape
     if _use_stream(is_bwd, x, G):
@@ -122,12 +137,8 @@ class GroupNormNHWC(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, bias, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dx = torch.empty_like(x)
-        C = x.shape[1]
-        dg = torch.empty(C, dtype=torch.float32, device=x.device)
-        db = torch.empty(C, dtype=torch.float32, device=x.device)
-        _launch(True, x, dy, dx, weight, bias, mean, rstd, dg, db, ctx.G, ctx.eps, ctx.silu)
-        return dx, None, dg.to(weight.dtype), db.to(bias.dtype), None, None
+        dx, dg, db = _native_bwd(x, dy, weight, bias, mean, rstd, ctx.G, ctx.eps, ctx.silu)
+        return dx, None, dg, db, None, None
 
 
 def group_norm_nhwc(x, G, weight, bias, eps=1e-5, act=""):
@@ -209,12 +220,7 @@ def group_norm_nhwc_bprop(grad_output, sums, x, G, weight, bias, eps, act=None, 
     act = act.lower() if act else ""
     if _native_ok(x, weight):
         dy = grad_output.contiguous(memory_format=torch.channels_last)
-        dx = torch.empty_like(x)
-        C = x.shape[1]
-        dg = torch.empty(C, dtype=torch.float32, device=x.device)
-        db = torch.empty(C, dtype=torch.float32, device=x.device)
-        _launch(True, x, dy, dx, weight, bias, sums[0], sums[1], dg, db, G, eps, act in ("silu", "swish"))
-        return dx, dg.to(weight.dtype), db.to(bias.dtype)
+        return _native_bwd(x, dy, weight, bias, sums[0], sums[1], G, eps, act in ("silu", "swish"))
     # explicit formulas (no autograd: this also runs underneath the autograd dispatch key, as the body of the custom op below)
     N, C = x.shape[0], x.shape[1]
     xf = x.float().reshape(N, G, C // G, -1)

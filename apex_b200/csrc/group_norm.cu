@@ -22,7 +22,7 @@ struct GnArgs {
   const void* gamma; const void* beta;   // [C] in the activation dtype or fp32 (w_fp32)
   int w_fp32;
   float* mean; float* rstd;               // [N, G]
-  float* dgamma; float* dbeta;            // [C] fp32 (bwd)
+  float* dgamma; float* dbeta;            // [C] (bwd): fp32 when w_fp32 or T is float, else T
   float* partial;                         // [N*C][S][3]
   float* chan;                            // [N*C][3] per-(n,c) merged values
   float* gsum;                            // [N*G][2] bwd: gamma-weighted group sums / M
@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(kGnThreads, 2) group_norm_kernel(GnArgs a) {
           for (int c = tid; c < C; c += kGnThreads) {
             float dg = 0.f, db = 0.f;
             for (int nn = 0; nn < a.N; nn++) { const float* cc = a.chan + ((size_t)nn * C + c) * 3; db += __ldcg(cc); dg += __ldcg(cc + 1); }
-            a.dgamma[c] = dg;
-            if (a.dbeta) a.dbeta[c] = db;
+            // parameter gradients in the parameters' own dtype (fp32 weights, or the activation type): no cast kernels afterwards
+            if (a.w_fp32 || sizeof(T) == 4) { a.dgamma[c] = dg; if (a.dbeta) a.dbeta[c] = db; }
+            else { reinterpret_cast<T*>(a.dgamma)[c] = from_f<T>(dg); if (a.dbeta) reinterpret_cast<T*>(a.dbeta)[c] = from_f<T>(db); }
           }
           if (tid == 0) a.ctrl[0] = 0u;
         }

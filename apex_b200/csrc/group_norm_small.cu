@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(kGsThreads, 2) gn_group_bwd(const T* __restric
       for (int c = threadIdx.x; c < C; c += kGsThreads) {
         float b = 0.f, gsum = 0.f;
         for (int nn = 0; nn < N; nn++) { b += __ldcg(chan + ((size_t)nn * C + c) * 2); gsum += __ldcg(chan + ((size_t)nn * C + c) * 2 + 1); }
-        dgamma[c] = gsum;
-        if (dbeta) dbeta[c] = b;
+        // parameter gradients in the parameters' own dtype (fp32 weights, or the activation type): no cast kernels afterwards
+        if (w_fp32 || sizeof(T) == 4) { dgamma[c] = gsum; if (dbeta) dbeta[c] = b; }
+        else { reinterpret_cast<T*>(dgamma)[c] = from_f<T>(gsum); if (dbeta) reinterpret_cast<T*>(dbeta)[c] = from_f<T>(b); }
       }
       if (threadIdx.x == 0) *ticket = 0u;
     }

@@ -12,7 +12,9 @@ import torch
 from .. import _lib
 from ..ops.amp_C import TensorTable
 
-CHUNK = 65536  # elements per work item (same granule as the reference's multi_tensor_applier)
+import os as _os
+
+CHUNK = int(_os.environ.get("APEX_B200_MT_CHUNK", 65536))  # elements per work item (default: the granule of the reference's multi_tensor_applier)
 
 
 class BucketCache:
