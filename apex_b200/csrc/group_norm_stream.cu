@@ -255,28 +255,34 @@ __global__ void __launch_bounds__(kGsT) gns_bwd_apply(const __grid_constant__ Gn
   }
 }
 
+// One FULL wave per kernel: the CTAs of these kernels live for a handful of loop iterations, so a grid that needs a second, partly
+// filled wave costs almost 2x (the first version sized the grid for 4 CTAs per SM while the kernels hold 77 - 126 registers, i.e. 2 - 3
+// resident CTAs: gns_stats took 44 us for 63 MB). Blocks per image = what the occupancy calculator says fits, divided over the batch.
+template <auto KERN> static int gns_blocks_per_image(const GnsArgs& a, int rpc) {
+  static int per_sm = 0;   // one copy per kernel (the kernel is the template argument)
+  if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KERN, kGsT, 0) != cudaSuccess || per_sm < 1)) per_sm = 2;
+  long long cap = (long long)kNumSMs * per_sm / (a.N > 0 ? a.N : 1);
+  long long blocks = ((long long)a.HW + rpc - 1) / rpc;   // at least one row per row-slot
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
 template <typename T, int V>
 static int gns_launch(const GnsArgs& a, int is_bwd, cudaStream_t st) {
   const int cols = gs_cols(a.C / V), rpc = kGsT / cols;
-  // every CTA issues 2 * C atomics at the end of pass 1 whatever it has read: give it >= 32 row-iterations (x kGsU rows) when the image
-  // is large enough, while keeping ~4 CTAs per SM over the whole batch for bandwidth
-  long long blocks = ((long long)a.HW + (long long)rpc * 8 - 1) / ((long long)rpc * 8);
-  long long cap = (long long)kNumSMs * 4 / (a.N > 0 ? a.N : 1);
-  if (cap < 1) cap = 1;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  const dim3 grid((unsigned)blocks, (unsigned)a.N);
   cudaError_t e = cudaMemsetAsync(a.chan, 0, sizeof(float) * 2 * (size_t)a.N * a.C, st);
   if (e != cudaSuccess) return (int)e;
+#define GNS_GO(KERN) { const dim3 grid((unsigned)gns_blocks_per_image<KERN>(a, rpc), (unsigned)a.N); KERN<<<grid, kGsT, 0, st>>>(a); }
   if (!is_bwd) {
-    gns_stats<T, V, false, false><<<grid, kGsT, 0, st>>>(a);
-    if (a.silu) gns_fwd_apply<T, V, true><<<grid, kGsT, 0, st>>>(a); else gns_fwd_apply<T, V, false><<<grid, kGsT, 0, st>>>(a);
+    GNS_GO((gns_stats<T, V, false, false>));
+    if (a.silu) GNS_GO((gns_fwd_apply<T, V, true>)) else GNS_GO((gns_fwd_apply<T, V, false>))
   } else {
     if (a.dgamma && (e = cudaMemsetAsync(a.dgamma, 0, sizeof(float) * a.C, st)) != cudaSuccess) return (int)e;
     if (a.dbeta && (e = cudaMemsetAsync(a.dbeta, 0, sizeof(float) * a.C, st)) != cudaSuccess) return (int)e;
-    if (a.silu) { gns_stats<T, V, true, true><<<grid, kGsT, 0, st>>>(a); gns_bwd_apply<T, V, true><<<grid, kGsT, 0, st>>>(a); }
-    else { gns_stats<T, V, true, false><<<grid, kGsT, 0, st>>>(a); gns_bwd_apply<T, V, false><<<grid, kGsT, 0, st>>>(a); }
+    if (a.silu) { GNS_GO((gns_stats<T, V, true, true>)); GNS_GO((gns_bwd_apply<T, V, true>)); }
+    else { GNS_GO((gns_stats<T, V, true, false>)); GNS_GO((gns_bwd_apply<T, V, false>)); }
   }
+#undef GNS_GO
   return (int)cudaGetLastError();
 }
 
