@@ -373,6 +373,146 @@ def _distopt_mods():
     }
 
 
+
+def _contrib_raw_mods():
+    """Raw-extension names of the contrib packages whose entry points map one-to-one onto this library's kernels (the reference's Python
+    modules drive exactly these calls): ``fused_conv_bias_relu`` (conv_bias_relu.py:13-94), ``group_norm_cuda`` / ``group_norm_v2_cuda``
+    (group_norm.py:75-141), ``transducer_joint_cuda`` / ``transducer_loss_cuda`` (transducer.py:190-300), ``nccl_p2p_cuda``
+    (csrc/nccl_p2p/nccl_p2p.cpp:20-28), ``_apex_nccl_allocator`` (NCCLAllocator.cpp:40), ``_apex_gpu_direct_storage`` (``_GDSFile``)."""
+    mods = {}
+
+    # ---- fused_conv_bias_relu: forward(inputs, padding, stride) -> [out]; backward([x, w, out, dy], ...) -> [dx, dw, db]
+    from .contrib.conv_bias_relu import conv_bias_relu as CB
+
+    def _conv_fwd(x, w, bias, scale, mask, padding, stride, relu):
+        ctx = _Ctx()
+        ctx.needs_input_grad = (False,) * 9
+        with torch.no_grad():
+            return CB.FusedConvEpilogue.forward(ctx, x, w, bias, scale, None, mask, stride, padding, relu)
+
+    def _conv_bwd(x, w, out, dy, scale, padding, stride, relu, want_bias):
+        dyc, xc, wc = CB._cl(dy), CB._cl(x), CB._cl(w)
+        sc32 = scale.detach().reshape(-1).float().contiguous() if scale is not None else None
+        g, _, dbias, _ = CB.epilogue_bwd(dyc, out if relu else None, None, None, sc32, relu, False, want_bias, False)
+        dx, dw, _ = torch.ops.aten.convolution_backward(g, xc, wc.to(xc.dtype), None, CB._pair(stride), CB._pair(padding), (1, 1), False, (0, 0), 1,
+                                                        (True, True, False))
+        return [dx, dw.to(w.dtype)] + ([dbias.reshape(1, -1, 1, 1).to(w.dtype)] if want_bias else [])
+
+    mods["fused_conv_bias_relu"] = _mod(
+        "fused_conv_bias_relu",
+        forward=lambda inputs, padding, stride: [_conv_fwd(inputs[0], inputs[1], inputs[2], None, None, padding, stride, True)],
+        forward_mask=lambda inputs, padding, stride: [_conv_fwd(inputs[0], inputs[1], inputs[2], None, inputs[3], padding, stride, True)],
+        forward_no_relu=lambda inputs, padding, stride: [_conv_fwd(inputs[0], inputs[1], inputs[2], None, None, padding, stride, False)],
+        forward_cscale_cbias_relu=lambda inputs, padding, stride: [_conv_fwd(inputs[0], inputs[1], inputs[3], inputs[2], None, padding, stride, True)],
+        backward=lambda inputs, padding, stride: _conv_bwd(inputs[0], inputs[1], inputs[2], inputs[3], None, padding, stride, True, True),
+        backward_no_relu=lambda inputs, padding, stride: _conv_bwd(inputs[0], inputs[1], None, inputs[2], None, padding, stride, False, True),
+        backward_cscale_cbias_relu=lambda inputs, padding, stride: _conv_bwd(inputs[0], inputs[1], inputs[3], inputs[4], inputs[2], padding, stride,
+                                                                             True, False))
+
+    # ---- group_norm_cuda (v1) / group_norm_v2_cuda: one kernel family serves both names
+    from .contrib.group_norm import group_norm as GN
+
+    def gn_forward(x, G, weight, bias, eps, passes, with_swish):
+        y, sums = GN.group_norm_nhwc_fprop(x, G, weight, bias, eps, "silu" if with_swish else "")
+        return y, sums.reshape(-1)
+
+    def gn_backward(grad_output, sums, x, G, weight, bias, eps, passes, with_swish):
+        return GN.group_norm_nhwc_bprop(grad_output, sums.reshape(2, -1), x, G, weight, bias, eps, "silu" if with_swish else "")
+
+    def gn_v2(x, weight, bias, eps, with_swish, G, mean_var_out=None, sm_margin=0):
+        y, sums = GN.group_norm_nhwc_fprop(x, G, weight, bias, eps, "silu" if with_swish else "")
+        if mean_var_out is not None:
+            mean_var_out.copy_(sums.reshape(-1))
+        return y
+
+    def gn_v2_bwd(grad_output, x, weight, bias, sums, eps, with_swish, G, sm_margin=0):
+        return GN.group_norm_nhwc_bprop(grad_output, sums.reshape(2, -1), x, G, weight, bias, eps, "silu" if with_swish else "")
+
+    mods["group_norm_cuda"] = _mod("group_norm_cuda", forward=gn_forward, backward=gn_backward)
+    mods["group_norm_v2_cuda"] = _mod("group_norm_v2_cuda", gn=gn_v2, gn_bwd=gn_v2_bwd)
+
+    # ---- transducer joint / loss
+    from .contrib.transducer import transducer as TR
+
+    def joint_forward(f, g, f_len, g_len, batch_offset, packed_batch, opt, pack_output, relu, dropout, dropout_prob, tile_size):
+        ctx = _Ctx()
+        p = float(dropout_prob) if dropout else 0.0
+        with torch.no_grad():
+            out = TR._JointFn.forward(ctx, f, g, f_len, g_len, batch_offset, packed_batch, bool(pack_output), bool(relu), p, None)
+        mask = ctx.saved_tensors[0]
+        return [out, mask.view(out.shape)] if mask is not None else [out]
+
+    def joint_backward(inputs, f_len, g_len, batch_offset, max_f_len, max_g_len, pack_output, scale):
+        dout = inputs[0]
+        mask = inputs[1].reshape(-1).to(torch.uint8) if len(inputs) > 1 else None
+        ctx = _Ctx()
+        B, H = f_len.shape[0], dout.shape[-1]
+        ctx.saved_tensors = (mask, TR._i32(f_len), TR._i32(g_len), batch_offset.to(torch.int64).contiguous() if pack_output else None)
+        ctx.dims = (B, int(max_f_len), int(max_g_len), H, bool(pack_output), float(scale))
+        with torch.no_grad():
+            return list(TR._JointFn.backward(ctx, dout)[:2])
+
+    def loss_forward(x, label, f_len, y_len, batch_offset, max_f_len, blank_idx, opt, packed_input):
+        """x: log-probabilities (the reference applies log_softmax first): their log-sum-exp is 0, so the logits kernel computes the same
+        alpha / beta / loss. -> (alpha, beta, loss)"""
+        ctx = _Ctx()
+        with torch.no_grad():
+            loss = TR._LossFn.forward(ctx, x, label, f_len, y_len, batch_offset, max_f_len, blank_idx, bool(packed_input))
+        return ctx.saved_tensors[2], ctx.saved_tensors[3], loss
+
+    def loss_backward(x, loss_grad, alpha, beta, f_len, y_len, label, batch_offset, max_f_len, blank_idx, opt, fuse_softmax_backward, packed_input):
+        if not fuse_softmax_backward:
+            raise NotImplementedError("transducer_loss_cuda.backward: only the fused softmax backward (gradient w.r.t. the logits) is provided; "
+                                      "use apex_b200.contrib.transducer.TransducerLoss for the unfused form")
+        ctx = _Ctx()
+        V = x.shape[-1]
+        B, T, U = alpha.shape
+        lse = torch.zeros(x.numel() // V, dtype=torch.float32, device=x.device)
+        ctx.saved_tensors = (x.contiguous(), lse, alpha, beta, TR._i32(label), TR._i32(f_len), TR._i32(y_len),
+                             batch_offset.to(torch.int64).contiguous() if packed_input else None)
+        ctx.dims = (B, T, U, V, int(blank_idx), int(bool(packed_input)))
+        with torch.no_grad():
+            return TR._LossFn.backward(ctx, loss_grad)[0]
+
+    mods["transducer_joint_cuda"] = _mod("transducer_joint_cuda", forward=joint_forward, backward=joint_backward)
+    mods["transducer_loss_cuda"] = _mod("transducer_loss_cuda", forward=loss_forward, backward=loss_backward)
+
+    # ---- communicator / allocator / storage modules: their Python modules already carry the raw entry points
+    from .contrib.nccl_p2p import nccl_p2p as NP
+
+    mods["nccl_p2p_cuda"] = _mod("nccl_p2p_cuda", get_unique_nccl_id=NP.get_unique_nccl_id, init_nccl_comm=NP.init_nccl_comm,
+                                 left_right_halo_exchange_inplace=NP.left_right_halo_exchange_inplace,
+                                 left_right_halo_exchange=NP.left_right_halo_exchange, add_delay=NP.add_delay)
+    from .contrib import gpu_direct_storage as GDS
+
+    class _GDSFile(GDS.GDSFile):
+        """The reference's pybind class is opened by its constructor and closed by ``close()`` (gpu_direct_storage/__init__.py:17-21)."""
+
+        def __init__(self, filename, mode):
+            super().__init__(filename, mode)
+            self.__enter__()
+
+        def close(self):
+            self.__exit__(None, None, None)
+
+    mods["_apex_gpu_direct_storage"] = _mod("_apex_gpu_direct_storage", _GDSFile=_GDSFile)
+    from .contrib.nccl_allocator import nccl_allocator as NA
+
+    def get_nccl_allocator():
+        """The pluggable allocator object behind ``create_nccl_mem_pool`` (reference NCCLAllocator.cpp:17-40): torch's NCCL ``mem_allocator``
+        when the build has one; the symmetric-heap pool of this library otherwise."""
+        import torch.distributed as dist
+
+        try:
+            backend = dist.distributed_c10d._get_default_group()._get_backend(torch.device("cuda"))
+            return backend.mem_allocator
+        except Exception:  # noqa: BLE001 - no process group / no NCCL allocator in this build
+            return NA.create_symmetric_mem_pool()
+
+    mods["_apex_nccl_allocator"] = _mod("_apex_nccl_allocator", get_nccl_allocator=get_nccl_allocator)
+    return mods
+
+
 class _Ctx:
     """Stand-in for an autograd context when a Function's forward / backward is driven directly."""
 
@@ -395,6 +535,12 @@ def extension_modules() -> dict:
     mods["fast_layer_norm"] = _fast_layer_norm_mod(mods["fused_layer_norm_cuda"])
     for group in (_dense_mods, _small_contrib_mods, _distopt_mods):
         mods.update(group())
+    try:
+        mods.update(_contrib_raw_mods())
+    except Exception as e:  # noqa: BLE001 - a contrib package that cannot be imported here must not take the core names down
+        import warnings
+
+        warnings.warn(f"apex_b200.ext_compat: contrib extension names not registered ({type(e).__name__}: {e})")
     try:
         from .contrib.optimizers import fused_adam_cuda
 

@@ -314,3 +314,62 @@ def test_every_submodule_imports():
         except Exception as e:  # noqa: BLE001
             failures.append((m.name, repr(e)))
     assert not failures, failures
+
+
+def test_contrib_raw_extension_names_cpu(tmp_path):
+    """The contrib extension names registered by ext_compat (fused_conv_bias_relu, group_norm_cuda / _v2_cuda, _apex_gpu_direct_storage,
+    nccl_p2p_cuda, _apex_nccl_allocator, transducer_*_cuda) with the reference's raw calling conventions; CPU tensors take the library's
+    PyTorch paths, so the list / tuple conventions and argument orders are what is checked here."""
+    from apex_b200 import ext_compat as E
+    m = E.extension_modules()
+    for name in ("fused_conv_bias_relu", "group_norm_cuda", "group_norm_v2_cuda", "transducer_joint_cuda", "transducer_loss_cuda", "nccl_p2p_cuda",
+                 "_apex_nccl_allocator", "_apex_gpu_direct_storage"):
+        assert name in m, name
+    torch.manual_seed(0)
+    cb = m["fused_conv_bias_relu"]
+    x = torch.randn(2, 8, 6, 6).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(16, 8, 3, 3).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(1, 16, 1, 1)
+    out = cb.forward([x, w, b], 1, 1)[0]
+    torch.testing.assert_close(out, torch.relu(torch.nn.functional.conv2d(x, w, b.reshape(-1), 1, 1)))
+    dy = torch.randn_like(out)
+    dx, dw, db = cb.backward([x, w, out, dy], 1, 1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.relu(torch.nn.functional.conv2d(xr, wr, br.reshape(-1), 1, 1)).backward(dy)
+    torch.testing.assert_close(dx, xr.grad)
+    torch.testing.assert_close(dw, wr.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(db, br.grad, atol=1e-4, rtol=1e-4)
+    out2 = cb.forward_no_relu([x, w, b], 1, 1)[0]
+    torch.testing.assert_close(out2, torch.nn.functional.conv2d(x, w, b.reshape(-1), 1, 1))
+    sc = torch.rand(1, 16, 1, 1) + 0.5
+    out3 = cb.forward_cscale_cbias_relu([x, w, sc, b], 1, 1)[0]
+    torch.testing.assert_close(out3, torch.relu(torch.nn.functional.conv2d(x, w, None, 1, 1) * sc + b))
+    g = cb.backward_cscale_cbias_relu([x, w, sc, out3, dy], 1, 1)
+    assert len(g) == 2 and g[0].shape == x.shape and g[1].shape == w.shape
+
+    gn = m["group_norm_cuda"]
+    xg = torch.randn(2, 8, 4, 4).contiguous(memory_format=torch.channels_last)
+    wg, bg = torch.randn(8), torch.randn(8)
+    y, sums = gn.forward(xg, 4, wg, bg, 1e-5, 1, True)
+    torch.testing.assert_close(y, torch.nn.functional.silu(torch.nn.functional.group_norm(xg, 4, wg, bg, 1e-5)))
+    assert sums.shape == (2 * 2 * 4,)
+    xr = xg.clone().requires_grad_(True)
+    wr, br2 = wg.clone().requires_grad_(True), bg.clone().requires_grad_(True)
+    torch.nn.functional.silu(torch.nn.functional.group_norm(xr, 4, wr, br2, 1e-5)).backward(torch.ones_like(y))
+    dxg, dwg, dbg = gn.backward(torch.ones_like(y), sums, xg, 4, wg, bg, 1e-5, 1, True)
+    torch.testing.assert_close(dxg, xr.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(dwg, wr.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(dbg, br2.grad, atol=1e-4, rtol=1e-4)
+    mv = torch.empty(16)
+    y2 = m["group_norm_v2_cuda"].gn(xg, wg, bg, 1e-5, True, 4, mean_var_out=mv)
+    torch.testing.assert_close(y2, y)
+    torch.testing.assert_close(mv, sums)
+    d2 = m["group_norm_v2_cuda"].gn_bwd(torch.ones_like(y), xg, wg, bg, mv, 1e-5, True, 4)
+    torch.testing.assert_close(d2[0], dxg)
+
+    F_ = m["_apex_gpu_direct_storage"]._GDSFile
+    path = str(tmp_path / "t.bin")
+    f = F_(path, "w"); t = torch.arange(10.); f.save_data(t); f.close()
+    f = F_(path, "r"); u = torch.empty(10); f.load_data(u); f.close()
+    assert torch.equal(t, u)
+    assert callable(m["nccl_p2p_cuda"].get_unique_nccl_id) and callable(m["_apex_nccl_allocator"].get_nccl_allocator)

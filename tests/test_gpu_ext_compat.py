@@ -218,3 +218,50 @@ def test_norm_modules_under_torch_compile_use_the_custom_ops(cuda_dev):
     out, want = cgn(img), gn(img)
     torch.testing.assert_close(out.float(), want.float(), atol=3e-2, rtol=3e-2)
     torch.testing.assert_close(torch.autograd.grad(out.float().sum(), img)[0].float(), torch.autograd.grad(want.float().sum(), img)[0].float(), atol=5e-2, rtol=5e-2)
+
+
+def test_contrib_raw_extension_names_gpu(cuda_dev, ext):
+    """fused_conv_bias_relu / group_norm_cuda / transducer_*_cuda raw entry points on the GPU kernels."""
+    cb, gn, tj, tl = ext("fused_conv_bias_relu"), ext("group_norm_cuda"), ext("transducer_joint_cuda"), ext("transducer_loss_cuda")
+    torch.manual_seed(0)
+    x = torch.randn(4, 32, 10, 10, device=cuda_dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 32, 3, 3, device=cuda_dev, dtype=torch.float16) * 0.1).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(1, 64, 1, 1, device=cuda_dev, dtype=torch.float16)
+    out = cb.forward([x, w, b], 1, 1)[0]
+    ref = torch.relu(F.conv2d(x.float(), w.float(), b.float().reshape(-1), 1, 1))
+    torch.testing.assert_close(out.float(), ref, atol=2e-2, rtol=2e-2)
+    dy = torch.randn_like(out)
+    dx, dw, db = cb.backward([x, w, out, dy], 1, 1)
+    g = dy.float() * (out > 0).float()
+    torch.testing.assert_close(db.float().reshape(-1), g.sum((0, 2, 3)), atol=0.5, rtol=2e-2)
+    assert dx.shape == x.shape and dw.shape == w.shape
+
+    xg = torch.randn(4, 64, 16, 16, device=cuda_dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wg, bg = torch.randn(64, device=cuda_dev, dtype=torch.bfloat16), torch.randn(64, device=cuda_dev, dtype=torch.bfloat16)
+    y, sums = gn.forward(xg, 16, wg, bg, 1e-5, 1, True)
+    torch.testing.assert_close(y.float(), F.silu(F.group_norm(xg.float(), 16, wg.float(), bg.float(), 1e-5)), atol=5e-2, rtol=5e-2)
+    dxg, dwg, dbg = gn.backward(torch.ones_like(y), sums, xg, 16, wg, bg, 1e-5, 1, True)
+    assert dxg.shape == xg.shape and dwg.dtype == wg.dtype and dbg.shape == bg.shape
+
+    B, T, U, H, V = 3, 11, 6, 64, 29
+    f, g2 = torch.randn(B, T, H, device=cuda_dev), torch.randn(B, U, H, device=cuda_dev)
+    f_len = torch.tensor([11, 7, 9], device=cuda_dev, dtype=torch.int32)
+    g_len = torch.tensor([6, 4, 5], device=cuda_dev, dtype=torch.int32)
+    h = tj.forward(f, g2, f_len, g_len, torch.empty(0, device=cuda_dev), 0, 1, False, True, False, 0.0, 4)
+    valid = (torch.arange(T, device=cuda_dev).view(1, T, 1) < f_len.view(B, 1, 1)) & (torch.arange(U, device=cuda_dev).view(1, 1, U) < g_len.view(B, 1, 1))
+    torch.testing.assert_close(h[0], torch.relu(f.unsqueeze(2) + g2.unsqueeze(1)) * valid.unsqueeze(-1))
+    df, dg = tj.backward([torch.ones_like(h[0]), h[1]], f_len, g_len, torch.empty(0, device=cuda_dev), T, U, False, 1.0)
+    torch.testing.assert_close(df, ((f.unsqueeze(2) + g2.unsqueeze(1) > 0) & valid.unsqueeze(-1)).float().sum(2))
+
+    from apex_b200.contrib.transducer.transducer import _TorchTransducerLoss
+    logits = torch.randn(B, T, U, V, device=cuda_dev)
+    label = torch.randint(1, V, (B, U - 1), device=cuda_dev, dtype=torch.int32)
+    y_len = g_len - 1
+    lp = torch.log_softmax(logits, -1)
+    alpha, beta, loss = tl.forward(lp, label, f_len, y_len, torch.empty(0, device=cuda_dev), T, 0, 1, False)
+    lr = logits.detach().clone().requires_grad_(True)
+    ref_loss = _TorchTransducerLoss.forward(_TorchTransducerLoss(), lr, label, f_len, y_len, 0)
+    torch.testing.assert_close(loss, ref_loss.detach(), atol=1e-3, rtol=1e-4)
+    ref_loss.sum().backward()
+    dxl = tl.backward(lp, torch.ones(B, device=cuda_dev), alpha, beta, f_len, y_len, label, torch.empty(0, device=cuda_dev), T, 0, 1, True, False)
+    torch.testing.assert_close(dxl, lr.grad, atol=1e-4, rtol=1e-3)
