@@ -32,6 +32,15 @@ elif what == "gemm":
     w = torch.randn(16384, 4096, device=dev, dtype=torch.bfloat16)
     for _ in range(4):
         G.gemm(x, w)
+elif what == "gemm_tf32":
+    from apex_b200.ops import gemm as G
+    torch.backends.cuda.matmul.allow_tf32 = True
+    x = torch.randn(8192, 4096, device=dev)
+    w = torch.randn(16384, 4096, device=dev)
+    dyy = torch.randn(8192, 16384, device=dev)
+    for _ in range(3):
+        G.gemm(x, w)
+        G.linear_wgrad(dyy, x)
 elif what == "layer_norm":
     from apex_b200.normalization import FusedLayerNorm
     m = FusedLayerNorm(4096).to(dev, torch.bfloat16)

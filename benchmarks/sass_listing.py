@@ -14,8 +14,9 @@ OUT = os.path.join(ROOT, "profiles", "sass")
 
 # object -> list of (regex on the demangled function name, short tag, marker mnemonics ranked)
 SELECT = {
-    "gemm_sm100.o": [(r"gemm2_kernel<__nv_bfloat16, 6, false>", "gemm2_bf16", ["UTCHMMA", "UTMALDG", "LDTM"]),
-                     (r"gemm2_kernel<__nv_bfloat16, 6, true>", "gemm2_fp8", ["UTCQMMA", "UTMALDG", "LDTM"]),
+    "gemm_sm100.o": [(r"gemm2_kernel<__nv_bfloat16, 6, 0>", "gemm2_bf16", ["UTCHMMA", "UTMALDG", "LDTM"]),
+                     (r"gemm2_kernel<__nv_bfloat16, 6, 1>", "gemm2_fp8", ["UTCQMMA", "UTMALDG", "LDTM"]),
+                     (r"gemm2_kernel<float, 6, 2>", "gemm2_tf32", ["UTCHMMA", "UTMALDG", "LDTM"]),
                      (r"gemm_kernel<__nv_bfloat16, 256, 4>", "gemm1_bf16", ["UTCHMMA", "UTMALDG", "LDTM"])],
     "fmha_fwd_sm100.o": [(r"fmha_fwd_kernel<__nv_bfloat16, 128>", "fmha_fwd_d128", ["UTCHMMA", "UTMALDG", "MUFU.EX2", "LDTM"])],
     "fmha_bwd_sm100.o": [(r"fmha_bwd_kernel<__nv_bfloat16, 128, true>", "fmha_bwd_dkv_d128", ["UTCHMMA", "UTMALDG", "MUFU.EX2", "LDTM"]),
@@ -31,8 +32,9 @@ SELECT = {
     "mt_basic.o": [(r"L2Norm", "mt_l2norm", ["LDG"]), (r"ScaleOp", "mt_scale", ["LDG", "STG"]), (r"Axpby", "mt_axpby", ["LDG", "STG"])],
     "mt_lamb_dist.o": [(r"LambStage1Op<false, 0>", "mt_lamb_stage1", ["LDG", "STG"]), (r"LambStage2Op<false", "mt_lamb_stage2", ["LDG", "STG"]),
                        (r"DistAdamOp<true>", "mt_dist_adam", ["LDG", "STG"])],
-    "layer_norm_fwd.o": [(r"__nv_bfloat16", "layer_norm_fwd_bf16", ["LDG", "STG"])],
-    "layer_norm_bwd.o": [(r"__nv_bfloat16", "layer_norm_bwd_bf16", ["LDG", "STG"])],
+    "layer_norm_fwd.o": [(r"ln_fwd_vec<4, __nv_bfloat16, __nv_bfloat16, false, false>", "layer_norm_fwd_bf16", ["LDG", "STG"])],
+    "layer_norm_bwd.o": [(r"ln_bwd_vec<2, __nv_bfloat16, __nv_bfloat16, false, false>", "layer_norm_bwd_bf16", ["LDG", "STG"])],
+    "group_norm_stream.o": [(r"gns_stats<__nv_bfloat16, 8, false, false>", "group_norm_stream_stats", ["LDG", "RED"])],
     "softmax.o": [(r"__nv_bfloat16", "softmax_bf16", ["MUFU.EX2", "LDG", "STG"])],
     "xentropy.o": [(r"__nv_bfloat16", "xentropy_bf16", ["MUFU", "LDG", "STG"])],
     "rope.o": [(r"__nv_bfloat16", "rope_bf16", ["LDG", "STG"])],
