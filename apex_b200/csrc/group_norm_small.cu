@@ -48,6 +48,10 @@ __device__ __forceinline__ void gs_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// A CTA may store into a peer's shared memory only once the peer is running: every cluster kernel ARRIVES at a cluster barrier first thing
+// and WAITS on it right before its first remote store (the loads in between hide the latency).
+__device__ __forceinline__ void gs_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gs_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void gs_st_cluster(float* local_addr, uint32_t cta, float v) {  // store into CTA `cta`'s copy of a shared variable
   uint32_t a = (uint32_t)__cvta_generic_to_shared(local_addr), ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
@@ -85,6 +89,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) gn_group_fwd(const T* __restric
   __shared__ float red[32];
   __shared__ float xs0[8], xs1[8];
   const uint32_t K = gs_cluster_size(), rank = gs_cluster_rank();
+  if (K > 1) gs_cluster_arrive();   // started: peers may write into this CTA's shared memory after their matching wait
   const int Cg = C / G, nchunk = Cg / VC, lanes = kGsThreads / nchunk;
   const int ng = blockIdx.x / K, n = ng / G, g = ng - n * G;
   const int row0 = (int)((long long)HW * rank / K), rows = (int)((long long)HW * (rank + 1) / K) - row0;
@@ -104,6 +109,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) gn_group_fwd(const T* __restric
     }
   }
   const float inv_m = 1.f / ((float)HW * (float)Cg);
+  if (K > 1) gs_cluster_wait();
   const float mu = gs_cluster_sum(gs_block_sum(s, red), xs0, K, rank) * inv_m;
   float ss = 0.f;
   if (active) {
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) gn_group_bwd(const T* __restric
   using Raw = typename ChunkN<T, VC>::Raw;
   extern __shared__ uint4 gs_smem_raw[];
   const uint32_t K = gs_cluster_size(), rank = gs_cluster_rank();
+  if (K > 1) gs_cluster_arrive();   // started: peers may write into this CTA's shared memory after their matching wait
   const int Cg = C / G, nchunk = Cg / VC, lanes = kGsThreads / nchunk;
   Raw* xs = reinterpret_cast<Raw*>(gs_smem_raw);
   Raw* gs = xs + (size_t)max_rows * nchunk;
@@ -188,6 +195,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) gn_group_bwd(const T* __restric
     }
   }
   __syncthreads();
+  if (K > 1) gs_cluster_wait();
   // per-channel sums of this CTA's rows -> slot [rank] of every cluster CTA's csum
   for (int c = threadIdx.x; c < Cg; c += kGsThreads) {
     float s0 = 0.f, s1 = 0.f;

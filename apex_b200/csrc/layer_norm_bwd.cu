@@ -40,6 +40,9 @@ __global__ void __launch_bounds__(512) ln_bwd_vec(const Tout* __restrict__ dy, c
     if (part_b) part_b += col0;
   }
   int xpar = 0;
+  // a CTA may store into its peer's shared memory only once the peer is running (compute-sanitizer racecheck: "located in a block that
+  // might not have entered yet"): one cluster barrier before the first exchange
+  if (cl == 2) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   const int nvec = n2 / E;
   const float inv_n = 1.f / (float)n_full;
   // per-thread dgamma / dbeta accumulators: registers, or (rows wider than 2 vectors per thread) this thread's private columns
