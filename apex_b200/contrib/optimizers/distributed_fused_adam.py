@@ -1045,11 +1045,97 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         st = self.param_groups[0].get("step", 0) if self.param_groups else 0
         return int(st.item()) if torch.is_tensor(st) else int(st)
 
-    def state_dict(self, *args, **kwargs):
-        """Every rank returns the same dict in the reference's v2 layout (:3059-3327): ``state["step"]`` plus, per parameter index,
+    def _state_dict_v1(self, gather_on_root: bool = True):
+        """Deprecated v1 format of the reference (:2907-3057): every rank serialises ITS OWN shard of the optimizer state
+        (``torch.save`` into bytes); the root rank returns ``{"gathered_states": [uint8 tensor per rank]}``, the other ranks ``None``.
+        Tied to the world size and bucket layout it was written with (load_state_dict checks both); v2 is the portable format."""
+        import io
+        import warnings
+
+        import torch.distributed as dist
+
+        warnings.warn("Making optimizer state dictionary in deprecated v1 format. Future support is not guaranteed.")
+        self.init_params()
+        self._join_overlap()
+        self._join_push()
+        if any(seg.scales is not None for seg in self._segments):
+            raise NotImplementedError("Deprecated v1 format does not support scaled state")
+        local = {"world": self.distributed_size, "rank": self.distributed_rank, "step": self._global_step(),
+                 "param_groups": [{k: (v.item() if torch.is_tensor(v) and v.numel() == 1 else v) for k, v in g.items() if k != "params"}
+                                  for g in self.param_groups],
+                 "segments": []}
+        for seg in self._segments:
+            ent = {"local_elems": int(seg.local_elems), "n_params": len(seg.params), "exp_avg": seg.exp_avg.detach().cpu(),
+                   "exp_avg_sq": seg.exp_avg_sq.detach().cpu()}
+            if seg.master is not None:
+                ent["master"] = seg.master.detach().cpu()
+            if seg.remainders is not None:
+                ent["remainders"] = seg.remainders.detach().cpu()
+            local["segments"].append(ent)
+        if not gather_on_root:
+            return local
+        buf = io.BytesIO()
+        torch.save(local, buf)
+        mine = torch.frombuffer(bytearray(buf.getvalue()), dtype=torch.uint8)
+        if self.distributed_size == 1:
+            return {"gathered_states": [mine], "format": 1}
+        gathered = [None] * self.distributed_size if self.distributed_rank == 0 else None
+        dist.gather_object(mine, gathered, dst=dist.get_global_rank(self.distributed_process_group, 0) if self.distributed_process_group is not None else 0,
+                           group=self.distributed_process_group)
+        return {"gathered_states": gathered, "format": 1} if self.distributed_rank == 0 else None
+
+    def _load_state_dict_v1(self, state_dict) -> None:
+        import io
+
+        import torch.distributed as dist
+
+        self.init_params()
+        self._join_overlap()
+        self._join_push()
+        if self.distributed_size > 1:   # the root holds everybody's bytes: hand each rank its own
+            mine = [None]
+            src = dist.get_global_rank(self.distributed_process_group, 0) if self.distributed_process_group is not None else 0
+            dist.scatter_object_list(mine, state_dict["gathered_states"] if self.distributed_rank == 0 else None, src=src, group=self.distributed_process_group)
+            blob = mine[0]
+        else:
+            blob = state_dict["gathered_states"][0]
+        local = torch.load(io.BytesIO(bytes(blob.numpy().tobytes())), weights_only=False)
+        if local["world"] != self.distributed_size or len(local["segments"]) != len(self._segments):
+            raise ValueError(f"v1 optimizer state was written by {local['world']} ranks / {len(local['segments'])} segments; this optimizer has "
+                             f"{self.distributed_size} / {len(self._segments)} (the v1 format cannot be resharded: save in the default v2 format)")
+        for seg, ent in zip(self._segments, local["segments"]):
+            if ent["local_elems"] != int(seg.local_elems) or ent["n_params"] != len(seg.params):
+                raise ValueError("v1 optimizer state does not match this optimizer's bucket layout")
+            seg.exp_avg.copy_(ent["exp_avg"])
+            seg.exp_avg_sq.copy_(ent["exp_avg_sq"])
+            if seg.master is not None and "master" in ent:
+                seg.master.copy_(ent["master"])
+            if seg.remainders is not None and "remainders" in ent:
+                seg.remainders.copy_(ent["remainders"])
+        for g, sg in zip(self.param_groups, local["param_groups"]):
+            for k, v in sg.items():
+                if self.capturable and k in ("lr", "step"):
+                    g[k].copy_(torch.as_tensor(v).reshape(1).to(g[k].dtype))
+                else:
+                    g[k] = v
+        for g in self.param_groups:
+            if self.capturable:
+                g["step"].fill_(int(local["step"]))
+            else:
+                g["step"] = int(local["step"])
+        # as in the reference, the model-dtype parameters themselves come from the MODEL's checkpoint; v1 restores the optimizer's shards
+        # (moments, fp32 master / remainder shards, step, hyper-parameters)
+
+    def state_dict(self, *args, state_dict_format=None, gather_on_root: bool = True, **kwargs):
+        """``state_dict_format=1``: the deprecated per-rank format (see :meth:`_state_dict_v1`). Default (2):
+        every rank returns the same dict in the reference's v2 layout (:3059-3327): ``state["step"]`` plus, per parameter index,
         full-size CPU tensors ``param`` (fp32 master), ``exp_avg``, ``exp_avg_sq`` — independent of world size and bucket layout, so it
         reloads under a different parallel configuration (and in the reference). The sharded state is streamed to the host in
         bounded pieces (double-buffered pinned staging), never materialised at full size on the GPU."""
+        if state_dict_format == 1:
+            return self._state_dict_v1(gather_on_root)
+        if state_dict_format not in (None, 2):
+            raise ValueError(f"Unrecognized state dict format ({state_dict_format})")
         self.init_params()
         self._join_overlap()
         self._join_push()
@@ -1137,6 +1223,8 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         slot[1] = None
 
     def load_state_dict(self, state_dict) -> None:
+        if state_dict is not None and "gathered_states" in state_dict or (state_dict is None and self.distributed_size > 1):
+            return self._load_state_dict_v1(state_dict)   # non-root ranks pass None, as they received it from state_dict()
         self.init_params()
         self._join_overlap()
         self._join_push()

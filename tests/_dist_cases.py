@@ -804,3 +804,42 @@ def spatial_bottleneck_matches_full(rank, world, device_type):
             g = p.grad.clone()
             dist.all_reduce(g)
             torch.testing.assert_close(g, q.grad, atol=10 * tol, rtol=10 * tol, msg=lambda m, n=n: f"{n}: {m}")
+
+
+def dist_adam_state_dict_v1_round_trip(rank, world, device_type):
+    """Deprecated v1 format (reference distributed_fused_adam.py:2907-3057): per-rank shards serialised to bytes and gathered on the root;
+    loading hands every rank its own shard back. Continue the original and a fresh optimizer on the same data: identical parameters."""
+    import copy
+    import warnings
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    model = _model(dev)
+    opt = DistributedFusedAdam(model.parameters(), lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20, weight_decay=0.01,
+                               fused_collectives=device_type == "cuda")
+    g = torch.Generator().manual_seed(11)
+
+    def one_step(m, o):
+        o.zero_grad()
+        x = torch.randn(5, 7, generator=g).to(dev)
+        m(x).pow(2).mean().backward()
+        o.step()
+
+    for _ in range(2):
+        one_step(model, opt)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sd = opt.state_dict(state_dict_format=1)
+    assert (sd is None) == (rank != 0)
+    if rank == 0:
+        assert sd["format"] == 1 and len(sd["gathered_states"]) == world and sd["gathered_states"][1].dtype == torch.uint8
+    model2 = copy.deepcopy(model)
+    opt2 = DistributedFusedAdam(model2.parameters(), lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20, weight_decay=0.01,
+                                fused_collectives=device_type == "cuda", process_group=dist.new_group(list(range(world))))
+    opt2.load_state_dict(sd)
+    state = g.get_state()
+    one_step(model, opt)
+    g.set_state(state)
+    one_step(model2, opt2)
+    for a, b in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(a, b)
+    assert opt2._global_step() == 3

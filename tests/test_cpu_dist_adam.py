@@ -55,6 +55,34 @@ def test_two_ranks_gloo_state_dict(tmp_path):
     run_distributed(cases.dist_adam_state_dict_reshards, 2, "cpu", str(tmp_path), backend="gloo")
 
 
+def test_two_ranks_gloo_state_dict_v1_round_trip():
+    run_distributed(cases.dist_adam_state_dict_v1_round_trip, 2, "cpu", backend="gloo")
+
+
+def test_state_dict_v1_single_rank_and_layout_check():
+    import warnings
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(40, 9)), torch.nn.Parameter(torch.randn(17))]
+    a = DistributedFusedAdam(ps, lr=1e-2, device="cpu")
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    a.step()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sd = a.state_dict(state_dict_format=1)
+    assert sd["format"] == 1 and len(sd["gathered_states"]) == 1
+    b = DistributedFusedAdam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1e-2, device="cpu")
+    b.load_state_dict(sd)
+    assert b._global_step() == 1
+    torch.testing.assert_close(b._segments[0].exp_avg, a._segments[0].exp_avg)
+    c = DistributedFusedAdam([torch.nn.Parameter(torch.randn(5))], lr=1e-2, device="cpu")
+    with pytest.raises(ValueError):
+        c.load_state_dict(sd)
+    with pytest.raises(ValueError):
+        a.state_dict(state_dict_format=3)
+
+
 def test_two_ranks_gloo_dist_lamb():
     run_distributed(cases.dist_lamb_matches_fused_lamb, 2, "cpu", backend="gloo")
 
