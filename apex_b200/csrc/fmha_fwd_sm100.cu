@@ -5,15 +5,17 @@
 //
 // One CTA per (128-query tile, head, sequence), 12 warps. Warp roles as in gemm_sm100.cu: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM
 // allocation, warps 4-11 softmax: TWO threads per query row (= TMEM lane; warps w and w + 4 share a lane quarter and take one 64-key
-// half of every tile each) — the softmax is instruction-issue bound, eight warps hide the TMEM-load / MUFU latencies that four could
+// half of every tile each) -- the softmax is instruction-issue bound, eight warps hide the TMEM-load / MUFU latencies that four could
 // not (ncu: 38 % issue utilisation with four). P is double buffered so the softmax of tile j + 1 overlaps the P V of tile j.
-// TWO PASSES over the keys instead of online-softmax rescaling (rescaling the TMEM accumulator costs a TMEM load + store per tile):
-//   pass 1  S = Q K_j^T (TMEM, double buffered) -> row maximum only (no exponentials)
-//   pass 2  S recomputed (K tiles come from L2), P = exp2((S - m) * scale * log2e) written as bf16/fp16 into shared memory in the
-//           128-byte-swizzled K-major layout a TMA load would produce, row sums accumulated in registers,
-//           O += P V_j accumulated in TMEM with no rescale; epilogue: O / l -> global, log-sum-exp optional.
-// The extra cost is one more QK^T per tile (tensor time is not the bottleneck of attention at d <= 128; exponentials are, and those
-// are computed once).
+// ONE pass over the keys, online softmax with LAZY rescaling (the first version made two passes: row maxima first, then a second
+// Q K^T per tile; that cost one extra MMA and one extra TMEM sweep per tile):
+//   * the two halves of a row are INDEPENDENT softmax streams: each thread keeps its own running maximum m and sum l over its 64-key
+//     half-tiles, and each half has its own accumulator O_h in TMEM (S double buffer 256 columns + 2 x d columns <= 512), so the two
+//     threads of a row never have to agree on a maximum; the epilogue merges O_0 * 2^(m_0 - m) + O_1 * 2^(m_1 - m);
+//   * P = exp2(S * scale * log2e - m_used); m_used only moves when the tile maximum exceeds it by more than 8 (a factor 256, harmless
+//     in fp32 accumulators and exact after the final division by l): then the thread waits for the previous P V to retire, multiplies
+//     its row of O_h by 2^(m_used - m_new) with a tcgen05.ld / tcgen05.st round trip and carries on -- after the first tiles this
+//     almost never happens, so the common tile costs one TMEM load of S, one maximum sweep, one exponential sweep.
 // Optional per-key additive bias [batch, seq_k] (key-padding masks: -inf / -10000 on padded keys) and Philox dropout on P
 // (fmha_common.cuh: the backward regenerates the same mask from (seed, offset)).
 #include "fmha_common.cuh"
@@ -106,19 +108,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_expect_tx(q_full, S::kQ);
       for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kQOff + i * (TQ * 128), &map_q, q_full, i * 64, head, q_row0 + qt * TQ);
       int ks = 0; uint32_t kph = 0; int vs = 0; uint32_t vph = 0;
-      for (int pass = 0; pass < 2; pass++) {
-        for (int j = 0; j < n_kv; j++) {
-          mbar_wait(&k_empty[ks], kph ^ 1, 101);
-          mbar_expect_tx(&k_full[ks], S::kKV);
-          for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kKOff + ks * S::kKV + i * (TK * 128), &map_k, &k_full[ks], i * 64, head, k_row0 + j * TK);
-          if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
-          if (pass == 1) {
-            mbar_wait(&v_empty[vs], vph ^ 1, 102);
-            mbar_expect_tx(&v_full[vs], S::kKV);
-            for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kVOff + vs * S::kKV + i * (TK * 128), &map_v, &v_full[vs], i * 64, head, k_row0 + j * TK);
-            if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
-          }
-        }
+      for (int j = 0; j < n_kv; j++) {
+        mbar_wait(&k_empty[ks], kph ^ 1, 101);
+        mbar_expect_tx(&k_full[ks], S::kKV);
+        for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kKOff + ks * S::kKV + i * (TK * 128), &map_k, &k_full[ks], i * 64, head, k_row0 + j * TK);
+        if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
+        mbar_wait(&v_empty[vs], vph ^ 1, 102);
+        mbar_expect_tx(&v_full[vs], S::kKV);
+        for (int i = 0; i < D / 64; i++) tma_load_3d(smem + S::kVOff + vs * S::kKV + i * (TK * 128), &map_v, &v_full[vs], i * 64, head, k_row0 + j * TK);
+        if (++vs == KV_STAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -146,8 +144,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (++ks == KV_STAGES) { ks = 0; kph ^= 1; }
       if (++sb == 2) { sb = 0; sph ^= 1; }
     };
-    for (int j = 0; j < n_kv; j++) issue_s();            // pass 1
-    if (n_kv > 0) issue_s();                             // pass 2, tile 0
+    if (n_kv > 0) issue_s();                             // tile 0
     for (int j = 0; j < n_kv; j++) {
       if (j + 1 < n_kv) issue_s();                       // S of the next tile overlaps the softmax of this one
       const int pb = j & 1;
@@ -157,10 +154,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (elect_one()) {
         const uint32_t v_addr = smem_u32(smem + S::kVOff + vs * S::kKV);
 #pragma unroll
-        for (int k = 0; k < TK / UMMA_K; k++) {
+        for (int k = 0; k < TK / UMMA_K; k++) {   // keys [0, 64) accumulate into O_0, keys [64, 128) into O_1 (independent softmax streams)
           const uint64_t adesc = make_desc(p_addr + pb * S::kP + (k >> 2) * (TQ * 128) + (k & 3) * 32, 16, 1024);
           const uint64_t bdesc = make_desc(v_addr + k * 2048, TK * 128, 1024);  // 16 key rows x 128 B per step; d blocks TK*128 B apart
-          umma_f16(tmem_o, adesc, bdesc, idesc_o, (j | k) ? 1u : 0u);
+          umma_f16(tmem_o + (uint32_t)((k >> 2) * D), adesc, bdesc, idesc_o, (j | (k & 3)) ? 1u : 0u);
         }
         umma_commit(&v_empty[vs]);
         umma_commit(&p_empty[pb]);
@@ -178,7 +175,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const bool row_ok = qi < q_len;
     const float sl2 = p.scale * 1.4426950408889634f;
     int sb = 0; uint32_t sph = 0;
-    float m = -INFINITY;                                    // row maximum of t = S * scale * log2(e) + bias * log2(e)
+    float m = -INFINITY;                                    // exponent offset in use for THIS thread's half: t = S * scale * log2(e) + bias * log2(e)
+    float l = 0.f;                                          // sum of exp2(t - m) over this half's keys so far
     float* bias_s = reinterpret_cast<float*>(smem + S::kBiasOff);
     const bool has_bias = p.key_bias != nullptr;
     auto stage_bias = [&](int j, int slot) {                // the 128 threads of one half stage one key each; double buffered, one barrier per tile
@@ -189,74 +187,83 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     auto key_ok = [&](int kidx) { return kidx < k_len && (!p.causal || kidx <= qi + diag); };
     // does key tile j contain a key that is masked for ANY row of this query tile (sequence tail, or the causal diagonal)?
     auto tile_masked = [&](int j) { return (j + 1) * TK > k_len || (p.causal && (j + 1) * TK - 1 > qt * TQ + diag); };
-    // ---- pass 1: row maximum
-    for (int j = 0; j < n_kv; j++) {
-      if (has_bias) stage_bias(j, j);
-      const float* bj = bias_s + (j & 1) * TK;
-      mbar_wait(&s_full[sb], sph, 120);
-      tc_fence_after();
-      // interior tiles (every key valid for every row of this query tile) skip the per-element predicates: they were half of the
-      // instructions the softmax warps issued (ncu: ISETP 25 %, FSEL 9 %, index adds 9 %)
-      const bool masked = tile_masked(j);
-#pragma unroll 1
-      for (int c0 = half * (TK / 2); c0 < (half + 1) * (TK / 2); c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
-        tmem_ld_wait();
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains instead of one 32-deep dependent one
-        if (!masked && !has_bias) {   // raw maximum, scaled once (scale > 0)
-#pragma unroll
-          for (int i = 0; i < 32; i++) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
-          m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const float t = has_bias ? fmaf(__uint_as_float(r[i]), sl2, bj[c0 + i]) : __uint_as_float(r[i]) * sl2;
-            if (!masked || key_ok(j * TK + c0 + i)) m4[i & 3] = fmaxf(m4[i & 3], t);
-          }
-          m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[sb]);
-      if (++sb == 2) { sb = 0; sph ^= 1; }
-    }
-    // the two threads of a row combine their partial maxima through the (still unused) first P buffer
-    float* xch = reinterpret_cast<float*>(smem + S::kPOff);
-    xch[half * TQ + row] = m;
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    m = fmaxf(xch[row], xch[TQ + row]);
-    asm volatile("bar.sync 2, 256;" ::: "memory");    // nobody overwrites the exchange area (P tile 0) before everybody has read it
-    if (m == -INFINITY) m = 0.f;  // fully masked row: every p becomes 0
-    // ---- pass 2: P = exp2(S * sl2 + bias2 - m), l = sum P, P -> shared memory (swizzled), O accumulated by the MMA warp
-    float l = 0.f;
     uint32_t peph[2] = {0, 0};
     const uint32_t bh = (uint32_t)(b * p.heads + head);
     const int comp_row = (qi & 1) * 2;
+    const uint32_t tmem_oh = tmem_o + (uint32_t)(half * D) + ((uint32_t)(q * 32) << 16);   // this thread's row of ITS half's accumulator
+    constexpr float kLazy = 8.f;                            // rescale only when the maximum grows by more than 2^8
     for (int j = 0; j < n_kv; j++) {
-      if (has_bias) stage_bias(j, n_kv + j);                  // keeps the (tile & 1) double-buffer parity running across the two passes
-      const float* bj = bias_s + ((n_kv + j) & 1) * TK;
+      if (has_bias) stage_bias(j, j);
+      const float* bj = bias_s + (j & 1) * TK;
       const int pb = j & 1;
       uint8_t* pbuf = smem + S::kPOff + pb * S::kP;
       const bool masked = tile_masked(j);
+      const int c_lo = half * (TK / 2);
       mbar_wait(&s_full[sb], sph, 121);
-      mbar_wait(&p_empty[pb], peph[pb] ^ 1, 122);  // the PV that last read this P buffer has finished (first use: passes immediately)
       tc_fence_after();
+      // ---- this thread's 64 scores, once
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c_lo), r0);
+      tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c_lo + 32), r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[sb]);                            // S is in registers: the next Q K^T may overwrite this buffer
+      // ---- tile maximum (scaled domain)
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (!masked && !has_bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) { m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r0[i])); m4[(i + 2) & 3] = fmaxf(m4[(i + 2) & 3], __uint_as_float(r1[i])); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) m4[i] *= sl2;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float t0 = has_bias ? fmaf(__uint_as_float(r0[i]), sl2, bj[c_lo + i]) : __uint_as_float(r0[i]) * sl2;
+          const float t1 = has_bias ? fmaf(__uint_as_float(r1[i]), sl2, bj[c_lo + 32 + i]) : __uint_as_float(r1[i]) * sl2;
+          if (!masked || key_ok(j * TK + c_lo + i)) m4[i & 3] = fmaxf(m4[i & 3], t0);
+          if (!masked || key_ok(j * TK + c_lo + 32 + i)) m4[(i + 2) & 3] = fmaxf(m4[(i + 2) & 3], t1);
+        }
+      }
+      const float m_tile = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      // ---- lazy rescale of this half's accumulator row
+      const bool grow = m_tile > m + kLazy || (m == -INFINITY && m_tile > -INFINITY);
+      if (__any_sync(0xffffffffu, grow)) {
+        const float f = grow ? (m == -INFINITY ? 0.f : ex2_approx(m - m_tile)) : 1.f;
+        if (j > 0) {                                        // O_h holds the tiles before this one: wait until P V (j - 1) has retired
+          mbar_wait(&p_empty[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1), 124);
+          tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * (TK / 2); c0 < (half + 1) * (TK / 2); c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * TK + c0), r);
-        tmem_ld_wait();
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_oh + (uint32_t)c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tmem_oh + (uint32_t)c0, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        l *= f;
+        if (grow) m = m_tile;
+      }
+      const float off = m == -INFINITY ? 0.f : m;           // nothing valid yet in this half: every p below is exp2(-inf) = 0
+      mbar_wait(&p_empty[pb], peph[pb] ^ 1, 122);           // the P V that last read this P buffer has finished (first use: passes immediately)
+      // ---- P = exp2(t - m), row sum, P -> shared memory (swizzled)
+#pragma unroll
+      for (int hseg = 0; hseg < 2; hseg++) {
+        const uint32_t (&r)[32] = hseg == 0 ? r0 : r1;
+        const int c0 = c_lo + hseg * 32;
         float pv[32];
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         if (!masked && !has_bias) {
-          const float nm = -m;
+          const float nm = -off;
 #pragma unroll
           for (int i = 0; i < 32; i++) { const float e = ex2_approx(fmaf(__uint_as_float(r[i]), sl2, nm)); pv[i] = e; l4[i & 3] += e; }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i++) {
-            const float e = (!masked || key_ok(j * TK + c0 + i)) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, (has_bias ? bj[c0 + i] : 0.f) - m)) : 0.f;
+            const float e = (!masked || key_ok(j * TK + c0 + i)) ? ex2_approx(fmaf(__uint_as_float(r[i]), sl2, (has_bias ? bj[c0 + i] : 0.f) - off)) : 0.f;
             pv[i] = e; l4[i & 3] += e;
           }
         }
@@ -278,36 +285,41 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           *reinterpret_cast<uint4*>(pbuf + (c >> 6) * (TQ * 128) + sw128_offset(row, c & 63)) = h8;
         }
       }
-      tc_fence_before();
       fence_proxy_async();          // generic-proxy stores to shared memory -> visible to the tensor-core (async) proxy
       mbar_arrive(&p_full[pb]);
-      mbar_arrive(&s_empty[sb]);
       peph[pb] ^= 1;
       if (++sb == 2) { sb = 0; sph ^= 1; }
     }
-    // ---- epilogue: O / l
+    // ---- epilogue: merge the two halves' streams, O = (O_0 * 2^(m_0 - m) + O_1 * 2^(m_1 - m)) / (l_0 * 2^(m_0 - m) + l_1 * 2^(m_1 - m))
     if (n_kv > 0) { mbar_wait(o_full, 0, 123); tc_fence_after(); }
-    // every MMA has completed: the P buffers are free again; the two threads of a row add their partial row sums through one of them
-    xch[half * TQ + row] = l;
+    // every MMA has completed: the P buffers are free again; the two threads of a row exchange (m, l) through one of them
+    float* xch = reinterpret_cast<float*>(smem + S::kPOff);
+    xch[half * TQ + row] = m;
+    xch[2 * TQ + half * TQ + row] = l;
     asm volatile("bar.sync 2, 256;" ::: "memory");
-    l = xch[row] + xch[TQ + row];
-    const float inv_l = l > 0.f ? (p.has_drop ? p.drop.rp : 1.f) / l : 0.f;
+    const float m0 = xch[row], m1 = xch[TQ + row], l0 = xch[2 * TQ + row], l1 = xch[3 * TQ + row];
+    const float mm = fmaxf(m0, m1);
+    const float f0 = m0 == -INFINITY ? 0.f : ex2_approx(m0 - mm), f1 = m1 == -INFINITY ? 0.f : ex2_approx(m1 - mm);
+    const float lt = l0 * f0 + l1 * f1;
+    const float inv_l = lt > 0.f ? (p.has_drop ? p.drop.rp : 1.f) / lt : 0.f;
+    const float g0 = f0 * inv_l, g1 = f1 * inv_l;
     T* orow = reinterpret_cast<T*>(p.out) + (size_t)(q_row0 + qi) * p.out_row_stride + (size_t)head * p.out_head_stride;
+    const uint32_t tmem_row = tmem_o + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int c0 = half * (D / 2); c0 < (half + 1) * (D / 2); c0 += 32) {
-      uint32_t r[32];
-      if (n_kv > 0) { tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r); tmem_ld_wait(); }
+      uint32_t ra[32], rb[32];
+      if (n_kv > 0) { tmem_ld32(tmem_row + (uint32_t)c0, ra); tmem_ld32(tmem_row + (uint32_t)(D + c0), rb); tmem_ld_wait(); }
       if (row_ok) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
           float o8[8];
 #pragma unroll
-          for (int e = 0; e < 8; e++) o8[e] = n_kv > 0 ? __uint_as_float(r[i + e]) * inv_l : 0.f;
+          for (int e = 0; e < 8; e++) o8[e] = n_kv > 0 ? fmaf(__uint_as_float(ra[i + e]), g0, __uint_as_float(rb[i + e]) * g1) : 0.f;
           store_vec<T, 8>(orow + c0 + i, o8);
         }
       }
     }
-    if (row_ok && p.lse && half == 0) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = l > 0.f ? m * 0.6931471805599453f + logf(l) : -INFINITY;
+    if (row_ok && p.lse && half == 0) p.lse[(size_t)(q_row0 + qi) * p.heads + head] = lt > 0.f ? mm * 0.6931471805599453f + logf(lt) : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
