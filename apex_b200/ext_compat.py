@@ -510,7 +510,71 @@ def _contrib_raw_mods():
             return NA.create_symmetric_mem_pool()
 
     mods["_apex_nccl_allocator"] = _mod("_apex_nccl_allocator", get_nccl_allocator=get_nccl_allocator)
+    mods["permutation_search_cuda"] = _perm_search_mod()
     return mods
+
+
+def _perm_search_mod():
+    """``permutation_search_cuda`` (reference apex/contrib/sparsity/permutation_search_kernels/CUDA_kernels/permutation_search_kernels.cu:
+    625-631): four entry points over flat numpy buffers; results are written into the caller's output arrays and 0 is returned. The launch
+    geometry arguments of ``sum_after_2_to_4`` (blocks, threads) are accepted and ignored. Runs on csrc/perm_search.cu when a GPU is
+    present, on the PyTorch forms of the same scores otherwise."""
+    import numpy as np
+
+    from .contrib.sparsity import permutation_search as PS
+
+    def _dev():
+        from . import _lib
+
+        return torch.device("cuda") if (torch.cuda.is_available() and _lib.available()) else torch.device("cpu")
+
+    def _matrix(buf, rows, cols):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(buf, dtype=np.float32))).view(int(rows), int(cols)).to(_dev())
+
+    def sum_after_2_to_4(matrix, rows, cols, start_col, end_col, blocks, threads, output):
+        m = _matrix(matrix, rows, cols)[:, int(start_col):int(end_col)].contiguous()
+        output[0] = float(PS.sum_after_2_to_4(m))
+        return 0
+
+    def build_permute_map(matrix, rows, cols, stripes, num_groups, group_width, permutations, perm_length, improvements, best_indices):
+        m = _matrix(matrix, rows, cols)
+        groups = torch.from_numpy(np.asarray(stripes, dtype=np.int64).reshape(int(num_groups), int(group_width)).astype(np.int32)).to(m.device)
+        cands = np.asarray(permutations, dtype=np.int64).reshape(-1, int(perm_length)).astype(np.uint8 if int(perm_length) <= 255 else np.int32)
+        imp, idx = PS._score_groups(m, groups, cands)
+        improvements[:int(num_groups)] = imp.float().cpu().numpy()
+        best_indices[:int(num_groups)] = idx.cpu().numpy().astype(np.uint32)
+        return 0
+
+    def check_permutations(matrix, rows, cols, stripe_groups, group_width, num_groups, permutations, num_permutations, improvement, permutation):
+        m = _matrix(matrix, rows, cols)
+        sg = np.asarray(stripe_groups, dtype=np.int64).reshape(int(num_groups), int(group_width))
+        perms = np.asarray(permutations, dtype=np.int64).reshape(int(num_permutations), -1)
+        for g in range(int(num_groups)):
+            colsel = torch.from_numpy((sg[g][:, None] * 4 + np.arange(4)).reshape(-1)).to(m.device)
+            sub = m[:, colsel].contiguous()
+            base = float(PS.sum_after_2_to_4(sub))
+            scores = PS.sum_after_2_to_4(sub, torch.from_numpy(perms.astype(np.int32)).to(m.device))
+            best = int(torch.argmax(scores))
+            improvement[g] = float(scores[best]) - base
+            permutation[g] = best
+        return 0
+
+    def build_swap_map(matrix, rows, cols, stripe_pairs, output):
+        m = _matrix(matrix, rows, cols).abs()
+        pairs = np.asarray(stripe_pairs, dtype=np.int64).reshape(-1, 2)
+        kept = lambda t: t.reshape(t.shape[0], -1, 4).topk(2, dim=-1).values.sum()   # noqa: E731
+        for i, (s0, s1) in enumerate(pairs):
+            c = torch.cat([m[:, s0 * 4:s0 * 4 + 4], m[:, s1 * 4:s1 * 4 + 4]], 1)    # [rows, 8]
+            base = float(kept(c))
+            for k in range(16):
+                a, b = k // 4, 4 + k % 4
+                sw = c.clone()
+                sw[:, [a, b]] = c[:, [b, a]]
+                output[i * 16 + k] = float(kept(sw)) - base
+        return 0
+
+    return _mod("permutation_search_cuda", sum_after_2_to_4=sum_after_2_to_4, build_permute_map=build_permute_map,
+                check_permutations=check_permutations, build_swap_map=build_swap_map)
 
 
 class _Ctx:

@@ -373,3 +373,39 @@ def test_contrib_raw_extension_names_cpu(tmp_path):
     f = F_(path, "r"); u = torch.empty(10); f.load_data(u); f.close()
     assert torch.equal(t, u)
     assert callable(m["nccl_p2p_cuda"].get_unique_nccl_id) and callable(m["_apex_nccl_allocator"].get_nccl_allocator)
+
+
+def test_permutation_search_cuda_raw_entry_points():
+    """``permutation_search_cuda`` with the reference's numpy-buffer conventions (results written into the caller's arrays)."""
+    import numpy as np
+    from apex_b200 import ext_compat as E
+    from apex_b200.contrib.sparsity.permutation_search import generate_all_unique_combinations
+    m = E.extension_modules()["permutation_search_cuda"]
+    rng = np.random.default_rng(0)
+    M = rng.standard_normal((16, 16)).astype(np.float32)
+
+    def kept(x):
+        return float(sum(np.sort(np.abs(x[r, c:c + 4]))[2:].sum() for r in range(x.shape[0]) for c in range(0, x.shape[1], 4)))
+
+    out = np.zeros(1, dtype=np.float32)
+    assert m.sum_after_2_to_4(M.flatten(), 16, 16, 0, 16, 2, 4, out) == 0
+    assert abs(out[0] - kept(M)) < 1e-3
+    m.sum_after_2_to_4(M.flatten(), 16, 16, 4, 12, 2, 4, out)
+    assert abs(out[0] - kept(M[:, 4:12])) < 1e-3
+    perms = generate_all_unique_combinations(8, 4)
+    imp, idx = np.zeros(2, dtype=np.float32), np.zeros(2, dtype=np.uint32)
+    m.build_permute_map(M.flatten(), 16, 16, np.array([0, 1, 2, 3], dtype=np.uint32), 2, 2, perms.astype(np.uint32).flatten(), 8, imp, idx)
+    for g, lo in enumerate((0, 8)):
+        sub = M[:, lo:lo + 8]
+        assert abs(imp[g] - (max(kept(sub[:, p]) for p in perms) - kept(sub))) < 1e-3
+        assert abs(kept(sub[:, perms[idx[g]]]) - kept(sub) - imp[g]) < 1e-3
+    imp1, pi = np.zeros(1, dtype=np.float32), np.zeros(1, dtype=np.uint32)
+    m.check_permutations(M.flatten(), 16, 16, np.array([0, 1], dtype=np.uint32), 2, 1, perms.astype(np.uint32).flatten(), len(perms), imp1, pi)
+    assert abs(imp1[0] - imp[0]) < 1e-3 and pi[0] == idx[0]
+    o = np.zeros(16, dtype=np.float32)
+    m.build_swap_map(M.flatten(), 16, 16, np.array([0, 1], dtype=np.uint32), o)
+    for k in (0, 5, 15):
+        c = M[:, :8].copy()
+        a, b = k // 4, 4 + k % 4
+        c[:, [a, b]] = c[:, [b, a]]
+        assert abs(o[k] - (kept(c) - kept(M[:, :8]))) < 1e-3
