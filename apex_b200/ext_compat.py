@@ -511,7 +511,59 @@ def _contrib_raw_mods():
 
     mods["_apex_nccl_allocator"] = _mod("_apex_nccl_allocator", get_nccl_allocator=get_nccl_allocator)
     mods["permutation_search_cuda"] = _perm_search_mod()
+    mods["fmhalib"] = _fmhalib_mod()
     return mods
+
+
+def _fmhalib_mod():
+    """``fmhalib`` (reference apex/contrib/csrc/fmha/fmha_api.cpp:86-127 as driven by apex/contrib/fmha/fmha.py:47-90): ``fwd`` / ``fwd_nl``
+    return ``(context, S_dmask)`` and ``bwd`` / ``bwd_nl`` take ``S_dmask`` back. The reference materialises the dropout-masked softmax in
+    ``S_dmask``; the kernels here recompute the probabilities from the log-sum-exp, so ``S_dmask`` is an OPAQUE fp32 state tensor (row
+    log-sum-exp, the forward output and the Philox counters) that is only meaningful when handed back to ``bwd``. No sequence-length or
+    head-dimension limit of the reference applies (head dim 64 / 128 on the tcgen05 kernels)."""
+    from .contrib.fmha import kernels as K
+
+    def _pack(lse, out, philox):
+        meta = torch.tensor([philox[0] & 0xFFFFFFFF, (philox[0] >> 32) & 0xFFFFFFFF, philox[1] & 0xFFFFFFFF, (philox[1] >> 32) & 0xFFFFFFFF,
+                             lse.numel(), out.numel()], dtype=torch.int64, device=lse.device).to(torch.int32)
+        return torch.cat([meta.view(torch.float32), lse.reshape(-1).float(), out.reshape(-1).float()])
+
+    def _unpack(state, like):
+        meta = state[:6].view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        m = [int(v) for v in meta.tolist()]
+        n_lse, n_out = m[4], m[5]
+        total, h, d = like.shape[0], like.shape[2], like.shape[3]
+        lse = state[6:6 + n_lse].view(total, h)
+        out = state[6 + n_lse:6 + n_lse + n_out].view(total, h, d).to(like.dtype)
+        return lse, out, (m[0] | (m[1] << 32), m[2] | (m[3] << 32))
+
+    def fwd(qkv, cu_seqlens, p_dropout, max_s, is_training, is_nl, zero_tensors, generator=None):
+        total, three, h, d = qkv.shape
+        if not K.supported(qkv, d):
+            raise RuntimeError("fmhalib: fp16 / bf16 CUDA tensors with head dim 64 or 128 are required (use apex_b200.contrib.fmha.FMHA for the generic path)")
+        p = float(p_dropout) if is_training else 0.0
+        cu = cu_seqlens if cu_seqlens.dtype == torch.int32 else cu_seqlens.to(torch.int32)
+        philox = K.next_philox(qkv.device) if p > 0.0 else (0, 0)
+        out, lse = K.fmha_fwd(qkv[:, 0], qkv[:, 1], qkv[:, 2], cu_seqlens_q=cu, cu_seqlens_k=cu, max_seqlen_q=int(max_s), seqlen_k=int(max_s),
+                              return_lse=True, dropout_p=p, philox=philox)
+        return out, _pack(lse, out, philox)
+
+    def bwd(dout, qkv, S_dmask, cu_seqlens, p_dropout, max_s, zero_tensors):
+        lse, out, philox = _unpack(S_dmask, qkv)
+        cu = cu_seqlens if cu_seqlens.dtype == torch.int32 else cu_seqlens.to(torch.int32)
+        p = float(p_dropout) if philox != (0, 0) else 0.0
+        dq, dk, dv = K.fmha_bwd(dout.contiguous(), qkv[:, 0], qkv[:, 1], qkv[:, 2], out, lse, cu_seqlens_q=cu, cu_seqlens_k=cu, max_seqlen_q=int(max_s),
+                                max_seqlen_k=int(max_s), dropout_p=p, philox=philox)
+        return torch.stack([dq, dk, dv], 1), None
+
+    def fwd_nl(qkv, cu_seqlens, p_dropout, max_s, is_training, is_nl, zero_tensors, generator=None):
+        return fwd(qkv, cu_seqlens, p_dropout, max_s, is_training, is_nl, zero_tensors, generator)
+
+    def bwd_nl(dout, qkv, S_dmask, cu_seqlens, p_dropout, max_s, zero_tensors):
+        dqkv, dp = bwd(dout, qkv, S_dmask, cu_seqlens, p_dropout, max_s, zero_tensors)
+        return dqkv, dp, None
+
+    return _mod("fmhalib", fwd=fwd, bwd=bwd, fwd_nl=fwd_nl, bwd_nl=bwd_nl)
 
 
 def _perm_search_mod():

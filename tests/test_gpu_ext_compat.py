@@ -265,3 +265,27 @@ def test_contrib_raw_extension_names_gpu(cuda_dev, ext):
     ref_loss.sum().backward()
     dxl = tl.backward(lp, torch.ones(B, device=cuda_dev), alpha, beta, f_len, y_len, label, torch.empty(0, device=cuda_dev), T, 0, 1, True, False)
     torch.testing.assert_close(dxl, lr.grad, atol=1e-4, rtol=1e-3)
+
+
+def test_fmhalib_raw_entry_points(cuda_dev, ext):
+    """fmhalib.fwd / bwd (packed qkv, cu_seqlens) against autograd through contrib.fmha; S_dmask is an opaque state tensor here."""
+    mha = ext("fmhalib")
+    from apex_b200.contrib.fmha.fmha import fmha_varlen
+    torch.manual_seed(0)
+    h, d = 4, 64
+    lens = [37, 128, 5, 200]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    qkv = torch.randn(sum(lens), 3, h, d, device=cuda_dev, dtype=torch.float16, requires_grad=True)
+    ctx, state = mha.fwd(qkv.detach(), cu, 0.0, max(lens), True, False, False, None)
+    ref = fmha_varlen(qkv, cu, max(lens), 0.0, True)
+    torch.testing.assert_close(ctx, ref.detach())
+    dout = torch.randn_like(ctx)
+    ref.backward(dout)
+    dqkv, dp = mha.bwd(dout, qkv.detach(), state, cu, 0.0, max(lens), False)
+    torch.testing.assert_close(dqkv, qkv.grad)
+    # dropout: the backward regenerates the forward's mask from the counters carried in the state tensor
+    ctx2, state2 = mha.fwd_nl(qkv.detach(), cu, 0.2, max(lens), True, True, False, None)
+    dq2, _, _ = mha.bwd_nl(dout, qkv.detach(), state2, cu, 0.2, max(lens), False)
+    assert torch.isfinite(dq2).all() and (ctx2 - ctx).abs().max() > 0
+    dq3, _, _ = mha.bwd_nl(dout, qkv.detach(), state2, cu, 0.2, max(lens), False)
+    torch.testing.assert_close(dq2, dq3)          # deterministic
