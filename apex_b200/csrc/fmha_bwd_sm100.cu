@@ -73,7 +73,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constan
   float* stat = reinterpret_cast<float*>(smem + S::kStatOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ot = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  // causal dQ: the last query tiles have the most key tiles -- heaviest first (dK / dV already is: key tile 0 meets every query tile)
+  const int ot = (!DKV && p.causal) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int q_row0 = p.cu_seqlens_q ? p.cu_seqlens_q[b] : b * p.seq_q;
   const int q_len = p.cu_seqlens_q ? p.cu_seqlens_q[b + 1] - q_row0 : p.seq_q;
   const int k_row0 = p.cu_seqlens_k ? p.cu_seqlens_k[b] : b * p.seq_k;

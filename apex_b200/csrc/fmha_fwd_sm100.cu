@@ -74,7 +74,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  // causal: the last query tiles have the most key tiles; launching them first (blocks are issued in increasing blockIdx.x) keeps the
+  // light tiles for the tail of the grid. The query tiles of one (head, sequence) stay adjacent, so their K / V tiles still meet in L2.
+  const int qt = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int q_row0 = p.cu_seqlens_q ? p.cu_seqlens_q[b] : b * p.seq_q;
   const int q_len = p.cu_seqlens_q ? p.cu_seqlens_q[b + 1] - q_row0 : p.seq_q;
   const int k_row0 = p.cu_seqlens_k ? p.cu_seqlens_k[b] : b * p.seq_k;
