@@ -11,8 +11,11 @@ Design here: CHANNEL SPACES. The model is symbolically traced and every tensor v
     along with the space.
   * flatten after a convolution keeps the space but records that every channel now covers `rep` consecutive columns of the next
     Linear (the reference's replicate_sequence case).
+  * a concatenation along the channel axis is a list of (space, offset, size) parts: the Linear / Conv / BatchNorm that consumes it is a
+    consumer (rider) of EVERY part through the matching slice of its weight, so each input keeps its own permutation (the reference's
+    fixup_concats case); parts whose offset or size is not a multiple of 4 would move the 2:4 groups and are frozen instead.
   * anything that mixes or exposes channel order (graph inputs and outputs, reshapes, matmuls, grouped convolutions, GroupNorm,
-    LocalResponseNorm, concatenation, slicing, unknown modules and functions) FREEZES the spaces it touches.
+    LocalResponseNorm, slicing, unknown modules and functions) FREEZES the spaces it touches.
 Every unfrozen space with at least one prunable consumer is one search problem: the consumers' weights are stacked row-wise (the
 reference's sibling group), one permutation is searched (csrc/perm_search.cu), applied to every consumer's input-channel dim and to
 every producer / pass-through tensor's channel dim (the reference's coparent group + K_passthru chain). Residual networks and
@@ -97,16 +100,53 @@ class _Val:
     """A traced tensor value: its channel space, where the channel axis is (1: N,C,spatial...; -1: last dim), the tensor rank when it is
     known (conv outputs), whether the spatial extent is known to be 1, and how many flattened columns each channel covers."""
 
-    __slots__ = ("space", "axis", "rank", "spatial1", "rep")
+    __slots__ = ("space", "axis", "rank", "spatial1", "rep", "size")
 
-    def __init__(self, space, axis, rank=None, spatial1=False, rep=1):
-        self.space, self.axis, self.rank, self.spatial1, self.rep = space, axis, rank, spatial1, rep
+    def __init__(self, space, axis, rank=None, spatial1=False, rep=1, size=None):
+        self.space, self.axis, self.rank, self.spatial1, self.rep, self.size = space, axis, rank, spatial1, rep, size
 
     def like(self, **kw):
-        v = _Val(self.space, self.axis, self.rank, self.spatial1, self.rep)
+        v = _Val(self.space, self.axis, self.rank, self.spatial1, self.rep, self.size)
         for k, x in kw.items():
             setattr(v, k, x)
         return v
+
+
+class _Cat:
+    """A traced concatenation along the channel axis: ``parts`` = [(value, channels)] in order."""
+
+    __slots__ = ("parts", "axis", "rank")
+
+    def __init__(self, parts, axis, rank):
+        self.parts, self.axis, self.rank = parts, axis, rank
+
+    def freeze(self, why):
+        for v, _ in self.parts:
+            v.space.freeze(why)
+
+
+class _Slice:
+    """Stands in for a module in a consumer / rider entry: the tensors are the [off, off + size) slice along ``dim`` of the owner's."""
+
+    __slots__ = ("owner", "dim", "off", "size")
+
+    def __init__(self, owner, dim, off, size):
+        self.owner, self.dim, self.off, self.size = owner, dim, off, size
+
+
+def _t(m, attr):
+    """The tensor behind a consumer / rider entry (a view for slices: in-place writes reach the parameter)."""
+    if isinstance(m, _Slice):
+        return getattr(m.owner, attr).narrow(m.dim, m.off, m.size)
+    return getattr(m, attr)
+
+
+def _base(m, attr):
+    return getattr(m.owner if isinstance(m, _Slice) else m, attr)
+
+
+def _tkey(m, attr, dim):
+    return (id(_base(m, attr)), dim, m.off if isinstance(m, _Slice) else -1)
 
 
 def _expand(perm, rep):
@@ -167,7 +207,7 @@ class Permutation:
     @classmethod
     def apply_permutation_in_C_dim(cls, module, perm, attr="weight", dim=1, rep=1):
         """Permute the input channels of a Linear / Conv (dim 1 of the weight; each channel covering `rep` columns after a flatten)."""
-        cls._permute_tensor(getattr(module, attr), dim, _expand(perm, rep))
+        cls._permute_tensor(_t(module, attr), dim, _expand(perm, rep))
 
     @classmethod
     def apply_permutation_in_K_dim(cls, module, perm):
@@ -230,6 +270,8 @@ class Permutation:
                 v = vals.get(a)
                 if isinstance(v, _Val):
                     v.space.freeze(why)
+                elif isinstance(v, _Cat):
+                    v.freeze(why)
                 elif isinstance(v, tuple):
                     for x in v:
                         if isinstance(x, _Val):
@@ -261,6 +303,8 @@ class Permutation:
         def join(node, operands, why):
             """Elementwise combination of tensor operands (some may be raw get_attr tensors riding on another operand's space)."""
             tvals = [vals.get(a) for a in operands if isinstance(a, fx.Node)]
+            if any(isinstance(v, _Cat) for v in tvals):
+                return opaque(node, why + " on a concatenation")
             real = [v for v in tvals if isinstance(v, _Val)]
             attrs = [a for a in operands if isinstance(a, fx.Node) and a.op == "get_attr"]
             if not real:
@@ -300,6 +344,39 @@ class Permutation:
             elif node.op == "call_module":
                 m = mods[node.target]
                 src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
+                if isinstance(src, _Cat):
+                    # consumer / pass-through of a channel concatenation: one sliced entry per part
+                    aligned = all(sz % 4 == 0 for _, sz in src.parts)
+                    if isinstance(m, _CONVS + (nn.Linear,)) and (not isinstance(m, _CONVS) or m.groups == 1) and aligned and id(m) not in first_use \
+                            and src.axis == (1 if isinstance(m, _CONVS) else -1):
+                        first_use[id(m)] = (None, None)
+                        off = 0
+                        for v, sz in src.parts:
+                            v.space.find().consumers.append((_Slice(m, 1, off, sz), "weight", 1, 1, True, node.target, sz))
+                            off += sz
+                        out = new_space()
+                        out.riders.append((m, "weight", 0, node.target))
+                        if m.bias is not None:
+                            out.riders.append((m, "bias", 0, node.target))
+                        is_conv = isinstance(m, _CONVS)
+                        vals[node] = _Val(out, 1 if is_conv else -1, m.weight.dim() if is_conv else None,
+                                          size=m.out_channels if is_conv else m.out_features)
+                    elif isinstance(m, _BN_MODULES) and src.axis == 1 and id(m) not in first_use:
+                        first_use[id(m)] = (None, None)
+                        off = 0
+                        for v, sz in src.parts:
+                            for name in ("weight", "bias", "running_mean", "running_var"):
+                                t = getattr(m, name, None)
+                                if torch.is_tensor(t) and t.dim() == 1 and not isinstance(t, (nn.parameter.UninitializedParameter, nn.parameter.UninitializedBuffer)):
+                                    v.space.find().riders.append((_Slice(m, 0, off, sz), name, 0, node.target))
+                            off += sz
+                        vals[node] = src
+                    elif isinstance(m, _PASS_MODULES) or (isinstance(m, _SPATIAL_MODULES) and src.axis == 1):
+                        vals[node] = src
+                    else:
+                        src.freeze(f"{type(m).__name__} at {node.target} on a concatenation")
+                        vals[node] = _Val(new_space("consumer of a frozen concatenation"), None)
+                    continue
                 if isinstance(m, _CONVS + (nn.Linear,)):
                     is_conv = isinstance(m, _CONVS)
                     cin = m.in_channels if is_conv else m.in_features
@@ -321,7 +398,7 @@ class Permutation:
                             out.riders.append((m, "weight", 0, node.target))
                             if m.bias is not None:
                                 out.riders.append((m, "bias", 0, node.target))
-                        vals[node] = _Val(out, 1 if is_conv else -1, rank)
+                        vals[node] = _Val(out, 1 if is_conv else -1, rank, size=cout)
                     elif groups == cin and cout == cin:   # depthwise: per-channel filter, channels pass straight through
                         if not reuse(m, src.space, None):
                             src.space.find().riders.append((m, "weight", 0, node.target))
@@ -340,12 +417,12 @@ class Permutation:
                         out.riders.append((m, "weight", 1, node.target))
                         if m.bias is not None:
                             out.riders.append((m, "bias", 0, node.target))
-                    vals[node] = _Val(out, 1, m.weight.dim())
+                    vals[node] = _Val(out, 1, m.weight.dim(), size=m.out_channels)
                 elif isinstance(m, nn.Embedding):
                     out = new_space()
                     if not reuse(m, None, out):
                         out.riders.append((m, "weight", 1, node.target))
-                    vals[node] = _Val(out, -1)
+                    vals[node] = _Val(out, -1, size=m.embedding_dim)
                 elif isinstance(m, _BN_MODULES):
                     if not isinstance(src, _Val) or src.axis not in (1, -1):
                         opaque(node, f"normalisation {node.target} on an unknown layout")
@@ -411,7 +488,7 @@ class Permutation:
                         out.riders.append((m.out_proj, "weight", 0, node.target + ".out_proj"))
                         if m.out_proj.bias is not None:
                             out.riders.append((m.out_proj, "bias", 0, node.target + ".out_proj"))
-                    vals[node] = (_Val(out, -1), None)
+                    vals[node] = (_Val(out, -1, size=m.embed_dim), None)
                 elif isinstance(m, _PASS_MODULES):
                     if isinstance(src, _Val):
                         vals[node] = src.like()
@@ -436,6 +513,20 @@ class Permutation:
                         vals[node] = None
                 elif tgt is getattr:
                     vals[node] = None   # x.shape and friends
+                elif tgt in (torch.cat, torch.concat, torch.concatenate):
+                    items = node.args[0] if node.args else node.kwargs.get("tensors", ())
+                    dim = node.kwargs.get("dim", node.args[1] if len(node.args) > 1 else 0)
+                    parts = [vals.get(a) for a in items if isinstance(a, fx.Node)]
+                    ok = len(parts) == len(items) and len(parts) > 0 and all(isinstance(v, _Val) and v.size is not None and v.rep == 1 for v in parts)
+                    if ok:
+                        axis = parts[0].axis
+                        ok = all(v.axis == axis for v in parts) and ((axis == 1 and dim == 1) or (axis == -1 and dim == -1))
+                    if ok:
+                        vals[node] = _Cat([(v, v.size) for v in parts], parts[0].axis, parts[0].rank)
+                    else:
+                        opaque(node, "concatenation that is not along the channel axis of known-size values")
+                elif tgt in _UNARY_FUNCS and node.args and isinstance(vals.get(node.args[0]), _Cat):
+                    vals[node] = vals[node.args[0]]
                 elif tgt in _UNARY_FUNCS:
                     src = vals.get(node.args[0]) if node.args and isinstance(node.args[0], fx.Node) else None
                     if isinstance(src, _Val):
@@ -484,7 +575,7 @@ class Permutation:
     @staticmethod
     def _space_size(space):
         for owner, name, dim, _ in space.riders:
-            return getattr(owner, name).shape[dim]
+            return _t(owner, name).shape[dim]
         return None
 
     @classmethod
@@ -494,12 +585,12 @@ class Permutation:
         if C is None or C % 4 != 0:
             return False, C, []
         for owner, name, dim, _ in space.riders:
-            t = getattr(owner, name, None)
+            t = _t(owner, name)
             if t is None or t.shape[dim] != C:
                 return False, C, []
         cons = []
         for m, attr, dim, rep, prunable, where, cin in space.consumers:
-            w = getattr(m, attr)
+            w = _t(m, attr)
             if rep is None:   # flattened [C, spatial...]: each channel covers in_features / C consecutive columns
                 if w.shape[dim] % C != 0:
                     return False, C, []
@@ -515,8 +606,8 @@ class Permutation:
         sparse = cls.__sparse_parameters
         mats = []
         for m, attr, dim, rep, prunable, _ in cons:
-            w = getattr(m, attr)
-            if not prunable or (sparse is not None and not any(w is p for p in sparse)):
+            w = _t(m, attr)
+            if not prunable or (sparse is not None and not any(_base(m, attr) is p for p in sparse)):
                 continue
             w2 = w.detach().movedim(dim, -1).reshape(-1, w.shape[dim]).float()    # [rows, C * rep], channel-major columns
             if rep > 1:
@@ -574,18 +665,17 @@ class Permutation:
                 continue
             seen = set()
             for m, attr, dim, rep, _, _ in cons:
-                if (id(getattr(m, attr)), dim) in seen:
+                if _tkey(m, attr, dim) in seen:
                     continue
-                seen.add((id(getattr(m, attr)), dim))
+                seen.add(_tkey(m, attr, dim))
                 cls.apply_permutation_in_C_dim(m, perm, attr, dim, rep)
                 cls.__stats["C"] += 1
             seen = set()
             for owner, name, dim, _ in space.riders:
-                t = getattr(owner, name)
-                if id(t) in seen:      # a module reused at several call sites rides once
+                if _tkey(owner, name, dim) in seen:      # a module reused at several call sites rides once
                     continue
-                seen.add(id(t))
-                cls._permute_tensor(t, dim, idx.long())
+                seen.add(_tkey(owner, name, dim))
+                cls._permute_tensor(_t(owner, name), dim, idx.long())
                 cls.__stats["K"] += 1
             report.append((len(cons), before, after))
             dumped.append({"consumers": [c[5] for c in cons], "riders": sorted({f"{r[3]}.{r[1]}" for r in space.riders}), "channels": C,

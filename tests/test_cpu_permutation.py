@@ -140,11 +140,46 @@ def test_broadcast_module_attribute_rides_along():
     _check(M(), torch.randn(2, 8, 5, 5), (1, 3))
 
 
-def test_concat_and_untraceable_models_are_left_alone():
-    class Cat(nn.Module):
+def test_concatenation_permutes_each_part_through_its_slice():
+    class Cat(nn.Module):       # two producers concatenated, BatchNorm over the concatenation, one consumer
         def __init__(self):
             super().__init__()
-            self.a, self.b, self.c = nn.Conv2d(8, 16, 1), nn.Conv2d(8, 16, 1), nn.Conv2d(32, 16, 1)
+            self.a, self.b, self.bn, self.c = nn.Conv2d(8, 16, 1), nn.Conv2d(8, 32, 1), nn.BatchNorm2d(48), nn.Conv2d(48, 16, 1)
+
+        def forward(self, x):
+            return self.c(F.relu(self.bn(torch.cat([self.a(x), self.b(x)], 1))))
+
+    class Dense(nn.Module):     # DenseNet style: later layers consume the concatenation of every earlier output
+        def __init__(self):
+            super().__init__()
+            self.stem, self.l1, self.l2, self.head = nn.Conv2d(3, 16, 3, padding=1), nn.Conv2d(16, 16, 3, padding=1), nn.Conv2d(32, 16, 3, padding=1), nn.Conv2d(48, 8, 1)
+
+        def forward(self, x):
+            a = F.relu(self.stem(x))
+            b = F.relu(self.l1(a))
+            c = F.relu(self.l2(torch.cat([a, b], 1)))
+            return self.head(torch.cat([a, b, c], 1))
+
+    class LinCat(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = nn.Linear(8, 16), nn.Linear(8, 16), nn.Linear(32, 4)
+
+        def forward(self, x):
+            return self.c(torch.cat([F.gelu(self.a(x)), self.b(x)], -1))
+
+    # Cat: each part = one slice of c's columns (2 C) + producer weight, bias and 4 BatchNorm tensors (2 x 6 K)
+    _check(Cat(), torch.randn(2, 8, 5, 5), (2, 12), min_groups=2)
+    # Dense: a feeds l1, l2[:, 0:16], head[:, 0:16]; b feeds l2[:, 16:32], head[:, 16:32]; c feeds head[:, 32:48]
+    _check(Dense(), torch.randn(2, 3, 6, 6), (6, 6), min_groups=3)
+    _check(LinCat(), torch.randn(3, 8), (2, 4), min_groups=2)
+
+
+def test_unaligned_concat_and_untraceable_models_are_left_alone():
+    class Odd(nn.Module):       # parts of 10 and 22 channels: a per-part permutation would move the consumer's groups of 4
+        def __init__(self):
+            super().__init__()
+            self.a, self.b, self.c = nn.Conv2d(8, 10, 1), nn.Conv2d(8, 22, 1), nn.Conv2d(32, 16, 1)
 
         def forward(self, x):
             return self.c(torch.cat([self.a(x), self.b(x)], 1))
@@ -157,7 +192,7 @@ def test_concat_and_untraceable_models_are_left_alone():
         def forward(self, x):
             return self.a(x) if x.sum() > 0 else x
 
-    _check(Cat(), torch.randn(2, 8, 5, 5), (0, 0))
+    _check(Odd(), torch.randn(2, 8, 5, 5), (0, 0))
     _check(Branchy(), torch.randn(3, 8), (0, 0))
 
 
