@@ -103,6 +103,39 @@ def test_transformer_block_with_mha():
     _check(Block(), torch.randn(2, 6, 8), (4, 12), min_groups=2)
 
 
+def test_hand_written_attention_keeps_the_residual_stream_permutable():
+    """HF-style block: q / k / v outputs go through view / transpose / matmul (their OUTPUT spaces freeze), but their input -- the residual
+    stream -- is one space over the embedding, every LayerNorm, q / k / v / fc1 / lm-head columns and out-proj / fc2 rows of all layers."""
+    import math
+
+    class Block(nn.Module):
+        def __init__(self, H=32, heads=4):
+            super().__init__()
+            self.h = heads
+            self.ln1, self.q, self.k, self.v, self.o = nn.LayerNorm(H), nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+            self.ln2, self.f1, self.f2 = nn.LayerNorm(H), nn.Linear(H, 4 * H), nn.Linear(4 * H, H)
+
+        def forward(self, x):
+            B, S, H = x.shape
+            a = self.ln1(x)
+            q, k, v = (lin(a).view(B, S, self.h, H // self.h).transpose(1, 2) for lin in (self.q, self.k, self.v))
+            att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(H // self.h), -1) @ v
+            x = x + self.o(att.transpose(1, 2).reshape(B, S, H))
+            return x + self.f2(F.gelu(self.f1(self.ln2(x))))
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb, self.b1, self.b2, self.lnf, self.head = nn.Embedding(50, 32), Block(), Block(), nn.LayerNorm(32), nn.Linear(32, 50)
+
+        def forward(self, ids):
+            return self.head(self.lnf(self.b2(self.b1(self.emb(ids)))))
+
+    torch.manual_seed(0)
+    rep = _check(Model(), torch.randint(0, 50, (2, 7)), (11, 23), min_groups=3)
+    assert sorted(r[0] for r in rep) == [1, 1, 9]
+
+
 def test_flatten_after_conv_permutes_blocks_of_columns():
     class Fl(nn.Module):
         def __init__(self):
