@@ -1,5 +1,5 @@
-"""GPU paths of the extension-name shims (apex_b200/ext_compat.py). Written after the round's GPU budget was spent, so they are opt-in until
-they have run once on a B200:  APEX_B200_UNVERIFIED_TESTS=1 python -m pytest tests/test_gpu_ext_compat.py -m gpu"""
+"""GPU paths of the extension-name shims (apex_b200/ext_compat.py): the reference's raw entry points (argument order, return conventions)
+on this library's kernels. Part of the default `pytest -m gpu` run (they were opt-in in round 1, before they had ever run on a B200)."""
 import importlib
 import os
 

@@ -183,3 +183,63 @@ def test_fused_adam_swa_single_launch(cuda_dev, mode):
             torch.testing.assert_close(p32[i].detach(), ref_p[i], rtol=1e-5, atol=1e-6)
             torch.testing.assert_close(swa[i].detach(), ref_swa[i], rtol=1e-5, atol=1e-6)
             torch.testing.assert_close(pbf[i].detach().float(), ref_p[i].bfloat16().float(), rtol=0, atol=0)
+
+
+def test_legacy_contrib_optimizers_on_gpu(cuda_dev):
+    """Deprecated contrib optimizers on the multi-tensor kernels (reference apex/contrib/optimizers/{fused_adam,fp16_optimizer}.py): explicit
+    ``grads`` / ``scale`` step, FP16_Optimizer master-weight round trip with a static loss scale, state_dict round trip."""
+    from apex_b200.contrib.optimizers import FP16_Optimizer, FusedAdam
+    from apex_b200.optimizers import FusedAdam as FA
+    p = torch.nn.Parameter(torch.ones(1000, device=cuda_dev))
+    o = FusedAdam([p], lr=0.1)
+    o.step(grads=[torch.full((1000,), 4.0, device=cuda_dev)], scale=2.0)
+    torch.testing.assert_close(p.detach(), torch.full((1000,), 0.9, device=cuda_dev))
+    torch.manual_seed(0)
+    m = torch.nn.Linear(64, 64).to(cuda_dev).half()
+    ref = torch.nn.Linear(64, 64).to(cuda_dev)
+    with torch.no_grad():
+        ref.weight.copy_(m.weight.float())
+        ref.bias.copy_(m.bias.float())
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    opt = FP16_Optimizer(FA(m.parameters(), lr=1e-2), static_loss_scale=8.0, verbose=False)
+    for _ in range(3):
+        x = torch.randn(16, 64, device=cuda_dev)
+        opt.zero_grad()
+        opt.backward(m(x.half()).float().pow(2).mean())
+        opt.step()
+        ropt.zero_grad()
+        ref(x).pow(2).mean().backward()
+        ropt.step()
+    torch.testing.assert_close(m.weight.float(), ref.weight, atol=3e-3, rtol=3e-2)
+    sd = opt.state_dict()
+    opt.load_state_dict(sd)
+
+
+def test_fused_adam_cuda_entry_points_on_gpu(cuda_dev):
+    """reversible_adam + maybe_adam_undo + strided_check_finite + maybe_cast on the device (reference fused_adam_cuda.cpp:92-104)."""
+    from apex_b200.contrib.optimizers import fused_adam_cuda as F
+    torch.manual_seed(0)
+    n = 4099
+    for mode in (0, 1):
+        p, m, v, g = (torch.randn(n, device=cuda_dev), torch.rand(n, device=cuda_dev) * 0.1, torch.rand(n, device=cuda_dev) * 0.1,
+                      torch.randn(n, device=cuda_dev) * 4)
+        p0, m0, v0 = p.clone(), m.clone(), v.clone()
+        args = (1e-2, 0.9, 0.999, 1e-8, 2.0, 3, mode, 1, 0.01)
+        copy = torch.empty(n, dtype=torch.bfloat16, device=cuda_dev)
+        F.reversible_adam(p, copy, m, v, g, *args)
+        assert not torch.equal(p, p0)
+        torch.testing.assert_close(copy.float(), p, atol=2e-2, rtol=2e-2)
+        F.maybe_adam_undo(torch.zeros(1, device=cuda_dev), p, m, v, g, *args)
+        assert not torch.equal(p, p0)
+        F.maybe_adam_undo(torch.ones(1, device=cuda_dev), p, m, v, g, *args)
+        for a, b in ((p, p0), (m, m0), (v, v0)):
+            torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-4)
+    flag, x = torch.zeros(1, device=cuda_dev), torch.ones(10, device=cuda_dev)
+    x[4] = float("inf")
+    F.strided_check_finite(flag, x, 2, 1)
+    assert flag.item() == 1
+    F.strided_check_finite(flag, x, 3, 1)
+    assert flag.item() == 0
+    src, dst = torch.randn(100, device=cuda_dev), torch.empty(100, dtype=torch.float16, device=cuda_dev)
+    F.maybe_cast(torch.zeros(1, device=cuda_dev), src, dst)
+    torch.testing.assert_close(dst.float(), src, atol=1e-3, rtol=1e-3)
