@@ -16,8 +16,8 @@ On CUDA the whole step is free of host synchronisation (reference :1078-1094): o
 found_inf) becomes a device flag that the stage kernels honour, the applied-update counter used for bias correction lives on the
 device, loss-unscaling is folded into stage 1 through the device ``_grad_scale``, and the per-segment tensor tables are built once.
 Knobs of the reference that only shaped its NCCL pipeline (dwu_num_blocks/chunks/rs_pg/ar_pg/ag_pg, full_ar, ...) are accepted and
-ignored; ``clip_after_ar`` semantics (clip by the GLOBAL norm) is what is implemented; ``e5m2_allgather`` is available through
-``param_sync_dtype=torch.float8_e5m2`` style casting of the gathered bucket.
+ignored; ``clip_after_ar`` semantics (clip by the GLOBAL norm) is what is implemented; ``e5m2_allgather=True`` sends the updated parameters as E5M2
+bytes (the generic collective path; the in-kernel push moves full-precision parameters).
 """
 from __future__ import annotations
 
@@ -46,6 +46,7 @@ class DistributedFusedLAMB(DistributedFusedAdam):
                          weight_decay=weight_decay, process_group=process_group, device=device, fused_collectives=fused_collectives,
                          dtype=torch.float32, **kwargs)
         self.grad_averaging = grad_averaging
+        self.e5m2_allgather = bool(e5m2_allgather)   # parameters travel as E5M2 bytes in the all-gather (reference :276-357): see _lamb_segment
         self.max_grad_norm = max_grad_norm
         self.use_nvlamb = use_nvlamb
         self._frag_cache: dict = {}
@@ -105,7 +106,7 @@ class DistributedFusedLAMB(DistributedFusedAdam):
             self._grad_scale *= (gs.detach().to(self.device, torch.float32).reshape([]).reciprocal() if torch.is_tensor(gs) else 1.0 / float(gs))
         # global gradient norm (already unscaled through _grad_scale)
         gnorm = self.grad_norm()
-        device_flow = self.device.type == "cuda" and all(seg.fused for seg in self._segments)
+        device_flow = self.device.type == "cuda" and all(seg.fused for seg in self._segments) and not self.e5m2_allgather
         found = None
         if grad_scaler is not None:
             st = grad_scaler._per_optimizer_states[id(self)]
@@ -265,6 +266,21 @@ class DistributedFusedLAMB(DistributedFusedAdam):
             else:
                 ref.multi_tensor_lamb_stage2([p_l, g_l], pn_f, un_f, group["lr"], group["weight_decay"], self.use_nvlamb)
         # low-precision copy of the shard into the parameter buffer, then all-gather of every bucket
+        if self.e5m2_allgather:
+            # reference multi_tensor_distopt_lamb_kernel.cu:276-357 (maybe_cast to e5m2 before the all-gather, widened after it): a quarter / half
+            # of the bytes on the wire; every rank -- the owner included -- ends up with the E5M2-rounded parameter, the fp32 master is exact
+            q = seg.master.view(seg.n_buckets, seg.shard_elems).to(torch.float8_e5m2)
+            if seg.D > 1:
+                pg = self.distributed_process_group
+                wire = q.view(torch.uint8)
+                for b in range(seg.n_buckets):
+                    parts = [torch.empty_like(wire[b]) for _ in range(seg.D)]
+                    dist.all_gather(parts, wire[b].contiguous(), group=pg)
+                    full = torch.cat(parts).view(torch.float8_e5m2)
+                    seg.param_buf[b * seg.bucket_elems:(b + 1) * seg.bucket_elems].copy_(full.to(seg.param_buf.dtype))
+            else:
+                seg.shard_view(seg.param_buf).copy_(q.to(seg.param_buf.dtype))
+            return
         seg.shard_view(seg.param_buf).copy_(seg.master.view(seg.n_buckets, seg.shard_elems))
         if seg.D > 1:
             pg = self.distributed_process_group

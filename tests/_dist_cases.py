@@ -843,3 +843,32 @@ def dist_adam_state_dict_v1_round_trip(rank, world, device_type):
     for a, b in zip(model.parameters(), model2.parameters()):
         assert torch.equal(a, b)
     assert opt2._global_step() == 3
+
+
+def dist_lamb_e5m2_allgather(rank, world, device_type):
+    """``e5m2_allgather=True`` (reference distributed_fused_lamb.py + multi_tensor_distopt_lamb_kernel.cu:276-357): the updated parameters cross
+    the wire as E5M2 bytes, so every rank holds the same E5M2-representable values while the fp32 master shards keep full precision and the
+    trajectory of the masters equals the plain run's first step."""
+    from apex_b200.contrib.optimizers import DistributedFusedLAMB
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(3)
+    models = [_model(dev) for _ in range(2)]
+    models[1].load_state_dict(models[0].state_dict())
+    opts = [DistributedFusedLAMB(m.parameters(), lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20, fused_collectives=False,
+                                 e5m2_allgather=flag, process_group=dist.new_group(list(range(world)))) for m, flag in zip(models, (True, False))]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(5, 7, generator=g).to(dev)
+    for m, o in zip(models, opts):
+        o.zero_grad()
+        m(x).pow(2).mean().backward()
+        o.step()
+    for pe, pf in zip(models[0].parameters(), models[1].parameters()):
+        # every value is exactly E5M2-representable and is the rounding of the full-precision result
+        torch.testing.assert_close(pe.detach().float().to(torch.float8_e5m2).float(), pe.detach().float(), atol=0, rtol=0)
+        torch.testing.assert_close(pe.detach().float(), pf.detach().float().to(torch.float8_e5m2).float(), atol=0, rtol=0)
+    flat = torch.cat([p.detach().float().reshape(-1) for p in models[0].parameters()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    assert all(torch.equal(gathered[0], t) for t in gathered)
+    for se, sf in zip(opts[0]._segments, opts[1]._segments):
+        torch.testing.assert_close(se.master, sf.master)      # the masters never see the quantisation

@@ -55,6 +55,10 @@ def test_two_ranks_gloo_state_dict(tmp_path):
     run_distributed(cases.dist_adam_state_dict_reshards, 2, "cpu", str(tmp_path), backend="gloo")
 
 
+def test_two_ranks_gloo_lamb_e5m2_allgather():
+    run_distributed(cases.dist_lamb_e5m2_allgather, 2, "cpu", backend="gloo")
+
+
 def test_two_ranks_gloo_state_dict_v1_round_trip():
     run_distributed(cases.dist_adam_state_dict_v1_round_trip, 2, "cpu", backend="gloo")
 
