@@ -525,9 +525,19 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     def init_param_buffer(self) -> None:
         self.init_params()
 
-    def init_params_bucket(self, params, **kwargs) -> None:
-        """Accepted for API compatibility: the layout here is already one contiguous space per (group, dtypes)."""
-        self.init_params()
+    def init_params_bucket(self, params, dtype: Optional[torch.dtype] = None, grad_sync_dtype: Optional[torch.dtype] = None,
+                           param_sync_dtype: Optional[torch.dtype] = None, **kwargs) -> None:
+        """Reference :1275-1344: initialise ``params`` together (their own bucket), optionally with their own dtypes. The layout here is one
+        contiguous space per (group, dtypes) that is cut into buckets afterwards, so there is nothing to place; what is honoured is the
+        per-parameter dtype override -- recorded now, applied when the layout is built (first ``step`` / ``zero_grad`` / ``init_params()``).
+        Several calls (one per layer, as NeMo / Megatron do) may precede that point: this call never triggers the layout itself."""
+        params = [params] if isinstance(params, torch.Tensor) else list(params)
+        if self._inited:
+            if dtype or grad_sync_dtype or param_sync_dtype:
+                raise RuntimeError("init_params_bucket with dtype overrides must be called before the optimizer state is laid out")
+            return
+        if dtype or grad_sync_dtype or param_sync_dtype:
+            self.init_params(params, dtype=dtype, grad_sync_dtype=grad_sync_dtype, param_sync_dtype=param_sync_dtype)
 
     def set_initial_values(self, param, values):
         """Optional: higher-precision initial values for a low-precision parameter's fp32 master copy."""

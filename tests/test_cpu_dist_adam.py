@@ -480,3 +480,26 @@ def test_zero_grad_set_to_none_moves_gradients_with_one_copy_and_matches_the_def
 
     for a, b in zip(run(False), run(True)):
         torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+
+
+def test_init_params_bucket_records_dtype_overrides_without_building_the_layout():
+    """NeMo / Megatron call ``init_params_bucket`` once per layer before the first step (reference distributed_fused_adam.py:1275-1344):
+    each call must only record its dtype overrides; the layout is built once, afterwards, with all of them."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    layers = [torch.nn.Linear(8, 8) for _ in range(3)]
+    params = [p for l in layers for p in l.parameters()]
+    opt = DistributedFusedAdam(params, lr=1e-2, device="cpu", dtype=torch.float32)
+    opt.init_params_bucket(layers[0].parameters())
+    assert not opt._inited
+    opt.init_params_bucket(layers[1].parameters(), dtype=torch.float32, grad_sync_dtype=torch.float32, param_sync_dtype=torch.float32)
+    opt.init_params_bucket(layers[2].weight, dtype=torch.float32)
+    assert not opt._inited and len(opt._dtype_overrides) == 3
+    for p in params:
+        p.grad = torch.randn_like(p)
+    before = [p.detach().clone() for p in params]
+    opt.step()
+    assert opt._inited and all(not torch.equal(a, b) for a, b in zip(before, params))
+    opt.init_params_bucket(layers[0].parameters())      # after the layout: a no-op without dtypes ...
+    with pytest.raises(RuntimeError):
+        opt.init_params_bucket(layers[0].parameters(), dtype=torch.float32)   # ... and an error with them
