@@ -43,6 +43,25 @@ def deprecated_warning(msg: str) -> None:
         warnings.warn(msg, DeprecatedFeatureWarning, stacklevel=2)
 
 
+# Reference sub-module paths whose content lives in a differently named module here (one file per class in the reference, grouped files
+# here). Resolved by the alias finder, so ``from apex.optimizers.fused_novograd import FusedNovoGrad`` works without a file per name.
+_PATH_ALIASES = {
+    "optimizers.fused_novograd": "optimizers.fused_sgd",
+    "optimizers.fused_adagrad": "optimizers.fused_sgd",
+    "optimizers.fused_mixed_precision_lamb": "optimizers.fused_lamb",
+    "multi_tensor_apply.multi_tensor_apply": "multi_tensor_apply",
+    "contrib.optimizers.fp16_optimizer": "contrib.optimizers.legacy",
+    "contrib.optimizers.fused_adam": "contrib.optimizers.legacy",
+    "contrib.optimizers.fused_lamb": "contrib.optimizers.legacy",
+    "contrib.optimizers.fused_sgd": "contrib.optimizers.legacy",
+    "contrib.sparsity.permutation_search_kernels": "contrib.sparsity.permutation_search",
+    "contrib.sparsity.permutation_search_kernels.call_permutation_search_kernels": "contrib.sparsity.permutation_search",
+    "contrib.sparsity.permutation_search_kernels.exhaustive_search": "contrib.sparsity.permutation_search",
+    "contrib.sparsity.permutation_search_kernels.channel_swap": "contrib.sparsity.permutation_search",
+    "contrib.sparsity.permutation_search_kernels.permutation_utilities": "contrib.sparsity.permutation_search",
+}
+
+
 class _ApexAliasFinder:
     """Meta-path finder that resolves ``apex.<anything>`` to the SAME module object as ``apex_b200.<anything>`` — without it a deep import
     such as ``apex.contrib.xentropy.softmax_xentropy`` would execute the file a second time under the other name (two copies of every class)."""
@@ -54,16 +73,28 @@ class _ApexAliasFinder:
 
         if not (fullname == "apex" or fullname.startswith("apex.")) or sys.modules.get("apex") is not sys.modules[__name__]:
             return None
+        target_name = __name__ + "." + _PATH_ALIASES[fullname[5:]] if fullname[5:] in _PATH_ALIASES else __name__ + fullname[4:]
         try:
-            importlib.import_module(__name__ + fullname[4:])
+            importlib.import_module(target_name)
         except ImportError:
             return None
-        return importlib.machinery.ModuleSpec(fullname, self)
+        spec = importlib.machinery.ModuleSpec(fullname, self)
+        spec.loader_state = target_name
+        return spec
 
     def create_module(self, spec):
         import sys
+        import types
 
-        return sys.modules[__name__ + spec.name[4:]]
+        target = sys.modules[spec.loader_state]
+        if any(k.startswith(spec.name[5:] + ".") for k in _PATH_ALIASES) and not hasattr(target, "__path__"):
+            # a reference PACKAGE that is a single module here (permutation_search_kernels): a package-shaped view of it, so that its
+            # sub-module names keep resolving through this finder
+            pkg = types.ModuleType(spec.name, target.__doc__)
+            pkg.__dict__.update({k: v for k, v in target.__dict__.items() if not k.startswith("__")})
+            pkg.__path__ = []
+            return pkg
+        return target
 
     def exec_module(self, module):  # already executed under its apex_b200 name
         return None

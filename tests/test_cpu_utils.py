@@ -50,6 +50,32 @@ def test_deprecated_warning_and_apex_alias():
     assert _cast_if_autocast_enabled(1, 2) == (1, 2)
 
 
+def test_reference_import_paths_resolve_to_the_same_objects():
+    """One-class-per-file paths of the reference (``apex.optimizers.fused_novograd``, ``apex.contrib.optimizers.fp16_optimizer``,
+    ``apex.contrib.sparsity.permutation_search_kernels.exhaustive_search`` ...) resolve through the alias finder to the grouped modules
+    here, as the SAME objects (no second execution of any file)."""
+    import apex_b200
+    apex_b200.install_as_apex()
+    from apex.contrib.optimizers.fp16_optimizer import FP16_Optimizer
+    from apex.contrib.optimizers.fused_adam import FusedAdam as LegacyAdam
+    from apex.contrib.sparsity.permutation_search_kernels import accelerated_search_for_good_permutation
+    from apex.contrib.sparsity.permutation_search_kernels.call_permutation_search_kernels import accelerated_search_for_good_permutation as again
+    from apex.contrib.sparsity.permutation_search_kernels.channel_swap import Channel_Swap  # noqa: F401
+    from apex.contrib.sparsity.permutation_search_kernels.exhaustive_search import Exhaustive_Search  # noqa: F401
+    from apex.multi_tensor_apply.multi_tensor_apply import MultiTensorApply
+    from apex.optimizers.fused_adagrad import FusedAdagrad
+    from apex.optimizers.fused_mixed_precision_lamb import FusedMixedPrecisionLamb
+    from apex.optimizers.fused_novograd import FusedNovoGrad
+    import apex.contrib.xentropy.softmax_xentropy as a
+    import apex_b200.contrib.optimizers.legacy as legacy
+    import apex_b200.contrib.xentropy.softmax_xentropy as b
+    import apex_b200.multi_tensor_apply as mta
+    import apex_b200.optimizers as O
+    assert a is b and again is accelerated_search_for_good_permutation
+    assert FusedNovoGrad is O.FusedNovoGrad and FusedAdagrad is O.FusedAdagrad and FusedMixedPrecisionLamb is O.FusedMixedPrecisionLamb
+    assert FP16_Optimizer is legacy.FP16_Optimizer and LegacyAdam is legacy.FusedAdam and MultiTensorApply is mta.MultiTensorApply
+
+
 def test_flatten_roundtrip():
     from apex_b200.utils.flatten import flatten, unflatten
     ts = [torch.randn(3, 4), torch.randn(5)]
