@@ -512,7 +512,72 @@ def _contrib_raw_mods():
     mods["_apex_nccl_allocator"] = _mod("_apex_nccl_allocator", get_nccl_allocator=get_nccl_allocator)
     mods["permutation_search_cuda"] = _perm_search_mod()
     mods["fmhalib"] = _fmhalib_mod()
+    mods["cudnn_gbn_lib"] = _cudnn_gbn_mod()
     return mods
+
+
+_gbn_groups: dict = {}
+
+
+def _cudnn_gbn_mod():
+    """``cudnn_gbn_lib`` (reference apex/contrib/cudnn_gbn/batch_norm.py:34-69 over apex/contrib/csrc/cudnn_gbn): NHWC batch norm whose
+    statistics span ``group_size`` consecutive ranks. ``forward`` fills ``minibatch_mean`` / ``minibatch_inv_var`` and updates the running
+    statistics in place; ``backward`` returns ``(dx, dscale, dbias)``. Composed from the SyncBN kernel's phase ops
+    (``apex_b200.parallel.syncbn_ops``: Welford statistics, normalise, backward reductions) plus one all-gather / all-reduce of the
+    per-channel vectors over the group's process group; the reference's ``peer_buffers`` lists (its hand-rolled exchange areas) are
+    accepted and not used."""
+    import torch.distributed as dist
+
+    from .parallel import syncbn_ops as S
+
+    def _group(group_size, group_rank):
+        if group_size <= 1 or not (dist.is_available() and dist.is_initialized()):
+            return None
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if group_size >= world:
+            return dist.group.WORLD
+        key = (world, group_size)
+        if key not in _gbn_groups:      # every rank creates every group, in the same order (new_group is collective)
+            _gbn_groups[key] = [dist.new_group(list(range(g0, g0 + group_size))) for g0 in range(0, world, group_size)]
+        return _gbn_groups[key][rank // group_size]
+
+    def forward(x, weight, bias, running_mean, running_var, minibatch_mean, minibatch_inv_var, momentum, eps, group_size, group_rank, peer_buffers):
+        mean, var_b = S.welford_mean_var(x)
+        count = x.numel() // x.shape[1]
+        pg = _group(int(group_size), int(group_rank))
+        if pg is not None:
+            n = dist.get_world_size(pg)
+            packed = torch.cat([mean, var_b, torch.full((1,), float(count), device=mean.device)])
+            gathered = [torch.empty_like(packed) for _ in range(n)]
+            dist.all_gather(gathered, packed, group=pg)
+            allm = torch.stack(gathered)
+            C = mean.numel()
+            mean, var_u, inv_std = S.welford_parallel(allm[:, :C], allm[:, C:2 * C], allm[:, 2 * C], float(eps))
+        else:
+            var_u = var_b * (count / max(count - 1, 1))
+            inv_std = torch.rsqrt(var_b + float(eps))
+        with torch.no_grad():
+            minibatch_mean.copy_(mean.reshape(minibatch_mean.shape))
+            minibatch_inv_var.copy_(inv_std.reshape(minibatch_inv_var.shape))
+            if running_mean is not None:
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var_u.to(running_var.dtype), alpha=momentum)
+        return S.batchnorm_forward(x, mean, inv_std, weight, bias)
+
+    def backward(x, dy, scale, minibatch_mean, minibatch_inv_var, eps, group_size, group_rank, peer_buffers):
+        mean, inv_std = minibatch_mean.reshape(-1).float(), minibatch_inv_var.reshape(-1).float()
+        sum_dy, sum_dy_xmu, dscale, dbias = S.reduce_bn(dy, x, mean, inv_std, scale)
+        count = torch.tensor([float(x.numel() // x.shape[1])], device=x.device)
+        pg = _group(int(group_size), int(group_rank))
+        if pg is not None:
+            packed = torch.cat([sum_dy, sum_dy_xmu, count])
+            dist.all_reduce(packed, group=pg)
+            C = sum_dy.numel()
+            sum_dy, sum_dy_xmu, count = packed[:C], packed[C:2 * C], packed[2 * C:]
+        dx = S.batchnorm_backward(dy, x, mean, inv_std, scale, sum_dy, sum_dy_xmu, count)
+        return dx, dscale, dbias
+
+    return _mod("cudnn_gbn_lib", forward=forward, backward=backward)
 
 
 def _fmhalib_mod():

@@ -872,3 +872,35 @@ def dist_lamb_e5m2_allgather(rank, world, device_type):
     assert all(torch.equal(gathered[0], t) for t in gathered)
     for se, sf in zip(opts[0]._segments, opts[1]._segments):
         torch.testing.assert_close(se.master, sf.master)      # the masters never see the quantisation
+
+
+def cudnn_gbn_lib_group_of_two(rank, world, device_type):
+    """``cudnn_gbn_lib.forward / backward`` with group_size = 2: every rank holds half of the batch; outputs, running statistics and gradients
+    must equal plain batch norm over the concatenated batch (reference apex/contrib/cudnn_gbn/batch_norm.py:34-69)."""
+    from apex_b200 import ext_compat as E
+    g = E.extension_modules()["cudnn_gbn_lib"]
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(0)
+    full = torch.randn(2 * world, 8, 5, 5)
+    dy_full = torch.randn(2 * world, 8, 5, 5)
+    w, b = torch.randn(8), torch.randn(8)
+    x = full[2 * rank:2 * rank + 2].contiguous(memory_format=torch.channels_last).to(dev)
+    dy = dy_full[2 * rank:2 * rank + 2].contiguous(memory_format=torch.channels_last).to(dev)
+    rm, rv = torch.zeros(8, device=dev), torch.ones(8, device=dev)
+    mm, miv = torch.empty(8, device=dev), torch.empty(8, device=dev)
+    y = g.forward(x, w.to(dev), b.to(dev), rm, rv, mm, miv, 0.1, 1e-5, world, rank, [])
+    rm2, rv2 = torch.zeros(8), torch.ones(8)
+    fr, wr, br = full.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(fr, rm2, rv2, wr, br, True, 0.1, 1e-5)
+    ref.backward(dy_full)
+    torch.testing.assert_close(y.cpu(), ref.detach()[2 * rank:2 * rank + 2], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(rm.cpu(), rm2, atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(rv.cpu(), rv2, atol=1e-6, rtol=1e-5)
+    dx, dw, db = g.backward(x, dy, w.to(dev), mm, miv, 1e-5, world, rank, [])
+    torch.testing.assert_close(dx.cpu(), fr.grad[2 * rank:2 * rank + 2], atol=1e-5, rtol=1e-4)
+    # dscale / dbias are this rank's contribution (the reference leaves their reduction to DDP)
+    tot_w, tot_b = dw.clone(), db.clone()
+    dist.all_reduce(tot_w)
+    dist.all_reduce(tot_b)
+    torch.testing.assert_close(tot_w.cpu(), wr.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(tot_b.cpu(), br.grad, atol=1e-4, rtol=1e-4)

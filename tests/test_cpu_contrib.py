@@ -409,3 +409,25 @@ def test_permutation_search_cuda_raw_entry_points():
         a, b = k // 4, 4 + k % 4
         c[:, [a, b]] = c[:, [b, a]]
         assert abs(o[k] - (kept(c) - kept(M[:, :8]))) < 1e-3
+
+
+def test_cudnn_gbn_lib_single_rank_matches_batch_norm():
+    from apex_b200 import ext_compat as E
+    g = E.extension_modules()["cudnn_gbn_lib"]
+    torch.manual_seed(0)
+    x = torch.randn(4, 8, 5, 5).contiguous(memory_format=torch.channels_last)
+    w, b = torch.randn(8), torch.randn(8)
+    rm, rv, mm, miv = torch.zeros(8), torch.ones(8), torch.empty(8), torch.empty(8)
+    y = g.forward(x, w, b, rm, rv, mm, miv, 0.1, 1e-5, 1, 0, [])
+    rm2, rv2 = torch.zeros(8), torch.ones(8)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.batch_norm(xr, rm2, rv2, wr, br, True, 0.1, 1e-5)
+    torch.testing.assert_close(y, ref.detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(rm, rm2)
+    torch.testing.assert_close(rv, rv2, atol=1e-6, rtol=1e-5)
+    dy = torch.randn_like(y)
+    ref.backward(dy)
+    dx, dw, db = g.backward(x, dy, w, mm, miv, 1e-5, 1, 0, [])
+    torch.testing.assert_close(dx, xr.grad, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(dw, wr.grad, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(db, br.grad, atol=1e-4, rtol=1e-4)

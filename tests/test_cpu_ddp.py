@@ -43,3 +43,7 @@ def test_reducer_gloo():
 
 def test_ddp_option_matrix_gloo():
     run_distributed(cases.ddp_option_matrix, 2, "cpu", backend="gloo")
+
+
+def test_cudnn_gbn_lib_raw_entry_points_two_ranks_gloo():
+    run_distributed(cases.cudnn_gbn_lib_group_of_two, 2, "cpu", backend="gloo")
