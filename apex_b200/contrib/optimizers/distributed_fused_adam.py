@@ -21,7 +21,8 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
-from typing import Iterable, Optional
+from dataclasses import dataclass
+from typing import Iterable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -546,6 +547,56 @@ class DistributedFusedAdam(torch.optim.Optimizer):
     def parameters(self):
         for g in self.param_groups:
             yield from g["params"]
+
+    @dataclass
+    class ParameterFragment:
+        """One (parameter x bucket) intersection, with the field names of the reference (distributed_fused_adam.py:388-413). Ranges are
+        half-open element ranges; ``bucket_id`` counts the buckets of all segments in creation order."""
+        param_group_id: int
+        param_id: int
+        bucket_id: int
+        param_range: Tuple[int, int]
+        bucket_range: Tuple[int, int]
+        in_local_shard: bool
+        shard_range: Optional[Tuple[int, int]]
+        shard_bucket_range: Optional[Tuple[int, int]]
+        shard_param_range: Optional[Tuple[int, int]]
+
+    def parameter(self, *args) -> torch.nn.Parameter:
+        """``parameter(param_group_id, param_id)`` or ``parameter(fragment)`` (reference :1199-1226)."""
+        if len(args) == 2 and all(isinstance(a, int) for a in args):
+            gi, pi = args
+        elif len(args) == 1 and isinstance(args[0], self.ParameterFragment):
+            gi, pi = args[0].param_group_id, args[0].param_id
+        else:
+            raise TypeError("Expected input types are [int, int] or [DistributedFusedAdam.ParameterFragment], "
+                            f"but found {[type(a).__name__ for a in args]}")
+        return self.param_groups[gi]["params"][pi]
+
+    def param_fragments(self, param: torch.nn.Parameter) -> list:
+        """The fragments of an initialised parameter — what the reference keeps in ``state[param]["fragments"]`` — computed from the
+        segment geometry: a parameter occupies ``[offset, offset + numel)`` of its segment's flat space, bucket ``b`` covers
+        ``[b * B, (b + 1) * B)`` of it and rank ``r`` owns ``[r * B / D, (r + 1) * B / D)`` of every bucket."""
+        self.init_params()
+        si, pi = next((si, pi) for si, sg in enumerate(self._segments) for pi, q in enumerate(sg.params) if q is param)
+        seg = self._segments[si]
+        base = sum(s.n_buckets for s in self._segments[:si])
+        group_params = self.param_groups[seg.group_idx]["params"]
+        param_id = next(i for i, q in enumerate(group_params) if q is param)
+        B, Sb, r = seg.bucket_elems, seg.shard_elems, seg.rank
+        lo, hi = seg.offsets[pi], seg.offsets[pi] + param.numel()
+        out = []
+        for b in range(lo // B, (max(hi, lo + 1) - 1) // B + 1):
+            a, z = max(lo, b * B), min(hi, (b + 1) * B)
+            s_lo, s_hi = max(a, b * B + r * Sb), min(z, b * B + (r + 1) * Sb)
+            local = s_hi > s_lo
+            out.append(self.ParameterFragment(
+                param_group_id=seg.group_idx, param_id=param_id, bucket_id=base + b, param_range=(a - lo, z - lo),
+                bucket_range=(a - b * B, z - b * B), in_local_shard=local,
+                shard_range=(s_lo - b * B - r * Sb, s_hi - b * B - r * Sb) if local else None,
+                shard_bucket_range=(s_lo - b * B, s_hi - b * B) if local else None,
+                shard_param_range=(s_lo - lo, s_hi - lo) if local else None))
+        return out
 
     # ---------------------------------------------------------------------------------------------------------------
     def zero_grad(self, set_to_none: bool = False) -> None:

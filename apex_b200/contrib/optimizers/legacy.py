@@ -12,6 +12,7 @@ import torch
 from ...ops import amp_C
 from ...optimizers import FusedLAMB as _FusedLAMB
 from ...optimizers import FusedSGD as _FusedSGD
+from ...optimizers._base import CHUNK
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -83,7 +84,48 @@ class FusedLAMB(_FusedLAMB):
 
 
 class FusedSGD(_FusedSGD):
-    """Legacy contrib FusedSGD."""
+    """Legacy contrib FusedSGD (reference contrib/optimizers/fused_sgd.py:129-260): ``step(grads=, output_params=, scale=)`` where
+    ``group['params']`` are the fp32 masters, ``output_params`` the model weights (fp16 ones receive a copy of the update inside the
+    same kernel launch) and ``scale`` divides the gradients. Without ``grads`` it behaves like ``apex_b200.optimizers.FusedSGD``
+    (the reference raises there; this is a superset)."""
+
+    @torch.no_grad()
+    def step(self, closure=None, grads=None, output_params=None, scale=1.0, grad_norms=None):
+        if hasattr(self, "_amp_stash"):
+            raise RuntimeError("apex.contrib.optimizers.FusedSGD should not be used with AMP.")
+        if grads is None and output_params is None:
+            return super().step(closure)
+        if grads is None or output_params is None:
+            raise RuntimeError("apex.contrib.optimizers.FusedSGD needs both grads and output_params (FP16_Optimizer provides them).")
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+
+        def _per_group(x):
+            x = list(x) if isinstance(x, types.GeneratorType) else x
+            return x if isinstance(x[0], list) else [x]
+
+        for group, gs, outs in zip(self.param_groups, _per_group(grads), _per_group(output_params)):
+            if gs is None or outs is None:
+                raise RuntimeError("apex.contrib.optimizers.FusedSGD only works when all parameters require grad.")
+            # two launches per group: model weights in fp32 (3 lists) and in half precision (4 lists: the kernel also writes the copy)
+            for half in (True, False):
+                sel = [(g, m, o) for g, m, o in zip(gs, group["params"], outs) if (o.dtype != torch.float32) == half]
+                if not sel:
+                    continue
+                masters = [m for _, m, _ in sel]
+                moms, first_run = self.get_momentums(masters)
+                lists = [[g for g, _, _ in sel], masters, moms] + ([[o for _, _, o in sel]] if half else [])
+                amp_C.multi_tensor_sgd(CHUNK, self._noop(masters[0]), lists, group["weight_decay"], group["momentum"], group["dampening"],
+                                       group["lr"], group["nesterov"], first_run, self.wd_after_momentum, 1.0 / scale)
+        return loss
+
+    def _noop(self, like):
+        buf = getattr(self, "_legacy_noop", None)
+        if buf is None or buf.device != like.device:
+            buf = self._legacy_noop = torch.zeros(1, dtype=torch.int32, device=like.device)
+        return buf
 
 
 class FP16_Optimizer:
@@ -162,7 +204,8 @@ class FP16_Optimizer:
             sd.update(last_overflow_iter=self.last_overflow_iter, scale_factor=self.scale_factor, scale_window=self.scale_window)
         return sd
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, state_dict):
+        sd = state_dict
         self.dynamic_loss_scale, self.cur_scale, self.cur_iter = sd["dynamic_loss_scale"], sd["cur_scale"], sd["cur_iter"]
         if self.dynamic_loss_scale:
             self.last_overflow_iter, self.scale_factor, self.scale_window = sd["last_overflow_iter"], sd["scale_factor"], sd["scale_window"]

@@ -904,3 +904,29 @@ def cudnn_gbn_lib_group_of_two(rank, world, device_type):
     dist.all_reduce(tot_b)
     torch.testing.assert_close(tot_w.cpu(), wr.grad, atol=1e-4, rtol=1e-4)
     torch.testing.assert_close(tot_b.cpu(), br.grad, atol=1e-4, rtol=1e-4)
+
+
+def dist_adam_fragments_partition_params(rank, world, device_type):
+    """``param_fragments``: across the ranks the local-shard sub-ranges cover every element of every parameter exactly once, and the
+    master shard holds the parameter's values at ``shard_range`` of the bucket's local shard."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(3)
+    params = [torch.nn.Parameter(torch.randn(n, device=dev)) for n in (9000, 130, 4097)]
+    opt = DistributedFusedAdam(params, lr=1e-2, device=dev, bucket_cap_mb=2048 * 4 * world / 2 ** 20, fused_collectives=False)
+    cover = [torch.zeros(p.numel(), dtype=torch.int32) for p in params]
+    for p, c in zip(params, cover):
+        for f in opt.param_fragments(p):
+            if f.in_local_shard:
+                c[f.shard_param_range[0]:f.shard_param_range[1]] += 1
+                n = f.shard_param_range[1] - f.shard_param_range[0]
+                assert f.shard_range[1] - f.shard_range[0] == n == f.shard_bucket_range[1] - f.shard_bucket_range[0]
+                assert f.bucket_range[0] <= f.shard_bucket_range[0] and f.shard_bucket_range[1] <= f.bucket_range[1]
+                seg = opt._segments[0]
+                lo = (f.bucket_id * seg.shard_elems) + f.shard_range[0]
+                torch.testing.assert_close(seg.master[lo:lo + n].cpu(), p.detach().flatten()[f.shard_param_range[0]:f.shard_param_range[1]].cpu())
+            else:
+                assert f.shard_range is None and f.shard_param_range is None
+    for c in cover:
+        dist.all_reduce(c)
+        assert bool((c == 1).all())

@@ -124,6 +124,32 @@ def test_legacy_contrib_optimizers_cpu():
     opt.load_state_dict(sd)
 
 
+def test_legacy_contrib_fused_sgd_explicit_grads():
+    """apex.contrib.optimizers.FusedSGD.step(grads=, output_params=, scale=): fp32 masters updated from scaled half gradients, half model
+    copies written by the same call, fp32 model weights in the same group take the 3-list launch."""
+    from apex_b200.contrib.optimizers import FusedSGD
+    torch.manual_seed(0)
+    masters = [nn.Parameter(torch.randn(33)), nn.Parameter(torch.randn(7, 5))]
+    model = [masters[0].detach().half(), masters[1].detach().clone()]
+    refs = [nn.Parameter(m.detach().clone()) for m in masters]
+    o = FusedSGD(masters, lr=0.1, momentum=0.9, weight_decay=0.01)
+    r = torch.optim.SGD(refs, lr=0.1, momentum=0.9, weight_decay=0.01)
+    for _ in range(3):
+        gs = [torch.randn(33), torch.randn(7, 5)]
+        for q, g in zip(refs, gs):
+            q.grad = g.clone()
+        r.step()
+        o.step(grads=[(gs[0] * 16).half(), gs[1] * 16], output_params=model, scale=16.0)
+    torch.testing.assert_close(masters[0].detach(), refs[0].detach(), atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(masters[1].detach(), refs[1].detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(model[0], masters[0].detach().half())
+    with pytest.raises(RuntimeError):
+        o.step(grads=[gs[0], gs[1]])
+    for m in masters:       # without explicit arguments it is the modern FusedSGD
+        m.grad = torch.ones_like(m)
+    o.step()
+
+
 def test_fused_adam_swa_tracks_adam_and_averages():
     from apex_b200.contrib.openfold import FusedAdamSWA
     torch.manual_seed(0)

@@ -63,6 +63,10 @@ def test_two_ranks_gloo_state_dict_v1_round_trip():
     run_distributed(cases.dist_adam_state_dict_v1_round_trip, 2, "cpu", backend="gloo")
 
 
+def test_fragments_partition_params_two_ranks():
+    run_distributed(cases.dist_adam_fragments_partition_params, 2, "cpu", backend="gloo")
+
+
 def test_state_dict_v1_single_rank_and_layout_check():
     import warnings
     from apex_b200.contrib.optimizers import DistributedFusedAdam
@@ -503,3 +507,28 @@ def test_init_params_bucket_records_dtype_overrides_without_building_the_layout(
     opt.init_params_bucket(layers[0].parameters())      # after the layout: a no-op without dtypes ...
     with pytest.raises(RuntimeError):
         opt.init_params_bucket(layers[0].parameters(), dtype=torch.float32)   # ... and an error with them
+
+
+def test_parameter_lookup_and_fragments():
+    """``parameter(group, index)`` / ``parameter(fragment)`` (reference distributed_fused_adam.py:1199-1226) and the fragment records
+    (:388-413): fragments of a parameter tile it exactly, bucket ranges stay inside the bucket, and the local-shard sub-ranges map the
+    same elements in parameter, bucket and shard coordinates."""
+    from apex_b200.contrib.optimizers import DistributedFusedAdam
+    torch.manual_seed(0)
+    a, b, c = (torch.nn.Parameter(torch.randn(n)) for n in (300_000, 70_000, 5))
+    opt = DistributedFusedAdam([{"params": [a, b]}, {"params": [c], "lr": 1.0}], lr=1e-2, device="cpu", bucket_cap_mb=0.5)
+    assert opt.parameter(0, 1) is b and opt.parameter(1, 0) is c
+    with pytest.raises(TypeError):
+        opt.parameter("0", 1)
+    seen = set()
+    for p in (a, b, c):
+        frags = opt.param_fragments(p)
+        assert [f.param_range[0] for f in frags] == [0] + [f.param_range[1] for f in frags[:-1]] and frags[-1].param_range[1] == p.numel()
+        for f in frags:
+            assert opt.parameter(f) is p and isinstance(f, DistributedFusedAdam.ParameterFragment)
+            n = f.param_range[1] - f.param_range[0]
+            assert f.bucket_range[1] - f.bucket_range[0] == n and f.bucket_range[0] >= 0
+            assert f.in_local_shard and f.shard_param_range == f.param_range        # world size 1: the whole bucket is the local shard
+            assert f.shard_bucket_range == f.bucket_range == f.shard_range
+            seen.add(f.bucket_id)
+    assert len(opt.param_fragments(a)) > 1 and seen == set(range(len(seen)))
