@@ -25,7 +25,8 @@ from . import config
 _COMPUTE_OPS = ("call_function", "call_method", "call_module")
 # measured B200 numbers (MEASURED_PEAKS.json): only their ratio matters for ranking paths
 _HBM_BYTES_PER_S, _TENSOR_FLOPS_PER_S, _LAUNCH_S = 6.5e12, 1.4e15, 3e-6
-_MATMUL_NAMES = ("matmul", "linear", "bmm", "mm", "addmm", "baddbmm", "conv1d", "conv2d", "conv3d", "einsum", "scaled_dot_product_attention")
+_MATMUL_NAMES = ("matmul", "linear", "bmm", "mm", "addmm", "baddbmm", "conv1d", "conv2d", "conv3d", "convolution", "einsum",
+                 "scaled_dot_product_attention")
 
 
 def _example(node: fx.Node):
@@ -211,11 +212,16 @@ class ScheduledGraph:
         self.gm = gm
         self.graph_id = ScheduledGraph._next_id
         ScheduledGraph._next_id += 1
-        skip = self.graph_id in config.skip_graph_ids
-        self.plan = plan_graph(gm, 0 if skip else num_streams)
+        skip = self.graph_id in config.skip_graph_ids or self.graph_id in config.skip_post_grad_graph_ids
+        self.num_streams = 0 if skip else num_streams
+        self.plan = plan_graph(gm, self.num_streams)
         self.cuda_graph = cuda_graph
         self._streams = self._events = None
         self._captured = None
+        # inductor.patch_graph_lowering(True) / TORCH_SCHED_CODEGEN=1 at construction time: run the generated program (inductor/), not
+        # the interpreter; built on first use
+        self.wrapper_codegen = bool(config.wrapper_codegen)
+        self._program = None
         if config.debug:
             print(f"[torchsched] graph {self.graph_id}\n{self.plan.describe()}")
 
@@ -227,7 +233,17 @@ class ScheduledGraph:
             self._events = {m: torch.cuda.Event() for m in self.plan.records} if multi else {}
         return self._streams, self._events
 
+    def program(self):
+        """The generated multi-stream program of this graph (``.source`` holds its text)."""
+        if self._program is None:
+            from .inductor.graph import lower_graph
+
+            self._program = lower_graph(self.gm, self.num_streams, self.graph_id)
+        return self._program
+
     def _run(self, *args):
+        if self.wrapper_codegen:
+            return self.program()(*args)
         streams, events = self._resources()
         if streams and not config.reuse_cuda_event:
             events = {m: torch.cuda.Event() for m in self.plan.records}

@@ -144,3 +144,272 @@ def test_stream_execution_against_a_recording_mock(monkeypatch):
         assert s.log[0] == ("wait_stream", "caller") and [op for op, _ in s.log].count("record") == 1
     assert [op for op, _ in caller.log].count("wait") == 2
     assert caller.log[-2:] == [("wait_stream", "side"), ("wait_stream", "side")]
+
+
+# ---- generated multi-stream programs (contrib/torchsched/inductor) ---------------------------------------------------------------------
+from apex_b200.contrib.torchsched import config as ts_config                                      # noqa: E402
+from apex_b200.contrib.torchsched.inductor import _utils as ind_utils                             # noqa: E402
+from apex_b200.contrib.torchsched.inductor import patch_graph_lowering                            # noqa: E402
+from apex_b200.contrib.torchsched.inductor.event import CudaEventFactory                          # noqa: E402
+from apex_b200.contrib.torchsched.inductor.scheduler import MultiCudaStreamScheduler              # noqa: E402
+
+
+def test_generated_program_matches_eager_including_backward():
+    torch.manual_seed(0)
+    m = Branchy()
+    x = torch.randn(32, 64, requires_grad=True)
+    patch_graph_lowering(True)
+    try:
+        cm, graphs = _compile(m)
+        out = cm(x)
+    finally:
+        patch_graph_lowering(False)
+    ref = m(x)
+    assert graphs[0].wrapper_codegen and "def call(" in graphs[0].program().source
+    torch.testing.assert_close(out, ref)
+    torch.testing.assert_close(torch.autograd.grad(out.sum(), x)[0], torch.autograd.grad(ref.sum(), x)[0])
+    cm2, graphs2 = _compile(m)                       # not patched any more: the interpreter
+    cm2(x)
+    assert not graphs2[0].wrapper_codegen and graphs2[0]._program is None
+
+
+class _SimStream:
+    """Vector-clock model of a CUDA stream: ``clock[s]`` = how much of stream ``s``'s work is known to precede what this stream does next."""
+    count = 0
+
+    def __init__(self, device=None, name=None):
+        _SimStream.count += 1
+        self.name = name or f"side{_SimStream.count}"
+        self.clock = {self.name: 0}
+        self.log = []
+
+    def tick(self):
+        self.clock[self.name] += 1
+        return self.clock[self.name]
+
+    def knows(self, stream_name, t):
+        return self.clock.get(stream_name, -1) >= t
+
+    def wait_event(self, ev):
+        assert ev.snapshot is not None, "wait on an event that was never recorded: a no-op on CUDA, i.e. a missed dependency"
+        self.log.append("wait")
+        for k, v in ev.snapshot.items():
+            self.clock[k] = max(self.clock.get(k, -1), v)
+
+
+class _SimEvent:
+    created = 0
+
+    def __init__(self):
+        _SimEvent.created += 1
+        self.snapshot = None
+
+    def record(self, stream):
+        stream.log.append("record")
+        self.snapshot = dict(stream.clock)
+
+
+def _simulate(monkeypatch, sched, args):
+    """Run the generated program of ``sched`` under the stream model; every tensor an op reads must have been produced at a time the
+    reading stream knows about. Returns (outputs, streams, number of events created)."""
+    caller = _SimStream(name="caller")
+    current = [caller]
+    produced = {}                                    # id(tensor) -> (stream name, time)
+
+    @contextlib.contextmanager
+    def use(stream):
+        current.append(stream)
+        try:
+            yield
+        finally:
+            current.pop()
+
+    monkeypatch.setattr(torch.cuda, "Stream", _SimStream)
+    monkeypatch.setattr(torch.cuda, "Event", _SimEvent)
+    monkeypatch.setattr(torch.cuda, "stream", use)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: current[-1])
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda *_: None)
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda *_: None)
+    monkeypatch.setattr(ind_utils, "_pools", {})
+    _SimEvent.created = 0
+    sched.codegen()
+    fn = sched.compile()
+
+    def tracked(target):
+        def run(*a, **k):
+            s = current[-1]
+            for t in S._tensors((a, k)):
+                if id(t) in produced:
+                    name, when, _ = produced[id(t)]
+                    assert s.knows(name, when), f"{getattr(target, '__name__', target)} on {s.name} reads a value of {name} it never waited for"
+            out = target(*a, **k)
+            now = s.tick()
+            for t in S._tensors(out):
+                produced[id(t)] = (s.name, now, t)       # holding the tensor keeps its id from being recycled
+            return out
+        return run
+
+    targets = fn.__globals__["_ts_t"]
+    targets[:] = [tracked(t) for t in targets]
+    now = caller.tick()
+    for t in S._tensors(args):
+        produced[id(t)] = ("caller", now, t)
+    out = fn(*args)
+    for t in S._tensors(out):                        # the caller's stream owns the results
+        name, when, _ = produced.get(id(t), ("caller", 0, None))
+        assert caller.knows(name, when), f"result produced on {name} is returned before the caller's stream waited for it"
+    streams = {s for s in fn.__globals__.values() if isinstance(s, _SimStream)}
+    for s in streams:                                # join: nothing a side stream did is left unordered
+        assert caller.knows(s.name, s.clock[s.name])
+    return out, streams, _SimEvent.created
+
+
+def _annotate(gm, *args):
+    """``example_value`` metadata (what dynamo attaches) for a hand-built graph."""
+    class Rec(torch.fx.Interpreter):
+        def run_node(self, n):
+            out = super().run_node(n)
+            n.meta["example_value"] = out
+            return out
+    Rec(gm).run(*args)
+    return gm
+
+
+def test_generated_program_stream_discipline(monkeypatch):
+    torch.manual_seed(0)
+    m = Branchy()
+    x = torch.randn(16, 64)
+    cm, graphs = _compile(m)
+    ref = m(x)
+    cm(x)
+    sg = graphs[0]
+    sched = MultiCudaStreamScheduler(sg.gm, multi_stream=True)
+    out, streams, n_events = _simulate(monkeypatch, sched, sg.last_args)
+    torch.testing.assert_close(out[0], ref)
+    src = sched.wrapper.source
+    assert len(streams) == 2 and n_events == 1 + 2                 # entrance event + one per branch
+    assert src.count("with torch.cuda.stream(") == 2 and src.count(".wait_event(event0)") == 2
+    assert src.count("default_stream.wait_event(") == 2 and "_ts_record_stream(y1, default_stream)" in src
+    assert src.index("h = ") < src.index("with torch.cuda.stream(stream1)")      # critical path is issued first, on the caller's stream
+
+
+def _random_graph(seed, n_ops=40):
+    g = torch.Generator().manual_seed(seed)
+    graph = torch.fx.Graph()
+    root = nn.Module()
+    root.w = nn.Parameter(torch.randn(64, 64, generator=g) / 8)
+    vals = [graph.placeholder("x0"), graph.placeholder("x1")]
+    w = graph.get_attr("w")
+    unary, binary = [torch.tanh, torch.relu, torch.sigmoid], [torch.add, torch.mul, torch.sub]
+    pick = lambda k: int(torch.randint(0, k, (1,), generator=g))                                  # noqa: E731
+    for _ in range(n_ops):
+        kind = pick(4)
+        a = vals[max(0, len(vals) - 1 - pick(6))] if pick(2) else vals[pick(len(vals))]
+        if kind == 0:
+            vals.append(graph.call_function(torch.matmul, (a, w)))
+        elif kind == 1:
+            vals.append(graph.call_function(unary[pick(3)], (a,)))
+        elif kind == 2:
+            vals.append(graph.call_function(binary[pick(3)], (a, vals[pick(len(vals))])))
+        else:
+            vals.append(graph.call_method("mul", (a, 0.5)))
+    leaves = [v for v in vals[2:] if not v.users]
+    graph.output(tuple(leaves))
+    return torch.fx.GraphModule(root, graph)
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("num_streams", [1, 3, 8])
+def test_generated_programs_of_random_dags_are_race_free_and_exact(monkeypatch, seed, num_streams):
+    gm = _random_graph(seed)
+    args = (torch.randn(8, 64), torch.randn(8, 64))
+    want = gm(*args)
+    _annotate(gm, *args)
+    sched = MultiCudaStreamScheduler(gm, num_streams=num_streams, multi_stream=True)
+    out, streams, n_events = _simulate(monkeypatch, sched, args)
+    for a, b in zip(out, want):
+        torch.testing.assert_close(a, b)
+    assert len(streams) <= num_streams
+    # every wait in the text refers to an event recorded earlier in the text, and no stream waits twice for the same record
+    lines = [ln.strip() for ln in sched.wrapper.source.splitlines()]
+    live = {"event0"}
+    for ln in lines:
+        if ".record(" in ln:
+            live.add(ln.split(".record(")[0])
+        elif ".wait_event(" in ln:
+            assert ln.split(".wait_event(")[1].split(")")[0] in live
+
+
+def test_event_reuse_bounds_the_number_of_events(monkeypatch):
+    gm = _random_graph(3, n_ops=60)
+    args = (torch.randn(8, 64), torch.randn(8, 64))
+    _annotate(gm, *args)
+    with ts_config.patch(reuse_cuda_event=True):
+        _, _, reused = _simulate(monkeypatch, MultiCudaStreamScheduler(gm, num_streams=4, multi_stream=True), args)
+    with ts_config.patch(reuse_cuda_event=False):
+        sched = MultiCudaStreamScheduler(gm, num_streams=4, multi_stream=True)
+        _, _, fresh = _simulate(monkeypatch, sched, args)
+    n_compute = sum(n.op in S._COMPUTE_OPS for n in gm.graph.nodes)
+    assert reused < fresh <= n_compute + 1
+
+
+def test_event_factory_lifecycle():
+    f = CudaEventFactory(reuse_cuda_event=True)
+    e0 = f.get_entrance_event()
+    assert e0.materialized_event == "event0" and f.get_entrance_event() is e0
+    a, b = f.get_sym_event(1), f.get_sym_event(2)
+    assert a < b and a != b and len({a, b, f.get_sym_event(1)}) == 3 and "idx=1" in str(a)
+    with pytest.raises(ValueError):
+        a.wait(1)
+
+    class Code:
+        def __init__(self):
+            self.lines = []
+
+        def writeline(self, s):
+            self.lines.append(s)
+
+    code = Code()
+    rec_a, wait_a, wait_a2, rec_b = a.record(1), a.wait(0), a.wait(2), b.record(2)
+    rec_a.codegen(code)
+    wait_a.codegen(code)
+    assert a.materialized_event == "event1"
+    wait_a2.codegen(code)
+    assert a.materialized_event is None and f.available_materialized_events == ["event1"]
+    rec_b.codegen(code)                                      # nobody waits for b: no line, no event
+    assert code.lines == ["event1.record(stream1)", "default_stream.wait_event(event1)", "stream2.wait_event(event1)  # last wait of event 1"]
+    c = f.get_sym_event(1)
+    lines = [c.record(1), c.wait(0)]
+    for ln in lines:
+        ln.codegen(code)
+    assert code.lines[-2:] == ["event1.record(stream1)", "default_stream.wait_event(event1)  # last wait of event 4"] and f.created == ["event1"]
+
+
+def test_stream_pool_names_and_reuse(monkeypatch):
+    monkeypatch.setattr(torch.cuda, "Stream", _SimStream)
+    assert ind_utils.get_stream_name(0) == "default_stream" and ind_utils.get_stream_name(3) == "stream3"
+    pool = ind_utils.CUDAStreamPool(pool_size=2)
+    a = pool.acquire()
+    b = pool.acquire()
+    with pytest.raises(RuntimeError):
+        pool.acquire()
+    pool.release(a)
+    assert pool.acquire() is a and pool.side_stream(2) is b
+    with pytest.raises(IndexError):
+        pool.side_stream(3)
+
+
+def test_config_parsing_and_code_dump(tmp_path):
+    assert ts_config._parse_ids("1,2,3-5,7-8") == {1, 2, 3, 4, 5, 7, 8} and ts_config._parse_ids("") == set()
+    assert ts_config._parse_dump("+inductor,/tmp/x") == (["torchsched", "inductor"], "/tmp/x")
+    assert ts_config._parse_dump("rel/dir")[0] == ["torchsched"] and ts_config._parse_dump("")[1] is None
+    from apex_b200.contrib.torchsched.inductor import lower_graph
+    gm = _random_graph(1, n_ops=6)
+    args = (torch.randn(2, 64), torch.randn(2, 64))
+    _annotate(gm, *args)
+    with ts_config.patch(dump_code_dir=str(tmp_path), dump_code_backends=["torchsched", "inductor"]):
+        fn = lower_graph(gm, graph_id=7, multi_stream=False)
+    for a, b in zip(fn(*args), gm(*args)):
+        torch.testing.assert_close(a, b)
+    assert (tmp_path / "torchsched" / "graph_7_wrapper_code.py").read_text() == fn.source
+    assert "def forward" in (tmp_path / "inductor" / "graph_7_wrapper_code.py").read_text()
