@@ -112,17 +112,7 @@ def torchsched_compile(model=None, **kwargs):
     return torch.compile(model, **kwargs) if model is not None else (lambda m: torch.compile(m, **kwargs))
 
 
-def get_backend(backend: str = "torch", scheme: str = "dwb"):
-    """``"torchsched"`` -> this package's backend callable; ``"torch"`` / ``"inductor"`` -> the stock Inductor backend name. ``scheme`` picks the
-    order in which the reference splits convolution backward ("dwb" / "wbd", backend.py:262-330); backward is run by the autograd engine
-    here, so it is validated and otherwise unused."""
-    if scheme not in ("dwb", "wbd"):
-        raise ValueError(f"Invalid {scheme=}, use scheme=dwb or wbd instead")
-    if backend in ("torch", "inductor"):
-        return "inductor"
-    if backend != "torchsched":
-        raise ValueError(f"Unknown compilation {backend=}")
-    return torchsched
+from .backend import DecompositionsWrapper, get_backend  # noqa: E402,F401
 
 
 def list_backends():
@@ -143,5 +133,5 @@ try:  # register so torch.compile(backend="torchsched") resolves
 except Exception:  # noqa: BLE001
     pass
 
-__all__ = ["StreamScheduler", "capture_graph", "set_default_backend", "config", "torchsched", "torchsched_compile", "get_backend", "list_backends",
+__all__ = ["DecompositionsWrapper", "StreamScheduler", "capture_graph", "set_default_backend", "config", "torchsched", "torchsched_compile", "get_backend", "list_backends",
            "ScheduledGraph", "Plan", "plan_graph", "replace_layer_norm", "fused_layer_norm_op"]

@@ -53,6 +53,17 @@ def _target_name(node: fx.Node) -> str:
     return t if isinstance(t, str) else getattr(t, "__name__", str(t))
 
 
+_VIEW_NAMES = frozenset(("view", "view_as", "t", "transpose", "permute", "expand", "expand_as", "unsqueeze", "squeeze", "detach", "narrow",
+                         "select", "unbind", "chunk", "split", "unflatten", "alias"))
+
+
+def _is_view(node: fx.Node) -> bool:
+    """Metadata-only ops launch nothing: they cost nothing and stay on their producer's stream."""
+    if isinstance(node.target, torch._ops.OpOverload):
+        return bool(node.target.is_view)
+    return node.op in ("call_method", "call_function") and _target_name(node) in _VIEW_NAMES
+
+
 def estimate_cost(node: fx.Node, modules: dict | None = None) -> float:
     """Seconds, from the fake-tensor metadata: max(bytes moved / HBM rate, matmul FLOPs / tensor rate) + one launch. Nodes without
     tensor outputs (shape arithmetic, getitem) are free."""
@@ -60,7 +71,7 @@ def estimate_cost(node: fx.Node, modules: dict | None = None) -> float:
         return 0.0
     out = _example(node)
     out_bytes = _nbytes(out)
-    if out_bytes == 0 or node.target is operator.getitem:
+    if out_bytes == 0 or node.target is operator.getitem or _is_view(node):
         return 0.0
     in_bytes = sum(_nbytes(_example(a)) for a in node.all_input_nodes)
     name = _target_name(node)
@@ -81,6 +92,8 @@ def _mutates(node: fx.Node) -> bool:
     if node.op == "call_method" and isinstance(node.target, str) and node.target.endswith("_") and not node.target.endswith("__"):
         return True
     if node.op == "call_function":
+        if isinstance(node.target, torch._ops.OpOverload):      # ATen-level graphs (AOT autograd): the schema says it
+            return node.target._schema.is_mutable
         if node.target in (operator.setitem, operator.iadd, operator.isub, operator.imul, operator.itruediv):
             return True
         if "out" in node.kwargs or _target_name(node).endswith("_"):

@@ -413,3 +413,179 @@ def test_config_parsing_and_code_dump(tmp_path):
         torch.testing.assert_close(a, b)
     assert (tmp_path / "torchsched" / "graph_7_wrapper_code.py").read_text() == fn.source
     assert "def forward" in (tmp_path / "inductor" / "graph_7_wrapper_code.py").read_text()
+
+
+# ---- backend: decompositions, AOT-autograd mode, pre-grad passes, graph-level LayerNorm ops ------------------------------------------------
+from apex_b200.contrib.torchsched import backend as ts_backend                                    # noqa: E402
+from apex_b200.contrib.torchsched.ops import layer_norm as ts_ln                                  # noqa: E402
+from apex_b200.contrib.torchsched.passes import pre_grad_passes as ts_passes                      # noqa: E402
+
+
+class ConvNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.c1, self.c2 = nn.Conv2d(4, 8, 3, padding=1), nn.Conv2d(8, 8, 3, padding=1, stride=2)
+        self.ln, self.fc = nn.LayerNorm(8), nn.Linear(8, 4)
+
+    def forward(self, x):
+        h = F.relu(self.c1(x))
+        return self.fc(self.ln(self.c2(h).permute(0, 2, 3, 1))).sum(-1)
+
+
+@pytest.mark.parametrize("scheme", ["dwb", "wbd"])
+def test_convolution_backward_decompositions_match_the_fused_call(monkeypatch, scheme):
+    torch.manual_seed(0)
+    x, w, go = torch.randn(2, 4, 9, 9), torch.randn(6, 2, 3, 3), torch.randn(2, 6, 5, 5)
+    geometry = ([6], [2, 2], [1, 1], [1, 1], False, [0, 0], 2)
+    decomp = getattr(ts_backend, f"convolution_backward_decomp_{scheme}")
+    assert decomp(go, x, w, *geometry, [True, True, True]) is NotImplemented          # CPU tensors: nothing to overlap, stay fused
+    monkeypatch.setattr(ts_backend, "_SPLIT_DEVICES", {"cuda", "cpu"})
+    assert decomp(go, x, w, *geometry, [True, True, False]) is NotImplemented         # no bias gradient asked for: stay fused
+    want = torch.ops.aten.convolution_backward(go, x, w, *geometry, [True, True, True])
+    for got, ref in zip(decomp(go, x, w, *geometry, [True, True, True]), want):
+        torch.testing.assert_close(got, ref)
+    dx, dw, db = decomp(go, x, w, *geometry, [False, True, True])
+    assert dx is None
+    torch.testing.assert_close(dw, want[1])
+    torch.testing.assert_close(db, want[2])
+
+
+@pytest.mark.parametrize("scheme", ["dwb", "wbd"])
+def test_aot_mode_schedules_forward_and_backward_graphs(monkeypatch, scheme):
+    monkeypatch.setattr(ts_backend, "_SPLIT_DEVICES", {"cuda", "cpu"})
+    torch._dynamo.reset()
+    torch.manual_seed(0)
+    m = ConvNet()
+    x = torch.randn(2, 4, 8, 8, requires_grad=True)
+    be = ts.get_backend("torchsched", scheme)
+    assert isinstance(be, ts.DecompositionsWrapper) and be == ts.get_backend("torchsched", scheme) and be != ts.get_backend("torchsched", "dwb" if scheme == "wbd" else "wbd")
+    with ts_config.patch(aot_autograd=True):
+        out = torch.compile(m, backend=be)(x)
+    ref = m(x)
+    torch.testing.assert_close(out, ref)
+    params = list(m.parameters())
+    for g, r in zip(torch.autograd.grad(out.sum(), [x] + params), torch.autograd.grad(ref.sum(), [x] + params)):
+        torch.testing.assert_close(g, r, atol=1e-4, rtol=1e-4)
+    fw, bw = be.graphs
+    assert bw.graph_id == fw.graph_id + 1
+    fw_names, bw_names = [n.name for n in fw.plan.order], [n.name for n in bw.plan.order]
+    assert "norm_fwd" in fw_names and "norm_bwd" in bw_names                         # LayerNorm is one fused node in each direction
+    # each convolution's backward became separate weight / bias / data gradient nodes, in the scheme's order, on more than one stream
+    convs = [n for n in bw.plan.order if n.target is torch.ops.aten.convolution_backward.default]
+    sums = [n for n in bw.plan.order if n.target is torch.ops.aten.sum.dim_IntList and n.args[1] == [0, 2, 3]]
+    assert len(convs) == 4 and len(sums) == 2
+    masks = [tuple(n.args[-1]) for n in convs]
+    want = [(True, False, False), (False, True, False)] if scheme == "dwb" else [(False, True, False), (True, False, False)]
+    assert masks == want * 2
+    assert len({bw.plan.stream_of[n] for n in convs + sums}) >= 3
+    assert all(fw.plan.cost[n] == 0.0 for n in fw.plan.order if n.name.startswith(("detach", "view", "t")))   # views launch nothing
+
+
+def test_aot_mode_with_generated_programs(monkeypatch):
+    monkeypatch.setattr(ts_backend, "_SPLIT_DEVICES", {"cuda", "cpu"})
+    torch._dynamo.reset()        # equal DecompositionsWrappers share dynamo's cache entry: start from a clean one
+    torch.manual_seed(0)
+    m = ConvNet()
+    x = torch.randn(2, 4, 8, 8, requires_grad=True)
+    be = ts.get_backend("torchsched")
+    compile_fn = ts_backend.enable_multi_stream_scheduling(lambda: torch.compile(m, backend=be)(x))
+    with ts_config.patch(aot_autograd=True):
+        out = compile_fn()
+    assert not ts_config.wrapper_codegen and all(sg.wrapper_codegen for sg in be.graphs)
+    ref = m(x)
+    torch.testing.assert_close(out, ref)
+    torch.testing.assert_close(torch.autograd.grad(out.sum(), x)[0], torch.autograd.grad(ref.sum(), x)[0], atol=1e-4, rtol=1e-4)
+    assert "convolution_backward" in be.graphs[1].program().source
+
+
+def test_aot_backward_program_is_race_free(monkeypatch):
+    monkeypatch.setattr(ts_backend, "_SPLIT_DEVICES", {"cuda", "cpu"})
+    torch._dynamo.reset()
+    torch.manual_seed(0)
+    m = ConvNet()
+    x = torch.randn(2, 4, 8, 8, requires_grad=True)
+    be = ts.get_backend("torchsched")
+    captured = {}
+    orig = be._schedule
+
+    def keep(gm, example_inputs=None, wrapper_codegen=None):
+        sg = orig(gm, example_inputs)
+
+        class Spy:
+            def __call__(self, *a):
+                captured[sg.graph_id] = a
+                return sg(*a)
+        return Spy()
+
+    be._schedule = keep
+    with ts_config.patch(aot_autograd=True):
+        out = torch.compile(m, backend=be)(x)
+    out.sum().backward()
+    fw, bw = be.graphs
+    want = bw(*captured[bw.graph_id])
+    sched = MultiCudaStreamScheduler(bw.gm, multi_stream=True)
+    got, streams, _ = _simulate(monkeypatch, sched, captured[bw.graph_id])
+    assert len(streams) >= 3
+    for a, b in zip(got, want):
+        if a is not None:
+            torch.testing.assert_close(a, b)
+
+
+def test_get_backend_arguments():
+    assert ts.get_backend("torch") == "inductor" and ts.get_backend("inductor") == "inductor"
+    with pytest.raises(ValueError):
+        ts.get_backend("tvm")
+    with pytest.raises(ValueError):
+        ts.get_backend("torchsched", "bdw")
+
+
+def test_pre_grad_pass_normalises_arguments_and_counts():
+    def f(x, w, b):
+        return F.layer_norm(x, (16,), bias=b, weight=w) + F.layer_norm(x, (16,), w, b, 1e-3) + F.layer_norm(x, (16,))
+
+    gm = torch.fx.symbolic_trace(f)
+    calls = []
+
+    def spy(x, normalized_shape, weight, bias, eps):
+        calls.append((tuple(normalized_shape), weight is not None, bias is not None, eps))
+        return F.layer_norm(x, normalized_shape, weight, bias, eps)
+
+    assert ts_passes.run_pre_grad_pass("spy", gm.graph, F.layer_norm, spy) == 3
+    x, w, b = torch.randn(4, 16), torch.randn(16), torch.randn(16)
+    torch.testing.assert_close(gm(x, w, b), f(x, w, b))
+    assert calls == [((16,), True, True, 1e-5), ((16,), True, True, 1e-3), ((16,), False, False, 1e-5)]
+    assert ts_passes.run_pre_grad_pass("spy", gm.graph, F.layer_norm, spy) == 0
+    with pytest.raises(ValueError):
+        ts_passes.register_pattern("fused_layer_norm", F.layer_norm, spy)
+    gm2 = torch.fx.symbolic_trace(f)
+    before = ts_passes.counters.get("pre_grad_fused_layer_norm", 0)
+    ts_passes.pre_grad_custom_pass(gm2.graph, traceable=True)
+    assert ts_passes.counters["pre_grad_fused_layer_norm"] == before + 3
+    assert sum(n.target is ts_passes.replace_layer_norm_traceable for n in gm2.graph.nodes) == 3
+    with ts_config.patch(pre_grad_pass_options=["nope"]), pytest.raises(AssertionError):
+        ts_passes.pre_grad_custom_pass(gm2.graph)
+    torch.testing.assert_close(ts_passes.replace_layer_norm(x, (16,), w, b, 1e-5), F.layer_norm(x, (16,), w, b, 1e-5))
+
+
+def test_graph_level_layer_norm_ops():
+    torch.manual_seed(0)
+    x = torch.randn(3, 5, 32, requires_grad=True)
+    w, b = torch.randn(32, requires_grad=True), torch.randn(32, requires_grad=True)
+    y, mean, invstd = ts_ln.layer_norm(x, [32], w, b, 1e-5)
+    ref = F.layer_norm(x, (32,), w, b, 1e-5)
+    torch.testing.assert_close(y, ref)
+    torch.testing.assert_close(mean, x.detach().reshape(15, 32).mean(1))
+    for got, want in zip(ts_ln.layer_norm_fake(x, [32], w, b), (y, mean, invstd)):
+        assert got.shape == want.shape and got.dtype == want.dtype
+    gy = torch.randn_like(y)
+    dx, dw, db = ts_ln.layer_norm_backward(gy, mean, invstd, x.detach(), [32], w.detach(), b.detach())
+    rx, rw, rb = torch.autograd.grad(ref, [x, w, b], gy)
+    torch.testing.assert_close(dx, rx, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(dw, rw, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(db, rb, atol=1e-5, rtol=1e-5)
+    for got, want in zip(ts_ln.layer_norm_backward_fake(gy, mean, invstd, x, [32], w, b), (dx, dw, db)):
+        assert got.shape == want.shape
+    ax, = torch.autograd.grad(y, x, gy)                                              # the op itself is differentiable
+    torch.testing.assert_close(ax, rx, atol=1e-5, rtol=1e-5)
+    with pytest.raises(ValueError):
+        ts_ln.layer_norm(x, [16], w, b)
