@@ -17,6 +17,7 @@ documents and parses the environment variables the library reads.
 | ``APEX_B200_GN_STREAM_MIN_MB`` | unset | GroupNorm: activation size (MB) from which the two-pass streaming kernels replace the slab kernels (default rule: backward slabs >= 300 KB) |
 | ``APEX_B200_MT_CHUNK`` / ``APEX_B200_MT_GRID_MULT`` | ``65536`` / ``12`` | multi-tensor engine: elements per work item / CTAs per SM of the persistent grid |
 | ``TORCH_SCHED_NUM_STREAMS`` (+ ``_DEBUG``, ``_SKIP_GRAPH_IDS``, ``_REUSE_CUDA_EVENT``, ``_DUMP_CODE``) | ``8`` | torchsched analogue (same names as the reference) |
+| ``TORCH_SCHED_CODEGEN`` / ``TORCH_SCHED_AOT`` | ``0`` / ``0`` | torchsched: run the generated multi-stream program instead of the interpreter / schedule forward AND backward graphs through AOT autograd |
 """
 from __future__ import annotations
 
