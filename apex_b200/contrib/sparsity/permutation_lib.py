@@ -157,6 +157,34 @@ def _expand(perm, rep):
     return (p.view(-1, 1) * rep + torch.arange(rep).view(1, -1)).reshape(-1)
 
 
+# ---- name helpers of the reference's module-level API (permutation_lib.py:24-85) -------------------------------------------------------
+def convert_fx_node_name(fx_node_name: str) -> str:
+    """fx spells ``layer1.0.conv1`` as ``layer1_0_conv1``: back to dots (ambiguous for names that contain underscores themselves, which is
+    why :func:`node_name_matches` compares without punctuation)."""
+    return fx_node_name.replace("_", ".")
+
+
+def get_node_parent_children(fx_node):
+    """(names of the nodes feeding ``fx_node``, names of the nodes reading it), dotted."""
+    return ([convert_fx_node_name(n.name) for n in fx_node.all_input_nodes], [convert_fx_node_name(n.name) for n in fx_node.users])
+
+
+def node_name_matches(node_name: str, module_name: str) -> bool:
+    """Does a graph node name denote the module called ``module_name``? Punctuation and case are ignored, and a DDP-wrapped model's
+    ``module.`` prefix on the module side is accepted."""
+    def squash(name):
+        return "".join(ch for ch in name.lower() if ch.isalnum())
+
+    a, b = squash(node_name), squash(module_name)
+    return node_name == module_name or a == b or "module." + node_name == module_name or "module" + a == b
+
+
+def replicate_sequence(sequence, replications: int) -> list:
+    """A permutation of C channels applied to ``replications`` consecutive blocks of C (what a flatten in front of a classifier needs)."""
+    n = len(sequence)
+    return [int(c) + n * r for r in range(replications) for c in sequence]
+
+
 class Permutation:
     __verbosity = 0
     __seed = 1

@@ -235,3 +235,263 @@ def efficacy(optimal_lost_magnitude, base_lost_magnitude, cur_lost_magnitude):
     if base_lost_magnitude == optimal_lost_magnitude:
         return 100.0
     return 100.0 * (base_lost_magnitude - cur_lost_magnitude) / (base_lost_magnitude - optimal_lost_magnitude)
+
+
+# ----------------------------------------------------------------------------------------------------------- analysis utilities
+# The helper surface of the reference's permutation_utilities.py / exhaustive_search.py / channel_swap.py that its analysis scripts and
+# tests use (apply_2_to_4, try_swap, search_matrix, permutation_distance, ...). Matrices may be numpy arrays or tensors; results come back
+# in the kind that went in. Everything is vectorised over rows (the reference loops over rows and stripes in Python on its CPU path).
+def _t(matrix) -> torch.Tensor:
+    return matrix if isinstance(matrix, torch.Tensor) else torch.as_tensor(np.asarray(matrix))
+
+
+def _back(result: torch.Tensor, like):
+    return result if isinstance(like, torch.Tensor) else result.cpu().numpy()
+
+
+def use_gpu(initial_override: bool = True) -> bool:
+    """Whether candidate scoring runs in csrc/perm_search.cu (reference permutation_utilities.py:23-43 probes nvidia-smi and the extension)."""
+    return bool(initial_override) and torch.cuda.is_available() and _lib.available()
+
+
+def apply_2_to_4(matrix):
+    """Zero the two smallest magnitudes of every group of 4 adjacent columns, in place (reference :46-52)."""
+    m = _t(matrix)
+    R, C = m.shape
+    drop = m.abs().reshape(R, C // 4, 4).argsort(dim=-1)[..., :2]                      # the two smallest of each group
+    mask = torch.ones(R, C // 4, 4, dtype=torch.bool, device=m.device).scatter_(-1, drop, False).reshape(R, C)
+    if isinstance(matrix, torch.Tensor):
+        matrix.mul_(mask)
+    else:
+        matrix[~mask.numpy()] = 0
+    return matrix
+
+
+def unstructured_prune(matrix, sparsity: float):
+    """Zero the ``sparsity`` fraction of entries with the smallest magnitude (whole-matrix ranking). The reference (:87-94) ranks by signed
+    value; its callers pass magnitudes, for which the two agree."""
+    m = _t(matrix).clone()
+    k = int(m.numel() * sparsity)
+    if k:
+        flat = m.reshape(-1)
+        flat[flat.abs().argsort()[:k]] = 0
+    return _back(m, matrix)
+
+
+def magnitude_after_pruning_rows(matrix, rate: float = 0.5):
+    """Magnitude kept when every row independently drops its ``rate`` smallest entries: the bound no column permutation can beat (:127-135)."""
+    a = _t(matrix).abs().float()
+    return float(a.sort(dim=1).values[:, int(a.shape[1] * rate):].sum())
+
+
+def _stripe_of(col: int) -> slice:
+    return slice(col // 4 * 4, col // 4 * 4 + 4)
+
+
+def try_swap(matrix, dst: int, src: int):
+    """(magnitude the two touched stripes keep after swapping columns ``src`` and ``dst``, improvement over not swapping) — the matrix is
+    left as it was (:98-112)."""
+    m = _t(matrix).float()
+    before = float(sum_after_2_to_4(m[:, _stripe_of(src)].contiguous())) + float(sum_after_2_to_4(m[:, _stripe_of(dst)].contiguous()))
+    sw = m.clone()
+    sw[:, [src, dst]] = m[:, [dst, src]]
+    after = float(sum_after_2_to_4(sw[:, _stripe_of(src)].contiguous())) + float(sum_after_2_to_4(sw[:, _stripe_of(dst)].contiguous()))
+    if src // 4 == dst // 4:            # same stripe: one stripe counted twice on both sides, nothing can change
+        return after, 0.0
+    return after, after - before
+
+
+def try_permutations_on_matrix(matrix, permutations):
+    """(best improvement over the identity order, the permutation that achieves it) among ``permutations`` [P, C] (:144-171)."""
+    m = _t(matrix).float()
+    perms = torch.as_tensor(np.asarray(permutations).astype(np.int64))
+    base = float(sum_after_2_to_4(m))
+    best_v, best_i = -float("inf"), 0
+    for c0 in range(0, perms.shape[0], 16384):
+        sc = sum_after_2_to_4(m, perms[c0:c0 + 16384].int())
+        v, i = sc.max(0)
+        if float(v) > best_v:
+            best_v, best_i = float(v), c0 + int(i)
+    return best_v - base, np.asarray(permutations)[best_i]
+
+
+def find_permutation(A, B) -> list:
+    """For every column of A, the index of an identical column of B (:174-182); columns without a twin are skipped, like the reference."""
+    a, b = _t(A), _t(B)
+    eq = (a.T[:, None, :] == b.T[None, :, :]).all(-1)                                  # [colsA, colsB]
+    return [int(row.float().argmax()) for row in eq if bool(row.any())]
+
+
+def predict_unique_combinations(C: int, M: int) -> int:
+    """Number of ways to deal C columns into C/M unordered groups of M: C! / (M!^(C/M) (C/M)!) (exhaustive_search.py:102-105), in
+    exact integer arithmetic (the reference goes through floats and loses the low digits beyond 2^53)."""
+    import math
+
+    assert C % M == 0
+    G = C // M
+    return math.factorial(C) // (math.factorial(M) ** G * math.factorial(G))
+
+
+def is_canonical(perm, col: int) -> bool:
+    """May ``col`` extend the partial arrangement ``perm`` in canonical form (groups ascending inside, ordered by first element)?
+    (exhaustive_search.py:21-32)"""
+    if len(perm) % 4 == 0:
+        return all(v in perm for v in range(col)) and (len(perm) == 0 or col > perm[-4])
+    return col > perm[-1]
+
+
+def search_matrix(matrix, group_width: int = 4):
+    """Try every distinct arrangement of the whole matrix (<= 16 columns in practice): (permuted matrix, seconds, permutation,
+    improvement); refuses with (matrix, prediction, identity) beyond 1e10 candidates (exhaustive_search.py:114-148)."""
+    start = time.perf_counter()
+    C = matrix.shape[1]
+    prediction = predict_unique_combinations(C, group_width)
+    identity = list(range(C))
+    if prediction > 1e10:
+        print(f"There are {prediction} unique combinations with {C} columns and a group width of {group_width}, not searching.")
+        return matrix, prediction, identity
+    if group_width != 4:
+        raise NotImplementedError("scoring is 2:4 specific: group_width must be 4")
+    improvement, perm = try_permutations_on_matrix(matrix, generate_all_unique_combinations(C, group_width))
+    if improvement <= 0:
+        improvement, perm = 0.0, np.asarray(identity)
+    perm = [int(c) for c in perm]
+    return matrix[:, perm], time.perf_counter() - start, perm, improvement
+
+
+def generate_stripe_groups(num_stripes: int, window_size: int) -> set:
+    """All ascending ``window_size``-tuples of stripe indices (exhaustive_search.py:184-199)."""
+    return set(itertools.combinations(range(num_stripes), window_size))
+
+
+def collect_stripes(matrix, stripes, group_width: int = 4):
+    """The columns of the listed stripes, side by side (exhaustive_search.py:156-162)."""
+    cols = [s * group_width + k for s in stripes for k in range(group_width)]
+    return matrix[:, cols]
+
+
+def apply_stripe_group_permutation(sgp, stripes, group_width: int, permutation):
+    """Fold a permutation ``sgp`` of the columns gathered by :func:`collect_stripes` back into the full-width ``permutation``
+    (exhaustive_search.py:166-180)."""
+    cols = np.asarray([s * group_width + k for s in stripes for k in range(group_width)])
+    out = np.array(permutation, copy=True)
+    out[cols] = np.asarray(permutation)[cols[np.asarray(sgp, dtype=np.int64)]]
+    return out if isinstance(permutation, np.ndarray) else out.tolist()
+
+
+def stripes_and_swap_idx_to_columns(stripe0: int, stripe1: int, idx: int):
+    """Swap number ``idx`` (0..15) between two stripes -> the two matrix columns it exchanges (channel_swap.py:30-37)."""
+    if not 0 <= idx < 16:
+        return None
+    return stripe0 * 4 + idx // 4, stripe1 * 4 + idx % 4
+
+
+def columns_to_stripes_and_swap_idx(col0: int, col1: int):
+    """Inverse of :func:`stripes_and_swap_idx_to_columns` (channel_swap.py:41-53)."""
+    return col0 // 4, col1 // 4, (col0 % 4) * 4 + col1 % 4
+
+
+def build_stripe_pairs(matrix, used_stripes):
+    """Stripe pairs whose swap scores are stale because one of their stripes changed (channel_swap.py:57-67)."""
+    total = matrix.shape[1] // 4
+    used = set(int(s) for s in used_stripes)
+    return np.asarray([[a, b] for a in range(total - 1) for b in range(a, total) if a in used or b in used])
+
+
+# ---- distance between two permutations: how many column swaps turn B's grouping into A's ---------------------------------------------
+def make_grouped(A, width: int = 4) -> list:
+    """The permutation as a list of groups of ``width``, each sorted (order inside a stripe does not matter to 2:4 pruning)."""
+    A = [int(v) for v in A]
+    return [sorted(A[i:i + width]) for i in range(0, len(A), width)]
+
+
+def _group_sets(A):
+    return {tuple(g) for g in make_grouped(A)}
+
+
+def common_groups(A, B) -> list:
+    return [list(g) for g in sorted(_group_sets(A) & _group_sets(B))]
+
+
+def remove_common_groups(A, B):
+    """(A, B) without the groups they share, flattened again in canonical order."""
+    sa, sb = _group_sets(A), _group_sets(B)
+    return [v for g in sorted(sa - sb) for v in g], [v for g in sorted(sb - sa) for v in g]
+
+
+def group_differences(A, B) -> list:
+    """(value, its group in B, the group of A that holds it) for every value of B that sits in a different group position than in A."""
+    where_a = {v: i for i, g in enumerate(make_grouped(A)) for v in g}
+    return [(v, i, where_a[v]) for i, g in enumerate(make_grouped(B)) for v in g if where_a[v] != i]
+
+
+def dictify(wrong_entries) -> dict:
+    out: dict = {}
+    for val, cur, want in wrong_entries:
+        out.setdefault((cur, want), []).append(val)
+    return out
+
+
+def move_groups_to_match(B, A, debug: bool = False) -> list:
+    """B with its groups reordered so that group i of B is the one sharing the most values with group i of A (an assignment problem;
+    the reference resolves it greedily, permutation_utilities.py:286-401)."""
+    from scipy.optimize import linear_sum_assignment
+
+    ga, gb = make_grouped(A), make_grouped(B)
+    overlap = np.array([[len(set(x) & set(y)) for y in gb] for x in ga])
+    rows, cols = linear_sum_assignment(-overlap)
+    order = [int(cols[list(rows).index(i)]) for i in range(len(ga))]
+    return [v for i in order for v in gb[i]]
+
+
+def swap_and_correct(permutation, src: int, tgt: int) -> list:
+    """Exchange positions ``src`` and ``tgt`` and return the permutation in canonical (sorted inside groups) form."""
+    p = [int(v) for v in permutation]
+    p[src], p[tgt] = p[tgt], p[src]
+    return [v for g in make_grouped(p) for v in g]
+
+
+def move_permutation_towards(B, A, debug: bool = False) -> list:
+    """One swap of B that moves its grouping towards A's: prefer a swap that puts BOTH exchanged values into their groups."""
+    B = move_groups_to_match(B, A, debug)
+    wrong = dictify(group_differences(A, B))
+    if not wrong:
+        return B
+    pos = {v: i for i, v in enumerate(B)}
+    for (cur, want), vals in wrong.items():
+        if (want, cur) in wrong:                                  # two values that want each other's group
+            return swap_and_correct(B, pos[vals[0]], pos[wrong[(want, cur)][0]])
+    (cur, want), vals = next(iter(wrong.items()))
+    partner = next(v for (c, _), vs in wrong.items() if c == want for v in vs)     # somebody in the wanted group is misplaced too
+    return swap_and_correct(B, pos[vals[0]], pos[partner])
+
+
+def permutation_distance(A, B, matrix=None, magnitude_targets=None, debug: bool = False, verbosity: int = 0):
+    """(number of swaps that turn B's grouping into A's, per magnitude target the (magnitude, permutation) met on the way that came
+    closest to it — or None). Reference permutation_utilities.py:558-618."""
+    A, B = [int(v) for v in A], [int(v) for v in B]
+    swaps, common = 0, []
+    limit = 2 ** max(len(A) // 4 - 1, 0) + 3
+    results = None
+    if magnitude_targets is not None:
+        assert matrix is not None, "magnitude targets need the matrix"
+        start = float(sum_after_2_to_4(_t(matrix).float()[:, A].contiguous()))
+        results = [(start, list(A)) for _ in magnitude_targets]
+    while _group_sets(A) != _group_sets(B):
+        common += [v for g in common_groups(A, B) for v in g]
+        A, B = remove_common_groups(A, B)
+        if not A:
+            break
+        B = move_permutation_towards(B, A, debug)
+        swaps += 1
+        if matrix is not None and (results is not None or verbosity > 0):
+            full = B + common
+            mag = float(sum_after_2_to_4(_t(matrix).float()[:, full].contiguous()))
+            for i, target in enumerate(magnitude_targets or ()):
+                if abs(target - mag) < abs(target - results[i][0]):
+                    results[i] = (mag, full)
+            if verbosity > 0:
+                print(f"swap {swaps:>4} {mag:>15.3f}")
+        if swaps > limit:
+            break
+    return swaps, results

@@ -248,3 +248,114 @@ def test_only_asp_sparse_consumers_drive_the_search():
     assert P.permute_model(model) == []
     P.set_permutation_params_from_asp(model, [("2", model[2], "weight", model[2].weight, None, None)])
     assert len(P.permute_model(model)) == 1
+
+
+# ---- analysis utilities of permutation_search (reference permutation_utilities.py / exhaustive_search.py / channel_swap.py helpers) -----------
+def test_search_utilities_against_brute_force():
+    import itertools
+
+    import numpy as np
+
+    from apex_b200.contrib.sparsity import permutation_search as P
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((16, 8)).astype(np.float32)
+    assert P.predict_unique_combinations(8, 4) == len(P.generate_all_unique_combinations(8, 4)) == 35
+    assert P.predict_unique_combinations(12, 4) == 5775 and P.predict_unique_combinations(32, 4) == 59287247761257140625
+    out, secs, perm, imp = P.search_matrix(m)
+    keep = lambda a: float(np.sort(np.abs(a).reshape(a.shape[0], -1, 4), axis=-1)[..., 2:].sum())          # noqa: E731
+    best = max(keep(m[:, list(p)]) for p in itertools.permutations(range(8)) if p[0] == 0)                   # 5040 orders
+    assert abs(keep(out) - best) < 1e-4 and abs(imp - (best - keep(m))) < 1e-4 and sorted(perm) == list(range(8))
+    assert P.find_permutation(out, m) == perm
+    # a matrix that is already optimal: identity, zero improvement; too many columns: refuses
+    o2, _, p2, i2 = P.search_matrix(np.tile(np.array([[3.0, 2.0, 0.1, 0.1]], dtype=np.float32), (4, 2)))
+    assert p2 == list(range(8)) and i2 == 0.0
+    big = np.zeros((2, 40), dtype=np.float32)
+    assert P.search_matrix(big)[1] == P.predict_unique_combinations(40, 4)
+    # try_swap: consistent with rescoring the two stripes, leaves the matrix alone, same-stripe swaps change nothing
+    before = m.copy()
+    total, gain = P.try_swap(m, 1, 6)
+    sw = m.copy()
+    sw[:, [1, 6]] = sw[:, [6, 1]]
+    assert abs(total - keep(sw)) < 1e-4 and abs(gain - (keep(sw) - keep(m))) < 1e-4 and (m == before).all()
+    assert P.try_swap(m, 0, 3)[1] == 0.0
+    imp2, p = P.try_permutations_on_matrix(m, np.array([list(range(8)), perm]))
+    assert abs(imp2 - imp) < 1e-4 and list(p) == perm
+    # pruning helpers, numpy in -> numpy out, tensors in -> tensors out
+    pruned = P.apply_2_to_4(m.copy())
+    assert ((pruned != 0).reshape(16, 2, 4).sum(-1) == 2).all() and abs(np.abs(pruned).sum() - keep(m)) < 1e-4
+    t = torch.from_numpy(m.copy())
+    assert P.apply_2_to_4(t) is t and torch.equal(t, torch.from_numpy(pruned))
+    u = P.unstructured_prune(np.abs(m), 0.25)
+    assert isinstance(u, np.ndarray) and (u == 0).sum() == 32 and u.max() == np.abs(m).max()
+    rows = P.magnitude_after_pruning_rows(m)
+    assert abs(rows - float(np.sort(np.abs(m), axis=1)[:, 4:].sum())) < 1e-4 and rows >= best - 1e-4
+    assert P.use_gpu() is False or torch.cuda.is_available()
+
+
+def test_stripe_and_swap_index_helpers():
+    import numpy as np
+
+    from apex_b200.contrib.sparsity import permutation_search as P
+    assert P.generate_stripe_groups(4, 2) == {(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)}
+    m = np.arange(2 * 16).reshape(2, 16)
+    assert (P.collect_stripes(m, (1, 3)) == m[:, [4, 5, 6, 7, 12, 13, 14, 15]]).all()
+    full = list(range(16))
+    assert P.apply_stripe_group_permutation([0, 5, 2, 3, 4, 1, 6, 7], (1, 3), 4, full) == [0, 1, 2, 3, 4, 13, 6, 7, 8, 9, 10, 11, 12, 5, 14, 15]
+    for idx in range(16):
+        c0, c1 = P.stripes_and_swap_idx_to_columns(2, 5, idx)
+        assert P.columns_to_stripes_and_swap_idx(c0, c1) == (2, 5, idx) and c0 // 4 == 2 and c1 // 4 == 5
+    assert P.stripes_and_swap_idx_to_columns(0, 1, 16) is None
+    pairs = P.build_stripe_pairs(np.zeros((1, 16)), [2])
+    assert all(2 in p for p in pairs.tolist()) and [0, 2] in pairs.tolist() and [2, 3] in pairs.tolist()
+    assert P.is_canonical([], 0) and not P.is_canonical([], 1) and P.is_canonical([0, 2], 5) and not P.is_canonical([0, 5], 2)
+    assert P.is_canonical([0, 1, 2, 3], 4) and not P.is_canonical([0, 1, 2, 3], 5)
+    for row in P.generate_all_unique_combinations(8, 4)[:10]:
+        assert all(P.is_canonical(list(row[:i]), int(row[i])) for i in range(8))
+
+
+def test_permutation_distance():
+    import numpy as np
+
+    from apex_b200.contrib.sparsity import permutation_search as P
+    ident = list(range(16))
+    assert P.permutation_distance(ident, ident) == (0, None)
+    assert P.permutation_distance(ident, [3, 2, 1, 0, 7, 6, 5, 4, 8, 9, 10, 11, 12, 13, 14, 15])[0] == 0      # order inside / of stripes is free
+    assert P.permutation_distance(ident, [4, 5, 6, 7, 0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 15])[0] == 0
+    one = ident.copy()
+    one[1], one[9] = one[9], one[1]
+    assert P.permutation_distance(ident, one)[0] == 1
+    transposed = [0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15]
+    assert P.permutation_distance(ident, transposed)[0] == 6            # 12 misplaced values, two fixed per swap
+    rng = np.random.default_rng(1)
+    for _ in range(20):                                                # k random swaps are never further than k away
+        p, k = ident.copy(), int(rng.integers(1, 5))
+        for _ in range(k):
+            i, j = rng.choice(16, 2, replace=False)
+            p[i], p[j] = p[j], p[i]
+        d = P.permutation_distance(ident, p)[0]
+        assert d <= k and (d == 0) == (P._group_sets(ident) == P._group_sets(p))
+    assert P.make_grouped([3, 1, 2, 0, 7, 5, 6, 4]) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    assert P.common_groups(ident, one) == [[4, 5, 6, 7], [12, 13, 14, 15]]
+    a, b = P.remove_common_groups(ident, one)
+    assert a == [0, 1, 2, 3, 8, 9, 10, 11] and b == [0, 2, 3, 9, 1, 8, 10, 11]
+    assert P.group_differences(a, b) == [(9, 0, 1), (1, 1, 0)] and P.dictify([(9, 0, 1), (1, 1, 0), (7, 0, 1)]) == {(0, 1): [9, 7], (1, 0): [1]}
+    assert P.move_groups_to_match([8, 9, 10, 11, 0, 1, 2, 3], ident[:4] + ident[8:12]) == [0, 1, 2, 3, 8, 9, 10, 11]
+    assert P.swap_and_correct([0, 2, 3, 9, 1, 8, 10, 11], 3, 4) == [0, 1, 2, 3, 8, 9, 10, 11]
+    assert P.move_permutation_towards(b, a) == a
+    # magnitude targets: the permutation met on the way whose kept magnitude is closest to each target
+    m = rng.standard_normal((8, 16)).astype(np.float32)
+    from apex_b200.contrib.sparsity.permutation_search import sum_after_2_to_4
+    mag_a = float(sum_after_2_to_4(torch.from_numpy(m)))
+    swaps, results = P.permutation_distance(ident, transposed, matrix=m, magnitude_targets=[mag_a, 0.0])
+    assert swaps == 6 and results[0][0] == pytest.approx(mag_a) and sorted(results[1][1]) == ident
+
+
+def test_permutation_lib_name_helpers():
+    from apex_b200.contrib.sparsity import permutation_lib as L
+    assert L.convert_fx_node_name("layer1_0_conv1") == "layer1.0.conv1"
+    assert L.node_name_matches("layer1_0_conv1", "layer1.0.conv1") and L.node_name_matches("layer1.0.conv1", "module.layer1.0.conv1")
+    assert L.node_name_matches("Layer1_0_Conv1", "module.layer1.0.conv1") and not L.node_name_matches("layer1_0_conv1", "layer1.0.conv2")
+    assert L.replicate_sequence([2, 0, 1], 3) == [2, 0, 1, 5, 3, 4, 8, 6, 7]
+    gm = torch.fx.symbolic_trace(torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU()))
+    node = next(n for n in gm.graph.nodes if n.op == "call_module" and n.target == "0")
+    assert L.get_node_parent_children(node) == (["input.1"], [".1"]) and L.node_name_matches(".1", "1")
