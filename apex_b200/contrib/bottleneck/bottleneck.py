@@ -228,3 +228,54 @@ class SpatialBottleneck(Bottleneck):
         if args is None or args[0] <= 1:
             return super()._conv2(out, s2, b2)
         return _SpatialConv3x3.apply(out, self.conv2.weight, s2, b2, args[3])
+
+
+# ---- functional entry points with the reference's argument lists -------------------------------------------------------------------------
+def _bottleneck_core(nhwc, stride_1x1, scale, bias, x, conv, conv2):
+    """The block as a function of explicit tensors: ``conv`` = (w1, w2, w3[, w4 of the downsample branch]), ``scale`` / ``bias`` the folded
+    frozen-BN pairs in the same order; weights are [K, C, R, S] ([K, R, S, C] when ``nhwc``), ``x`` is NCHW-shaped (NHWC when ``nhwc``)."""
+    vec = lambda t: t.reshape(1, -1, 1, 1)                                              # noqa: E731
+    if nhwc:
+        x = x.permute(0, 3, 1, 2)
+        conv = [w.permute(0, 3, 1, 2) for w in conv]
+    s, b = [vec(t) for t in scale], [vec(t) for t in bias]
+    out = fused_conv_epilogue(x, conv[0], bias=b[0], scale=s[0], stride=stride_1x1, padding=0, relu=True)
+    out = conv2(out, conv[1], s[1], b[1])
+    identity = x
+    if len(conv) > 3:
+        identity = fused_conv_epilogue(x, conv[3], bias=b[3], scale=s[3], stride=stride_1x1, padding=0, relu=False)
+    out = fused_conv_epilogue(out, conv[2], bias=b[2], scale=s[2], z=identity, stride=1, padding=0, relu=True)
+    return out.permute(0, 2, 3, 1) if nhwc else out
+
+
+class BottleneckFunction:
+    """``BottleneckFunction.apply(nhwc, stride_1x1, scale, bias, x, *conv)`` (reference bottleneck.py:80-132 over ``fast_bottleneck``): the
+    whole block from explicit weights and folded BN vectors. Differentiable through the per-convolution autograd Functions of
+    contrib/conv_bias_relu (fused epilogue forward, fused drelu / dscale backward), so no block-level backward is needed."""
+
+    @staticmethod
+    def apply(nhwc, stride_1x1, scale, bias, x, *conv):
+        plain = lambda t, w, s, b: fused_conv_epilogue(t, w, bias=b, scale=s, stride=1, padding=1, relu=True)     # noqa: E731
+        return _bottleneck_core(nhwc, stride_1x1, scale, bias, x, list(conv), plain)
+
+
+bottleneck_function = BottleneckFunction.apply
+
+
+class SpatialBottleneckFunction:
+    """``SpatialBottleneckFunction.apply(spatial_group_size, spatial_group_rank, spatial_communicator, spatial_halo_exchanger,
+    spatial_method, use_delay_kernel, explicit_nhwc, stride_1x1, scale, bias, thresholdTop, thresholdBottom, x, *conv)`` (reference
+    bottleneck.py:304-605). ``spatial_method`` / ``use_delay_kernel`` / the thresholds select between the reference's three halo
+    strategies; here there is one (halo exchange on a side stream under the interior convolution, see :class:`_SpatialConv3x3`)."""
+
+    @staticmethod
+    def apply(spatial_group_size, spatial_group_rank, spatial_communicator, spatial_halo_exchanger, spatial_method, use_delay_kernel,
+              explicit_nhwc, stride_1x1, scale, bias, thresholdTop, thresholdBottom, x, *conv):
+        if spatial_group_size > 1:
+            conv2 = lambda t, w, s, b: _SpatialConv3x3.apply(t, w, s, b, spatial_halo_exchanger)                   # noqa: E731
+        else:
+            conv2 = lambda t, w, s, b: fused_conv_epilogue(t, w, bias=b, scale=s, stride=1, padding=1, relu=True)  # noqa: E731
+        return _bottleneck_core(explicit_nhwc, stride_1x1, scale, bias, x, list(conv), conv2)
+
+
+spatial_bottleneck_function = SpatialBottleneckFunction.apply

@@ -930,3 +930,25 @@ def dist_adam_fragments_partition_params(rank, world, device_type):
     for c in cover:
         dist.all_reduce(c)
         assert bool((c == 1).all())
+
+
+def spatial_bottleneck_function_matches_full(rank, world, device_type):
+    """SpatialBottleneckFunction.apply with the reference's argument list == the module on the whole image, on this rank's rows."""
+    from apex_b200.contrib.bottleneck import Bottleneck
+    from apex_b200.contrib.bottleneck.bottleneck import SpatialBottleneckFunction
+    from apex_b200.contrib.bottleneck.halo_exchangers import HaloExchangerSendRecv
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(0)
+    full = Bottleneck(16, 8, 32).to(dev)
+    norms = [full.bn1, full.bn2, full.bn3, full.downsample[1]]
+    for bn in norms:
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(2, 16, 6 * world, 5, device=dev)
+    want = full(x)
+    rows = slice(6 * rank, 6 * (rank + 1))
+    scale, bias = zip(*(bn.get_scale_bias() for bn in norms))
+    convs = [full.conv1.weight, full.conv2.weight, full.conv3.weight, full.downsample[0].weight]
+    got = SpatialBottleneckFunction.apply(world, rank, None, HaloExchangerSendRecv(list(range(world)), rank), 1, False, False, (1, 1),
+                                          list(scale), list(bias), None, None, x[:, :, rows].contiguous(), *convs)
+    tol = 1e-5 if device_type == "cpu" else 1e-2
+    torch.testing.assert_close(got, want[:, :, rows], atol=tol, rtol=tol)

@@ -19,6 +19,10 @@ def test_spatial_bottleneck_gloo():
     run_distributed(cases.spatial_bottleneck_matches_full, 2, "cpu", backend="gloo")
 
 
+def test_spatial_bottleneck_function_gloo():
+    run_distributed(cases.spatial_bottleneck_function_matches_full, 2, "cpu", backend="gloo")
+
+
 @pytest.mark.parametrize("uneven,fuse_relu", [(False, False), (True, True)])
 def test_syncbn_generic_path_gloo(uneven, fuse_relu):
     run_distributed(cases.syncbn_generic_matches_concatenated_batchnorm, 2, "cpu", uneven, fuse_relu, backend="gloo")

@@ -493,6 +493,34 @@ def test_bottleneck_scale_bias_callable():
         assert not torch.allclose(m(x), y0)
 
 
+def test_bottleneck_function_matches_the_module():
+    """BottleneckFunction.apply(nhwc, stride_1x1, scale, bias, x, *conv) (reference bottleneck.py:80-132) == Bottleneck.forward, values and
+    gradients, with and without the downsample branch, NCHW and explicit NHWC (weights [K, R, S, C] there)."""
+    from apex_b200.contrib.bottleneck import Bottleneck
+    from apex_b200.contrib.bottleneck.bottleneck import BottleneckFunction, SpatialBottleneckFunction, bottleneck_function
+    torch.manual_seed(0)
+    for cin, cout, stride in ((16, 32, 2), (32, 32, 1)):
+        m = Bottleneck(cin, 8, cout, stride=stride)
+        norms = [m.bn1, m.bn2, m.bn3] + ([m.downsample[1]] if m.downsample is not None else [])
+        for bn in norms:
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+        convs = [m.conv1.weight, m.conv2.weight, m.conv3.weight] + ([m.downsample[0].weight] if m.downsample is not None else [])
+        scale, bias = zip(*(bn.get_scale_bias() for bn in norms))
+        x = torch.randn(2, cin, 8, 8, requires_grad=True)
+        want = m(x)
+        got = bottleneck_function(False, (stride, stride), list(scale), list(bias), x, *convs)
+        torch.testing.assert_close(got, want)
+        gw = torch.autograd.grad(want.sum(), [x, m.conv2.weight])
+        gg = torch.autograd.grad(got.sum(), [x, m.conv2.weight])
+        for a, b in zip(gg, gw):
+            torch.testing.assert_close(a, b)
+        nhwc = BottleneckFunction.apply(True, (stride, stride), list(scale), list(bias), x.detach().permute(0, 2, 3, 1),
+                                        *[w.detach().permute(0, 2, 3, 1) for w in convs])
+        torch.testing.assert_close(nhwc, want.detach().permute(0, 2, 3, 1))
+        one = SpatialBottleneckFunction.apply(1, 0, None, None, 1, False, False, (stride, stride), list(scale), list(bias), None, None, x, *convs)
+        torch.testing.assert_close(one, want)
+
+
 def test_norm_custom_ops_numerics_opcheck_and_fullgraph_compile(monkeypatch):
     """apex_b200::norm_fwd / norm_bwd (normalization/custom_ops.py): values and gradients against torch, torch.library.opcheck (schema, fake
     implementation, autograd registration, AOT dispatch), a fullgraph torch.compile, and the modules' compile-time route (forced on for CPU
