@@ -54,6 +54,10 @@ _PATH_ALIASES = {
     "contrib.optimizers.fused_adam": "contrib.optimizers.legacy",
     "contrib.optimizers.fused_lamb": "contrib.optimizers.legacy",
     "contrib.optimizers.fused_sgd": "contrib.optimizers.legacy",
+    **{f"contrib.multihead_attn.{name}": "contrib.multihead_attn.funcs" for name in (
+        "self_multihead_attn", "encdec_multihead_attn", "self_multihead_attn_func", "encdec_multihead_attn_func", "fast_self_multihead_attn_func",
+        "fast_encdec_multihead_attn_func", "fast_self_multihead_attn_norm_add_func", "fast_encdec_multihead_attn_norm_add_func",
+        "mask_softmax_dropout_func")},
     "contrib.sparsity.permutation_search_kernels": "contrib.sparsity.permutation_search",
     "contrib.sparsity.permutation_search_kernels.call_permutation_search_kernels": "contrib.sparsity.permutation_search",
     "contrib.sparsity.permutation_search_kernels.exhaustive_search": "contrib.sparsity.permutation_search",

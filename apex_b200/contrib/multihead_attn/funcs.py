@@ -1,7 +1,10 @@
 """Functional forms of the attention blocks, with the argument lists of the reference's autograd Functions
 (apex/contrib/multihead_attn/{self,encdec}_multihead_attn_func.py, fast_*_func.py, *_norm_add_func.py, mask_softmax_dropout_func.py).
 The reference hand-writes each backward around its C++ kernels; here every form is the composition the modules use — tcgen05 GEMM projections,
-fused LayerNorm, the tcgen05 attention kernels (or fused masked softmax on the generic path) — so autograd derives the backward and there is one implementation of the math."""
+fused LayerNorm, the tcgen05 attention kernels (or fused masked softmax on the generic path) — so autograd derives the backward and there is one implementation of the math.
+
+The reference spreads these over nine files; ``apex_b200.install_as_apex()`` resolves each of those import paths
+(``apex.contrib.multihead_attn.self_multihead_attn_func`` ...) to this module."""
 from __future__ import annotations
 
 import torch
@@ -9,7 +12,7 @@ import torch.nn.functional as F
 
 from ...fused_dense import fused_dense_function
 from ...normalization.fused_layer_norm import fused_layer_norm_affine
-from .multihead_attn import _attention, fast_mask_softmax_dropout_func
+from .multihead_attn import EncdecMultiheadAttn, SelfMultiheadAttn, _attention, fast_mask_softmax_dropout_func  # noqa: F401
 
 
 def jit_dropout_add(x, residual, prob, is_training):

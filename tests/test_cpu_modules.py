@@ -426,14 +426,17 @@ def test_syncbatchnorm_follows_torch_batchnorm_semantics_sweep():
 def test_attention_functional_forms_match_the_modules():
     """The reference's XxxAttnFunc.apply argument lists (self / encdec, fast, norm-add) evaluate the same function as the modules."""
     from apex_b200.contrib.multihead_attn import EncdecMultiheadAttn, SelfMultiheadAttn
-    from apex_b200.contrib.multihead_attn.encdec_multihead_attn_func import encdec_attn_func
-    from apex_b200.contrib.multihead_attn.fast_encdec_multihead_attn_func import fast_encdec_attn_func
-    from apex_b200.contrib.multihead_attn.fast_encdec_multihead_attn_norm_add_func import fast_encdec_attn_norm_add_func
-    from apex_b200.contrib.multihead_attn.fast_self_multihead_attn_func import fast_self_attn_func
-    from apex_b200.contrib.multihead_attn.fast_self_multihead_attn_norm_add_func import fast_self_attn_norm_add_func
-    from apex_b200.contrib.multihead_attn.mask_softmax_dropout_func import MaskSoftmaxDropout, fast_mask_softmax_dropout_func
-    from apex_b200.contrib.multihead_attn.self_multihead_attn import jit_dropout_add
-    from apex_b200.contrib.multihead_attn.self_multihead_attn_func import self_attn_func
+    import apex_b200
+    apex_b200.install_as_apex()          # the reference's one-file-per-function import paths resolve to contrib/multihead_attn/funcs.py
+    from apex.contrib.multihead_attn.encdec_multihead_attn_func import encdec_attn_func
+    from apex.contrib.multihead_attn.fast_encdec_multihead_attn_func import fast_encdec_attn_func
+    from apex.contrib.multihead_attn.fast_encdec_multihead_attn_norm_add_func import fast_encdec_attn_norm_add_func
+    from apex.contrib.multihead_attn.fast_self_multihead_attn_func import fast_self_attn_func
+    from apex.contrib.multihead_attn.fast_self_multihead_attn_norm_add_func import fast_self_attn_norm_add_func
+    from apex.contrib.multihead_attn.mask_softmax_dropout_func import MaskSoftmaxDropout, fast_mask_softmax_dropout_func
+    from apex.contrib.multihead_attn.self_multihead_attn import SelfMultiheadAttn as _SameClass, jit_dropout_add
+    from apex.contrib.multihead_attn.self_multihead_attn_func import self_attn_func
+    assert _SameClass is SelfMultiheadAttn
     torch.manual_seed(0)
     E, H, T, B = 32, 4, 6, 2
     x, mem = torch.randn(T, B, E), torch.randn(5, B, E)
