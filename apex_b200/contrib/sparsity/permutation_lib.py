@@ -26,6 +26,7 @@ from __future__ import annotations
 import operator
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -66,10 +67,14 @@ class _Space:
     channel dim; ``riders``: (owner, attr, dim) -- producer weights / biases / norm statistics / broadcast attributes permuted along
     their channel dim."""
 
-    __slots__ = ("parent", "frozen", "why", "consumers", "riders")
+    # the second row is filled by the search / apply stages of :class:`Permutation` (roots only)
+    __slots__ = ("parent", "frozen", "why", "consumers", "riders",
+                 "permutation", "skipped", "before", "after", "checked", "search_device")
 
     def __init__(self):
         self.parent, self.frozen, self.why, self.consumers, self.riders = self, False, "", [], []
+        self.permutation = self.skipped = self.checked = self.search_device = None
+        self.before = self.after = 0.0
 
     def find(self):
         s = self
@@ -655,44 +660,96 @@ class Permutation:
         dist.broadcast(t, 0)
         return [int(i) for i in t.cpu()]
 
-    # -------------------------------------------------------------------------------------------------------------- driver
+    # ------------------------------------------------------------------------------------------------------------- stages
+    # The reference drives the same five stages (permutation_lib.py:196-254: build_fx_graph, init / propagate flags, find_permutations,
+    # sync_permutations, apply_permutations); its "flags" are what a _Space carries here (frozen / why / consumers / riders).
     @classmethod
-    def permute_model(cls, model, dump_fx_graph=False, save_dumped_fx_graph=None, verbosity=0):
-        """Search and apply a permutation for every unfrozen channel space; returns [(n consumers, magnitude before, after)]."""
-        cls.__verbosity = verbosity
-        cls.__stats = {"C": 0, "K": 0}
+    def build_fx_graph(cls, model, dump_fx_graph=False, save_dumped_fx_graph="./model_fx_graph.json"):
+        """(channel spaces of ``model``, success). Tracing failures are not fatal: an untraceable model is left unpermuted, as the
+        reference does (:1776-1997). With ``dump_fx_graph`` the space description is written as JSON before anything is searched."""
         try:
             roots = cls.build_spaces(model)
-        except Exception as e:  # untraceable model: leave it unpermuted, like the reference does on trace failure
-            if verbosity:
+        except Exception as e:  # noqa: BLE001
+            if cls.__verbosity:
                 print(f"[permutation_lib] model is not fx-traceable ({type(e).__name__}: {e}); skipping channel permutations")
-            return []
-        report, dumped = [], []
+            return [], False
+        if dump_fx_graph and save_dumped_fx_graph:
+            cls.save_graph_to_json(cls.describe_spaces(roots), save_dumped_fx_graph)
+        return roots, True
+
+    @classmethod
+    def describe_spaces(cls, roots) -> dict:
+        """JSON-able description of the channel spaces: who consumes / rides each, why a space is skipped, and — once the later stages
+        ran — the permutation and the kept magnitude before / after."""
+        groups = []
         for space in roots:
+            d = {"consumers": [c[5] for c in space.consumers], "riders": sorted({f"{r[3]}.{r[1]}" for r in space.riders})}
+            if getattr(space, "skipped", None) or space.frozen or not space.consumers:
+                d["skipped"] = getattr(space, "skipped", None) or space.why or "no consumers"
+            if getattr(space, "permutation", None) is not None:
+                d.update(channels=len(space.permutation), permutation=space.permutation, kept_magnitude_before=space.before,
+                         kept_magnitude_after=space.after)
+            groups.append(d)
+        return {"groups": groups}
+
+    @classmethod
+    def find_permutations(cls, roots) -> int:
+        """Search stage: every eligible space gets ``space.permutation`` (None when there is nothing to gain) and the kept-magnitude pair
+        ``space.before / space.after``; returns how many spaces found an improving permutation."""
+        found = 0
+        for space in roots:
+            space.permutation = space.skipped = None
             if space.frozen or not space.consumers:
-                if verbosity and space.consumers:
+                if cls.__verbosity and space.consumers:
                     print(f"[permutation_lib] skipping a space with {len(space.consumers)} consumer(s): {space.why}")
-                dumped.append({"skipped": space.why or "no consumers", "consumers": [c[5] for c in space.consumers]})
                 continue
             ok, C, cons = cls._validate(space)
             if not ok:
-                dumped.append({"skipped": f"dimension mismatch (C = {C})", "consumers": [c[5] for c in space.consumers]})
+                space.skipped = f"dimension mismatch (C = {C})"
                 continue
             stacked = cls._search_matrix(cons)
             if stacked is None:
-                dumped.append({"skipped": "no prunable consumer", "consumers": [c[5] for c in cons]})
+                space.skipped = "no prunable consumer"
                 continue
-            before = float(sum_after_2_to_4(stacked))
+            space.checked, space.search_device = cons, stacked.device
+            space.before = float(sum_after_2_to_4(stacked))
             cls.reset_seed()
-            perm = accelerated_search_for_good_permutation(stacked, cls.search_options, verbosity)
-            perm = cls.sync_permutation([int(i) for i in perm], stacked.device)
-            idx = torch.as_tensor(perm, device=stacked.device)
-            after = float(sum_after_2_to_4(stacked[:, idx]))
-            if after <= before:
-                dumped.append({"skipped": "no improvement", "consumers": [c[5] for c in cons]})
+            perm = [int(i) for i in accelerated_search_for_good_permutation(stacked, cls.search_options, cls.__verbosity)]
+            space.after = float(sum_after_2_to_4(stacked[:, torch.as_tensor(perm, device=stacked.device)]))
+            space.permutation = perm
+            found += space.after > space.before
+        return found
+
+    @classmethod
+    def sync_permutations(cls, roots) -> None:
+        """Distributed stage: rank 0's permutation of every searched space replaces the local one, so that all data-parallel replicas permute
+        identically (reference :577-640 broadcasts through a TCPStore / the default group). Ranks search the same weights, so ``before`` is
+        identical everywhere and ``after`` is rank 0's."""
+        for space in roots:
+            if getattr(space, "permutation", None) is None:
                 continue
+            space.permutation = cls.sync_permutation(space.permutation, space.search_device)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                pair = torch.tensor([space.before, space.after], dtype=torch.float64,
+                                    device=space.search_device if dist.get_backend() == "nccl" else "cpu")
+                dist.broadcast(pair, 0)
+                space.before, space.after = (float(v) for v in pair.cpu())
+
+    @classmethod
+    def apply_permutations(cls, roots) -> list:
+        """Apply stage: permute the input channels (C) of every consumer and the matching output-side tensors (K: producers' rows, biases,
+        norm parameters ... the riders) of every space whose permutation improves the kept magnitude. -> [(n consumers, before, after)]."""
+        report = []
+        for space in roots:
+            perm = getattr(space, "permutation", None)
+            if perm is None:
+                continue
+            if space.after <= space.before:
+                space.skipped, space.permutation = "no improvement", None
+                continue
+            idx = torch.as_tensor(perm, device=space.search_device)
             seen = set()
-            for m, attr, dim, rep, _, _ in cons:
+            for m, attr, dim, rep, _, _ in space.checked:
                 if _tkey(m, attr, dim) in seen:
                     continue
                 seen.add(_tkey(m, attr, dim))
@@ -705,15 +762,50 @@ class Permutation:
                 seen.add(_tkey(owner, name, dim))
                 cls._permute_tensor(_t(owner, name), dim, idx.long())
                 cls.__stats["K"] += 1
-            report.append((len(cons), before, after))
-            dumped.append({"consumers": [c[5] for c in cons], "riders": sorted({f"{r[3]}.{r[1]}" for r in space.riders}), "channels": C,
-                           "permutation": perm, "kept_magnitude_before": before, "kept_magnitude_after": after})
-            if verbosity:
-                print(f"[permutation_lib] space of {C} channels, {len(cons)} consumer(s), {len(seen)} rider tensor(s): kept magnitude "
-                      f"{before:.3f} -> {after:.3f}")
-        if dump_fx_graph and save_dumped_fx_graph:   # what was permuted and how, for offline inspection (the reference dumps its annotated fx graph)
-            import json
+            report.append((len(space.checked), space.before, space.after))
+            if cls.__verbosity:
+                print(f"[permutation_lib] space of {len(perm)} channels, {len(space.checked)} consumer(s), {len(seen)} rider tensor(s): kept "
+                      f"magnitude {space.before:.3f} -> {space.after:.3f}")
+        return report
 
-            with open(save_dumped_fx_graph, "w") as f:
-                json.dump({"groups": dumped}, f, indent=1)
+    @classmethod
+    def trace_and_print_raw_fx_graph(cls, model, print_tabular=False, generate_python_code=False):
+        """Symbolically trace ``model`` and print its fx graph (optionally as a table / as generated Python); None if it cannot be traced
+        (reference :1999-2057)."""
+        try:
+            traced = torch.fx.symbolic_trace(model)
+        except Exception as e:  # noqa: BLE001
+            if cls.__verbosity and (not dist.is_available() or not dist.is_initialized() or dist.get_rank() == 0):
+                print(f"[print_raw_fx_graph] cannot symbolically trace the model: {type(e).__name__}: {e}")
+            return None
+        if cls.__verbosity > 1:
+            print(traced.graph)
+        if print_tabular:
+            for n in traced.graph.nodes:
+                print(f"{n.op:<14} {n.name:<28} {str(n.target):<40} {[a.name for a in n.all_input_nodes]}")
+        if generate_python_code:
+            print(traced.code)
+        return traced
+
+    @classmethod
+    def save_graph_to_json(cls, graph, save_dumped_graph_path_with_name="./model_fx_graph.json"):
+        import json
+
+        with open(save_dumped_graph_path_with_name, "w", encoding="utf-8") as f:
+            json.dump(graph, f, indent=1)
+
+    # -------------------------------------------------------------------------------------------------------------- driver
+    @classmethod
+    def permute_model(cls, model, dump_fx_graph=False, save_dumped_fx_graph=None, verbosity=0):
+        """Search and apply a permutation for every unfrozen channel space; returns [(n consumers, magnitude before, after)]."""
+        cls.__verbosity = verbosity
+        cls.__stats = {"C": 0, "K": 0}
+        roots, ok = cls.build_fx_graph(model)
+        if not ok:
+            return []
+        cls.find_permutations(roots)
+        cls.sync_permutations(roots)
+        report = cls.apply_permutations(roots)
+        if dump_fx_graph and save_dumped_fx_graph:   # what was permuted and how, for offline inspection (the reference dumps its annotated fx graph)
+            cls.save_graph_to_json(cls.describe_spaces(roots), save_dumped_fx_graph)
         return report

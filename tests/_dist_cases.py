@@ -952,3 +952,26 @@ def spatial_bottleneck_function_matches_full(rank, world, device_type):
                                           list(scale), list(bias), None, None, x[:, :, rows].contiguous(), *convs)
     tol = 1e-5 if device_type == "cpu" else 1e-2
     torch.testing.assert_close(got, want[:, :, rows], atol=tol, rtol=tol)
+
+
+def permutation_sync_uses_rank0(rank, world, device_type):
+    """sync_permutations: whatever each rank found, all ranks apply rank 0's permutation (weights differ per rank here, so the local
+    searches disagree), and the function of the network is preserved on every rank."""
+    from apex_b200.contrib.sparsity.permutation_lib import Permutation
+    dev = torch.device("cuda", rank) if device_type == "cuda" else torch.device("cpu")
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8)).to(dev)
+    x = torch.randn(4, 16, device=dev)
+    want = net(x)
+    roots, ok = Permutation.build_fx_graph(net)
+    assert ok
+    Permutation.find_permutations(roots)
+    local = [s.permutation for s in roots if s.permutation is not None]
+    Permutation.sync_permutations(roots)
+    synced = [s.permutation for s in roots if s.permutation is not None]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (local, synced))
+    assert all(g[1] == gathered[0][0] for g in gathered), "every rank must end up with rank 0's permutations"
+    assert gathered[0][0] != gathered[1][0], "the test is vacuous if the local searches agree"
+    Permutation.apply_permutations(roots)
+    torch.testing.assert_close(net(x), want, atol=1e-5, rtol=1e-5)

@@ -51,3 +51,7 @@ def test_ddp_option_matrix_gloo():
 
 def test_cudnn_gbn_lib_raw_entry_points_two_ranks_gloo():
     run_distributed(cases.cudnn_gbn_lib_group_of_two, 2, "cpu", backend="gloo")
+
+
+def test_permutation_sync_gloo():
+    run_distributed(cases.permutation_sync_uses_rank0, 2, "cpu", backend="gloo")

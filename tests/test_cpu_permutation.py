@@ -359,3 +359,46 @@ def test_permutation_lib_name_helpers():
     gm = torch.fx.symbolic_trace(torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU()))
     node = next(n for n in gm.graph.nodes if n.op == "call_module" and n.target == "0")
     assert L.get_node_parent_children(node) == (["input.1"], [".1"]) and L.node_name_matches(".1", "1")
+
+
+def test_staged_api_equals_permute_model(tmp_path, capsys):
+    """build_fx_graph -> find_permutations -> sync_permutations -> apply_permutations (the reference's stage names) is what permute_model
+    runs; the JSON dump describes every space before and after the search."""
+    import copy
+    import json
+
+    from apex_b200.contrib.sparsity.permutation_lib import Permutation
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.ReLU(), torch.nn.Linear(48, 24), torch.nn.ReLU(), torch.nn.Linear(24, 8))
+    twin = copy.deepcopy(net)
+    x = torch.randn(5, 32)
+    want = net(x)
+    report = Permutation.permute_model(twin)
+    path = tmp_path / "graph.json"
+    roots, ok = Permutation.build_fx_graph(net, dump_fx_graph=True, save_dumped_fx_graph=str(path))
+    assert ok and all("permutation" not in g for g in json.loads(path.read_text())["groups"])
+    found = Permutation.find_permutations(roots)
+    assert found == len(report) == 2
+    before = [p.detach().clone() for p in net.parameters()]
+    assert all(torch.equal(a, b) for a, b in zip(before, net.parameters()))          # searching changes nothing
+    Permutation.sync_permutations(roots)                                             # single process: a no-op
+    staged = Permutation.apply_permutations(roots)
+    assert staged == report
+    for p, q in zip(net.parameters(), twin.parameters()):
+        assert torch.equal(p, q)
+    torch.testing.assert_close(net(x), want)                                         # the function is preserved
+    desc = Permutation.describe_spaces(roots)
+    done = [g for g in desc["groups"] if "permutation" in g]
+    assert len(done) == 2 and all(g["kept_magnitude_after"] > g["kept_magnitude_before"] for g in done)
+    assert any("skipped" in g for g in desc["groups"])                               # the network input / output spaces are frozen
+    Permutation.save_graph_to_json(desc, str(path))
+    assert json.loads(path.read_text()) == desc
+    # untraceable model: reported, not fatal
+    class Dyn(torch.nn.Module):
+        def forward(self, x):
+            return x if x.sum() > 0 else -x
+    assert Permutation.build_fx_graph(Dyn()) == ([], False) and Permutation.permute_model(Dyn()) == []
+    assert Permutation.trace_and_print_raw_fx_graph(Dyn()) is None
+    traced = Permutation.trace_and_print_raw_fx_graph(net, print_tabular=True, generate_python_code=True)
+    out = capsys.readouterr().out
+    assert isinstance(traced, torch.fx.GraphModule) and "call_module" in out and "def forward" in out
