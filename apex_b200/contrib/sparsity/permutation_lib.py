@@ -14,7 +14,10 @@ Design here: CHANNEL SPACES. The model is symbolically traced and every tensor v
   * a concatenation along the channel axis is a list of (space, offset, size) parts: the Linear / Conv / BatchNorm that consumes it is a
     consumer (rider) of EVERY part through the matching slice of its weight, so each input keeps its own permutation (the reference's
     fixup_concats case); parts whose offset or size is not a multiple of 4 would move the 2:4 groups and are frozen instead.
-  * anything that mixes or exposes channel order (graph inputs and outputs, reshapes, matmuls, grouped convolutions, GroupNorm,
+  * a grouped convolution (1 < groups < channels, at least 8 channels per group) cuts its input space into `groups` blocks: the space
+    stays permutable, but only by one permutation of the channels-per-group, replicated in every block; ungrouped consumers of the same
+    tensor fold their blocks into rows for the search (the reference's init_grouped_conv_permutation_flags). Its output space is frozen.
+  * anything that mixes or exposes channel order (graph inputs and outputs, reshapes, matmuls, outputs of grouped convolutions, GroupNorm,
     LocalResponseNorm, slicing, unknown modules and functions) FREEZES the spaces it touches.
 Every unfrozen space with at least one prunable consumer is one search problem: the consumers' weights are stacked row-wise (the
 reference's sibling group), one permutation is searched (csrc/perm_search.cu), applied to every consumer's input-channel dim and to
@@ -69,12 +72,13 @@ class _Space:
 
     # the second row is filled by the search / apply stages of :class:`Permutation` (roots only)
     __slots__ = ("parent", "frozen", "why", "consumers", "riders",
-                 "permutation", "skipped", "before", "after", "checked", "search_device")
+                 "permutation", "skipped", "before", "after", "checked", "search_device", "blocks")
 
     def __init__(self):
         self.parent, self.frozen, self.why, self.consumers, self.riders = self, False, "", [], []
         self.permutation = self.skipped = self.checked = self.search_device = None
         self.before = self.after = 0.0
+        self.blocks = 1
 
     def find(self):
         s = self
@@ -139,15 +143,29 @@ class _Slice:
         self.owner, self.dim, self.off, self.size = owner, dim, off, size
 
 
+class _Grouped:
+    """Stands in for a grouped convolution (1 < groups < channels) in a consumer entry. Its weight is [K, C / groups, taps...]: group g
+    reads the g-th block of C / groups input channels, so the only input permutations it tolerates move channels INSIDE their block, the
+    same way in every block — the space is searched over C / groups columns and the result replicated per block (the reference's
+    init_grouped_conv_permutation_flags / replicate_sequence, permutation_lib.py:1152-1180,76-85)."""
+
+    __slots__ = ("owner", "groups")
+
+    def __init__(self, owner, groups):
+        self.owner, self.groups = owner, groups
+
+
 def _t(m, attr):
     """The tensor behind a consumer / rider entry (a view for slices: in-place writes reach the parameter)."""
     if isinstance(m, _Slice):
         return getattr(m.owner, attr).narrow(m.dim, m.off, m.size)
+    if isinstance(m, _Grouped):
+        return getattr(m.owner, attr)
     return getattr(m, attr)
 
 
 def _base(m, attr):
-    return getattr(m.owner if isinstance(m, _Slice) else m, attr)
+    return getattr(m.owner if isinstance(m, (_Slice, _Grouped)) else m, attr)
 
 
 def _tkey(m, attr, dim):
@@ -438,6 +456,11 @@ class Permutation:
                             if m.bias is not None:
                                 src.space.find().riders.append((m, "bias", 0, node.target))
                         vals[node] = src.like(spatial1=False)
+                    elif (src.axis == 1 and cin % groups == 0 and (cin // groups) % 4 == 0 and cin // groups > 4 and id(m) not in first_use):
+                        # grouped: the input space stays permutable inside its channel blocks; the output channels are tied to the groups
+                        first_use[id(m)] = (None, None)
+                        src.space.find().consumers.append((_Grouped(m, groups), "weight", 1, 1, True, node.target, cin))
+                        vals[node] = _Val(new_space(f"output of grouped convolution {node.target}"), 1, rank, size=cout)
                     else:
                         opaque(node, f"grouped convolution {node.target}")
                 elif isinstance(m, _CONV_T):
@@ -621,9 +644,18 @@ class Permutation:
             t = _t(owner, name)
             if t is None or t.shape[dim] != C:
                 return False, C, []
+        blocks = {m.groups for m, *_ in space.consumers if isinstance(m, _Grouped)}
+        if len(blocks) > 1 or any(C % b for b in blocks):
+            return False, C, []         # grouped consumers that cut the channels differently: no common block structure
+        space.blocks = blocks.pop() if blocks else 1
         cons = []
         for m, attr, dim, rep, prunable, where, cin in space.consumers:
             w = _t(m, attr)
+            if isinstance(m, _Grouped):
+                if w.shape[dim] * m.groups != C:
+                    return False, C, []
+                cons.append((m, attr, dim, 1, prunable, where))
+                continue
             if rep is None:   # flattened [C, spatial...]: each channel covers in_features / C consecutive columns
                 if w.shape[dim] % C != 0:
                     return False, C, []
@@ -634,8 +666,9 @@ class Permutation:
         return True, C, cons
 
     @classmethod
-    def _search_matrix(cls, cons):
-        """Stack the prunable consumers' weights into [rows, C] (spatial taps and flattened repeats folded into rows)."""
+    def _search_matrix(cls, cons, blocks=1):
+        """Stack the prunable consumers' weights into [rows, C / blocks] (spatial taps, flattened repeats and — in a space that a grouped
+        convolution cuts into ``blocks`` channel blocks — the blocks of the ungrouped consumers folded into rows)."""
         sparse = cls.__sparse_parameters
         mats = []
         for m, attr, dim, rep, prunable, _ in cons:
@@ -645,6 +678,8 @@ class Permutation:
             w2 = w.detach().movedim(dim, -1).reshape(-1, w.shape[dim]).float()    # [rows, C * rep], channel-major columns
             if rep > 1:
                 w2 = w2.reshape(-1, w2.shape[1] // rep, rep).permute(0, 2, 1).reshape(-1, w2.shape[1] // rep)
+            if blocks > 1 and not isinstance(m, _Grouped):
+                w2 = w2.reshape(-1, w2.shape[1] // blocks)                          # [rows * blocks, C / blocks]
             mats.append(w2)
         return torch.cat(mats, 0) if mats else None
 
@@ -687,8 +722,8 @@ class Permutation:
             if getattr(space, "skipped", None) or space.frozen or not space.consumers:
                 d["skipped"] = getattr(space, "skipped", None) or space.why or "no consumers"
             if getattr(space, "permutation", None) is not None:
-                d.update(channels=len(space.permutation), permutation=space.permutation, kept_magnitude_before=space.before,
-                         kept_magnitude_after=space.after)
+                d.update(channels=len(space.permutation) * space.blocks, blocks=space.blocks, permutation=space.permutation,
+                         kept_magnitude_before=space.before, kept_magnitude_after=space.after)
             groups.append(d)
         return {"groups": groups}
 
@@ -707,9 +742,12 @@ class Permutation:
             if not ok:
                 space.skipped = f"dimension mismatch (C = {C})"
                 continue
-            stacked = cls._search_matrix(cons)
+            stacked = cls._search_matrix(cons, space.blocks)
             if stacked is None:
                 space.skipped = "no prunable consumer"
+                continue
+            if stacked.shape[1] <= 4:
+                space.skipped = "a single 2:4 group per block: nothing to permute"
                 continue
             space.checked, space.search_device = cons, stacked.device
             space.before = float(sum_after_2_to_4(stacked))
@@ -747,13 +785,14 @@ class Permutation:
             if space.after <= space.before:
                 space.skipped, space.permutation = "no improvement", None
                 continue
-            idx = torch.as_tensor(perm, device=space.search_device)
+            full = replicate_sequence(perm, space.blocks)       # the permutation of all C channels (== perm without grouped consumers)
+            idx = torch.as_tensor(full, device=space.search_device)
             seen = set()
             for m, attr, dim, rep, _, _ in space.checked:
                 if _tkey(m, attr, dim) in seen:
                     continue
                 seen.add(_tkey(m, attr, dim))
-                cls.apply_permutation_in_C_dim(m, perm, attr, dim, rep)
+                cls.apply_permutation_in_C_dim(m, perm if isinstance(m, _Grouped) else full, attr, dim, rep)
                 cls.__stats["C"] += 1
             seen = set()
             for owner, name, dim, _ in space.riders:

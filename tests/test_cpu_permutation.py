@@ -148,8 +148,10 @@ def test_flatten_after_conv_permutes_blocks_of_columns():
     _check(Fl(), torch.randn(4, 16, 3, 3), (1, 2), min_groups=1)
 
 
-@pytest.mark.parametrize("groups,exp", [(32, (1, 4)), (4, (0, 0))])
-def test_depthwise_passes_through_and_grouped_freezes(groups, exp):
+@pytest.mark.parametrize("groups,exp", [(32, (1, 4)), (4, (1, 2)), (8, (0, 0))])
+def test_depthwise_passes_through_and_grouped_permutes_inside_blocks(groups, exp):
+    """depthwise: channels pass straight through; 4 groups of 8 channels: permuted inside the blocks (a.weight / a.bias ride); 8 groups of 4:
+    a single 2:4 group per block, nothing to permute."""
     class M(nn.Module):
         def __init__(self):
             super().__init__()
@@ -402,3 +404,87 @@ def test_staged_api_equals_permute_model(tmp_path, capsys):
     traced = Permutation.trace_and_print_raw_fx_graph(net, print_tabular=True, generate_python_code=True)
     out = capsys.readouterr().out
     assert isinstance(traced, torch.fx.GraphModule) and "call_module" in out and "def forward" in out
+
+
+def _kept(w):
+    """Magnitude 2:4 pruning along the input-channel dim keeps."""
+    w2 = w.detach().movedim(1, -1).reshape(-1, w.shape[1]).abs()
+    return float(w2.reshape(w2.shape[0], -1, 4).topk(2, dim=-1).values.sum())
+
+
+def test_grouped_convolution_consumers_get_block_replicated_permutations():
+    """A grouped convolution (1 < groups < channels) keeps its input space permutable: channels move inside their group's block, identically
+    in every block (reference init_grouped_conv_permutation_flags / replicate_sequence); an ungrouped consumer of the same tensor is
+    permuted with the replicated sequence; the grouped convolution's output space is frozen."""
+    from apex_b200.contrib.sparsity.permutation_lib import Permutation
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = torch.nn.Conv2d(8, 32, 1)
+            self.bn = torch.nn.BatchNorm2d(32)
+            self.grouped = torch.nn.Conv2d(32, 32, 3, padding=1, groups=2)        # 16 channels per group
+            self.side = torch.nn.Conv2d(32, 16, 1)                                # ungrouped consumer of the same tensor
+            self.head = torch.nn.Conv2d(32, 8, 1)
+
+        def forward(self, x):
+            h = torch.relu(self.bn(self.stem(x)))
+            return self.head(torch.relu(self.grouped(h))), self.side(h)
+
+    torch.manual_seed(0)
+    net = Net().eval()
+    with torch.no_grad():
+        net.bn.running_mean.normal_()
+        net.bn.running_var.uniform_(0.5, 2)
+        net.bn.weight.normal_()
+    x = torch.randn(2, 8, 6, 6)
+    want = net(x)
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    kept0 = _kept(net.grouped.weight) + sum(_kept(net.side.weight[:, b * 16:(b + 1) * 16]) for b in range(2))
+    roots, ok = Permutation.build_fx_graph(net)
+    assert ok and Permutation.find_permutations(roots) == 1
+    space = next(s for s in roots if s.permutation is not None)
+    assert space.blocks == 2 and sorted(space.permutation) == list(range(16))
+    Permutation.sync_permutations(roots)
+    (n_cons, b, a), = Permutation.apply_permutations(roots)
+    assert n_cons == 2 and a > b
+    for got, ref in zip(net(x), want):
+        torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+    p = torch.tensor(space.permutation)
+    full = torch.cat([p, p + 16])
+    assert torch.equal(net.grouped.weight, before["grouped.weight"][:, p])                 # the same move inside every group's block
+    assert torch.equal(net.side.weight, before["side.weight"][:, full])
+    assert torch.equal(net.stem.weight, before["stem.weight"][full]) and torch.equal(net.bn.weight, before["bn.weight"][full])
+    assert torch.equal(net.head.weight, before["head.weight"])                             # behind the grouped convolution: untouched
+    kept1 = _kept(net.grouped.weight) + sum(_kept(net.side.weight[:, b * 16:(b + 1) * 16]) for b in range(2))
+    assert kept1 > kept0 and abs((kept1 - kept0) - (a - b)) < 1e-2
+    desc = Permutation.describe_spaces(roots)
+    assert any(g.get("blocks") == 2 and g["channels"] == 32 for g in desc["groups"])
+    assert any("grouped convolution" in g.get("skipped", "") for g in desc["groups"])
+
+
+def test_grouped_convolutions_without_room_to_permute_are_left_alone():
+    from apex_b200.contrib.sparsity.permutation_lib import Permutation
+    torch.manual_seed(0)
+    # 4 channels per group: one 2:4 group per block, nothing to gain -> the tensor feeding it stays as it is
+    net = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 1), torch.nn.ReLU(), torch.nn.Conv2d(16, 16, 3, padding=1, groups=4), torch.nn.ReLU(),
+                              torch.nn.Conv2d(16, 8, 1))
+    before = [p.detach().clone() for p in net.parameters()]
+    assert Permutation.permute_model(net) == []
+    assert all(torch.equal(a, b) for a, b in zip(before, net.parameters()))
+
+    class TwoCuts(torch.nn.Module):           # two grouped consumers that cut the same tensor differently: no common block structure
+        def __init__(self):
+            super().__init__()
+            self.stem = torch.nn.Conv2d(8, 64, 1)
+            self.a = torch.nn.Conv2d(64, 64, 3, padding=1, groups=2)
+            self.b = torch.nn.Conv2d(64, 64, 3, padding=1, groups=4)
+
+        def forward(self, x):
+            h = torch.relu(self.stem(x))
+            return self.a(h) + self.b(h)
+
+    net = TwoCuts()
+    before = [p.detach().clone() for p in net.parameters()]
+    assert Permutation.permute_model(net) == []
+    assert all(torch.equal(a, b) for a, b in zip(before, net.parameters()))
