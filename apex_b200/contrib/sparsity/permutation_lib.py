@@ -728,11 +728,11 @@ class Permutation:
         return {"groups": groups}
 
     @classmethod
-    def find_permutations(cls, roots) -> int:
+    def find_permutations(cls, fx_graph) -> int:
         """Search stage: every eligible space gets ``space.permutation`` (None when there is nothing to gain) and the kept-magnitude pair
         ``space.before / space.after``; returns how many spaces found an improving permutation."""
         found = 0
-        for space in roots:
+        for space in fx_graph:     # the channel spaces build_fx_graph returned
             space.permutation = space.skipped = None
             if space.frozen or not space.consumers:
                 if cls.__verbosity and space.consumers:
@@ -759,11 +759,11 @@ class Permutation:
         return found
 
     @classmethod
-    def sync_permutations(cls, roots) -> None:
+    def sync_permutations(cls, fx_graph) -> None:
         """Distributed stage: rank 0's permutation of every searched space replaces the local one, so that all data-parallel replicas permute
         identically (reference :577-640 broadcasts through a TCPStore / the default group). Ranks search the same weights, so ``before`` is
         identical everywhere and ``after`` is rank 0's."""
-        for space in roots:
+        for space in fx_graph:     # the channel spaces build_fx_graph returned
             if getattr(space, "permutation", None) is None:
                 continue
             space.permutation = cls.sync_permutation(space.permutation, space.search_device)
@@ -774,11 +774,11 @@ class Permutation:
                 space.before, space.after = (float(v) for v in pair.cpu())
 
     @classmethod
-    def apply_permutations(cls, roots) -> list:
+    def apply_permutations(cls, fx_graph) -> list:
         """Apply stage: permute the input channels (C) of every consumer and the matching output-side tensors (K: producers' rows, biases,
         norm parameters ... the riders) of every space whose permutation improves the kept magnitude. -> [(n consumers, before, after)]."""
         report = []
-        for space in roots:
+        for space in fx_graph:     # the channel spaces build_fx_graph returned
             perm = getattr(space, "permutation", None)
             if perm is None:
                 continue
