@@ -225,8 +225,15 @@ def accelerated_search_for_good_permutation(matrix_group, options=None, verbosit
         _, _, perm = Channel_Swap(m, escape_attempts=options.get("escape_attempts", options.get("improvement_threshold", 0) and 0))
     elif strategy == "random":
         _, _, perm = Random_Search(m, num_seeds=options.get("num_seeds", 10))
-    else:
-        raise ValueError(f"unknown permutation search strategy {strategy!r}")
+    elif strategy == "user defined":
+        # the reference leaves the permutation untouched here and expects the user to replace this function; a callable under
+        # options["function"] (matrix -> permutation) is the same hook without monkey-patching
+        fn = options.get("function")
+        perm = [int(c) for c in fn(m)] if callable(fn) else list(range(m.shape[1]))
+    else:   # as the reference: report and keep the channel order
+        if verbosity >= 0:
+            print("[accelerated_search_for_good_permutation] Cannot find the implementation of the required strategy!")
+        perm = list(range(m.shape[1]))
     return perm
 
 

@@ -488,3 +488,22 @@ def test_grouped_convolutions_without_room_to_permute_are_left_alone():
     before = [p.detach().clone() for p in net.parameters()]
     assert Permutation.permute_model(net) == []
     assert all(torch.equal(a, b) for a, b in zip(before, net.parameters()))
+
+
+def test_search_dispatcher_strategies(capsys):
+    """accelerated_search_for_good_permutation: every strategy name of the reference (call_permutation_search_kernels.py:6-105) returns a
+    permutation of the columns; 'user defined' takes a callable; an unknown strategy is reported and keeps the order."""
+    from apex_b200.contrib.sparsity.permutation_search import accelerated_search_for_good_permutation as search, sum_after_2_to_4
+    torch.manual_seed(0)
+    m = torch.randn(24, 16)
+    base = float(sum_after_2_to_4(m))
+    for opts in (None, {"strategy": "exhaustive", "stripe_group_size": 8, "escape_attempts": 2},
+                 {"strategy": "progressive channel swap", "progressive_search_time_limit": 1, "improvement_threshold": 1e-9},
+                 {"strategy": "random", "num_seeds": 20}):
+        perm = search(m, opts)
+        assert sorted(perm) == list(range(16)) and float(sum_after_2_to_4(m[:, perm])) >= base - 1e-4
+    assert search(m, {"strategy": "user defined"}) == list(range(16))
+    rev = search(m, {"strategy": "user defined", "function": lambda mat: list(range(mat.shape[1]))[::-1]})
+    assert rev == list(range(16))[::-1]
+    assert search(m, {"strategy": "simulated annealing"}) == list(range(16))
+    assert "Cannot find the implementation" in capsys.readouterr().out
