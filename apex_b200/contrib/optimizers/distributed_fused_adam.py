@@ -1187,14 +1187,14 @@ class DistributedFusedAdam(torch.optim.Optimizer):
         # as in the reference, the model-dtype parameters themselves come from the MODEL's checkpoint; v1 restores the optimizer's shards
         # (moments, fp32 master / remainder shards, step, hyper-parameters)
 
-    def state_dict(self, *args, state_dict_format=None, gather_on_root: bool = True, **kwargs):
+    def state_dict(self, *args, state_dict_format=None, gather_on_root: Optional[bool] = None, **kwargs):
         """``state_dict_format=1``: the deprecated per-rank format (see :meth:`_state_dict_v1`). Default (2):
         every rank returns the same dict in the reference's v2 layout (:3059-3327): ``state["step"]`` plus, per parameter index,
         full-size CPU tensors ``param`` (fp32 master), ``exp_avg``, ``exp_avg_sq`` — independent of world size and bucket layout, so it
         reloads under a different parallel configuration (and in the reference). The sharded state is streamed to the host in
         bounded pieces (double-buffered pinned staging), never materialised at full size on the GPU."""
         if state_dict_format == 1:
-            return self._state_dict_v1(gather_on_root)
+            return self._state_dict_v1(True if gather_on_root is None else gather_on_root)
         if state_dict_format not in (None, 2):
             raise ValueError(f"Unrecognized state dict format ({state_dict_format})")
         self.init_params()

@@ -232,7 +232,7 @@ class Permutation:
         cls.__tcpstore_port = tcpstore_port
 
     @classmethod
-    def set_permutation_saving_params(cls, allow_permutation=True, save_permutation_graph=False, permutation_output_dir="."):
+    def set_permutation_saving_params(cls, allow_permutation=False, save_permutation_graph=False, permutation_output_dir="."):
         cls.__allow_permutation = allow_permutation
         cls.__save_permutation_graph = save_permutation_graph
         cls.__permutation_output_dir = permutation_output_dir
@@ -835,7 +835,7 @@ class Permutation:
 
     # -------------------------------------------------------------------------------------------------------------- driver
     @classmethod
-    def permute_model(cls, model, dump_fx_graph=False, save_dumped_fx_graph=None, verbosity=0):
+    def permute_model(cls, model, dump_fx_graph=False, save_dumped_fx_graph="./model_permutation_graph.json", verbosity=0):
         """Search and apply a permutation for every unfrozen channel space; returns [(n consumers, magnitude before, after)]."""
         cls.__verbosity = verbosity
         cls.__stats = {"C": 0, "K": 0}
