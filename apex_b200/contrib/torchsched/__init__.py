@@ -10,7 +10,6 @@ fused kernel first. Also exported: :class:`StreamScheduler` (the same fork / joi
 from __future__ import annotations
 
 import os
-from contextlib import contextmanager
 
 import torch
 

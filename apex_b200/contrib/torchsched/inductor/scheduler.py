@@ -150,7 +150,7 @@ class MultiCudaStreamScheduler:
         self._recorded_on_current.update(fresh)
 
     # ---- program ------------------------------------------------------------------------------------------------------------------
-    def _side_streams_need_final_event(self) -> None:
+    def _find_tail_nodes(self) -> None:
         """A side stream whose last node has no cross-stream consumer (its value is dead, or consumed on the same stream) still has to be
         joined: give its last node an event."""
         last_node: dict = {}
@@ -172,7 +172,7 @@ class MultiCudaStreamScheduler:
         for m, n in last_use.items():
             if n.op != "output" and m.op != "placeholder":
                 frees.setdefault(n, []).append(m.name)
-        self._side_streams_need_final_event()
+        self._find_tail_nodes()
         for n in self.nodes:
             if n.op == "placeholder":
                 continue
