@@ -281,11 +281,29 @@ class Permutation:
         spaces: list = []
         first_use: dict = {}   # id(module) -> (input space, output space): a module called twice ties both call sites together
 
+        def poison(m, why):
+            """``m`` is called again at a site that cannot be merged with its earlier call(s) (one of them reads a concatenation slice by slice,
+            or the module is a grouped convolution): the tensors are shared, so NO call site may be permuted."""
+            prev = first_use.get(id(m))
+            if prev is None:
+                return
+            ins, outs = (prev[1], [prev[2]]) if prev[0] == "exclusive" else ([prev[0]], [prev[1]])
+            for sp in list(ins) + outs:
+                if sp is not None:
+                    sp.freeze(why)
+
         def reuse(m, src_space, out_space):
             prev = first_use.get(id(m))
             if prev is None:
                 first_use[id(m)] = (src_space, out_space)
                 return False
+            if prev[0] == "exclusive":
+                why = f"{type(m).__name__} reused at call sites that cannot be merged"
+                poison(m, why)
+                for sp in (src_space, out_space):
+                    if sp is not None:
+                        sp.freeze(why)
+                return True
             if src_space is not None and prev[0] is not None:
                 prev[0].union(src_space)
             if out_space is not None and prev[1] is not None:
@@ -400,12 +418,12 @@ class Permutation:
                     aligned = all(sz % 4 == 0 for _, sz in src.parts)
                     if isinstance(m, _CONVS + (nn.Linear,)) and (not isinstance(m, _CONVS) or m.groups == 1) and aligned and id(m) not in first_use \
                             and src.axis == (1 if isinstance(m, _CONVS) else -1):
-                        first_use[id(m)] = (None, None)
+                        out = new_space()
+                        first_use[id(m)] = ("exclusive", [v.space for v, _ in src.parts], out)
                         off = 0
                         for v, sz in src.parts:
                             v.space.find().consumers.append((_Slice(m, 1, off, sz), "weight", 1, 1, True, node.target, sz))
                             off += sz
-                        out = new_space()
                         out.riders.append((m, "weight", 0, node.target))
                         if m.bias is not None:
                             out.riders.append((m, "bias", 0, node.target))
@@ -413,7 +431,7 @@ class Permutation:
                         vals[node] = _Val(out, 1 if is_conv else -1, m.weight.dim() if is_conv else None,
                                           size=m.out_channels if is_conv else m.out_features)
                     elif isinstance(m, _BN_MODULES) and src.axis == 1 and id(m) not in first_use:
-                        first_use[id(m)] = (None, None)
+                        first_use[id(m)] = ("exclusive", [v.space for v, _ in src.parts], None)
                         off = 0
                         for v, sz in src.parts:
                             for name in ("weight", "bias", "running_mean", "running_var"):
@@ -425,7 +443,9 @@ class Permutation:
                     elif isinstance(m, _PASS_MODULES) or (isinstance(m, _SPATIAL_MODULES) and src.axis == 1):
                         vals[node] = src
                     else:
-                        src.freeze(f"{type(m).__name__} at {node.target} on a concatenation")
+                        why = f"{type(m).__name__} at {node.target} on a concatenation"
+                        src.freeze(why)
+                        poison(m, why)
                         vals[node] = _Val(new_space("consumer of a frozen concatenation"), None)
                     continue
                 if isinstance(m, _CONVS + (nn.Linear,)):
@@ -458,10 +478,12 @@ class Permutation:
                         vals[node] = src.like(spatial1=False)
                     elif (src.axis == 1 and cin % groups == 0 and (cin // groups) % 4 == 0 and cin // groups > 4 and id(m) not in first_use):
                         # grouped: the input space stays permutable inside its channel blocks; the output channels are tied to the groups
-                        first_use[id(m)] = (None, None)
+                        out = new_space(f"output of grouped convolution {node.target}")
+                        first_use[id(m)] = ("exclusive", [src.space], out)
                         src.space.find().consumers.append((_Grouped(m, groups), "weight", 1, 1, True, node.target, cin))
-                        vals[node] = _Val(new_space(f"output of grouped convolution {node.target}"), 1, rank, size=cout)
+                        vals[node] = _Val(out, 1, rank, size=cout)
                     else:
+                        poison(m, f"grouped convolution {node.target} called more than once")
                         opaque(node, f"grouped convolution {node.target}")
                 elif isinstance(m, _CONV_T):
                     if not isinstance(src, _Val) or m.groups != 1:
