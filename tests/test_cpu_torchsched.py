@@ -635,3 +635,14 @@ def test_transformer_layer_forward_and_backward_programs(monkeypatch):
                 torch.testing.assert_close(a, b)
         checked += 1
     assert checked >= 2
+
+
+def test_codegen_fuzz_over_many_node_kinds():
+    """tests/fuzz/fuzz_torchsched_codegen.py (modules, kwargs, getitem of multi-output ops, slices, dtype / inf constants, python scalars,
+    tuple / dict / single outputs): the generated program returns exactly what the graph module returns; 300 seeds run offline."""
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz", "fuzz_torchsched_codegen.py")
+    out = subprocess.run([sys.executable, script, "0", "40"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().splitlines()[-1] == "bad 0", out.stdout[-2000:] + out.stderr[-2000:]
