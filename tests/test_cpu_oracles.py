@@ -85,3 +85,36 @@ def test_transducer_loss_reference_against_alignment_enumeration(seed):
     xm[idx] -= eps
     fd = (TransducerLoss()(xp, label, f_len, y_len, blank).sum() - TransducerLoss()(xm, label, f_len, y_len, blank).sum()) / (2 * eps)
     assert g[idx].item() == pytest.approx(fd.item(), abs=2e-3)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_focal_loss_reference_against_the_closed_form(seed):
+    """Element by element: loss = c_f (base + softplus(-x)), d loss / dx = c_f (c_b (base + softplus(-x)) - off_b), with the smoothing
+    constants and the positive / negative coefficients of the reference kernel (focal_loss_cuda_kernel.cu:30-106), ignored rows (label -2)
+    and padded classes contributing nothing."""
+    from apex_b200.contrib.focal_loss import focal_loss
+    rng = random.Random(seed)
+    torch.manual_seed(seed)
+    n, n_cls = rng.randint(1, 12), rng.randint(3, 9)
+    real = rng.randint(2, n_cls)
+    alpha, gamma, s = rng.choice([0.25, 0.5]), rng.choice([0.0, 1.5, 2.0]), rng.choice([0.0, 0.1])
+    x = torch.randn(n, n_cls, requires_grad=True)
+    tgt = torch.tensor([rng.choice([-2, -1] + list(range(real))) for _ in range(n)])
+    npos = torch.tensor([float(rng.randint(1, 5))])
+    loss = focal_loss(x, tgt, npos, real, alpha, gamma, s)
+    (grad,) = torch.autograd.grad(loss, x)
+    want, want_grad = 0.0, torch.zeros(n, n_cls, dtype=torch.float64)
+    for i in range(n):
+        if int(tgt[i]) == -2:
+            continue
+        for c in range(real):
+            p = float(x[i, c].detach())
+            sig, softplus = 1 / (1 + math.exp(-p)), math.log1p(math.exp(-abs(p))) + max(-p, 0.0)
+            if int(tgt[i]) == c:
+                base, off_b, c_f, c_b = (s - s / 2) * p, (1 - s + s / 2) - sig, alpha * (1 - sig) ** gamma, -gamma * sig
+            else:
+                base, off_b, c_f, c_b = (1 - s / 2) * p, s / 2 - sig, (1 - alpha) * sig ** gamma, gamma * (1 - sig)
+            want += c_f * (base + softplus)
+            want_grad[i, c] = c_f * (c_b * (base + softplus) - off_b)
+    assert loss.item() == pytest.approx(want / float(npos), rel=1e-4, abs=1e-6)
+    torch.testing.assert_close(grad.double(), want_grad / float(npos), atol=1e-5, rtol=1e-4)
