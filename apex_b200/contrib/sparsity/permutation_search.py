@@ -502,3 +502,203 @@ def permutation_distance(A, B, matrix=None, magnitude_targets=None, debug: bool 
         if swaps > limit:
             break
     return swaps, results
+
+
+# ---- incremental map stages: the pieces of the reference's greedy loops, for callers that drive the loop themselves ------------------
+# `_greedy` above rescans every stripe group per round on the device; these keep a score table between rounds and rescore only the
+# entries whose stripes changed (reference exhaustive_search.py:36-72, 209-372 and channel_swap.py:72-206). Scoring goes through the
+# same batched `_score_groups` (ab_stripe_search on a GPU) instead of one search_matrix / try_swap call per entry.
+def generate_unique_combinations(built_permutation, remaining_columns, full_permutation_list, group_width: int = 4):
+    """Append to ``full_permutation_list`` every canonical arrangement that extends ``built_permutation`` with ``remaining_columns``
+    (ascending): columns ascend inside a group and a group opens with the smallest column not placed yet. The two argument lists are
+    left as they were (exhaustive_search.py:36-72; iterative here, no recursion depth limit)."""
+    stack = [(list(built_permutation), list(remaining_columns))]
+    while stack:
+        built, rest = stack.pop()
+        if not rest:
+            full_permutation_list.append(np.asarray(built))
+            continue
+        if len(built) % group_width == 0:
+            # only the smallest unused column may open a group, and it must follow the opener of the group before
+            nxt = [0] if all(v in built for v in range(rest[0])) and (not built or rest[0] > built[-group_width]) else []
+        else:
+            nxt = [i for i, c in enumerate(rest) if c > built[-1]]
+        for i in reversed(nxt):                                   # reversed: the stack pops them in ascending order
+            stack.append((built + [rest[i]], rest[:i] + rest[i + 1:]))
+    return full_permutation_list
+
+
+_stripe_group_cache: dict = {}
+
+
+def _ordered_stripe_groups(num_stripes: int, window: int):
+    key = (num_stripes, window)
+    if key not in _stripe_group_cache:
+        _stripe_group_cache[key] = list(itertools.combinations(range(num_stripes), window))
+    return _stripe_group_cache[key]
+
+
+def build_stripe_map(matrix, group_width, window_size, stripe_map, stripe_ids, perm_map, used_stripes):
+    """Score table of the exhaustive strategy: one entry per group of ``window_size / group_width`` stripes = (best improvement any
+    arrangement of its columns gives, that arrangement). Entries are created on the first call; afterwards only groups containing a
+    stripe of ``used_stripes`` are rescored. -> (stripe_map, stripe_ids, perm_map), updated in place (exhaustive_search.py:209-288)."""
+    if group_width != 4:
+        raise NotImplementedError("scoring is 2:4 specific: group_width must be 4")
+    C = matrix.shape[1]
+    S = int(window_size) // group_width
+    assert C % group_width == 0 and 2 <= S <= C // group_width
+    groups = _ordered_stripe_groups(C // group_width, S)
+    used = set(int(s) for s in used_stripes)
+    stale = []
+    for i, sg in enumerate(groups):
+        if i >= len(stripe_map):
+            stripe_ids.append(list(sg))
+            stripe_map.append(0.0)
+            perm_map.append(list(range(group_width * S)))
+            stale.append(i)
+        elif used.intersection(sg):
+            stale.append(i)
+    if stale:
+        m = _t(matrix).detach().float().contiguous()
+        cands = generate_all_unique_combinations(group_width * S, group_width)
+        imp, idx = _score_groups(m, torch.tensor([groups[i] for i in stale], dtype=torch.int32, device=m.device), cands)
+        for i, v, k in zip(stale, imp.tolist(), idx.tolist()):
+            stripe_map[i] = float(v)
+            perm_map[i] = [int(c) for c in cands[k if v > 0 else 0]]
+    return stripe_map, stripe_ids, perm_map
+
+
+sm_perturbations = 0          # escape moves spent / allowed by use_stripe_map (module state, as in the reference)
+sm_perturbation_limit = 0
+
+
+def use_stripe_map(matrix, group_width, stripe_map, stripe_ids, perm_map, permutation):
+    """Apply the table of :func:`build_stripe_map` greedily, best improvement first, skipping groups that share a stripe with one already
+    applied this round. ``matrix`` (numpy or tensor) is permuted in place. With nothing left to gain, and while
+    ``sm_perturbations < sm_perturbation_limit``, one random group is applied with two of its columns exchanged across its halves.
+    -> (matrix, groups applied, stripe_map, stripe_ids, stripes whose content changed, summed improvement, permutation)
+    (exhaustive_search.py:296-372)."""
+    global sm_perturbations
+    eps = float(np.finfo(np.float16).tiny) * 5.0
+    order = np.argsort(-np.asarray(stripe_map, dtype=np.float64), kind="stable")
+    touched: set = set()
+    changed_stripes: list = []
+    applied, gain = 0, 0.0
+    for gid in order:
+        gid = int(gid)
+        arrangement = list(perm_map[gid])
+        if stripe_map[gid] <= eps:
+            if touched or sm_perturbations >= sm_perturbation_limit:
+                break
+            sm_perturbations += 1
+            gid = int(order[np.random.randint(len(order))])
+            arrangement = list(perm_map[gid])
+            half = len(arrangement) // 2
+            a, b = np.random.randint(half), half + np.random.randint(half)
+            arrangement[a], arrangement[b] = arrangement[b], arrangement[a]
+        sg = stripe_ids[gid]
+        if touched.intersection(sg):
+            continue
+        touched.update(sg)
+        cols = [s * group_width + k for s in sg for k in range(group_width)]
+        src = [cols[c] for c in arrangement]
+        matrix[..., cols] = matrix[..., src]
+        permutation = apply_stripe_group_permutation(arrangement, sg, group_width, permutation)
+        for k, s in enumerate(sg):
+            blk = arrangement[k * group_width:(k + 1) * group_width]
+            # a stripe keeps its content when it received one whole source stripe in order
+            if blk[0] % group_width or any(blk[j] != blk[0] + j for j in range(1, group_width)):
+                changed_stripes.append(s)
+        gain += stripe_map[gid]
+        applied += 1
+    return matrix, applied, stripe_map, stripe_ids, changed_stripes, gain, permutation
+
+
+def compute_swap_map(matrix, used_stripes):
+    """{(col0, col1): improvement of exchanging the two columns} for the 16 swaps of every stripe pair that contains a stripe of
+    ``used_stripes``, all pairs scored in one batch (channel_swap.py:72-90). Runs on the CPU too (the reference asserts a GPU)."""
+    pairs = build_stripe_pairs(matrix, used_stripes)
+    out: dict = {}
+    if len(pairs) == 0:
+        return out
+    m = _t(matrix).detach().float().contiguous()
+    a = m.abs()
+    R = a.shape[0]
+    kept = _stripe_sums(m)                                                              # [C/4]
+    p = torch.as_tensor(pairs.astype(np.int64), device=m.device)
+    stripes = a.view(R, -1, 4)
+    imp = torch.empty(len(pairs), 16, device=m.device)
+    step = max(1, (1 << 22) // max(1, R * 4))                                           # bound the [R, pairs, 4] temporaries
+    for c0 in range(0, len(pairs), step):
+        q = p[c0:c0 + step]
+        left, right = stripes[:, q[:, 0]], stripes[:, q[:, 1]]                           # [R, P, 4]
+        base = kept[q[:, 0]] + kept[q[:, 1]]
+        for i in range(4):
+            for j in range(4):
+                l2, r2 = left.clone(), right.clone()
+                l2[..., i], r2[..., j] = right[..., j], left[..., i]
+                imp[c0:c0 + step, i * 4 + j] = l2.topk(2, dim=-1).values.sum((0, 2)) + r2.topk(2, dim=-1).values.sum((0, 2)) - base
+    imp[p[:, 0] == p[:, 1]] = 0.0                                                       # a stripe paired with itself: nothing moves
+    imp_h = imp.tolist()
+    for (s0, s1), row in zip(pairs.tolist(), imp_h):
+        for k in range(16):
+            out[stripes_and_swap_idx_to_columns(s0, s1, k)] = row[k]
+    return out
+
+
+def build_swap_map(matrix, swap_map, swap_ids, used_stripes, verbosity=0):
+    """Score table of the channel-swap strategy: one entry per column pair (src < dst) from two different stripes, in row-major order.
+    First call (empty ``swap_map``) scores everything, later calls only pairs touching ``used_stripes``. -> (swap_map, swap_ids),
+    updated in place (channel_swap.py:94-138)."""
+    C = matrix.shape[1]
+    fresh = len(swap_map) == 0
+    used = list(range(C // 4)) if fresh else sorted(set(int(s) for s in used_stripes))
+    scores = compute_swap_map(matrix, used)
+    used_set = set(used)
+    idx = updates = 0
+    for src in range(C - 1):
+        for dst in range(src + 1, C):
+            if src // 4 == dst // 4:
+                continue
+            if fresh or src // 4 in used_set or dst // 4 in used_set:
+                v = float(scores[(src, dst)])
+                if idx >= len(swap_map):
+                    swap_map.append(v)
+                    swap_ids.append((src, dst))
+                else:
+                    swap_map[idx], swap_ids[idx] = v, (src, dst)
+                updates += 1
+            idx += 1
+    if verbosity > 15:
+        print(f"\tupdated {updates} map entries")
+    return swap_map, swap_ids
+
+
+def use_swap_map(matrix, swap_map, swap_ids, threshold, used_escape_attempts, escape_attempts, permutation, verbosity=0):
+    """Apply the table of :func:`build_swap_map`: swaps in order of benefit while the benefit stays above ``threshold`` x the best one
+    (clamped to [1e-4, 1]), at most one swap per stripe per round; once converged, up to ``escape_attempts`` random swaps.
+    ``matrix`` and ``permutation`` are modified in place. -> (matrix, swaps, swap_map, swap_ids, used_stripes, improvement,
+    used_escape_attempts, permutation) (channel_swap.py:141-206)."""
+    scores = np.asarray(swap_map, dtype=np.float64)
+    order = np.argsort(-scores, kind="stable")
+    floor = min(max(float(scores[order[0]]) * threshold, 1e-4), 1.0)
+    used_stripes: list = []
+    swaps, gain = 0, 0.0
+    for sid in order:
+        sid = int(sid)
+        if scores[sid] < floor:
+            if used_stripes or used_escape_attempts >= escape_attempts:
+                break
+            sid = int(order[np.random.randint(len(order))])
+            used_escape_attempts += 1
+            if verbosity > 15:
+                print(f"converged, escape attempt #{used_escape_attempts}: swapping columns {swap_ids[sid]}")
+        src, dst = swap_ids[sid]
+        if src // 4 in used_stripes or dst // 4 in used_stripes:
+            continue
+        used_stripes += [src // 4, dst // 4]
+        matrix[..., [src, dst]] = matrix[..., [dst, src]]
+        permutation[src], permutation[dst] = permutation[dst], permutation[src]
+        gain += float(scores[sid])
+        swaps += 1
+    return matrix, swaps, swap_map, swap_ids, used_stripes, gain, used_escape_attempts, permutation

@@ -2,11 +2,13 @@
 after permute_model, and the number of tensors permuted along C / K must match what the graph allows. Modelled on the reference's
 apex/contrib/sparsity/test/test_permutation_application.py (simple_convs x normalisations, forks / joins, grouped and depthwise convs,
 module attributes, MHA, concat, flatten, trace failure)."""
+import numpy as np
 import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from apex_b200.contrib.sparsity import permutation_search as ps
 from apex_b200.contrib.sparsity.permutation_lib import Permutation as P
 
 
@@ -720,3 +722,68 @@ def test_module_reused_on_a_concatenation_and_on_a_plain_value_is_left_alone(cat
     P.permute_model(m)
     torch.testing.assert_close(m(x).detach(), y0, atol=1e-5, rtol=1e-5)
     assert torch.equal(m.shared.weight, before)
+
+
+# ---- incremental map stages (build_* / use_* of the reference's greedy loops) against the one-entry-at-a-time oracles ----
+
+def test_generate_unique_combinations_matches_closed_form():
+    for C in (4, 8, 12):
+        out = []
+        ps.generate_unique_combinations([0], list(range(1, C)), out, 4)
+        assert len(out) == ps.predict_unique_combinations(C, 4)
+        ref = ps.generate_all_unique_combinations(C, 4)
+        assert sorted(map(tuple, out)) == sorted(map(tuple, ref.tolist()))
+        assert tuple(out[0]) == tuple(range(C))
+
+def test_swap_map_matches_try_swap_and_loop_improves():
+    rng = np.random.default_rng(0)
+    m = rng.standard_normal((16, 24)).astype(np.float32)
+    sm, ids = ps.build_swap_map(m, [], [], [], 0)
+    assert len(sm) == len(ids) == (24 * 23 // 2 - 6 * 6)
+    for k in range(0, len(ids), 7):
+        _, imp = ps.try_swap(m, ids[k][1], ids[k][0])
+        assert abs(imp - sm[k]) < 1e-4, (ids[k], imp, sm[k])
+    orig = m.copy(); perm = list(range(24)); base = float(ps.sum_after_2_to_4(torch.from_numpy(m)))
+    used_esc = 0; total = base
+    for _ in range(50):
+        m, swaps, sm, ids, used, gain, used_esc, perm = ps.use_swap_map(m, sm, ids, 0.5, used_esc, 0, perm, 0)
+        now = float(ps.sum_after_2_to_4(torch.from_numpy(m)))
+        assert abs((now - total) - gain) < 1e-3
+        total = now
+        assert np.array_equal(m, orig[:, perm])
+        if swaps == 0: break
+        sm, ids = ps.build_swap_map(m, sm, ids, used, 0)
+    assert total > base
+    # the incrementally maintained table equals a table built from scratch
+    fresh, _ = ps.build_swap_map(m, [], [], [], 0)
+    assert np.allclose(fresh, sm, atol=1e-4)
+
+def test_stripe_map_matches_search_matrix_and_loop_improves():
+    rng = np.random.default_rng(1)
+    m = rng.standard_normal((12, 20)).astype(np.float32)
+    smap, sids, pmap = ps.build_stripe_map(m, 4, 8, [], [], [], [])
+    assert len(smap) == 10
+    for g in range(len(sids)):
+        sub = ps.collect_stripes(m, sids[g], 4)
+        _, _, p, imp = ps.search_matrix(sub, 4)
+        assert abs(imp - smap[g]) < 1e-3
+        kept = float(ps.sum_after_2_to_4(torch.from_numpy(np.ascontiguousarray(sub[:, pmap[g]])))) - float(ps.sum_after_2_to_4(torch.from_numpy(np.ascontiguousarray(sub))))
+        assert abs(kept - smap[g]) < 1e-3
+    orig = m.copy(); perm = list(range(20)); total = base = float(ps.sum_after_2_to_4(torch.from_numpy(m)))
+    for _ in range(50):
+        m, n, smap, sids, used, gain, perm = ps.use_stripe_map(m, 4, smap, sids, pmap, perm)
+        now = float(ps.sum_after_2_to_4(torch.from_numpy(np.ascontiguousarray(m))))
+        assert abs((now - total) - gain) < 1e-3
+        total = now
+        assert np.array_equal(m, orig[:, list(perm)])
+        if n == 0: break
+        smap, sids, pmap = ps.build_stripe_map(m, 4, 8, smap, sids, pmap, used)
+    assert total > base
+    fresh = ps.build_stripe_map(m, 4, 8, [], [], [], [])[0]
+    assert np.allclose(fresh, smap, atol=1e-3)
+    # perturbation: converged table + budget of one escape move changes the matrix
+    ps.sm_perturbations, ps.sm_perturbation_limit = 0, 1
+    np.random.seed(0)
+    m2, n, *_ , perm2 = ps.use_stripe_map(m.copy(), 4, smap, sids, pmap, list(perm))
+    assert n == 1 and ps.sm_perturbations == 1 and np.array_equal(m2, orig[:, list(perm2)])
+    ps.sm_perturbation_limit = ps.sm_perturbations = 0
