@@ -77,6 +77,31 @@ def test_batchnorm_family_cpu():
     torch.testing.assert_close(m(x, z), ref, atol=1e-5, rtol=1e-5)
     m(x, z).sum().backward()
     assert x.grad.shape == x.shape
+    # functional forms with the reference's argument lists (bnp plumbing arguments are ignored): training + eval, gradients vs autograd
+    from apex_b200.contrib.groupbn.batch_norm import bn_addrelu_NHWC_impl, bn_NHWC_impl
+    w, b = torch.randn(8, requires_grad=True), torch.randn(8, requires_grad=True)
+    rm, rv = torch.zeros(8), torch.ones(8)
+    xa, za = torch.randn(2, 4, 4, 8, requires_grad=True), torch.randn(2, 4, 4, 8, requires_grad=True)
+    scratch = (torch.empty(8), torch.empty(8), torch.zeros(8192, dtype=torch.uint8))
+    ipc = (None, None, torch.IntTensor([0]), None, None, 2, 284, 2, 284, False)
+    y = bn_NHWC_impl.apply(xa, w, b, rm, rv, *scratch, 0.1, 1e-5, False, True, 1, *ipc)
+    rm2, rv2 = torch.zeros(8), torch.ones(8)
+    yr = F.batch_norm(xa.permute(0, 3, 1, 2), rm2, rv2, w, b, True, 0.1, 1e-5).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y, yr, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(rm, rm2, atol=1e-6, rtol=1e-5)
+    torch.testing.assert_close(rv, rv2, atol=1e-6, rtol=1e-5)
+    gy = torch.randn_like(y)
+    for a, r in zip(torch.autograd.grad(y, (xa, w, b), gy), torch.autograd.grad(yr, (xa, w, b), gy)):
+        torch.testing.assert_close(a, r, atol=1e-4, rtol=1e-4)
+    y = bn_addrelu_NHWC_impl.apply(xa, za, w, b, rm, rv, scratch[0], scratch[1], 1, scratch[2], 0.1, 1e-5, True, 1, *ipc)
+    yr = torch.relu(F.batch_norm(xa.permute(0, 3, 1, 2), None, None, w, b, True, 0.1, 1e-5).permute(0, 2, 3, 1) + za)
+    torch.testing.assert_close(y, yr, atol=1e-5, rtol=1e-5)
+    for a, r in zip(torch.autograd.grad(y, (xa, za, w, b), gy), torch.autograd.grad(yr, (xa, za, w, b), gy)):
+        torch.testing.assert_close(a, r, atol=1e-4, rtol=1e-4)
+    y = bn_NHWC_impl.apply(xa, w, b, rm, rv, *scratch, 0.1, 1e-5, True, False, 1, *ipc)                  # eval: running statistics + ReLU
+    torch.testing.assert_close(y, torch.relu(F.batch_norm(xa.permute(0, 3, 1, 2), rm, rv, w, b, False, 0.0, 1e-5)).permute(0, 2, 3, 1))
+    with pytest.raises(RuntimeError, match="bn_group=4"):
+        bn_NHWC_impl.apply(xa, w, b, rm, rv, *scratch, 0.1, 1e-5, False, True, 4, *ipc)
     assert GroupBatchNorm2d(8, group_size=1)(torch.randn(2, 8, 4, 4)).shape == (2, 8, 4, 4)
     net = convert_syncbn_model(nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4)))
     assert isinstance(net[1], SyncBatchNorm)
