@@ -513,6 +513,10 @@ def _contrib_raw_mods():
     mods["permutation_search_cuda"] = _perm_search_mod()
     mods["fmhalib"] = _fmhalib_mod()
     mods["cudnn_gbn_lib"] = _cudnn_gbn_mod()
+    # ---- fast_multihead_attn: the 8 forward / backward pairs with the reference's intermediate-tensor conventions
+    from .contrib.multihead_attn import raw_ext
+
+    mods["fast_multihead_attn"] = _mod("fast_multihead_attn", **{n: getattr(raw_ext, n) for n in raw_ext.ENTRY_POINTS})
     return mods
 
 
