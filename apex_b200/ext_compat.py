@@ -516,8 +516,117 @@ def _contrib_raw_mods():
     # ---- fast_multihead_attn: the 8 forward / backward pairs with the reference's intermediate-tensor conventions
     from .contrib.multihead_attn import raw_ext
 
+    mods["peer_memory_cuda"] = _peer_memory_mod()
     mods["fast_multihead_attn"] = _mod("fast_multihead_attn", **{n: getattr(raw_ext, n) for n in raw_ext.ENTRY_POINTS})
     return mods
+
+
+def blob_strides(shape, channels_last: bool):
+    """Strides of a typed view into a raw blob: dense row-major, or the NHWC strides of a logical [N, C, H, W] shape
+    (reference peer_memory_cuda.cu:34-55)."""
+    shape = [int(d) for d in shape]
+    if channels_last:
+        assert len(shape) == 4, "channels_last views are 4-D"
+        n, c, h, w = shape
+        return [c * h * w, 1, c * w, c]
+    strides, acc = [], 1
+    for d in reversed(shape):
+        strides.append(acc)
+        acc *= d
+    return strides[::-1]
+
+
+def _peer_memory_mod():
+    """``peer_memory_cuda`` (reference apex/contrib/csrc/peer_memory/peer_memory.cpp:19-36): raw cudaIpc blobs addressed by integer
+    pointers. ``PeerMemoryPool`` here lives on the VMM symmetric heap and needs none of this; the raw calls serve code written against
+    the extension: blobs come from the cudaIpc functions of csrc/symm_heap.cpp, the halo exchange is staged as copy -> barrier -> copy
+    (the one-kernel exchange, csrc/halo_exchange.cu, needs the heap's signal pads, which a bare pointer API cannot name)."""
+    import ctypes
+
+    from . import _lib
+    from .parallel.symmetric import _tensor_from_ptr
+
+    _lib.declare("ab_ipc_alloc", "i l p p")
+    _lib.declare("ab_ipc_open", "i p p")
+    _lib.declare("ab_ipc_free", "l")
+    blobs: dict = {}                                                   # raw pointer -> (ipc handle bytes, nbytes)
+
+    def _need_gpu(what):
+        if not (_lib.available() and torch.cuda.is_available()):
+            raise RuntimeError(f"peer_memory_cuda.{what} needs a CUDA device and the apex_b200 native library")
+
+    def _bytes_view(raw, nbytes):
+        return _tensor_from_ptr(int(raw), int(nbytes), torch.device("cuda", torch.cuda.current_device()), None)
+
+    def allocate_raw(size):
+        _need_gpu("allocate_raw")
+        p, h = ctypes.c_uint64(0), ctypes.create_string_buffer(64)
+        _lib.fn("ab_ipc_alloc")(torch.cuda.current_device(), int(size), ctypes.addressof(p), ctypes.addressof(h))
+        blobs[int(p.value)] = (bytes(h.raw), int(size))
+        _bytes_view(p.value, size).zero_()
+        return int(p.value)
+
+    def free_raw(raw):
+        _need_gpu("free_raw")
+        torch.cuda.synchronize()
+        blobs.pop(int(raw), None)
+        _lib.fn("ab_ipc_free")(int(raw))
+
+    def zero(raw, size):
+        _need_gpu("zero")
+        _bytes_view(raw, size).zero_()
+
+    def get_raw_ipc_address(raw):
+        if int(raw) not in blobs:
+            raise ValueError("get_raw_ipc_address: not a pointer returned by allocate_raw")
+        return torch.frombuffer(bytearray(blobs[int(raw)][0]), dtype=torch.uint8).clone()
+
+    def get_raw_peers(ipc_addresses, peer_rank, raw):
+        _need_gpu("get_raw_peers")
+        out = []
+        for i in range(ipc_addresses.size(0)):
+            if i == int(peer_rank):
+                out.append(int(raw))
+                continue
+            h = ctypes.create_string_buffer(bytes(ipc_addresses[i].cpu().contiguous().numpy().tobytes()), 64)
+            p = ctypes.c_uint64(0)
+            _lib.fn("ab_ipc_open")(torch.cuda.current_device(), ctypes.addressof(h), ctypes.addressof(p))
+            out.append(int(p.value))
+        return out
+
+    def _blob_view(dtype):
+        def view(raw, shape, channels_last):
+            _need_gpu("blob_view")
+            numel = 1
+            for d in shape:
+                numel *= int(d)
+            flat = _bytes_view(raw, numel * torch.empty((), dtype=dtype).element_size()).view(dtype)
+            return flat.as_strided([int(d) for d in shape], blob_strides(shape, channels_last))
+        return view
+
+    def push_pull_halos_1d(diagnostics, explicit_nhwc, numSM, rank, top_zero, top_out_halo, top_in_transfer, top_out_transfer,
+                           top_in_halo, btm_zero, btm_out_halo, btm_in_transfer, btm_out_transfer, btm_in_halo):
+        """Send the two outgoing halos into the neighbours' transfer buffers, receive the incoming ones from the local transfer buffers
+        (or zero them at the ends of the split). Collective over the default process group."""
+        import torch.distributed as dist
+
+        assert not (top_zero and btm_zero)
+        if not top_zero:
+            top_out_transfer.copy_(top_out_halo)
+        if not btm_zero:
+            btm_out_transfer.copy_(btm_out_halo)
+        torch.cuda.current_stream().synchronize()
+        if dist.is_initialized():
+            dist.barrier()                                   # every push has landed
+        top_in_halo.zero_() if top_zero else top_in_halo.copy_(top_in_transfer)
+        btm_in_halo.zero_() if btm_zero else btm_in_halo.copy_(btm_in_transfer)
+        torch.cuda.current_stream().synchronize()
+        if dist.is_initialized():
+            dist.barrier()                                   # transfer buffers may be overwritten by the next exchange
+
+    return _mod("peer_memory_cuda", allocate_raw=allocate_raw, free_raw=free_raw, zero=zero, get_raw_ipc_address=get_raw_ipc_address,
+                get_raw_peers=get_raw_peers, blob_view_half=_blob_view(torch.float16), blob_view_float=_blob_view(torch.float32),
+                blob_view_int=_blob_view(torch.int32), push_pull_halos_1d=push_pull_halos_1d)
 
 
 _gbn_groups: dict = {}

@@ -457,3 +457,22 @@ def test_cudnn_gbn_lib_single_rank_matches_batch_norm():
     torch.testing.assert_close(dx, xr.grad, atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(dw, wr.grad, atol=1e-4, rtol=1e-4)
     torch.testing.assert_close(db, br.grad, atol=1e-4, rtol=1e-4)
+
+
+def test_peer_memory_cuda_extension_name_cpu():
+    """Registration, the typed-view stride rule (reference peer_memory_cuda.cu:34-55) and the loud failure without a GPU."""
+    import pytest
+    import torch
+    from apex_b200 import ext_compat
+    m = ext_compat.extension_modules()["peer_memory_cuda"]
+    for n in ("allocate_raw", "free_raw", "zero", "get_raw_ipc_address", "get_raw_peers", "blob_view_half", "blob_view_float",
+              "blob_view_int", "push_pull_halos_1d"):
+        assert callable(getattr(m, n))
+    assert ext_compat.blob_strides([2, 3, 4, 5], False) == list(torch.empty(2, 3, 4, 5).stride())
+    assert ext_compat.blob_strides([2, 3, 4, 5], True) == list(torch.empty(2, 3, 4, 5).contiguous(memory_format=torch.channels_last).stride())
+    assert ext_compat.blob_strides([7], False) == [1]
+    with pytest.raises(ValueError):
+        m.get_raw_ipc_address(1234)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA device"):
+            m.allocate_raw(1024)
