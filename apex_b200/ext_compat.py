@@ -517,6 +517,7 @@ def _contrib_raw_mods():
     from .contrib.multihead_attn import raw_ext
 
     mods["peer_memory_cuda"] = _peer_memory_mod()
+    mods["fast_bottleneck"] = _fast_bottleneck_mod()
     mods["fast_multihead_attn"] = _mod("fast_multihead_attn", **{n: getattr(raw_ext, n) for n in raw_ext.ENTRY_POINTS})
     return mods
 
@@ -534,6 +535,63 @@ def blob_strides(shape, channels_last: bool):
         strides.append(acc)
         acc *= d
     return strides[::-1]
+
+
+def _fast_bottleneck_mod():
+    """``fast_bottleneck.forward / backward`` (reference apex/contrib/csrc/bottleneck/bottleneck.cpp:1004-1141, 1143-1378): the whole
+    ResNet bottleneck on explicit tensor lists, as ``BottleneckFunction`` of the reference drives them (bottleneck.py:80-132).
+    forward(nhwc, stride, [x, w1, w2, w3, s1, s2, s3, b1, b2, b3(, w4, s4, b4)]) -> [out1, out2, out3];
+    backward(nhwc, stride, [x, w1, w2, w3, s1, s2, s3, b1, b2, b3, grad_conv3, grad_conv4, out1, out2(, w4)]) -> [dx, dw1, dw2, dw3(, dw4)]
+    where grad_conv3 / grad_conv4 are the caller's drelu x scale products of the main and the identity branch. Library convolutions
+    (as in the reference) around the fused scale-bias-(add)-ReLU tail of contrib/conv_bias_relu. The 21 staged entry points of the
+    spatial-parallel pipeline (forward_out2_halo, backward_grad_out1_halo_corr, ...) have no counterpart: ``SpatialBottleneck`` here
+    runs one halo-overlapped convolution Function instead of a hand-staged cuDNN graph sequence."""
+    from torch.nn import grad as G
+
+    from .contrib.conv_bias_relu.conv_bias_relu import fused_conv_epilogue
+
+    def _nchw(t, nhwc):
+        return t.permute(0, 3, 1, 2) if nhwc else t
+
+    def _back(t, nhwc):
+        return t.permute(0, 2, 3, 1).contiguous() if nhwc else t
+
+    vec = lambda t: t.reshape(1, -1, 1, 1)                                              # noqa: E731
+
+    def forward(explicit_nhwc, stride_1X1, inputs):
+        x, w1, w2, w3, s1, s2, s3, b1, b2, b3 = inputs[:10]
+        x, w1, w2, w3 = (_nchw(t, explicit_nhwc) for t in (x, w1, w2, w3))
+        with torch.no_grad():
+            out1 = fused_conv_epilogue(x, w1, bias=vec(b1), scale=vec(s1), stride=stride_1X1, padding=0, relu=True)
+            out2 = fused_conv_epilogue(out1, w2, bias=vec(b2), scale=vec(s2), stride=1, padding=1, relu=True)
+            identity = x
+            if len(inputs) > 10:
+                w4, s4, b4 = inputs[10:13]
+                identity = fused_conv_epilogue(x, _nchw(w4, explicit_nhwc), bias=vec(b4), scale=vec(s4), stride=stride_1X1, padding=0,
+                                               relu=False)
+            out3 = fused_conv_epilogue(out2, w3, bias=vec(b3), scale=vec(s3), z=identity, stride=1, padding=0, relu=True)
+        return [_back(o, explicit_nhwc) for o in (out1, out2, out3)]
+
+    def backward(explicit_nhwc, stride_1X1, inputs):
+        x, w1, w2, w3, s1, s2, s3 = inputs[:7]
+        g3, g4, out1, out2 = inputs[10:14]
+        x, w1, w2, w3, g3, g4, out1, out2 = (_nchw(t, explicit_nhwc) for t in (x, w1, w2, w3, g3, g4, out1, out2))
+        dw3 = G.conv2d_weight(out2, w3.shape, g3)
+        g2 = G.conv2d_input(out2.shape, w3, g3) * (out2 > 0).to(g3.dtype) * vec(s2).to(g3.dtype)
+        dw2 = G.conv2d_weight(out1, w2.shape, g2, padding=1)
+        g1 = G.conv2d_input(out1.shape, w2, g2, padding=1) * (out1 > 0).to(g3.dtype) * vec(s1).to(g3.dtype)
+        dw1 = G.conv2d_weight(x, w1.shape, g1, stride=stride_1X1)
+        dx = G.conv2d_input(x.shape, w1, g1, stride=stride_1X1)
+        grads = [dw1, dw2, dw3]
+        if len(inputs) > 14:
+            w4 = _nchw(inputs[14], explicit_nhwc)
+            dx = dx + G.conv2d_input(x.shape, w4, g4, stride=stride_1X1)
+            grads.append(G.conv2d_weight(x, w4.shape, g4, stride=stride_1X1))
+        else:
+            dx = dx + g4
+        return [_back(t, explicit_nhwc) for t in [dx] + grads]
+
+    return _mod("fast_bottleneck", forward=forward, backward=backward)
 
 
 def _peer_memory_mod():

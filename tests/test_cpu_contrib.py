@@ -476,3 +476,41 @@ def test_peer_memory_cuda_extension_name_cpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="CUDA device"):
             m.allocate_raw(1024)
+
+
+def test_fast_bottleneck_extension_name_cpu():
+    """fast_bottleneck.forward / backward on explicit tensor lists, driven the way the reference's BottleneckFunction drives them
+    (bottleneck.py:80-132), against autograd through the same block written with plain torch ops."""
+    import pytest
+    import torch
+    import torch.nn.functional as F
+    from apex_b200 import ext_compat
+    fb = ext_compat.extension_modules()["fast_bottleneck"]
+    for nhwc, stride, down in ((False, 1, False), (True, 2, True), (False, 2, True)):
+        torch.manual_seed(0)
+        Cin, Cmid, Cout = (8, 4, 8) if not down else (8, 4, 16)
+        x = torch.randn(2, Cin, 8, 8, dtype=torch.double, requires_grad=True)
+        ws = [torch.randn(Cmid, Cin, 1, 1, dtype=torch.double, requires_grad=True), torch.randn(Cmid, Cmid, 3, 3, dtype=torch.double, requires_grad=True),
+              torch.randn(Cout, Cmid, 1, 1, dtype=torch.double, requires_grad=True)]
+        if down:
+            ws.append(torch.randn(Cout, Cin, 1, 1, dtype=torch.double, requires_grad=True))
+        ss = [torch.rand(w.shape[0], dtype=torch.double) + 0.5 for w in ws]
+        bs = [torch.randn(w.shape[0], dtype=torch.double) for w in ws]
+        v = lambda t: t.view(1, -1, 1, 1)
+        o1 = torch.relu(F.conv2d(x, ws[0], stride=stride) * v(ss[0]) + v(bs[0]))
+        o2 = torch.relu(F.conv2d(o1, ws[1], padding=1) * v(ss[1]) + v(bs[1]))
+        idn = F.conv2d(x, ws[3], stride=stride) * v(ss[3]) + v(bs[3]) if down else x
+        o3 = torch.relu(F.conv2d(o2, ws[2]) * v(ss[2]) + v(bs[2]) + idn)
+        lay = (lambda t: t.detach().permute(0, 2, 3, 1).contiguous()) if nhwc else (lambda t: t.detach())
+        args = [lay(x)] + [lay(w) for w in ws[:3]] + ss[:3] + bs[:3] + ([lay(ws[3]), ss[3], bs[3]] if down else [])
+        outs = fb.forward(nhwc, stride, args)
+        for got, want in zip(outs, (o1, o2, o3)):
+            torch.testing.assert_close(got, lay(want))
+        go = torch.randn_like(o3)
+        want = torch.autograd.grad(o3, [x] + ws, go)
+        dre = go * (o3 > 0)
+        t_list = args[:10] + [lay(dre * v(ss[2])), lay(dre * v(ss[3]) if down else dre), outs[0], outs[1]] + ([args[10]] if down else [])
+        got = fb.backward(nhwc, stride, t_list)
+        assert len(got) == len(want)
+        for a, r in zip(got, want):
+            torch.testing.assert_close(a, lay(r))
