@@ -516,6 +516,9 @@ def _contrib_raw_mods():
     # ---- fast_multihead_attn: the 8 forward / backward pairs with the reference's intermediate-tensor conventions
     from .contrib.multihead_attn import raw_ext
 
+    from .contrib.groupbn import raw_ext as bnp_ext
+
+    mods["bnp"] = _mod("bnp", **{n: getattr(bnp_ext, n) for n in bnp_ext.ENTRY_POINTS})
     mods["peer_memory_cuda"] = _peer_memory_mod()
     mods["fast_bottleneck"] = _fast_bottleneck_mod()
     mods["fast_multihead_attn"] = _mod("fast_multihead_attn", **{n: getattr(raw_ext, n) for n in raw_ext.ENTRY_POINTS})

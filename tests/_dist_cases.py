@@ -595,6 +595,21 @@ def group_batchnorm_spans_only_its_group(rank, world, device_type):
     gbn = GroupBatchNorm2d(C, group_size=2)
     got = gbn(mine.contiguous(memory_format=torch.channels_last))
     torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+    # raw bnp entry points over the same group of two (forward, then the backward against autograd through BN of the group's batch)
+    from apex_b200.contrib.groupbn import raw_ext as bnp
+    both = full[grp * 2 * per:(grp + 1) * 2 * per].clone().requires_grad_(True)
+    w, b = torch.rand(C) + 0.5, torch.randn(C)
+    yref = torch.nn.functional.batch_norm(both, None, None, w, b, training=True)
+    gy = torch.randn(world * per, C, 4, 3)[grp * 2 * per:(grp + 1) * 2 * per]
+    dref = torch.autograd.grad(yref, both, gy)[0][(rank % 2) * per:(rank % 2 + 1) * per]
+    mm, mi, rm, rv = torch.empty(C), torch.empty(C), torch.zeros(C), torch.ones(C)
+    tail = (None, None, None, None, 2, torch.IntTensor([2]), 2, 100, False)
+    xn = mine.permute(0, 2, 3, 1).contiguous()
+    y = bnp.bn_fwd_nhwc(xn, w, b, rm, rv, mm, mi, None, 0.1, 1e-5, False, *tail)
+    torch.testing.assert_close(y.permute(0, 3, 1, 2), yref[(rank % 2) * per:(rank % 2 + 1) * per].detach(), atol=1e-5, rtol=1e-5)
+    dx, _, _ = bnp.bn_bwd_nhwc(xn, gy[(rank % 2) * per:(rank % 2 + 1) * per].permute(0, 2, 3, 1).contiguous(), w, b, rm, rv, mm, mi, None, 0.1,
+                               1e-5, False, *tail)
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), dref, atol=1e-5, rtol=1e-4)
 
 
 def one_rank_raises_while_the_others_wait(rank, world, device_type):

@@ -514,3 +514,52 @@ def test_fast_bottleneck_extension_name_cpu():
         assert len(got) == len(want)
         for a, r in zip(got, want):
             torch.testing.assert_close(a, lay(r))
+
+
+def test_bnp_extension_name_cpu():
+    """Raw bnp entry points (contrib/groupbn/raw_ext.py), bn_group = 1: forward state tensors, running statistics, the ReLU bitmask and both
+    backward calls against autograd; the grouped case runs in tests/test_cpu_ddp.py::test_group_batchnorm_four_ranks_gloo."""
+    import torch
+    import torch.nn.functional as F
+    from apex_b200 import ext_compat
+    from apex_b200.contrib.groupbn import raw_ext
+    bnp = ext_compat.extension_modules()["bnp"]
+    assert all(callable(getattr(bnp, n)) for n in raw_ext.ENTRY_POINTS)
+    torch.manual_seed(0)
+    N, H, W, C = 3, 5, 4, 6
+    x, z = torch.randn(N, H, W, C, requires_grad=True), torch.randn(N, H, W, C, requires_grad=True)
+    w, b = (torch.rand(C) + 0.5).requires_grad_(True), torch.randn(C, requires_grad=True)
+    tail = (None, None, None, None, 1, torch.IntTensor([0]), 2, 100, False)
+    bits = torch.randint(0, 2, (1000,)).bool()
+    packed = torch.zeros(40, dtype=torch.int32)
+    raw_ext._pack_bits(bits, packed)
+    assert torch.equal(raw_ext._unpack_bits(packed, (1000,)), bits)
+    for relu in (False, True):
+        rm, rv, rm2, rv2 = torch.zeros(C), torch.ones(C), torch.zeros(C), torch.ones(C)
+        mm, mi = torch.empty(C), torch.empty(C)
+        y = bnp.bn_fwd_nhwc(x.detach(), w.detach(), b.detach(), rm, rv, mm, mi, None, 0.1, 1e-5, relu, *tail)
+        ref = F.batch_norm(x.permute(0, 3, 1, 2), rm2, rv2, w, b, True, 0.1, 1e-5).permute(0, 2, 3, 1)
+        ref = torch.relu(ref) if relu else ref
+        torch.testing.assert_close(y, ref, atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(rm, rm2, atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(rv, rv2, atol=1e-6, rtol=1e-5)
+        torch.testing.assert_close(mm, x.detach().mean((0, 1, 2)), atol=1e-6, rtol=1e-5)
+        gy = torch.randn_like(y)
+        got = bnp.bn_bwd_nhwc(x.detach(), gy, w.detach(), b.detach(), rm, rv, mm, mi, None, 0.1, 1e-5, relu, *tail)
+        for a, r in zip(got, torch.autograd.grad(ref, (x, w, b), gy)):
+            torch.testing.assert_close(a, r, atol=1e-4, rtol=1e-4)
+        ye = bnp.bn_fwd_eval_nhwc(x.detach(), w.detach(), b.detach(), rm, rv, None, 1, 0.1, 1e-5, relu)
+        re = F.batch_norm(x.detach().permute(0, 3, 1, 2), rm, rv, w.detach(), b.detach(), False, 0.0, 1e-5).permute(0, 2, 3, 1)
+        torch.testing.assert_close(ye, torch.relu(re) if relu else re, atol=1e-5, rtol=1e-5)
+    rm, rv, mm, mi = torch.zeros(C), torch.ones(C), torch.empty(C), torch.empty(C)
+    bitmask = torch.zeros(((x.numel() + 31) // 32) * 2, dtype=torch.int32)
+    y = bnp.bn_addrelu_fwd_nhwc(x.detach(), z.detach(), w.detach(), b.detach(), rm, rv, mm, mi, bitmask, None, 0.1, 1e-5, *tail)
+    ref = torch.relu(F.batch_norm(x.permute(0, 3, 1, 2), None, None, w, b, True, 0.1, 1e-5).permute(0, 2, 3, 1) + z)
+    torch.testing.assert_close(y, ref, atol=1e-5, rtol=1e-5)
+    gy = torch.randn_like(y)
+    got = bnp.bn_addrelu_bwd_nhwc(x.detach(), gy, w.detach(), b.detach(), rm, rv, mm, mi, bitmask, None, 0.1, 1e-5, *tail)
+    for a, r in zip(got, torch.autograd.grad(ref, (x, z, w, b), gy)):
+        torch.testing.assert_close(a, r, atol=1e-4, rtol=1e-4)
+    ye = bnp.bn_addrelu_fwd_eval_nhwc(x.detach(), z.detach(), w.detach(), b.detach(), rm, rv, None, 1, 0.1, 1e-5)
+    re = F.batch_norm(x.detach().permute(0, 3, 1, 2), rm, rv, w.detach(), b.detach(), False, 0.0, 1e-5).permute(0, 2, 3, 1) + z.detach()
+    torch.testing.assert_close(ye, torch.relu(re), atol=1e-5, rtol=1e-5)
