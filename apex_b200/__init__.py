@@ -66,6 +66,22 @@ _PATH_ALIASES = {
 }
 
 
+def _pin_shadowed_submodules() -> None:
+    """A package attribute may shadow a sub-module of the same name (``contrib.index_mul_2d.index_mul_2d`` is the function, as in the
+    reference). Python binds ``package.child = module`` whenever a sub-module is LOADED, so loading such a sub-module a second time under
+    its ``apex.`` name would replace the function by the module. Registering the alias in ``sys.modules`` up front means the import
+    system finds it loaded and rebinds nothing."""
+    import sys
+
+    for name, m in list(sys.modules.items()):
+        if m is None or not name.startswith(__name__ + "."):
+            continue
+        parent, _, child = name.rpartition(".")
+        pm = sys.modules.get(parent)
+        if pm is not None and getattr(pm, child, m) is not m:
+            sys.modules.setdefault("apex" + name[len(__name__):], m)
+
+
 class _ApexAliasFinder:
     """Meta-path finder that resolves ``apex.<anything>`` to the SAME module object as ``apex_b200.<anything>`` — without it a deep import
     such as ``apex.contrib.xentropy.softmax_xentropy`` would execute the file a second time under the other name (two copies of every class)."""
@@ -82,6 +98,7 @@ class _ApexAliasFinder:
             importlib.import_module(target_name)
         except ImportError:
             return None
+        _pin_shadowed_submodules()          # importing the target may have loaded sub-modules that a package attribute shadows
         spec = importlib.machinery.ModuleSpec(fullname, self)
         spec.loader_state = target_name
         return spec

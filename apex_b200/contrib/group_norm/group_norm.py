@@ -6,6 +6,8 @@ else ``torch_group_norm``). Here one persistent kernel per direction covers ever
 (logical NCHW, physical NHWC) like the reference; anything else goes through ``torch_group_norm``."""
 from __future__ import annotations
 
+import functools
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -251,7 +253,7 @@ if hasattr(torch.library, "custom_op"):
         return y, sums
 
     @group_norm_nhwc_fprop_op.register_fake
-    def _(x, G, weight, bias, eps, act):
+    def fake_group_norm_nhwc_fprop(x, G, weight, bias, eps, act):
         return torch.empty_like(x), x.new_empty(2, x.shape[0] * G, dtype=torch.float32)
 
     @torch.library.custom_op("apex_b200::group_norm_nhwc_bprop", mutates_args=())
@@ -261,21 +263,29 @@ if hasattr(torch.library, "custom_op"):
         return dx.contiguous(memory_format=torch.channels_last) if dx.dim() == 4 else dx, dw.clone(), db.clone()
 
     @group_norm_nhwc_bprop_op.register_fake
-    def _(grad_output, sums, x, G, weight, bias, eps, act):
+    def fake_group_norm_nhwc_bprop(grad_output, sums, x, G, weight, bias, eps, act):
         return torch.empty_like(x), torch.empty_like(weight), torch.empty_like(bias)
 
-    def _gn_setup(ctx, inputs, output):
+    def setup_context(ctx, inputs, output):
         x, G, weight, bias, eps, act = inputs
         ctx.save_for_backward(x, weight, bias, output[1])
         ctx.cfg = (G, eps, act)
 
-    def _gn_backward(ctx, gy, gsums):
+    def backward(ctx, gy, gsums):
         x, weight, bias, sums = ctx.saved_tensors
         G, eps, act = ctx.cfg
         dx, dw, db = group_norm_nhwc_bprop_op(gy, sums, x, G, weight, bias, eps, act)
         return dx, None, dw, db, None, None
 
-    group_norm_nhwc_fprop_op.register_autograd(_gn_backward, setup_context=_gn_setup)
+    group_norm_nhwc_fprop_op.register_autograd(backward, setup_context=setup_context)
+
+
+@functools.cache
+def one_time_warning(msg: str) -> None:
+    """Warn once per distinct message (reference group_norm.py:22-25)."""
+    import warnings
+
+    warnings.warn(msg, stacklevel=2)
 
 
 def _compiled_cuda(x) -> bool:

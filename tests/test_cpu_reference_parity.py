@@ -22,7 +22,6 @@ MISSING_MODULES = {
 }
 # public names with no counterpart, and why
 MISSING_NAMES = {
-    "apex.contrib.group_norm.group_norm": {"one_time_warning", "fake_group_norm_nhwc_fprop", "fake_group_norm_nhwc_bprop", "backward", "setup_context"},  # torch.library plumbing of the reference's ops; ours: apex_b200::group_norm custom ops
     "apex.contrib.nccl_allocator.nccl_allocator": {"get_func_args"},
     "apex.contrib.torchsched.ops.layer_norm": {"CuDNNManager", "get_cudnn_manager", "LayerNormGraphFactory", "layer_norm_setup_context", "layer_norm_backward_wrapper"},  # cuDNN handle / graph cache; autograd is registered on apex_b200::norm_fwd
     "apex.contrib.torchsched.inductor.wrapper": {"EnterDeviceContextManagerWithStreamInfoLine", "ExitDeviceContextManagerWithStreamInfoLine"},  # Inductor wrapper-line subclasses

@@ -135,6 +135,13 @@ def test_apex_alias_resolves_deep_imports_to_the_same_module_objects():
     from apex_b200.contrib.openfold import FusedAdamSWA as same
 
     assert FusedAdamSWA is same
+    # a package attribute that shadows a sub-module of the same name must survive a deep import of that sub-module under the alias
+    for pkg in ("contrib.index_mul_2d", "contrib.focal_loss"):
+        leaf = pkg.rsplit(".", 1)[1]
+        fn = getattr(importlib.import_module("apex_b200." + pkg), leaf)
+        assert callable(fn)
+        assert importlib.import_module(f"apex.{pkg}.{leaf}") is importlib.import_module(f"apex_b200.{pkg}.{leaf}")
+        assert getattr(importlib.import_module("apex_b200." + pkg), leaf) is fn and getattr(importlib.import_module("apex." + pkg), leaf) is fn
     with pytest.raises(ImportError):
         importlib.import_module("apex.no_such_module")
 
