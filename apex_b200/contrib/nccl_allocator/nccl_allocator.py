@@ -24,14 +24,38 @@ def init() -> None:
     os.environ.setdefault("TORCH_NCCL_USE_TENSOR_REGISTER_ALLOCATOR_HOOK", "0")
 
 
+def get_func_args(func) -> list:
+    """Parameter names of ``func`` (reference nccl_allocator.py:11-15); [] for callables without an introspectable signature."""
+    import inspect
+
+    try:
+        return [p.name for p in inspect.signature(func).parameters.values()]
+    except (TypeError, ValueError):
+        return []
+
+
+def _symmetric_kwargs(symmetric, pool_cls) -> dict:
+    """``symmetric`` (None = the pool's default) as the keyword this torch build's MemPool understands: upstream calls it ``symmetric``,
+    NVIDIA's builds ``symm_mem`` (reference nccl_allocator.py:18-33); neither -> ValueError."""
+    if symmetric is None:
+        return {}
+    names = get_func_args(pool_cls.__init__) + get_func_args(pool_cls)
+    for key in ("symmetric", "symm_mem"):
+        if key in names:
+            return {key: symmetric}
+    raise ValueError("symmetric setting with torch.cuda.MemPool requires higher PyTorch version")
+
+
 def create_nccl_mem_pool(symmetric=None):
-    """A torch.cuda.MemPool backed by the process group's NCCL allocator when this torch build exposes one, else the default pool."""
+    """A torch.cuda.MemPool backed by the process group's NCCL allocator when this torch build exposes one, else the default pool.
+    ``symmetric=True / False`` asks for (or forbids) symmetric registration when the pool type has such a switch."""
     global _pool
+    kw = _symmetric_kwargs(symmetric, torch.cuda.MemPool)
     try:
         backend = dist.distributed_c10d._get_default_group()._get_backend(torch.device("cuda"))
-        _pool = torch.cuda.MemPool(backend.mem_allocator)
+        _pool = torch.cuda.MemPool(backend.mem_allocator, **kw)
     except Exception:  # noqa: BLE001
-        _pool = torch.cuda.MemPool()
+        _pool = torch.cuda.MemPool(**kw)
     return _pool
 
 

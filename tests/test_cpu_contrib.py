@@ -563,3 +563,24 @@ def test_bnp_extension_name_cpu():
     ye = bnp.bn_addrelu_fwd_eval_nhwc(x.detach(), z.detach(), w.detach(), b.detach(), rm, rv, None, 1, 0.1, 1e-5)
     re = F.batch_norm(x.detach().permute(0, 3, 1, 2), rm, rv, w.detach(), b.detach(), False, 0.0, 1e-5).permute(0, 2, 3, 1) + z.detach()
     torch.testing.assert_close(ye, torch.relu(re), atol=1e-5, rtol=1e-5)
+
+
+def test_nccl_allocator_symmetric_keyword_selection_cpu():
+    import pytest
+    from apex_b200.contrib.nccl_allocator import nccl_allocator as na
+
+    class Upstream:
+        def __init__(self, allocator=None, symmetric=False): ...
+
+    class Nvidia:
+        def __init__(self, allocator=None, symm_mem=False): ...
+
+    class Old:
+        def __init__(self, allocator=None): ...
+
+    assert na.get_func_args(lambda a, b=1, *c, **d: 0) == ["a", "b", "c", "d"]
+    assert na._symmetric_kwargs(None, Old) == {}
+    assert na._symmetric_kwargs(True, Upstream) == {"symmetric": True}
+    assert na._symmetric_kwargs(False, Nvidia) == {"symm_mem": False}
+    with pytest.raises(ValueError, match="higher PyTorch version"):
+        na._symmetric_kwargs(True, Old)
