@@ -70,6 +70,29 @@ class ExitCudaStreamContextLine:
         code.do_unindent()
 
 
+@dataclasses.dataclass
+class EnterDeviceContextManagerWithStreamInfoLine:
+    """Entry of a generated program (reference inductor/wrapper.py:39-66): name the caller's stream and record the entrance event on it —
+    every side stream waits for that event the first time it is entered. The reference also emits the acquisition of
+    ``config.num_streams`` pool streams here; in this design the streams are bound into the program's namespace once, at ``compile()``,
+    so a call pays no pool traffic."""
+    multi_stream: bool = True
+
+    def codegen(self, code: IndentedBuffer) -> None:
+        if self.multi_stream:
+            code.writeline(f"{DEFAULT_STREAM} = torch.cuda.current_stream()")
+            code.writeline(f"{ENTRANCE_EVENT}.record({DEFAULT_STREAM})")
+
+
+@dataclasses.dataclass
+class ExitDeviceContextManagerWithStreamInfoLine:
+    """Exit of a generated program (reference inductor/wrapper.py:69-90 releases the pool streams): nothing to hand back here — the
+    scheduler has already joined every side stream into the caller's stream through events, and the streams stay bound to the function."""
+
+    def codegen(self, code: IndentedBuffer) -> None:
+        return None
+
+
 def record_stream_tree(value, stream) -> None:
     """``Tensor.record_stream`` on every CUDA tensor inside ``value``: the caching allocator must not hand a block that ``stream`` still
     reads to a later allocation of the stream that owns it."""
@@ -149,12 +172,10 @@ class MultiStreamWrapperCodegen:
 
     def codegen_device_guard_enter(self) -> None:
         """Entry of the program: name the caller's stream and record the entrance event on it."""
-        if self.multi_stream:
-            self.writeline(f"{DEFAULT_STREAM} = torch.cuda.current_stream()")
-            self.writeline(f"{ENTRANCE_EVENT}.record({DEFAULT_STREAM})")
+        self.lines.append(EnterDeviceContextManagerWithStreamInfoLine(self.multi_stream))
 
     def codegen_device_guard_exit(self) -> None:
-        pass
+        self.lines.append(ExitDeviceContextManagerWithStreamInfoLine())
 
     def codegen_cuda_stream_enter(self, stream_idx: int) -> None:
         assert stream_idx != DEFAULT_STREAM_IDX

@@ -23,7 +23,6 @@ MISSING_MODULES = {
 # public names with no counterpart, and why
 MISSING_NAMES = {
     "apex.contrib.torchsched.ops.layer_norm": {"CuDNNManager", "get_cudnn_manager", "LayerNormGraphFactory", "layer_norm_setup_context", "layer_norm_backward_wrapper"},  # cuDNN handle / graph cache; autograd is registered on apex_b200::norm_fwd
-    "apex.contrib.torchsched.inductor.wrapper": {"EnterDeviceContextManagerWithStreamInfoLine", "ExitDeviceContextManagerWithStreamInfoLine"},  # Inductor wrapper-line subclasses
 }
 
 
